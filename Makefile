@@ -1,0 +1,31 @@
+# Builds libnecat_b200.so (sm_100a only) and the drop-in executables, in-tree.
+NVCC  ?= /usr/local/cuda/bin/nvcc
+ARCH  := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-O2 -Xptxas -v
+CSRC  := necat_b200/csrc
+LIBD  := necat_b200/lib
+BIND  := necat_b200/bin
+OBJD  := build/obj
+CU    := $(wildcard $(CSRC)/*.cu)
+OBJ   := $(patsubst $(CSRC)/%.cu,$(OBJD)/%.o,$(CU))
+HOSTC := necat_b200/host/nb_host.c
+CC    := gcc
+CFLAGS := -O2 -g -std=gnu99 -Wall
+
+all: $(LIBD)/libnecat_b200.so $(BIND)/oc2pmov
+
+$(OBJD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/necat_b200.h
+	@mkdir -p $(OBJD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJD)/$*.ptxas.log || (cat $(OBJD)/$*.ptxas.log; false)
+
+$(LIBD)/libnecat_b200.so: $(OBJ)
+	@mkdir -p $(LIBD)
+	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
+
+$(BIND)/%: necat_b200/host/%.c $(HOSTC) necat_b200/host/nb_host.h $(LIBD)/libnecat_b200.so
+	@mkdir -p $(BIND)
+	$(CC) $(CFLAGS) -o $@ $< $(HOSTC) -L$(LIBD) -lnecat_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm
+
+clean:
+	rm -rf build $(LIBD) $(BIND)
+.PHONY: all clean

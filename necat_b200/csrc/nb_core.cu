@@ -1,0 +1,155 @@
+// nb_core.cu -- context, error handling, volume upload (C-ABI part 1).
+#include <stdarg.h>
+
+#include "nb_common.cuh"
+
+char g_nb_err[512] = "";
+
+int nb_fail(nb_ctx* ctx, int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_nb_err, sizeof g_nb_err, fmt, ap);
+    va_end(ap);
+    if (ctx) memcpy(ctx->err, g_nb_err, sizeof g_nb_err);
+    return code;
+}
+
+extern "C" const char* nb_version(void) { return "necat_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* nb_last_error(const nb_ctx* ctx) { return ctx ? ctx->err : g_nb_err; }
+
+extern "C" int nb_ctx_create(int device, nb_ctx** out)
+{
+    if (!out) return nb_fail(NULL, NB_EINVAL, "nb_ctx_create: out is NULL");
+    *out = NULL;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return nb_fail(NULL, NB_ENODEVICE, "no CUDA device available (%s): libnecat_b200 has no CPU fallback",
+                       cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return nb_fail(NULL, NB_EINVAL, "device %d out of range (%d present)", device, ndev);
+    NB_CUDA(NULL, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NB_CUDA(NULL, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return nb_fail(NULL, NB_ENODEVICE, "device %d is sm_%d%d; this library only carries sm_100a code", device,
+                       prop.major, prop.minor);
+    nb_ctx* c = (nb_ctx*)calloc(1, sizeof(nb_ctx));
+    if (!c) return nb_fail(NULL, NB_ENOMEM, "out of host memory");
+    c->device = device;
+    NB_CUDA(NULL, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    NB_CUDA(NULL, cudaEventCreate(&c->ev0));
+    NB_CUDA(NULL, cudaEventCreate(&c->ev1));
+    NB_CUDA(NULL, cudaEventCreate(&c->ev2));
+    NB_CUDA(NULL, cudaEventCreate(&c->ev3));
+    *out = c;
+    return NB_OK;
+}
+
+extern "C" void nb_ctx_destroy(nb_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->ev2);
+    cudaEventDestroy(c->ev3);
+    cudaStreamDestroy(c->stream);
+    free(c);
+}
+
+extern "C" uint64_t nb_launch_count(const nb_ctx* c) { return c ? c->launches : 0; }
+extern "C" void nb_get_timings(const nb_ctx* c, nb_timings* out) { if (c && out) *out = c->tm; }
+extern "C" void nb_get_map_counters(const nb_ctx* c, nb_map_counters* out) { if (c && out) *out = c->mc; }
+extern "C" void nb_get_cns_counters(const nb_ctx* c, nb_cns_counters* out) { if (c && out) *out = c->cc; }
+extern "C" void nb_free(void* p) { free(p); }
+
+extern "C" int nb_volume_upload(nb_ctx* ctx, const uint8_t* pac, uint64_t db_size, const uint64_t* seq_offset,
+                                const uint64_t* seq_size, uint64_t nseq, nb_volume** out)
+{
+    if (!ctx || !out || (!pac && db_size) || (nseq && (!seq_offset || !seq_size)))
+        return nb_fail(ctx, NB_EINVAL, "nb_volume_upload: bad arguments");
+    if (db_size >= (1ull << 32)) return nb_fail(ctx, NB_ELIMIT, "volume of %llu bases exceeds the 2^32 limit", (unsigned long long)db_size);
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    nb_volume* v = (nb_volume*)calloc(1, sizeof(nb_volume));
+    if (!v) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    v->db_size = db_size;
+    v->nseq = nseq;
+    uint64_t nb = (db_size + 3) >> 2;
+    uint64_t padded = ((nb + 15) & ~15ull) + 256;
+    NB_CUDA(ctx, cudaMalloc(&v->d_pac, padded));
+    NB_CUDA(ctx, cudaMemsetAsync(v->d_pac, 0, padded, ctx->stream));
+    NB_CUDA(ctx, cudaMalloc(&v->d_off, sizeof(uint64_t) * (nseq + 1)));
+    NB_CUDA(ctx, cudaMalloc(&v->d_len, sizeof(uint32_t) * (nseq + 1)));
+    v->h_off = (uint64_t*)malloc(sizeof(uint64_t) * (nseq + 1));
+    v->h_len = (uint32_t*)malloc(sizeof(uint32_t) * (nseq + 1));
+    if (!v->h_off || !v->h_len) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    v->max_len = 0;
+    for (uint64_t i = 0; i < nseq; ++i) {
+        if (seq_size[i] >= (1ull << 31) || seq_offset[i] + seq_size[i] > db_size) {
+            return nb_fail(ctx, NB_EINVAL, "sequence %llu out of range", (unsigned long long)i);
+        }
+        v->h_off[i] = seq_offset[i];
+        v->h_len[i] = (uint32_t)seq_size[i];
+        if (v->h_len[i] > v->max_len) v->max_len = v->h_len[i];
+    }
+    v->h_off[nseq] = db_size;
+    v->h_len[nseq] = 0;
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    NB_CUDA(ctx, cudaMemcpyAsync(v->d_pac, pac, nb, cudaMemcpyHostToDevice, ctx->stream));
+    NB_CUDA(ctx, cudaMemcpyAsync(v->d_off, v->h_off, sizeof(uint64_t) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream));
+    NB_CUDA(ctx, cudaMemcpyAsync(v->d_len, v->h_len, sizeof(uint32_t) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream));
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->tm.h2d_ms += ms;
+    ctx->tm.h2d_bytes += nb + 12 * (nseq + 1);
+    *out = v;
+    return NB_OK;
+}
+
+extern "C" void nb_volume_free(nb_ctx* ctx, nb_volume* v)
+{
+    if (!v) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(v->d_pac);
+    cudaFree(v->d_off);
+    cudaFree(v->d_len);
+    free(v->h_off);
+    free(v->h_len);
+    free(v);
+}
+
+extern "C" void nb_map_options_default(nb_map_options* o)
+{
+    o->kmer_size = 15; o->scan_window = 10; o->kmer_cnt_cutoff = 500; o->block_size = 2000;
+    o->block_score_cutoff = 3; o->num_candidates = 500; o->align_size_cutoff = 500;
+    o->ddfs_cutoff = 0.25; o->error = 0.5; o->num_output = 500; o->num_threads = 1;
+    o->job = 1; o->binary_output = 0; o->use_hdr_as_id = 1;
+}
+
+extern "C" void nb_cns_options_default(nb_cns_options* o)
+{
+    o->min_align_size = 400; o->min_cov = 4; o->max_cov = 12; o->min_size = 500; o->full_consensus = 0;
+    o->error = 0.5; o->mapping_ratio = 0.8; o->num_threads = 1; o->rescue_long_indels = 0;
+    o->use_fixed_ident_cutoff = 0; o->small_memory = 0;
+}
+
+extern "C" void nb_pack_candidate(const nb_candidate* c, nb_packed_candidate* p)
+{
+    uint32_t w = 0;
+    if (c->sdir == 1) w |= 1u << 31;
+    if (c->qdir == 1) w |= 1u << 30;
+    if (c->qoff == c->qbeg) w |= 1u << 29;
+    w |= (uint32_t)(c->score > 1000000 ? 1000000 : c->score);
+    p->item[0] = w;
+    p->item[1] = (uint32_t)c->sid;
+    p->item[2] = (uint32_t)c->sbeg;
+    p->item[3] = (uint32_t)c->send;
+    p->item[4] = (uint32_t)c->qid;
+    p->item[5] = (uint32_t)c->qbeg;
+    p->item[6] = (uint32_t)c->qend;
+}

@@ -1,0 +1,41 @@
+/* nb_host.h -- file-format helpers shared by the drop-in executables (plain C). */
+#ifndef NB_HOST_H
+#define NB_HOST_H
+
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/necat_b200.h"
+
+/* PackedDB volume file (common/packed_db.c:291-348). */
+typedef struct {
+    uint8_t*  pac;
+    uint64_t  db_size, nseq;
+    uint64_t* offset;
+    uint64_t* size;
+    uint64_t* hdr_offset;
+    char*     hdr;
+    uint64_t  hdr_size;
+} nbh_volume;
+
+int  nbh_volume_load(const char* path, nbh_volume* v);
+int  nbh_volume_append(nbh_volume* dst, const nbh_volume* src);    /* pdb_merge, packed_db.c:419-448 */
+void nbh_volume_free(nbh_volume* v);
+
+/* wrk_dir/reads_info.txt + volume_names.txt (common/makedb_aux.c:78-118). */
+typedef struct {
+    int    num_volumes, num_reads;
+    char** names;
+    int*   start_id;
+    int*   count;
+} nbh_volumes_info;
+int  nbh_volumes_info_load(const char* wrk_dir, nbh_volumes_info* vi);
+void nbh_volumes_info_free(nbh_volumes_info* vi);
+
+/* "[time] LEVEL: msg (file, line)" banners of common/ontcns_aux.c:29-46 */
+void nbh_log(const char* level, const char* file, int line, const char* fmt, ...);
+#define NBH_LOG(...)   nbh_log("INFO", __FILE__, __LINE__, __VA_ARGS__)
+#define NBH_ERROR(...) do { nbh_log("ERROR", __FILE__, __LINE__, __VA_ARGS__); exit(1); } while (0)
+double nbh_now(void);
+
+#endif

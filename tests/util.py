@@ -1,0 +1,61 @@
+"""Shared helpers of the test-suite: synthetic data sets, oracle / reference runners,
+canonical comparators."""
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_CLI = os.path.join(ORACLE_DIR, "_build", "oracle_cli")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+BIN_DIR = os.path.join(ROOT, "necat_b200", "bin")
+
+PM_SENSITIVE = "-k 15 -z 10 -q 500 -b 2000 -s 3 -n 500 -a 1000 -d 0.25 -e 0.5 -m 500 -t 1 -j 0 -u 1 -i 1"
+PM_FAST = "-k 15 -z 20 -q 500 -b 2000 -s 3 -n 500 -a 1000 -d 0.25 -e 0.5 -m 500 -t 1 -j 0 -u 1 -i 1"
+CNS_SENSITIVE = "-a 2000 -x 4 -y 12 -l 1000 -e 0.5 -p 0.8 -u 0 -r 0 -f 0"
+
+
+def ensure_oracle():
+    if not (os.path.exists(ORACLE_CLI) and os.path.exists(ORACLE_LIB)):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+
+
+def ref_bin(name):
+    p = os.path.join(REF_DIR, name)
+    return p if os.path.exists(p) else None
+
+
+def make_workdir(path, genome=100_000, depth=20, seed=7, vol_size=2_000_000_000, **gen_kw):
+    """Synthetic reads -> PackedDB work dir.  Returns (wrk_dir, reads)."""
+    import gen_reads
+    from necat_b200 import formats
+    _, reads = gen_reads.generate(genome, depth, seed, **gen_kw)
+    wrk = os.path.join(str(path), "vol")
+    formats.write_workdir(wrk, reads, vol_size=vol_size)
+    return wrk, reads
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, **kw)
+
+
+def run_pmov(binary, opts, wrk, vid, out, prefix=()):
+    run(list(prefix) + ([binary, "pmov"] if binary == ORACLE_CLI else [binary]) + opts.split() + [wrk, str(vid), out])
+    from necat_b200 import formats
+    return formats.read_candidates(out)
+
+
+def canon(a):
+    from necat_b200 import formats
+    return formats.canonical_records(a)
+
+
+def same_multiset(a, b):
+    return a.shape == b.shape and np.array_equal(canon(a), canon(b))
+
+
+def fasta_canon(path):
+    from necat_b200 import formats
+    return sorted(formats.read_fasta_records(path))

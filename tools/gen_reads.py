@@ -40,9 +40,20 @@ def mutate(seq, rng, err, fsub=0.35, fdel=0.35, fins=0.30):
 
 
 def generate(genome_size, depth, seed, err=0.15, min_len=3000, max_len=60000,
-             mean_log=8.75, sd_log=0.55):
+             mean_log=8.75, sd_log=0.55, repeat_len=0, repeat_copies=0, n_repeats=0):
+    """n_repeats families of `repeat_copies` near-identical (1 % diverged) copies of a
+    random repeat_len segment are planted into the genome (exercises the k-mer count
+    cutoff, the 40-seed block cap and block zeroing)."""
     rng = np.random.default_rng(seed)
     genome = rng.integers(0, 4, genome_size, dtype=np.uint8)
+    for _ in range(n_repeats):
+        unit = rng.integers(0, 4, repeat_len, dtype=np.uint8)
+        for _c in range(repeat_copies):
+            cp = unit.copy()
+            m = rng.random(repeat_len) < 0.01
+            cp[m] = (cp[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) & 3
+            s0 = int(rng.integers(0, genome_size - repeat_len))
+            genome[s0:s0 + repeat_len] = cp
     target = int(genome_size * depth)
     reads = []
     total = 0
