@@ -20,6 +20,8 @@ struct nb_ctx {
     nb_map_counters mc;
     nb_cns_counters cc;
     cudaEvent_t  ev0, ev1, ev2, ev3;
+    void*        ext_mat;        // walk-back scratch of the extension kernel (kept across calls)
+    size_t       ext_mat_slots;
 };
 
 struct nb_volume {

@@ -57,6 +57,7 @@ extern "C" void nb_ctx_destroy(nb_ctx* c)
     cudaEventDestroy(c->ev2);
     cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->stream);
+    if (c->ext_mat) cudaFree(c->ext_mat);
     free(c);
 }
 

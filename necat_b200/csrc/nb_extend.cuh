@@ -1,0 +1,46 @@
+// nb_extend.cuh -- device-side interface of the block-wise Myers extension kernel.
+#pragma once
+#include "nb_common.cuh"
+
+// One extension request: a candidate normalised so that the template (subject) is forward.
+struct ExtTask {
+    uint32_t qid, sid;      // read ids in the (merged) read volume
+    int32_t  qoff, soff;    // extension start (gapped_candidate.c:44-50)
+    int32_t  qdir;          // query strand
+    int32_t  pad_;
+    uint64_t ops_base;      // start of this task's region in the ops pool
+    uint32_t ops_cap;       // region size
+    uint32_t lcap;          // columns reserved for the left extension (= qoff + soff)
+};
+
+// op codes, one byte per alignment column, left to right along the template
+#define OP_MATCH 0      // query base == template base
+#define OP_QONLY 1      // query base against a gap   (insertion w.r.t. the template)
+#define OP_TONLY 2      // gap against a template base (deletion)
+#define OP_MISMATCH 3   // query base != template base
+
+#define EXT_MAX_BLK 832         // >= 1.3 * 611 + slack (oc_aligner.c:127-137), multiple of 32
+#define EXT_WARPS 8             // warps per CTA
+#define EXT_MAT_WORDS 26        // 32-bit words per column (832 / 32)
+
+struct ExtParams {
+    const uint8_t*  pac;
+    const uint64_t* seq_off;
+    const uint32_t* seq_len;
+    const ExtTask*  tasks;
+    uint32_t        n_tasks;
+    nb_alignment*   results;
+    uint8_t*        ops;            // pool
+    uint2*          mat;            // per resident warp: (EXT_MAX_BLK + 32) * EXT_MAT_WORDS entries
+    uint32_t*       next_task;      // work queue cursor
+    unsigned long long* counters;   // [0] block alignments, [1] DP columns, [2] word updates
+    double          error;
+    int             min_align_size;
+    int             tail_match_len;
+    int             block_size;     // 512
+};
+
+#define EXT_MAT_STRIDE ((size_t)(EXT_MAX_BLK + 32) * EXT_MAT_WORDS)
+
+int nb_run_extension(nb_ctx* ctx, const nb_volume* reads, const ExtTask* d_tasks, uint32_t n_tasks,
+                     nb_alignment* d_results, uint8_t* d_ops, double error, int min_align_size, int tail_match_len);

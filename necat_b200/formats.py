@@ -140,3 +140,46 @@ def read_fasta_records(path):
             else:
                 recs.append((hdr, line))
     return recs
+
+
+def swap_roles(rec):
+    """change_pcan_roles (common/gapped_candidate.c:54-69) on (n, 7) uint32 records."""
+    out = rec.copy()
+    w = rec[:, 0]
+    r = w & np.uint32((1 << 30) - 1)
+    r |= ((w >> 31) & 1) << 30
+    r |= ((w >> 30) & 1) << 31
+    out[:, 0] = r
+    out[:, 1:4] = rec[:, 4:7]
+    out[:, 4:7] = rec[:, 1:4]
+    return out
+
+
+def normalise_sdir(rec, sizes):
+    """normalise_pcan_sdir (gapped_candidate.c:72-93): make the subject forward."""
+    out = rec.copy()
+    rev = (rec[:, 0] >> 31) == 1
+    w = rec[rev, 0]
+    r = w & np.uint32((1 << 29) - 1)
+    r |= (1 - ((w >> 30) & 1)) << 30
+    r |= (1 - ((w >> 29) & 1)) << 29
+    out[rev, 0] = r
+    qs = sizes[rec[rev, 4]].astype(np.uint32)
+    ss = sizes[rec[rev, 1]].astype(np.uint32)
+    out[rev, 5] = qs - rec[rev, 6]
+    out[rev, 6] = qs - rec[rev, 5]
+    out[rev, 2] = ss - rec[rev, 3]
+    out[rev, 3] = ss - rec[rev, 2]
+    return out
+
+
+def partition_records(rec, sizes, lo=0, hi=None):
+    """What oc2pcan + oc2cns' loader produce for templates [lo, hi): every record under
+    its subject and, roles swapped, under its query; subject made forward."""
+    if hi is None:
+        hi = sizes.size
+    a = rec[(rec[:, 1] >= lo) & (rec[:, 1] < hi)]
+    b = swap_roles(rec[(rec[:, 4] >= lo) & (rec[:, 4] < hi)])
+    allr = np.concatenate([a, b])
+    allr = allr[np.argsort(allr[:, 1], kind="stable")]
+    return normalise_sdir(allr, sizes)
