@@ -12,7 +12,7 @@ HOSTC := necat_b200/host/nb_host.c
 CC    := gcc
 CFLAGS := -O2 -g -std=gnu99 -Wall
 
-all: $(LIBD)/libnecat_b200.so $(BIND)/oc2pmov
+all: $(LIBD)/libnecat_b200.so $(BIND)/oc2pmov $(BIND)/oc2cns $(BIND)/oc2pcan
 
 $(OBJD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/necat_b200.h
 	@mkdir -p $(OBJD)

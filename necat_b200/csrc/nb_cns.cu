@@ -1,0 +1,534 @@
+// nb_cns.cu -- nb_consensus_job: one oc2cns partition on the GPU.
+//
+// Replaces consensus_one_partition / consensus_one_read
+// (consensus/consensus_one_partition.c:110-201, consensus/consensus_one_read.c:216-392).
+// Division of labour:
+//   * GPU: every candidate extension (k_extend, nb_extend.cu) and the whole
+//     consensus (k_consensus, nb_cns_kernel.cuh);
+//   * host (C++, this file): the order-dependent accept/skip logic of
+//     consensus_one_read.  An extension's result does not depend on that state,
+//     only whether it is used does -- so extensions are computed speculatively in
+//     rounds (first 50 candidates of every template, then the remaining windows of
+//     50 minus the candidates that are already skippable: both skip tests are
+//     monotone) and the reference's loop is replayed over the results.
+#include <algorithm>
+#include <cmath>
+#include <thread>
+#include <vector>
+
+#include "nb_cns_kernel.cuh"
+
+namespace {
+
+struct Can {
+    int qid, qdir, qoff, soff, sbeg, send, qsize, score, qbeg;
+    int res;            // index into the template chunk's result arrays, -1 = not extended yet
+};
+
+struct Accepted { int can; double weight; };
+
+struct Tpl {
+    int tid, T;
+    size_t first, n;            // candidates (sorted, truncated) in the chunk's `cans`
+    // replay state
+    int stage;                  // 0 = phase 1 pending, 1 = main loop, 2 = finished
+    size_t next, win_to, win_i;
+    bool in_window;
+    double cutoff;
+    int num_can, num_ovlps;
+    std::vector<uint16_t> cov;
+    std::vector<int> used;
+    std::vector<Accepted> acc;
+    std::vector<size_t> request; // candidate indices to extend in the next round
+};
+
+inline bool good_overlap(int qoff, int qend, int qsize, int soff, int send, int ssize)   // error_estimate.c:8-30
+{
+    const int M = 200;
+    const int ql = qoff, qr = qsize - qend, sl = soff, sr = ssize - send;
+    return (ql <= M && qr <= M) || (sl <= M && sr <= M) || (qr <= M && sl <= M) || (sr <= M && ql <= M);
+}
+inline bool full_cov_ovlp(int ql, int qr, int qs, int tl, int tr, int ts, int L, int M)  // consensus_aux.c:93-112
+{
+    if (ql <= M && qs - qr <= M) return true;
+    if (tl <= M && ts - tr <= M) return true;
+    if (qs - qr <= M) { if (tl > M) return false; if (qr - ql >= L) return true; }
+    if (ts - tr <= M) { if (ql > M) return false; if (qr - ql >= L) return true; }
+    return false;
+}
+inline bool mapping_range_ok(int ql, int qr, int qs, int tl, int tr, int ts, int min_size, double ratio)  // :115-121
+{
+    if (qr - ql >= min_size || tr - tl >= min_size) return true;
+    return (qr - ql >= qs * ratio) || (tr - tl >= ts * ratio);
+}
+inline double cns_weight(double ident)      // consensus_one_read.c:11-16
+{
+    double e = (100.0 - ident) / 100.0 / 2.0;
+    double w = (1.0 - e) * (1.0 - e) + e * e / 3.0;
+    if (100.0 - ident <= 1.0e-6) w = 1.0;
+    return w;
+}
+inline double ident_of(const nb_alignment& a) { return a.aln_size ? 100.0 * a.n_match / a.aln_size : 0.0; }
+
+inline bool is_used(const Tpl& t, int qid) { for (int u : t.used) if (u == qid) return true; return false; }
+inline void set_used(Tpl& t, int qid) { if (!is_used(t, qid)) t.used.push_back(qid); }
+inline bool cov_full(const Tpl& t, int from, int to, int max_cov)   // consensus_one_read.c:139-145
+{
+    for (int i = from; i < to; ++i) if (t.cov[i] < max_cov) return false;
+    return true;
+}
+inline void accept(Tpl& t, size_t ci, const nb_alignment& a)
+{
+    Accepted ac; ac.can = (int)ci; ac.weight = cns_weight(ident_of(a));
+    t.acc.push_back(ac);
+    for (int i = a.toff; i < a.tend; ++i) ++t.cov[i];
+}
+
+// Replays consensus_one_read for one template as far as the available extension results allow.
+void replay(Tpl& t, std::vector<Can>& cans, const std::vector<nb_alignment>& res, const nb_cns_options& o)
+{
+    t.request.clear();
+    Can* c = cans.data() + t.first;
+    if (t.stage == 0) {
+        if (o.use_fixed_ident_cutoff) {                     // :276-281
+            t.cutoff = 100.0 * (1.0 - o.error); t.next = 0; t.num_can = 0; t.num_ovlps = 0;
+        } else {
+            // get_good_overlaps, error_estimate.c:96-184
+            std::vector<size_t> pool;
+            double ident[15]; int n_ident = 0;
+            size_t i;
+            for (i = 0; i < t.n && i < 50; ++i) {
+                if (is_used(t, c[i].qid)) continue;
+                const nb_alignment& a = res[(size_t)c[i].res];
+                if (!a.ok) continue;
+                pool.push_back(i);
+                set_used(t, c[i].qid);
+                if (good_overlap(a.qoff, a.qend, c[i].qsize, a.toff, a.tend, t.T)) {
+                    ident[n_ident++] = ident_of(a);
+                    if (n_ident == 15) break;
+                }
+            }
+            t.next = i;
+            if (n_ident < 15) {                             // get_idents, :66-93
+                int m = 0;
+                for (size_t p : pool) {
+                    const nb_alignment& a = res[(size_t)c[p].res];
+                    if (good_overlap(a.qoff, a.qend, c[p].qsize, a.toff, a.tend, t.T)) { ident[m++] = ident_of(a); if (m == 15) break; }
+                }
+                if (m < 15) {
+                    m = 0;
+                    for (size_t p : pool) {
+                        const nb_alignment& a = res[(size_t)c[p].res];
+                        if ((a.qend - a.qoff >= c[p].qsize * 0.6) || (a.tend - a.toff >= t.T * 0.6)) { ident[m++] = ident_of(a); if (m == 15) break; }
+                    }
+                }
+                n_ident = m;
+            }
+            std::sort(ident, ident + n_ident, [](double x, double y) { return x > y; });
+            if (n_ident >= 8) n_ident = (int)(n_ident * 0.7);
+            if (n_ident < 5) t.cutoff = 0.0;                 // :38-43
+            else {
+                double sum = 0.0;
+                for (int x = 0; x < n_ident; ++x) sum += ident[x];
+                const double avg = sum / n_ident;
+                double se = 0.0;
+                for (int x = 0; x < n_ident; ++x) se += (avg - ident[x]) * (avg - ident[x]);
+                se /= n_ident;
+                se = std::sqrt(se);
+                t.cutoff = avg - se * 5;
+            }
+            t.num_ovlps = 0;
+            for (size_t p : pool) {                         // add_extended_overlaps, consensus_one_read.c:148-183
+                const nb_alignment& a = res[(size_t)c[p].res];
+                if (ident_of(a) < t.cutoff) continue;
+                if (!mapping_range_ok(a.qoff, a.qend, c[p].qsize, a.toff, a.tend, t.T, o.min_align_size, o.mapping_ratio)) continue;
+                ++t.num_ovlps;
+                accept(t, p, a);
+                set_used(t, c[p].qid);
+            }
+            t.num_can = (int)t.next;
+        }
+        t.stage = 1;
+        t.in_window = false;
+    }
+    // main loop, consensus_one_read.c:316-372
+    for (;;) {
+        if (!t.in_window) {
+            if (t.next >= t.n || cov_full(t, 0, t.T, o.max_cov)) { t.stage = 2; return; }
+            t.win_i = t.next;
+            t.win_to = std::min(t.next + 50, t.n);
+            t.next = t.win_to;
+            t.in_window = true;
+        }
+        for (; t.win_i < t.win_to; ++t.win_i) {
+            const size_t i = t.win_i;
+            if (is_used(t, c[i].qid)) continue;
+            if (cov_full(t, c[i].sbeg, c[i].send, o.max_cov)) continue;
+            if (c[i].res < 0) {
+                // result missing: ask for everything in the window that is not skippable right now
+                for (size_t k = i; k < t.win_to; ++k) {
+                    if (c[k].res >= 0 || is_used(t, c[k].qid)) continue;
+                    if (cov_full(t, c[k].sbeg, c[k].send, o.max_cov)) continue;
+                    t.request.push_back(k);
+                }
+                return;
+            }
+            const nb_alignment& a = res[(size_t)c[i].res];
+            ++t.num_can;
+            if (!a.ok) continue;
+            const double id = ident_of(a);
+            if (id < t.cutoff && !full_cov_ovlp(a.qoff, a.qend, c[i].qsize, a.toff, a.tend, t.T, 5000, 100)) continue;
+            if (!mapping_range_ok(a.qoff, a.qend, c[i].qsize, a.toff, a.tend, t.T, o.min_align_size, o.mapping_ratio)) continue;
+            ++t.num_ovlps;
+            accept(t, i, a);
+            set_used(t, c[i].qid);
+        }
+        t.in_window = false;
+    }
+}
+
+struct DevBuf {
+    std::vector<void*> ptrs;
+    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+    template <typename T> int get(nb_ctx* ctx, T** p, uint64_t n)
+    {
+        NB_CUDA(ctx, cudaMalloc(p, sizeof(T) * (n ? n : 1)));
+        ptrs.push_back(*p);
+        return NB_OK;
+    }
+};
+
+inline int host_base(const nb_volume* v, uint64_t p) { return (v->h_pac[p >> 2] >> (((~p) & 3) << 1)) & 3; }
+
+struct OutRec { nb_cns_record r; std::vector<char> seq; };
+
+void push_raw(std::vector<nb_cns_record>& recs, std::vector<char>& seqs, const nb_volume* v, int id, int left, int right,
+              int org, int ncan, int novl, double cutoff)
+{
+    nb_cns_record r;
+    r.id = id; r.left = left; r.right = right; r.org_size = org; r.num_can = ncan; r.num_ovlps = novl;
+    r.ident_cutoff = cutoff; r.seq_offset = seqs.size(); r.seq_len = right - left; r.is_raw = 1;
+    const uint64_t off = v->h_off[id];
+    for (int i = left; i < right; ++i) seqs.push_back("ACGT"[host_base(v, off + (uint64_t)i)]);
+    recs.push_back(r);
+}
+
+}  // namespace
+
+extern "C" int nb_consensus_job(nb_ctx* ctx, const nb_volume* reads, const nb_packed_candidate* cans_in, uint64_t n_in,
+                                const nb_cns_options* opt, nb_cns_record** out_recs, uint64_t* n_recs, char** out_seq,
+                                uint64_t* out_seq_bytes)
+{
+    if (!ctx || !reads || (!cans_in && n_in) || !opt || !out_recs || !n_recs || !out_seq || !out_seq_bytes)
+        return nb_fail(ctx, NB_EINVAL, "nb_consensus_job: bad arguments");
+    *out_recs = NULL; *n_recs = 0; *out_seq = NULL; *out_seq_bytes = 0;
+    if (opt->rescue_long_indels)
+        return nb_fail(ctx, NB_EINVAL, "-r 1 (DALIGNER rescue, oc_daligner.c) is not implemented in the B200 build");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    memset(&ctx->cc, 0, sizeof ctx->cc);
+    ctx->tm.extend_ms = 0; ctx->tm.consensus_ms = 0;
+    const nb_cns_options o = *opt;
+    std::vector<nb_cns_record> recs;
+    std::vector<char> seqs;
+    if (n_in == 0) return NB_OK;
+
+    // ---- load order + normalisation (consensus_one_partition.c:10-95)
+    std::vector<nb_packed_candidate> pc(cans_in, cans_in + n_in);
+    for (auto& p : pc) {
+        if (p.item[1] >= reads->nseq || p.item[4] >= reads->nseq) return nb_fail(ctx, NB_EINVAL, "candidate read id out of range");
+    }
+    std::stable_sort(pc.begin(), pc.end(), [](const nb_packed_candidate& a, const nb_packed_candidate& b) { return a.item[1] < b.item[1]; });
+    const int min_id = (int)pc.front().item[1], max_id = (int)pc.back().item[1];
+    for (auto& p : pc) {                                            // normalise_pcan_sdir, gapped_candidate.c:72-93
+        const uint32_t w = p.item[0];
+        if (!(w >> 31)) continue;
+        uint32_t r = w & ((1u << 29) - 1);
+        if (!((w >> 30) & 1)) r |= 1u << 30;
+        if (!(w & (1u << 29))) r |= 1u << 29;
+        p.item[0] = r;
+        const uint32_t qs = reads->h_len[p.item[4]], ss = reads->h_len[p.item[1]];
+        const uint32_t qb = qs - p.item[6], qe = qs - p.item[5];
+        p.item[5] = qb; p.item[6] = qe;
+        const uint32_t sb = ss - p.item[3], se = ss - p.item[2];
+        p.item[2] = sb; p.item[3] = se;
+    }
+    std::vector<uint8_t> corrected(reads->nseq, 0);
+
+    // ---- templates
+    std::vector<Tpl> tpls;
+    std::vector<Can> cans;
+    {
+        size_t i = 0;
+        std::vector<nb_packed_candidate> one;
+        while (i < pc.size()) {
+            size_t j = i + 1;
+            while (j < pc.size() && pc[j].item[1] == pc[i].item[1]) ++j;
+            if ((size_t)o.min_cov <= j - i) {                       // consensus_one_read.c:218
+                one.assign(pc.begin() + i, pc.begin() + j);
+                std::sort(one.begin(), one.end(), [](const nb_packed_candidate& a, const nb_packed_candidate& b) {
+                    // PackedGappedCandidate_CnsScoreGT, gapped_candidate.c:96-126
+                    const int as = (int)(a.item[0] & ((1u << 29) - 1)), bs = (int)(b.item[0] & ((1u << 29) - 1));
+                    if (as != bs) return as > bs;
+                    if (a.item[4] != b.item[4]) return (int)a.item[4] < (int)b.item[4];
+                    const int ad = (a.item[0] >> 30) & 1, bd = (b.item[0] >> 30) & 1;
+                    if (ad != bd) return ad < bd;
+                    if (a.item[5] != b.item[5]) return (int)a.item[5] < (int)b.item[5];
+                    return (int)a.item[2] < (int)b.item[2];
+                });
+                if (one.size() > 300) one.resize(300);              // MAX_EXAMINED_CAN
+                Tpl t;
+                t.tid = (int)pc[i].item[1]; t.T = (int)reads->h_len[t.tid];
+                t.first = cans.size(); t.n = one.size();
+                t.stage = 0; t.next = 0; t.win_to = 0; t.win_i = 0; t.in_window = false; t.cutoff = 0; t.num_can = 0; t.num_ovlps = 0;
+                for (const auto& p : one) {
+                    Can c;
+                    const uint32_t w = p.item[0];
+                    c.qid = (int)p.item[4]; c.qdir = (int)((w >> 30) & 1); c.score = (int)(w & ((1u << 29) - 1));
+                    c.sbeg = (int)p.item[2]; c.send = (int)p.item[3]; c.qbeg = (int)p.item[5];
+                    if (w & (1u << 29)) { c.qoff = (int)p.item[5]; c.soff = (int)p.item[2]; }
+                    else                { c.qoff = (int)p.item[6]; c.soff = (int)p.item[3]; }
+                    c.qsize = (int)reads->h_len[c.qid];
+                    c.res = -1;
+                    cans.push_back(c);
+                }
+                tpls.push_back(std::move(t));
+            }
+            i = j;
+        }
+    }
+    ctx->cc.n_templates = tpls.size();
+
+    // ---- chunks of templates: bounded device memory
+    const size_t kChunk = 8192;
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads == 0) nthreads = 4;
+    if (nthreads > 32) nthreads = 32;
+    float ext_ms = 0, cns_ms = 0;
+    for (size_t c0 = 0; c0 < tpls.size(); c0 += kChunk) {
+        const size_t c1 = std::min(tpls.size(), c0 + kChunk);
+        DevBuf D;                                   // everything allocated for this chunk
+        std::vector<nb_alignment> res;              // results of all rounds of this chunk
+        std::vector<const uint8_t*> res_ops;        // device pointer of each result's ops
+        for (size_t t = c0; t < c1; ++t) tpls[t].cov.assign((size_t)tpls[t].T + 1, 0);
+        // round 0 requests: the first 50 candidates (phase 1), or the first window with -u 1
+        for (size_t t = c0; t < c1; ++t) {
+            Tpl& T = tpls[t];
+            T.request.clear();
+            if (!o.use_fixed_ident_cutoff) for (size_t k = 0; k < T.n && k < 50; ++k) T.request.push_back(k);
+        }
+        for (int round = 0;; ++round) {
+            if (round > 0 || o.use_fixed_ident_cutoff) {
+                // replay in parallel over templates
+                std::vector<std::thread> th;
+                std::vector<size_t> todo;
+                for (size_t t = c0; t < c1; ++t) if (tpls[t].stage != 2) todo.push_back(t);
+                const size_t per = (todo.size() + nthreads - 1) / nthreads;
+                for (unsigned w = 0; w < nthreads && per; ++w) {
+                    const size_t a = w * per, b = std::min(todo.size(), a + per);
+                    if (a >= b) break;
+                    th.emplace_back([&, a, b]() { for (size_t x = a; x < b; ++x) replay(tpls[todo[x]], cans, res, o); });
+                }
+                for (auto& x : th) x.join();
+            }
+            // gather requests
+            std::vector<ExtTask> tasks;
+            std::vector<size_t> task_can;
+            uint64_t pool = 0;
+            for (size_t t = c0; t < c1; ++t) {
+                Tpl& T = tpls[t];
+                if (T.stage == 2) continue;
+                for (size_t k : T.request) {
+                    const Can& c = cans[T.first + k];
+                    ExtTask e;
+                    e.qid = (uint32_t)c.qid; e.sid = (uint32_t)T.tid; e.qoff = c.qoff; e.soff = c.soff; e.qdir = c.qdir; e.pad_ = 0;
+                    if (c.qoff < 0 || c.soff < 0 || c.qoff > c.qsize || c.soff > T.T)
+                        return nb_fail(ctx, NB_EINVAL, "candidate offsets out of range (template %d)", T.tid);
+                    const uint64_t mn = (uint64_t)std::min(c.qoff, c.soff);
+                    e.lcap = (uint32_t)(c.qoff + c.soff);
+                    e.ops_cap = (uint32_t)((uint64_t)c.qsize + (uint64_t)T.T + mn + 64);
+                    e.ops_base = pool;
+                    pool += (e.ops_cap + 15) & ~15ull;
+                    tasks.push_back(e);
+                    task_can.push_back(T.first + k);
+                }
+            }
+            if (tasks.empty()) break;
+            if (tasks.size() >= (1ull << 31)) return nb_fail(ctx, NB_ELIMIT, "too many extension tasks in one round");
+            ExtTask* d_tasks; nb_alignment* d_res; uint8_t* d_ops;
+            int rc;
+            if ((rc = D.get(ctx, &d_tasks, tasks.size()))) return rc;
+            if ((rc = D.get(ctx, &d_res, tasks.size()))) return rc;
+            if ((rc = D.get(ctx, &d_ops, pool + 64))) return rc;
+            NB_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ExtTask) * tasks.size(), cudaMemcpyHostToDevice, st));
+            cudaEventRecord(ctx->ev0, st);
+            rc = nb_run_extension(ctx, reads, d_tasks, (uint32_t)tasks.size(), d_res, d_ops, o.error, o.min_align_size, 4 /* ONC_TAIL_MATCH_LEN_LONG */);
+            if (rc) return rc;
+            cudaEventRecord(ctx->ev1, st);
+            const size_t r0 = res.size();
+            res.resize(r0 + tasks.size());
+            NB_CUDA(ctx, cudaMemcpyAsync(res.data() + r0, d_res, sizeof(nb_alignment) * tasks.size(), cudaMemcpyDeviceToHost, st));
+            NB_CUDA(ctx, cudaStreamSynchronize(st));
+            float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ext_ms += ms;
+            ctx->tm.h2d_bytes += sizeof(ExtTask) * tasks.size();
+            ctx->tm.d2h_bytes += sizeof(nb_alignment) * tasks.size();
+            res_ops.resize(res.size());
+            for (size_t k = 0; k < tasks.size(); ++k) {
+                cans[task_can[k]].res = (int)(r0 + k);
+                res_ops[r0 + k] = d_ops + res[r0 + k].ops_offset;
+            }
+            if (round > 64) return nb_fail(ctx, NB_ECUDA, "extension rounds do not converge");
+        }
+
+        // ---- consensus of the chunk
+        std::vector<CnsAln> alns;
+        std::vector<CnsTemplate> dt;
+        std::vector<size_t> dt_tpl;
+        uint64_t out_pool = 0; uint32_t seg_total = 0; uint32_t maxT = 0;
+        for (size_t t = c0; t < c1; ++t) {
+            Tpl& T = tpls[t];
+            CnsTemplate ct;
+            ct.aln_first = (uint32_t)alns.size(); ct.n_aln = (uint32_t)T.acc.size(); ct.T = T.T;
+            for (const Accepted& a : T.acc) {
+                const Can& c = cans[T.first + (size_t)a.can];
+                const nb_alignment& r = res[(size_t)c.res];
+                CnsAln ca;
+                ca.ops = res_ops[(size_t)c.res]; ca.qseq_off = reads->h_off[c.qid];
+                ca.aln_size = r.aln_size; ca.toff = r.toff; ca.tend = r.tend; ca.qstart = r.qoff;
+                ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight;
+                alns.push_back(ca);
+            }
+            ct.seg_cap = (uint32_t)(T.T / std::max(1, (int)(o.min_size * 0.85)) + 2);
+            ct.seg_first = seg_total; seg_total += ct.seg_cap;
+            ct.out_cap = (uint32_t)(T.T * 2 + 1024);
+            ct.out_base = out_pool; out_pool += ct.out_cap;
+            ct.pad_ = 0;
+            if ((uint32_t)T.T > maxT) maxT = (uint32_t)T.T;
+            ctx->cc.n_accepted += T.acc.size();
+            dt.push_back(ct); dt_tpl.push_back(t);
+        }
+        std::vector<CnsSegment> segs(seg_total);
+        std::vector<uint32_t> nseg(dt.size(), 0);
+        std::vector<uint8_t> seq_codes;
+        if (!dt.empty()) {
+            int rc;
+            const unsigned grid = NB_SMS * 4;           // 16 warps per SM
+            const size_t slots = (size_t)grid * CNS_WARPS;
+            const uint32_t cap_steps = maxT * 4 + 4096;
+            CnsParams P;
+            memset(&P, 0, sizeof P);
+            CnsTemplate* d_tpl; CnsAln* d_aln;
+            if ((rc = D.get(ctx, &d_tpl, dt.size()))) return rc;
+            if ((rc = D.get(ctx, &d_aln, alns.size()))) return rc;
+            if ((rc = D.get(ctx, &P.seg, seg_total))) return rc;
+            if ((rc = D.get(ctx, &P.tpl_nseg, dt.size()))) return rc;
+            if ((rc = D.get(ctx, &P.seq_pool, out_pool))) return rc;
+            if ((rc = D.get(ctx, &P.next_tpl, 1))) return rc;
+            if ((rc = D.get(ctx, &P.cov, slots * (maxT + 2)))) return rc;
+            if ((rc = D.get(ctx, &P.pos_first, slots * (maxT + 2)))) return rc;
+            if ((rc = D.get(ctx, &P.bp, slots * (size_t)cap_steps))) return rc;
+            if ((rc = D.get(ctx, &P.rev, slots * (size_t)cap_steps))) return rc;
+            if ((rc = D.get(ctx, &P.error_flag, 1))) return rc;
+            if ((rc = D.get(ctx, &P.counters, 4))) return rc;
+            NB_CUDA(ctx, cudaMemcpyAsync(d_tpl, dt.data(), sizeof(CnsTemplate) * dt.size(), cudaMemcpyHostToDevice, st));
+            NB_CUDA(ctx, cudaMemcpyAsync(d_aln, alns.data(), sizeof(CnsAln) * alns.size(), cudaMemcpyHostToDevice, st));
+            NB_CUDA(ctx, cudaMemsetAsync(P.next_tpl, 0, sizeof(uint32_t), st));
+            NB_CUDA(ctx, cudaMemsetAsync(P.error_flag, 0, sizeof(uint32_t), st));
+            NB_CUDA(ctx, cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 4, st));
+            P.pac = reads->d_pac; P.tpl = d_tpl; P.aln = d_aln; P.n_tpl = (uint32_t)dt.size();
+            P.maxT = maxT; P.cap_steps = cap_steps; P.min_cov = o.min_cov; P.min_size = o.min_size;
+            const size_t smem = sizeof(CnsWarpShared) * CNS_WARPS;
+            if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaEventRecord(ctx->ev2, st);
+            k_consensus<<<grid, CNS_WARPS * 32, smem, st>>>(P);
+            NB_LAUNCH_CHECK(ctx);
+            cudaEventRecord(ctx->ev3, st);
+            uint32_t eflag = 0; unsigned long long cnt[4];
+            NB_CUDA(ctx, cudaMemcpyAsync(&eflag, P.error_flag, sizeof eflag, cudaMemcpyDeviceToHost, st));
+            NB_CUDA(ctx, cudaMemcpyAsync(cnt, P.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
+            NB_CUDA(ctx, cudaMemcpyAsync(segs.data(), P.seg, sizeof(CnsSegment) * seg_total, cudaMemcpyDeviceToHost, st));
+            NB_CUDA(ctx, cudaMemcpyAsync(nseg.data(), P.tpl_nseg, sizeof(uint32_t) * dt.size(), cudaMemcpyDeviceToHost, st));
+            seq_codes.resize(out_pool);
+            NB_CUDA(ctx, cudaMemcpyAsync(seq_codes.data(), P.seq_pool, out_pool, cudaMemcpyDeviceToHost, st));
+            NB_CUDA(ctx, cudaStreamSynchronize(st));
+            float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); cns_ms += ms;
+            ctx->tm.d2h_bytes += out_pool + sizeof(CnsSegment) * seg_total;
+            ctx->cc.n_tags += cnt[1];
+            if (eflag) return nb_fail(ctx, NB_ELIMIT, "consensus kernel capacity exceeded (flags %u)", eflag);
+        }
+        // ---- records (tasc/cbcns.c:108-264, consensus_one_read.c:20-136)
+        for (size_t x = 0; x < dt.size(); ++x) {
+            Tpl& T = tpls[dt_tpl[x]];
+            const CnsSegment* sg = segs.data() + dt[x].seg_first;
+            const uint32_t ns = nseg[x];
+            if (!o.full_consensus) {
+                for (uint32_t k = 0; k < ns; ++k) {
+                    nb_cns_record r;
+                    r.id = T.tid; r.left = sg[k].left; r.right = sg[k].right; r.org_size = T.T; r.num_can = T.num_can;
+                    r.num_ovlps = T.num_ovlps; r.ident_cutoff = T.cutoff; r.seq_offset = seqs.size(); r.seq_len = (int)sg[k].len; r.is_raw = 0;
+                    for (uint32_t b = 0; b < sg[k].len; ++b) seqs.push_back("ACGT"[seq_codes[sg[k].seq_off + b]]);
+                    recs.push_back(r);
+                    ctx->cc.cns_bases += sg[k].len;
+                }
+                // raw stretches between the corrected runs (get_raw_intvs, consensus_one_read.c:20-65)
+                bool first = true, open = true;
+                int left = 0;
+                const int end_off = T.T - 1;
+                for (uint32_t k = 0; k < ns; ++k) {
+                    const int fs = sg[k].left, fe = sg[k].right;
+                    if (first) {
+                        open = false; first = false;
+                        if (fs > 0) left = 0;
+                        else { left = fe + 1; continue; }
+                    }
+                    const int right = fs - 1;
+                    if (right - left + 1 >= 1000) push_raw(recs, seqs, reads, T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff);
+                    if (fe >= end_off) { open = false; break; }
+                    left = fe + 1;
+                }
+                if (open) {
+                    const int right = end_off;
+                    if (right - left + 1 >= 1000) push_raw(recs, seqs, reads, T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff);
+                }
+                corrected[(size_t)T.tid] = 1;                       // consensus_one_read.c:391 (r stays 1)
+            } else if (ns) {
+                // consensus_unbroken (cbcns.c:218-257): corrected runs spliced into the raw read
+                nb_cns_record r;
+                r.id = T.tid; r.left = 0; r.right = T.T; r.org_size = T.T; r.num_can = T.num_can; r.num_ovlps = T.num_ovlps;
+                r.ident_cutoff = T.cutoff; r.seq_offset = seqs.size(); r.is_raw = 0;
+                const uint64_t off = reads->h_off[T.tid];
+                int last_raw = 0;
+                for (uint32_t k = 0; k < ns; ++k) {
+                    const int rf = sg[k].cns_from, rt = sg[k].cns_to;
+                    for (int i = last_raw; i < rf; ++i) seqs.push_back("ACGT"[host_base(reads, off + (uint64_t)i)]);
+                    for (uint32_t b = 0; b < sg[k].len; ++b) seqs.push_back("ACGT"[seq_codes[sg[k].seq_off + b]]);
+                    last_raw = rt;
+                }
+                for (int i = last_raw; i < T.T; ++i) seqs.push_back("ACGT"[host_base(reads, off + (uint64_t)i)]);
+                r.seq_len = (int)(seqs.size() - r.seq_offset);
+                recs.push_back(r);
+                ctx->cc.cns_bases += (uint64_t)r.seq_len;
+                corrected[(size_t)T.tid] = 1;
+            }
+            T.cov.clear(); T.cov.shrink_to_fit();
+        }
+    }
+    ctx->tm.extend_ms = ext_ms;
+    ctx->tm.consensus_ms = cns_ms;
+
+    // ---- reads of [min_id, max_id) that were never corrected go to raw_out whole (consensus_one_partition.c:173-194)
+    for (int id = min_id; id < max_id; ++id) {
+        if (corrected[(size_t)id]) continue;
+        const int L = (int)reads->h_len[id];
+        push_raw(recs, seqs, reads, id, 0, L, L, 0, 0, 0.0);
+    }
+    ctx->cc.n_cns_records = recs.size();
+
+    nb_cns_record* r_out = (nb_cns_record*)malloc(sizeof(nb_cns_record) * (recs.size() ? recs.size() : 1));
+    char* s_out = (char*)malloc(seqs.size() ? seqs.size() : 1);
+    if (!r_out || !s_out) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    if (!recs.empty()) memcpy(r_out, recs.data(), sizeof(nb_cns_record) * recs.size());
+    if (!seqs.empty()) memcpy(s_out, seqs.data(), seqs.size());
+    *out_recs = r_out; *n_recs = recs.size(); *out_seq = s_out; *out_seq_bytes = seqs.size();
+    return NB_OK;
+}

@@ -33,6 +33,7 @@ struct nb_volume {
     uint64_t* h_off;        // host copies (the sequential host logic needs them)
     uint32_t* h_len;
     uint32_t  max_len;
+    uint8_t*  h_pac;        // host copy of the packed bases (raw leftovers are cut on the host)
 };
 
 struct nb_index {

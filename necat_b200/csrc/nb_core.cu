@@ -96,6 +96,9 @@ extern "C" int nb_volume_upload(nb_ctx* ctx, const uint8_t* pac, uint64_t db_siz
         v->h_len[i] = (uint32_t)seq_size[i];
         if (v->h_len[i] > v->max_len) v->max_len = v->h_len[i];
     }
+    v->h_pac = (uint8_t*)malloc(nb + 16);
+    if (!v->h_pac) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    memcpy(v->h_pac, pac, nb);
     v->h_off[nseq] = db_size;
     v->h_len[nseq] = 0;
     cudaEventRecord(ctx->ev0, ctx->stream);
@@ -121,6 +124,7 @@ extern "C" void nb_volume_free(nb_ctx* ctx, nb_volume* v)
     cudaFree(v->d_len);
     free(v->h_off);
     free(v->h_len);
+    free(v->h_pac);
     free(v);
 }
 

@@ -1,0 +1,66 @@
+"""GPU parity of the oc2cns half: oc2pcan + oc2cns drop-in executables against the
+CPU oracle on the same candidates (canonical record order)."""
+import os
+import shutil
+
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+OC2CNS = os.path.join(util.BIN_DIR, "oc2cns")
+OC2PCAN = os.path.join(util.BIN_DIR, "oc2pcan")
+
+
+def _run_cns(tmp_path, wrk, cand, opts, tag):
+    c = str(tmp_path / f"cand_{tag}.bin")
+    shutil.copy(cand, c)
+    util.run([OC2PCAN, "-t", "1", wrk, c])
+    cns, raw = str(tmp_path / f"{tag}_cns.fasta"), str(tmp_path / f"{tag}_raw.fasta")
+    util.run([OC2CNS] + opts.split() + [wrk, c, cns, raw])
+    return cns, raw
+
+
+def _run_oracle(tmp_path, wrk, cand, opts, tag):
+    cns, raw = str(tmp_path / f"{tag}_cns.fasta"), str(tmp_path / f"{tag}_raw.fasta")
+    util.run([util.ORACLE_CLI, "cns"] + opts.split() + ["-M", "0", wrk, cand, cns, raw])
+    return cns, raw
+
+
+@pytest.mark.parametrize("opts,gen", [
+    (util.CNS_SENSITIVE, dict(genome=100_000, depth=25, seed=41)),
+    ("-a 2000 -x 4 -y 12 -l 1000 -e 0.5 -p 0.8 -u 0 -r 0 -f 1", dict(genome=80_000, depth=25, seed=42)),
+    ("-a 1000 -x 3 -y 8 -l 500 -e 0.5 -p 0.6 -u 1 -r 0 -f 0", dict(genome=60_000, depth=30, seed=43, err=0.10)),
+    (util.CNS_SENSITIVE, dict(genome=80_000, depth=40, seed=44, err=0.10, repeat_len=4000, repeat_copies=6, n_repeats=2)),
+])
+def test_cns_matches_oracle(built, tmp_path, opts, gen):
+    wrk, _ = util.make_workdir(tmp_path, **gen)
+    cand = str(tmp_path / "cand.bin")
+    util.run_pmov(util.ORACLE_CLI, util.PM_SENSITIVE, wrk, 0, cand)
+    g_cns, g_raw = _run_cns(tmp_path, wrk, cand, opts, "gpu")
+    o_cns, o_raw = _run_oracle(tmp_path, wrk, cand, opts, "oracle")
+    ec, er = util.fasta_canon(o_cns), util.fasta_canon(o_raw)
+    assert len(ec) > 20
+    gc, gr = util.fasta_canon(g_cns), util.fasta_canon(g_raw)
+    assert len(gc) == len(ec) and len(gr) == len(er), f"record counts: cns {len(gc)}/{len(ec)} raw {len(gr)}/{len(er)}"
+    bad = [i for i, (a, b) in enumerate(zip(gc, ec)) if a != b]
+    assert not bad, f"{len(bad)} corrected records differ, first: {gc[bad[0]][0]} vs {ec[bad[0]][0]}"
+    assert gr == er
+
+
+def test_cns_multi_volume(built, tmp_path):
+    """Several volumes: oc2cns merges them (consensus/main.c:66) and ids stay global."""
+    wrk, _ = util.make_workdir(tmp_path, genome=80_000, depth=24, seed=45, vol_size=700_000)
+    nvol = int(open(os.path.join(wrk, "reads_info.txt")).read().split()[0])
+    assert nvol >= 2
+    cand = str(tmp_path / "cand.bin")
+    with open(cand, "wb") as out:
+        for vid in range(nvol):
+            p = str(tmp_path / f"pm{vid}.bin")
+            util.run_pmov(util.ORACLE_CLI, util.PM_SENSITIVE, wrk, vid, p)
+            out.write(open(p, "rb").read())
+    g_cns, g_raw = _run_cns(tmp_path, wrk, cand, util.CNS_SENSITIVE, "gpu")
+    o_cns, o_raw = _run_oracle(tmp_path, wrk, cand, util.CNS_SENSITIVE, "oracle")
+    assert util.fasta_canon(g_cns) == util.fasta_canon(o_cns)
+    assert util.fasta_canon(g_raw) == util.fasta_canon(o_raw)
