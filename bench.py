@@ -1,0 +1,322 @@
+#!/usr/bin/env python3
+"""bench.py -- one correction iteration of NECAT's hot path (oc2pmov -> oc2pcan -> oc2cns)
+on N B200s, BASELINE.json config[1]: E. coli-size 4.6 Mb genome, 40x synthetic ONT-like
+reads (15 % error), OVLP_SENSITIVE + CNS_SENSITIVE options, -r 0 -f 0.
+
+A "step" is one full pass over the read set: k-mer index build, candidate finding,
+candidate regrouping, extension + consensus.  `value` = corrected bases per second
+with the packed reads already resident in HBM; `e2e` = the same through the C-ABI
+with host buffers (volume upload included; candidates and FASTA records always come
+back to the host).  One process per GPU; N > 1 shards the query reads for the mapping
+half, exchanges the 28-byte candidate records with an NCCL all-gather, and shards
+the templates (id mod N) for the correction half.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+PM_OPTS = dict(kmer_size=15, scan_window=10, kmer_cnt_cutoff=500, block_size=2000, block_score_cutoff=3,
+               num_candidates=500, align_size_cutoff=1000, ddfs_cutoff=0.25, error=0.5, num_output=500,
+               num_threads=1, job=0, binary_output=1, use_hdr_as_id=1)            # necat.pl:20,32
+CNS_OPTS = dict(min_align_size=2000, min_cov=4, max_cov=12, min_size=1000, full_consensus=0, error=0.5,
+                mapping_ratio=0.8, rescue_long_indels=0, use_fixed_ident_cutoff=0)  # necat.pl:34,251-261
+PM_STR = "-k 15 -z 10 -q 500 -b 2000 -s 3 -n 500 -a 1000 -d 0.25 -e 0.5 -m 500 -j 0 -u 1 -i 1"
+CNS_STR = "-a 2000 -x 4 -y 12 -l 1000 -e 0.5 -p 0.8 -u 0 -r 0 -f 0"
+SEED = 20260925
+
+
+def make_reads(genome, depth):
+    import gen_reads
+    _, reads = gen_reads.generate(genome, depth, SEED)
+    return reads
+
+
+def reads_to_volume(reads):
+    from necat_b200 import formats
+    info = np.zeros(len(reads), formats.SEQINFO)
+    hdr = bytearray()
+    off = 0
+    for i, r in enumerate(reads):
+        info[i] = (off, r.size, len(hdr), 0, 0)
+        hdr += b"r%d\0" % i
+        off += r.size
+    return formats.Volume(formats.pack_bases(np.concatenate(reads)), off, info, bytes(hdr))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(genome, depth, threads, td, reads=None):
+    """The unmodified reference binaries (oracle/_ref) on a read set; returns timings + outputs."""
+    from necat_b200 import formats
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if reads is None:
+        reads = make_reads(genome, depth)
+    wrk = os.path.join(td, "vol")
+    formats.write_workdir(wrk, reads)
+    cand = os.path.join(td, "cns_candidates.txt")
+    t = {}
+    t0 = time.perf_counter()
+    log = subprocess.run([os.path.join(ref, "oc2pmov")] + PM_STR.split() + ["-t", str(threads), wrk, "0", cand],
+                         check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    t["pmov_s"] = time.perf_counter() - t0
+    for line in log.splitlines():
+        if "'pairwise mapping v0 vs v0' takes" in line:
+            t["pmov_mapping_s"] = float(line.split("takes")[1].split("secs")[0])
+    t0 = time.perf_counter()
+    subprocess.run([os.path.join(ref, "oc2pcan"), "-t", str(threads), wrk, cand], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t["pcan_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    subprocess.run([os.path.join(ref, "oc2cns")] + CNS_STR.split() + ["-t", str(threads), wrk, cand,
+                   os.path.join(td, "cns.fasta"), os.path.join(td, "raw.fasta")], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t["cns_s"] = time.perf_counter() - t0
+    t["n_candidates"] = os.path.getsize(cand) // 28
+    t["cns_bases"] = sum(len(s) for _, s in formats.read_fasta_records(os.path.join(td, "cns.fasta")))
+    t["total_s"] = t["pmov_s"] + t["pcan_s"] + t["cns_s"]
+    return t
+
+
+def reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation on the host cores, bounded sample."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ref = os.path.join(ROOT, "oracle", "_ref", "oc2cns")
+    if not os.path.exists(ref):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binaries are missing (build with make -C oracle ref)"}))
+        return
+    sample_genome = args.sample_genome
+    times = []
+    last = None
+    for it in range(args.warmup + args.steps):
+        with tempfile.TemporaryDirectory() as td:
+            last = run_reference(sample_genome, args.depth, threads, td)
+        if it >= args.warmup:
+            times.append(last["total_s"])
+    sec = float(np.mean(times))
+    val = last["cns_bases"] / sec
+    sample = f"{sample_genome / 1e6:.2f} Mb genome x {args.depth:g} (same generator, seed {SEED}), oc2pmov+oc2pcan+oc2cns wall"
+    print(json.dumps({
+        "impl": "reference", "metric": "corrected_bases_per_sec", "value": val, "unit": "bases/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"E. coli-size {args.genome / 1e6:.1f} Mb x {args.depth:g} synthetic ONT reads, one correction iteration "
+                               "(oc2pmov SENSITIVE -> oc2pcan -> oc2cns -r 0 -f 0)", "bounded_sample": sample},
+        "overlaps_per_sec": last["n_candidates"] / sec,
+        "stage_s": {k: last[k] for k in ("pmov_s", "pmov_mapping_s", "pcan_s", "cns_s") if k in last},
+        "cpu_baseline": {"value": val, "unit": "bases/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome", type=int, default=4_600_000)
+    ap.add_argument("--depth", type=float, default=40.0)
+    ap.add_argument("--sample-genome", type=int, default=400_000, help="genome size of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from necat_b200 import capi, formats
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    reads = make_reads(args.genome, args.depth)
+    vol = reads_to_volume(reads)
+    nreads = vol.nseq
+    sizes = vol.info["size"].astype(np.int64)
+    ctx = capi.Context(local_rank)
+    popt = capi.default_map_options(**PM_OPTS)
+    copt = capi.default_cns_options(**CNS_OPTS)
+    lo, hi = (nreads * rank) // world, (nreads * (rank + 1)) // world
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    stats = {}
+
+    def one_step(dvol):
+        """index -> candidates -> exchange -> regroup -> correct.  Returns corrected bases of this rank."""
+        idx = ctx.build_index(dvol, PM_OPTS["kmer_size"], PM_OPTS["kmer_cnt_cutoff"])
+        t = ctx.timings(); stats["index_ms"] = t.index_ms
+        cands = ctx.map_volume(idx, dvol, 0, dvol, 0, lo, hi, popt)
+        t = ctx.timings(); stats["map_ms"] = t.map_ms; stats["map_probe_ms"] = t.map_probe_ms
+        mc = ctx.map_counters()
+        stats["map_counters"] = {k: int(getattr(mc, k)) for k, _ in mc._fields_}
+        ctx.free_index(idx)
+        packed = capi.pack_candidates(cands)
+        if world > 1:
+            # the one exchange step: every rank needs the candidates of all query shards
+            mine = torch.from_numpy(packed.reshape(-1).view(np.int32).copy()).to(dev)
+            counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(counts, torch.tensor([mine.numel()], dtype=torch.int64, device=dev))
+            counts = [int(c.item()) for c in counts]
+            bufs = [torch.empty(max(counts), dtype=torch.int32, device=dev) for _ in range(world)]
+            pad = torch.zeros(max(counts), dtype=torch.int32, device=dev)
+            pad[:mine.numel()] = mine
+            dist.all_gather(bufs, pad)
+            packed = np.concatenate([b[:c].cpu().numpy().view(np.uint32).reshape(-1, 7) for b, c in zip(bufs, counts)])
+        stats["n_candidates"] = int(packed.shape[0])
+        # oc2pcan: every record under its subject and (swapped) under its query; one partition (< 100000 reads)
+        part = np.concatenate([packed, formats.swap_roles(packed)])
+        recs, seq = ctx.consensus_job(dvol, part, copt, world, rank)
+        t = ctx.timings(); stats["extend_ms"] = t.extend_ms; stats["consensus_ms"] = t.consensus_ms
+        cc = ctx.cns_counters()
+        stats["cns_counters"] = {k: int(getattr(cc, k)) for k, _ in cc._fields_}
+        return int(recs["seq_len"][recs["is_raw"] == 0].sum())
+
+    def timed(n_steps, upload_each):
+        dvol = None if upload_each else ctx.upload(vol)
+        total_bases = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            flush.fill_(1)                              # flush L2 between iterations
+            torch.cuda.synchronize()
+            d = ctx.upload(vol) if upload_each else dvol
+            total_bases = one_step(d)
+            if upload_each:
+                ctx.free_volume(d)
+        barrier()
+        dt = time.perf_counter() - t0
+        if not upload_each:
+            ctx.free_volume(dvol)
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        bb = torch.tensor([total_bases], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bb, op=dist.ReduceOp.SUM)
+        return float(tt.item()), int(bb.item())
+
+    timed(args.warmup, False)
+    launches0 = ctx.launches()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dt, bases = timed(args.steps, False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (ctx.launches() - launches0) // max(args.steps, 1)
+    tm0 = ctx.timings()
+    dt_e2e, bases_e2e = timed(args.steps, True)
+    tm1 = ctx.timings()
+    if rank != 0:
+        return
+    sec = dt / args.steps
+    sec_e2e = dt_e2e / args.steps
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    cc, mc = stats["cns_counters"], stats["map_counters"]
+    # dominant kernel = the extension kernel k_extend: algorithmic bytes per launch =
+    # walk-back state written once (8 B per 32-row word per DP column) + packed bases of every block
+    # (0.25 B per base, ~2 x 512 per block) + one op byte per alignment column (~1.2 x 512 per block)
+    ext_bytes = cc["n_dp_word_updates"] * 8 + cc["n_block_aligns"] * (0.25 * 1024 + 620)
+    ext_gbs = ext_bytes / (stats["extend_ms"] * 1e-3) / 1e9 if stats["extend_ms"] else 0.0
+    out = {
+        "metric": "corrected_bases_per_sec", "value": bases / sec, "unit": "bases/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"E. coli-size {args.genome / 1e6:.1f} Mb x {args.depth:g} synthetic ONT reads (15% error, seed {SEED}), "
+                               "one correction iteration: oc2pmov SENSITIVE (-j 0) -> oc2pcan -> oc2cns -r 0 -f 0",
+                   "reads": int(nreads), "bases": int(vol.db_size), "parallelism": f"reads/templates sharded x{world}",
+                   "l2": "512 MB flush write between iterations; index (4 GiB table) and DP scratch exceed L2"},
+        "overlaps_per_sec": stats["n_candidates"] / sec,
+        "corrected_bases": bases, "candidates": stats["n_candidates"],
+        "stage_ms": {k: stats[k] for k in ("index_ms", "map_ms", "map_probe_ms", "extend_ms", "consensus_ms")},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "e2e": {"value": bases_e2e / sec_e2e, "unit": "bases/s", "ms_per_step": sec_e2e * 1e3,
+                "h2d_bytes_per_step": int((tm1.h2d_bytes - tm0.h2d_bytes) // max(args.steps, 1)),
+                "d2h_bytes_per_step": int((tm1.d2h_bytes - tm0.d2h_bytes) // max(args.steps, 1))},
+        "roofline": {"kernel": "k_extend", "bound": "hbm", "achieved": ext_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": ext_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "word_updates_per_s": cc["n_dp_word_updates"] / (stats["extend_ms"] * 1e-3) if stats["extend_ms"] else 0.0},
+        "counters": {"map": mc, "cns": cc},
+    }
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "oc2cns")):
+            with tempfile.TemporaryDirectory() as td:
+                r = run_reference(args.sample_genome, args.depth, threads, td)
+            out["cpu_baseline"] = {"value": r["cns_bases"] / r["total_s"], "unit": "bases/s", "cores": threads, "kind": "reference",
+                                   "sample": f"{args.sample_genome / 1e6:.2f} Mb genome x {args.depth:g}, same generator; "
+                                             f"oc2pmov {r['pmov_s']:.1f}s (mapping {r.get('pmov_mapping_s', 0):.2f}s) + oc2pcan "
+                                             f"{r['pcan_s']:.2f}s + oc2cns {r['cns_s']:.1f}s"}
+        else:
+            out["cpu_baseline"] = {"value": None, "unit": "bases/s", "cores": threads, "kind": "reference",
+                                   "sample": "oracle/_ref missing"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -184,6 +184,19 @@ int  nb_consensus_job(nb_ctx* ctx, const nb_volume* reads,
                       nb_cns_record** out_recs, uint64_t* n_recs,
                       char** out_seq, uint64_t* out_seq_bytes);
 
+/*
+ * Multi-GPU form: the same partition is handed to every rank, rank `shard_index`
+ * of `shard_count` corrects the templates with id % shard_count == shard_index
+ * (and dumps only those uncorrected reads); the union of the ranks' records is
+ * exactly nb_consensus_job's output.  Templates are independent
+ * (consensus/main.c:71-73), so no collective is needed inside.
+ */
+int  nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads,
+                              const nb_packed_candidate* cans, uint64_t n,
+                              const nb_cns_options* opt, int shard_count, int shard_index,
+                              nb_cns_record** out_recs, uint64_t* n_recs,
+                              char** out_seq, uint64_t* out_seq_bytes);
+
 typedef struct {
     uint64_t n_templates, n_extensions, n_block_aligns, n_dp_columns, n_dp_word_updates;
     uint64_t n_accepted, n_tags, n_cns_records, cns_bases;

@@ -53,6 +53,7 @@ EXPORTS = ["nb_ctx_create", "nb_ctx_destroy", "nb_last_error", "nb_version", "nb
            "nb_volume_upload", "nb_volume_free", "nb_index_build", "nb_index_free", "nb_index_stats",
            "nb_index_download", "nb_map_options_default", "nb_map_volume", "nb_pack_candidate", "nb_free",
            "nb_get_map_counters", "nb_cns_options_default", "nb_extend_candidates", "nb_consensus_job",
+           "nb_consensus_job_sharded",
            "nb_get_cns_counters"]
 
 _lib = None
@@ -144,6 +145,23 @@ class Context:
             arr = np.zeros(0, CANDIDATE)
         self.L.nb_free(out)
         return arr
+
+    def consensus_job(self, dreads, recs, opt, shard_count=1, shard_index=0):
+        """recs: (n, 7) uint32 partition records.  Returns (CNS_RECORD array, bytes of all sequences)."""
+        recs = np.ascontiguousarray(recs, np.uint32)
+        out = C.c_void_p(); n = C.c_uint64(); seq = C.c_void_p(); nb = C.c_uint64()
+        self._check(self.L.nb_consensus_job_sharded(self.h, dreads, recs.ctypes.data_as(C.c_void_p),
+                                                    C.c_uint64(recs.shape[0]), C.byref(opt), C.c_int(shard_count),
+                                                    C.c_int(shard_index), C.byref(out), C.byref(n), C.byref(seq),
+                                                    C.byref(nb)))
+        if n.value:
+            r = np.frombuffer((C.c_char * (CNS_RECORD.itemsize * n.value)).from_address(out.value), CNS_RECORD).copy()
+        else:
+            r = np.zeros(0, CNS_RECORD)
+        s = C.string_at(seq.value, nb.value) if nb.value else b""
+        self.L.nb_free(out)
+        self.L.nb_free(seq)
+        return r, s
 
     def timings(self):
         t = Timings()

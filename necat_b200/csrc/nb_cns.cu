@@ -215,10 +215,23 @@ void push_raw(std::vector<nb_cns_record>& recs, std::vector<char>& seqs, const n
 
 }  // namespace
 
+extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, const nb_packed_candidate* cans_in, uint64_t n_in,
+                                        const nb_cns_options* opt, int shard_count, int shard_index,
+                                        nb_cns_record** out_recs, uint64_t* n_recs, char** out_seq, uint64_t* out_seq_bytes);
+
 extern "C" int nb_consensus_job(nb_ctx* ctx, const nb_volume* reads, const nb_packed_candidate* cans_in, uint64_t n_in,
                                 const nb_cns_options* opt, nb_cns_record** out_recs, uint64_t* n_recs, char** out_seq,
                                 uint64_t* out_seq_bytes)
 {
+    return nb_consensus_job_sharded(ctx, reads, cans_in, n_in, opt, 1, 0, out_recs, n_recs, out_seq, out_seq_bytes);
+}
+
+extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, const nb_packed_candidate* cans_in, uint64_t n_in,
+                                        const nb_cns_options* opt, int shard_count, int shard_index,
+                                        nb_cns_record** out_recs, uint64_t* n_recs, char** out_seq, uint64_t* out_seq_bytes)
+{
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count)
+        return nb_fail(ctx, NB_EINVAL, "nb_consensus_job_sharded: bad shard %d of %d", shard_index, shard_count);
     if (!ctx || !reads || (!cans_in && n_in) || !opt || !out_recs || !n_recs || !out_seq || !out_seq_bytes)
         return nb_fail(ctx, NB_EINVAL, "nb_consensus_job: bad arguments");
     *out_recs = NULL; *n_recs = 0; *out_seq = NULL; *out_seq_bytes = 0;
@@ -264,7 +277,7 @@ extern "C" int nb_consensus_job(nb_ctx* ctx, const nb_volume* reads, const nb_pa
         while (i < pc.size()) {
             size_t j = i + 1;
             while (j < pc.size() && pc[j].item[1] == pc[i].item[1]) ++j;
-            if ((size_t)o.min_cov <= j - i) {                       // consensus_one_read.c:218
+            if ((size_t)o.min_cov <= j - i && (int)(pc[i].item[1] % (uint32_t)shard_count) == shard_index) {   // consensus_one_read.c:218
                 one.assign(pc.begin() + i, pc.begin() + j);
                 std::sort(one.begin(), one.end(), [](const nb_packed_candidate& a, const nb_packed_candidate& b) {
                     // PackedGappedCandidate_CnsScoreGT, gapped_candidate.c:96-126
@@ -518,7 +531,7 @@ extern "C" int nb_consensus_job(nb_ctx* ctx, const nb_volume* reads, const nb_pa
 
     // ---- reads of [min_id, max_id) that were never corrected go to raw_out whole (consensus_one_partition.c:173-194)
     for (int id = min_id; id < max_id; ++id) {
-        if (corrected[(size_t)id]) continue;
+        if (corrected[(size_t)id] || id % shard_count != shard_index) continue;
         const int L = (int)reads->h_len[id];
         push_raw(recs, seqs, reads, id, 0, L, L, 0, 0, 0.0);
     }
