@@ -203,9 +203,12 @@ def main():
 
     def one_step(dvol):
         """index -> candidates -> exchange -> regroup -> correct.  Returns corrected bases of this rank."""
+        w0 = time.perf_counter()
         idx = ctx.build_index(dvol, PM_OPTS["kmer_size"], PM_OPTS["kmer_cnt_cutoff"])
         t = ctx.timings(); stats["index_ms"] = t.index_ms
+        w1 = time.perf_counter()
         cands = ctx.map_volume(idx, dvol, 0, dvol, 0, lo, hi, popt)
+        w2 = time.perf_counter()
         t = ctx.timings(); stats["map_ms"] = t.map_ms; stats["map_probe_ms"] = t.map_probe_ms
         mc = ctx.map_counters()
         stats["map_counters"] = {k: int(getattr(mc, k)) for k, _ in mc._fields_}
@@ -225,7 +228,11 @@ def main():
         stats["n_candidates"] = int(packed.shape[0])
         # oc2pcan: every record under its subject and (swapped) under its query; one partition (< 100000 reads)
         part = np.concatenate([packed, formats.swap_roles(packed)])
+        w3 = time.perf_counter()
         recs, seq = ctx.consensus_job(dvol, part, copt, world, rank)
+        w4 = time.perf_counter()
+        stats["wall_ms"] = {"index_call": (w1 - w0) * 1e3, "map_call": (w2 - w1) * 1e3, "exchange_regroup": (w3 - w2) * 1e3,
+                            "consensus_call": (w4 - w3) * 1e3}
         t = ctx.timings(); stats["extend_ms"] = t.extend_ms; stats["consensus_ms"] = t.consensus_ms
         cc = ctx.cns_counters()
         stats["cns_counters"] = {k: int(getattr(cc, k)) for k, _ in cc._fields_}
@@ -291,6 +298,7 @@ def main():
         "overlaps_per_sec": stats["n_candidates"] / sec,
         "corrected_bases": bases, "candidates": stats["n_candidates"],
         "stage_ms": {k: stats[k] for k in ("index_ms", "map_ms", "map_probe_ms", "extend_ms", "consensus_ms")},
+        "wall_ms": stats.get("wall_ms"),
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": {"value": bases_e2e / sec_e2e, "unit": "bases/s", "ms_per_step": sec_e2e * 1e3,

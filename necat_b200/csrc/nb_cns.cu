@@ -18,7 +18,14 @@
 
 #include "nb_cns_kernel.cuh"
 
+#include <chrono>
+
 namespace {
+
+struct HostTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double lap() { auto t1 = std::chrono::steady_clock::now(); double d = std::chrono::duration<double, std::milli>(t1 - t0).count(); t0 = t1; return d; }
+};
 
 struct Can {
     int qid, qdir, qoff, soff, sbeg, send, qsize, score, qbeg;
@@ -187,30 +194,70 @@ void replay(Tpl& t, std::vector<Can>& cans, const std::vector<nb_alignment>& res
     }
 }
 
-struct DevBuf {
-    std::vector<void*> ptrs;
-    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
-    template <typename T> int get(nb_ctx* ctx, T** p, uint64_t n)
+inline int host_base(const nb_volume* v, uint64_t p) { return (v->h_pac[p >> 2] >> (((~p) & 3) << 1)) & 3; }
+
+// Output sequences are written in bulk: records are planned first (offsets into one growing
+// buffer), then the bytes are filled by several host threads.
+struct Fill {
+    uint64_t dst;       // offset in the output buffer
+    uint32_t len;
+    uint32_t kind;      // 0 = copy from the chunk's ASCII consensus buffer at src, 1 = decode read bases from volume position src
+    uint64_t src;
+};
+
+struct SeqOut {
+    char*    buf = NULL;
+    uint64_t cap = 0, used = 0;
+    bool reserve(uint64_t need)
     {
-        NB_CUDA(ctx, cudaMalloc(p, sizeof(T) * (n ? n : 1)));
-        ptrs.push_back(*p);
-        return NB_OK;
+        if (need <= cap) return true;
+        uint64_t nc = cap ? cap : (1u << 20);
+        while (nc < need) nc += nc / 2 + (1u << 20);
+        char* nb = (char*)realloc(buf, nc);
+        if (!nb) return false;
+        buf = nb; cap = nc;
+        return true;
     }
 };
 
-inline int host_base(const nb_volume* v, uint64_t p) { return (v->h_pac[p >> 2] >> (((~p) & 3) << 1)) & 3; }
-
-struct OutRec { nb_cns_record r; std::vector<char> seq; };
-
-void push_raw(std::vector<nb_cns_record>& recs, std::vector<char>& seqs, const nb_volume* v, int id, int left, int right,
-              int org, int ncan, int novl, double cutoff)
+void run_fills(const std::vector<Fill>& fills, char* out, const char* ascii, const nb_volume* v, unsigned nthreads)
 {
-    nb_cns_record r;
-    r.id = id; r.left = left; r.right = right; r.org_size = org; r.num_can = ncan; r.num_ovlps = novl;
-    r.ident_cutoff = cutoff; r.seq_offset = seqs.size(); r.seq_len = right - left; r.is_raw = 1;
-    const uint64_t off = v->h_off[id];
-    for (int i = left; i < right; ++i) seqs.push_back("ACGT"[host_base(v, off + (uint64_t)i)]);
-    recs.push_back(r);
+    if (fills.empty()) return;
+    auto work = [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) {
+            const Fill& f = fills[i];
+            char* d = out + f.dst;
+            if (f.kind == 0) memcpy(d, ascii + f.src, f.len);
+            else {
+                uint64_t p = f.src;
+                for (uint32_t k = 0; k < f.len; ++k, ++p) d[k] = "ACGT"[(v->h_pac[p >> 2] >> (((~p) & 3) << 1)) & 3];
+            }
+        }
+    };
+    uint64_t total = 0;
+    for (const Fill& f : fills) total += f.len;
+    std::vector<std::thread> th;
+    const uint64_t per = total / nthreads + 1;
+    size_t a = 0;
+    while (a < fills.size()) {
+        uint64_t acc = 0;
+        size_t b = a;
+        while (b < fills.size() && acc < per) acc += fills[b++].len;
+        th.emplace_back(work, a, b);
+        a = b;
+    }
+    for (auto& t : th) t.join();
+}
+
+// codes (0..3) of the consensus stretches -> ASCII, gathered densely: one CTA per stretch
+__global__ void k_gather_ascii(const uint8_t* __restrict__ pool, const uint64_t* __restrict__ src, const uint64_t* __restrict__ dst,
+                               const uint32_t* __restrict__ len, uint32_t n, char* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint8_t* s = pool + src[i];
+        char* d = out + dst[i];
+        for (uint32_t k = threadIdx.x; k < len[i]; k += blockDim.x) d[k] = "ACGT"[s[k] & 3];
+    }
 }
 
 }  // namespace
@@ -242,8 +289,12 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     memset(&ctx->cc, 0, sizeof ctx->cc);
     ctx->tm.extend_ms = 0; ctx->tm.consensus_ms = 0;
     const nb_cns_options o = *opt;
+    const bool trace = getenv("NB_TRACE") != NULL;
+    HostTimer ht;
+    double t_setup = 0, t_replay = 0, t_gather = 0, t_ext = 0, t_prep = 0, t_kern = 0, t_rec = 0, t_tail = 0;
     std::vector<nb_cns_record> recs;
-    std::vector<char> seqs;
+    SeqOut so;
+    std::vector<Fill> fills;
     if (n_in == 0) return NB_OK;
 
     // ---- load order + normalisation (consensus_one_partition.c:10-95)
@@ -311,16 +362,17 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
         }
     }
     ctx->cc.n_templates = tpls.size();
+    t_setup += ht.lap();
 
     // ---- chunks of templates: bounded device memory
     const size_t kChunk = 8192;
     unsigned nthreads = std::thread::hardware_concurrency();
     if (nthreads == 0) nthreads = 4;
-    if (nthreads > 32) nthreads = 32;
+    if (nthreads > 64) nthreads = 64;
     float ext_ms = 0, cns_ms = 0;
     for (size_t c0 = 0; c0 < tpls.size(); c0 += kChunk) {
         const size_t c1 = std::min(tpls.size(), c0 + kChunk);
-        DevBuf D;                                   // everything allocated for this chunk
+        NbDevBuf D(ctx);                            // everything allocated for this chunk
         std::vector<nb_alignment> res;              // results of all rounds of this chunk
         std::vector<const uint8_t*> res_ops;        // device pointer of each result's ops
         for (size_t t = c0; t < c1; ++t) tpls[t].cov.assign((size_t)tpls[t].T + 1, 0);
@@ -344,6 +396,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
                 }
                 for (auto& x : th) x.join();
             }
+            t_replay += ht.lap();
             // gather requests
             std::vector<ExtTask> tasks;
             std::vector<size_t> task_can;
@@ -366,13 +419,14 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
                     task_can.push_back(T.first + k);
                 }
             }
+            t_gather += ht.lap();
             if (tasks.empty()) break;
             if (tasks.size() >= (1ull << 31)) return nb_fail(ctx, NB_ELIMIT, "too many extension tasks in one round");
             ExtTask* d_tasks; nb_alignment* d_res; uint8_t* d_ops;
             int rc;
-            if ((rc = D.get(ctx, &d_tasks, tasks.size()))) return rc;
-            if ((rc = D.get(ctx, &d_res, tasks.size()))) return rc;
-            if ((rc = D.get(ctx, &d_ops, pool + 64))) return rc;
+            if ((rc = D.get(&d_tasks, tasks.size()))) return rc;
+            if ((rc = D.get(&d_res, tasks.size()))) return rc;
+            if ((rc = D.get(&d_ops, pool + 64))) return rc;
             NB_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ExtTask) * tasks.size(), cudaMemcpyHostToDevice, st));
             cudaEventRecord(ctx->ev0, st);
             rc = nb_run_extension(ctx, reads, d_tasks, (uint32_t)tasks.size(), d_res, d_ops, o.error, o.min_align_size, 4 /* ONC_TAIL_MATCH_LEN_LONG */);
@@ -390,6 +444,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
                 cans[task_can[k]].res = (int)(r0 + k);
                 res_ops[r0 + k] = d_ops + res[r0 + k].ops_offset;
             }
+            t_ext += ht.lap();
             if (round > 64) return nb_fail(ctx, NB_ECUDA, "extension rounds do not converge");
         }
 
@@ -422,27 +477,31 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
         }
         std::vector<CnsSegment> segs(seg_total);
         std::vector<uint32_t> nseg(dt.size(), 0);
-        std::vector<uint8_t> seq_codes;
+        std::vector<char> ascii;            // consensus stretches of this chunk, dense
+        std::vector<uint64_t> seg_dense(seg_total, 0);
+        uint8_t* d_seq_pool = NULL;
         if (!dt.empty()) {
             int rc;
-            const unsigned grid = NB_SMS * 4;           // 16 warps per SM
+            const unsigned grid = NB_SMS * 5;           // 5 CTAs x 2 warps per SM (shared memory bound)
             const size_t slots = (size_t)grid * CNS_WARPS;
             const uint32_t cap_steps = maxT * 4 + 4096;
             CnsParams P;
             memset(&P, 0, sizeof P);
             CnsTemplate* d_tpl; CnsAln* d_aln;
-            if ((rc = D.get(ctx, &d_tpl, dt.size()))) return rc;
-            if ((rc = D.get(ctx, &d_aln, alns.size()))) return rc;
-            if ((rc = D.get(ctx, &P.seg, seg_total))) return rc;
-            if ((rc = D.get(ctx, &P.tpl_nseg, dt.size()))) return rc;
-            if ((rc = D.get(ctx, &P.seq_pool, out_pool))) return rc;
-            if ((rc = D.get(ctx, &P.next_tpl, 1))) return rc;
-            if ((rc = D.get(ctx, &P.cov, slots * (maxT + 2)))) return rc;
-            if ((rc = D.get(ctx, &P.pos_first, slots * (maxT + 2)))) return rc;
-            if ((rc = D.get(ctx, &P.bp, slots * (size_t)cap_steps))) return rc;
-            if ((rc = D.get(ctx, &P.rev, slots * (size_t)cap_steps))) return rc;
-            if ((rc = D.get(ctx, &P.error_flag, 1))) return rc;
-            if ((rc = D.get(ctx, &P.counters, 4))) return rc;
+            if ((rc = D.get(&d_tpl, dt.size()))) return rc;
+            if ((rc = D.get(&d_aln, alns.size()))) return rc;
+            if ((rc = D.get(&P.seg, seg_total))) return rc;
+            if ((rc = D.get(&P.tpl_nseg, dt.size()))) return rc;
+            if ((rc = D.get(&P.seq_pool, out_pool))) return rc;
+            d_seq_pool = P.seq_pool;
+            if ((rc = D.get(&P.next_tpl, 1))) return rc;
+            if ((rc = D.get(&P.cov, slots * (maxT + 2)))) return rc;
+            if ((rc = D.get(&P.pos_first, slots * (maxT + 2)))) return rc;
+            if ((rc = D.get(&P.flag, slots * (maxT + 2)))) return rc;
+            if ((rc = D.get(&P.bp, slots * (size_t)cap_steps))) return rc;
+            if ((rc = D.get(&P.rev, slots * (size_t)cap_steps))) return rc;
+            if ((rc = D.get(&P.error_flag, 1))) return rc;
+            if ((rc = D.get(&P.counters, 4))) return rc;
             NB_CUDA(ctx, cudaMemcpyAsync(d_tpl, dt.data(), sizeof(CnsTemplate) * dt.size(), cudaMemcpyHostToDevice, st));
             NB_CUDA(ctx, cudaMemcpyAsync(d_aln, alns.data(), sizeof(CnsAln) * alns.size(), cudaMemcpyHostToDevice, st));
             NB_CUDA(ctx, cudaMemsetAsync(P.next_tpl, 0, sizeof(uint32_t), st));
@@ -452,6 +511,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
             P.maxT = maxT; P.cap_steps = cap_steps; P.min_cov = o.min_cov; P.min_size = o.min_size;
             const size_t smem = sizeof(CnsWarpShared) * CNS_WARPS;
             if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            t_prep += ht.lap();
             cudaEventRecord(ctx->ev2, st);
             k_consensus<<<grid, CNS_WARPS * 32, smem, st>>>(P);
             NB_LAUNCH_CHECK(ctx);
@@ -461,26 +521,66 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
             NB_CUDA(ctx, cudaMemcpyAsync(cnt, P.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
             NB_CUDA(ctx, cudaMemcpyAsync(segs.data(), P.seg, sizeof(CnsSegment) * seg_total, cudaMemcpyDeviceToHost, st));
             NB_CUDA(ctx, cudaMemcpyAsync(nseg.data(), P.tpl_nseg, sizeof(uint32_t) * dt.size(), cudaMemcpyDeviceToHost, st));
-            seq_codes.resize(out_pool);
-            NB_CUDA(ctx, cudaMemcpyAsync(seq_codes.data(), P.seq_pool, out_pool, cudaMemcpyDeviceToHost, st));
             NB_CUDA(ctx, cudaStreamSynchronize(st));
             float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); cns_ms += ms;
-            ctx->tm.d2h_bytes += out_pool + sizeof(CnsSegment) * seg_total;
+            ctx->tm.d2h_bytes += sizeof(CnsSegment) * seg_total;
             ctx->cc.n_tags += cnt[1];
             if (eflag) return nb_fail(ctx, NB_ELIMIT, "consensus kernel capacity exceeded (flags %u)", eflag);
+            {
+                // gather the stretches densely as ASCII, one exact-size D2H copy
+                std::vector<uint64_t> gsrc, gdst; std::vector<uint32_t> glen;
+                uint64_t dense = 0;
+                for (size_t x = 0; x < dt.size(); ++x)
+                    for (uint32_t k = 0; k < nseg[x]; ++k) {
+                        const CnsSegment& g = segs[dt[x].seg_first + k];
+                        gsrc.push_back(g.seq_off); gdst.push_back(dense); glen.push_back(g.len);
+                        seg_dense[dt[x].seg_first + k] = dense;
+                        dense += g.len;
+                    }
+                ascii.resize(dense);
+                if (!gsrc.empty()) {
+                    uint64_t *d_src, *d_dst; uint32_t* d_len; char* d_out;
+                    if ((rc = D.get(&d_src, gsrc.size()))) return rc;
+                    if ((rc = D.get(&d_dst, gsrc.size()))) return rc;
+                    if ((rc = D.get(&d_len, gsrc.size()))) return rc;
+                    if ((rc = D.get(&d_out, dense))) return rc;
+                    NB_CUDA(ctx, cudaMemcpyAsync(d_src, gsrc.data(), 8 * gsrc.size(), cudaMemcpyHostToDevice, st));
+                    NB_CUDA(ctx, cudaMemcpyAsync(d_dst, gdst.data(), 8 * gsrc.size(), cudaMemcpyHostToDevice, st));
+                    NB_CUDA(ctx, cudaMemcpyAsync(d_len, glen.data(), 4 * gsrc.size(), cudaMemcpyHostToDevice, st));
+                    k_gather_ascii<<<NB_SMS * 8, 256, 0, st>>>(d_seq_pool, d_src, d_dst, d_len, (uint32_t)gsrc.size(), d_out);
+                    NB_LAUNCH_CHECK(ctx);
+                    NB_CUDA(ctx, cudaMemcpyAsync(ascii.data(), d_out, dense, cudaMemcpyDeviceToHost, st));
+                    NB_CUDA(ctx, cudaStreamSynchronize(st));
+                    ctx->tm.d2h_bytes += dense;
+                }
+            }
+            t_kern += ht.lap();
         }
-        // ---- records (tasc/cbcns.c:108-264, consensus_one_read.c:20-136)
+        // ---- records (tasc/cbcns.c:108-264, consensus_one_read.c:20-136): plan, then fill in parallel
+        fills.clear();
+        auto plan = [&](int id, int left, int right, int org, int ncan, int novl, double cutoff, int is_raw, uint32_t len) {
+            nb_cns_record r;
+            r.id = id; r.left = left; r.right = right; r.org_size = org; r.num_can = ncan; r.num_ovlps = novl;
+            r.ident_cutoff = cutoff; r.seq_offset = so.used; r.seq_len = (int)len; r.is_raw = is_raw;
+            recs.push_back(r);
+        };
+        auto add_raw = [&](int id, int from, int to) {      // read bases [from, to)
+            Fill f; f.dst = so.used; f.len = (uint32_t)(to - from); f.kind = 1; f.src = reads->h_off[id] + (uint64_t)from;
+            fills.push_back(f); so.used += f.len;
+        };
+        auto add_cns = [&](const CnsSegment& g, uint64_t dense_off) {
+            Fill f; f.dst = so.used; f.len = g.len; f.kind = 0; f.src = dense_off;
+            fills.push_back(f); so.used += f.len;
+        };
         for (size_t x = 0; x < dt.size(); ++x) {
             Tpl& T = tpls[dt_tpl[x]];
             const CnsSegment* sg = segs.data() + dt[x].seg_first;
+            const uint64_t* sd = seg_dense.data() + dt[x].seg_first;
             const uint32_t ns = nseg[x];
             if (!o.full_consensus) {
                 for (uint32_t k = 0; k < ns; ++k) {
-                    nb_cns_record r;
-                    r.id = T.tid; r.left = sg[k].left; r.right = sg[k].right; r.org_size = T.T; r.num_can = T.num_can;
-                    r.num_ovlps = T.num_ovlps; r.ident_cutoff = T.cutoff; r.seq_offset = seqs.size(); r.seq_len = (int)sg[k].len; r.is_raw = 0;
-                    for (uint32_t b = 0; b < sg[k].len; ++b) seqs.push_back("ACGT"[seq_codes[sg[k].seq_off + b]]);
-                    recs.push_back(r);
+                    plan(T.tid, sg[k].left, sg[k].right, T.T, T.num_can, T.num_ovlps, T.cutoff, 0, sg[k].len);
+                    add_cns(sg[k], sd[k]);
                     ctx->cc.cns_bases += sg[k].len;
                 }
                 // raw stretches between the corrected runs (get_raw_intvs, consensus_one_read.c:20-65)
@@ -495,53 +595,71 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
                         else { left = fe + 1; continue; }
                     }
                     const int right = fs - 1;
-                    if (right - left + 1 >= 1000) push_raw(recs, seqs, reads, T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff);
+                    if (right - left + 1 >= 1000) {
+                        plan(T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff, 1, (uint32_t)(right + 1 - left));
+                        add_raw(T.tid, left, right + 1);
+                    }
                     if (fe >= end_off) { open = false; break; }
                     left = fe + 1;
                 }
                 if (open) {
                     const int right = end_off;
-                    if (right - left + 1 >= 1000) push_raw(recs, seqs, reads, T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff);
+                    if (right - left + 1 >= 1000) {
+                        plan(T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff, 1, (uint32_t)(right + 1 - left));
+                        add_raw(T.tid, left, right + 1);
+                    }
                 }
                 corrected[(size_t)T.tid] = 1;                       // consensus_one_read.c:391 (r stays 1)
             } else if (ns) {
                 // consensus_unbroken (cbcns.c:218-257): corrected runs spliced into the raw read
-                nb_cns_record r;
-                r.id = T.tid; r.left = 0; r.right = T.T; r.org_size = T.T; r.num_can = T.num_can; r.num_ovlps = T.num_ovlps;
-                r.ident_cutoff = T.cutoff; r.seq_offset = seqs.size(); r.is_raw = 0;
-                const uint64_t off = reads->h_off[T.tid];
+                const uint64_t start = so.used;
+                const size_t ri = recs.size();
+                plan(T.tid, 0, T.T, T.T, T.num_can, T.num_ovlps, T.cutoff, 0, 0);
                 int last_raw = 0;
                 for (uint32_t k = 0; k < ns; ++k) {
                     const int rf = sg[k].cns_from, rt = sg[k].cns_to;
-                    for (int i = last_raw; i < rf; ++i) seqs.push_back("ACGT"[host_base(reads, off + (uint64_t)i)]);
-                    for (uint32_t b = 0; b < sg[k].len; ++b) seqs.push_back("ACGT"[seq_codes[sg[k].seq_off + b]]);
+                    if (rf > last_raw) add_raw(T.tid, last_raw, rf);
+                    add_cns(sg[k], sd[k]);
                     last_raw = rt;
                 }
-                for (int i = last_raw; i < T.T; ++i) seqs.push_back("ACGT"[host_base(reads, off + (uint64_t)i)]);
-                r.seq_len = (int)(seqs.size() - r.seq_offset);
-                recs.push_back(r);
-                ctx->cc.cns_bases += (uint64_t)r.seq_len;
+                if (last_raw < T.T) add_raw(T.tid, last_raw, T.T);
+                recs[ri].seq_len = (int)(so.used - start);
+                ctx->cc.cns_bases += so.used - start;
                 corrected[(size_t)T.tid] = 1;
             }
-            T.cov.clear(); T.cov.shrink_to_fit();
+            std::vector<uint16_t>().swap(T.cov);
         }
+        if (!so.reserve(so.used)) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+        run_fills(fills, so.buf, ascii.data(), reads, nthreads);
+        t_rec += ht.lap();
     }
     ctx->tm.extend_ms = ext_ms;
     ctx->tm.consensus_ms = cns_ms;
 
     // ---- reads of [min_id, max_id) that were never corrected go to raw_out whole (consensus_one_partition.c:173-194)
+    fills.clear();
     for (int id = min_id; id < max_id; ++id) {
         if (corrected[(size_t)id] || id % shard_count != shard_index) continue;
         const int L = (int)reads->h_len[id];
-        push_raw(recs, seqs, reads, id, 0, L, L, 0, 0, 0.0);
+        nb_cns_record r;
+        r.id = id; r.left = 0; r.right = L; r.org_size = L; r.num_can = 0; r.num_ovlps = 0; r.ident_cutoff = 0.0;
+        r.seq_offset = so.used; r.seq_len = L; r.is_raw = 1;
+        recs.push_back(r);
+        Fill f; f.dst = so.used; f.len = (uint32_t)L; f.kind = 1; f.src = reads->h_off[id];
+        fills.push_back(f); so.used += f.len;
     }
+    if (!so.reserve(so.used ? so.used : 1)) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    run_fills(fills, so.buf, NULL, reads, nthreads);
     ctx->cc.n_cns_records = recs.size();
 
     nb_cns_record* r_out = (nb_cns_record*)malloc(sizeof(nb_cns_record) * (recs.size() ? recs.size() : 1));
-    char* s_out = (char*)malloc(seqs.size() ? seqs.size() : 1);
+    char* s_out = so.buf;
     if (!r_out || !s_out) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
     if (!recs.empty()) memcpy(r_out, recs.data(), sizeof(nb_cns_record) * recs.size());
-    if (!seqs.empty()) memcpy(s_out, seqs.data(), seqs.size());
-    *out_recs = r_out; *n_recs = recs.size(); *out_seq = s_out; *out_seq_bytes = seqs.size();
+    t_tail += ht.lap();
+    if (trace)
+        fprintf(stderr, "[nb_consensus_job] host ms: setup %.1f replay %.1f gather %.1f ext(call) %.1f cns_prep %.1f cns(call) %.1f records %.1f tail %.1f | gpu ms: extend %.1f consensus %.1f\n",
+                t_setup, t_replay, t_gather, t_ext, t_prep, t_kern, t_rec, t_tail, ext_ms, cns_ms);
+    *out_recs = r_out; *n_recs = recs.size(); *out_seq = s_out; *out_seq_bytes = so.used;
     return NB_OK;
 }

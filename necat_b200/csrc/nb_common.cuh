@@ -22,6 +22,7 @@ struct nb_ctx {
     cudaEvent_t  ev0, ev1, ev2, ev3;
     void*        ext_mat;        // walk-back scratch of the extension kernel (kept across calls)
     size_t       ext_mat_slots;
+    void*        dev_cache;      // NbDevCache*: device blocks kept for reuse (cudaMalloc/cudaFree are slow and synchronising)
 };
 
 struct nb_volume {
@@ -47,6 +48,30 @@ struct nb_index {
 };
 
 extern char g_nb_err[512];
+
+// caching device allocator (per context, single stream): blocks return to the cache on release
+int  nb_dev_alloc(nb_ctx* ctx, void** p, size_t bytes);
+void nb_dev_release(nb_ctx* ctx, void* p);
+void nb_dev_cache_destroy(nb_ctx* ctx);
+
+#ifdef __cplusplus
+#include <vector>
+struct NbDevBuf {          // RAII list of cached device blocks
+    nb_ctx* ctx;
+    std::vector<void*> ptrs;
+    explicit NbDevBuf(nb_ctx* c) : ctx(c) {}
+    ~NbDevBuf() { for (void* q : ptrs) nb_dev_release(ctx, q); }
+    template <typename T> int get(T** p, uint64_t n)
+    {
+        void* q = NULL;
+        int rc = nb_dev_alloc(ctx, &q, sizeof(T) * (size_t)(n ? n : 1));
+        if (rc) return rc;
+        *p = (T*)q;
+        ptrs.push_back(q);
+        return NB_OK;
+    }
+};
+#endif
 
 int nb_fail(nb_ctx* ctx, int code, const char* fmt, ...);
 

@@ -5,6 +5,56 @@
 
 char g_nb_err[512] = "";
 
+struct NbDevBlock { void* p; size_t bytes; bool used; };
+struct NbDevCache { std::vector<NbDevBlock> blocks; };
+
+int nb_dev_alloc(nb_ctx* ctx, void** p, size_t bytes)
+{
+    if (!ctx->dev_cache) ctx->dev_cache = new NbDevCache();
+    NbDevCache* C = (NbDevCache*)ctx->dev_cache;
+    bytes = (bytes + 511) & ~(size_t)511;
+    int best = -1;
+    for (size_t i = 0; i < C->blocks.size(); ++i) {
+        const NbDevBlock& b = C->blocks[i];
+        if (b.used || b.bytes < bytes || b.bytes > bytes * 2 + (8u << 20)) continue;
+        if (best < 0 || b.bytes < C->blocks[(size_t)best].bytes) best = (int)i;
+    }
+    if (best >= 0) { C->blocks[(size_t)best].used = true; *p = C->blocks[(size_t)best].p; return NB_OK; }
+    void* q = NULL;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        // give the cached, unused blocks back and retry once
+        for (size_t i = 0; i < C->blocks.size();) {
+            if (!C->blocks[i].used) { cudaFree(C->blocks[i].p); C->blocks.erase(C->blocks.begin() + (long)i); }
+            else ++i;
+        }
+        e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) return nb_fail(ctx, NB_ENOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    NbDevBlock b; b.p = q; b.bytes = bytes; b.used = true;
+    C->blocks.push_back(b);
+    *p = q;
+    return NB_OK;
+}
+
+void nb_dev_release(nb_ctx* ctx, void* p)
+{
+    if (!p || !ctx || !ctx->dev_cache) return;
+    NbDevCache* C = (NbDevCache*)ctx->dev_cache;
+    for (auto& b : C->blocks) if (b.p == p) { b.used = false; return; }
+    cudaFree(p);
+}
+
+void nb_dev_cache_destroy(nb_ctx* ctx)
+{
+    if (!ctx || !ctx->dev_cache) return;
+    NbDevCache* C = (NbDevCache*)ctx->dev_cache;
+    for (auto& b : C->blocks) cudaFree(b.p);
+    delete C;
+    ctx->dev_cache = NULL;
+}
+
 int nb_fail(nb_ctx* ctx, int code, const char* fmt, ...)
 {
     va_list ap;
@@ -58,6 +108,7 @@ extern "C" void nb_ctx_destroy(nb_ctx* c)
     cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->stream);
     if (c->ext_mat) cudaFree(c->ext_mat);
+    nb_dev_cache_destroy(c);
     free(c);
 }
 

@@ -34,12 +34,13 @@ __device__ __forceinline__ int seq_base(const SeqView& v, int idx)
 
 struct WarpScratch {
     uint8_t q[EXT_MAX_BLK];
-    uint8_t t[EXT_MAX_BLK];
+    uint8_t t[EXT_MAX_BLK + 64];        // padded: the forward pass reads one column ahead
     uint8_t rev[2 * EXT_MAX_BLK];
+    uint32_t peq[4][32];                // match masks: peq[symbol][lane] covers query rows [32 lane, 32 lane + 32)
 };
 
 // Forward pass over one block.  Returns best prefix distance and its column.
-__device__ __forceinline__ void myers_forward(const WarpScratch& S, int qblk, int tblk, uint2* __restrict__ mat, int lane,
+__device__ __forceinline__ void myers_forward(WarpScratch& S, int qblk, int tblk, uint2* __restrict__ mat, int lane,
                                               int* best_out, int* bestj_out)
 {
     const int nw = (qblk + 31) >> 5;
@@ -56,18 +57,28 @@ __device__ __forceinline__ void myers_forward(const WarpScratch& S, int qblk, in
             }
         }
     }
+    S.peq[0][lane] = pe0; S.peq[1][lane] = pe1; S.peq[2][lane] = pe2; S.peq[3][lane] = pe3;
+    __syncwarp();
     uint32_t Pv = 0xffffffffu, Mv = 0;
     int hout = 0;
     const int lw = (qblk - 1) >> 5, lb = (qblk - 1) & 31;
     int score = qblk, best = 0x7fffffff, bestj = -1;
     const int nsteps = tblk + nw - 1;
-    for (int s = 0; s < nsteps; ++s) {
+    const bool mine = lane < nw;
+    uint2* mp = mat + lane;                                 // skewed [step][lane] layout, advanced by nw per step
+    // match mask of the column this lane handles at step 0, fetched one step ahead of its use
+    int colp = -lane;
+    uint32_t Eq_next = S.peq[S.t[colp >= 0 ? colp : 0] & 3][lane];
+    for (int s = 0; s < nsteps; ++s, mp += nw) {
         int hin = __shfl_up_sync(0xffffffffu, hout, 1);
         if (lane == 0) hin = 1;
         const int col = s - lane;
-        if (lane < nw && col >= 0 && col < tblk) {
-            const int c = S.t[col];
-            uint32_t Eq = c == 0 ? pe0 : (c == 1 ? pe1 : (c == 2 ? pe2 : pe3));
+        uint32_t Eq = Eq_next;
+        {
+            const int cn = col + 1;                          // next step's column (padding of S.t makes the read safe)
+            Eq_next = S.peq[S.t[cn >= 0 ? cn : 0] & 3][lane];
+        }
+        if (mine && (unsigned)col < (unsigned)tblk) {
             const uint32_t neg = hin < 0, pos = hin > 0;
             const uint32_t Xv = Eq | Mv;
             Eq |= neg;
@@ -82,7 +93,7 @@ __device__ __forceinline__ void myers_forward(const WarpScratch& S, int qblk, in
             const uint32_t Phs = (Ph << 1) | pos, Mhs = (Mh << 1) | neg;
             Pv = Mhs | ~(Xv | Phs);
             Mv = Phs & Xv;
-            mat[(size_t)s * nw + lane] = make_uint2(Pv, Ph);
+            *mp = make_uint2(Pv, Ph);
         }
     }
     *best_out = __shfl_sync(0xffffffffu, best, lw);
@@ -214,7 +225,7 @@ __device__ int extend_side(WarpScratch& S, const ExtParams& P, uint2* mat, int l
     return ncol;
 }
 
-__global__ void __launch_bounds__(EXT_WARPS * 32)
+__global__ void __launch_bounds__(EXT_WARPS * 32, 2)
 k_extend(ExtParams P)
 {
     __shared__ WarpScratch s_scratch[EXT_WARPS];
@@ -311,10 +322,10 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* reads, const ExtTask* d_tasks
         ctx->ext_mat_slots = slots;
     }
     uint2* s_mat = (uint2*)ctx->ext_mat;
+    NbDevBuf B(ctx);
     uint32_t* d_next = NULL;
     unsigned long long* d_cnt = NULL;
-    NB_CUDA(ctx, cudaMalloc(&d_next, sizeof(uint32_t)));
-    NB_CUDA(ctx, cudaMalloc(&d_cnt, sizeof(unsigned long long) * 4));
+    { int rc; if ((rc = B.get(&d_next, 1))) return rc; if ((rc = B.get(&d_cnt, 4))) return rc; }
     NB_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(uint32_t), st));
     NB_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 4, st));
     ExtParams P;
@@ -331,8 +342,6 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* reads, const ExtTask* d_tasks
     ctx->cc.n_block_aligns += cnt[0];
     ctx->cc.n_dp_columns += cnt[1];
     ctx->cc.n_dp_word_updates += cnt[2];
-    cudaFree(d_next);
-    cudaFree(d_cnt);
     return NB_OK;
 }
 

@@ -257,13 +257,17 @@ extern "C" int nb_index_build(nb_ctx* ctx, const nb_volume* ref, int k, int q, n
     uint64_t* d_tot = NULL;
     const uint64_t inv_words = ((ref->db_size + 31) >> 5) + 2;
     cudaEventRecord(ctx->ev0, st);
-    NB_CUDA(ctx, cudaMalloc(&d_cnt, sizeof(uint32_t) * (nh + 8)));
-    NB_CUDA(ctx, cudaMalloc(&ix->d_tbl, sizeof(uint32_t) * (nh + 8)));
-    NB_CUDA(ctx, cudaMalloc(&d_invalid, sizeof(uint32_t) * inv_words));
-    NB_CUDA(ctx, cudaMalloc(&d_tile, sizeof(uint32_t) * ntiles));
-    NB_CUDA(ctx, cudaMalloc(&d_tiled, sizeof(uint32_t) * ntiles));
-    NB_CUDA(ctx, cudaMalloc(&d_tot, sizeof(uint64_t) * 2));
-    NB_CUDA(ctx, cudaMalloc(&d_nlong, sizeof(uint32_t)));
+    NbDevBuf B(ctx);
+    {
+        int rc;
+        if ((rc = B.get(&d_cnt, nh + 8))) return rc;
+        if ((rc = nb_dev_alloc(ctx, (void**)&ix->d_tbl, sizeof(uint32_t) * (nh + 8)))) return rc;
+        if ((rc = B.get(&d_invalid, inv_words))) return rc;
+        if ((rc = B.get(&d_tile, ntiles))) return rc;
+        if ((rc = B.get(&d_tiled, ntiles))) return rc;
+        if ((rc = B.get(&d_tot, 2))) return rc;
+        if ((rc = B.get(&d_nlong, 1))) return rc;
+    }
     NB_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * (nh + 8), st));
     NB_CUDA(ctx, cudaMemsetAsync(d_invalid, 0, sizeof(uint32_t) * inv_words, st));
     NB_CUDA(ctx, cudaMemsetAsync(d_nlong, 0, sizeof(uint32_t), st));
@@ -290,8 +294,11 @@ extern "C" int nb_index_build(nb_ctx* ctx, const nb_volume* ref, int k, int q, n
     NB_CUDA(ctx, cudaStreamSynchronize(st));
     ix->n_off = tot[0];
     ix->n_distinct = tot[1];
-    NB_CUDA(ctx, cudaMalloc(&ix->d_off, sizeof(uint32_t) * (ix->n_off + 16)));
-    NB_CUDA(ctx, cudaMalloc(&d_long, sizeof(uint32_t) * (ix->n_off / LONG_RUN + 16)));
+    {
+        int rc;
+        if ((rc = nb_dev_alloc(ctx, (void**)&ix->d_off, sizeof(uint32_t) * (ix->n_off + 16)))) return rc;
+        if ((rc = B.get(&d_long, ix->n_off / LONG_RUN + 16))) return rc;
+    }
     k_scan_kmers<true><<<grid_scan, IDX_THREADS, 0, st>>>(words, ref->db_size, d_invalid, k, d_cnt, ix->d_tbl, ix->d_off);
     NB_LAUNCH_CHECK(ctx);
     unsigned grid_h = (unsigned)((nh + IDX_THREADS - 1) / IDX_THREADS);
@@ -309,8 +316,6 @@ extern "C" int nb_index_build(nb_ctx* ctx, const nb_volume* ref, int k, int q, n
     cudaEventRecord(ctx->ev1, st);
     NB_CUDA(ctx, cudaStreamSynchronize(st));
     cudaEventElapsedTime(&ctx->tm.index_ms, ctx->ev0, ctx->ev1);
-    cudaFree(d_cnt); cudaFree(d_invalid); cudaFree(d_tile); cudaFree(d_tiled); cudaFree(d_tot);
-    cudaFree(d_long); cudaFree(d_nlong);
     *out = ix;
     return NB_OK;
 }
@@ -318,9 +323,8 @@ extern "C" int nb_index_build(nb_ctx* ctx, const nb_volume* ref, int k, int q, n
 extern "C" void nb_index_free(nb_ctx* ctx, nb_index* ix)
 {
     if (!ix) return;
-    if (ctx) cudaSetDevice(ctx->device);
-    cudaFree(ix->d_tbl);
-    cudaFree(ix->d_off);
+    if (ctx) { cudaSetDevice(ctx->device); nb_dev_release(ctx, ix->d_tbl); nb_dev_release(ctx, ix->d_off); }
+    else { cudaFree(ix->d_tbl); cudaFree(ix->d_off); }
     free(ix);
 }
 

@@ -687,24 +687,6 @@ k_candidates(MapDev P)
 
 // ------------------------------------------------------------------- host
 
-template <typename T>
-static int dev_alloc(nb_ctx* ctx, T** p, uint64_t n)
-{
-    NB_CUDA(ctx, cudaMalloc(p, sizeof(T) * (n ? n : 1)));
-    return NB_OK;
-}
-
-struct MapScratch {
-    std::vector<void*> ptrs;
-    ~MapScratch() { for (void* p : ptrs) cudaFree(p); }
-    template <typename T> int get(nb_ctx* ctx, T** p, uint64_t n)
-    {
-        int rc = dev_alloc(ctx, p, n);
-        if (rc == NB_OK) ptrs.push_back(*p);
-        return rc;
-    }
-};
-
 extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, int ref_start_id,
                              const nb_volume* reads, int read_start_id, uint64_t read_lo, uint64_t read_hi,
                              const nb_map_options* opt, nb_candidate** out, uint64_t* n_out)
@@ -740,7 +722,7 @@ extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* 
     const size_t probe_smem = ((size_t)max_len / 4 + 64 + 15) & ~(size_t)15;
     if (probe_smem > 200 * 1024) return nb_fail(ctx, NB_ELIMIT, "read of %u bases does not fit the shared-memory stage", max_len);
 
-    MapScratch S;
+    NbDevBuf S(ctx);
     MapDev P;
     memset(&P, 0, sizeof P);
     P.tbl = idx->d_tbl; P.offs = idx->d_off;
@@ -757,15 +739,15 @@ extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* 
     }
     int rc;
     uint64_t* d_probe_base; uint64_t* d_hit_base; uint64_t* d_scratch_base;
-    if ((rc = S.get(ctx, &d_probe_base, U + 1))) return rc;
-    if ((rc = S.get(ctx, &d_hit_base, U + 1))) return rc;
-    if ((rc = S.get(ctx, &d_scratch_base, U))) return rc;
-    if ((rc = S.get(ctx, &P.unit_hits, U))) return rc;
-    if ((rc = S.get(ctx, &P.unit_nblk, U))) return rc;
-    if ((rc = S.get(ctx, &P.unit_nelig, U))) return rc;
-    if ((rc = S.get(ctx, &P.probe_lo, np))) return rc;
-    if ((rc = S.get(ctx, &P.probe_n, np))) return rc;
-    if ((rc = S.get(ctx, &P.counters, 8))) return rc;
+    if ((rc = S.get(&d_probe_base, U + 1))) return rc;
+    if ((rc = S.get(&d_hit_base, U + 1))) return rc;
+    if ((rc = S.get(&d_scratch_base, U))) return rc;
+    if ((rc = S.get(&P.unit_hits, U))) return rc;
+    if ((rc = S.get(&P.unit_nblk, U))) return rc;
+    if ((rc = S.get(&P.unit_nelig, U))) return rc;
+    if ((rc = S.get(&P.probe_lo, np))) return rc;
+    if ((rc = S.get(&P.probe_n, np))) return rc;
+    if ((rc = S.get(&P.counters, 8))) return rc;
     P.probe_base = d_probe_base; P.hit_base = d_hit_base; P.scratch_base = d_scratch_base;
     NB_CUDA(ctx, cudaMemsetAsync(P.counters, 0, 8 * sizeof(unsigned long long), st));
     NB_CUDA(ctx, cudaMemcpyAsync(d_probe_base, probe_base.data(), sizeof(uint64_t) * (U + 1), cudaMemcpyHostToDevice, st));
@@ -796,20 +778,20 @@ extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* 
     hit_base[U] = H;
     NB_CUDA(ctx, cudaMemcpyAsync(d_hit_base, hit_base.data(), sizeof(uint64_t) * (U + 1), cudaMemcpyHostToDevice, st));
     NB_CUDA(ctx, cudaMemcpyAsync(d_scratch_base, scratch_base.data(), sizeof(uint64_t) * U, cudaMemcpyHostToDevice, st));
-    if ((rc = S.get(ctx, &P.seed_kid, H))) return rc;
-    if ((rc = S.get(ctx, &P.seed_off, H))) return rc;
-    if ((rc = S.get(ctx, &P.blk_id, H))) return rc;
-    if ((rc = S.get(ctx, &P.blk_seg, H))) return rc;
-    if ((rc = S.get(ctx, &P.blk_cnt, H))) return rc;
-    if ((rc = S.get(ctx, &P.elig_tmp, H))) return rc;
-    if ((rc = S.get(ctx, &P.elig_idx, H))) return rc;
-    if ((rc = S.get(ctx, &P.ch_q, H))) return rc;
-    if ((rc = S.get(ctx, &P.ch_s, H))) return rc;
-    if ((rc = S.get(ctx, &P.dp_f, H))) return rc;
-    if ((rc = S.get(ctx, &P.dp_p, H))) return rc;
-    if ((rc = S.get(ctx, &P.dp_t, H))) return rc;
-    if ((rc = S.get(ctx, &P.dp_v, H))) return rc;
-    if ((rc = S.get(ctx, &P.sort_scratch, scratch))) return rc;
+    if ((rc = S.get(&P.seed_kid, H))) return rc;
+    if ((rc = S.get(&P.seed_off, H))) return rc;
+    if ((rc = S.get(&P.blk_id, H))) return rc;
+    if ((rc = S.get(&P.blk_seg, H))) return rc;
+    if ((rc = S.get(&P.blk_cnt, H))) return rc;
+    if ((rc = S.get(&P.elig_tmp, H))) return rc;
+    if ((rc = S.get(&P.elig_idx, H))) return rc;
+    if ((rc = S.get(&P.ch_q, H))) return rc;
+    if ((rc = S.get(&P.ch_s, H))) return rc;
+    if ((rc = S.get(&P.dp_f, H))) return rc;
+    if ((rc = S.get(&P.dp_p, H))) return rc;
+    if ((rc = S.get(&P.dp_t, H))) return rc;
+    if ((rc = S.get(&P.dp_v, H))) return rc;
+    if ((rc = S.get(&P.sort_scratch, scratch))) return rc;
 
     k_build_blocks<<<U, BUILD_THREADS, 0, st>>>(P);
     NB_LAUNCH_CHECK(ctx);
@@ -819,9 +801,9 @@ extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* 
     NB_CUDA(ctx, cudaMemcpyAsync(cnts, P.counters, sizeof cnts, cudaMemcpyDeviceToHost, st));
     NB_CUDA(ctx, cudaStreamSynchronize(st));
     const uint64_t E = cnts[3];
-    if ((rc = S.get(ctx, &P.out, E))) return rc;
-    if ((rc = S.get(ctx, &P.out_unit, E))) return rc;
-    if ((rc = S.get(ctx, &P.out_seq, E))) return rc;
+    if ((rc = S.get(&P.out, E))) return rc;
+    if ((rc = S.get(&P.out_unit, E))) return rc;
+    if ((rc = S.get(&P.out_seq, E))) return rc;
 
     k_candidates<<<(U + CAND_WARPS - 1) / CAND_WARPS, CAND_WARPS * 32, 0, st>>>(P);
     NB_LAUNCH_CHECK(ctx);
