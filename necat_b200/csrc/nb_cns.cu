@@ -365,7 +365,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     t_setup += ht.lap();
 
     // ---- chunks of templates: bounded device memory
-    const size_t kChunk = 8192;
+    const size_t kChunk = 32768;
     unsigned nthreads = std::thread::hardware_concurrency();
     if (nthreads == 0) nthreads = 4;
     if (nthreads > 64) nthreads = 64;
@@ -452,11 +452,13 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
         std::vector<CnsAln> alns;
         std::vector<CnsTemplate> dt;
         std::vector<size_t> dt_tpl;
-        uint64_t out_pool = 0; uint32_t seg_total = 0; uint32_t maxT = 0;
+        uint64_t out_pool = 0, pos_total = 0, link_total = 0, level_total = 0; uint32_t seg_total = 0;
         for (size_t t = c0; t < c1; ++t) {
             Tpl& T = tpls[t];
             CnsTemplate ct;
+            memset(&ct, 0, sizeof ct);
             ct.aln_first = (uint32_t)alns.size(); ct.n_aln = (uint32_t)T.acc.size(); ct.T = T.T;
+            uint64_t cols = 0;
             for (const Accepted& a : T.acc) {
                 const Can& c = cans[T.first + (size_t)a.can];
                 const nb_alignment& r = res[(size_t)c.res];
@@ -465,13 +467,17 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
                 ca.aln_size = r.aln_size; ca.toff = r.toff; ca.tend = r.tend; ca.qstart = r.qoff;
                 ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight;
                 alns.push_back(ca);
+                cols += (uint64_t)r.aln_size;
             }
             ct.seg_cap = (uint32_t)(T.T / std::max(1, (int)(o.min_size * 0.85)) + 2);
             ct.seg_first = seg_total; seg_total += ct.seg_cap;
             ct.out_cap = (uint32_t)(T.T * 2 + 1024);
             ct.out_base = out_pool; out_pool += ct.out_cap;
-            ct.pad_ = 0;
-            if ((uint32_t)T.T > maxT) maxT = (uint32_t)T.T;
+            ct.pos_base = pos_total; pos_total += (uint64_t)T.T + 2;
+            ct.link_cap = (uint32_t)std::min<uint64_t>(cols + 32, 0xfffffff0ull);      // links <= columns
+            ct.link_base = link_total; link_total += ct.link_cap;
+            ct.level_cap = (uint32_t)(T.T * 3 + 2048);
+            ct.level_base = level_total; level_total += ct.level_cap;
             ctx->cc.n_accepted += T.acc.size();
             dt.push_back(ct); dt_tpl.push_back(t);
         }
@@ -482,9 +488,6 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
         uint8_t* d_seq_pool = NULL;
         if (!dt.empty()) {
             int rc;
-            const unsigned grid = NB_SMS * 5;           // 5 CTAs x 2 warps per SM (shared memory bound)
-            const size_t slots = (size_t)grid * CNS_WARPS;
-            const uint32_t cap_steps = maxT * 4 + 4096;
             CnsParams P;
             memset(&P, 0, sizeof P);
             CnsTemplate* d_tpl; CnsAln* d_aln;
@@ -495,25 +498,35 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
             if ((rc = D.get(&P.seq_pool, out_pool))) return rc;
             d_seq_pool = P.seq_pool;
             if ((rc = D.get(&P.next_tpl, 1))) return rc;
-            if ((rc = D.get(&P.cov, slots * (maxT + 2)))) return rc;
-            if ((rc = D.get(&P.pos_first, slots * (maxT + 2)))) return rc;
-            if ((rc = D.get(&P.flag, slots * (maxT + 2)))) return rc;
-            if ((rc = D.get(&P.bp, slots * (size_t)cap_steps))) return rc;
-            if ((rc = D.get(&P.rev, slots * (size_t)cap_steps))) return rc;
+            if ((rc = D.get(&P.cov, pos_total))) return rc;
+            if ((rc = D.get(&P.flag, pos_total))) return rc;
+            if ((rc = D.get(&P.pos_start, pos_total))) return rc;
+            if ((rc = D.get(&P.pos_first, pos_total))) return rc;
+            if ((rc = D.get(&P.link_key, link_total))) return rc;
+            if ((rc = D.get(&P.link_w, link_total))) return rc;
+            if ((rc = D.get(&P.bp, level_total))) return rc;
+            if ((rc = D.get(&P.rev, level_total))) return rc;
             if ((rc = D.get(&P.error_flag, 1))) return rc;
             if ((rc = D.get(&P.counters, 4))) return rc;
+            CnsRun* d_runs; uint32_t* d_nrun;
+            if ((rc = D.get(&d_runs, seg_total))) return rc;
+            if ((rc = D.get(&d_nrun, dt.size()))) return rc;
             NB_CUDA(ctx, cudaMemcpyAsync(d_tpl, dt.data(), sizeof(CnsTemplate) * dt.size(), cudaMemcpyHostToDevice, st));
             NB_CUDA(ctx, cudaMemcpyAsync(d_aln, alns.data(), sizeof(CnsAln) * alns.size(), cudaMemcpyHostToDevice, st));
             NB_CUDA(ctx, cudaMemsetAsync(P.next_tpl, 0, sizeof(uint32_t), st));
             NB_CUDA(ctx, cudaMemsetAsync(P.error_flag, 0, sizeof(uint32_t), st));
             NB_CUDA(ctx, cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 4, st));
             P.pac = reads->d_pac; P.tpl = d_tpl; P.aln = d_aln; P.n_tpl = (uint32_t)dt.size();
-            P.maxT = maxT; P.cap_steps = cap_steps; P.min_cov = o.min_cov; P.min_size = o.min_size;
+            P.min_cov = o.min_cov; P.min_size = o.min_size;
             const size_t smem = sizeof(CnsWarpShared) * CNS_WARPS;
-            if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_cns_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             t_prep += ht.lap();
             cudaEventRecord(ctx->ev2, st);
-            k_consensus<<<grid, CNS_WARPS * 32, smem, st>>>(P);
+            k_cns_links<<<NB_SMS * 3, CNS_WARPS * 32, smem, st>>>(P);
+            NB_LAUNCH_CHECK(ctx);
+            k_cns_dp<<<(unsigned)((dt.size() + 127) / 128), 128, 0, st>>>(P, d_runs, d_nrun);
+            NB_LAUNCH_CHECK(ctx);
+            k_cns_walk<<<(unsigned)((dt.size() + 127) / 128), 128, 0, st>>>(P, d_runs, d_nrun);
             NB_LAUNCH_CHECK(ctx);
             cudaEventRecord(ctx->ev3, st);
             uint32_t eflag = 0; unsigned long long cnt[4];

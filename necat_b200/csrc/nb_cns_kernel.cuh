@@ -16,20 +16,21 @@
 //            distinct (t_pos, delta) keys, alignments are processed one after the
 //            other, so every link weight is the sum in acceptance order -- the
 //            order add_one_align was called (cns_aux.c:48).
-//   phase B  positions of the tile are then scored in order: lanes = links of the
-//            position; per delta level the <= 5 nodes take their best link
-//            (cns_aux.c:157-184) and an 11-bit back pointer per node is packed into
-//            one u64 per (t_pos, delta) step.
-// At the end of a coverage run the walk-back follows the back pointers
-// (cns_aux.c:187-212).
+//            At the end of a tile every position's links are written to HBM sorted by
+//            (delta, base, predecessor): k_cns_links.
+//   phase B  k_cns_dp: the best-path recurrence (cns_aux.c:157-184) is a chain over
+//            template positions with ~4 links each -- no intra-template parallelism
+//            worth a warp -- so it runs one THREAD per template, tens of thousands
+//            of templates in flight; per (t_pos, delta) level an 11-bit back pointer
+//            per node is packed into one u64.  At the end of a coverage run the same
+//            thread walks the back pointers (cns_aux.c:187-212) and emits the bases.
 #pragma once
 #include "nb_common.cuh"
 #include "nb_extend.cuh"
 
 #define CNS_MAX_ALN 320         // >= MAX_EXAMINED_CAN (consensus_aux.h:15)
-#define CNS_WARPS 2
+#define CNS_WARPS 4
 #define CNS_POOL 1024           // links per tile
-#define CNS_NODES 160           // nodes of one position
 
 struct CnsAln {                 // one accepted alignment, in acceptance order
     const uint8_t* ops;
@@ -45,9 +46,12 @@ struct CnsTemplate {
     int32_t  T;
     uint32_t seg_first;         // first slot in the segment arrays
     uint32_t seg_cap;
-    uint64_t out_base;          // into the sequence pool
     uint32_t out_cap;
-    uint32_t pad_;
+    uint64_t out_base;          // into the sequence pool
+    uint64_t pos_base;          // into cov / flag / pos_start / pos_first   (T + 2 slots)
+    uint64_t link_base;         // into link_key / link_w                    (link_cap slots)
+    uint64_t level_base;        // into bp / rev                             (level_cap slots)
+    uint32_t link_cap, level_cap;
 };
 
 struct CnsSegment {             // one consensus stretch of >= min_size bases
@@ -66,16 +70,21 @@ struct CnsParams {
     CnsSegment*        seg;
     uint32_t*          tpl_nseg;        // [n_tpl]
     uint8_t*           seq_pool;
-    uint32_t*          next_tpl;        // work queue
-    int32_t*           cov;             // per warp slot: [maxT + 2]
-    uint32_t*          pos_first;       // per warp slot: [maxT + 2]
-    uint8_t*           flag;            // per warp slot: [maxT + 2]  1 = in a scored run, 2 = first of run, 4 = last of run
-    unsigned long long* bp;             // per warp slot: [cap_steps]
-    uint8_t*           rev;             // per warp slot: [cap_steps]
-    uint32_t           maxT, cap_steps;
+    uint32_t*          next_tpl;        // work queue of k_cns_links
+    // per template position
+    int32_t*           cov;
+    uint8_t*           flag;            // 1 = in a scored run, 2 = first of run, 4 = last of run
+    uint32_t*          pos_start;       // first link of the position (relative to link_base); [T] = total
+    uint32_t*          pos_first;       // level index of (t, delta 0)
+    // per link, sorted by key inside a position
+    uint32_t*          link_key;        // delta(8) << 24 | base(3) << 20 | pred base(3) << 16 | pred rank(16)
+    double*            link_w;          // weight; k_cns_dp overwrites the first link of a node with the node score
+    // per level
+    unsigned long long* bp;
+    uint8_t*           rev;
     int                min_cov, min_size;
-    uint32_t*          error_flag;      // 1 = step capacity, 2 = link pool / node list full, 4 = output capacity
-    unsigned long long* counters;       // [0] steps, [1] columns (tags)
+    uint32_t*          error_flag;      // 1 = level capacity, 2 = link pool / link capacity, 4 = output capacity
+    unsigned long long* counters;       // [0] levels, [1] columns (tags), [2] links
 };
 
 struct CnsWarpShared {
@@ -86,15 +95,11 @@ struct CnsWarpShared {
     uint16_t last_node[CNS_MAX_ALN];    // delta << 3 | base of column x-1; 0xffff = none
     uint8_t  valid[CNS_MAX_ALN];
     // links of the current tile: per-position singly linked lists
-    uint32_t e_key[CNS_POOL];           // delta(8) << 24 | base(3) << 20 | pred base(3) << 16 | pred rank(16)
+    uint32_t e_key[CNS_POOL];
     double   e_w[CNS_POOL];
     uint16_t e_next[CNS_POOL];
     uint32_t head[32];
     uint32_t pool_used;
-    // node scores of the previous / current position
-    uint16_t n_key[2][CNS_NODES];       // delta << 3 | base
-    double   n_score[2][CNS_NODES];
-    uint32_t n_cnt[2];
 };
 
 __device__ __forceinline__ int cns_qbase(const uint8_t* __restrict__ pac, uint64_t qseq_off, int qlen, int qdir, uint32_t qpos)
@@ -107,27 +112,15 @@ __device__ __forceinline__ int cns_qbase(const uint8_t* __restrict__ pac, uint64
 // rank of a base in the reference's tag order (ASCII: '-' < 'A' < 'C' < 'G' < 'T')
 __device__ __forceinline__ uint32_t cns_char_rank(uint32_t b) { return b == 4 ? 0u : b + 1u; }
 
-__device__ __forceinline__ double cns_node_lookup(const CnsWarpShared& S, int buf, uint32_t nkey)
-{
-    const uint32_t n = S.n_cnt[buf];
-    for (uint32_t i = 0; i < n; ++i) if (S.n_key[buf][i] == nkey) return S.n_score[buf][i];
-    return 0.0;         // never scored (outside the run): cns_aux.c:63-70 initialises scores to 0
-}
-
+// ------------------------------------------------------------------ phase A
 __global__ void __launch_bounds__(CNS_WARPS * 32)
-k_consensus(CnsParams P)
+k_cns_links(CnsParams P)
 {
     extern __shared__ __align__(16) uint8_t cns_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1, le_mask = lt_mask | (1u << lane);
     CnsWarpShared& S = reinterpret_cast<CnsWarpShared*>(cns_smem)[wid];
-    const size_t slot = (size_t)blockIdx.x * CNS_WARPS + wid;
-    int32_t* cov = P.cov + slot * (size_t)(P.maxT + 2);
-    uint32_t* pos_first = P.pos_first + slot * (size_t)(P.maxT + 2);
-    uint8_t* flag = P.flag + slot * (size_t)(P.maxT + 2);
-    unsigned long long* bp = P.bp + slot * (size_t)P.cap_steps;
-    uint8_t* rev = P.rev + slot * (size_t)P.cap_steps;
-    unsigned long long n_steps_total = 0, n_cols_total = 0;
+    unsigned long long n_cols_total = 0, n_links_total = 0;
 
     for (;;) {
         uint32_t ti = 0;
@@ -137,7 +130,11 @@ k_consensus(CnsParams P)
         const CnsTemplate TP = P.tpl[ti];
         const CnsAln* AL = P.aln + TP.aln_first;
         const int A = (int)TP.n_aln, T = TP.T;
-        uint32_t nseg = 0, out_used = 0;
+        int32_t* cov = P.cov + TP.pos_base;
+        uint8_t* flag = P.flag + TP.pos_base;
+        uint32_t* pos_start = P.pos_start + TP.pos_base;
+        uint32_t* lkey = P.link_key + TP.link_base;
+        double* lw = P.link_w + TP.link_base;
         uint32_t fail = 0;
 
         // ---- 0. an insertion run of >= 255 drops the whole alignment (align_tags.c:40-44); lane = column
@@ -205,17 +202,12 @@ k_consensus(CnsParams P)
         }
         __syncwarp();
 
-        // ---- 3. sweep the template tile by tile
-        uint32_t step = 0;
-        double g_best = -1.0;
-        int g_step = -1, g_b = -1, g_t = 0, g_delta = 0, run_from = 0;
-        int cur = 0;                            // node buffer of the current position
-        if (lane == 0) { S.n_cnt[0] = 0; S.n_cnt[1] = 0; }
+        // ---- 3. tile sweep: links of 32 positions at a time, alignments in acceptance order
+        uint32_t ebase = 0;                     // links written so far
         for (int t0 = 0; t0 < T && !fail; t0 += 32) {
             const int t1 = (t0 + 32 < T) ? t0 + 32 : T;
             const uint32_t tile_flag = (t0 + lane < T) ? flag[t0 + lane] : 0;
             const uint32_t tile_any = __ballot_sync(0xffffffffu, tile_flag & 1);
-            // ---------------- phase A: links of the tile, alignments in acceptance order
             if (lane == 0) S.pool_used = 0;
             S.head[lane] = 0xffffu;
             __syncwarp();
@@ -286,143 +278,208 @@ k_consensus(CnsParams P)
                 __syncwarp();
             }
             if (S.pool_used > CNS_POOL) { fail |= 2; break; }
-            if (!tile_any) continue;
-            // ---------------- phase B: score the positions of the tile in order; lanes = links of the position
-            for (int t = t0; t < t1 && !fail; ++t) {
-                const uint32_t fl = __shfl_sync(0xffffffffu, tile_flag, t - t0);
-                if (!(fl & 1)) continue;
-                if (fl & 2) {                       // a run starts: nothing scored so far
-                    if (lane == 0) { S.n_cnt[0] = 0; S.n_cnt[1] = 0; }
-                    g_best = -1.0; g_step = -1; step = 0; run_from = t;
-                    __syncwarp();
-                }
-                const int prev = cur ^ 1;
-                if (lane == 0) { S.n_cnt[cur] = 0; pos_first[t] = step; }
-                // hand the links of this position to the lanes (two per lane at most)
-                int e0 = 0xffff, e1 = 0xffff, cnt = 0;
-                for (int e = (int)S.head[t - t0]; e != 0xffff; e = S.e_next[e], ++cnt) {
-                    if (cnt == lane) e0 = e;
-                    if (cnt == lane + 32) e1 = e;
-                }
-                if (cnt > 64) { fail |= 2; break; }
-                const double pen = __dmul_rn(0.2, (double)cov[t]);             // 0.4 * 0.5 * coverage (cns_aux.c:164)
-                int maxd = 0;
-                uint32_t k0 = 0, k1 = 0;
-                double w0 = 0, w1 = 0;
-                if (e0 != 0xffff) { k0 = S.e_key[e0]; w0 = S.e_w[e0]; maxd = (int)(k0 >> 24); }
-                if (e1 != 0xffff) { k1 = S.e_key[e1]; w1 = S.e_w[e1]; maxd = max(maxd, (int)(k1 >> 24)); }
-                for (int d = 16; d > 0; d >>= 1) maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, d));
-                __syncwarp();
-                for (int d = 0; d <= maxd && !fail; ++d) {
-                    if (step >= P.cap_steps) { fail |= 1; break; }
-                    double nsc[5]; uint32_t nrank[5], ncode[5]; bool npres[5], nchosen[5];
+            // ---- flush: lane = position; its links go to HBM in key order
+            int cnt = 0;
+            for (int e = (int)S.head[lane]; e != 0xffff; e = S.e_next[e]) ++cnt;
+            int off = cnt;
 #pragma unroll
-                    for (int bb = 0; bb < 5; ++bb) { nsc[bb] = -1.0; nrank[bb] = 0; ncode[bb] = 7; npres[bb] = false; nchosen[bb] = false; }
-                    // each link of this delta level gets its score; two passes for lanes holding two links
-                    for (int half = 0; half < 2; ++half) {
-                        const int e = half ? e1 : e0;
-                        const uint32_t key = half ? k1 : k0;
-                        const bool act = e != 0xffff && (int)(key >> 24) == d;
-                        const uint32_t am = __ballot_sync(0xffffffffu, act);
-                        if (!am) continue;
-                        const uint32_t b = (key >> 20) & 7, pb = (key >> 16) & 7, rank = key & 0xffff;
-                        double sc = 0.0;
-                        if (act) {
-                            sc = __dsub_rn(half ? w1 : w0, pen);
-                            if (rank != 0) {
-                                double ps;
-                                if (d == 0) ps = cns_node_lookup(S, prev, (uint32_t)(((rank - 1 - cns_char_rank(pb)) / 5u) << 3) | pb);
-                                else ps = cns_node_lookup(S, cur, (uint32_t)((d - 1) << 3) | pb);
-                                sc = __dadd_rn(sc, ps);
-                            }
-                        }
-                        // per base: best link = largest score, ties to the smallest predecessor rank; needs score > -1
-#pragma unroll
-                        for (int bb = 0; bb < 5; ++bb) {
-                            uint32_t gm = __ballot_sync(0xffffffffu, act && b == (uint32_t)bb);
-                            if (!gm) continue;
-                            npres[bb] = true;
-                            for (; gm; gm &= gm - 1) {
-                                const int src = __ffs(gm) - 1;
-                                const double s2 = __shfl_sync(0xffffffffu, sc, src);
-                                const uint32_t key2 = __shfl_sync(0xffffffffu, key, src);
-                                const uint32_t r2 = key2 & 0xffff, pb2 = (key2 >> 16) & 7;
-                                const bool better = nchosen[bb] ? (s2 > nsc[bb] || (s2 == nsc[bb] && r2 < nrank[bb])) : (s2 > -1.0);
-                                if (better) {
-                                    nsc[bb] = s2; nrank[bb] = r2; nchosen[bb] = true;
-                                    ncode[bb] = r2 == 0 ? 7u : (((d == 0 ? (r2 - 1 - cns_char_rank(pb2)) / 5u : 0u) << 3) | pb2);
-                                }
-                            }
-                        }
-                    }
-                    unsigned long long packed = 0;
-                    // record the nodes of this level, the back pointers, the run's best node (cns_aux.c:177-184)
-                    uint32_t n0 = S.n_cnt[cur];
-                    __syncwarp();
-#pragma unroll
-                    for (int bb = 0; bb < 5; ++bb) {
-                        if (!npres[bb]) continue;
-                        const double ns = nchosen[bb] ? nsc[bb] : -1.0;
-                        packed |= (unsigned long long)(nchosen[bb] ? ncode[bb] : 7u) << (11 * bb);
-                        if (n0 < CNS_NODES) {
-                            if (lane == 0) { S.n_key[cur][n0] = (uint16_t)((d << 3) | bb); S.n_score[cur][n0] = ns; }
-                        } else fail |= 2;
-                        ++n0;
-                        if (ns > g_best) { g_best = ns; g_step = (int)step; g_b = bb; g_t = t; g_delta = d; }
-                    }
-                    if (lane == 0) { S.n_cnt[cur] = n0 < CNS_NODES ? n0 : CNS_NODES; bp[step] = packed; }
-                    __syncwarp();
-                    ++step;
+            for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, off, d); if (lane >= d) off += o; }
+            const int tile_total = __shfl_sync(0xffffffffu, off, 31);
+            off -= cnt;
+            if (ebase + (uint32_t)tile_total > TP.link_cap) { fail |= 2; break; }
+            if (t0 + lane < T) pos_start[t0 + lane] = ebase + (uint32_t)off;
+            uint32_t lastkey = 0;
+            for (int i = 0; i < cnt; ++i) {        // selection by increasing key (keys of a position are distinct)
+                uint32_t bk = 0xffffffffu; int be = 0xffff;
+                for (int e = (int)S.head[lane]; e != 0xffff; e = S.e_next[e]) {
+                    const uint32_t kk = S.e_key[e];
+                    if (kk < bk && (i == 0 || kk > lastkey)) { bk = kk; be = e; }
                 }
-                cur ^= 1;
-                // ---------------- the run ends here: walk back from its best node (cns_aux.c:187-212)
-                if ((fl & 4) && !fail) {
-                    n_steps_total += step;
-                    if (g_step >= 0) {
-                        int cs = g_step, cb = g_b, ct = g_t, cd = g_delta;
-                        uint32_t n = 0;
-                        int cns_from = 0;
-                        for (;;) {
-                            const uint32_t code = (uint32_t)(bp[cs] >> (11 * cb)) & 0x7ff;
-                            const uint32_t pb = code & 7;
-                            if (pb == 7) break;                         // best_p_t_pos == -1: this node is not emitted
-                            const int emit = cb;
-                            int ns, nt, nd;
-                            bool stop_after = false;
-                            if (cd > 0) { ns = cs - 1; nt = ct; nd = cd - 1; }
-                            else {
-                                nt = ct - 1; nd = (int)(code >> 3);
-                                if (nt < run_from) { stop_after = true; ns = 0; }   // predecessor outside the run: never scored
-                                else ns = (int)pos_first[nt] + nd;
-                            }
-                            cns_from = nt;
-                            if (emit != 4) { if (lane == 0) rev[n] = (uint8_t)emit; ++n; }
-                            if (stop_after) break;
-                            cs = ns; cb = (int)pb; ct = nt; cd = nd;
-                        }
-                        __syncwarp();
-                        if ((int)n >= P.min_size) {
-                            if (nseg < TP.seg_cap && out_used + n <= TP.out_cap) {
-                                uint8_t* dst = P.seq_pool + TP.out_base + out_used;
-                                for (uint32_t k = lane; k < n; k += 32) dst[k] = rev[n - 1 - k];
-                                if (lane == 0) {
-                                    CnsSegment sg;
-                                    sg.left = run_from; sg.right = t + 1; sg.cns_from = cns_from; sg.cns_to = g_t + 1;
-                                    sg.len = n; sg.pad_ = 0; sg.seq_off = TP.out_base + out_used;
-                                    P.seg[TP.seg_first + nseg] = sg;
-                                }
-                                ++nseg; out_used += n;
-                            } else fail |= 4;
-                        }
-                    }
-                    __syncwarp();
-                }
+                lkey[ebase + off + i] = bk;
+                lw[ebase + off + i] = S.e_w[be];
+                lastkey = bk;
             }
+            ebase += (uint32_t)tile_total;
+            __syncwarp();
         }
+        if (lane == 0) pos_start[T] = ebase;
+        n_links_total += ebase;
         if (fail && lane == 0) atomicOr(P.error_flag, fail);
-        if (lane == 0) P.tpl_nseg[ti] = nseg;
         __syncwarp();
     }
     for (int d = 16; d > 0; d >>= 1) n_cols_total += __shfl_xor_sync(0xffffffffu, n_cols_total, d);
-    if (lane == 0) { atomicAdd(P.counters + 0, n_steps_total); atomicAdd(P.counters + 1, n_cols_total); }
+    if (lane == 0) { atomicAdd(P.counters + 1, n_cols_total); atomicAdd(P.counters + 2, n_links_total); }
+}
+
+// ------------------------------------------------------------------ phase B
+// Score of node (d, b) among the sorted links [s, e) of one position: its first link holds it.
+__device__ __forceinline__ double cns_node_score(const uint32_t* __restrict__ lkey, const double* __restrict__ lw,
+                                                 uint32_t s, uint32_t e, uint32_t node_db)
+{
+    for (uint32_t x = s; x < e; ++x)
+        if ((lkey[x] >> 20) == node_db) return lw[x];
+    return 0.0;         // never scored (outside the run): cns_aux.c:63-70 initialises scores to 0
+}
+
+// One run of a template, recorded by k_cns_dp for k_cns_walk.
+struct CnsRun {
+    int32_t from, to;           // coverage run [from, to)
+    int32_t g_level, g_b, g_t, g_delta;     // best node of the run (cns_aux.c:177-184), g_level < 0: none
+};
+
+// Flat loop: every iteration either advances to the next template position or scores one link, so the
+// 32 templates of a warp stay converged although their link counts differ.
+__global__ void __launch_bounds__(128)
+k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun)
+{
+    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= P.n_tpl) return;
+    const CnsTemplate TP = P.tpl[ti];
+    const int T = TP.T;
+    const int32_t* cov = P.cov + TP.pos_base;
+    const uint8_t* flag = P.flag + TP.pos_base;
+    const uint32_t* pos_start = P.pos_start + TP.pos_base;
+    uint32_t* pos_first = P.pos_first + TP.pos_base;
+    const uint32_t* lkey = P.link_key + TP.link_base;
+    double* lw = P.link_w + TP.link_base;
+    unsigned long long* bp = P.bp + TP.level_base;
+    CnsRun* my_runs = runs + TP.seg_first;
+    uint32_t nrun = 0, fail = 0, level = 0;
+    double g_best = -1.0;
+    int g_level = -1, g_b = -1, g_t = 0, g_delta = 0, run_from = 0;
+    // current position
+    int t = -1;
+    uint32_t s = 0, e = 0, ps = 0, fl = 0;      // links [s, e) of position t, [ps, s) of the previous position of the run
+    double pen = 0.0;
+    // current level / node
+    bool have_node = false, have_level = false;
+    uint32_t cur_d = 0, cur_db = 0, node_first = 0, best_rank = 0, code = 7;
+    double best = -1.0;
+    bool chosen = false;
+    unsigned long long packed = 0;
+    uint32_t x = 0;
+    for (;;) {
+        if (x == e) {
+            // ---- finish the position, move to the next one
+            if (have_node) {
+                const double ns = chosen ? best : -1.0;
+                lw[node_first] = ns;                                    // node score lives in the node's first link
+                packed |= (unsigned long long)(chosen ? code : 7u) << (11 * (cur_db & 7));
+                if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)(cur_db & 7); g_t = t; g_delta = (int)cur_d; }
+                have_node = false;
+            }
+            if (have_level) {
+                if (level < TP.level_cap) bp[level] = packed; else fail |= 1;
+                ++level; have_level = false;
+            }
+            if (t >= 0 && (fl & 4)) {                                   // the run ends at t
+                if (nrun < TP.seg_cap) {
+                    CnsRun r; r.from = run_from; r.to = t + 1; r.g_level = g_level; r.g_b = g_b; r.g_t = g_t; r.g_delta = g_delta;
+                    my_runs[nrun] = r;
+                }
+                ++nrun;
+            }
+            ++t;
+            if (t >= T) break;
+            fl = flag[t];
+            ps = s;
+            s = e;                                                      // == pos_start[t]
+            e = pos_start[t + 1];
+            if (fl & 2) { g_best = -1.0; g_level = -1; run_from = t; }
+            if (fl & 1) { pen = __dmul_rn(0.2, (double)cov[t]); pos_first[t] = level; }   // 0.4 * 0.5 * coverage (cns_aux.c:164)
+            continue;
+        }
+        // ---- one link
+        const uint32_t key = lkey[x];
+        const uint32_t db = key >> 20, d = key >> 24;                   // db = delta << 4 | base
+        if (have_node && db != cur_db) {
+            const double ns = chosen ? best : -1.0;
+            lw[node_first] = ns;
+            packed |= (unsigned long long)(chosen ? code : 7u) << (11 * (cur_db & 7));
+            if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)(cur_db & 7); g_t = t; g_delta = (int)cur_d; }
+            have_node = false;
+        }
+        if (have_level && d != cur_d) {
+            if (level < TP.level_cap) bp[level] = packed; else fail |= 1;
+            ++level; have_level = false;
+        }
+        if (!have_level) { have_level = true; cur_d = d; packed = 0; }
+        if (!have_node) { have_node = true; cur_db = db; node_first = x; best = -1.0; best_rank = 0; code = 7; chosen = false; }
+        const uint32_t rank = key & 0xffff, pb = (key >> 16) & 7;
+        double sc = __dsub_rn(lw[x], pen);
+        if (rank != 0) {
+            // score of the predecessor node: first link of that node among the sorted links of its position
+            uint32_t a, bnd, want;
+            if (d == 0) { a = ps; bnd = (t > run_from) ? s : ps; want = (((rank - 1 - cns_char_rank(pb)) / 5u) << 4) | pb; }
+            else        { a = s;  bnd = x;                       want = ((d - 1) << 4) | pb; }
+            double pscore = 0.0;                                        // never scored (outside the run): cns_aux.c:63-70
+            for (; a < bnd; ++a) if ((lkey[a] >> 20) == want) { pscore = lw[a]; break; }
+            sc = __dadd_rn(sc, pscore);
+        }
+        const bool better = chosen ? (sc > best || (sc == best && rank < best_rank)) : (sc > -1.0);
+        if (better) {
+            best = sc; best_rank = rank; chosen = true;
+            code = rank == 0 ? 7u : (((d == 0 ? (rank - 1 - cns_char_rank(pb)) / 5u : 0u) << 3) | pb);
+        }
+        ++x;
+    }
+    if (fail) atomicOr(P.error_flag, fail);
+    if (nrun > TP.seg_cap) { atomicOr(P.error_flag, 4u); nrun = TP.seg_cap; }
+    tpl_nrun[ti] = nrun;
+    atomicAdd(P.counters + 0, (unsigned long long)level);
+}
+
+// Walk-back of one run per thread (cns_aux.c:187-212); consensus bases written back to front into the
+// template's slice of the sequence pool.  Runs of one template write disjoint slices: run k of a template
+// owns out_base + (offset computed from the level ranges), here simply the levels [pos_first[from], ...).
+__global__ void __launch_bounds__(128)
+k_cns_walk(CnsParams P, const CnsRun* __restrict__ runs, const uint32_t* __restrict__ tpl_nrun)
+{
+    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= P.n_tpl) return;
+    const CnsTemplate TP = P.tpl[ti];
+    const uint32_t* pos_first = P.pos_first + TP.pos_base;
+    const unsigned long long* bp = P.bp + TP.level_base;
+    uint8_t* rev = P.rev + TP.level_base;
+    const uint32_t nrun = tpl_nrun[ti];
+    uint32_t nseg = 0, out_used = 0, fail = 0;
+    for (uint32_t k = 0; k < nrun; ++k) {
+        const CnsRun R = runs[TP.seg_first + k];
+        if (R.g_level < 0) continue;
+        int cs = R.g_level, cb = R.g_b, ct = R.g_t, cd = R.g_delta;
+        uint8_t* out = rev + pos_first[R.from];         // a run emits at most one base per level
+        uint32_t n = 0;
+        int cns_from = 0;
+        for (;;) {
+            const uint32_t code = (uint32_t)(bp[cs] >> (11 * cb)) & 0x7ff;
+            const uint32_t pb = code & 7;
+            if (pb == 7) break;                         // best_p_t_pos == -1: this node is not emitted
+            const int emit = cb;
+            int ns, nt, nd;
+            bool stop_after = false;
+            if (cd > 0) { ns = cs - 1; nt = ct; nd = cd - 1; }
+            else {
+                nt = ct - 1; nd = (int)(code >> 3);
+                if (nt < R.from) { stop_after = true; ns = 0; }     // predecessor outside the run: never scored
+                else ns = (int)pos_first[nt] + nd;
+            }
+            cns_from = nt;
+            if (emit != 4) { out[n] = (uint8_t)emit; ++n; }
+            if (stop_after) break;
+            cs = ns; cb = (int)pb; ct = nt; cd = nd;
+        }
+        if ((int)n >= P.min_size) {
+            if (nseg < TP.seg_cap && out_used + n <= TP.out_cap) {
+                uint8_t* dst = P.seq_pool + TP.out_base + out_used;
+                for (uint32_t i = 0; i < n; ++i) dst[i] = out[n - 1 - i];
+                CnsSegment sg;
+                sg.left = R.from; sg.right = R.to; sg.cns_from = cns_from; sg.cns_to = R.g_t + 1;
+                sg.len = n; sg.pad_ = 0; sg.seq_off = TP.out_base + out_used;
+                P.seg[TP.seg_first + nseg] = sg;
+                ++nseg; out_used += n;
+            } else fail |= 4;
+        }
+    }
+    if (fail) atomicOr(P.error_flag, fail);
+    P.tpl_nseg[ti] = nseg;
 }
