@@ -453,7 +453,12 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
         std::vector<CnsTemplate> dt;
         std::vector<size_t> dt_tpl;
         uint64_t out_pool = 0, pos_total = 0, link_total = 0, level_total = 0; uint32_t seg_total = 0;
-        for (size_t t = c0; t < c1; ++t) {
+        std::vector<size_t> order;
+        for (size_t t = c0; t < c1; ++t) order.push_back(t);
+        static const int kSort = getenv("NB_CNS_SORT") ? atoi(getenv("NB_CNS_SORT")) : 1;
+        static const int kLanes = getenv("NB_CNS_LANES") ? atoi(getenv("NB_CNS_LANES")) : 1;
+        if (kSort) std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tpls[a].T != tpls[b].T ? tpls[a].T > tpls[b].T : a < b; });
+        for (size_t t : order) {
             Tpl& T = tpls[t];
             CnsTemplate ct;
             memset(&ct, 0, sizeof ct);
@@ -473,13 +478,15 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
             ct.seg_first = seg_total; seg_total += ct.seg_cap;
             ct.out_cap = (uint32_t)(T.T * 2 + 1024);
             ct.out_base = out_pool; out_pool += ct.out_cap;
-            ct.pos_base = pos_total; pos_total += (uint64_t)T.T + 2;
             ct.link_cap = (uint32_t)std::min<uint64_t>(cols + 32, 0xfffffff0ull);      // links <= columns
-            ct.link_base = link_total; link_total += ct.link_cap;
             ct.level_cap = (uint32_t)(T.T * 3 + 2048);
-            ct.level_base = level_total; level_total += ct.level_cap;
             ctx->cc.n_accepted += T.acc.size();
             dt.push_back(ct); dt_tpl.push_back(t);
+        }
+        for (auto& ct : dt) {
+            ct.pos_base = pos_total; pos_total += (uint64_t)ct.T + 2;
+            ct.link_base = link_total; link_total += ct.link_cap;
+            ct.level_base = level_total; level_total += ct.level_cap;
         }
         std::vector<CnsSegment> segs(seg_total);
         std::vector<uint32_t> nseg(dt.size(), 0);
@@ -498,12 +505,8 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
             if ((rc = D.get(&P.seq_pool, out_pool))) return rc;
             d_seq_pool = P.seq_pool;
             if ((rc = D.get(&P.next_tpl, 1))) return rc;
-            if ((rc = D.get(&P.cov, pos_total))) return rc;
-            if ((rc = D.get(&P.flag, pos_total))) return rc;
-            if ((rc = D.get(&P.pos_start, pos_total))) return rc;
-            if ((rc = D.get(&P.pos_first, pos_total))) return rc;
-            if ((rc = D.get(&P.link_key, link_total))) return rc;
-            if ((rc = D.get(&P.link_w, link_total))) return rc;
+            if ((rc = D.get(&P.pos, pos_total))) return rc;
+            if ((rc = D.get(&P.link, link_total))) return rc;
             if ((rc = D.get(&P.bp, level_total))) return rc;
             if ((rc = D.get(&P.rev, level_total))) return rc;
             if ((rc = D.get(&P.error_flag, 1))) return rc;
@@ -517,16 +520,17 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
             NB_CUDA(ctx, cudaMemsetAsync(P.error_flag, 0, sizeof(uint32_t), st));
             NB_CUDA(ctx, cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 4, st));
             P.pac = reads->d_pac; P.tpl = d_tpl; P.aln = d_aln; P.n_tpl = (uint32_t)dt.size();
-            P.min_cov = o.min_cov; P.min_size = o.min_size;
+            P.min_cov = o.min_cov; P.min_size = o.min_size; P.lanes = kLanes < 1 ? 1 : (kLanes > 32 ? 32 : kLanes);
             const size_t smem = sizeof(CnsWarpShared) * CNS_WARPS;
             if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_cns_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             t_prep += ht.lap();
             cudaEventRecord(ctx->ev2, st);
             k_cns_links<<<NB_SMS * 3, CNS_WARPS * 32, smem, st>>>(P);
             NB_LAUNCH_CHECK(ctx);
-            k_cns_dp<<<(unsigned)((dt.size() + 127) / 128), 128, 0, st>>>(P, d_runs, d_nrun);
+            const unsigned dp_warps = (unsigned)((dt.size() + P.lanes - 1) / P.lanes);
+            k_cns_dp<<<(dp_warps + 3) / 4, 128, 0, st>>>(P, d_runs, d_nrun);
             NB_LAUNCH_CHECK(ctx);
-            k_cns_walk<<<(unsigned)((dt.size() + 127) / 128), 128, 0, st>>>(P, d_runs, d_nrun);
+            k_cns_walk<<<(dp_warps + 3) / 4, 128, 0, st>>>(P, d_runs, d_nrun);
             NB_LAUNCH_CHECK(ctx);
             cudaEventRecord(ctx->ev3, st);
             uint32_t eflag = 0; unsigned long long cnt[4];

@@ -31,6 +31,7 @@
 #define CNS_MAX_ALN 320         // >= MAX_EXAMINED_CAN (consensus_aux.h:15)
 #define CNS_WARPS 4
 #define CNS_POOL 1024           // links per tile
+#define CNS_NOPRED 0xffffffffu
 
 struct CnsAln {                 // one accepted alignment, in acceptance order
     const uint8_t* ops;
@@ -44,14 +45,27 @@ struct CnsAln {                 // one accepted alignment, in acceptance order
 struct CnsTemplate {
     uint32_t aln_first, n_aln;
     int32_t  T;
-    uint32_t seg_first;         // first slot in the segment arrays
+    uint32_t seg_first;         // first slot in the segment / run arrays
     uint32_t seg_cap;
     uint32_t out_cap;
     uint64_t out_base;          // into the sequence pool
-    uint64_t pos_base;          // into cov / flag / pos_start / pos_first   (T + 2 slots)
-    uint64_t link_base;         // into link_key / link_w                    (link_cap slots)
-    uint64_t level_base;        // into bp / rev                             (level_cap slots)
+    uint64_t pos_base;          // into pos[]    (T + 1 records)
+    uint64_t link_base;         // into link[]   (link_cap records)
+    uint64_t level_base;        // into bp / rev (level_cap slots)
     uint32_t link_cap, level_cap;
+};
+
+struct __align__(16) CnsPos {   // one template position
+    uint32_t start;             // first link (relative to link_base); pos[T].start = total
+    int32_t  cov;               // tag-producing alignments covering it (cns_aux.c:96-98)
+    uint32_t flags;             // 1 = in a scored run, 2 = first of run, 4 = last of run
+    uint32_t first_level;       // level index of (t, delta 0), written by k_cns_dp
+};
+
+struct __align__(16) CnsLink {  // one link = (node, predecessor node), sorted by key inside a position
+    uint32_t key;               // delta(8) << 24 | base(3) << 20 | pred base(3) << 16 | pred rank(16)
+    uint32_t pred;              // index of the predecessor node's first link, CNS_NOPRED = no scored predecessor
+    double   w;                 // summed weight; k_cns_dp overwrites the first link of a node with the node score
 };
 
 struct CnsSegment {             // one consensus stretch of >= min_size bases
@@ -71,18 +85,12 @@ struct CnsParams {
     uint32_t*          tpl_nseg;        // [n_tpl]
     uint8_t*           seq_pool;
     uint32_t*          next_tpl;        // work queue of k_cns_links
-    // per template position
-    int32_t*           cov;
-    uint8_t*           flag;            // 1 = in a scored run, 2 = first of run, 4 = last of run
-    uint32_t*          pos_start;       // first link of the position (relative to link_base); [T] = total
-    uint32_t*          pos_first;       // level index of (t, delta 0)
-    // per link, sorted by key inside a position
-    uint32_t*          link_key;        // delta(8) << 24 | base(3) << 20 | pred base(3) << 16 | pred rank(16)
-    double*            link_w;          // weight; k_cns_dp overwrites the first link of a node with the node score
-    // per level
-    unsigned long long* bp;
+    CnsPos*            pos;
+    CnsLink*           link;
+    unsigned long long* bp;             // per level: 5 x 11-bit back pointers
     uint8_t*           rev;
     int                min_cov, min_size;
+    int                lanes;           // k_cns_dp / k_cns_walk: templates per warp (the other lanes idle)
     uint32_t*          error_flag;      // 1 = level capacity, 2 = link pool / link capacity, 4 = output capacity
     unsigned long long* counters;       // [0] levels, [1] columns (tags), [2] links
 };
@@ -130,11 +138,8 @@ k_cns_links(CnsParams P)
         const CnsTemplate TP = P.tpl[ti];
         const CnsAln* AL = P.aln + TP.aln_first;
         const int A = (int)TP.n_aln, T = TP.T;
-        int32_t* cov = P.cov + TP.pos_base;
-        uint8_t* flag = P.flag + TP.pos_base;
-        uint32_t* pos_start = P.pos_start + TP.pos_base;
-        uint32_t* lkey = P.link_key + TP.link_base;
-        double* lw = P.link_w + TP.link_base;
+        CnsPos* pos = P.pos + TP.pos_base;
+        CnsLink* link = P.link + TP.link_base;
         uint32_t fail = 0;
 
         // ---- 0. an insertion run of >= 255 drops the whole alignment (align_tags.c:40-44); lane = column
@@ -155,21 +160,21 @@ k_cns_links(CnsParams P)
                 S.x[a] = 0; S.qpos[a] = (uint32_t)AL[a].qstart; S.last_pos[a] = AL[a].toff - 1; S.last_node[a] = 0xffff;
             }
         }
-        // ---- 1. coverage[t] = number of tag-producing alignments covering t (cns_aux.c:96-98)
-        for (int t = lane; t <= T; t += 32) { cov[t] = 0; flag[t] = 0; }
+        // ---- 1. coverage
+        for (int t = lane; t <= T; t += 32) { CnsPos z; z.start = 0; z.cov = 0; z.flags = 0; z.first_level = 0; pos[t] = z; }
         __syncwarp();
         for (int a = lane; a < A; a += 32)
-            if (S.valid[a]) { atomicAdd(cov + AL[a].toff, 1); atomicAdd(cov + AL[a].tend, -1); }
+            if (S.valid[a]) { atomicAdd(&pos[AL[a].toff].cov, 1); atomicAdd(&pos[AL[a].tend].cov, -1); }
         __syncwarp();
         {
             int carry = 0;
             for (int base = 0; base < T; base += 32) {
                 const int t = base + lane;
-                int v = t < T ? cov[t] : 0;
+                int v = t < T ? pos[t].cov : 0;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
                 v += carry;
-                if (t < T) cov[t] = v;
+                if (t < T) pos[t].cov = v;
                 carry = __shfl_sync(0xffffffffu, v, 31);
             }
         }
@@ -180,7 +185,7 @@ k_cns_links(CnsParams P)
             while (i < T) {
                 for (;;) {
                     const int t = i + lane;
-                    const uint32_t low = __ballot_sync(0xffffffffu, t < T && cov[t] < P.min_cov);
+                    const uint32_t low = __ballot_sync(0xffffffffu, t < T && pos[t].cov < P.min_cov);
                     if (low == 0xffffffffu) { i += 32; continue; }
                     i += __ffs(~low) - 1;
                     break;
@@ -189,13 +194,13 @@ k_cns_links(CnsParams P)
                 int j = i + 1;
                 for (;;) {
                     const int t = j + lane;
-                    const uint32_t hi = __ballot_sync(0xffffffffu, t < T && cov[t] >= P.min_cov);
+                    const uint32_t hi = __ballot_sync(0xffffffffu, t < T && pos[t].cov >= P.min_cov);
                     if (hi == 0xffffffffu) { j += 32; continue; }
                     j += __ffs(~hi) - 1;
                     break;
                 }
                 if (i < T && (double)(j - i) >= __dmul_rn((double)P.min_size, 0.85)) {
-                    for (int t = i + lane; t < j; t += 32) flag[t] = (uint8_t)(1 | (t == i ? 2 : 0) | (t == j - 1 ? 4 : 0));
+                    for (int t = i + lane; t < j; t += 32) pos[t].flags = 1u | (t == i ? 2u : 0u) | (t == j - 1 ? 4u : 0u);
                 }
                 i = j;
             }
@@ -204,9 +209,10 @@ k_cns_links(CnsParams P)
 
         // ---- 3. tile sweep: links of 32 positions at a time, alignments in acceptance order
         uint32_t ebase = 0;                     // links written so far
+        uint32_t prev_start = 0, prev_cnt = 0;  // links of the last position of the previous tile
         for (int t0 = 0; t0 < T && !fail; t0 += 32) {
             const int t1 = (t0 + 32 < T) ? t0 + 32 : T;
-            const uint32_t tile_flag = (t0 + lane < T) ? flag[t0 + lane] : 0;
+            const uint32_t tile_flag = (t0 + lane < T) ? pos[t0 + lane].flags : 0;
             const uint32_t tile_any = __ballot_sync(0xffffffffu, tile_flag & 1);
             if (lane == 0) S.pool_used = 0;
             S.head[lane] = 0xffffu;
@@ -231,9 +237,9 @@ k_cns_links(CnsParams P)
                     const uint32_t vmask = __ballot_sync(0xffffffffu, ok);
                     const uint32_t tle = tmask & le_mask;
                     const int k = __popc(tle);
-                    const int pos = last_pos + k;
+                    const int ps = last_pos + k;
                     const int delta = (k == 0) ? (int)(last_node >> 3) + lane + 1 : lane - (31 - __clz(tle));
-                    const uint32_t late = __ballot_sync(0xffffffffu, ok && pos >= t1);   // columns of later tiles
+                    const uint32_t late = __ballot_sync(0xffffffffu, ok && ps >= t1);    // columns of later tiles
                     const int n_take = late ? __ffs(late) - 1 : __popc(vmask);
                     if (n_take == 0) break;
                     const bool take = lane < n_take;
@@ -242,7 +248,7 @@ k_cns_links(CnsParams P)
                     const uint32_t node = ((uint32_t)delta << 3) | (uint32_t)b;
                     uint32_t pnode = __shfl_up_sync(0xffffffffu, node, 1);
                     if (lane == 0) pnode = last_node;
-                    const int pl = pos - t0;
+                    const int pl = ps - t0;
                     const bool ins = take && pl >= 0 && ((tile_any >> (pl & 31)) & 1);   // position inside a scored run
                     uint32_t key = 0;
                     int e = 0xffff;
@@ -267,7 +273,7 @@ k_cns_links(CnsParams P)
                         ++n_cols_total;
                     }
                     const int lastl = n_take - 1;
-                    last_pos = __shfl_sync(0xffffffffu, pos, lastl);
+                    last_pos = __shfl_sync(0xffffffffu, ps, lastl);
                     last_node = __shfl_sync(0xffffffffu, node, lastl);
                     qp += __popc(qmask & ((n_take >= 32) ? 0xffffffffu : ((1u << n_take) - 1)));
                     x += (uint32_t)n_take;
@@ -278,7 +284,8 @@ k_cns_links(CnsParams P)
                 __syncwarp();
             }
             if (S.pool_used > CNS_POOL) { fail |= 2; break; }
-            // ---- flush: lane = position; its links go to HBM in key order
+            // ---- flush: lane = position; its links go to HBM in key order, with the index of the
+            //      predecessor node's first link resolved here so that k_cns_dp needs no search
             int cnt = 0;
             for (int e = (int)S.head[lane]; e != 0xffff; e = S.e_next[e]) ++cnt;
             int off = cnt;
@@ -287,7 +294,12 @@ k_cns_links(CnsParams P)
             const int tile_total = __shfl_sync(0xffffffffu, off, 31);
             off -= cnt;
             if (ebase + (uint32_t)tile_total > TP.link_cap) { fail |= 2; break; }
-            if (t0 + lane < T) pos_start[t0 + lane] = ebase + (uint32_t)off;
+            const uint32_t my_start = ebase + (uint32_t)off;
+            if (t0 + lane < T) pos[t0 + lane].start = my_start;
+            // links of the previous position: the lane below, or the last position of the previous tile (in HBM)
+            uint32_t pv_start = __shfl_up_sync(0xffffffffu, my_start, 1);
+            if (lane == 0) pv_start = prev_start;
+            const bool pv_in_run = (tile_flag & 1) && !(tile_flag & 2);            // the previous position belongs to the same run
             uint32_t lastkey = 0;
             for (int i = 0; i < cnt; ++i) {        // selection by increasing key (keys of a position are distinct)
                 uint32_t bk = 0xffffffffu; int be = 0xffff;
@@ -295,14 +307,36 @@ k_cns_links(CnsParams P)
                     const uint32_t kk = S.e_key[e];
                     if (kk < bk && (i == 0 || kk > lastkey)) { bk = kk; be = e; }
                 }
-                lkey[ebase + off + i] = bk;
-                lw[ebase + off + i] = S.e_w[be];
+                const uint32_t rank = bk & 0xffff, pb = (bk >> 16) & 7, d = bk >> 24;
+                uint32_t pred = CNS_NOPRED;
+                if (rank != 0) {
+                    if (d > 0) {
+                        // node (d - 1, pb) of this position: its first link = number of links of this position below it
+                        const uint32_t want = ((d - 1) << 4) | pb;
+                        uint32_t less = 0;
+                        for (int e = (int)S.head[lane]; e != 0xffff; e = S.e_next[e]) less += (S.e_key[e] >> 20) < want;
+                        pred = my_start + less;
+                    } else if (pv_in_run) {
+                        const uint32_t want = (((rank - 1 - cns_char_rank(pb)) / 5u) << 4) | pb;
+                        uint32_t less = 0;
+                        if (lane > 0) {
+                            for (int e = (int)S.head[lane - 1]; e != 0xffff; e = S.e_next[e]) less += (S.e_key[e] >> 20) < want;
+                        } else {
+                            for (uint32_t q = 0; q < prev_cnt; ++q) less += (link[prev_start + q].key >> 20) < want;
+                        }
+                        pred = pv_start + less;
+                    }
+                }
+                CnsLink L; L.key = bk; L.pred = pred; L.w = S.e_w[be];
+                link[my_start + i] = L;
                 lastkey = bk;
             }
+            prev_start = __shfl_sync(0xffffffffu, my_start, 31);
+            prev_cnt = (uint32_t)__shfl_sync(0xffffffffu, cnt, 31);
             ebase += (uint32_t)tile_total;
             __syncwarp();
         }
-        if (lane == 0) pos_start[T] = ebase;
+        if (lane == 0) pos[T].start = ebase;
         n_links_total += ebase;
         if (fail && lane == 0) atomicOr(P.error_flag, fail);
         __syncwarp();
@@ -312,15 +346,6 @@ k_cns_links(CnsParams P)
 }
 
 // ------------------------------------------------------------------ phase B
-// Score of node (d, b) among the sorted links [s, e) of one position: its first link holds it.
-__device__ __forceinline__ double cns_node_score(const uint32_t* __restrict__ lkey, const double* __restrict__ lw,
-                                                 uint32_t s, uint32_t e, uint32_t node_db)
-{
-    for (uint32_t x = s; x < e; ++x)
-        if ((lkey[x] >> 20) == node_db) return lw[x];
-    return 0.0;         // never scored (outside the run): cns_aux.c:63-70 initialises scores to 0
-}
-
 // One run of a template, recorded by k_cns_dp for k_cns_walk.
 struct CnsRun {
     int32_t from, to;           // coverage run [from, to)
@@ -328,42 +353,43 @@ struct CnsRun {
 };
 
 // Flat loop: every iteration either advances to the next template position or scores one link, so the
-// 32 templates of a warp stay converged although their link counts differ.
+// templates sharing a warp stay converged although their link counts differ.  Per link: one 16-byte load of
+// the link and one 8-byte load of the predecessor's score.
 __global__ void __launch_bounds__(128)
 k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun)
 {
-    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)(gt & 31) >= P.lanes) return;
+    const uint32_t ti = (gt >> 5) * (uint32_t)P.lanes + (gt & 31);
     if (ti >= P.n_tpl) return;
     const CnsTemplate TP = P.tpl[ti];
     const int T = TP.T;
-    const int32_t* cov = P.cov + TP.pos_base;
-    const uint8_t* flag = P.flag + TP.pos_base;
-    const uint32_t* pos_start = P.pos_start + TP.pos_base;
-    uint32_t* pos_first = P.pos_first + TP.pos_base;
-    const uint32_t* lkey = P.link_key + TP.link_base;
-    double* lw = P.link_w + TP.link_base;
+    CnsPos* pos = P.pos + TP.pos_base;
+    CnsLink* link = P.link + TP.link_base;
     unsigned long long* bp = P.bp + TP.level_base;
     CnsRun* my_runs = runs + TP.seg_first;
     uint32_t nrun = 0, fail = 0, level = 0;
     double g_best = -1.0;
     int g_level = -1, g_b = -1, g_t = 0, g_delta = 0, run_from = 0;
-    // current position
     int t = -1;
-    uint32_t s = 0, e = 0, ps = 0, fl = 0;      // links [s, e) of position t, [ps, s) of the previous position of the run
+    uint32_t e = 0, fl = 0;                     // links [.., e) of position t
     double pen = 0.0;
-    // current level / node
     bool have_node = false, have_level = false;
     uint32_t cur_d = 0, cur_db = 0, node_first = 0, best_rank = 0, code = 7;
     double best = -1.0;
     bool chosen = false;
     unsigned long long packed = 0;
     uint32_t x = 0;
+    // the link and position records are streamed: each is loaded one iteration before it is used
+    uint4 pr_next = *reinterpret_cast<const uint4*>(pos);           // pos[t + 1]
+    uint4 pr_next2 = *reinterpret_cast<const uint4*>(pos + 1);      // pos[t + 2]
+    uint4 lr_next = *reinterpret_cast<const uint4*>(link);          // link[x]
     for (;;) {
         if (x == e) {
             // ---- finish the position, move to the next one
             if (have_node) {
                 const double ns = chosen ? best : -1.0;
-                lw[node_first] = ns;                                    // node score lives in the node's first link
+                link[node_first].w = ns;                                // node score lives in the node's first link
                 packed |= (unsigned long long)(chosen ? code : 7u) << (11 * (cur_db & 7));
                 if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)(cur_db & 7); g_t = t; g_delta = (int)cur_d; }
                 have_node = false;
@@ -381,20 +407,24 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
             }
             ++t;
             if (t >= T) break;
-            fl = flag[t];
-            ps = s;
-            s = e;                                                      // == pos_start[t]
-            e = pos_start[t + 1];
+            const uint4 pr = pr_next;                                   // start, cov, flags, -
+            pr_next = pr_next2;
+            pr_next2 = *reinterpret_cast<const uint4*>(pos + (t + 2 <= T ? t + 2 : T));
+            fl = pr.z;
+            e = pr_next.x;                                              // pos[t + 1].start
             if (fl & 2) { g_best = -1.0; g_level = -1; run_from = t; }
-            if (fl & 1) { pen = __dmul_rn(0.2, (double)cov[t]); pos_first[t] = level; }   // 0.4 * 0.5 * coverage (cns_aux.c:164)
+            if (fl & 1) { pen = __dmul_rn(0.2, (double)(int)pr.y); pos[t].first_level = level; }   // 0.4 * 0.5 * coverage (cns_aux.c:164)
             continue;
         }
         // ---- one link
-        const uint32_t key = lkey[x];
+        const uint4 lr = lr_next;
+        lr_next = *reinterpret_cast<const uint4*>(link + x + 1);        // capacity leaves room past the last link
+        const uint32_t key = lr.x, pred = lr.y;
+        const double w = __hiloint2double((int)lr.w, (int)lr.z);
         const uint32_t db = key >> 20, d = key >> 24;                   // db = delta << 4 | base
         if (have_node && db != cur_db) {
             const double ns = chosen ? best : -1.0;
-            lw[node_first] = ns;
+            link[node_first].w = ns;
             packed |= (unsigned long long)(chosen ? code : 7u) << (11 * (cur_db & 7));
             if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)(cur_db & 7); g_t = t; g_delta = (int)cur_d; }
             have_node = false;
@@ -406,16 +436,8 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
         if (!have_level) { have_level = true; cur_d = d; packed = 0; }
         if (!have_node) { have_node = true; cur_db = db; node_first = x; best = -1.0; best_rank = 0; code = 7; chosen = false; }
         const uint32_t rank = key & 0xffff, pb = (key >> 16) & 7;
-        double sc = __dsub_rn(lw[x], pen);
-        if (rank != 0) {
-            // score of the predecessor node: first link of that node among the sorted links of its position
-            uint32_t a, bnd, want;
-            if (d == 0) { a = ps; bnd = (t > run_from) ? s : ps; want = (((rank - 1 - cns_char_rank(pb)) / 5u) << 4) | pb; }
-            else        { a = s;  bnd = x;                       want = ((d - 1) << 4) | pb; }
-            double pscore = 0.0;                                        // never scored (outside the run): cns_aux.c:63-70
-            for (; a < bnd; ++a) if ((lkey[a] >> 20) == want) { pscore = lw[a]; break; }
-            sc = __dadd_rn(sc, pscore);
-        }
+        double sc = __dsub_rn(w, pen);
+        if (pred != CNS_NOPRED) sc = __dadd_rn(sc, link[pred].w);      // never-scored predecessors count 0 (cns_aux.c:63-70)
         const bool better = chosen ? (sc > best || (sc == best && rank < best_rank)) : (sc > -1.0);
         if (better) {
             best = sc; best_rank = rank; chosen = true;
@@ -429,16 +451,16 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
     atomicAdd(P.counters + 0, (unsigned long long)level);
 }
 
-// Walk-back of one run per thread (cns_aux.c:187-212); consensus bases written back to front into the
-// template's slice of the sequence pool.  Runs of one template write disjoint slices: run k of a template
-// owns out_base + (offset computed from the level ranges), here simply the levels [pos_first[from], ...).
+// Walk-back of the runs of one template per thread (cns_aux.c:187-212).
 __global__ void __launch_bounds__(128)
 k_cns_walk(CnsParams P, const CnsRun* __restrict__ runs, const uint32_t* __restrict__ tpl_nrun)
 {
-    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)(gt & 31) >= P.lanes) return;
+    const uint32_t ti = (gt >> 5) * (uint32_t)P.lanes + (gt & 31);
     if (ti >= P.n_tpl) return;
     const CnsTemplate TP = P.tpl[ti];
-    const uint32_t* pos_first = P.pos_first + TP.pos_base;
+    const CnsPos* pos = P.pos + TP.pos_base;
     const unsigned long long* bp = P.bp + TP.level_base;
     uint8_t* rev = P.rev + TP.level_base;
     const uint32_t nrun = tpl_nrun[ti];
@@ -447,7 +469,7 @@ k_cns_walk(CnsParams P, const CnsRun* __restrict__ runs, const uint32_t* __restr
         const CnsRun R = runs[TP.seg_first + k];
         if (R.g_level < 0) continue;
         int cs = R.g_level, cb = R.g_b, ct = R.g_t, cd = R.g_delta;
-        uint8_t* out = rev + pos_first[R.from];         // a run emits at most one base per level
+        uint8_t* out = rev + pos[R.from].first_level;        // a run emits at most one base per level
         uint32_t n = 0;
         int cns_from = 0;
         for (;;) {
@@ -461,7 +483,7 @@ k_cns_walk(CnsParams P, const CnsRun* __restrict__ runs, const uint32_t* __restr
             else {
                 nt = ct - 1; nd = (int)(code >> 3);
                 if (nt < R.from) { stop_after = true; ns = 0; }     // predecessor outside the run: never scored
-                else ns = (int)pos_first[nt] + nd;
+                else ns = (int)pos[nt].first_level + nd;
             }
             cns_from = nt;
             if (emit != 4) { out[n] = (uint8_t)emit; ++n; }

@@ -111,43 +111,82 @@ __device__ __forceinline__ WalkInfo myers_walkback(WarpScratch& S, int qblk, int
     int i = qblk, j = jstar, r = 0;
     WalkInfo W; W.asize = 0; W.found = 0; W.acnt = 0; W.qcnt = 0; W.tcnt = 0;
     int m = 0;
-    // register window: lane l caches words wa, wa+1 of column jw - l
+    // Register window over 32 columns: lane l caches words wa, wa+1 (rows 32 wa + 1 .. 32 wa + 64) of column
+    // jw - l, centred on the diagonal through the cell the window was filled at.  Whole diagonal runs are
+    // then resolved in one step: lane l tests the cell (i - (l - l0), j - (l - l0)).
     int jw = -1000, wa = 0;
     uint2 pa = make_uint2(0, 0), pb = make_uint2(0, 0);
-    int cur_j = -1, cur_w = -1;
-    uint2 cur = make_uint2(0, 0);
     while (i > 0 || j > 0) {
-        int op;
-        if (i == 0) { op = OP_TONLY; --j; }
-        else if (j == 0) { op = OP_QONLY; --i; }
-        else {
-            const int w = (i - 1) >> 5, b = (i - 1) & 31;
-            if (j != cur_j || w != cur_w) {
-                int l = jw - j;
-                if (l < 0 || l >= 32) {
-                    // refill: lane x takes column j - x on the predicted diagonal
-                    jw = j;
-                    const int col = j - lane, row = i - lane;
-                    int ww = ((row - 1) - 16) >> 5;
-                    ww = ww < 0 ? 0 : (ww > nw - 1 ? nw - 1 : ww);
-                    wa = ww;
-                    if (col >= 1) {
-                        pa = mat[(size_t)(col - 1 + ww) * nw + ww];
-                        pb = (ww + 1 < nw) ? mat[(size_t)(col + ww) * nw + ww + 1] : make_uint2(0, 0);
-                    }
-                    l = 0;
-                }
-                const int swa = __shfl_sync(0xffffffffu, wa, l);
-                const int d = w - swa;
-                if (d == 0) { cur.x = __shfl_sync(0xffffffffu, pa.x, l); cur.y = __shfl_sync(0xffffffffu, pa.y, l); }
-                else if (d == 1) { cur.x = __shfl_sync(0xffffffffu, pb.x, l); cur.y = __shfl_sync(0xffffffffu, pb.y, l); }
-                else cur = mat[(size_t)(j - 1 + w) * nw + w];
-                cur_j = j; cur_w = w;
+        if (i == 0 || j == 0) {                                 // along the matrix border
+            const int op = (i == 0) ? OP_TONLY : OP_QONLY;
+            if (i == 0) --j; else --i;
+            if (lane == 0) S.rev[r] = (uint8_t)op;
+            ++r;
+            if (!W.found) {
+                W.qcnt += op != OP_TONLY; W.tcnt += op != OP_QONLY; m = 0; ++W.acnt;
             }
-            if ((cur.x >> b) & 1) { op = OP_QONLY; --i; }
-            else if ((cur.y >> b) & 1) { op = OP_TONLY; --j; }
-            else { op = (S.q[i - 1] == S.t[j - 1]) ? OP_MATCH : OP_MISMATCH; --i; --j; }
+            continue;
         }
+        int l0 = jw - j;
+        bool known = false, up = false, left = false;
+        int k = 0, ri = 0, cj = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (l0 < 0 || l0 >= 32 || attempt == 1) {
+                jw = j; l0 = 0;
+                const int col = j - lane, row = i - lane;
+                int ww = ((row - 1) - 16) >> 5;
+                ww = ww < 0 ? 0 : (ww > nw - 1 ? nw - 1 : ww);
+                wa = ww;
+                if (col >= 1) {
+                    pa = mat[(size_t)(col - 1 + ww) * nw + ww];
+                    pb = (ww + 1 < nw) ? mat[(size_t)(col + ww) * nw + ww + 1] : make_uint2(0, 0);
+                }
+            }
+            // my cell on the current diagonal
+            k = lane - l0; ri = i - k; cj = j - k;
+            known = false; up = false; left = false;
+            if (k >= 0 && ri >= 1 && cj >= 1) {
+                const int w = (ri - 1) >> 5, b = (ri - 1) & 31, d = w - wa;
+                if (d == 0) { known = true; up = (pa.x >> b) & 1; left = (pa.y >> b) & 1; }
+                else if (d == 1) { known = true; up = (pb.x >> b) & 1; left = (pb.y >> b) & 1; }
+            }
+            if ((__ballot_sync(0xffffffffu, known) >> l0) & 1) break;       // the current cell is in the window
+        }
+        const uint32_t dm = __ballot_sync(0xffffffffu, known && !up && !left) >> l0;
+        const int run = (dm == 0xffffffffu) ? 32 : __ffs(~dm) - 1;
+        if (run > 0) {
+            // a run of diagonal moves: all its columns at once
+            bool mt = false;
+            if (k >= 0 && k < run) {
+                mt = S.q[ri - 1] == S.t[cj - 1];
+                S.rev[r + k] = (uint8_t)(mt ? OP_MATCH : OP_MISMATCH);
+            }
+            if (!W.found) {
+                const uint32_t mm = __ballot_sync(0xffffffffu, mt) >> l0;
+                for (int p = 0; p < run; ++p) {
+                    ++W.qcnt; ++W.tcnt; ++W.acnt;
+                    m = ((mm >> p) & 1) ? m + 1 : 0;
+                    if (m == M) { W.found = 1; break; }
+                }
+            }
+            i -= run; j -= run; r += run;
+            continue;
+        }
+        // a single up / left move at (i, j)
+        const uint32_t km = __ballot_sync(0xffffffffu, known);
+        int isup, isleft;
+        if ((km >> l0) & 1) {
+            isup = __shfl_sync(0xffffffffu, (int)up, l0);
+            isleft = __shfl_sync(0xffffffffu, (int)left, l0);
+        } else {
+            const int w = (i - 1) >> 5, b = (i - 1) & 31;
+            const uint2 cur = mat[(size_t)(j - 1 + w) * nw + w];       // outside the window: read it directly
+            isup = (cur.x >> b) & 1; isleft = (cur.y >> b) & 1;
+        }
+        int op;
+        if (isup) { op = OP_QONLY; --i; }
+        else if (isleft) { op = OP_TONLY; --j; }
+        else { op = (S.q[i - 1] == S.t[j - 1]) ? OP_MATCH : OP_MISMATCH; --i; --j; }    // diagonal seen through the direct read
         if (lane == 0) S.rev[r] = (uint8_t)op;
         ++r;
         if (!W.found) {
@@ -225,7 +264,7 @@ __device__ int extend_side(WarpScratch& S, const ExtParams& P, uint2* mat, int l
     return ncol;
 }
 
-__global__ void __launch_bounds__(EXT_WARPS * 32, 2)
+__global__ void __launch_bounds__(EXT_WARPS * 32, 4)
 k_extend(ExtParams P)
 {
     __shared__ WarpScratch s_scratch[EXT_WARPS];
@@ -312,7 +351,8 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* reads, const ExtTask* d_tasks
 {
     if (n_tasks == 0) return NB_OK;
     cudaStream_t st = ctx->stream;
-    int ctas_per_sm = 2;                    // 16 warps per SM
+    static const int kCtas = getenv("NB_EXT_CTAS") ? atoi(getenv("NB_EXT_CTAS")) : 4;
+    int ctas_per_sm = kCtas;                // x 8 warps per SM
     const unsigned grid = NB_SMS * ctas_per_sm;
     const size_t slots = (size_t)grid * EXT_WARPS;
     if (!ctx->ext_mat || ctx->ext_mat_slots < slots) {
