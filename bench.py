@@ -175,6 +175,7 @@ def main():
     import torch
     import torch.distributed as dist
     from necat_b200 import capi, formats
+    from necat_b200 import dist as nbdist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -190,7 +191,7 @@ def main():
     ctx = capi.Context(local_rank)
     popt = capi.default_map_options(**PM_OPTS)
     copt = capi.default_cns_options(**CNS_OPTS)
-    lo, hi = (nreads * rank) // world, (nreads * (rank + 1)) // world
+    lo, hi = nbdist.shard_range(nreads, rank, world)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
@@ -214,17 +215,8 @@ def main():
         stats["map_counters"] = {k: int(getattr(mc, k)) for k, _ in mc._fields_}
         ctx.free_index(idx)
         packed = capi.pack_candidates(cands)
-        if world > 1:
-            # the one exchange step: every rank needs the candidates of all query shards
-            mine = torch.from_numpy(packed.reshape(-1).view(np.int32).copy()).to(dev)
-            counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-            dist.all_gather(counts, torch.tensor([mine.numel()], dtype=torch.int64, device=dev))
-            counts = [int(c.item()) for c in counts]
-            bufs = [torch.empty(max(counts), dtype=torch.int32, device=dev) for _ in range(world)]
-            pad = torch.zeros(max(counts), dtype=torch.int32, device=dev)
-            pad[:mine.numel()] = mine
-            dist.all_gather(bufs, pad)
-            packed = np.concatenate([b[:c].cpu().numpy().view(np.uint32).reshape(-1, 7) for b, c in zip(bufs, counts)])
+        # the one exchange step: every rank needs the candidates of all query shards
+        packed = nbdist.all_gather_records(packed, dev, world)
         stats["n_candidates"] = int(packed.shape[0])
         # oc2pcan: every record under its subject and (swapped) under its query; one partition (< 100000 reads)
         part = np.concatenate([packed, formats.swap_roles(packed)])

@@ -1,0 +1,104 @@
+"""CPU: host-side logic -- file formats, candidate regrouping, the C-ABI surface -- no GPU compute."""
+import ctypes as C
+import os
+import re
+import shutil
+
+import numpy as np
+import pytest
+
+import util
+
+
+def test_packeddb_roundtrip(tmp_path):
+    from necat_b200 import formats
+    rng = np.random.default_rng(1)
+    reads = [rng.integers(0, 4, n, dtype=np.uint8) for n in (5, 1, 4097, 33, 1000)]
+    vols = formats.write_workdir(str(tmp_path / "w"), reads, vol_size=4000)
+    assert len(vols) == 2                                  # a volume closes once it holds >= vol_size bases
+    k = 0
+    for p in vols:
+        v = formats.read_volume(p)
+        for i in range(v.nseq):
+            assert np.array_equal(v.sequence(i), reads[k])
+            assert np.array_equal(v.sequence(i, 1), 3 - reads[k][::-1])
+            assert v.name(i) == f"r{k}"
+            k += 1
+    assert k == len(reads)
+
+
+def test_golden_volume_readable_by_both_readers(built, tmp_path):
+    """formats.read_volume and the C host reader see the same reads as the reference's oc2mkdb wrote them."""
+    from necat_b200 import formats
+    v = formats.read_volume(os.path.join(util.GOLDEN, "vol0"))
+    assert v.nseq == 94 and v.db_size == int(v.info["size"].sum())
+    assert v.info["offset"][1] == v.info["size"][0]
+
+
+def test_partition_matches_oc2pcan(built, tmp_path):
+    """formats.partition_records (numpy) == our oc2pcan host == the reference's oc2pcan + loader normalisation."""
+    from necat_b200 import formats
+    wrk = util.golden_workdir(tmp_path)
+    cand = str(tmp_path / "c.bin")
+    shutil.copy(os.path.join(util.GOLDEN, "cand_k15.bin"), cand)
+    rec = formats.read_candidates(cand)
+    both = np.concatenate([rec, formats.swap_roles(rec)])
+    ours = os.path.join(util.BIN_DIR, "oc2pcan")
+    if os.path.exists(ours):
+        util.run([ours, wrk, cand], cwd=str(tmp_path))
+        assert open(cand + ".partitions").read().split() == ["1"]
+        got = formats.read_candidates(cand + ".p0")
+        assert util.same_multiset(got, both)
+    ref = util.ref_bin("oc2pcan")
+    if ref:
+        c2 = str(tmp_path / "c2.bin")
+        shutil.copy(os.path.join(util.GOLDEN, "cand_k15.bin"), c2)
+        util.run([ref, "-t", "1", wrk, c2], cwd=str(tmp_path))
+        assert util.same_multiset(formats.read_candidates(c2 + ".p0"), both)
+    # subject made forward, coordinates mirrored
+    sizes = formats.read_volume(os.path.join(util.GOLDEN, "vol0")).info["size"].astype(np.int64)
+    part = formats.partition_records(rec, sizes)
+    assert part.shape[0] == 2 * rec.shape[0] and np.all((part[:, 0] >> 31) == 0)
+    assert np.all(part[:, 3] <= sizes[part[:, 1]]) and np.all(part[:, 6] <= sizes[part[:, 4]])
+
+
+def test_capi_exports_every_declared_symbol(built):
+    """The shared library loads without a GPU and exports exactly what include/necat_b200.h declares."""
+    from necat_b200 import capi
+    if not os.path.exists(capi.LIB_PATH):
+        pytest.skip("libnecat_b200.so not built (nvcc missing?)")
+    hdr = open(os.path.join(util.ROOT, "include", "necat_b200.h")).read()
+    declared = set(re.findall(r"\b(nb_[a-z_]+)\s*\(", hdr))
+    lib = C.CDLL(capi.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared but not exported"
+    assert declared == set(capi.EXPORTS), (declared ^ set(capi.EXPORTS))
+
+
+def test_no_cpu_fallback(built):
+    """Without a B200 the product path refuses loudly instead of computing on the host."""
+    import torch
+    from necat_b200 import capi
+    if torch.cuda.is_available() or not os.path.exists(capi.LIB_PATH):
+        pytest.skip("needs the library and a machine without GPU")
+    with pytest.raises(capi.NbError, match="no CUDA device|no CPU fallback"):
+        capi.Context(0)
+    p = os.path.join(util.BIN_DIR, "oc2pmov")
+    if os.path.exists(p):
+        import subprocess
+        r = subprocess.run([p, "-j", "0", util.GOLDEN, "0", "/dev/null"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode != 0
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under necat_b200/ or include/ may include, link or execute oracle/ (it is test infrastructure)."""
+    bad = []
+    for base in ("necat_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(util.ROOT, base)):
+            for f in fs:
+                if f.endswith((".c", ".h", ".cu", ".cuh", ".py")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"oracle[/_]|liboracle|necat_oracle", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+    assert "oracle" not in open(os.path.join(util.ROOT, "Makefile")).read()

@@ -1,0 +1,36 @@
+"""CPU: the oracle (CPU restatement) against the golden vectors produced by the unmodified reference
+binaries (tests/golden/make_golden.py).  This is what pins the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+MAN = json.load(open(os.path.join(util.GOLDEN, "manifest.json")))
+
+
+@pytest.mark.parametrize("name", ["cand_k13.bin", "cand_k15.bin"])
+def test_candidates_match_golden(built, tmp_path, name):
+    from necat_b200 import formats
+    wrk = util.golden_workdir(tmp_path)
+    out = str(tmp_path / "o.bin")
+    util.run([util.ORACLE_CLI, "pmov"] + MAN[name]["options"].split() + [wrk, "0", out], cwd=str(tmp_path))
+    got = formats.canonical_records(formats.read_candidates(out))
+    exp = formats.read_candidates(os.path.join(util.GOLDEN, name))
+    assert exp.shape[0] == MAN[name]["records"] > 100
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("f,mode", [("0", "1"), ("0", "0"), ("1", "0")])
+def test_consensus_matches_golden(built, tmp_path, f, mode):
+    """mode 1 = klib introsort emulated (what the reference binary does), mode 0 = acceptance-order
+    weight sums (what the GPU does): both reproduce the reference FASTA."""
+    wrk = util.golden_workdir(tmp_path)
+    cand = os.path.join(util.GOLDEN, "cand_k15.bin")
+    opts = MAN[f"cns_f{f}"]["options"].split()
+    util.run([util.ORACLE_CLI, "cns"] + opts + ["-M", mode, wrk, cand, "cns.fa", "raw.fa"], cwd=str(tmp_path))
+    assert util.fasta_canon(str(tmp_path / "cns.fa")) == util.golden_fasta(f"cns_f{f}")
+    assert util.fasta_canon(str(tmp_path / "raw.fa")) == util.golden_fasta(f"raw_f{f}")
+    assert len(util.golden_fasta(f"cns_f{f}")) == MAN[f"cns_f{f}"]["records"] > 50

@@ -1,0 +1,32 @@
+"""CPU: the oracle against the reference binaries run here (oracle/_ref; skipped where they are absent).
+Complements the golden vectors with fresh seeded inputs, k = 13 keeps the reference's dense table small."""
+import os
+
+import pytest
+
+import util
+
+needs_ref = pytest.mark.skipif(util.ref_bin("oc2pmov") is None, reason="oracle/_ref not built (needs /root/reference)")
+
+PM13 = "-k 13 -z 10 -q 100 -b 2000 -s 3 -n 500 -a 1000 -d 0.25 -e 0.5 -m 500 -t 2 -j 0 -u 1 -i 1"
+
+
+@needs_ref
+@pytest.mark.parametrize("gen", [dict(genome=50_000, depth=20, seed=51, err=0.12),
+                                 dict(genome=40_000, depth=25, seed=52, err=0.10, repeat_len=2000, repeat_copies=5, n_repeats=2)])
+def test_pipeline_matches_reference(built, tmp_path, gen):
+    import shutil
+    wrk, _ = util.make_workdir(tmp_path, **gen)
+    r = util.run_pmov(util.ref_bin("oc2pmov"), PM13, wrk, 0, str(tmp_path / "r.bin"))
+    o = util.run_pmov(util.ORACLE_CLI, PM13, wrk, 0, str(tmp_path / "o.bin"))
+    assert r.shape[0] > 100 and util.same_multiset(r, o)
+    c = str(tmp_path / "c.bin")
+    shutil.copy(str(tmp_path / "r.bin"), c)
+    util.run([util.ref_bin("oc2pcan"), "-t", "1", wrk, c])
+    cns = "-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0 -r 0 -f 0"
+    util.run([util.ref_bin("oc2cns")] + cns.split() + ["-t", "2", wrk, c, str(tmp_path / "r_cns.fa"), str(tmp_path / "r_raw.fa")])
+    for mode in ("1", "0"):
+        util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", mode, wrk, str(tmp_path / "r.bin"),
+                  str(tmp_path / "o_cns.fa"), str(tmp_path / "o_raw.fa")])
+        assert util.fasta_canon(str(tmp_path / "o_cns.fa")) == util.fasta_canon(str(tmp_path / "r_cns.fa")), f"mode {mode}"
+        assert util.fasta_canon(str(tmp_path / "o_raw.fa")) == util.fasta_canon(str(tmp_path / "r_raw.fa"))

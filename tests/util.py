@@ -59,3 +59,35 @@ def same_multiset(a, b):
 def fasta_canon(path):
     from necat_b200 import formats
     return sorted(formats.read_fasta_records(path))
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_workdir(tmp):
+    """Copies the committed golden volume into tmp/vol (volume_names.txt holds the relative path vol/vol0);
+    commands must run with cwd=tmp."""
+    import shutil
+    d = os.path.join(str(tmp), "vol")
+    os.makedirs(d, exist_ok=True)
+    for f in ("vol0", "volume_names.txt", "reads_info.txt"):
+        shutil.copy(os.path.join(GOLDEN, f), os.path.join(d, f))
+    return "vol"
+
+
+def golden_fasta(name):
+    import gzip
+    data = gzip.open(os.path.join(GOLDEN, name + ".fasta.gz")).read().split(b"\n")
+    return sorted((data[i], data[i + 1]) for i in range(0, len(data) - 1, 2))
+
+
+def smoke_cns(td, wrk, cand):
+    """Used by __graft_entry__.smoke(): oc2pcan + oc2cns on the GPU against the oracle."""
+    import shutil
+    c = os.path.join(td, "cand_cns.bin")
+    shutil.copy(cand, c)
+    run([os.path.join(BIN_DIR, "oc2pcan"), wrk, c])
+    run([os.path.join(BIN_DIR, "oc2cns")] + CNS_SENSITIVE.split() + [wrk, c, os.path.join(td, "g_cns.fa"), os.path.join(td, "g_raw.fa")])
+    run([ORACLE_CLI, "cns"] + CNS_SENSITIVE.split() + ["-M", "0", wrk, cand, os.path.join(td, "o_cns.fa"), os.path.join(td, "o_raw.fa")])
+    assert fasta_canon(os.path.join(td, "g_cns.fa")) == fasta_canon(os.path.join(td, "o_cns.fa")), "cns.fasta mismatch vs oracle"
+    assert fasta_canon(os.path.join(td, "g_raw.fa")) == fasta_canon(os.path.join(td, "o_raw.fa")), "raw.fasta mismatch vs oracle"
