@@ -228,6 +228,7 @@ def main():
         t = ctx.timings(); stats["extend_ms"] = t.extend_ms; stats["consensus_ms"] = t.consensus_ms
         cc = ctx.cns_counters()
         stats["cns_counters"] = {k: int(getattr(cc, k)) for k, _ in cc._fields_}
+        seq.free()
         return int(recs["seq_len"][recs["is_raw"] == 0].sum())
 
     def timed(n_steps, upload_each):

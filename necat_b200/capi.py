@@ -80,6 +80,32 @@ class NbError(RuntimeError):
     pass
 
 
+class HostBuffer:
+    """A malloc()ed buffer returned by the library: numpy view without copy, nb_free on release."""
+
+    def __init__(self, L, addr, nbytes):
+        self._L, self._addr, self.nbytes = L, addr, int(nbytes)
+
+    def array(self):
+        if not self.nbytes:
+            return np.zeros(0, np.uint8)
+        return np.frombuffer((C.c_char * self.nbytes).from_address(self._addr), np.uint8)
+
+    def slice(self, off, n):
+        return self.array()[int(off):int(off) + int(n)].tobytes()
+
+    def free(self):
+        if self._addr:
+            self._L.nb_free(C.c_void_p(self._addr))
+            self._addr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def _u64p(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint64))
 
@@ -158,10 +184,9 @@ class Context:
             r = np.frombuffer((C.c_char * (CNS_RECORD.itemsize * n.value)).from_address(out.value), CNS_RECORD).copy()
         else:
             r = np.zeros(0, CNS_RECORD)
-        s = C.string_at(seq.value, nb.value) if nb.value else b""
         self.L.nb_free(out)
-        self.L.nb_free(seq)
-        return r, s
+        # the sequence buffer (hundreds of MB) is handed over without a copy; it is freed with the returned object
+        return r, HostBuffer(self.L, seq.value, nb.value)
 
     def timings(self):
         t = Timings()

@@ -490,7 +490,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
         }
         std::vector<CnsSegment> segs(seg_total);
         std::vector<uint32_t> nseg(dt.size(), 0);
-        std::vector<char> ascii;            // consensus stretches of this chunk, dense
+        const char* ascii = NULL;           // consensus stretches of this chunk, dense (pinned staging buffer)
         std::vector<uint64_t> seg_dense(seg_total, 0);
         uint8_t* d_seq_pool = NULL;
         if (!dt.empty()) {
@@ -509,6 +509,8 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
             if ((rc = D.get(&P.link, link_total))) return rc;
             if ((rc = D.get(&P.bp, level_total))) return rc;
             if ((rc = D.get(&P.rev, level_total))) return rc;
+            const unsigned links_grid = NB_SMS * 4;          // 16 warps per SM
+            if ((rc = D.get(&P.cursor, (size_t)links_grid * CNS_WARPS * CNS_MAX_ALN))) return rc;
             if ((rc = D.get(&P.error_flag, 1))) return rc;
             if ((rc = D.get(&P.counters, 4))) return rc;
             CnsRun* d_runs; uint32_t* d_nrun;
@@ -525,13 +527,48 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
             if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_cns_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             t_prep += ht.lap();
             cudaEventRecord(ctx->ev2, st);
-            k_cns_links<<<NB_SMS * 3, CNS_WARPS * 32, smem, st>>>(P);
-            NB_LAUNCH_CHECK(ctx);
-            const unsigned dp_warps = (unsigned)((dt.size() + P.lanes - 1) / P.lanes);
-            k_cns_dp<<<(dp_warps + 3) / 4, 128, 0, st>>>(P, d_runs, d_nrun);
-            NB_LAUNCH_CHECK(ctx);
-            k_cns_walk<<<(dp_warps + 3) / 4, 128, 0, st>>>(P, d_runs, d_nrun);
-            NB_LAUNCH_CHECK(ctx);
+            // Slices of the length-sorted templates (equal total bases) alternate between two side streams: the
+            // link building of one slice overlaps the latency-bound DP chains of another; the slice with the
+            // longest templates starts first, its DP tail is hidden behind everything else.
+            {
+                static const int kSlices = getenv("NB_CNS_SLICES") ? atoi(getenv("NB_CNS_SLICES")) : 1;
+                int nsl = dt.size() >= 256 ? kSlices : 1;
+                if (nsl < 1) nsl = 1;
+                if (nsl > 64) nsl = 64;
+                uint64_t total_T = 0;
+                for (const auto& ct : dt) total_T += (uint64_t)ct.T;
+                uint32_t* d_next;
+                if ((rc = D.get(&d_next, 64))) return rc;
+                NB_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(uint32_t) * 64, st));
+                NB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[2], st));
+                for (int k = 0; k < 2; ++k) NB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[k], ctx->aux_ev[2], 0));
+                size_t a = 0;
+                uint64_t acc = 0;
+                for (int sl = 0; sl < nsl && a < dt.size(); ++sl) {
+                    size_t b = a;
+                    const uint64_t want = total_T * (uint64_t)(sl + 1) / (uint64_t)nsl;
+                    while (b < dt.size() && (acc < want || sl == nsl - 1)) { acc += (uint64_t)dt[b].T; ++b; }
+                    if (b == a) continue;
+                    cudaStream_t ss = nsl == 1 ? st : ctx->aux[sl & 1];
+                    CnsParams Q = P;
+                    Q.tpl = d_tpl + a; Q.n_tpl = (uint32_t)(b - a); Q.tpl_nseg = P.tpl_nseg + a; Q.next_tpl = d_next + sl;
+                    unsigned lg = (unsigned)((b - a + CNS_WARPS - 1) / CNS_WARPS);
+                    if (lg > links_grid) lg = links_grid;
+                    k_cns_links<<<lg, CNS_WARPS * 32, smem, ss>>>(Q);
+                    NB_LAUNCH_CHECK(ctx);
+                    const unsigned dp_warps = (unsigned)((b - a + Q.lanes - 1) / Q.lanes);
+                    k_cns_dp<<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
+                    NB_LAUNCH_CHECK(ctx);
+                    k_cns_walk<<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
+                    NB_LAUNCH_CHECK(ctx);
+                    a = b;
+                }
+                if (nsl > 1)
+                    for (int k = 0; k < 2; ++k) {
+                        NB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[k], ctx->aux[k]));
+                        NB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->aux_ev[k], 0));
+                    }
+            }
             cudaEventRecord(ctx->ev3, st);
             uint32_t eflag = 0; unsigned long long cnt[4];
             NB_CUDA(ctx, cudaMemcpyAsync(&eflag, P.error_flag, sizeof eflag, cudaMemcpyDeviceToHost, st));
@@ -554,7 +591,8 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
                         seg_dense[dt[x].seg_first + k] = dense;
                         dense += g.len;
                     }
-                ascii.resize(dense);
+                if ((rc = nb_pinned_reserve(ctx, dense + 16))) return rc;
+                ascii = (const char*)ctx->pinned;
                 if (!gsrc.empty()) {
                     uint64_t *d_src, *d_dst; uint32_t* d_len; char* d_out;
                     if ((rc = D.get(&d_src, gsrc.size()))) return rc;
@@ -566,7 +604,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
                     NB_CUDA(ctx, cudaMemcpyAsync(d_len, glen.data(), 4 * gsrc.size(), cudaMemcpyHostToDevice, st));
                     k_gather_ascii<<<NB_SMS * 8, 256, 0, st>>>(d_seq_pool, d_src, d_dst, d_len, (uint32_t)gsrc.size(), d_out);
                     NB_LAUNCH_CHECK(ctx);
-                    NB_CUDA(ctx, cudaMemcpyAsync(ascii.data(), d_out, dense, cudaMemcpyDeviceToHost, st));
+                    NB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, d_out, dense, cudaMemcpyDeviceToHost, st));
                     NB_CUDA(ctx, cudaStreamSynchronize(st));
                     ctx->tm.d2h_bytes += dense;
                 }
@@ -647,7 +685,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
             std::vector<uint16_t>().swap(T.cov);
         }
         if (!so.reserve(so.used)) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
-        run_fills(fills, so.buf, ascii.data(), reads, nthreads);
+        run_fills(fills, so.buf, ascii, reads, nthreads);
         t_rec += ht.lap();
     }
     ctx->tm.extend_ms = ext_ms;

@@ -76,6 +76,13 @@ struct CnsSegment {             // one consensus stretch of >= min_size bases
     uint64_t seq_off;           // into the sequence pool (base codes 0..3)
 };
 
+struct __align__(16) CnsCursor {    // per alignment cursor of k_cns_links (describes column x-1), kept in HBM/L1 per resident warp
+    uint32_t x, qpos;
+    int32_t  last_pos;
+    uint16_t last_node;             // delta << 3 | base of column x-1; 0xffff = none
+    uint8_t  valid, pad_;
+};
+
 struct CnsParams {
     const uint8_t*     pac;
     const CnsTemplate* tpl;
@@ -87,6 +94,7 @@ struct CnsParams {
     uint32_t*          next_tpl;        // work queue of k_cns_links
     CnsPos*            pos;
     CnsLink*           link;
+    CnsCursor*         cursor;          // k_cns_links: [resident warps][CNS_MAX_ALN]
     unsigned long long* bp;             // per level: 5 x 11-bit back pointers
     uint8_t*           rev;
     int                min_cov, min_size;
@@ -96,12 +104,6 @@ struct CnsParams {
 };
 
 struct CnsWarpShared {
-    // per alignment cursor (describes column x-1; warp-uniform reads)
-    uint32_t x[CNS_MAX_ALN];
-    uint32_t qpos[CNS_MAX_ALN];
-    int32_t  last_pos[CNS_MAX_ALN];
-    uint16_t last_node[CNS_MAX_ALN];    // delta << 3 | base of column x-1; 0xffff = none
-    uint8_t  valid[CNS_MAX_ALN];
     // links of the current tile: per-position singly linked lists
     uint32_t e_key[CNS_POOL];
     double   e_w[CNS_POOL];
@@ -128,6 +130,7 @@ k_cns_links(CnsParams P)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1, le_mask = lt_mask | (1u << lane);
     CnsWarpShared& S = reinterpret_cast<CnsWarpShared*>(cns_smem)[wid];
+    CnsCursor* CU = P.cursor + ((size_t)blockIdx.x * CNS_WARPS + wid) * CNS_MAX_ALN;
     unsigned long long n_cols_total = 0, n_links_total = 0;
 
     for (;;) {
@@ -156,15 +159,16 @@ k_cns_links(CnsParams P)
                 carry = __clz(~ins);                               // ones at the high end (inner runs are < 32)
             }
             if (lane == 0) {
-                S.valid[a] = (uint8_t)!bad;
-                S.x[a] = 0; S.qpos[a] = (uint32_t)AL[a].qstart; S.last_pos[a] = AL[a].toff - 1; S.last_node[a] = 0xffff;
+                CnsCursor c; c.x = 0; c.qpos = (uint32_t)AL[a].qstart; c.last_pos = AL[a].toff - 1; c.last_node = 0xffff;
+                c.valid = (uint8_t)!bad; c.pad_ = 0;
+                CU[a] = c;
             }
         }
         // ---- 1. coverage
         for (int t = lane; t <= T; t += 32) { CnsPos z; z.start = 0; z.cov = 0; z.flags = 0; z.first_level = 0; pos[t] = z; }
         __syncwarp();
         for (int a = lane; a < A; a += 32)
-            if (S.valid[a]) { atomicAdd(&pos[AL[a].toff].cov, 1); atomicAdd(&pos[AL[a].tend].cov, -1); }
+            if (CU[a].valid) { atomicAdd(&pos[AL[a].toff].cov, 1); atomicAdd(&pos[AL[a].tend].cov, -1); }
         __syncwarp();
         {
             int carry = 0;
@@ -218,16 +222,17 @@ k_cns_links(CnsParams P)
             S.head[lane] = 0xffffu;
             __syncwarp();
             for (int a = 0; a < A; ++a) {
-                if (!S.valid[a]) continue;
                 if (AL[a].toff >= t1 || AL[a].tend <= t0) continue;
+                const CnsCursor cu = CU[a];
+                if (!cu.valid) continue;
                 const uint8_t* ops = AL[a].ops;
                 const int n = AL[a].aln_size;
                 const uint64_t qso = AL[a].qseq_off;
                 const int qlen = AL[a].qlen, qdir = AL[a].qdir;
                 const double w = AL[a].weight;
-                uint32_t x = S.x[a], qp = S.qpos[a];
-                int last_pos = S.last_pos[a];
-                uint32_t last_node = S.last_node[a];
+                uint32_t x = cu.x, qp = cu.qpos;
+                int last_pos = cu.last_pos;
+                uint32_t last_node = cu.last_node;
                 while (x < (uint32_t)n) {
                     const uint32_t c = x + lane;
                     const bool ok = c < (uint32_t)n;
@@ -280,7 +285,7 @@ k_cns_links(CnsParams P)
                     __syncwarp();
                     if (n_take < 32) break;
                 }
-                if (lane == 0) { S.x[a] = x; S.qpos[a] = qp; S.last_pos[a] = last_pos; S.last_node[a] = (uint16_t)last_node; }
+                if (lane == 0) { CnsCursor c; c.x = x; c.qpos = qp; c.last_pos = last_pos; c.last_node = (uint16_t)last_node; c.valid = 1; c.pad_ = 0; CU[a] = c; }
                 __syncwarp();
             }
             if (S.pool_used > CNS_POOL) { fail |= 2; break; }

@@ -20,6 +20,10 @@ struct nb_ctx {
     nb_map_counters mc;
     nb_cns_counters cc;
     cudaEvent_t  ev0, ev1, ev2, ev3;
+    cudaStream_t aux[2];         // side streams: slices of the consensus pipeline overlap (links of one, DP chain of another)
+    cudaEvent_t  aux_ev[3];
+    void*        pinned;         // pinned host staging buffer for large device-to-host copies
+    size_t       pinned_bytes;
     void*        ext_mat;        // walk-back scratch of the extension kernel (kept across calls)
     size_t       ext_mat_slots;
     void*        dev_cache;      // NbDevCache*: device blocks kept for reuse (cudaMalloc/cudaFree are slow and synchronising)
@@ -53,6 +57,7 @@ extern char g_nb_err[512];
 int  nb_dev_alloc(nb_ctx* ctx, void** p, size_t bytes);
 void nb_dev_release(nb_ctx* ctx, void* p);
 void nb_dev_cache_destroy(nb_ctx* ctx);
+int  nb_pinned_reserve(nb_ctx* ctx, size_t bytes);      // ctx->pinned holds at least `bytes` afterwards
 
 #ifdef __cplusplus
 #include <vector>

@@ -46,6 +46,17 @@ void nb_dev_release(nb_ctx* ctx, void* p)
     cudaFree(p);
 }
 
+int nb_pinned_reserve(nb_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->pinned_bytes) return NB_OK;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = NULL; ctx->pinned_bytes = 0;
+    const size_t want = bytes + bytes / 4 + (1u << 20);
+    NB_CUDA(ctx, cudaHostAlloc(&ctx->pinned, want, cudaHostAllocDefault));
+    ctx->pinned_bytes = want;
+    return NB_OK;
+}
+
 void nb_dev_cache_destroy(nb_ctx* ctx)
 {
     if (!ctx || !ctx->dev_cache) return;
@@ -93,6 +104,8 @@ extern "C" int nb_ctx_create(int device, nb_ctx** out)
     NB_CUDA(NULL, cudaEventCreate(&c->ev1));
     NB_CUDA(NULL, cudaEventCreate(&c->ev2));
     NB_CUDA(NULL, cudaEventCreate(&c->ev3));
+    for (int i = 0; i < 2; ++i) NB_CUDA(NULL, cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) NB_CUDA(NULL, cudaEventCreateWithFlags(&c->aux_ev[i], cudaEventDisableTiming));
     *out = c;
     return NB_OK;
 }
@@ -107,8 +120,11 @@ extern "C" void nb_ctx_destroy(nb_ctx* c)
     cudaEventDestroy(c->ev2);
     cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->stream);
+    for (int i = 0; i < 2; ++i) cudaStreamDestroy(c->aux[i]);
+    for (int i = 0; i < 3; ++i) cudaEventDestroy(c->aux_ev[i]);
     if (c->ext_mat) cudaFree(c->ext_mat);
     nb_dev_cache_destroy(c);
+    if (c->pinned) cudaFreeHost(c->pinned);
     free(c);
 }
 
