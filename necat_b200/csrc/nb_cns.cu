@@ -44,6 +44,7 @@ struct Tpl {
     double cutoff;
     int num_can, num_ovlps;
     std::vector<uint16_t> cov;
+    int n_below;                // positions whose coverage is still below max_cov
     std::vector<int> used;
     std::vector<Accepted> acc;
     std::vector<size_t> request; // candidate indices to extend in the next round
@@ -84,11 +85,13 @@ inline bool cov_full(const Tpl& t, int from, int to, int max_cov)   // consensus
     for (int i = from; i < to; ++i) if (t.cov[i] < max_cov) return false;
     return true;
 }
-inline void accept(Tpl& t, size_t ci, const nb_alignment& a)
+inline void accept(Tpl& t, size_t ci, const nb_alignment& a, int max_cov)
 {
     Accepted ac; ac.can = (int)ci; ac.weight = cns_weight(ident_of(a));
     t.acc.push_back(ac);
-    for (int i = a.toff; i < a.tend; ++i) ++t.cov[i];
+    int reached = 0;
+    for (int i = a.toff; i < a.tend; ++i) reached += (++t.cov[i] == max_cov);
+    t.n_below -= reached;
 }
 
 // Replays consensus_one_read for one template as far as the available extension results allow.
@@ -150,7 +153,7 @@ void replay(Tpl& t, std::vector<Can>& cans, const std::vector<nb_alignment>& res
                 if (ident_of(a) < t.cutoff) continue;
                 if (!mapping_range_ok(a.qoff, a.qend, c[p].qsize, a.toff, a.tend, t.T, o.min_align_size, o.mapping_ratio)) continue;
                 ++t.num_ovlps;
-                accept(t, p, a);
+                accept(t, p, a, o.max_cov);
                 set_used(t, c[p].qid);
             }
             t.num_can = (int)t.next;
@@ -161,7 +164,7 @@ void replay(Tpl& t, std::vector<Can>& cans, const std::vector<nb_alignment>& res
     // main loop, consensus_one_read.c:316-372
     for (;;) {
         if (!t.in_window) {
-            if (t.next >= t.n || cov_full(t, 0, t.T, o.max_cov)) { t.stage = 2; return; }
+            if (t.next >= t.n || t.n_below == 0) { t.stage = 2; return; }     // region_coverage_is_full(0, T)
             t.win_i = t.next;
             t.win_to = std::min(t.next + 50, t.n);
             t.next = t.win_to;
@@ -187,7 +190,7 @@ void replay(Tpl& t, std::vector<Can>& cans, const std::vector<nb_alignment>& res
             if (id < t.cutoff && !full_cov_ovlp(a.qoff, a.qend, c[i].qsize, a.toff, a.tend, t.T, 5000, 100)) continue;
             if (!mapping_range_ok(a.qoff, a.qend, c[i].qsize, a.toff, a.tend, t.T, o.min_align_size, o.mapping_ratio)) continue;
             ++t.num_ovlps;
-            accept(t, i, a);
+            accept(t, i, a, o.max_cov);
             set_used(t, c[i].qid);
         }
         t.in_window = false;
@@ -375,7 +378,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
         NbDevBuf D(ctx);                            // everything allocated for this chunk
         std::vector<nb_alignment> res;              // results of all rounds of this chunk
         std::vector<const uint8_t*> res_ops;        // device pointer of each result's ops
-        for (size_t t = c0; t < c1; ++t) tpls[t].cov.assign((size_t)tpls[t].T + 1, 0);
+        for (size_t t = c0; t < c1; ++t) { tpls[t].cov.assign((size_t)tpls[t].T + 1, 0); tpls[t].n_below = o.max_cov > 0 ? tpls[t].T : 0; }
         // round 0 requests: the first 50 candidates (phase 1), or the first window with -u 1
         for (size_t t = c0; t < c1; ++t) {
             Tpl& T = tpls[t];
@@ -509,7 +512,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
             if ((rc = D.get(&P.link, link_total))) return rc;
             if ((rc = D.get(&P.bp, level_total))) return rc;
             if ((rc = D.get(&P.rev, level_total))) return rc;
-            const unsigned links_grid = NB_SMS * 4;          // 16 warps per SM
+            const unsigned links_grid = NB_SMS * 5;          // 20 warps per SM (shared-memory bound)
             if ((rc = D.get(&P.cursor, (size_t)links_grid * CNS_WARPS * CNS_MAX_ALN))) return rc;
             if ((rc = D.get(&P.error_flag, 1))) return rc;
             if ((rc = D.get(&P.counters, 4))) return rc;

@@ -30,7 +30,7 @@
 
 #define CNS_MAX_ALN 320         // >= MAX_EXAMINED_CAN (consensus_aux.h:15)
 #define CNS_WARPS 4
-#define CNS_POOL 1024           // links per tile
+#define CNS_POOL 768            // links per tile (shared-memory pool; ~115 used on average)
 #define CNS_NOPRED 0xffffffffu
 
 struct CnsAln {                 // one accepted alignment, in acceptance order
@@ -63,7 +63,7 @@ struct __align__(16) CnsPos {   // one template position
 };
 
 struct __align__(16) CnsLink {  // one link = (node, predecessor node), sorted by key inside a position
-    uint32_t key;               // delta(8) << 24 | base(3) << 20 | pred base(3) << 16 | pred rank(16)
+    uint32_t key;               // delta(8) << 24 | node-start << 23 | base(3) << 20 | level-start << 19 | pred base(3) << 16 | pred rank(16)
     uint32_t pred;              // index of the predecessor node's first link, CNS_NOPRED = no scored predecessor
     double   w;                 // summed weight; k_cns_dp overwrites the first link of a node with the node score
 };
@@ -327,12 +327,15 @@ k_cns_links(CnsParams P)
                         if (lane > 0) {
                             for (int e = (int)S.head[lane - 1]; e != 0xffff; e = S.e_next[e]) less += (S.e_key[e] >> 20) < want;
                         } else {
-                            for (uint32_t q = 0; q < prev_cnt; ++q) less += (link[prev_start + q].key >> 20) < want;
+                            for (uint32_t q = 0; q < prev_cnt; ++q) less += ((link[prev_start + q].key >> 20) & 0xff7u) < want;
                         }
                         pred = pv_start + less;
                     }
                 }
-                CnsLink L; L.key = bk; L.pred = pred; L.w = S.e_w[be];
+                // bit 23: first link of its node, bit 19: first link of its delta level (spares k_cns_dp the key compares)
+                const uint32_t fl_node = (i == 0 || (bk >> 20) != (lastkey >> 20)) ? (1u << 23) : 0u;
+                const uint32_t fl_level = (i == 0 || (bk >> 24) != (lastkey >> 24)) ? (1u << 19) : 0u;
+                CnsLink L; L.key = bk | fl_node | fl_level; L.pred = pred; L.w = S.e_w[be];
                 link[my_start + i] = L;
                 lastkey = bk;
             }
@@ -380,7 +383,7 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
     uint32_t e = 0, fl = 0;                     // links [.., e) of position t
     double pen = 0.0;
     bool have_node = false, have_level = false;
-    uint32_t cur_d = 0, cur_db = 0, node_first = 0, best_rank = 0, code = 7;
+    uint32_t cur_d = 0, cur_b = 0, node_first = 0, best_rank = 0, code = 7;
     double best = -1.0;
     bool chosen = false;
     unsigned long long packed = 0;
@@ -395,8 +398,8 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
             if (have_node) {
                 const double ns = chosen ? best : -1.0;
                 link[node_first].w = ns;                                // node score lives in the node's first link
-                packed |= (unsigned long long)(chosen ? code : 7u) << (11 * (cur_db & 7));
-                if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)(cur_db & 7); g_t = t; g_delta = (int)cur_d; }
+                packed |= (unsigned long long)(chosen ? code : 7u) << (11 * cur_b);
+                if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)cur_d; }
                 have_node = false;
             }
             if (have_level) {
@@ -426,20 +429,23 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
         lr_next = *reinterpret_cast<const uint4*>(link + x + 1);        // capacity leaves room past the last link
         const uint32_t key = lr.x, pred = lr.y;
         const double w = __hiloint2double((int)lr.w, (int)lr.z);
-        const uint32_t db = key >> 20, d = key >> 24;                   // db = delta << 4 | base
-        if (have_node && db != cur_db) {
-            const double ns = chosen ? best : -1.0;
-            link[node_first].w = ns;
-            packed |= (unsigned long long)(chosen ? code : 7u) << (11 * (cur_db & 7));
-            if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)(cur_db & 7); g_t = t; g_delta = (int)cur_d; }
-            have_node = false;
+        const uint32_t d = key >> 24, b = (key >> 20) & 7;
+        if ((key >> 23) & 1) {                                          // a new node starts: close the previous one
+            if (have_node) {
+                const double ns = chosen ? best : -1.0;
+                link[node_first].w = ns;
+                packed |= (unsigned long long)(chosen ? code : 7u) << (11 * cur_b);
+                if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)cur_d; }
+            }
+            if ((key >> 19) & 1) {                                      // ... and a new delta level
+                if (have_level) {
+                    if (level < TP.level_cap) bp[level] = packed; else fail |= 1;
+                    ++level;
+                }
+                have_level = true; packed = 0;
+            }
+            have_node = true; cur_b = b; cur_d = d; node_first = x; best = -1.0; best_rank = 0; code = 7; chosen = false;
         }
-        if (have_level && d != cur_d) {
-            if (level < TP.level_cap) bp[level] = packed; else fail |= 1;
-            ++level; have_level = false;
-        }
-        if (!have_level) { have_level = true; cur_d = d; packed = 0; }
-        if (!have_node) { have_node = true; cur_db = db; node_first = x; best = -1.0; best_rank = 0; code = 7; chosen = false; }
         const uint32_t rank = key & 0xffff, pb = (key >> 16) & 7;
         double sc = __dsub_rn(w, pen);
         if (pred != CNS_NOPRED) sc = __dadd_rn(sc, link[pred].w);      // never-scored predecessors count 0 (cns_aux.c:63-70)
