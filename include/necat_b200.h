@@ -116,6 +116,28 @@ int  nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, int r
 void nb_pack_candidate(const nb_candidate* c, nb_packed_candidate* p);  /* gapped_candidate.c:13-28 */
 void nb_free(void* p);
 
+/* 96-byte M4Record, common/m4_record.h:10-25 (binary form of oc2pmov -j 1 -u 1) */
+typedef struct {
+    int32_t  qid, qdir;
+    uint64_t qoff, qend, qext, qsize;
+    int32_t  sid, sdir;
+    uint64_t soff, send, sext, ssize;
+    double   ident_perc;
+    int32_t  vscore;
+    int32_t  pad_;
+} nb_m4_record;
+
+/*
+ * ALN mode of pm_worker.c:84-161 (oc2pmov -j 1): the candidates of every read are sorted by
+ * (score desc, qdir, sid, qoff, soff), cut to opt->num_candidates, and extended from their seed with
+ * onc_align (error opt->error, tail match length 1, minimum size opt->align_size_cutoff) unless the seed
+ * lies inside an alignment already reported for the same strand and subject (common/map_aux.c:4-18).
+ * Query coordinates of reverse-strand records are flipped to the forward strand (pm_worker.c:73-78).
+ */
+int  nb_map_volume_aln(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, int ref_start_id,
+                       const nb_volume* reads, int read_start_id, uint64_t read_lo, uint64_t read_hi,
+                       const nb_map_options* opt, nb_m4_record** out, uint64_t* n_out);
+
 /* Work counters of the last nb_map_volume call (roofline arithmetic). */
 typedef struct {
     uint64_t n_units;       /* (read, strand) pairs */

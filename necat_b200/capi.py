@@ -51,7 +51,7 @@ CNS_RECORD = np.dtype([("id", "<i4"), ("left", "<i4"), ("right", "<i4"), ("org_s
 
 EXPORTS = ["nb_ctx_create", "nb_ctx_destroy", "nb_last_error", "nb_version", "nb_launch_count", "nb_get_timings",
            "nb_volume_upload", "nb_volume_free", "nb_index_build", "nb_index_free", "nb_index_stats",
-           "nb_index_download", "nb_map_options_default", "nb_map_volume", "nb_pack_candidate", "nb_free",
+           "nb_index_download", "nb_map_options_default", "nb_map_volume", "nb_map_volume_aln", "nb_pack_candidate", "nb_free",
            "nb_get_map_counters", "nb_cns_options_default", "nb_extend_candidates", "nb_consensus_job",
            "nb_consensus_job_sharded",
            "nb_get_cns_counters"]

@@ -432,7 +432,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
             if ((rc = D.get(&d_ops, pool + 64))) return rc;
             NB_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ExtTask) * tasks.size(), cudaMemcpyHostToDevice, st));
             cudaEventRecord(ctx->ev0, st);
-            rc = nb_run_extension(ctx, reads, d_tasks, (uint32_t)tasks.size(), d_res, d_ops, o.error, o.min_align_size, 4 /* ONC_TAIL_MATCH_LEN_LONG */);
+            rc = nb_run_extension(ctx, reads, reads, d_tasks, (uint32_t)tasks.size(), d_res, d_ops, o.error, o.min_align_size, 4 /* ONC_TAIL_MATCH_LEN_LONG */);
             if (rc) return rc;
             cudaEventRecord(ctx->ev1, st);
             const size_t r0 = res.size();

@@ -279,7 +279,7 @@ k_extend(ExtParams P)
         ti = __shfl_sync(0xffffffffu, ti, 0);
         if (ti >= P.n_tasks) break;
         const ExtTask T = P.tasks[ti];
-        SeqView qv; qv.pac = P.pac; qv.off = P.seq_off[T.qid]; qv.len = (int)P.seq_len[T.qid]; qv.strand = T.qdir;
+        SeqView qv; qv.pac = P.q_pac; qv.off = P.q_off[T.qid]; qv.len = (int)P.q_len[T.qid]; qv.strand = T.qdir;
         SeqView tv; tv.pac = P.pac; tv.off = P.seq_off[T.sid]; tv.len = (int)P.seq_len[T.sid]; tv.strand = 0;
         uint8_t* ops = P.ops + T.ops_base;
         int QS = T.qoff, TS = T.soff;
@@ -346,8 +346,8 @@ k_extend(ExtParams P)
 }
 
 // Launches the persistent extension kernel over d_tasks.  d_ops must hold every task's region.
-int nb_run_extension(nb_ctx* ctx, const nb_volume* reads, const ExtTask* d_tasks, uint32_t n_tasks, nb_alignment* d_results,
-                     uint8_t* d_ops, double error, int min_align_size, int tail_match_len)
+int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* templates, const ExtTask* d_tasks, uint32_t n_tasks,
+                     nb_alignment* d_results, uint8_t* d_ops, double error, int min_align_size, int tail_match_len)
 {
     if (n_tasks == 0) return NB_OK;
     cudaStream_t st = ctx->stream;
@@ -369,7 +369,8 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* reads, const ExtTask* d_tasks
     NB_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(uint32_t), st));
     NB_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 4, st));
     ExtParams P;
-    P.pac = reads->d_pac; P.seq_off = reads->d_off; P.seq_len = reads->d_len;
+    P.pac = templates->d_pac; P.seq_off = templates->d_off; P.seq_len = templates->d_len;
+    P.q_pac = queries->d_pac; P.q_off = queries->d_off; P.q_len = queries->d_len;
     P.tasks = d_tasks; P.n_tasks = n_tasks; P.results = d_results; P.ops = d_ops; P.mat = s_mat;
     P.next_task = d_next; P.counters = d_cnt;
     P.error = error; P.min_align_size = min_align_size; P.tail_match_len = tail_match_len; P.block_size = 512;
@@ -445,7 +446,7 @@ extern "C" int nb_extend_candidates(nb_ctx* ctx, const nb_volume* reads, const n
     NB_CUDA(ctx, cudaMalloc(&d_ops, pool + 64));
     NB_CUDA(ctx, cudaMemcpyAsync(d_tasks, h_tasks, sizeof(ExtTask) * n, cudaMemcpyHostToDevice, st));
     cudaEventRecord(ctx->ev0, st);
-    int rc = nb_run_extension(ctx, reads, d_tasks, (uint32_t)n, d_res, d_ops, error, min_align_size, tail_match_len);
+    int rc = nb_run_extension(ctx, reads, reads, d_tasks, (uint32_t)n, d_res, d_ops, error, min_align_size, tail_match_len);
     cudaEventRecord(ctx->ev1, st);
     if (rc) { cudaFree(d_tasks); cudaFree(d_res); cudaFree(d_ops); free(h_tasks); return rc; }
     nb_alignment* h_res = (nb_alignment*)malloc(sizeof(nb_alignment) * n);

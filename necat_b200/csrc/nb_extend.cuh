@@ -24,9 +24,12 @@ struct ExtTask {
 #define EXT_MAT_WORDS 26        // 32-bit words per column (832 / 32)
 
 struct ExtParams {
-    const uint8_t*  pac;
+    const uint8_t*  pac;            // template (subject) volume
     const uint64_t* seq_off;
     const uint32_t* seq_len;
+    const uint8_t*  q_pac;          // query volume (the same one in oc2cns, possibly another in oc2pmov -j 1)
+    const uint64_t* q_off;
+    const uint32_t* q_len;
     const ExtTask*  tasks;
     uint32_t        n_tasks;
     nb_alignment*   results;
@@ -42,5 +45,5 @@ struct ExtParams {
 
 #define EXT_MAT_STRIDE ((size_t)(EXT_MAX_BLK + 32) * EXT_MAT_WORDS)
 
-int nb_run_extension(nb_ctx* ctx, const nb_volume* reads, const ExtTask* d_tasks, uint32_t n_tasks,
+int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* templates, const ExtTask* d_tasks, uint32_t n_tasks,
                      nb_alignment* d_results, uint8_t* d_ops, double error, int min_align_size, int tail_match_len);

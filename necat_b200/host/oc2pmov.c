@@ -7,8 +7,9 @@
  * (28-byte candidate records with -u 1, candidate text with -u 0).  Options may
  * come in any order and default to sDefaultPairwiseMapingOptions
  * (map_options.c:12-28) -- the reference leaves them uninitialised.
- * CAN mode (-j 0) is what necat.pl uses (necat.pl:31-32,197); -j 1 (M4 output)
- * is not implemented yet and is refused loudly.
+ * CAN mode (-j 0) is what necat.pl uses (necat.pl:31-32,197); ALN mode (-j 1)
+ * writes M4 records: text (m4_record.h:72-124, read names instead of ids with
+ * -i 1) or the raw 96-byte struct with -u 1.
  */
 #include <getopt.h>
 #include <stdlib.h>
@@ -54,7 +55,7 @@ int main(int argc, char* argv[])
     const char* wrk_dir = argv[argc - 3];
     const int vid = atoi(argv[argc - 2]);
     const char* output = argv[argc - 1];
-    if (o.job != 0) NBH_ERROR("-j %d (alignment / M4 output) is not implemented in the B200 build yet; necat.pl uses -j 0", o.job);
+    if (o.job != 0 && o.job != 1) NBH_ERROR("invalid job -j %d", o.job);
 
     nbh_volumes_info vi;
     if (nbh_volumes_info_load(wrk_dir, &vi)) NBH_ERROR("cannot read volume info in '%s'", wrk_dir);
@@ -89,6 +90,28 @@ int main(int argc, char* argv[])
             if (nb_volume_upload(ctx, rd.pac, rd.db_size, rd.offset, rd.size, rd.nseq, &drd)) NBH_ERROR("%s", nb_last_error(ctx));
         }
         const uint64_t nreads = v == vid ? ref.nseq : rd.nseq;
+        if (o.job == 1) {                                   /* ALN mode, pm_worker.c:138-161 */
+            const nbh_volume* qv = (v == vid) ? &ref : &rd;
+            nb_m4_record* m4 = NULL;
+            uint64_t nm4 = 0;
+            if (nb_map_volume_aln(ctx, idx, dref, vi.start_id[vid], drd, vi.start_id[v], 0, nreads, &o, &m4, &nm4))
+                NBH_ERROR("%s", nb_last_error(ctx));
+            if (o.binary_output) {
+                if (fwrite(m4, sizeof(nb_m4_record), nm4, out) != nm4) NBH_ERROR("write to '%s' failed", output);
+            } else {
+                for (uint64_t i = 0; i < nm4; ++i) {
+                    const nb_m4_record* m = &m4[i];
+                    if (o.use_hdr_as_id)
+                        fprintf(out, "%s\t%s\t", qv->hdr + qv->hdr_offset[m->qid - vi.start_id[v]],
+                                ref.hdr + ref.hdr_offset[m->sid - vi.start_id[vid]]);
+                    else fprintf(out, "%d\t%d\t", m->qid, m->sid);
+                    fprintf(out, "%.2f\t%d\t%d\t%lu\t%lu\t%lu\t%d\t%lu\t%lu\t%lu\n", m->ident_perc, m->vscore, m->qdir,
+                            (unsigned long)m->qoff, (unsigned long)m->qend, (unsigned long)m->qsize, m->sdir,
+                            (unsigned long)m->soff, (unsigned long)m->send, (unsigned long)m->ssize);
+                }
+            }
+            nb_free(m4);
+        } else {
         nb_candidate* cans = NULL;
         uint64_t ncan = 0;
         if (nb_map_volume(ctx, idx, dref, vi.start_id[vid], drd, vi.start_id[v], 0, nreads, &o, &cans, &ncan))
@@ -107,6 +130,7 @@ int main(int argc, char* argv[])
             }
         }
         nb_free(cans);
+        }
         if (v != vid) { nb_volume_free(ctx, drd); nbh_volume_free(&rd); }
         NBH_LOG("'%s' takes %.2lf secs.", job, nbh_now() - t0);
     }

@@ -125,6 +125,24 @@ void o_map_volume(const OVolume* reads, int read_start_id, const OVolume* ref,
                   int ref_start_id, const OIndex* idx, const OMapOptions* opt,
                   OCandVec* out);
 
+/* common/m4_record.h:10-25 (96-byte struct, 4 bytes of tail padding) */
+typedef struct {
+    int32_t  qid, qdir;
+    uint64_t qoff, qend, qext, qsize;
+    int32_t  sid, sdir;
+    uint64_t soff, send, sext, ssize;
+    double   ident_perc;
+    int32_t  vscore;
+    int32_t  pad_;
+} OM4Record;
+typedef struct { OM4Record* a; size_t n, m; } OM4Vec;
+
+/* pm_worker.c:84-161 (ALN mode, -j 1) for every read of `reads`: candidates sorted, truncated to -n,
+ * extended with onc_align (tail match 1) unless their seed lies inside an alignment already reported
+ * for the same (strand, subject) (common/map_aux.c:4-18); ids made global. */
+void o_map_volume_aln(const OVolume* reads, int read_start_id, const OVolume* ref,
+                      int ref_start_id, const OIndex* idx, const OMapOptions* opt, OM4Vec* out);
+
 /* -------------------------------------------------------------- extension */
 
 typedef struct {

@@ -52,6 +52,24 @@ static int run_pmov(int argc, char** argv)
     for (int v = vid; v < vi.num_volumes; ++v) {
         OVolume reads;
         if (o_volume_load(vi.names[v], &reads)) { fprintf(stderr, "cannot load %s\n", vi.names[v]); return 1; }
+        if (o.job == 1) {                                   /* ALN mode: M4 records (pm_worker.c:138-161) */
+            OM4Vec mv = {0, 0, 0};
+            o_map_volume_aln(&reads, vi.start_id[v], &ref, vi.start_id[vid], &idx, &o, &mv);
+            for (size_t i = 0; i < mv.n; ++i) {
+                const OM4Record* m = &mv.a[i];
+                if (o.binary_output) { fwrite(m, sizeof *m, 1, out); continue; }
+                if (o.use_hdr_as_id)                          /* m4_record.h:99-124 */
+                    fprintf(out, "%s\t%s\t", reads.hdr + reads.seq[m->qid - vi.start_id[v]].hdr_offset,
+                            ref.hdr + ref.seq[m->sid - vi.start_id[vid]].hdr_offset);
+                else fprintf(out, "%d\t%d\t", m->qid, m->sid);
+                fprintf(out, "%.2f\t%d\t%d\t%lu\t%lu\t%lu\t%d\t%lu\t%lu\t%lu\n", m->ident_perc, m->vscore, m->qdir,
+                        (unsigned long)m->qoff, (unsigned long)m->qend, (unsigned long)m->qsize, m->sdir,
+                        (unsigned long)m->soff, (unsigned long)m->send, (unsigned long)m->ssize);
+            }
+            free(mv.a);
+            o_volume_free(&reads);
+            continue;
+        }
         OCandVec cv = {0, 0, 0};
         o_map_volume(&reads, vi.start_id[v], &ref, vi.start_id[vid], &idx, &o, &cv);
         for (size_t i = 0; i < cv.n; ++i) {

@@ -749,3 +749,64 @@ void o_map_volume(const OVolume* reads, int read_start_id, const OVolume* ref,
     free(buf);
     o_finder_free(f);
 }
+
+/* ---------------------------------------------------------------- ALN mode */
+
+void o_map_volume_aln(const OVolume* reads, int read_start_id, const OVolume* ref,
+                      int ref_start_id, const OIndex* idx, const OMapOptions* opt, OM4Vec* out)
+{
+    OFinder* f = o_finder_new(ref, opt);
+    OAligner* al = o_aligner_new(opt->error);
+    uint64_t maxlen = 0, maxref = 0;
+    for (uint64_t i = 0; i < reads->nseq; ++i) if (reads->seq[i].size > maxlen) maxlen = reads->seq[i].size;
+    for (uint64_t i = 0; i < ref->nseq; ++i) if (ref->seq[i].size > maxref) maxref = ref->seq[i].size;
+    uint8_t* fwd = (uint8_t*)malloc(maxlen + 1);
+    uint8_t* rev = (uint8_t*)malloc(maxlen + 1);
+    uint8_t* sub = (uint8_t*)malloc(maxref + 1);
+    OCandVec one = {0, 0, 0};
+    OM4Record* m4 = NULL; size_t nm4 = 0, mm4 = 0;
+    for (uint64_t i = 0; i < reads->nseq; ++i) {
+        one.n = 0;
+        const int L = (int)reads->seq[i].size;
+        o_extract(reads, i, 0, fwd);
+        o_find_candidates(f, fwd, L, (int)i, 0, read_start_id, ref_start_id, ref, idx, opt, &one);
+        o_extract(reads, i, 1, rev);
+        o_find_candidates(f, rev, L, (int)i, 1, read_start_id, ref_start_id, ref, idx, opt, &one);
+        qsort(one.a, one.n, sizeof(OCandidate), cand_pm_gt);                      /* pm_worker.c:139 */
+        if (one.n > (size_t)opt->num_candidates) one.n = (size_t)opt->num_candidates;
+        nm4 = 0;
+        for (size_t c = 0; c < one.n; ++c) {                                       /* extend_candidates, :28-82 */
+            const OCandidate* k = &one.a[c];
+            int contained = 0;
+            for (size_t x = 0; x < nm4 && !contained; ++x) {                       /* map_aux.c:4-18 */
+                const OM4Record* m = &m4[x];
+                contained = k->qdir == m->qdir && k->sid == m->sid &&
+                            (uint64_t)k->qoff >= m->qoff && (uint64_t)k->qoff <= m->qend &&
+                            (uint64_t)k->soff >= m->soff && (uint64_t)k->soff <= m->send;
+            }
+            if (contained) continue;
+            o_extract(ref, (uint64_t)k->sid, 0, sub);
+            OAlignment A;
+            if (!o_onc_align(al, k->qdir == 0 ? fwd : rev, (int)k->qoff, (int)k->qsize, sub, (int)k->soff, (int)k->ssize,
+                             512, opt->align_size_cutoff, 1, &A)) continue;
+            if (nm4 == mm4) { mm4 = mm4 ? mm4 * 2 : 64; m4 = (OM4Record*)realloc(m4, sizeof(OM4Record) * mm4); }
+            OM4Record* m = &m4[nm4++];
+            memset(m, 0, sizeof *m);
+            m->qid = k->qid; m->sid = k->sid; m->ident_perc = A.ident_perc; m->vscore = k->score; m->qdir = k->qdir;
+            m->qoff = (uint64_t)A.qoff; m->qend = (uint64_t)A.qend; m->qext = (uint64_t)k->qoff; m->qsize = (uint64_t)k->qsize;
+            m->sdir = 0; m->soff = (uint64_t)A.toff; m->send = (uint64_t)A.tend; m->sext = (uint64_t)k->soff; m->ssize = (uint64_t)k->ssize;
+            if (m->qdir == 1) {                                                     /* :73-78 */
+                uint64_t a = m->qsize - m->qend, b = m->qsize - m->qoff;
+                m->qoff = a; m->qend = b;
+            }
+        }
+        for (size_t x = 0; x < nm4; ++x) {
+            m4[x].qid += read_start_id; m4[x].sid += ref_start_id;
+            if (out->n == out->m) { out->m = out->m ? out->m * 2 : 256; out->a = (OM4Record*)realloc(out->a, sizeof(OM4Record) * out->m); }
+            out->a[out->n++] = m4[x];
+        }
+    }
+    free(m4); free(one.a); free(fwd); free(rev); free(sub);
+    o_aligner_free(al);
+    o_finder_free(f);
+}

@@ -10,6 +10,7 @@ Files written:
     cand_k15.bin                             oc2pmov SENSITIVE options (necat.pl:20,32)
     cns_f0.fasta.gz / raw_f0.fasta.gz        oc2pcan + oc2cns CNS_SENSITIVE -r 0 -f 0 on cand_k15.bin
     cns_f1.fasta.gz / raw_f1.fasta.gz        same with -f 1
+    m4_k13.txt.gz                            oc2pmov -j 1 -u 0 -i 1 (M4 text lines, sorted)
     manifest.json                            options, counts, sha256 of the canonical (sorted) outputs
 All outputs are stored in canonical order (records sorted) because the reference's own order varies.
 """
@@ -54,6 +55,13 @@ def main():
             rec = formats.canonical_records(formats.read_candidates(name))
             rec.astype("<u4").tofile(os.path.join(HERE, name))
             man[name] = {"options": opts, "records": int(rec.shape[0]), "sha256": hashlib.sha256(rec.tobytes()).hexdigest()}
+        # ALN mode (M4 text, names as ids): sorted lines
+        m4opts = "-k 13 -z 10 -q 500 -b 2000 -s 3 -n 100 -a 400 -d 0.25 -e 0.5 -m 500 -t 2 -j 1 -u 0 -i 1"
+        subprocess.check_call([os.path.join(ref, "oc2pmov")] + m4opts.split() + ["vol", "0", "m4.txt"], stdout=subprocess.DEVNULL)
+        data = b"".join(sorted(open("m4.txt", "rb").read().splitlines(keepends=True)))
+        with gzip.GzipFile(os.path.join(HERE, "m4_k13.txt.gz"), "wb", mtime=0) as g:
+            g.write(data)
+        man["m4_k13"] = {"options": m4opts, "records": data.count(b"\n"), "sha256": hashlib.sha256(data).hexdigest()}
         for f in ("0", "1"):
             shutil.copy("cand_k15.bin", "c.bin")
             subprocess.check_call([os.path.join(ref, "oc2pcan"), "-t", "1", "vol", "c.bin"], stdout=subprocess.DEVNULL)

@@ -34,3 +34,13 @@ def test_consensus_matches_golden(built, tmp_path, f, mode):
     assert util.fasta_canon(str(tmp_path / "cns.fa")) == util.golden_fasta(f"cns_f{f}")
     assert util.fasta_canon(str(tmp_path / "raw.fa")) == util.golden_fasta(f"raw_f{f}")
     assert len(util.golden_fasta(f"cns_f{f}")) == MAN[f"cns_f{f}"]["records"] > 50
+
+
+def test_m4_matches_golden(built, tmp_path):
+    import gzip
+    wrk = util.golden_workdir(tmp_path)
+    util.run([util.ORACLE_CLI, "pmov"] + MAN["m4_k13"]["options"].split() + [wrk, "0", "o.m4"], cwd=str(tmp_path))
+    got = sorted(open(str(tmp_path / "o.m4"), "rb").read().splitlines())
+    exp = gzip.open(os.path.join(util.GOLDEN, "m4_k13.txt.gz")).read().splitlines()
+    assert len(exp) == MAN["m4_k13"]["records"] > 100
+    assert got == exp
