@@ -13,6 +13,8 @@
 //     monotone) and the reference's loop is replayed over the results.
 #include <algorithm>
 #include <cmath>
+#include <atomic>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -265,6 +267,437 @@ __global__ void k_gather_ascii(const uint8_t* __restrict__ pool, const uint64_t*
 
 }  // namespace
 
+// Shared between the pipeline workers of one job.
+struct JobShared {
+    char*    buf;                       // output sequences: one allocation sized by an upper bound, dense prefix in use
+    uint64_t cap;
+    std::atomic<uint64_t> used;
+    std::vector<uint8_t>* corrected;
+    std::mutex gpu;                     // one chunk at a time submits to the GPU and waits for it: the kernels are sized
+                                        // to fill the machine, running two side by side only makes both slower;
+                                        // what overlaps is the host work of one chunk with the kernels of another
+};
+
+struct ChunkTimes { double replay = 0, gather = 0, ext = 0, prep = 0, kern = 0, rec = 0, wait = 0, ext_wall = 0; float ext_ms = 0, cns_ms = 0; };
+
+// Extension rounds + consensus + records of the templates [c0, c1): everything the GPU does for them runs on the
+// stream of `ctx` (a pipeline worker: its own stream, events, staging buffer and walk-back scratch).
+static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_options& o, std::vector<Tpl>& tpls, std::vector<Can>& cans,
+                         size_t c0, size_t c1, JobShared& sh, std::vector<nb_cns_record>& recs, ChunkTimes& tms, unsigned nthreads)
+{
+    cudaStream_t st = ctx->stream;
+    HostTimer ht;
+    double t_replay = 0, t_gather = 0, t_ext = 0, t_prep = 0, t_kern = 0, t_rec = 0, t_wait = 0;
+    float ext_ms = 0, cns_ms = 0;
+    std::vector<Fill> fills;
+    std::vector<uint8_t>& corrected = *sh.corrected;
+    struct { uint64_t used; } so;
+    so.used = 0;                        // chunk-local offsets; rebased once the chunk knows how many bytes it emits
+    // ---- extension rounds.  The templates of the chunk form up to NB_MAX_WORKERS groups, each driven by its own host
+    //      thread on its own stream; one group at a time holds the GPU (sh.gpu), so the kernels run alone and at full
+    //      width while the other groups replay the accept/skip logic and gather their next requests on the host.
+    struct ExtGroup {
+        size_t t0 = 0, t1 = 0;
+        nb_ctx* wc = NULL;
+        NbDevBuf* D = NULL;                     // the groups' ops pools stay alive until the consensus has read them
+        std::vector<nb_alignment> res;          // results of all rounds of this group
+        std::vector<const uint8_t*> res_ops;    // device pointer of each result's ops
+        ChunkTimes tm;
+        int rc = NB_OK;
+    };
+    for (size_t t = c0; t < c1; ++t) { tpls[t].cov.assign((size_t)tpls[t].T + 1, 0); tpls[t].n_below = o.max_cov > 0 ? tpls[t].T : 0; }
+    // round 0 requests: the first 50 candidates (phase 1), or the first window with -u 1
+    for (size_t t = c0; t < c1; ++t) {
+        Tpl& T = tpls[t];
+        T.request.clear();
+        if (!o.use_fixed_ident_cutoff) for (size_t k = 0; k < T.n && k < 50; ++k) T.request.push_back(k);
+    }
+    const char* env_groups = getenv("NB_CNS_GROUPS");
+    int n_groups = env_groups ? atoi(env_groups) : 3;
+    const char* env_gmin = getenv("NB_CNS_GROUPS_MIN");       // (tests lower it to run small sets through several groups)
+    if (ctx->is_worker || c1 - c0 < (size_t)(env_gmin ? atoi(env_gmin) : 1024)) n_groups = 1;   // workers of the chunk pipeline have no workers of their own
+    if (n_groups > NB_MAX_WORKERS) n_groups = NB_MAX_WORKERS;
+    if (n_groups < 1) n_groups = 1;
+    std::vector<ExtGroup> groups((size_t)n_groups);
+    {
+        uint64_t total = 0, acc = 0;                        // equal numbers of first-round extensions x template length
+        auto weight = [&](size_t t) { return (uint64_t)std::min<size_t>(tpls[t].n, 50) * (uint64_t)tpls[t].T; };
+        for (size_t t = c0; t < c1; ++t) total += weight(t);
+        size_t t = c0;
+        for (int k = 0; k < n_groups; ++k) {
+            groups[(size_t)k].t0 = t;
+            const uint64_t want = total * (uint64_t)(k + 1) / (uint64_t)n_groups;
+            while (t < c1 && (acc < want || k == n_groups - 1)) { acc += weight(t); ++t; }
+            groups[(size_t)k].t1 = t;
+        }
+    }
+    std::vector<NbDevBuf> group_bufs;
+    group_bufs.reserve((size_t)n_groups);
+    for (int k = 0; k < n_groups; ++k) {
+        ExtGroup& g = groups[(size_t)k];
+        g.wc = ctx;
+        if (k > 0) { const int rc = nb_worker_ctx(ctx, k, &g.wc); if (rc) return rc; }
+        group_bufs.emplace_back(g.wc);
+        g.D = &group_bufs.back();
+    }
+    auto ext_phase = [&](ExtGroup& g) -> int {
+        nb_ctx* wc = g.wc;
+        if (cudaSetDevice(wc->device) != cudaSuccess) return nb_fail(wc, NB_ECUDA, "cudaSetDevice failed");
+        cudaStream_t gst = wc->stream;
+        HostTimer gt;
+        for (int round = 0;; ++round) {
+            if (round > 0 || o.use_fixed_ident_cutoff) {
+                // replay in parallel over templates
+                std::vector<std::thread> th;
+                std::vector<size_t> todo;
+                for (size_t t = g.t0; t < g.t1; ++t) if (tpls[t].stage != 2) todo.push_back(t);
+                const size_t per = (todo.size() + nthreads - 1) / nthreads;
+                for (unsigned w = 0; w < nthreads && per; ++w) {
+                    const size_t a = w * per, b = std::min(todo.size(), a + per);
+                    if (a >= b) break;
+                    th.emplace_back([&, a, b]() { for (size_t x = a; x < b; ++x) replay(tpls[todo[x]], cans, g.res, o); });
+                }
+                for (auto& x : th) x.join();
+            }
+            g.tm.replay += gt.lap();
+            // gather requests
+            std::vector<ExtTask> tasks;
+            std::vector<size_t> task_can;
+            uint64_t pool = 0;
+            for (size_t t = g.t0; t < g.t1; ++t) {
+                Tpl& T = tpls[t];
+                if (T.stage == 2) continue;
+                for (size_t k : T.request) {
+                    const Can& c = cans[T.first + k];
+                    ExtTask e;
+                    e.qid = (uint32_t)c.qid; e.sid = (uint32_t)T.tid; e.qoff = c.qoff; e.soff = c.soff; e.qdir = c.qdir; e.pad_ = 0;
+                    if (c.qoff < 0 || c.soff < 0 || c.qoff > c.qsize || c.soff > T.T)
+                        return nb_fail(wc, NB_EINVAL, "candidate offsets out of range (template %d)", T.tid);
+                    const uint64_t mn = (uint64_t)std::min(c.qoff, c.soff);
+                    e.lcap = (uint32_t)(c.qoff + c.soff);
+                    e.ops_cap = (uint32_t)((uint64_t)c.qsize + (uint64_t)T.T + mn + 64);
+                    e.ops_base = pool;
+                    pool += (e.ops_cap + 15) & ~15ull;
+                    tasks.push_back(e);
+                    task_can.push_back(T.first + k);
+                }
+            }
+            g.tm.gather += gt.lap();
+            if (tasks.empty()) break;
+            if (tasks.size() >= (1ull << 31)) return nb_fail(wc, NB_ELIMIT, "too many extension tasks in one round");
+            ExtTask* d_tasks; nb_alignment* d_res; uint8_t* d_ops;
+            int rc;
+            if ((rc = g.D->get(&d_tasks, tasks.size()))) return rc;
+            if ((rc = g.D->get(&d_res, tasks.size()))) return rc;
+            if ((rc = g.D->get(&d_ops, pool + 64))) return rc;
+            std::unique_lock<std::mutex> gpu(sh.gpu);
+            g.tm.wait += gt.lap();
+            NB_CUDA(wc, cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ExtTask) * tasks.size(), cudaMemcpyHostToDevice, gst));
+            cudaEventRecord(wc->ev0, st);
+            rc = nb_run_extension(wc, reads, reads, d_tasks, (uint32_t)tasks.size(), d_res, d_ops, o.error, o.min_align_size, 4 /* ONC_TAIL_MATCH_LEN_LONG */);
+            if (rc) return rc;
+            cudaEventRecord(wc->ev1, st);
+            const size_t r0 = g.res.size();
+            g.res.resize(r0 + tasks.size());
+            NB_CUDA(wc, cudaMemcpyAsync(g.res.data() + r0, d_res, sizeof(nb_alignment) * tasks.size(), cudaMemcpyDeviceToHost, gst));
+            NB_CUDA(wc, cudaStreamSynchronize(st));
+            gpu.unlock();
+            float ms = 0; cudaEventElapsedTime(&ms, wc->ev0, wc->ev1); g.tm.ext_ms += ms;
+            wc->tm.h2d_bytes += sizeof(ExtTask) * tasks.size();
+            wc->tm.d2h_bytes += sizeof(nb_alignment) * tasks.size();
+            g.res_ops.resize(g.res.size());
+            for (size_t k = 0; k < tasks.size(); ++k) {
+                cans[task_can[k]].res = (int)(r0 + k);
+                g.res_ops[r0 + k] = d_ops + g.res[r0 + k].ops_offset;
+            }
+            g.tm.ext += gt.lap();
+            if (round > 64) return nb_fail(wc, NB_ECUDA, "extension rounds do not converge");
+        }
+        return NB_OK;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int k = 1; k < n_groups; ++k) th.emplace_back([&, k]() { groups[(size_t)k].rc = ext_phase(groups[(size_t)k]); });
+        groups[0].rc = ext_phase(groups[0]);
+        for (auto& x : th) x.join();
+    }
+    std::vector<uint8_t> group_of(c1 - c0, 0);
+    for (int k = 0; k < n_groups; ++k) {
+        ExtGroup& g = groups[(size_t)k];
+        if (g.rc) { if (g.wc != ctx) memcpy(ctx->err, g.wc->err, sizeof ctx->err); return g.rc; }
+        for (size_t t = g.t0; t < g.t1; ++t) group_of[t - c0] = (uint8_t)k;
+        t_replay += g.tm.replay; t_gather += g.tm.gather; t_wait += g.tm.wait; t_ext += g.tm.ext; ext_ms += g.tm.ext_ms;
+        if (g.wc != ctx) {                              // fold the worker's counters into this context
+            nb_ctx* wc = g.wc;
+            ctx->launches += wc->launches; wc->launches = 0;
+            ctx->tm.h2d_bytes += wc->tm.h2d_bytes; ctx->tm.d2h_bytes += wc->tm.d2h_bytes;
+            ctx->cc.n_extensions += wc->cc.n_extensions; ctx->cc.n_block_aligns += wc->cc.n_block_aligns;
+            ctx->cc.n_dp_columns += wc->cc.n_dp_columns; ctx->cc.n_dp_word_updates += wc->cc.n_dp_word_updates;
+            memset(&wc->cc, 0, sizeof wc->cc); memset(&wc->tm, 0, sizeof wc->tm);
+        }
+    }
+    const double t_ext_wall = ht.lap();
+    NbDevBuf D(ctx);                            // everything the consensus of this chunk allocates
+
+    // ---- consensus of the chunk
+    std::vector<CnsAln> alns;
+    std::vector<CnsTemplate> dt;
+    std::vector<size_t> dt_tpl;
+    uint64_t out_pool = 0, pos_total = 0, link_total = 0, level_total = 0; uint32_t seg_total = 0;
+    std::vector<size_t> order;
+    for (size_t t = c0; t < c1; ++t) order.push_back(t);
+    static const int kSort = getenv("NB_CNS_SORT") ? atoi(getenv("NB_CNS_SORT")) : 1;
+    static const int kLanes = 1;
+    static const int kWalkLanes = getenv("NB_CNS_WALK_LANES") ? atoi(getenv("NB_CNS_WALK_LANES")) : 1;
+    static const int kDpTest = getenv("NB_CNS_DP_TEST") ? atoi(getenv("NB_CNS_DP_TEST")) : 0;   // 1 = test build of k_cns_dp: tiny fast path and score ring
+    if (kSort) std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tpls[a].T != tpls[b].T ? tpls[a].T > tpls[b].T : a < b; });
+    for (size_t t : order) {
+        Tpl& T = tpls[t];
+        CnsTemplate ct;
+        memset(&ct, 0, sizeof ct);
+        ct.aln_first = (uint32_t)alns.size(); ct.n_aln = (uint32_t)T.acc.size(); ct.T = T.T;
+        uint64_t cols = 0;
+        const ExtGroup& G = groups[group_of[t - c0]];
+        for (const Accepted& a : T.acc) {
+            const Can& c = cans[T.first + (size_t)a.can];
+            const nb_alignment& r = G.res[(size_t)c.res];
+            CnsAln ca;
+            ca.ops = G.res_ops[(size_t)c.res]; ca.qseq_off = reads->h_off[c.qid];
+            ca.aln_size = r.aln_size; ca.toff = r.toff; ca.tend = r.tend; ca.qstart = r.qoff;
+            ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight;
+            alns.push_back(ca);
+            cols += (uint64_t)r.aln_size;
+        }
+        ct.seg_cap = (uint32_t)(T.T / std::max(1, (int)(o.min_size * 0.85)) + 2);
+        ct.seg_first = seg_total; seg_total += ct.seg_cap;
+        ct.out_cap = (uint32_t)(T.T * 2 + 1024);
+        ct.out_base = out_pool; out_pool += ct.out_cap;
+        ct.link_cap = (uint32_t)std::min<uint64_t>(cols + 32, 0xfffffff0ull);      // links <= columns
+        ct.level_cap = (uint32_t)(T.T * 3 + 2048);
+        ctx->cc.n_accepted += T.acc.size();
+        dt.push_back(ct); dt_tpl.push_back(t);
+    }
+    for (auto& ct : dt) {
+        ct.pos_base = pos_total; pos_total += (uint64_t)ct.T + 2;
+        ct.link_base = link_total; link_total += ct.link_cap;
+        ct.level_base = level_total; level_total += ct.level_cap;
+    }
+    std::vector<CnsSegment> segs(seg_total);
+    std::vector<uint32_t> nseg(dt.size(), 0);
+    const char* ascii = NULL;           // consensus stretches of this chunk, dense (pinned staging buffer)
+    std::vector<uint64_t> seg_dense(seg_total, 0);
+    uint8_t* d_seq_pool = NULL;
+    if (!dt.empty()) {
+        int rc;
+        CnsParams P;
+        memset(&P, 0, sizeof P);
+        CnsTemplate* d_tpl; CnsAln* d_aln;
+        if ((rc = D.get(&d_tpl, dt.size()))) return rc;
+        if ((rc = D.get(&d_aln, alns.size()))) return rc;
+        if ((rc = D.get(&P.seg, seg_total))) return rc;
+        if ((rc = D.get(&P.tpl_nseg, dt.size()))) return rc;
+        if ((rc = D.get(&P.seq_pool, out_pool))) return rc;
+        d_seq_pool = P.seq_pool;
+        if ((rc = D.get(&P.next_tpl, 1))) return rc;
+        if ((rc = D.get(&P.pos, pos_total))) return rc;
+        if ((rc = D.get(&P.link, link_total + 64))) return rc;      // k_cns_dp stages whole chunks: slack past the last link
+        if ((rc = D.get(&P.bp, level_total))) return rc;
+        if ((rc = D.get(&P.rev, level_total))) return rc;
+        const unsigned links_grid = NB_SMS * 5;          // 20 warps per SM (shared-memory bound)
+        const size_t cursor_area = (size_t)links_grid * CNS_WARPS * CNS_MAX_ALN;    // one per side stream: slices run concurrently
+        if ((rc = D.get(&P.cursor, cursor_area * 2))) return rc;
+        if ((rc = D.get(&P.error_flag, 1))) return rc;
+        if ((rc = D.get(&P.counters, 4))) return rc;
+        CnsRun* d_runs; uint32_t* d_nrun;
+        if ((rc = D.get(&d_runs, seg_total))) return rc;
+        if ((rc = D.get(&d_nrun, dt.size()))) return rc;
+        NB_CUDA(ctx, cudaMemcpyAsync(d_tpl, dt.data(), sizeof(CnsTemplate) * dt.size(), cudaMemcpyHostToDevice, st));
+        NB_CUDA(ctx, cudaMemcpyAsync(d_aln, alns.data(), sizeof(CnsAln) * alns.size(), cudaMemcpyHostToDevice, st));
+        NB_CUDA(ctx, cudaMemsetAsync(P.next_tpl, 0, sizeof(uint32_t), st));
+        NB_CUDA(ctx, cudaMemsetAsync(P.error_flag, 0, sizeof(uint32_t), st));
+        NB_CUDA(ctx, cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 4, st));
+        P.pac = reads->d_pac; P.tpl = d_tpl; P.aln = d_aln; P.n_tpl = (uint32_t)dt.size();
+        P.min_cov = o.min_cov; P.min_size = o.min_size; P.lanes = kLanes < 1 ? 1 : (kLanes > 32 ? 32 : kLanes);
+        P.walk_lanes = kWalkLanes < 1 ? 1 : (kWalkLanes > 32 ? 32 : kWalkLanes);
+        const size_t smem = sizeof(CnsWarpShared) * CNS_WARPS;
+        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_cns_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        t_prep += ht.lap();
+        std::unique_lock<std::mutex> gpu(sh.gpu);
+        t_wait += ht.lap();
+        cudaEventRecord(ctx->ev2, st);
+        // Slices of the length-sorted templates (equal total bases) alternate between two side streams: the
+        // link building of one slice overlaps the latency-bound DP chains of another; the slice with the
+        // longest templates starts first, its DP tail is hidden behind everything else.
+        {
+            static const int kSlices = getenv("NB_CNS_SLICES") ? atoi(getenv("NB_CNS_SLICES")) : 1;
+            int nsl = dt.size() >= 256 ? kSlices : 1;
+            if (nsl < 1) nsl = 1;
+            if (nsl > 64) nsl = 64;
+            uint64_t total_T = 0;
+            for (const auto& ct : dt) total_T += (uint64_t)ct.T;
+            uint32_t* d_next;
+            if ((rc = D.get(&d_next, 64))) return rc;
+            NB_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(uint32_t) * 64, st));
+            NB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[2], st));
+            for (int k = 0; k < 2; ++k) NB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[k], ctx->aux_ev[2], 0));
+            size_t a = 0;
+            uint64_t acc = 0;
+            for (int sl = 0; sl < nsl && a < dt.size(); ++sl) {
+                size_t b = a;
+                const uint64_t want = total_T * (uint64_t)(sl + 1) / (uint64_t)nsl;
+                while (b < dt.size() && (acc < want || sl == nsl - 1)) { acc += (uint64_t)dt[b].T; ++b; }
+                if (b == a) continue;
+                cudaStream_t ss = nsl == 1 ? st : ctx->aux[sl & 1];
+                CnsParams Q = P;
+                Q.tpl = d_tpl + a; Q.n_tpl = (uint32_t)(b - a); Q.tpl_nseg = P.tpl_nseg + a; Q.next_tpl = d_next + sl;
+                Q.cursor = P.cursor + (size_t)(sl & 1) * cursor_area;
+                unsigned lg = (unsigned)((b - a + CNS_WARPS - 1) / CNS_WARPS);
+                if (lg > links_grid) lg = links_grid;
+                k_cns_links<<<lg, CNS_WARPS * 32, smem, ss>>>(Q);
+                NB_LAUNCH_CHECK(ctx);
+                const unsigned dp_warps = (unsigned)(b - a);      // one warp per template; the slice is sorted by length, the longest start first
+                if (kDpTest) k_cns_dp<3, 8><<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
+                else k_cns_dp<32, 256><<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
+                NB_LAUNCH_CHECK(ctx);
+                const unsigned walk_warps = (unsigned)((b - a + Q.walk_lanes - 1) / Q.walk_lanes);
+                k_cns_walk<<<(walk_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
+                NB_LAUNCH_CHECK(ctx);
+                a = b;
+            }
+            if (nsl > 1)
+                for (int k = 0; k < 2; ++k) {
+                    NB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[k], ctx->aux[k]));
+                    NB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->aux_ev[k], 0));
+                }
+        }
+        cudaEventRecord(ctx->ev3, st);
+        uint32_t eflag = 0; unsigned long long cnt[4];
+        NB_CUDA(ctx, cudaMemcpyAsync(&eflag, P.error_flag, sizeof eflag, cudaMemcpyDeviceToHost, st));
+        NB_CUDA(ctx, cudaMemcpyAsync(cnt, P.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
+        NB_CUDA(ctx, cudaMemcpyAsync(segs.data(), P.seg, sizeof(CnsSegment) * seg_total, cudaMemcpyDeviceToHost, st));
+        NB_CUDA(ctx, cudaMemcpyAsync(nseg.data(), P.tpl_nseg, sizeof(uint32_t) * dt.size(), cudaMemcpyDeviceToHost, st));
+        NB_CUDA(ctx, cudaStreamSynchronize(st));
+        float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); cns_ms += ms;
+        ctx->tm.d2h_bytes += sizeof(CnsSegment) * seg_total;
+        ctx->cc.n_tags += cnt[1];
+        if (eflag) return nb_fail(ctx, NB_ELIMIT, "consensus kernel capacity exceeded (flags %u)", eflag);
+        {
+            // gather the stretches densely as ASCII, one exact-size D2H copy
+            std::vector<uint64_t> gsrc, gdst; std::vector<uint32_t> glen;
+            uint64_t dense = 0;
+            for (size_t x = 0; x < dt.size(); ++x)
+                for (uint32_t k = 0; k < nseg[x]; ++k) {
+                    const CnsSegment& g = segs[dt[x].seg_first + k];
+                    gsrc.push_back(g.seq_off); gdst.push_back(dense); glen.push_back(g.len);
+                    seg_dense[dt[x].seg_first + k] = dense;
+                    dense += g.len;
+                }
+            if ((rc = nb_pinned_reserve(ctx, dense + 16))) return rc;
+            ascii = (const char*)ctx->pinned;
+            if (!gsrc.empty()) {
+                uint64_t *d_src, *d_dst; uint32_t* d_len; char* d_out;
+                if ((rc = D.get(&d_src, gsrc.size()))) return rc;
+                if ((rc = D.get(&d_dst, gsrc.size()))) return rc;
+                if ((rc = D.get(&d_len, gsrc.size()))) return rc;
+                if ((rc = D.get(&d_out, dense))) return rc;
+                NB_CUDA(ctx, cudaMemcpyAsync(d_src, gsrc.data(), 8 * gsrc.size(), cudaMemcpyHostToDevice, st));
+                NB_CUDA(ctx, cudaMemcpyAsync(d_dst, gdst.data(), 8 * gsrc.size(), cudaMemcpyHostToDevice, st));
+                NB_CUDA(ctx, cudaMemcpyAsync(d_len, glen.data(), 4 * gsrc.size(), cudaMemcpyHostToDevice, st));
+                k_gather_ascii<<<NB_SMS * 8, 256, 0, st>>>(d_seq_pool, d_src, d_dst, d_len, (uint32_t)gsrc.size(), d_out);
+                NB_LAUNCH_CHECK(ctx);
+                NB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, d_out, dense, cudaMemcpyDeviceToHost, st));
+                NB_CUDA(ctx, cudaStreamSynchronize(st));
+                ctx->tm.d2h_bytes += dense;
+            }
+        }
+        gpu.unlock();
+        t_kern += ht.lap();
+    }
+    // ---- records (tasc/cbcns.c:108-264, consensus_one_read.c:20-136): plan, then fill in parallel
+    fills.clear();
+    auto plan = [&](int id, int left, int right, int org, int ncan, int novl, double cutoff, int is_raw, uint32_t len) {
+        nb_cns_record r;
+        r.id = id; r.left = left; r.right = right; r.org_size = org; r.num_can = ncan; r.num_ovlps = novl;
+        r.ident_cutoff = cutoff; r.seq_offset = so.used; r.seq_len = (int)len; r.is_raw = is_raw;
+        recs.push_back(r);
+    };
+    auto add_raw = [&](int id, int from, int to) {      // read bases [from, to)
+        Fill f; f.dst = so.used; f.len = (uint32_t)(to - from); f.kind = 1; f.src = reads->h_off[id] + (uint64_t)from;
+        fills.push_back(f); so.used += f.len;
+    };
+    auto add_cns = [&](const CnsSegment& g, uint64_t dense_off) {
+        Fill f; f.dst = so.used; f.len = g.len; f.kind = 0; f.src = dense_off;
+        fills.push_back(f); so.used += f.len;
+    };
+    for (size_t x = 0; x < dt.size(); ++x) {
+        Tpl& T = tpls[dt_tpl[x]];
+        const CnsSegment* sg = segs.data() + dt[x].seg_first;
+        const uint64_t* sd = seg_dense.data() + dt[x].seg_first;
+        const uint32_t ns = nseg[x];
+        if (!o.full_consensus) {
+            for (uint32_t k = 0; k < ns; ++k) {
+                plan(T.tid, sg[k].left, sg[k].right, T.T, T.num_can, T.num_ovlps, T.cutoff, 0, sg[k].len);
+                add_cns(sg[k], sd[k]);
+                ctx->cc.cns_bases += sg[k].len;
+            }
+            // raw stretches between the corrected runs (get_raw_intvs, consensus_one_read.c:20-65)
+            bool first = true, open = true;
+            int left = 0;
+            const int end_off = T.T - 1;
+            for (uint32_t k = 0; k < ns; ++k) {
+                const int fs = sg[k].left, fe = sg[k].right;
+                if (first) {
+                    open = false; first = false;
+                    if (fs > 0) left = 0;
+                    else { left = fe + 1; continue; }
+                }
+                const int right = fs - 1;
+                if (right - left + 1 >= 1000) {
+                    plan(T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff, 1, (uint32_t)(right + 1 - left));
+                    add_raw(T.tid, left, right + 1);
+                }
+                if (fe >= end_off) { open = false; break; }
+                left = fe + 1;
+            }
+            if (open) {
+                const int right = end_off;
+                if (right - left + 1 >= 1000) {
+                    plan(T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff, 1, (uint32_t)(right + 1 - left));
+                    add_raw(T.tid, left, right + 1);
+                }
+            }
+            corrected[(size_t)T.tid] = 1;                       // consensus_one_read.c:391 (r stays 1)
+        } else if (ns) {
+            // consensus_unbroken (cbcns.c:218-257): corrected runs spliced into the raw read
+            const uint64_t start = so.used;
+            const size_t ri = recs.size();
+            plan(T.tid, 0, T.T, T.T, T.num_can, T.num_ovlps, T.cutoff, 0, 0);
+            int last_raw = 0;
+            for (uint32_t k = 0; k < ns; ++k) {
+                const int rf = sg[k].cns_from, rt = sg[k].cns_to;
+                if (rf > last_raw) add_raw(T.tid, last_raw, rf);
+                add_cns(sg[k], sd[k]);
+                last_raw = rt;
+            }
+            if (last_raw < T.T) add_raw(T.tid, last_raw, T.T);
+            recs[ri].seq_len = (int)(so.used - start);
+            ctx->cc.cns_bases += so.used - start;
+            corrected[(size_t)T.tid] = 1;
+        }
+        std::vector<uint16_t>().swap(T.cov);
+    }
+    // ---- the chunk's bytes get their place in the job's buffer; then fill in parallel
+    const uint64_t base = sh.used.fetch_add(so.used);
+    if (base + so.used > sh.cap) return nb_fail(ctx, NB_ELIMIT, "output exceeds its upper bound");
+    for (auto& r : recs) r.seq_offset += base;
+    for (auto& f : fills) f.dst += base;
+    run_fills(fills, sh.buf, ascii, reads, nthreads);
+    t_rec += ht.lap();
+    tms.replay = t_replay; tms.gather = t_gather; tms.ext = t_ext; tms.prep = t_prep; tms.kern = t_kern; tms.rec = t_rec; tms.wait = t_wait; tms.ext_wall = t_ext_wall;
+    tms.ext_ms = ext_ms; tms.cns_ms = cns_ms;
+    return NB_OK;
+}
+
 extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, const nb_packed_candidate* cans_in, uint64_t n_in,
                                         const nb_cns_options* opt, int shard_count, int shard_index,
                                         nb_cns_record** out_recs, uint64_t* n_recs, char** out_seq, uint64_t* out_seq_bytes);
@@ -288,15 +721,13 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     if (opt->rescue_long_indels)
         return nb_fail(ctx, NB_EINVAL, "-r 1 (DALIGNER rescue, oc_daligner.c) is not implemented in the B200 build");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     memset(&ctx->cc, 0, sizeof ctx->cc);
     ctx->tm.extend_ms = 0; ctx->tm.consensus_ms = 0;
     const nb_cns_options o = *opt;
     const bool trace = getenv("NB_TRACE") != NULL;
     HostTimer ht;
-    double t_setup = 0, t_replay = 0, t_gather = 0, t_ext = 0, t_prep = 0, t_kern = 0, t_rec = 0, t_tail = 0;
+    double t_setup = 0, t_tail = 0;
     std::vector<nb_cns_record> recs;
-    SeqOut so;
     std::vector<Fill> fills;
     if (n_in == 0) return NB_OK;
 
@@ -367,357 +798,128 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     ctx->cc.n_templates = tpls.size();
     t_setup += ht.lap();
 
-    // ---- chunks of templates: bounded device memory
-    const size_t kChunk = 32768;
+    // ---- the templates are cut into chunks of equal total length that go through a small pipeline: every
+    //      worker owns a stream, events, a pinned staging buffer and walk-back scratch, so the host phases of one
+    //      chunk (replay of the accept/skip logic, request gathering, record planning and filling) overlap the
+    //      kernels of the others.  Chunks also bound the device memory of a 100 000-template partition.
     unsigned nthreads = std::thread::hardware_concurrency();
     if (nthreads == 0) nthreads = 4;
     if (nthreads > 64) nthreads = 64;
-    float ext_ms = 0, cns_ms = 0;
-    for (size_t c0 = 0; c0 < tpls.size(); c0 += kChunk) {
-        const size_t c1 = std::min(tpls.size(), c0 + kChunk);
-        NbDevBuf D(ctx);                            // everything allocated for this chunk
-        std::vector<nb_alignment> res;              // results of all rounds of this chunk
-        std::vector<const uint8_t*> res_ops;        // device pointer of each result's ops
-        for (size_t t = c0; t < c1; ++t) { tpls[t].cov.assign((size_t)tpls[t].T + 1, 0); tpls[t].n_below = o.max_cov > 0 ? tpls[t].T : 0; }
-        // round 0 requests: the first 50 candidates (phase 1), or the first window with -u 1
-        for (size_t t = c0; t < c1; ++t) {
-            Tpl& T = tpls[t];
-            T.request.clear();
-            if (!o.use_fixed_ident_cutoff) for (size_t k = 0; k < T.n && k < 50; ++k) T.request.push_back(k);
+    const char* env_chunks = getenv("NB_CNS_CHUNKS");
+    const char* env_pipes = getenv("NB_CNS_PIPES");
+    size_t n_chunks = env_chunks ? (size_t)atoi(env_chunks) : 1;
+    const size_t kChunkMax = 32768;
+    if (n_chunks < (tpls.size() + kChunkMax - 1) / kChunkMax) n_chunks = (tpls.size() + kChunkMax - 1) / kChunkMax;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > tpls.size()) n_chunks = tpls.size() ? tpls.size() : 1;
+    int n_workers = env_pipes ? atoi(env_pipes) : 1;
+    if (n_workers > NB_MAX_WORKERS) n_workers = NB_MAX_WORKERS;
+    if ((size_t)n_workers > n_chunks) n_workers = (int)n_chunks;
+    if (n_workers < 1) n_workers = 1;
+    std::vector<size_t> cut(n_chunks + 1, tpls.size());
+    {
+        uint64_t total_T = 0, acc = 0;
+        for (const Tpl& t : tpls) total_T += (uint64_t)t.T;
+        size_t k = 1;
+        cut[0] = 0;
+        for (size_t t = 0; t < tpls.size() && k < n_chunks; ++t) {
+            acc += (uint64_t)tpls[t].T;
+            if (acc * n_chunks >= total_T * k || t + 1 - cut[k - 1] >= kChunkMax) cut[k++] = t + 1;
         }
-        for (int round = 0;; ++round) {
-            if (round > 0 || o.use_fixed_ident_cutoff) {
-                // replay in parallel over templates
-                std::vector<std::thread> th;
-                std::vector<size_t> todo;
-                for (size_t t = c0; t < c1; ++t) if (tpls[t].stage != 2) todo.push_back(t);
-                const size_t per = (todo.size() + nthreads - 1) / nthreads;
-                for (unsigned w = 0; w < nthreads && per; ++w) {
-                    const size_t a = w * per, b = std::min(todo.size(), a + per);
-                    if (a >= b) break;
-                    th.emplace_back([&, a, b]() { for (size_t x = a; x < b; ++x) replay(tpls[todo[x]], cans, res, o); });
-                }
-                for (auto& x : th) x.join();
-            }
-            t_replay += ht.lap();
-            // gather requests
-            std::vector<ExtTask> tasks;
-            std::vector<size_t> task_can;
-            uint64_t pool = 0;
-            for (size_t t = c0; t < c1; ++t) {
-                Tpl& T = tpls[t];
-                if (T.stage == 2) continue;
-                for (size_t k : T.request) {
-                    const Can& c = cans[T.first + k];
-                    ExtTask e;
-                    e.qid = (uint32_t)c.qid; e.sid = (uint32_t)T.tid; e.qoff = c.qoff; e.soff = c.soff; e.qdir = c.qdir; e.pad_ = 0;
-                    if (c.qoff < 0 || c.soff < 0 || c.qoff > c.qsize || c.soff > T.T)
-                        return nb_fail(ctx, NB_EINVAL, "candidate offsets out of range (template %d)", T.tid);
-                    const uint64_t mn = (uint64_t)std::min(c.qoff, c.soff);
-                    e.lcap = (uint32_t)(c.qoff + c.soff);
-                    e.ops_cap = (uint32_t)((uint64_t)c.qsize + (uint64_t)T.T + mn + 64);
-                    e.ops_base = pool;
-                    pool += (e.ops_cap + 15) & ~15ull;
-                    tasks.push_back(e);
-                    task_can.push_back(T.first + k);
-                }
-            }
-            t_gather += ht.lap();
-            if (tasks.empty()) break;
-            if (tasks.size() >= (1ull << 31)) return nb_fail(ctx, NB_ELIMIT, "too many extension tasks in one round");
-            ExtTask* d_tasks; nb_alignment* d_res; uint8_t* d_ops;
-            int rc;
-            if ((rc = D.get(&d_tasks, tasks.size()))) return rc;
-            if ((rc = D.get(&d_res, tasks.size()))) return rc;
-            if ((rc = D.get(&d_ops, pool + 64))) return rc;
-            NB_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ExtTask) * tasks.size(), cudaMemcpyHostToDevice, st));
-            cudaEventRecord(ctx->ev0, st);
-            rc = nb_run_extension(ctx, reads, reads, d_tasks, (uint32_t)tasks.size(), d_res, d_ops, o.error, o.min_align_size, 4 /* ONC_TAIL_MATCH_LEN_LONG */);
-            if (rc) return rc;
-            cudaEventRecord(ctx->ev1, st);
-            const size_t r0 = res.size();
-            res.resize(r0 + tasks.size());
-            NB_CUDA(ctx, cudaMemcpyAsync(res.data() + r0, d_res, sizeof(nb_alignment) * tasks.size(), cudaMemcpyDeviceToHost, st));
-            NB_CUDA(ctx, cudaStreamSynchronize(st));
-            float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ext_ms += ms;
-            ctx->tm.h2d_bytes += sizeof(ExtTask) * tasks.size();
-            ctx->tm.d2h_bytes += sizeof(nb_alignment) * tasks.size();
-            res_ops.resize(res.size());
-            for (size_t k = 0; k < tasks.size(); ++k) {
-                cans[task_can[k]].res = (int)(r0 + k);
-                res_ops[r0 + k] = d_ops + res[r0 + k].ops_offset;
-            }
-            t_ext += ht.lap();
-            if (round > 64) return nb_fail(ctx, NB_ECUDA, "extension rounds do not converge");
-        }
-
-        // ---- consensus of the chunk
-        std::vector<CnsAln> alns;
-        std::vector<CnsTemplate> dt;
-        std::vector<size_t> dt_tpl;
-        uint64_t out_pool = 0, pos_total = 0, link_total = 0, level_total = 0; uint32_t seg_total = 0;
-        std::vector<size_t> order;
-        for (size_t t = c0; t < c1; ++t) order.push_back(t);
-        static const int kSort = getenv("NB_CNS_SORT") ? atoi(getenv("NB_CNS_SORT")) : 1;
-        static const int kLanes = getenv("NB_CNS_LANES") ? atoi(getenv("NB_CNS_LANES")) : 1;
-        if (kSort) std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tpls[a].T != tpls[b].T ? tpls[a].T > tpls[b].T : a < b; });
-        for (size_t t : order) {
-            Tpl& T = tpls[t];
-            CnsTemplate ct;
-            memset(&ct, 0, sizeof ct);
-            ct.aln_first = (uint32_t)alns.size(); ct.n_aln = (uint32_t)T.acc.size(); ct.T = T.T;
-            uint64_t cols = 0;
-            for (const Accepted& a : T.acc) {
-                const Can& c = cans[T.first + (size_t)a.can];
-                const nb_alignment& r = res[(size_t)c.res];
-                CnsAln ca;
-                ca.ops = res_ops[(size_t)c.res]; ca.qseq_off = reads->h_off[c.qid];
-                ca.aln_size = r.aln_size; ca.toff = r.toff; ca.tend = r.tend; ca.qstart = r.qoff;
-                ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight;
-                alns.push_back(ca);
-                cols += (uint64_t)r.aln_size;
-            }
-            ct.seg_cap = (uint32_t)(T.T / std::max(1, (int)(o.min_size * 0.85)) + 2);
-            ct.seg_first = seg_total; seg_total += ct.seg_cap;
-            ct.out_cap = (uint32_t)(T.T * 2 + 1024);
-            ct.out_base = out_pool; out_pool += ct.out_cap;
-            ct.link_cap = (uint32_t)std::min<uint64_t>(cols + 32, 0xfffffff0ull);      // links <= columns
-            ct.level_cap = (uint32_t)(T.T * 3 + 2048);
-            ctx->cc.n_accepted += T.acc.size();
-            dt.push_back(ct); dt_tpl.push_back(t);
-        }
-        for (auto& ct : dt) {
-            ct.pos_base = pos_total; pos_total += (uint64_t)ct.T + 2;
-            ct.link_base = link_total; link_total += ct.link_cap;
-            ct.level_base = level_total; level_total += ct.level_cap;
-        }
-        std::vector<CnsSegment> segs(seg_total);
-        std::vector<uint32_t> nseg(dt.size(), 0);
-        const char* ascii = NULL;           // consensus stretches of this chunk, dense (pinned staging buffer)
-        std::vector<uint64_t> seg_dense(seg_total, 0);
-        uint8_t* d_seq_pool = NULL;
-        if (!dt.empty()) {
-            int rc;
-            CnsParams P;
-            memset(&P, 0, sizeof P);
-            CnsTemplate* d_tpl; CnsAln* d_aln;
-            if ((rc = D.get(&d_tpl, dt.size()))) return rc;
-            if ((rc = D.get(&d_aln, alns.size()))) return rc;
-            if ((rc = D.get(&P.seg, seg_total))) return rc;
-            if ((rc = D.get(&P.tpl_nseg, dt.size()))) return rc;
-            if ((rc = D.get(&P.seq_pool, out_pool))) return rc;
-            d_seq_pool = P.seq_pool;
-            if ((rc = D.get(&P.next_tpl, 1))) return rc;
-            if ((rc = D.get(&P.pos, pos_total))) return rc;
-            if ((rc = D.get(&P.link, link_total))) return rc;
-            if ((rc = D.get(&P.bp, level_total))) return rc;
-            if ((rc = D.get(&P.rev, level_total))) return rc;
-            const unsigned links_grid = NB_SMS * 5;          // 20 warps per SM (shared-memory bound)
-            if ((rc = D.get(&P.cursor, (size_t)links_grid * CNS_WARPS * CNS_MAX_ALN))) return rc;
-            if ((rc = D.get(&P.error_flag, 1))) return rc;
-            if ((rc = D.get(&P.counters, 4))) return rc;
-            CnsRun* d_runs; uint32_t* d_nrun;
-            if ((rc = D.get(&d_runs, seg_total))) return rc;
-            if ((rc = D.get(&d_nrun, dt.size()))) return rc;
-            NB_CUDA(ctx, cudaMemcpyAsync(d_tpl, dt.data(), sizeof(CnsTemplate) * dt.size(), cudaMemcpyHostToDevice, st));
-            NB_CUDA(ctx, cudaMemcpyAsync(d_aln, alns.data(), sizeof(CnsAln) * alns.size(), cudaMemcpyHostToDevice, st));
-            NB_CUDA(ctx, cudaMemsetAsync(P.next_tpl, 0, sizeof(uint32_t), st));
-            NB_CUDA(ctx, cudaMemsetAsync(P.error_flag, 0, sizeof(uint32_t), st));
-            NB_CUDA(ctx, cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 4, st));
-            P.pac = reads->d_pac; P.tpl = d_tpl; P.aln = d_aln; P.n_tpl = (uint32_t)dt.size();
-            P.min_cov = o.min_cov; P.min_size = o.min_size; P.lanes = kLanes < 1 ? 1 : (kLanes > 32 ? 32 : kLanes);
-            const size_t smem = sizeof(CnsWarpShared) * CNS_WARPS;
-            if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_cns_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            t_prep += ht.lap();
-            cudaEventRecord(ctx->ev2, st);
-            // Slices of the length-sorted templates (equal total bases) alternate between two side streams: the
-            // link building of one slice overlaps the latency-bound DP chains of another; the slice with the
-            // longest templates starts first, its DP tail is hidden behind everything else.
-            {
-                static const int kSlices = getenv("NB_CNS_SLICES") ? atoi(getenv("NB_CNS_SLICES")) : 1;
-                int nsl = dt.size() >= 256 ? kSlices : 1;
-                if (nsl < 1) nsl = 1;
-                if (nsl > 64) nsl = 64;
-                uint64_t total_T = 0;
-                for (const auto& ct : dt) total_T += (uint64_t)ct.T;
-                uint32_t* d_next;
-                if ((rc = D.get(&d_next, 64))) return rc;
-                NB_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(uint32_t) * 64, st));
-                NB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[2], st));
-                for (int k = 0; k < 2; ++k) NB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[k], ctx->aux_ev[2], 0));
-                size_t a = 0;
-                uint64_t acc = 0;
-                for (int sl = 0; sl < nsl && a < dt.size(); ++sl) {
-                    size_t b = a;
-                    const uint64_t want = total_T * (uint64_t)(sl + 1) / (uint64_t)nsl;
-                    while (b < dt.size() && (acc < want || sl == nsl - 1)) { acc += (uint64_t)dt[b].T; ++b; }
-                    if (b == a) continue;
-                    cudaStream_t ss = nsl == 1 ? st : ctx->aux[sl & 1];
-                    CnsParams Q = P;
-                    Q.tpl = d_tpl + a; Q.n_tpl = (uint32_t)(b - a); Q.tpl_nseg = P.tpl_nseg + a; Q.next_tpl = d_next + sl;
-                    unsigned lg = (unsigned)((b - a + CNS_WARPS - 1) / CNS_WARPS);
-                    if (lg > links_grid) lg = links_grid;
-                    k_cns_links<<<lg, CNS_WARPS * 32, smem, ss>>>(Q);
-                    NB_LAUNCH_CHECK(ctx);
-                    const unsigned dp_warps = (unsigned)((b - a + Q.lanes - 1) / Q.lanes);
-                    k_cns_dp<<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
-                    NB_LAUNCH_CHECK(ctx);
-                    k_cns_walk<<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
-                    NB_LAUNCH_CHECK(ctx);
-                    a = b;
-                }
-                if (nsl > 1)
-                    for (int k = 0; k < 2; ++k) {
-                        NB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[k], ctx->aux[k]));
-                        NB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->aux_ev[k], 0));
-                    }
-            }
-            cudaEventRecord(ctx->ev3, st);
-            uint32_t eflag = 0; unsigned long long cnt[4];
-            NB_CUDA(ctx, cudaMemcpyAsync(&eflag, P.error_flag, sizeof eflag, cudaMemcpyDeviceToHost, st));
-            NB_CUDA(ctx, cudaMemcpyAsync(cnt, P.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
-            NB_CUDA(ctx, cudaMemcpyAsync(segs.data(), P.seg, sizeof(CnsSegment) * seg_total, cudaMemcpyDeviceToHost, st));
-            NB_CUDA(ctx, cudaMemcpyAsync(nseg.data(), P.tpl_nseg, sizeof(uint32_t) * dt.size(), cudaMemcpyDeviceToHost, st));
-            NB_CUDA(ctx, cudaStreamSynchronize(st));
-            float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); cns_ms += ms;
-            ctx->tm.d2h_bytes += sizeof(CnsSegment) * seg_total;
-            ctx->cc.n_tags += cnt[1];
-            if (eflag) return nb_fail(ctx, NB_ELIMIT, "consensus kernel capacity exceeded (flags %u)", eflag);
-            {
-                // gather the stretches densely as ASCII, one exact-size D2H copy
-                std::vector<uint64_t> gsrc, gdst; std::vector<uint32_t> glen;
-                uint64_t dense = 0;
-                for (size_t x = 0; x < dt.size(); ++x)
-                    for (uint32_t k = 0; k < nseg[x]; ++k) {
-                        const CnsSegment& g = segs[dt[x].seg_first + k];
-                        gsrc.push_back(g.seq_off); gdst.push_back(dense); glen.push_back(g.len);
-                        seg_dense[dt[x].seg_first + k] = dense;
-                        dense += g.len;
-                    }
-                if ((rc = nb_pinned_reserve(ctx, dense + 16))) return rc;
-                ascii = (const char*)ctx->pinned;
-                if (!gsrc.empty()) {
-                    uint64_t *d_src, *d_dst; uint32_t* d_len; char* d_out;
-                    if ((rc = D.get(&d_src, gsrc.size()))) return rc;
-                    if ((rc = D.get(&d_dst, gsrc.size()))) return rc;
-                    if ((rc = D.get(&d_len, gsrc.size()))) return rc;
-                    if ((rc = D.get(&d_out, dense))) return rc;
-                    NB_CUDA(ctx, cudaMemcpyAsync(d_src, gsrc.data(), 8 * gsrc.size(), cudaMemcpyHostToDevice, st));
-                    NB_CUDA(ctx, cudaMemcpyAsync(d_dst, gdst.data(), 8 * gsrc.size(), cudaMemcpyHostToDevice, st));
-                    NB_CUDA(ctx, cudaMemcpyAsync(d_len, glen.data(), 4 * gsrc.size(), cudaMemcpyHostToDevice, st));
-                    k_gather_ascii<<<NB_SMS * 8, 256, 0, st>>>(d_seq_pool, d_src, d_dst, d_len, (uint32_t)gsrc.size(), d_out);
-                    NB_LAUNCH_CHECK(ctx);
-                    NB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, d_out, dense, cudaMemcpyDeviceToHost, st));
-                    NB_CUDA(ctx, cudaStreamSynchronize(st));
-                    ctx->tm.d2h_bytes += dense;
-                }
-            }
-            t_kern += ht.lap();
-        }
-        // ---- records (tasc/cbcns.c:108-264, consensus_one_read.c:20-136): plan, then fill in parallel
-        fills.clear();
-        auto plan = [&](int id, int left, int right, int org, int ncan, int novl, double cutoff, int is_raw, uint32_t len) {
-            nb_cns_record r;
-            r.id = id; r.left = left; r.right = right; r.org_size = org; r.num_can = ncan; r.num_ovlps = novl;
-            r.ident_cutoff = cutoff; r.seq_offset = so.used; r.seq_len = (int)len; r.is_raw = is_raw;
-            recs.push_back(r);
-        };
-        auto add_raw = [&](int id, int from, int to) {      // read bases [from, to)
-            Fill f; f.dst = so.used; f.len = (uint32_t)(to - from); f.kind = 1; f.src = reads->h_off[id] + (uint64_t)from;
-            fills.push_back(f); so.used += f.len;
-        };
-        auto add_cns = [&](const CnsSegment& g, uint64_t dense_off) {
-            Fill f; f.dst = so.used; f.len = g.len; f.kind = 0; f.src = dense_off;
-            fills.push_back(f); so.used += f.len;
-        };
-        for (size_t x = 0; x < dt.size(); ++x) {
-            Tpl& T = tpls[dt_tpl[x]];
-            const CnsSegment* sg = segs.data() + dt[x].seg_first;
-            const uint64_t* sd = seg_dense.data() + dt[x].seg_first;
-            const uint32_t ns = nseg[x];
-            if (!o.full_consensus) {
-                for (uint32_t k = 0; k < ns; ++k) {
-                    plan(T.tid, sg[k].left, sg[k].right, T.T, T.num_can, T.num_ovlps, T.cutoff, 0, sg[k].len);
-                    add_cns(sg[k], sd[k]);
-                    ctx->cc.cns_bases += sg[k].len;
-                }
-                // raw stretches between the corrected runs (get_raw_intvs, consensus_one_read.c:20-65)
-                bool first = true, open = true;
-                int left = 0;
-                const int end_off = T.T - 1;
-                for (uint32_t k = 0; k < ns; ++k) {
-                    const int fs = sg[k].left, fe = sg[k].right;
-                    if (first) {
-                        open = false; first = false;
-                        if (fs > 0) left = 0;
-                        else { left = fe + 1; continue; }
-                    }
-                    const int right = fs - 1;
-                    if (right - left + 1 >= 1000) {
-                        plan(T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff, 1, (uint32_t)(right + 1 - left));
-                        add_raw(T.tid, left, right + 1);
-                    }
-                    if (fe >= end_off) { open = false; break; }
-                    left = fe + 1;
-                }
-                if (open) {
-                    const int right = end_off;
-                    if (right - left + 1 >= 1000) {
-                        plan(T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff, 1, (uint32_t)(right + 1 - left));
-                        add_raw(T.tid, left, right + 1);
-                    }
-                }
-                corrected[(size_t)T.tid] = 1;                       // consensus_one_read.c:391 (r stays 1)
-            } else if (ns) {
-                // consensus_unbroken (cbcns.c:218-257): corrected runs spliced into the raw read
-                const uint64_t start = so.used;
-                const size_t ri = recs.size();
-                plan(T.tid, 0, T.T, T.T, T.num_can, T.num_ovlps, T.cutoff, 0, 0);
-                int last_raw = 0;
-                for (uint32_t k = 0; k < ns; ++k) {
-                    const int rf = sg[k].cns_from, rt = sg[k].cns_to;
-                    if (rf > last_raw) add_raw(T.tid, last_raw, rf);
-                    add_cns(sg[k], sd[k]);
-                    last_raw = rt;
-                }
-                if (last_raw < T.T) add_raw(T.tid, last_raw, T.T);
-                recs[ri].seq_len = (int)(so.used - start);
-                ctx->cc.cns_bases += so.used - start;
-                corrected[(size_t)T.tid] = 1;
-            }
-            std::vector<uint16_t>().swap(T.cov);
-        }
-        if (!so.reserve(so.used)) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
-        run_fills(fills, so.buf, ascii, reads, nthreads);
-        t_rec += ht.lap();
     }
+    JobShared sh;
+    sh.used = 0; sh.corrected = &corrected;
+    {
+        // upper bound of the output: a template emits at most its consensus pool (2 T + 1024, enforced by the kernel)
+        // plus its raw leftovers; every other read of the id range may be dumped whole
+        uint64_t bound = 64;
+        for (const Tpl& t : tpls) bound += (uint64_t)t.T * 3 + 1024;
+        for (int id = min_id; id < max_id; ++id) bound += reads->h_len[id];
+        sh.cap = bound;
+        sh.buf = (char*)malloc(bound);      // untouched pages cost nothing; shrunk to the used prefix at the end
+        if (!sh.buf) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    }
+    std::vector<std::vector<nb_cns_record>> chunk_recs(n_chunks);
+    std::vector<ChunkTimes> chunk_tm(n_chunks);
+    std::vector<int> worker_rc((size_t)n_workers, NB_OK);
+    std::vector<nb_ctx*> wctx((size_t)n_workers, ctx);
+    for (int w = 1; w < n_workers; ++w) {
+        int rc = nb_worker_ctx(ctx, w, &wctx[(size_t)w]);
+        if (rc) { free(sh.buf); return rc; }
+    }
+    std::atomic<size_t> next_chunk(0);
+    auto work = [&](int w) {
+        nb_ctx* wc = wctx[(size_t)w];
+        if (cudaSetDevice(wc->device) != cudaSuccess) { worker_rc[(size_t)w] = nb_fail(wc, NB_ECUDA, "cudaSetDevice failed"); return; }
+        for (;;) {
+            const size_t k = next_chunk.fetch_add(1);
+            if (k >= n_chunks) break;
+            if (cut[k] >= cut[k + 1]) continue;
+            const int rc = process_chunk(wc, reads, o, tpls, cans, cut[k], cut[k + 1], sh, chunk_recs[k], chunk_tm[k],
+                                         n_workers > 1 ? std::max(2u, nthreads / 2) : nthreads);
+            if (rc) { worker_rc[(size_t)w] = rc; next_chunk.store(n_chunks); break; }
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int w = 1; w < n_workers; ++w) th.emplace_back(work, w);
+        work(0);
+        for (auto& t : th) t.join();
+    }
+    for (int w = 1; w < n_workers; ++w) {               // fold the workers' counters into the job's context
+        nb_ctx* wc = wctx[(size_t)w];
+        ctx->launches += wc->launches; wc->launches = 0;
+        ctx->tm.h2d_bytes += wc->tm.h2d_bytes; ctx->tm.d2h_bytes += wc->tm.d2h_bytes;
+        ctx->cc.n_extensions += wc->cc.n_extensions; ctx->cc.n_block_aligns += wc->cc.n_block_aligns;
+        ctx->cc.n_dp_columns += wc->cc.n_dp_columns; ctx->cc.n_dp_word_updates += wc->cc.n_dp_word_updates;
+        ctx->cc.n_accepted += wc->cc.n_accepted; ctx->cc.n_tags += wc->cc.n_tags; ctx->cc.cns_bases += wc->cc.cns_bases;
+        memset(&wc->cc, 0, sizeof wc->cc); memset(&wc->tm, 0, sizeof wc->tm);
+    }
+    for (int w = 0; w < n_workers; ++w)
+        if (worker_rc[(size_t)w]) {
+            if (w) memcpy(ctx->err, wctx[(size_t)w]->err, sizeof ctx->err);
+            free(sh.buf);
+            return worker_rc[(size_t)w];
+        }
+    float ext_ms = 0, cns_ms = 0;
+    for (size_t k = 0; k < n_chunks; ++k) {
+        recs.insert(recs.end(), chunk_recs[k].begin(), chunk_recs[k].end());
+        ext_ms += chunk_tm[k].ext_ms; cns_ms += chunk_tm[k].cns_ms;
+    }
+    const double t_chunks = ht.lap();
     ctx->tm.extend_ms = ext_ms;
     ctx->tm.consensus_ms = cns_ms;
 
     // ---- reads of [min_id, max_id) that were never corrected go to raw_out whole (consensus_one_partition.c:173-194)
     fills.clear();
+    uint64_t used = sh.used.load();
     for (int id = min_id; id < max_id; ++id) {
         if (corrected[(size_t)id] || id % shard_count != shard_index) continue;
         const int L = (int)reads->h_len[id];
         nb_cns_record r;
         r.id = id; r.left = 0; r.right = L; r.org_size = L; r.num_can = 0; r.num_ovlps = 0; r.ident_cutoff = 0.0;
-        r.seq_offset = so.used; r.seq_len = L; r.is_raw = 1;
+        r.seq_offset = used; r.seq_len = L; r.is_raw = 1;
         recs.push_back(r);
-        Fill f; f.dst = so.used; f.len = (uint32_t)L; f.kind = 1; f.src = reads->h_off[id];
-        fills.push_back(f); so.used += f.len;
+        Fill f; f.dst = used; f.len = (uint32_t)L; f.kind = 1; f.src = reads->h_off[id];
+        fills.push_back(f); used += f.len;
     }
-    if (!so.reserve(so.used ? so.used : 1)) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
-    run_fills(fills, so.buf, NULL, reads, nthreads);
+    if (used > sh.cap) { free(sh.buf); return nb_fail(ctx, NB_ELIMIT, "output exceeds its upper bound"); }
+    run_fills(fills, sh.buf, NULL, reads, nthreads);
     ctx->cc.n_cns_records = recs.size();
 
     nb_cns_record* r_out = (nb_cns_record*)malloc(sizeof(nb_cns_record) * (recs.size() ? recs.size() : 1));
-    char* s_out = so.buf;
+    char* s_out = (char*)realloc(sh.buf, used ? used : 1);
+    if (!s_out) s_out = sh.buf;
     if (!r_out || !s_out) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
     if (!recs.empty()) memcpy(r_out, recs.data(), sizeof(nb_cns_record) * recs.size());
     t_tail += ht.lap();
-    if (trace)
-        fprintf(stderr, "[nb_consensus_job] host ms: setup %.1f replay %.1f gather %.1f ext(call) %.1f cns_prep %.1f cns(call) %.1f records %.1f tail %.1f | gpu ms: extend %.1f consensus %.1f\n",
-                t_setup, t_replay, t_gather, t_ext, t_prep, t_kern, t_rec, t_tail, ext_ms, cns_ms);
-    *out_recs = r_out; *n_recs = recs.size(); *out_seq = s_out; *out_seq_bytes = so.used;
+    if (trace) {
+        ChunkTimes s;
+        for (const ChunkTimes& c : chunk_tm) { s.replay += c.replay; s.gather += c.gather; s.ext += c.ext; s.prep += c.prep; s.kern += c.kern; s.rec += c.rec; s.wait += c.wait; s.ext_wall += c.ext_wall; }
+        fprintf(stderr, "[nb_consensus_job] %zu chunks on %d workers; wall ms: setup %.1f chunks %.1f tail %.1f | summed over chunks: replay %.1f gather %.1f "
+                        "gpu-wait %.1f ext(call) %.1f [extension phase wall %.1f] cns_prep %.1f cns(call) %.1f records %.1f | gpu ms: extend %.1f consensus %.1f\n",
+                n_chunks, n_workers, t_setup, t_chunks, t_tail, s.replay, s.gather, s.wait, s.ext, s.ext_wall, s.prep, s.kern, s.rec, ext_ms, cns_ms);
+    }
+    *out_recs = r_out; *n_recs = recs.size(); *out_seq = s_out; *out_seq_bytes = used;
     return NB_OK;
 }

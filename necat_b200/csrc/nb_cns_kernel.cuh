@@ -98,7 +98,8 @@ struct CnsParams {
     unsigned long long* bp;             // per level: 5 x 11-bit back pointers
     uint8_t*           rev;
     int                min_cov, min_size;
-    int                lanes;           // k_cns_dp / k_cns_walk: templates per warp (the other lanes idle)
+    int                lanes;           // k_cns_dp: templates per warp (the other lanes idle)
+    int                walk_lanes;      // k_cns_walk: likewise
     uint32_t*          error_flag;      // 1 = level capacity, 2 = link pool / link capacity, 4 = output capacity
     unsigned long long* counters;       // [0] levels, [1] columns (tags), [2] links
 };
@@ -360,16 +361,55 @@ struct CnsRun {
     int32_t g_level, g_b, g_t, g_delta;     // best node of the run (cns_aux.c:177-184), g_level < 0: none
 };
 
-// Flat loop: every iteration either advances to the next template position or scores one link, so the
-// templates sharing a warp stay converged although their link counts differ.  Per link: one 16-byte load of
-// the link and one 8-byte load of the predecessor's score.
+// One template per WARP.  The recurrence is a chain over template positions -- and, inside a position, over its
+// delta levels -- so the only parallelism inside a template is across the links of one level (1 to ~10).  That is
+// still what decides the kernel's duration: the longest template of a job has ~60 k positions, and a single thread
+// walking its ~280 k links and positions one after the other takes longer than all other templates together.  Here
+// the lanes of the warp take the links of the current position (lane = link), so a position costs one pass per delta
+// level instead of one iteration per link:
+//   * links are streamed through a 256-link ring in shared memory with cp.async, 128 links ahead of their use;
+//   * position records are loaded 32 at a time (lane = position), one chunk ahead, and handed out by shuffles;
+//   * node scores live in a 256-entry ring in shared memory indexed by the first link of the node; a predecessor is
+//     at most two positions back, so the ring misses only where two neighbouring positions hold more than SC_RING
+//     links -- those positions also spill their scores into link[].w (where the reference-shaped kernel kept them);
+//   * the links of a node are reduced with shuffles (max score, ties to the lower predecessor rank), the five 11-bit
+//     back pointers of a level are OR-reduced into one u64, the best node of a run is tracked per lane and reduced
+//     when the run ends (ties to the lowest link index = the first one in the reference's traversal order).
+// A position with more than FAST_MAX links is handed to lane 0, which scores it link by link.
+#define CNS_DP_LINK_RING 256
+
+__device__ __forceinline__ void cns_cp_async16(void* dst_smem, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(nb_smem_addr(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cns_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cns_cp_async_wait(int pending)      // at most `pending` (0..3) groups stay in flight
+{
+    if (pending <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else asm volatile("cp.async.wait_group 3;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t cns_bp_code(uint32_t key)       // back pointer of a node whose best link has this key
+{
+    const uint32_t rank = key & 0xffff, pb = (key >> 16) & 7;
+    if (rank == 0) return 7u;
+    return (((key >> 24) == 0 ? (rank - 1 - cns_char_rank(pb)) / 5u : 0u) << 3) | pb;
+}
+
+template <int FAST_MAX, int SC_RING>
 __global__ void __launch_bounds__(128)
 k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun)
 {
-    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((int)(gt & 31) >= P.lanes) return;
-    const uint32_t ti = (gt >> 5) * (uint32_t)P.lanes + (gt & 31);
+    __shared__ __align__(16) uint4 s_links[4][CNS_DP_LINK_RING];
+    __shared__ double s_score[4][SC_RING];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t ti = blockIdx.x * 4 + wid;
     if (ti >= P.n_tpl) return;
+    uint4* LK = s_links[wid];
+    double* SC = s_score[wid];
+    const uint32_t lt_mask = (1u << lane) - 1, le_mask = lt_mask | (1u << lane);
     const CnsTemplate TP = P.tpl[ti];
     const int T = TP.T;
     CnsPos* pos = P.pos + TP.pos_base;
@@ -377,89 +417,167 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
     unsigned long long* bp = P.bp + TP.level_base;
     CnsRun* my_runs = runs + TP.seg_first;
     uint32_t nrun = 0, fail = 0, level = 0;
+    // best node of the current run, per lane
     double g_best = -1.0;
     int g_level = -1, g_b = -1, g_t = 0, g_delta = 0, run_from = 0;
-    int t = -1;
-    uint32_t e = 0, fl = 0;                     // links [.., e) of position t
-    double pen = 0.0;
-    bool have_node = false, have_level = false;
-    uint32_t cur_d = 0, cur_b = 0, node_first = 0, best_rank = 0, code = 7;
-    double best = -1.0;
-    bool chosen = false;
-    unsigned long long packed = 0;
-    uint32_t x = 0;
-    // the link and position records are streamed: each is loaded one iteration before it is used
-    uint4 pr_next = *reinterpret_cast<const uint4*>(pos);           // pos[t + 1]
-    uint4 pr_next2 = *reinterpret_cast<const uint4*>(pos + 1);      // pos[t + 2]
-    uint4 lr_next = *reinterpret_cast<const uint4*>(link);          // link[x]
-    for (;;) {
-        if (x == e) {
-            // ---- finish the position, move to the next one
-            if (have_node) {
-                const double ns = chosen ? best : -1.0;
-                link[node_first].w = ns;                                // node score lives in the node's first link
-                packed |= (unsigned long long)(chosen ? code : 7u) << (11 * cur_b);
-                if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)cur_d; }
-                have_node = false;
+    uint32_t g_x = 0xffffffffu;
+    // link staging: batches of 32 links, [.., fill) issued, [.., landed) known to have arrived
+    uint32_t fill = 0, landed = 0;
+    auto issue_batch = [&]() {
+        cns_cp_async16(LK + ((fill + lane) & (CNS_DP_LINK_RING - 1)), link + fill + lane);     // the pool has slack past the end
+        cns_cp_async_commit();
+        fill += 32;
+    };
+    auto load_pos = [&](int tbase) {
+        const int idx = tbase + lane;
+        return *reinterpret_cast<const uint4*>(pos + (idx <= T ? idx : T));
+    };
+    uint4 pc = load_pos(0), pn = load_pos(32);
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        // lane j describes position t0 + j: first link, number of links, flags, whether its scores must be spilled
+        const uint32_t n0 = __shfl_sync(0xffffffffu, pn.x, 0), n1 = __shfl_sync(0xffffffffu, pn.x, 1);
+        uint32_t e1 = __shfl_down_sync(0xffffffffu, pc.x, 1), e2 = __shfl_down_sync(0xffffffffu, pc.x, 2);
+        if (lane == 31) { e1 = n0; e2 = n1; }
+        if (lane == 30) e2 = n0;
+        const bool inside = t0 + lane < T;
+        const uint32_t my_n = inside ? e1 - pc.x : 0u;
+        const uint32_t my_info = (my_n & 0xffffu) | ((inside ? pc.z & 7u : 0u) << 16) | ((e2 - pc.x > (uint32_t)SC_RING ? 1u : 0u) << 20);
+        const int jn = T - t0 < 32 ? T - t0 : 32;
+        for (int j = 0; j < jn; ++j) {
+            const int t = t0 + j;
+            const uint32_t s = __shfl_sync(0xffffffffu, pc.x, j);
+            const uint32_t info = __shfl_sync(0xffffffffu, my_info, j);
+            const uint32_t n = info & 0xffffu, fl = (info >> 16) & 7u;
+            const bool spill = (info >> 20) & 1u;
+            if (fl & 2) { g_best = -1.0; g_level = -1; g_x = 0xffffffffu; run_from = t; }
+            if ((fl & 1) && n > 0) {
+                const int cov = __shfl_sync(0xffffffffu, (int)pc.y, j);
+                const double pen = __dmul_rn(0.2, (double)cov);                 // 0.4 * 0.5 * coverage (cns_aux.c:164)
+                if (lane == 0) pos[t].first_level = level;
+                const uint32_t e = s + n;
+                if (n <= (uint32_t)FAST_MAX) {
+                    // ---- staging: the links of this position must have landed; keep 128 links ahead
+                    if ((s & ~31u) > fill) { cns_cp_async_wait(0); fill = s & ~31u; landed = fill; }      // after a position that bypassed the ring
+                    while (fill < e + 128 && fill + 32 - (s & ~31u) <= CNS_DP_LINK_RING) issue_batch();
+                    if (e > landed) {
+                        const uint32_t pending = (fill - ((e + 31) & ~31u)) >> 5;
+                        cns_cp_async_wait((int)pending);
+                        landed = fill - 32 * (pending > 3 ? 3 : pending);
+                        __syncwarp();
+                    }
+                    const bool act = (uint32_t)lane < n;
+                    const uint32_t x = s + lane;
+                    uint4 lr = make_uint4(0, CNS_NOPRED, 0, 0);
+                    if (act) lr = LK[x & (CNS_DP_LINK_RING - 1)];
+                    const uint32_t key = lr.x, pred = lr.y;
+                    const double base = __dsub_rn(__hiloint2double((int)lr.w, (int)lr.z), pen);
+                    const bool isstart = act && ((key >> 23) & 1);
+                    uint32_t lf = __ballot_sync(0xffffffffu, act && ((key >> 19) & 1));
+                    while (lf) {                                                // one pass per delta level
+                        const int lo = __ffs(lf) - 1;
+                        lf &= lf - 1;
+                        const int hi = lf ? __ffs(lf) - 1 : (int)n;
+                        const bool in = lane >= lo && lane < hi;
+                        double sc = base;
+                        if (in && pred != CNS_NOPRED)                           // never-scored predecessors count 0 (cns_aux.c:63-70)
+                            sc = __dadd_rn(base, (x - pred < (uint32_t)SC_RING) ? SC[pred & (SC_RING - 1)] : link[pred].w);
+                        const uint32_t nf = __ballot_sync(0xffffffffu, in && isstart);
+                        const uint32_t above = nf & ~le_mask;
+                        const int nend = above ? __ffs(above) - 1 : hi;         // my node ends here (meaningful in its first lane)
+                        const int len = (in && isstart) ? nend - lane : 0;
+                        const int maxlen = __reduce_max_sync(0xffffffffu, len);
+                        double best = sc;
+                        uint32_t bkey = key;
+                        bool chosen = in && sc > -1.0;
+                        for (int k = 1; k < maxlen; ++k) {                      // the other links of the node, one shuffle distance at a time
+                            const double osc = __shfl_down_sync(0xffffffffu, sc, k);
+                            const uint32_t okey = __shfl_down_sync(0xffffffffu, key, k);
+                            if (lane + k < nend && osc > -1.0 &&
+                                (!chosen || osc > best || (osc == best && (okey & 0xffff) < (bkey & 0xffff)))) { best = osc; bkey = okey; chosen = true; }
+                        }
+                        unsigned long long contrib = 0;
+                        if (in && isstart) {
+                            const double ns = chosen ? best : -1.0;
+                            SC[x & (SC_RING - 1)] = ns;
+                            if (spill) link[x].w = ns;
+                            const uint32_t b = (key >> 20) & 7;
+                            contrib = (unsigned long long)(chosen ? cns_bp_code(bkey) : 7u) << (11 * b);
+                            if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)b; g_t = t; g_delta = (int)(key >> 24); g_x = x; }
+                        }
+                        const uint32_t plo = __reduce_or_sync(0xffffffffu, (uint32_t)contrib);
+                        const uint32_t phi = __reduce_or_sync(0xffffffffu, (uint32_t)(contrib >> 32));
+                        if (lane == 0) {
+                            if (level < TP.level_cap) bp[level] = ((unsigned long long)phi << 32) | plo; else fail |= 1;
+                        }
+                        ++level;
+                        __syncwarp();
+                    }
+                } else {
+                    // ---- a crowded position: lane 0 scores it link by link, straight from HBM
+                    if (lane == 0) {
+                        bool have_node = false, have_level = false, chosen = false;
+                        uint32_t cur_d = 0, cur_b = 0, node_first = 0, best_key = 0;
+                        double best = -1.0;
+                        unsigned long long packed = 0;
+                        auto close_node = [&]() {
+                            const double ns = chosen ? best : -1.0;
+                            SC[node_first & (SC_RING - 1)] = ns;
+                            if (spill) link[node_first].w = ns;
+                            packed |= (unsigned long long)(chosen ? cns_bp_code(best_key) : 7u) << (11 * cur_b);
+                            if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)cur_d; g_x = node_first; }
+                        };
+                        for (uint32_t x = s; x < e; ++x) {
+                            const uint4 lr = *reinterpret_cast<const uint4*>(link + x);
+                            const uint32_t key = lr.x, pred = lr.y;
+                            if ((key >> 23) & 1) {
+                                if (have_node) close_node();
+                                if ((key >> 19) & 1) {
+                                    if (have_level) { if (level < TP.level_cap) bp[level] = packed; else fail |= 1; ++level; }
+                                    have_level = true; packed = 0;
+                                }
+                                have_node = true; cur_b = (key >> 20) & 7; cur_d = key >> 24; node_first = x; best = -1.0; best_key = 0; chosen = false;
+                            }
+                            double sc = __dsub_rn(__hiloint2double((int)lr.w, (int)lr.z), pen);
+                            if (pred != CNS_NOPRED)
+                                sc = __dadd_rn(sc, (x - pred < (uint32_t)SC_RING) ? SC[pred & (SC_RING - 1)] : link[pred].w);
+                            const bool better = chosen ? (sc > best || (sc == best && (key & 0xffff) < (best_key & 0xffff))) : (sc > -1.0);
+                            if (better) { best = sc; best_key = key; chosen = true; }
+                        }
+                        if (have_node) close_node();
+                        if (have_level) { if (level < TP.level_cap) bp[level] = packed; else fail |= 1; ++level; }
+                    }
+                    level = __shfl_sync(0xffffffffu, level, 0);
+                    __syncwarp();
+                }
             }
-            if (have_level) {
-                if (level < TP.level_cap) bp[level] = packed; else fail |= 1;
-                ++level; have_level = false;
-            }
-            if (t >= 0 && (fl & 4)) {                                   // the run ends at t
-                if (nrun < TP.seg_cap) {
-                    CnsRun r; r.from = run_from; r.to = t + 1; r.g_level = g_level; r.g_b = g_b; r.g_t = g_t; r.g_delta = g_delta;
+            if (fl & 4) {
+                // ---- the run ends at t: its best node (cns_aux.c:177-184) = highest score, first in traversal order
+                double mx = g_best;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, mx, d); mx = o > mx ? o : mx; }
+                const uint32_t cand = __ballot_sync(0xffffffffu, g_best == mx);
+                const uint32_t mnx = __reduce_min_sync(0xffffffffu, g_best == mx ? g_x : 0xffffffffu);
+                const uint32_t win = __ballot_sync(0xffffffffu, g_best == mx && g_x == mnx) & cand;
+                const int wl = __ffs(win) - 1;
+                const int r_level = __shfl_sync(0xffffffffu, g_level, wl), r_b = __shfl_sync(0xffffffffu, g_b, wl);
+                const int r_t = __shfl_sync(0xffffffffu, g_t, wl), r_delta = __shfl_sync(0xffffffffu, g_delta, wl);
+                if (lane == 0 && nrun < TP.seg_cap) {
+                    CnsRun r; r.from = run_from; r.to = t + 1; r.g_level = r_level; r.g_b = r_b; r.g_t = r_t; r.g_delta = r_delta;
                     my_runs[nrun] = r;
                 }
                 ++nrun;
             }
-            ++t;
-            if (t >= T) break;
-            const uint4 pr = pr_next;                                   // start, cov, flags, -
-            pr_next = pr_next2;
-            pr_next2 = *reinterpret_cast<const uint4*>(pos + (t + 2 <= T ? t + 2 : T));
-            fl = pr.z;
-            e = pr_next.x;                                              // pos[t + 1].start
-            if (fl & 2) { g_best = -1.0; g_level = -1; run_from = t; }
-            if (fl & 1) { pen = __dmul_rn(0.2, (double)(int)pr.y); pos[t].first_level = level; }   // 0.4 * 0.5 * coverage (cns_aux.c:164)
-            continue;
         }
-        // ---- one link
-        const uint4 lr = lr_next;
-        lr_next = *reinterpret_cast<const uint4*>(link + x + 1);        // capacity leaves room past the last link
-        const uint32_t key = lr.x, pred = lr.y;
-        const double w = __hiloint2double((int)lr.w, (int)lr.z);
-        const uint32_t d = key >> 24, b = (key >> 20) & 7;
-        if ((key >> 23) & 1) {                                          // a new node starts: close the previous one
-            if (have_node) {
-                const double ns = chosen ? best : -1.0;
-                link[node_first].w = ns;
-                packed |= (unsigned long long)(chosen ? code : 7u) << (11 * cur_b);
-                if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)cur_d; }
-            }
-            if ((key >> 19) & 1) {                                      // ... and a new delta level
-                if (have_level) {
-                    if (level < TP.level_cap) bp[level] = packed; else fail |= 1;
-                    ++level;
-                }
-                have_level = true; packed = 0;
-            }
-            have_node = true; cur_b = b; cur_d = d; node_first = x; best = -1.0; best_rank = 0; code = 7; chosen = false;
-        }
-        const uint32_t rank = key & 0xffff, pb = (key >> 16) & 7;
-        double sc = __dsub_rn(w, pen);
-        if (pred != CNS_NOPRED) sc = __dadd_rn(sc, link[pred].w);      // never-scored predecessors count 0 (cns_aux.c:63-70)
-        const bool better = chosen ? (sc > best || (sc == best && rank < best_rank)) : (sc > -1.0);
-        if (better) {
-            best = sc; best_rank = rank; chosen = true;
-            code = rank == 0 ? 7u : (((d == 0 ? (rank - 1 - cns_char_rank(pb)) / 5u : 0u) << 3) | pb);
-        }
-        ++x;
+        pc = pn;
+        pn = load_pos(t0 + 64);
     }
-    if (fail) atomicOr(P.error_flag, fail);
-    if (nrun > TP.seg_cap) { atomicOr(P.error_flag, 4u); nrun = TP.seg_cap; }
-    tpl_nrun[ti] = nrun;
-    atomicAdd(P.counters + 0, (unsigned long long)level);
+    cns_cp_async_wait(0);
+    if (lane == 0) {
+        if (fail) atomicOr(P.error_flag, fail);
+        if (nrun > TP.seg_cap) { atomicOr(P.error_flag, 4u); nrun = TP.seg_cap; }
+        tpl_nrun[ti] = nrun;
+        atomicAdd(P.counters + 0, (unsigned long long)level);
+    }
 }
 
 // Walk-back of the runs of one template per thread (cns_aux.c:187-212).
@@ -467,8 +585,8 @@ __global__ void __launch_bounds__(128)
 k_cns_walk(CnsParams P, const CnsRun* __restrict__ runs, const uint32_t* __restrict__ tpl_nrun)
 {
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((int)(gt & 31) >= P.lanes) return;
-    const uint32_t ti = (gt >> 5) * (uint32_t)P.lanes + (gt & 31);
+    if ((int)(gt & 31) >= P.walk_lanes) return;
+    const uint32_t ti = (gt >> 5) * (uint32_t)P.walk_lanes + (gt & 31);
     if (ti >= P.n_tpl) return;
     const CnsTemplate TP = P.tpl[ti];
     const CnsPos* pos = P.pos + TP.pos_base;

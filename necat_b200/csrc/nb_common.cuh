@@ -10,6 +10,7 @@
 #include "../../include/necat_b200.h"
 
 #define NB_SMS 148          // B200: 2 dies x 74 SMs
+#define NB_MAX_WORKERS 4    // pipeline workers of nb_consensus_job (the context itself is worker 0)
 
 struct nb_ctx {
     int          device;
@@ -27,6 +28,9 @@ struct nb_ctx {
     void*        ext_mat;        // walk-back scratch of the extension kernel (kept across calls)
     size_t       ext_mat_slots;
     void*        dev_cache;      // NbDevCache*: device blocks kept for reuse (cudaMalloc/cudaFree are slow and synchronising)
+    nb_ctx*      workers[NB_MAX_WORKERS];   // [1..]: shadow contexts of the pipeline workers (own stream, events, staging,
+                                            // scratch; they share dev_cache with their parent), created on first use
+    int          is_worker;
 };
 
 struct nb_volume {
@@ -53,11 +57,12 @@ struct nb_index {
 
 extern char g_nb_err[512];
 
-// caching device allocator (per context, single stream): blocks return to the cache on release
+// caching device allocator (per context, thread-safe; a block is released only after the work using it was synchronised)
 int  nb_dev_alloc(nb_ctx* ctx, void** p, size_t bytes);
 void nb_dev_release(nb_ctx* ctx, void* p);
 void nb_dev_cache_destroy(nb_ctx* ctx);
 int  nb_pinned_reserve(nb_ctx* ctx, size_t bytes);      // ctx->pinned holds at least `bytes` afterwards
+int  nb_worker_ctx(nb_ctx* parent, int w, nb_ctx** out);    // the w-th pipeline worker of `parent` (1 <= w < NB_MAX_WORKERS)
 
 #ifdef __cplusplus
 #include <vector>

@@ -1,17 +1,20 @@
 // nb_core.cu -- context, error handling, volume upload (C-ABI part 1).
 #include <stdarg.h>
 
+#include <mutex>
+
 #include "nb_common.cuh"
 
 char g_nb_err[512] = "";
 
 struct NbDevBlock { void* p; size_t bytes; bool used; };
-struct NbDevCache { std::vector<NbDevBlock> blocks; };
+struct NbDevCache { std::vector<NbDevBlock> blocks; std::mutex mu; };
 
 int nb_dev_alloc(nb_ctx* ctx, void** p, size_t bytes)
 {
     if (!ctx->dev_cache) ctx->dev_cache = new NbDevCache();
     NbDevCache* C = (NbDevCache*)ctx->dev_cache;
+    std::lock_guard<std::mutex> lock(C->mu);
     bytes = (bytes + 511) & ~(size_t)511;
     int best = -1;
     for (size_t i = 0; i < C->blocks.size(); ++i) {
@@ -42,6 +45,7 @@ void nb_dev_release(nb_ctx* ctx, void* p)
 {
     if (!p || !ctx || !ctx->dev_cache) return;
     NbDevCache* C = (NbDevCache*)ctx->dev_cache;
+    std::lock_guard<std::mutex> lock(C->mu);
     for (auto& b : C->blocks) if (b.p == p) { b.used = false; return; }
     cudaFree(p);
 }
@@ -80,6 +84,8 @@ extern "C" const char* nb_version(void) { return "necat_b200 0.1 (sm_100a)"; }
 
 extern "C" const char* nb_last_error(const nb_ctx* ctx) { return ctx ? ctx->err : g_nb_err; }
 
+static int nb_ctx_init_streams(nb_ctx* c);
+
 extern "C" int nb_ctx_create(int device, nb_ctx** out)
 {
     if (!out) return nb_fail(NULL, NB_EINVAL, "nb_ctx_create: out is NULL");
@@ -99,6 +105,13 @@ extern "C" int nb_ctx_create(int device, nb_ctx** out)
     nb_ctx* c = (nb_ctx*)calloc(1, sizeof(nb_ctx));
     if (!c) return nb_fail(NULL, NB_ENOMEM, "out of host memory");
     c->device = device;
+    { const int rc = nb_ctx_init_streams(c); if (rc) { free(c); return rc; } }
+    *out = c;
+    return NB_OK;
+}
+
+static int nb_ctx_init_streams(nb_ctx* c)
+{
     NB_CUDA(NULL, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     NB_CUDA(NULL, cudaEventCreate(&c->ev0));
     NB_CUDA(NULL, cudaEventCreate(&c->ev1));
@@ -106,7 +119,25 @@ extern "C" int nb_ctx_create(int device, nb_ctx** out)
     NB_CUDA(NULL, cudaEventCreate(&c->ev3));
     for (int i = 0; i < 2; ++i) NB_CUDA(NULL, cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
     for (int i = 0; i < 3; ++i) NB_CUDA(NULL, cudaEventCreateWithFlags(&c->aux_ev[i], cudaEventDisableTiming));
-    *out = c;
+    return NB_OK;
+}
+
+int nb_worker_ctx(nb_ctx* parent, int w, nb_ctx** out)
+{
+    if (w < 1 || w >= NB_MAX_WORKERS) return nb_fail(parent, NB_EINVAL, "worker index %d out of range", w);
+    if (!parent->workers[w]) {
+        if (!parent->dev_cache) parent->dev_cache = new NbDevCache();
+        nb_ctx* c = (nb_ctx*)calloc(1, sizeof(nb_ctx));
+        if (!c) return nb_fail(parent, NB_ENOMEM, "out of host memory");
+        c->device = parent->device;
+        c->is_worker = 1;
+        c->dev_cache = parent->dev_cache;
+        NB_CUDA(parent, cudaSetDevice(parent->device));
+        const int rc = nb_ctx_init_streams(c);
+        if (rc) { free(c); memcpy(parent->err, g_nb_err, sizeof g_nb_err); return rc; }
+        parent->workers[w] = c;
+    }
+    *out = parent->workers[w];
     return NB_OK;
 }
 
@@ -114,6 +145,18 @@ extern "C" void nb_ctx_destroy(nb_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (int w = 1; w < NB_MAX_WORKERS; ++w) {
+        nb_ctx* k = c->workers[w];
+        if (!k) continue;
+        cudaStreamSynchronize(k->stream);
+        cudaEventDestroy(k->ev0); cudaEventDestroy(k->ev1); cudaEventDestroy(k->ev2); cudaEventDestroy(k->ev3);
+        cudaStreamDestroy(k->stream);
+        for (int i = 0; i < 2; ++i) cudaStreamDestroy(k->aux[i]);
+        for (int i = 0; i < 3; ++i) cudaEventDestroy(k->aux_ev[i]);
+        if (k->ext_mat) cudaFree(k->ext_mat);
+        if (k->pinned) cudaFreeHost(k->pinned);
+        free(k);
+    }
     cudaStreamSynchronize(c->stream);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);

@@ -13,12 +13,12 @@ OC2CNS = os.path.join(util.BIN_DIR, "oc2cns")
 OC2PCAN = os.path.join(util.BIN_DIR, "oc2pcan")
 
 
-def _run_cns(tmp_path, wrk, cand, opts, tag):
+def _run_cns(tmp_path, wrk, cand, opts, tag, env=None):
     c = str(tmp_path / f"cand_{tag}.bin")
     shutil.copy(cand, c)
     util.run([OC2PCAN, "-t", "1", wrk, c])
     cns, raw = str(tmp_path / f"{tag}_cns.fasta"), str(tmp_path / f"{tag}_raw.fasta")
-    util.run([OC2CNS] + opts.split() + [wrk, c, cns, raw])
+    util.run([OC2CNS] + opts.split() + [wrk, c, cns, raw], env=dict(os.environ, **(env or {})))
     return cns, raw
 
 
@@ -62,5 +62,26 @@ def test_cns_multi_volume(built, tmp_path):
             out.write(open(p, "rb").read())
     g_cns, g_raw = _run_cns(tmp_path, wrk, cand, util.CNS_SENSITIVE, "gpu")
     o_cns, o_raw = _run_oracle(tmp_path, wrk, cand, util.CNS_SENSITIVE, "oracle")
+    assert util.fasta_canon(g_cns) == util.fasta_canon(o_cns)
+    assert util.fasta_canon(g_raw) == util.fasta_canon(o_raw)
+
+
+@pytest.mark.parametrize("env", [
+    {"NB_CNS_DP_TEST": "1"},                        # k_cns_dp with a 3-link fast path and a score ring of 8: serial + spill paths
+    {"NB_CNS_WALK_LANES": "32"},
+    {"NB_CNS_SLICES": "4"},
+    {"NB_CNS_CHUNKS": "5", "NB_CNS_PIPES": "3"},    # the chunk pipeline: three workers on their own streams
+    {"NB_CNS_CHUNKS": "2", "NB_CNS_PIPES": "1"},
+    {"NB_CNS_GROUPS": "4", "NB_CNS_GROUPS_MIN": "8"},   # extension rounds of four template groups interleaved on the GPU
+])
+def test_cns_kernel_variants(built, tmp_path, env):
+    """The tunables of the consensus kernels (templates per warp, score-ring size, sliced launch) change
+    the schedule, never the result."""
+    wrk, _ = util.make_workdir(tmp_path, genome=70_000, depth=30, seed=46, err=0.12)
+    cand = str(tmp_path / "cand.bin")
+    util.run_pmov(util.ORACLE_CLI, util.PM_SENSITIVE, wrk, 0, cand)
+    g_cns, g_raw = _run_cns(tmp_path, wrk, cand, util.CNS_SENSITIVE, "gpu", env=env)
+    o_cns, o_raw = _run_oracle(tmp_path, wrk, cand, util.CNS_SENSITIVE, "oracle")
+    assert len(util.fasta_canon(o_cns)) > 20
     assert util.fasta_canon(g_cns) == util.fasta_canon(o_cns)
     assert util.fasta_canon(g_raw) == util.fasta_canon(o_raw)

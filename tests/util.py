@@ -38,7 +38,11 @@ def make_workdir(path, genome=100_000, depth=20, seed=7, vol_size=2_000_000_000,
 
 
 def run(cmd, **kw):
-    return subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, **kw)
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, **kw)
+    if p.returncode:
+        raise RuntimeError("%s exited with %d\nstdout: %s\nstderr: %s" % (" ".join(map(str, cmd)), p.returncode,
+                           p.stdout[-2000:].decode(errors="replace"), p.stderr[-2000:].decode(errors="replace")))
+    return p
 
 
 def run_pmov(binary, opts, wrk, vid, out, prefix=()):
