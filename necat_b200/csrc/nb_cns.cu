@@ -278,7 +278,7 @@ struct JobShared {
                                         // what overlaps is the host work of one chunk with the kernels of another
 };
 
-struct ChunkTimes { double replay = 0, gather = 0, ext = 0, prep = 0, kern = 0, rec = 0, wait = 0, ext_wall = 0; float ext_ms = 0, cns_ms = 0; };
+struct ChunkTimes { double replay = 0, gather = 0, ext = 0, prep = 0, kern = 0, rec = 0, wait = 0, ext_wall = 0, init = 0; float ext_ms = 0, cns_ms = 0; };
 
 // Extension rounds + consensus + records of the templates [c0, c1): everything the GPU does for them runs on the
 // stream of `ctx` (a pipeline worker: its own stream, events, staging buffer and walk-back scratch).
@@ -287,7 +287,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
 {
     cudaStream_t st = ctx->stream;
     HostTimer ht;
-    double t_replay = 0, t_gather = 0, t_ext = 0, t_prep = 0, t_kern = 0, t_rec = 0, t_wait = 0;
+    double t_replay = 0, t_gather = 0, t_ext = 0, t_prep = 0, t_kern = 0, t_rec = 0, t_wait = 0, t_init = 0;
     float ext_ms = 0, cns_ms = 0;
     std::vector<Fill> fills;
     std::vector<uint8_t>& corrected = *sh.corrected;
@@ -305,13 +305,6 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         ChunkTimes tm;
         int rc = NB_OK;
     };
-    for (size_t t = c0; t < c1; ++t) { tpls[t].cov.assign((size_t)tpls[t].T + 1, 0); tpls[t].n_below = o.max_cov > 0 ? tpls[t].T : 0; }
-    // round 0 requests: the first 50 candidates (phase 1), or the first window with -u 1
-    for (size_t t = c0; t < c1; ++t) {
-        Tpl& T = tpls[t];
-        T.request.clear();
-        if (!o.use_fixed_ident_cutoff) for (size_t k = 0; k < T.n && k < 50; ++k) T.request.push_back(k);
-    }
     const char* env_groups = getenv("NB_CNS_GROUPS");
     int n_groups = env_groups ? atoi(env_groups) : 3;
     const char* env_gmin = getenv("NB_CNS_GROUPS_MIN");       // (tests lower it to run small sets through several groups)
@@ -345,6 +338,28 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         if (cudaSetDevice(wc->device) != cudaSuccess) return nb_fail(wc, NB_ECUDA, "cudaSetDevice failed");
         cudaStream_t gst = wc->stream;
         HostTimer gt;
+        {
+            // coverage arrays (2 bytes per template base) and the round-0 requests: the first 50 candidates (phase 1),
+            // or nothing with -u 1 (the replay then asks for the first window)
+            auto init = [&](size_t a, size_t b) {
+                for (size_t t = a; t < b; ++t) {
+                    Tpl& T = tpls[t];
+                    T.cov.assign((size_t)T.T + 1, 0); T.n_below = o.max_cov > 0 ? T.T : 0;
+                    T.request.clear();
+                    if (!o.use_fixed_ident_cutoff) for (size_t k = 0; k < T.n && k < 50; ++k) T.request.push_back(k);
+                }
+            };
+            const size_t nt = g.t1 - g.t0, per = (nt + nthreads - 1) / nthreads;
+            std::vector<std::thread> th;
+            for (unsigned w = 1; w < nthreads && per; ++w) {
+                const size_t a = g.t0 + w * per, b = std::min(g.t1, a + per);
+                if (a >= b) break;
+                th.emplace_back(init, a, b);
+            }
+            init(g.t0, std::min(g.t1, g.t0 + per));
+            for (auto& x : th) x.join();
+        }
+        g.tm.prep += gt.lap();
         for (int round = 0;; ++round) {
             if (round > 0 || o.use_fixed_ident_cutoff) {
                 // replay in parallel over templates
@@ -426,7 +441,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         ExtGroup& g = groups[(size_t)k];
         if (g.rc) { if (g.wc != ctx) memcpy(ctx->err, g.wc->err, sizeof ctx->err); return g.rc; }
         for (size_t t = g.t0; t < g.t1; ++t) group_of[t - c0] = (uint8_t)k;
-        t_replay += g.tm.replay; t_gather += g.tm.gather; t_wait += g.tm.wait; t_ext += g.tm.ext; ext_ms += g.tm.ext_ms;
+        t_replay += g.tm.replay; t_gather += g.tm.gather; t_wait += g.tm.wait; t_ext += g.tm.ext; ext_ms += g.tm.ext_ms; t_init += g.tm.prep;
         if (g.wc != ctx) {                              // fold the worker's counters into this context
             nb_ctx* wc = g.wc;
             ctx->launches += wc->launches; wc->launches = 0;
@@ -500,7 +515,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         d_seq_pool = P.seq_pool;
         if ((rc = D.get(&P.next_tpl, 1))) return rc;
         if ((rc = D.get(&P.pos, pos_total))) return rc;
-        if ((rc = D.get(&P.link, link_total + 64))) return rc;      // k_cns_dp stages whole chunks: slack past the last link
+        if ((rc = D.get(&P.link, link_total + 512))) return rc;     // k_cns_dp stages batches of 32 links up to 160 links ahead: slack past the last link
         if ((rc = D.get(&P.bp, level_total))) return rc;
         if ((rc = D.get(&P.rev, level_total))) return rc;
         const unsigned links_grid = NB_SMS * 5;          // 20 warps per SM (shared-memory bound)
@@ -693,7 +708,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
     for (auto& f : fills) f.dst += base;
     run_fills(fills, sh.buf, ascii, reads, nthreads);
     t_rec += ht.lap();
-    tms.replay = t_replay; tms.gather = t_gather; tms.ext = t_ext; tms.prep = t_prep; tms.kern = t_kern; tms.rec = t_rec; tms.wait = t_wait; tms.ext_wall = t_ext_wall;
+    tms.replay = t_replay; tms.gather = t_gather; tms.ext = t_ext; tms.prep = t_prep; tms.kern = t_kern; tms.rec = t_rec; tms.wait = t_wait; tms.ext_wall = t_ext_wall; tms.init = t_init;
     tms.ext_ms = ext_ms; tms.cns_ms = cns_ms;
     return NB_OK;
 }
@@ -915,10 +930,10 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     t_tail += ht.lap();
     if (trace) {
         ChunkTimes s;
-        for (const ChunkTimes& c : chunk_tm) { s.replay += c.replay; s.gather += c.gather; s.ext += c.ext; s.prep += c.prep; s.kern += c.kern; s.rec += c.rec; s.wait += c.wait; s.ext_wall += c.ext_wall; }
+        for (const ChunkTimes& c : chunk_tm) { s.replay += c.replay; s.gather += c.gather; s.ext += c.ext; s.prep += c.prep; s.kern += c.kern; s.rec += c.rec; s.wait += c.wait; s.ext_wall += c.ext_wall; s.init += c.init; }
         fprintf(stderr, "[nb_consensus_job] %zu chunks on %d workers; wall ms: setup %.1f chunks %.1f tail %.1f | summed over chunks: replay %.1f gather %.1f "
                         "gpu-wait %.1f ext(call) %.1f [extension phase wall %.1f] cns_prep %.1f cns(call) %.1f records %.1f | gpu ms: extend %.1f consensus %.1f\n",
-                n_chunks, n_workers, t_setup, t_chunks, t_tail, s.replay, s.gather, s.wait, s.ext, s.ext_wall, s.prep, s.kern, s.rec, ext_ms, cns_ms);
+                n_chunks, n_workers, t_setup, t_chunks, t_tail, s.init, s.replay, s.gather, s.wait, s.ext, s.ext_wall, s.prep, s.kern, s.rec, ext_ms, cns_ms);
     }
     *out_recs = r_out; *n_recs = recs.size(); *out_seq = s_out; *out_seq_bytes = used;
     return NB_OK;
