@@ -466,31 +466,53 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
     static const int kWalkLanes = getenv("NB_CNS_WALK_LANES") ? atoi(getenv("NB_CNS_WALK_LANES")) : 1;
     static const int kDpTest = getenv("NB_CNS_DP_TEST") ? atoi(getenv("NB_CNS_DP_TEST")) : 0;   // 1 = test build of k_cns_dp: tiny fast path and score ring
     if (kSort) std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tpls[a].T != tpls[b].T ? tpls[a].T > tpls[b].T : a < b; });
-    for (size_t t : order) {
-        Tpl& T = tpls[t];
-        CnsTemplate ct;
-        memset(&ct, 0, sizeof ct);
-        ct.aln_first = (uint32_t)alns.size(); ct.n_aln = (uint32_t)T.acc.size(); ct.T = T.T;
-        uint64_t cols = 0;
-        const ExtGroup& G = groups[group_of[t - c0]];
-        for (const Accepted& a : T.acc) {
-            const Can& c = cans[T.first + (size_t)a.can];
-            const nb_alignment& r = G.res[(size_t)c.res];
-            CnsAln ca;
-            ca.ops = G.res_ops[(size_t)c.res]; ca.qseq_off = reads->h_off[c.qid];
-            ca.aln_size = r.aln_size; ca.toff = r.toff; ca.tend = r.tend; ca.qstart = r.qoff;
-            ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight;
-            alns.push_back(ca);
-            cols += (uint64_t)r.aln_size;
+    dt.resize(order.size()); dt_tpl.resize(order.size());
+    {
+        uint32_t aln_total = 0;
+        for (size_t x = 0; x < order.size(); ++x) {
+            const Tpl& T = tpls[order[x]];
+            CnsTemplate& ct = dt[x];
+            memset(&ct, 0, sizeof ct);
+            ct.aln_first = aln_total; ct.n_aln = (uint32_t)T.acc.size(); ct.T = T.T;
+            aln_total += ct.n_aln;
+            ct.seg_cap = (uint32_t)(T.T / std::max(1, (int)(o.min_size * 0.85)) + 2);
+            ct.seg_first = seg_total; seg_total += ct.seg_cap;
+            ct.out_cap = (uint32_t)(T.T * 2 + 1024);
+            ct.out_base = out_pool; out_pool += ct.out_cap;
+            ct.level_cap = (uint32_t)(T.T * 3 + 2048);
+            ctx->cc.n_accepted += T.acc.size();
+            dt_tpl[x] = order[x];
         }
-        ct.seg_cap = (uint32_t)(T.T / std::max(1, (int)(o.min_size * 0.85)) + 2);
-        ct.seg_first = seg_total; seg_total += ct.seg_cap;
-        ct.out_cap = (uint32_t)(T.T * 2 + 1024);
-        ct.out_base = out_pool; out_pool += ct.out_cap;
-        ct.link_cap = (uint32_t)std::min<uint64_t>(cols + 32, 0xfffffff0ull);      // links <= columns
-        ct.level_cap = (uint32_t)(T.T * 3 + 2048);
-        ctx->cc.n_accepted += T.acc.size();
-        dt.push_back(ct); dt_tpl.push_back(t);
+        alns.resize(aln_total);
+        auto fill = [&](size_t x0, size_t x1) {             // the alignment descriptions, in parallel over templates
+            for (size_t x = x0; x < x1; ++x) {
+                const size_t t = order[x];
+                const Tpl& T = tpls[t];
+                const ExtGroup& G = groups[group_of[t - c0]];
+                CnsAln* dst = alns.data() + dt[x].aln_first;
+                uint64_t cols = 0;
+                for (const Accepted& a : T.acc) {
+                    const Can& c = cans[T.first + (size_t)a.can];
+                    const nb_alignment& r = G.res[(size_t)c.res];
+                    CnsAln ca;
+                    ca.ops = G.res_ops[(size_t)c.res]; ca.qseq_off = reads->h_off[c.qid];
+                    ca.aln_size = r.aln_size; ca.toff = r.toff; ca.tend = r.tend; ca.qstart = r.qoff;
+                    ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight;
+                    *dst++ = ca;
+                    cols += (uint64_t)r.aln_size;
+                }
+                dt[x].link_cap = (uint32_t)std::min<uint64_t>(cols + 32, 0xfffffff0ull);      // links <= columns
+            }
+        };
+        const size_t per = (order.size() + nthreads - 1) / nthreads;
+        std::vector<std::thread> th;
+        for (unsigned w = 1; w < nthreads && per; ++w) {
+            const size_t x0 = w * per, x1 = std::min(order.size(), x0 + per);
+            if (x0 >= x1) break;
+            th.emplace_back(fill, x0, x1);
+        }
+        if (per) fill(0, std::min(order.size(), per));
+        for (auto& x : th) x.join();
     }
     for (auto& ct : dt) {
         ct.pos_base = pos_total; pos_total += (uint64_t)ct.T + 2;
@@ -534,6 +556,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         P.pac = reads->d_pac; P.tpl = d_tpl; P.aln = d_aln; P.n_tpl = (uint32_t)dt.size();
         P.min_cov = o.min_cov; P.min_size = o.min_size; P.lanes = kLanes < 1 ? 1 : (kLanes > 32 ? 32 : kLanes);
         P.walk_lanes = kWalkLanes < 1 ? 1 : (kWalkLanes > 32 ? 32 : kWalkLanes);
+        P.flush_slow = getenv("NB_CNS_FLUSH_SLOW") ? atoi(getenv("NB_CNS_FLUSH_SLOW")) : 0;
         const size_t smem = sizeof(CnsWarpShared) * CNS_WARPS;
         if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_cns_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         t_prep += ht.lap();
@@ -746,39 +769,62 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     std::vector<Fill> fills;
     if (n_in == 0) return NB_OK;
 
-    // ---- load order + normalisation (consensus_one_partition.c:10-95)
-    std::vector<nb_packed_candidate> pc(cans_in, cans_in + n_in);
-    for (auto& p : pc) {
+    // ---- load order + normalisation (consensus_one_partition.c:10-95): records grouped by template, input order
+    //      kept inside a group (a stable counting sort on the template id)
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads == 0) nthreads = 4;
+    if (nthreads > 64) nthreads = 64;
+    std::vector<uint32_t> grp_start(reads->nseq + 1, 0);
+    for (uint64_t i = 0; i < n_in; ++i) {
+        const nb_packed_candidate& p = cans_in[i];
         if (p.item[1] >= reads->nseq || p.item[4] >= reads->nseq) return nb_fail(ctx, NB_EINVAL, "candidate read id out of range");
+        ++grp_start[p.item[1] + 1];
     }
-    std::stable_sort(pc.begin(), pc.end(), [](const nb_packed_candidate& a, const nb_packed_candidate& b) { return a.item[1] < b.item[1]; });
+    for (uint64_t i = 0; i < reads->nseq; ++i) grp_start[i + 1] += grp_start[i];
+    std::vector<nb_packed_candidate> pc(n_in);
+    {
+        std::vector<uint32_t> cur(grp_start.begin(), grp_start.end() - 1);
+        for (uint64_t i = 0; i < n_in; ++i) pc[cur[cans_in[i].item[1]]++] = cans_in[i];
+    }
     const int min_id = (int)pc.front().item[1], max_id = (int)pc.back().item[1];
-    for (auto& p : pc) {                                            // normalise_pcan_sdir, gapped_candidate.c:72-93
-        const uint32_t w = p.item[0];
-        if (!(w >> 31)) continue;
-        uint32_t r = w & ((1u << 29) - 1);
-        if (!((w >> 30) & 1)) r |= 1u << 30;
-        if (!(w & (1u << 29))) r |= 1u << 29;
-        p.item[0] = r;
-        const uint32_t qs = reads->h_len[p.item[4]], ss = reads->h_len[p.item[1]];
-        const uint32_t qb = qs - p.item[6], qe = qs - p.item[5];
-        p.item[5] = qb; p.item[6] = qe;
-        const uint32_t sb = ss - p.item[3], se = ss - p.item[2];
-        p.item[2] = sb; p.item[3] = se;
-    }
     std::vector<uint8_t> corrected(reads->nseq, 0);
 
-    // ---- templates
+    // ---- templates: at least -x records (consensus_one_read.c:218), this shard's share; their candidates sorted and
+    //      cut to MAX_EXAMINED_CAN, in parallel over templates
     std::vector<Tpl> tpls;
     std::vector<Can> cans;
     {
-        size_t i = 0;
-        std::vector<nb_packed_candidate> one;
-        while (i < pc.size()) {
-            size_t j = i + 1;
-            while (j < pc.size() && pc[j].item[1] == pc[i].item[1]) ++j;
-            if ((size_t)o.min_cov <= j - i && (int)(pc[i].item[1] % (uint32_t)shard_count) == shard_index) {   // consensus_one_read.c:218
-                one.assign(pc.begin() + i, pc.begin() + j);
+        size_t ncan = 0;
+        for (uint64_t id = 0; id < reads->nseq; ++id) {
+            const size_t cnt = grp_start[id + 1] - grp_start[id];
+            if (cnt == 0 || (size_t)o.min_cov > cnt || (int)(id % (uint64_t)shard_count) != shard_index) continue;
+            Tpl t;
+            t.tid = (int)id; t.T = (int)reads->h_len[id];
+            t.first = ncan; t.n = cnt > 300 ? 300 : cnt;               // MAX_EXAMINED_CAN
+            t.stage = 0; t.next = 0; t.win_to = 0; t.win_i = 0; t.in_window = false; t.cutoff = 0; t.num_can = 0; t.num_ovlps = 0;
+            t.n_below = 0;
+            ncan += t.n;
+            tpls.push_back(std::move(t));
+        }
+        cans.resize(ncan);
+        auto build = [&](size_t t0, size_t t1) {
+            std::vector<nb_packed_candidate> one;
+            for (size_t x = t0; x < t1; ++x) {
+                const Tpl& t = tpls[x];
+                one.assign(pc.begin() + grp_start[(size_t)t.tid], pc.begin() + grp_start[(size_t)t.tid + 1]);
+                for (auto& p : one) {                                   // normalise_pcan_sdir, gapped_candidate.c:72-93
+                    const uint32_t w = p.item[0];
+                    if (!(w >> 31)) continue;
+                    uint32_t r = w & ((1u << 29) - 1);
+                    if (!((w >> 30) & 1)) r |= 1u << 30;
+                    if (!(w & (1u << 29))) r |= 1u << 29;
+                    p.item[0] = r;
+                    const uint32_t qs = reads->h_len[p.item[4]], ss = reads->h_len[p.item[1]];
+                    const uint32_t qb = qs - p.item[6], qe = qs - p.item[5];
+                    p.item[5] = qb; p.item[6] = qe;
+                    const uint32_t sb = ss - p.item[3], se = ss - p.item[2];
+                    p.item[2] = sb; p.item[3] = se;
+                }
                 std::sort(one.begin(), one.end(), [](const nb_packed_candidate& a, const nb_packed_candidate& b) {
                     // PackedGappedCandidate_CnsScoreGT, gapped_candidate.c:96-126
                     const int as = (int)(a.item[0] & ((1u << 29) - 1)), bs = (int)(b.item[0] & ((1u << 29) - 1));
@@ -789,12 +835,8 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
                     if (a.item[5] != b.item[5]) return (int)a.item[5] < (int)b.item[5];
                     return (int)a.item[2] < (int)b.item[2];
                 });
-                if (one.size() > 300) one.resize(300);              // MAX_EXAMINED_CAN
-                Tpl t;
-                t.tid = (int)pc[i].item[1]; t.T = (int)reads->h_len[t.tid];
-                t.first = cans.size(); t.n = one.size();
-                t.stage = 0; t.next = 0; t.win_to = 0; t.win_i = 0; t.in_window = false; t.cutoff = 0; t.num_can = 0; t.num_ovlps = 0;
-                for (const auto& p : one) {
+                for (size_t k = 0; k < t.n; ++k) {
+                    const nb_packed_candidate& p = one[k];
                     Can c;
                     const uint32_t w = p.item[0];
                     c.qid = (int)p.item[4]; c.qdir = (int)((w >> 30) & 1); c.score = (int)(w & ((1u << 29) - 1));
@@ -803,12 +845,19 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
                     else                { c.qoff = (int)p.item[6]; c.soff = (int)p.item[3]; }
                     c.qsize = (int)reads->h_len[c.qid];
                     c.res = -1;
-                    cans.push_back(c);
+                    cans[t.first + k] = c;
                 }
-                tpls.push_back(std::move(t));
             }
-            i = j;
+        };
+        const size_t per = (tpls.size() + nthreads - 1) / nthreads;
+        std::vector<std::thread> th;
+        for (unsigned w = 1; w < nthreads && per; ++w) {
+            const size_t t0 = w * per, t1 = std::min(tpls.size(), t0 + per);
+            if (t0 >= t1) break;
+            th.emplace_back(build, t0, t1);
         }
+        if (per) build(0, std::min(tpls.size(), per));
+        for (auto& x : th) x.join();
     }
     ctx->cc.n_templates = tpls.size();
     t_setup += ht.lap();
@@ -817,9 +866,6 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     //      worker owns a stream, events, a pinned staging buffer and walk-back scratch, so the host phases of one
     //      chunk (replay of the accept/skip logic, request gathering, record planning and filling) overlap the
     //      kernels of the others.  Chunks also bound the device memory of a 100 000-template partition.
-    unsigned nthreads = std::thread::hardware_concurrency();
-    if (nthreads == 0) nthreads = 4;
-    if (nthreads > 64) nthreads = 64;
     const char* env_chunks = getenv("NB_CNS_CHUNKS");
     const char* env_pipes = getenv("NB_CNS_PIPES");
     size_t n_chunks = env_chunks ? (size_t)atoi(env_chunks) : 1;
@@ -931,7 +977,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     if (trace) {
         ChunkTimes s;
         for (const ChunkTimes& c : chunk_tm) { s.replay += c.replay; s.gather += c.gather; s.ext += c.ext; s.prep += c.prep; s.kern += c.kern; s.rec += c.rec; s.wait += c.wait; s.ext_wall += c.ext_wall; s.init += c.init; }
-        fprintf(stderr, "[nb_consensus_job] %zu chunks on %d workers; wall ms: setup %.1f chunks %.1f tail %.1f | summed over chunks: replay %.1f gather %.1f "
+        fprintf(stderr, "[nb_consensus_job] %zu chunks on %d workers; wall ms: setup %.1f chunks %.1f tail %.1f | summed over chunks: init %.1f replay %.1f gather %.1f "
                         "gpu-wait %.1f ext(call) %.1f [extension phase wall %.1f] cns_prep %.1f cns(call) %.1f records %.1f | gpu ms: extend %.1f consensus %.1f\n",
                 n_chunks, n_workers, t_setup, t_chunks, t_tail, s.init, s.replay, s.gather, s.wait, s.ext, s.ext_wall, s.prep, s.kern, s.rec, ext_ms, cns_ms);
     }

@@ -32,6 +32,7 @@
 #define CNS_WARPS 4
 #define CNS_POOL 768            // links per tile (shared-memory pool; ~115 used on average)
 #define CNS_NOPRED 0xffffffffu
+#define CNS_FLUSH_REGS 8        // links of one position sorted in registers at the flush (more: the list-walking flush)
 
 struct CnsAln {                 // one accepted alignment, in acceptance order
     const uint8_t* ops;
@@ -100,11 +101,12 @@ struct CnsParams {
     int                min_cov, min_size;
     int                lanes;           // k_cns_dp: templates per warp (the other lanes idle)
     int                walk_lanes;      // k_cns_walk: likewise
+    int                flush_slow;      // k_cns_links: 1 = always take the list-walking flush (tests)
     uint32_t*          error_flag;      // 1 = level capacity, 2 = link pool / link capacity, 4 = output capacity
     unsigned long long* counters;       // [0] levels, [1] columns (tags), [2] links
 };
 
-struct CnsWarpShared {
+struct __align__(16) CnsWarpShared {
     // links of the current tile: per-position singly linked lists
     uint32_t e_key[CNS_POOL];
     double   e_w[CNS_POOL];
@@ -132,6 +134,7 @@ k_cns_links(CnsParams P)
     const uint32_t lt_mask = (1u << lane) - 1, le_mask = lt_mask | (1u << lane);
     CnsWarpShared& S = reinterpret_cast<CnsWarpShared*>(cns_smem)[wid];
     CnsCursor* CU = P.cursor + ((size_t)blockIdx.x * CNS_WARPS + wid) * CNS_MAX_ALN;
+    const bool kFlushSlow = P.flush_slow != 0;
     unsigned long long n_cols_total = 0, n_links_total = 0;
 
     for (;;) {
@@ -213,6 +216,19 @@ k_cns_links(CnsParams P)
         __syncwarp();
 
         // ---- 3. tile sweep: links of 32 positions at a time, alignments in acceptance order
+        uint32_t r_x = 0, r_qp = 0, r_ln = 0xffff, r_ql = 0;       // lane a < 32: cursor and description of alignment a
+        int r_lp = 0, r_n = 0, r_toff = 0, r_tend = 0;
+        const uint8_t* r_ops = NULL;
+        uint64_t r_qso = 0;
+        double r_w = 0.0;
+        bool r_valid = false;
+        if (lane < A) {
+            const CnsAln al = AL[lane];
+            r_ops = al.ops; r_n = al.aln_size; r_toff = al.toff; r_tend = al.tend; r_qso = al.qseq_off;
+            r_ql = (uint32_t)al.qlen | ((uint32_t)al.qdir << 31); r_w = al.weight;
+            r_valid = CU[lane].valid != 0;
+            r_qp = (uint32_t)al.qstart; r_lp = al.toff - 1;
+        }
         uint32_t ebase = 0;                     // links written so far
         uint32_t prev_start = 0, prev_cnt = 0;  // links of the last position of the previous tile
         for (int t0 = 0; t0 < T && !fail; t0 += 32) {
@@ -222,22 +238,18 @@ k_cns_links(CnsParams P)
             if (lane == 0) S.pool_used = 0;
             S.head[lane] = 0xffffu;
             __syncwarp();
-            for (int a = 0; a < A; ++a) {
-                if (AL[a].toff >= t1 || AL[a].tend <= t0) continue;
-                const CnsCursor cu = CU[a];
-                if (!cu.valid) continue;
-                const uint8_t* ops = AL[a].ops;
-                const int n = AL[a].aln_size;
-                const uint64_t qso = AL[a].qseq_off;
-                const int qlen = AL[a].qlen, qdir = AL[a].qdir;
-                const double w = AL[a].weight;
-                uint32_t x = cu.x, qp = cu.qpos;
-                int last_pos = cu.last_pos;
-                uint32_t last_node = cu.last_node;
-                while (x < (uint32_t)n) {
+            // Columns [x, ..) of one alignment that fall on this tile: derive (position, delta, base, predecessor) of
+            // each column with ballots, add the alignment's weight to the matching link.  cur0 / cur1 are the op bytes
+            // of columns x + lane and x + 32 + lane when `pre` says they were fetched ahead of time.
+            auto sweep = [&](const uint8_t* __restrict__ ops, const int n, const uint64_t qso, const int qlen, const int qdir, const double w,
+                             uint32_t& x, uint32_t& qp, int& last_pos, uint32_t& last_node, const bool pre, const int cur0, const int cur1) {
+                for (int it = 0; x < (uint32_t)n; ++it) {
                     const uint32_t c = x + lane;
                     const bool ok = c < (uint32_t)n;
-                    const int op = ok ? ops[c] : OP_TONLY;
+                    int op;
+                    if (pre && it == 0) op = cur0;
+                    else if (pre && it == 1) op = cur1;
+                    else op = ok ? ops[c] : OP_TONLY;
                     const uint32_t tmask = __ballot_sync(0xffffffffu, ok && op != OP_QONLY);
                     const uint32_t qmask = __ballot_sync(0xffffffffu, ok && op != OP_TONLY);
                     const uint32_t vmask = __ballot_sync(0xffffffffu, ok);
@@ -286,14 +298,67 @@ k_cns_links(CnsParams P)
                     __syncwarp();
                     if (n_take < 32) break;
                 }
+            };
+            // the first 32 alignments: cursor and description live in the registers of lane a; the op bytes of the next
+            // alignment are fetched while the current one is processed
+            {
+                uint32_t amask = __ballot_sync(0xffffffffu, r_valid && r_toff < t1 && r_tend > t0);
+                int a = amask ? __ffs(amask) - 1 : -1;
+                int pre0 = OP_TONLY, pre1 = OP_TONLY;
+                auto fetch = [&](int an) {
+                    const uint32_t fx = __shfl_sync(0xffffffffu, r_x, an);
+                    const uint32_t fn = (uint32_t)__shfl_sync(0xffffffffu, r_n, an);
+                    const uint8_t* fo = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, (unsigned long long)r_ops, an));
+                    const uint32_t c = fx + lane;
+                    pre0 = c < fn ? fo[c] : OP_TONLY;
+                    pre1 = c + 32 < fn ? fo[c + 32] : OP_TONLY;
+                };
+                if (a >= 0) fetch(a);
+                while (a >= 0) {
+                    amask &= amask - 1;
+                    const int nxt = amask ? __ffs(amask) - 1 : -1;
+                    uint32_t x = __shfl_sync(0xffffffffu, r_x, a), qp = __shfl_sync(0xffffffffu, r_qp, a);
+                    int last_pos = __shfl_sync(0xffffffffu, r_lp, a);
+                    uint32_t last_node = __shfl_sync(0xffffffffu, r_ln, a);
+                    const uint8_t* ops = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, (unsigned long long)r_ops, a));
+                    const int n = __shfl_sync(0xffffffffu, r_n, a);
+                    const uint64_t qso = __shfl_sync(0xffffffffu, (unsigned long long)r_qso, a);
+                    const uint32_t ql = __shfl_sync(0xffffffffu, r_ql, a);
+                    const double w = __shfl_sync(0xffffffffu, r_w, a);
+                    const int cur0 = pre0, cur1 = pre1;
+                    if (nxt >= 0) fetch(nxt);
+                    sweep(ops, n, qso, (int)(ql & 0x7fffffffu), (int)(ql >> 31), w, x, qp, last_pos, last_node, true, cur0, cur1);
+                    if (lane == a) { r_x = x; r_qp = qp; r_lp = last_pos; r_ln = last_node; }
+                    a = nxt;
+                }
+            }
+            // alignments beyond the 32nd: cursor in HBM / L1
+            for (int a = 32; a < A; ++a) {
+                if (AL[a].toff >= t1 || AL[a].tend <= t0) continue;
+                const CnsCursor cu = CU[a];
+                if (!cu.valid) continue;
+                uint32_t x = cu.x, qp = cu.qpos;
+                int last_pos = cu.last_pos;
+                uint32_t last_node = cu.last_node;
+                sweep(AL[a].ops, AL[a].aln_size, AL[a].qseq_off, AL[a].qlen, AL[a].qdir, AL[a].weight, x, qp, last_pos, last_node, false, 0, 0);
                 if (lane == 0) { CnsCursor c; c.x = x; c.qpos = qp; c.last_pos = last_pos; c.last_node = (uint16_t)last_node; c.valid = 1; c.pad_ = 0; CU[a] = c; }
                 __syncwarp();
             }
             if (S.pool_used > CNS_POOL) { fail |= 2; break; }
             // ---- flush: lane = position; its links go to HBM in key order, with the index of the
             //      predecessor node's first link resolved here so that k_cns_dp needs no search
+            // one walk over my position's list: up to CNS_FLUSH_REGS links go to registers as key << 16 | pool slot
+            unsigned long long kv[CNS_FLUSH_REGS];
             int cnt = 0;
-            for (int e = (int)S.head[lane]; e != 0xffff; e = S.e_next[e]) ++cnt;
+            int e_walk = (int)S.head[lane];
+#pragma unroll
+            for (int j = 0; j < CNS_FLUSH_REGS; ++j) {
+                kv[j] = ~0ull;
+                if (e_walk != 0xffff) { kv[j] = ((unsigned long long)S.e_key[e_walk] << 16) | (unsigned)e_walk; e_walk = S.e_next[e_walk]; ++cnt; }
+            }
+            const bool crowded = e_walk != 0xffff;                  // more links than registers: the slow flush below
+            for (; e_walk != 0xffff; e_walk = S.e_next[e_walk]) ++cnt;
+            const bool any_crowded = __any_sync(0xffffffffu, crowded) || kFlushSlow;
             int off = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, off, d); if (lane >= d) off += o; }
@@ -306,6 +371,71 @@ k_cns_links(CnsParams P)
             uint32_t pv_start = __shfl_up_sync(0xffffffffu, my_start, 1);
             if (lane == 0) pv_start = prev_start;
             const bool pv_in_run = (tile_flag & 1) && !(tile_flag & 2);            // the previous position belongs to the same run
+            if (!any_crowded) {
+                // ---- fast flush: sort the registers (keys of a position are distinct), publish the node ids of the
+                //      sorted links so that the next lane can locate its predecessors, resolve, write
+#define CNS_CSWAP(a, b) { const unsigned long long lo_ = kv[a] < kv[b] ? kv[a] : kv[b], hi_ = kv[a] < kv[b] ? kv[b] : kv[a]; kv[a] = lo_; kv[b] = hi_; }
+                CNS_CSWAP(0, 1) CNS_CSWAP(2, 3) CNS_CSWAP(4, 5) CNS_CSWAP(6, 7)
+                CNS_CSWAP(0, 2) CNS_CSWAP(1, 3) CNS_CSWAP(4, 6) CNS_CSWAP(5, 7)
+                CNS_CSWAP(1, 2) CNS_CSWAP(5, 6)
+                CNS_CSWAP(0, 4) CNS_CSWAP(1, 5) CNS_CSWAP(2, 6) CNS_CSWAP(3, 7)
+                CNS_CSWAP(2, 4) CNS_CSWAP(3, 5)
+                CNS_CSWAP(1, 2) CNS_CSWAP(3, 4) CNS_CSWAP(5, 6)
+#undef CNS_CSWAP
+                uint32_t nid[CNS_FLUSH_REGS];                       // delta << 4 | base of each sorted link; 0xfff = none
+#pragma unroll
+                for (int j = 0; j < CNS_FLUSH_REGS; ++j) nid[j] = (uint32_t)(kv[j] >> 36) & 0xfffu;
+                // (the 512 bytes reuse the list pointers: every lane has its whole list in registers by now)
+                uint4* sorted_nid = reinterpret_cast<uint4*>(S.e_next);
+                __syncwarp();
+                {
+                    uint4 pk;
+                    pk.x = nid[0] | (nid[1] << 16); pk.y = nid[2] | (nid[3] << 16); pk.z = nid[4] | (nid[5] << 16); pk.w = nid[6] | (nid[7] << 16);
+                    sorted_nid[lane] = pk;
+                }
+                __syncwarp();
+                uint32_t pn[CNS_FLUSH_REGS];                        // the previous position's sorted node ids
+                {
+                    const uint4 pk = sorted_nid[lane > 0 ? lane - 1 : 0];
+                    pn[0] = pk.x & 0xffff; pn[1] = pk.x >> 16; pn[2] = pk.y & 0xffff; pn[3] = pk.y >> 16;
+                    pn[4] = pk.z & 0xffff; pn[5] = pk.z >> 16; pn[6] = pk.w & 0xffff; pn[7] = pk.w >> 16;
+                }
+#pragma unroll
+                for (int i = 0; i < CNS_FLUSH_REGS; ++i) {
+                    if (i < cnt) {
+                        const uint32_t bk = (uint32_t)(kv[i] >> 16);
+                        const int be = (int)(kv[i] & 0xffff);
+                        const uint32_t rank = bk & 0xffff, pb = (bk >> 16) & 7, d = bk >> 24;
+                        uint32_t pred = CNS_NOPRED;
+                        if (rank != 0) {
+                            if (d > 0) {
+                                // node (d - 1, pb) of this position: its first link = number of links of this position below it
+                                const uint32_t want = ((d - 1) << 4) | pb;
+                                uint32_t less = 0;
+#pragma unroll
+                                for (int j = 0; j < CNS_FLUSH_REGS; ++j) less += nid[j] < want;
+                                pred = my_start + less;
+                            } else if (pv_in_run) {
+                                const uint32_t want = (((rank - 1 - cns_char_rank(pb)) / 5u) << 4) | pb;
+                                uint32_t less = 0;
+                                if (lane > 0) {
+#pragma unroll
+                                    for (int j = 0; j < CNS_FLUSH_REGS; ++j) less += pn[j] < want;
+                                } else {
+                                    for (uint32_t q = 0; q < prev_cnt; ++q) less += ((link[prev_start + q].key >> 20) & 0xff7u) < want;
+                                }
+                                pred = pv_start + less;
+                            }
+                        }
+                        // bit 23: first link of its node, bit 19: first link of its delta level (spares k_cns_dp the key compares)
+                        const uint32_t lastnid = i > 0 ? nid[i > 0 ? i - 1 : 0] : 0xffffu;
+                        const uint32_t fl_node = (i == 0 || nid[i] != lastnid) ? (1u << 23) : 0u;
+                        const uint32_t fl_level = (i == 0 || (nid[i] >> 4) != (lastnid >> 4)) ? (1u << 19) : 0u;
+                        CnsLink L; L.key = bk | fl_node | fl_level; L.pred = pred; L.w = S.e_w[be];
+                        link[my_start + i] = L;
+                    }
+                }
+            } else {
             uint32_t lastkey = 0;
             for (int i = 0; i < cnt; ++i) {        // selection by increasing key (keys of a position are distinct)
                 uint32_t bk = 0xffffffffu; int be = 0xffff;
@@ -339,6 +469,7 @@ k_cns_links(CnsParams P)
                 CnsLink L; L.key = bk | fl_node | fl_level; L.pred = pred; L.w = S.e_w[be];
                 link[my_start + i] = L;
                 lastkey = bk;
+            }
             }
             prev_start = __shfl_sync(0xffffffffu, my_start, 31);
             prev_cnt = (uint32_t)__shfl_sync(0xffffffffu, cnt, 31);

@@ -28,6 +28,8 @@ struct nb_ctx {
     void*        ext_mat;        // walk-back scratch of the extension kernel (kept across calls)
     size_t       ext_mat_slots;
     void*        dev_cache;      // NbDevCache*: device blocks kept for reuse (cudaMalloc/cudaFree are slow and synchronising)
+    void*        pin_cache[4];   // pinned host blocks of freed volumes, reused by the next upload (pinning 50 MB costs ~10 ms)
+    size_t       pin_cache_bytes[4];
     nb_ctx*      workers[NB_MAX_WORKERS];   // [1..]: shadow contexts of the pipeline workers (own stream, events, staging,
                                             // scratch; they share dev_cache with their parent), created on first use
     int          is_worker;
@@ -42,7 +44,10 @@ struct nb_volume {
     uint64_t* h_off;        // host copies (the sequential host logic needs them)
     uint32_t* h_len;
     uint32_t  max_len;
-    uint8_t*  h_pac;        // host copy of the packed bases (raw leftovers are cut on the host)
+    uint8_t*  h_pac;        // host copy of the packed bases (raw leftovers are cut on the host); pinned: it is also the
+                            // staging buffer of the upload
+    size_t    h_pac_bytes;
+    nb_ctx*   owner;        // device blocks and the pinned copy go back to this context's caches
 };
 
 struct nb_index {

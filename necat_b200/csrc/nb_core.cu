@@ -168,6 +168,7 @@ extern "C" void nb_ctx_destroy(nb_ctx* c)
     if (c->ext_mat) cudaFree(c->ext_mat);
     nb_dev_cache_destroy(c);
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (int k = 0; k < 4; ++k) if (c->pin_cache[k]) cudaFreeHost(c->pin_cache[k]);
     free(c);
 }
 
@@ -188,12 +189,14 @@ extern "C" int nb_volume_upload(nb_ctx* ctx, const uint8_t* pac, uint64_t db_siz
     if (!v) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
     v->db_size = db_size;
     v->nseq = nseq;
-    uint64_t nb = (db_size + 3) >> 2;
-    uint64_t padded = ((nb + 15) & ~15ull) + 256;
-    NB_CUDA(ctx, cudaMalloc(&v->d_pac, padded));
-    NB_CUDA(ctx, cudaMemsetAsync(v->d_pac, 0, padded, ctx->stream));
-    NB_CUDA(ctx, cudaMalloc(&v->d_off, sizeof(uint64_t) * (nseq + 1)));
-    NB_CUDA(ctx, cudaMalloc(&v->d_len, sizeof(uint32_t) * (nseq + 1)));
+    v->owner = ctx;
+    cudaStream_t st = ctx->stream;
+    const uint64_t nb = (db_size + 3) >> 2;
+    const uint64_t padded = ((nb + 15) & ~15ull) + 256;
+    int rc;
+    if ((rc = nb_dev_alloc(ctx, (void**)&v->d_pac, padded))) return rc;
+    if ((rc = nb_dev_alloc(ctx, (void**)&v->d_off, sizeof(uint64_t) * (nseq + 1)))) return rc;
+    if ((rc = nb_dev_alloc(ctx, (void**)&v->d_len, sizeof(uint32_t) * (nseq + 1)))) return rc;
     v->h_off = (uint64_t*)malloc(sizeof(uint64_t) * (nseq + 1));
     v->h_len = (uint32_t*)malloc(sizeof(uint32_t) * (nseq + 1));
     if (!v->h_off || !v->h_len) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
@@ -206,17 +209,27 @@ extern "C" int nb_volume_upload(nb_ctx* ctx, const uint8_t* pac, uint64_t db_siz
         v->h_len[i] = (uint32_t)seq_size[i];
         if (v->h_len[i] > v->max_len) v->max_len = v->h_len[i];
     }
-    v->h_pac = (uint8_t*)malloc(nb + 16);
-    if (!v->h_pac) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    // the library's host copy of the packed bases is pinned: one memcpy from the caller's buffer, then the upload
+    // runs from it at full link speed
+    for (int k = 0; k < 4 && !v->h_pac; ++k)
+        if (ctx->pin_cache[k] && ctx->pin_cache_bytes[k] >= padded && ctx->pin_cache_bytes[k] <= padded * 2 + (1u << 20)) {
+            v->h_pac = (uint8_t*)ctx->pin_cache[k]; v->h_pac_bytes = ctx->pin_cache_bytes[k];
+            ctx->pin_cache[k] = NULL; ctx->pin_cache_bytes[k] = 0;
+        }
+    if (!v->h_pac) {
+        NB_CUDA(ctx, cudaHostAlloc((void**)&v->h_pac, padded, cudaHostAllocDefault));
+        v->h_pac_bytes = padded;
+    }
     memcpy(v->h_pac, pac, nb);
+    memset(v->h_pac + nb, 0, padded - nb);
     v->h_off[nseq] = db_size;
     v->h_len[nseq] = 0;
-    cudaEventRecord(ctx->ev0, ctx->stream);
-    NB_CUDA(ctx, cudaMemcpyAsync(v->d_pac, pac, nb, cudaMemcpyHostToDevice, ctx->stream));
-    NB_CUDA(ctx, cudaMemcpyAsync(v->d_off, v->h_off, sizeof(uint64_t) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream));
-    NB_CUDA(ctx, cudaMemcpyAsync(v->d_len, v->h_len, sizeof(uint32_t) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream));
-    cudaEventRecord(ctx->ev1, ctx->stream);
-    NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventRecord(ctx->ev0, st);
+    NB_CUDA(ctx, cudaMemcpyAsync(v->d_pac, v->h_pac, padded, cudaMemcpyHostToDevice, st));
+    NB_CUDA(ctx, cudaMemcpyAsync(v->d_off, v->h_off, sizeof(uint64_t) * (nseq + 1), cudaMemcpyHostToDevice, st));
+    NB_CUDA(ctx, cudaMemcpyAsync(v->d_len, v->h_len, sizeof(uint32_t) * (nseq + 1), cudaMemcpyHostToDevice, st));
+    cudaEventRecord(ctx->ev1, st);
+    NB_CUDA(ctx, cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->tm.h2d_ms += ms;
@@ -228,13 +241,20 @@ extern "C" int nb_volume_upload(nb_ctx* ctx, const uint8_t* pac, uint64_t db_siz
 extern "C" void nb_volume_free(nb_ctx* ctx, nb_volume* v)
 {
     if (!v) return;
-    if (ctx) cudaSetDevice(ctx->device);
-    cudaFree(v->d_pac);
-    cudaFree(v->d_off);
-    cudaFree(v->d_len);
+    nb_ctx* c = v->owner ? v->owner : ctx;
+    if (c) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        nb_dev_release(c, v->d_pac);
+        nb_dev_release(c, v->d_off);
+        nb_dev_release(c, v->d_len);
+        int slot = -1;
+        for (int k = 0; k < 4; ++k) if (!c->pin_cache[k]) { slot = k; break; }
+        if (slot >= 0) { c->pin_cache[slot] = v->h_pac; c->pin_cache_bytes[slot] = v->h_pac_bytes; }
+        else cudaFreeHost(v->h_pac);
+    }
     free(v->h_off);
     free(v->h_len);
-    free(v->h_pac);
     free(v);
 }
 

@@ -828,11 +828,20 @@ extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* 
 
     // ---- host: per-read grouping (FWD before REV, emission order), -n truncation, global ids
     std::vector<uint64_t> order(C);
-    for (uint64_t i = 0; i < C; ++i) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
-        if (cu[a] != cu[b]) return cu[a] < cu[b];
-        return cseq[a] < cseq[b];
-    });
+    {
+        // counting sort on the unit, then the few records of a unit by their emission number
+        std::vector<uint32_t> first(U + 1, 0);
+        for (uint64_t i = 0; i < C; ++i) {
+            if (cu[i] >= U) return nb_fail(ctx, NB_ECUDA, "candidate kernel returned unit %u of %u", cu[i], U);
+            ++first[cu[i] + 1];
+        }
+        for (uint32_t u = 0; u < U; ++u) first[u + 1] += first[u];
+        std::vector<uint32_t> cur(first.begin(), first.end() - 1);
+        for (uint64_t i = 0; i < C; ++i) order[cur[cu[i]]++] = i;
+        for (uint32_t u = 0; u < U; ++u)
+            if (first[u + 1] - first[u] > 1)
+                std::sort(order.begin() + first[u], order.begin() + first[u + 1], [&](uint64_t a, uint64_t b) { return cseq[a] < cseq[b]; });
+    }
     nb_candidate* res = (nb_candidate*)malloc(sizeof(nb_candidate) * (C ? C : 1));
     if (!res) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
     uint64_t nres = 0;
