@@ -166,6 +166,8 @@ typedef struct {
     int32_t qoff, qend, toff, tend;
     int32_t aln_size;           /* alignment columns */
     int32_t n_match;            /* identical columns: ident_perc = 100.0 * n_match / aln_size */
+    int32_t long_ins;           /* 1 = the alignment holds a run of >= 255 query-only columns: get_cns_tags drops it
+                                   whole (tasc/align_tags.c:40-44) */
     uint64_t ops_offset;        /* into the ops buffer returned alongside */
 } nb_alignment;
 

@@ -44,7 +44,7 @@ CANDIDATE = np.dtype([("qid", "<i4"), ("sid", "<i4"), ("qdir", "<i4"), ("sdir", 
                       ("pad", "<i4"), ("qbeg", "<i8"), ("qend", "<i8"), ("qsize", "<i8"), ("sbeg", "<i8"),
                       ("send", "<i8"), ("ssize", "<i8"), ("qoff", "<i8"), ("soff", "<i8")])
 ALIGNMENT = np.dtype([("ok", "<i4"), ("qoff", "<i4"), ("qend", "<i4"), ("toff", "<i4"), ("tend", "<i4"),
-                      ("aln_size", "<i4"), ("n_match", "<i4"), ("pad", "<i4"), ("ops_offset", "<u8")])
+                      ("aln_size", "<i4"), ("n_match", "<i4"), ("long_ins", "<i4"), ("ops_offset", "<u8")])
 CNS_RECORD = np.dtype([("id", "<i4"), ("left", "<i4"), ("right", "<i4"), ("org_size", "<i4"), ("num_can", "<i4"),
                        ("num_ovlps", "<i4"), ("ident_cutoff", "<f8"), ("seq_offset", "<u8"), ("seq_len", "<i4"),
                        ("is_raw", "<i4")])

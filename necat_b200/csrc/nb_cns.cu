@@ -497,7 +497,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                     CnsAln ca;
                     ca.ops = G.res_ops[(size_t)c.res]; ca.qseq_off = reads->h_off[c.qid];
                     ca.aln_size = r.aln_size; ca.toff = r.toff; ca.tend = r.tend; ca.qstart = r.qoff;
-                    ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight;
+                    ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight; ca.drop = r.long_ins; ca.pad_ = 0;
                     *dst++ = ca;
                     cols += (uint64_t)r.aln_size;
                 }

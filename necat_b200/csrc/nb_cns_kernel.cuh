@@ -41,6 +41,8 @@ struct CnsAln {                 // one accepted alignment, in acceptance order
     int32_t  qstart;            // first query base, in query-strand coordinates
     int32_t  qlen, qdir;
     double   weight;
+    int32_t  drop;              // 1 = a run of >= 255 insertions: the alignment produces no tags (align_tags.c:40-44; found by k_extend)
+    int32_t  pad_;
 };
 
 struct CnsTemplate {
@@ -67,6 +69,12 @@ struct __align__(16) CnsLink {  // one link = (node, predecessor node), sorted b
     uint32_t key;               // delta(8) << 24 | node-start << 23 | base(3) << 20 | level-start << 19 | pred base(3) << 16 | pred rank(16)
     uint32_t pred;              // index of the predecessor node's first link, CNS_NOPRED = no scored predecessor
     double   w;                 // summed weight; k_cns_dp overwrites the first link of a node with the node score
+};
+
+struct __align__(16) CnsLevel { // one (position, delta) level of the best-path recurrence, written by k_cns_dp for k_cns_walk
+    unsigned long long packed;  // 5 x 11-bit back pointers, one per base: predecessor delta << 3 | predecessor base, 7 = none
+    uint32_t prev_first_level;  // level index of (position - 1, delta 0): the walk needs no second load per step
+    uint32_t pad_;
 };
 
 struct CnsSegment {             // one consensus stretch of >= min_size bases
@@ -96,7 +104,7 @@ struct CnsParams {
     CnsPos*            pos;
     CnsLink*           link;
     CnsCursor*         cursor;          // k_cns_links: [resident warps][CNS_MAX_ALN]
-    unsigned long long* bp;             // per level: 5 x 11-bit back pointers
+    CnsLevel*          bp;              // per level: 5 x 11-bit back pointers + where the previous position's levels start
     uint8_t*           rev;
     int                min_cov, min_size;
     int                lanes;           // k_cns_dp: templates per warp (the other lanes idle)
@@ -149,25 +157,13 @@ k_cns_links(CnsParams P)
         CnsLink* link = P.link + TP.link_base;
         uint32_t fail = 0;
 
-        // ---- 0. an insertion run of >= 255 drops the whole alignment (align_tags.c:40-44); lane = column
-        for (int a = 0; a < A; ++a) {
-            const uint8_t* ops = AL[a].ops;
-            const int n = AL[a].aln_size;
-            int carry = 0, bad = 0;
-            for (int base = 0; base < n && !bad; base += 32) {
-                const int c = base + lane;
-                const uint32_t ins = __ballot_sync(0xffffffffu, c < n && ops[c] == OP_QONLY);
-                if (ins == 0xffffffffu) { carry += 32; if (carry >= 255) bad = 1; continue; }
-                const int lead = __ffs(~ins) - 1;                  // ones at the low end continue the carried run
-                if (carry + lead >= 255) bad = 1;
-                carry = __clz(~ins);                               // ones at the high end (inner runs are < 32)
-            }
-            if (lane == 0) {
-                CnsCursor c; c.x = 0; c.qpos = (uint32_t)AL[a].qstart; c.last_pos = AL[a].toff - 1; c.last_node = 0xffff;
-                c.valid = (uint8_t)!bad; c.pad_ = 0;
-                CU[a] = c;
-            }
+        // ---- 0. cursors; an insertion run of >= 255 drops the whole alignment (align_tags.c:40-44; flagged by k_extend)
+        for (int a = lane; a < A; a += 32) {
+            CnsCursor c; c.x = 0; c.qpos = (uint32_t)AL[a].qstart; c.last_pos = AL[a].toff - 1; c.last_node = 0xffff;
+            c.valid = (uint8_t)!AL[a].drop; c.pad_ = 0;
+            CU[a] = c;
         }
+        __syncwarp();
         // ---- 1. coverage
         for (int t = lane; t <= T; t += 32) { CnsPos z; z.start = 0; z.cov = 0; z.flags = 0; z.first_level = 0; pos[t] = z; }
         __syncwarp();
@@ -231,6 +227,10 @@ k_cns_links(CnsParams P)
         }
         uint32_t ebase = 0;                     // links written so far
         uint32_t prev_start = 0, prev_cnt = 0;  // links of the last position of the previous tile
+        uint32_t prev_nid[CNS_FLUSH_REGS];      // ... and their node ids in key order, when the fast flush left them (prev_fast)
+        bool prev_fast = false;
+#pragma unroll
+        for (int j = 0; j < CNS_FLUSH_REGS; ++j) prev_nid[j] = 0xfffu;
         for (int t0 = 0; t0 < T && !fail; t0 += 32) {
             const int t1 = (t0 + 32 < T) ? t0 + 32 : T;
             const uint32_t tile_flag = (t0 + lane < T) ? pos[t0 + lane].flags : 0;
@@ -242,7 +242,8 @@ k_cns_links(CnsParams P)
             // each column with ballots, add the alignment's weight to the matching link.  cur0 / cur1 are the op bytes
             // of columns x + lane and x + 32 + lane when `pre` says they were fetched ahead of time.
             auto sweep = [&](const uint8_t* __restrict__ ops, const int n, const uint64_t qso, const int qlen, const int qdir, const double w,
-                             uint32_t& x, uint32_t& qp, int& last_pos, uint32_t& last_node, const bool pre, const int cur0, const int cur1) {
+                             uint32_t& x, uint32_t& qp, int& last_pos, uint32_t& last_node, const bool pre, const int cur0, const int cur1,
+                             const uint32_t cur_pac, const long long pac_lo) {
                 for (int it = 0; x < (uint32_t)n; ++it) {
                     const uint32_t c = x + lane;
                     const bool ok = c < (uint32_t)n;
@@ -262,7 +263,14 @@ k_cns_links(CnsParams P)
                     if (n_take == 0) break;
                     const bool take = lane < n_take;
                     int b = 4;
-                    if (take && op != OP_TONLY) b = cns_qbase(P.pac, qso, qlen, qdir, qp + __popc(qmask & lt_mask));
+                    if (pre && it < 2) {
+                        // lanes 0..16 hold the 17 bytes of packed query bases around the cursor (fetched with the ops)
+                        const uint32_t q = qp + __popc(qmask & lt_mask);
+                        const long long p = qdir ? (long long)qso + (qlen - 1 - (int)q) : (long long)qso + q;
+                        const bool want = take && op != OP_TONLY;
+                        const uint32_t byte = __shfl_sync(0xffffffffu, cur_pac, want ? (int)((p >> 2) - pac_lo) : 0);
+                        if (want) { b = (byte >> (((~p) & 3) << 1)) & 3; if (qdir) b = 3 - b; }
+                    } else if (take && op != OP_TONLY) b = cns_qbase(P.pac, qso, qlen, qdir, qp + __popc(qmask & lt_mask));
                     const uint32_t node = ((uint32_t)delta << 3) | (uint32_t)b;
                     uint32_t pnode = __shfl_up_sync(0xffffffffu, node, 1);
                     if (lane == 0) pnode = last_node;
@@ -305,6 +313,8 @@ k_cns_links(CnsParams P)
                 uint32_t amask = __ballot_sync(0xffffffffu, r_valid && r_toff < t1 && r_tend > t0);
                 int a = amask ? __ffs(amask) - 1 : -1;
                 int pre0 = OP_TONLY, pre1 = OP_TONLY;
+                uint32_t pre_pac = 0;
+                long long pre_lo = 0;
                 auto fetch = [&](int an) {
                     const uint32_t fx = __shfl_sync(0xffffffffu, r_x, an);
                     const uint32_t fn = (uint32_t)__shfl_sync(0xffffffffu, r_n, an);
@@ -312,6 +322,13 @@ k_cns_links(CnsParams P)
                     const uint32_t c = fx + lane;
                     pre0 = c < fn ? fo[c] : OP_TONLY;
                     pre1 = c + 32 < fn ? fo[c + 32] : OP_TONLY;
+                    // packed query bases [qp, qp + 64) of that alignment: 17 bytes, one per lane
+                    const uint32_t fq = __shfl_sync(0xffffffffu, r_qp, an), fl = __shfl_sync(0xffffffffu, r_ql, an);
+                    const long long fso = (long long)__shfl_sync(0xffffffffu, (unsigned long long)r_qso, an);
+                    long long lo = (fl >> 31) ? fso + ((int)(fl & 0x7fffffffu) - 1 - (int)(fq + 63)) : fso + fq;
+                    if (lo < 0) lo = 0;
+                    pre_lo = lo >> 2;
+                    pre_pac = lane <= 16 ? __ldg(P.pac + pre_lo + lane) : 0u;
                 };
                 if (a >= 0) fetch(a);
                 while (a >= 0) {
@@ -326,8 +343,10 @@ k_cns_links(CnsParams P)
                     const uint32_t ql = __shfl_sync(0xffffffffu, r_ql, a);
                     const double w = __shfl_sync(0xffffffffu, r_w, a);
                     const int cur0 = pre0, cur1 = pre1;
+                    const uint32_t cur_pac = pre_pac;
+                    const long long cur_lo = pre_lo;
                     if (nxt >= 0) fetch(nxt);
-                    sweep(ops, n, qso, (int)(ql & 0x7fffffffu), (int)(ql >> 31), w, x, qp, last_pos, last_node, true, cur0, cur1);
+                    sweep(ops, n, qso, (int)(ql & 0x7fffffffu), (int)(ql >> 31), w, x, qp, last_pos, last_node, true, cur0, cur1, cur_pac, cur_lo);
                     if (lane == a) { r_x = x; r_qp = qp; r_lp = last_pos; r_ln = last_node; }
                     a = nxt;
                 }
@@ -340,7 +359,7 @@ k_cns_links(CnsParams P)
                 uint32_t x = cu.x, qp = cu.qpos;
                 int last_pos = cu.last_pos;
                 uint32_t last_node = cu.last_node;
-                sweep(AL[a].ops, AL[a].aln_size, AL[a].qseq_off, AL[a].qlen, AL[a].qdir, AL[a].weight, x, qp, last_pos, last_node, false, 0, 0);
+                sweep(AL[a].ops, AL[a].aln_size, AL[a].qseq_off, AL[a].qlen, AL[a].qdir, AL[a].weight, x, qp, last_pos, last_node, false, 0, 0, 0u, 0);
                 if (lane == 0) { CnsCursor c; c.x = x; c.qpos = qp; c.last_pos = last_pos; c.last_node = (uint16_t)last_node; c.valid = 1; c.pad_ = 0; CU[a] = c; }
                 __syncwarp();
             }
@@ -400,6 +419,11 @@ k_cns_links(CnsParams P)
                     pn[0] = pk.x & 0xffff; pn[1] = pk.x >> 16; pn[2] = pk.y & 0xffff; pn[3] = pk.y >> 16;
                     pn[4] = pk.z & 0xffff; pn[5] = pk.z >> 16; pn[6] = pk.w & 0xffff; pn[7] = pk.w >> 16;
                 }
+                const bool lane0_regs = prev_fast;
+                if (lane == 0 && lane0_regs) {
+#pragma unroll
+                    for (int j = 0; j < CNS_FLUSH_REGS; ++j) pn[j] = prev_nid[j];
+                }
 #pragma unroll
                 for (int i = 0; i < CNS_FLUSH_REGS; ++i) {
                     if (i < cnt) {
@@ -418,7 +442,7 @@ k_cns_links(CnsParams P)
                             } else if (pv_in_run) {
                                 const uint32_t want = (((rank - 1 - cns_char_rank(pb)) / 5u) << 4) | pb;
                                 uint32_t less = 0;
-                                if (lane > 0) {
+                                if (lane > 0 || lane0_regs) {
 #pragma unroll
                                     for (int j = 0; j < CNS_FLUSH_REGS; ++j) less += pn[j] < want;
                                 } else {
@@ -435,7 +459,11 @@ k_cns_links(CnsParams P)
                         link[my_start + i] = L;
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < CNS_FLUSH_REGS; ++j) prev_nid[j] = __shfl_sync(0xffffffffu, nid[j], 31);
+                prev_fast = true;
             } else {
+            prev_fast = false;
             uint32_t lastkey = 0;
             for (int i = 0; i < cnt; ++i) {        // selection by increasing key (keys of a position are distinct)
                 uint32_t bk = 0xffffffffu; int be = 0xffff;
@@ -545,9 +573,10 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
     const int T = TP.T;
     CnsPos* pos = P.pos + TP.pos_base;
     CnsLink* link = P.link + TP.link_base;
-    unsigned long long* bp = P.bp + TP.level_base;
+    CnsLevel* bp = P.bp + TP.level_base;
     CnsRun* my_runs = runs + TP.seg_first;
     uint32_t nrun = 0, fail = 0, level = 0;
+    uint32_t prev_fl = 0;                       // first level of the previous scored position
     // best node of the current run, per lane
     double g_best = -1.0;
     int g_level = -1, g_b = -1, g_t = 0, g_delta = 0, run_from = 0;
@@ -585,6 +614,7 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
                 const int cov = __shfl_sync(0xffffffffu, (int)pc.y, j);
                 const double pen = __dmul_rn(0.2, (double)cov);                 // 0.4 * 0.5 * coverage (cns_aux.c:164)
                 if (lane == 0) pos[t].first_level = level;
+                const uint32_t cur_fl = level;
                 const uint32_t e = s + n;
                 if (n <= (uint32_t)FAST_MAX) {
                     // ---- staging: the links of this position must have landed; keep 128 links ahead
@@ -638,7 +668,8 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
                         const uint32_t plo = __reduce_or_sync(0xffffffffu, (uint32_t)contrib);
                         const uint32_t phi = __reduce_or_sync(0xffffffffu, (uint32_t)(contrib >> 32));
                         if (lane == 0) {
-                            if (level < TP.level_cap) bp[level] = ((unsigned long long)phi << 32) | plo; else fail |= 1;
+                            if (level < TP.level_cap) { CnsLevel L; L.packed = ((unsigned long long)phi << 32) | plo; L.prev_first_level = prev_fl; L.pad_ = 0; bp[level] = L; }
+                            else fail |= 1;
                         }
                         ++level;
                         __syncwarp();
@@ -657,13 +688,17 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
                             packed |= (unsigned long long)(chosen ? cns_bp_code(best_key) : 7u) << (11 * cur_b);
                             if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)cur_d; g_x = node_first; }
                         };
+                        auto put_level = [&]() {
+                            if (level < TP.level_cap) { CnsLevel L; L.packed = packed; L.prev_first_level = prev_fl; L.pad_ = 0; bp[level] = L; }
+                            else fail |= 1;
+                        };
                         for (uint32_t x = s; x < e; ++x) {
                             const uint4 lr = *reinterpret_cast<const uint4*>(link + x);
                             const uint32_t key = lr.x, pred = lr.y;
                             if ((key >> 23) & 1) {
                                 if (have_node) close_node();
                                 if ((key >> 19) & 1) {
-                                    if (have_level) { if (level < TP.level_cap) bp[level] = packed; else fail |= 1; ++level; }
+                                    if (have_level) { put_level(); ++level; }
                                     have_level = true; packed = 0;
                                 }
                                 have_node = true; cur_b = (key >> 20) & 7; cur_d = key >> 24; node_first = x; best = -1.0; best_key = 0; chosen = false;
@@ -675,11 +710,12 @@ k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun
                             if (better) { best = sc; best_key = key; chosen = true; }
                         }
                         if (have_node) close_node();
-                        if (have_level) { if (level < TP.level_cap) bp[level] = packed; else fail |= 1; ++level; }
+                        if (have_level) { put_level(); ++level; }
                     }
                     level = __shfl_sync(0xffffffffu, level, 0);
                     __syncwarp();
                 }
+                prev_fl = cur_fl;
             }
             if (fl & 4) {
                 // ---- the run ends at t: its best node (cns_aux.c:177-184) = highest score, first in traversal order
@@ -721,7 +757,7 @@ k_cns_walk(CnsParams P, const CnsRun* __restrict__ runs, const uint32_t* __restr
     if (ti >= P.n_tpl) return;
     const CnsTemplate TP = P.tpl[ti];
     const CnsPos* pos = P.pos + TP.pos_base;
-    const unsigned long long* bp = P.bp + TP.level_base;
+    const CnsLevel* bp = P.bp + TP.level_base;
     uint8_t* rev = P.rev + TP.level_base;
     const uint32_t nrun = tpl_nrun[ti];
     uint32_t nseg = 0, out_used = 0, fail = 0;
@@ -733,7 +769,8 @@ k_cns_walk(CnsParams P, const CnsRun* __restrict__ runs, const uint32_t* __restr
         uint32_t n = 0;
         int cns_from = 0;
         for (;;) {
-            const uint32_t code = (uint32_t)(bp[cs] >> (11 * cb)) & 0x7ff;
+            const uint4 lv = *reinterpret_cast<const uint4*>(bp + cs);             // packed (x, y), prev_first_level (z)
+            const uint32_t code = (uint32_t)((((unsigned long long)lv.y << 32) | lv.x) >> (11 * cb)) & 0x7ff;
             const uint32_t pb = code & 7;
             if (pb == 7) break;                         // best_p_t_pos == -1: this node is not emitted
             const int emit = cb;
@@ -743,7 +780,7 @@ k_cns_walk(CnsParams P, const CnsRun* __restrict__ runs, const uint32_t* __restr
             else {
                 nt = ct - 1; nd = (int)(code >> 3);
                 if (nt < R.from) { stop_after = true; ns = 0; }     // predecessor outside the run: never scored
-                else ns = (int)pos[nt].first_level + nd;
+                else ns = (int)lv.z + nd;
             }
             cns_from = nt;
             if (emit != 4) { out[n] = (uint8_t)emit; ++n; }

@@ -279,11 +279,21 @@ __device__ __forceinline__ void ext_finish(ExtCtx& C, const ExtParams& P, int la
     const uint8_t* fin = left_keep ? ops + (lcap - L) : rbase + rstart;
     const int n_left = left_keep, n_all = left_keep + right_keep;
     int lq = 0, lt = 0, rq = 0, rt = 0, nm = 0;
-    for (int x = lane; x < n_all; x += 32) {
-        const int op = fin[x];
-        const int cq = op != OP_TONLY, ct = op != OP_QONLY;
-        if (x < n_left) { lq += cq; lt += ct; } else { rq += cq; rt += ct; }
-        nm += op == OP_MATCH;
+    int ins_carry = 0, long_ins = 0;                    // a run of >= 255 query-only columns (align_tags.c:40-44)
+    for (int base = 0; base < n_all; base += 32) {
+        const int x = base + lane;
+        const int op = x < n_all ? fin[x] : OP_MATCH;
+        if (x < n_all) {
+            const int cq = op != OP_TONLY, ct = op != OP_QONLY;
+            if (x < n_left) { lq += cq; lt += ct; } else { rq += cq; rt += ct; }
+            nm += op == OP_MATCH;
+        }
+        const uint32_t ins = __ballot_sync(0xffffffffu, x < n_all && op == OP_QONLY);
+        if (ins == 0xffffffffu) { ins_carry += 32; if (ins_carry >= 255) long_ins = 1; }
+        else {
+            if (ins_carry + __ffs(~ins) - 1 >= 255) long_ins = 1;       // ones at the low end continue the carried run
+            ins_carry = __clz(~ins);                                    // ones at the high end (inner runs are < 32)
+        }
     }
     for (int d = 16; d > 0; d >>= 1) {
         lq += __shfl_xor_sync(0xffffffffu, lq, d); lt += __shfl_xor_sync(0xffffffffu, lt, d);
@@ -296,6 +306,7 @@ __device__ __forceinline__ void ext_finish(ExtCtx& C, const ExtParams& P, int la
         A.qoff = QS - lq; A.qend = QS + rq; A.toff = TS - lt; A.tend = TS + rt;
         A.aln_size = n_all; A.n_match = nm;
         A.ok = n_all >= P.min_align_size;
+        A.long_ins = long_ins;
         A.ops_offset = (uint64_t)(fin - P.ops);
         P.results[C.ti] = A;
         C.active = 0;
