@@ -311,11 +311,22 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     cc, mc = stats["cns_counters"], stats["map_counters"]
-    # dominant kernel = the extension kernel k_extend: algorithmic bytes per launch =
-    # walk-back state written once (8 B per 32-row word per DP column) + packed bases of every block
-    # (0.25 B per base, ~2 x 512 per block) + one op byte per alignment column (~1.2 x 512 per block)
-    ext_bytes = cc["n_dp_word_updates"] * 8 + cc["n_block_aligns"] * (0.25 * 1024 + 620)
-    ext_gbs = ext_bytes / (stats["extend_ms"] * 1e-3) / 1e9 if stats["extend_ms"] else 0.0
+    # dominant kernel = the extension kernel k_extend.  The roofline describes its largest launch (round 0
+    # of the extensions, one template group: the extra pass above): algorithmic bytes of that launch = walk-back state
+    # written once (8 B per 32-row word per DP column) + packed bases of every block (0.25 B per base, ~2 x 512 per
+    # block) + one op byte per alignment column (~1.2 x 512 per block), divided by the launch's duration (CUDA events
+    # on the library's stream, around the kernel alone).
+    ext_bytes = cc["big_ext_word_updates"] * 8 + cc["big_ext_block_aligns"] * (0.25 * 1024 + 620)
+    ext_s = cc["big_ext_usec"] * 1e-6
+    ext_gbs = ext_bytes / ext_s / 1e9 if ext_s else 0.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("word_updates") and cc["big_ext_word_updates"]:
+            # DRAM bytes of the same launch under ncu --set full, scaled by the launch's word-updates
+            traffic = tj["dram_bytes"] * cc["big_ext_word_updates"] / tj["word_updates"]
+            traffic_src = tj.get("source")
     out = {
         "metric": "corrected_bases_per_sec", "value": bases / sec, "unit": "bases/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -337,8 +348,11 @@ def main():
                 "h2d_bytes_per_step": int((tm1.h2d_bytes - tm0.h2d_bytes) // max(args.steps, 1)),
                 "d2h_bytes_per_step": int((tm1.d2h_bytes - tm0.d2h_bytes) // max(args.steps, 1))},
         "roofline": {"kernel": "k_extend", "bound": "hbm", "achieved": ext_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": ext_gbs / peak, "traffic": None, "peak_source": peak_src,
-                     "word_updates_per_s": cc["n_dp_word_updates"] / (stats["extend_ms"] * 1e-3) if stats["extend_ms"] else 0.0},
+                     "frac": ext_gbs / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "launch": {"what": "largest k_extend launch (round 0, one template group)", "ms": cc["big_ext_usec"] / 1e3,
+                                "tasks": cc["big_ext_tasks"], "block_alignments": cc["big_ext_block_aligns"],
+                                "word_updates": cc["big_ext_word_updates"], "algorithmic_bytes": ext_bytes},
+                     "word_updates_per_s": cc["big_ext_word_updates"] / ext_s if ext_s else 0.0},
         "counters": {"map": mc, "cns": cc},
     }
     if not args.no_cpu_baseline:

@@ -224,6 +224,8 @@ int  nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads,
 typedef struct {
     uint64_t n_templates, n_extensions, n_block_aligns, n_dp_columns, n_dp_word_updates;
     uint64_t n_accepted, n_tags, n_cns_records, cns_bases;
+    /* the largest k_extend launch of the job (the roofline of bench.py describes this launch) */
+    uint64_t big_ext_tasks, big_ext_block_aligns, big_ext_word_updates, big_ext_usec;
 } nb_cns_counters;
 void nb_get_cns_counters(const nb_ctx* ctx, nb_cns_counters* out);
 

@@ -37,7 +37,8 @@ class MapCounters(C.Structure):
 
 class CnsCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_templates", "n_extensions", "n_block_aligns", "n_dp_columns",
-                                          "n_dp_word_updates", "n_accepted", "n_tags", "n_cns_records", "cns_bases")]
+                                          "n_dp_word_updates", "n_accepted", "n_tags", "n_cns_records", "cns_bases",
+                                          "big_ext_tasks", "big_ext_block_aligns", "big_ext_word_updates", "big_ext_usec")]
 
 
 CANDIDATE = np.dtype([("qid", "<i4"), ("sid", "<i4"), ("qdir", "<i4"), ("sdir", "<i4"), ("score", "<i4"),

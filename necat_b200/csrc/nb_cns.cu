@@ -448,6 +448,10 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             ctx->tm.h2d_bytes += wc->tm.h2d_bytes; ctx->tm.d2h_bytes += wc->tm.d2h_bytes;
             ctx->cc.n_extensions += wc->cc.n_extensions; ctx->cc.n_block_aligns += wc->cc.n_block_aligns;
             ctx->cc.n_dp_columns += wc->cc.n_dp_columns; ctx->cc.n_dp_word_updates += wc->cc.n_dp_word_updates;
+            if (wc->cc.big_ext_word_updates > ctx->cc.big_ext_word_updates) {
+                ctx->cc.big_ext_tasks = wc->cc.big_ext_tasks; ctx->cc.big_ext_block_aligns = wc->cc.big_ext_block_aligns;
+                ctx->cc.big_ext_word_updates = wc->cc.big_ext_word_updates; ctx->cc.big_ext_usec = wc->cc.big_ext_usec;
+            }
             memset(&wc->cc, 0, sizeof wc->cc); memset(&wc->tm, 0, sizeof wc->tm);
         }
     }

@@ -495,8 +495,10 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     P.error = error; P.min_align_size = min_align_size; P.tail_match_len = tail_match_len; P.block_size = 512;
     const size_t smem = sizeof(WarpScratch) * EXT_WARPS;
     NB_CUDA(ctx, cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(ctx->ev2, st);
     k_extend<<<grid, EXT_WARPS * 32, smem, st>>>(P);
     NB_LAUNCH_CHECK(ctx);
+    cudaEventRecord(ctx->ev3, st);
     unsigned long long cnt[4];
     NB_CUDA(ctx, cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
     NB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -504,6 +506,12 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     ctx->cc.n_block_aligns += cnt[0];
     ctx->cc.n_dp_columns += cnt[1];
     ctx->cc.n_dp_word_updates += cnt[2];
+    if (cnt[2] > ctx->cc.big_ext_word_updates) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+        ctx->cc.big_ext_tasks = n_tasks; ctx->cc.big_ext_block_aligns = cnt[0]; ctx->cc.big_ext_word_updates = cnt[2];
+        ctx->cc.big_ext_usec = (uint64_t)(ms * 1000.0f);
+    }
     return NB_OK;
 }
 
