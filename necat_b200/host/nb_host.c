@@ -9,6 +9,8 @@
 
 static const char kMagic[] = "ontcns_pac_header_hofuwhogfuewo";   /* 31 bytes, no NUL on disk */
 
+double nbh_phase_t0 = 0.0;
+
 double nbh_now(void)
 {
     struct timeval tv;

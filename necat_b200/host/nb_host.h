@@ -37,5 +37,8 @@ void nbh_log(const char* level, const char* file, int line, const char* fmt, ...
 #define NBH_LOG(...)   nbh_log("INFO", __FILE__, __LINE__, __VA_ARGS__)
 #define NBH_ERROR(...) do { nbh_log("ERROR", __FILE__, __LINE__, __VA_ARGS__); exit(1); } while (0)
 double nbh_now(void);
+/* NB_TRACE=1: wall-clock of the phases of an executable on stderr (start-up, I/O and tear-down dominate small jobs) */
+#define NBH_PHASE(name) do { if (getenv("NB_TRACE")) { const double now__ = nbh_now(); fprintf(stderr, "[phase] %-28s %8.3f s\n", name, now__ - nbh_phase_t0); nbh_phase_t0 = now__; } } while (0)
+extern double nbh_phase_t0;
 
 #endif

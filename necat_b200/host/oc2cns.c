@@ -72,6 +72,7 @@ int main(int argc, char* argv[])
     const char* raw_path = argv[argc - 1];
     if (nnode < 1) NBH_ERROR("invalid node count %d", nnode);
 
+    nbh_phase_t0 = nbh_now();
     nbh_volumes_info vi;
     if (nbh_volumes_info_load(wrk_dir, &vi)) NBH_ERROR("cannot read volume info in '%s'", wrk_dir);
     nbh_volume reads;
@@ -90,13 +91,16 @@ int main(int argc, char* argv[])
     if (fscanf(pf, "%d", &num_partitions) != 1) NBH_ERROR("cannot parse '%s'", path);
     fclose(pf);
 
+    NBH_PHASE("volume load");
     int dev = 0;
     const char* devs = getenv("NECAT_B200_DEVICE");
     if (devs) dev = atoi(devs);
     nb_ctx* ctx = NULL;
     if (nb_ctx_create(dev, &ctx)) NBH_ERROR("%s", nb_last_error(NULL));
+    NBH_PHASE("context");
     nb_volume* dreads = NULL;
     if (nb_volume_upload(ctx, reads.pac, reads.db_size, reads.offset, reads.size, reads.nseq, &dreads)) NBH_ERROR("%s", nb_last_error(ctx));
+    NBH_PHASE("volume upload");
 
     FILE* cns_out = fopen(cns_path, "w");
     FILE* raw_out = fopen(raw_path, "w");
@@ -124,6 +128,7 @@ int main(int argc, char* argv[])
         if (n) {
             nb_cns_record* recs = NULL; uint64_t nrec = 0; char* seq = NULL; uint64_t nseq = 0;
             if (nb_consensus_job(ctx, dreads, cans, n, &o, &recs, &nrec, &seq, &nseq)) NBH_ERROR("%s", nb_last_error(ctx));
+            NBH_PHASE("consensus job");
             char hdr[4096];
             for (uint64_t i = 0; i < nrec; ++i) {
                 const nb_cns_record* r = &recs[i];
@@ -136,6 +141,7 @@ int main(int argc, char* argv[])
             }
             nb_free(recs);
             nb_free(seq);
+            NBH_PHASE("fasta output");
         }
         free(cans);
         NBH_LOG("'%s' takes %.2lf secs.", job, nbh_now() - t0);
@@ -145,5 +151,6 @@ int main(int argc, char* argv[])
     nb_ctx_destroy(ctx);
     nbh_volume_free(&reads);
     nbh_volumes_info_free(&vi);
+    NBH_PHASE("tear-down");
     return 0;
 }

@@ -57,6 +57,7 @@ int main(int argc, char* argv[])
     const char* output = argv[argc - 1];
     if (o.job != 0 && o.job != 1) NBH_ERROR("invalid job -j %d", o.job);
 
+    nbh_phase_t0 = nbh_now();
     nbh_volumes_info vi;
     if (nbh_volumes_info_load(wrk_dir, &vi)) NBH_ERROR("cannot read volume info in '%s'", wrk_dir);
     if (vid < 0 || vid >= vi.num_volumes) NBH_ERROR("volume id %d out of range", vid);
@@ -65,16 +66,20 @@ int main(int argc, char* argv[])
     if (devs) dev = atoi(devs);
     nb_ctx* ctx = NULL;
     if (nb_ctx_create(dev, &ctx)) NBH_ERROR("%s", nb_last_error(NULL));
+    NBH_PHASE("context");
 
     nbh_volume ref;
     if (nbh_volume_load(vi.names[vid], &ref)) NBH_ERROR("cannot load volume '%s'", vi.names[vid]);
+    NBH_PHASE("volume load");
     nb_volume* dref = NULL;
     if (nb_volume_upload(ctx, ref.pac, ref.db_size, ref.offset, ref.size, ref.nseq, &dref)) NBH_ERROR("%s", nb_last_error(ctx));
+    NBH_PHASE("volume upload");
     double t0 = nbh_now();
     NBH_LOG("'build_lookup_table' BEGINS");
     nb_index* idx = NULL;
     if (nb_index_build(ctx, dref, o.kmer_size, o.kmer_cnt_cutoff, &idx)) NBH_ERROR("%s", nb_last_error(ctx));
     NBH_LOG("'build_lookup_table' takes %.2lf secs.", nbh_now() - t0);
+    NBH_PHASE("index");
 
     FILE* out = fopen(output, "w");
     if (!out) NBH_ERROR("cannot open '%s' for writing", output);
@@ -135,10 +140,12 @@ int main(int argc, char* argv[])
         NBH_LOG("'%s' takes %.2lf secs.", job, nbh_now() - t0);
     }
     if (fclose(out)) NBH_ERROR("closing '%s' failed", output);
+    NBH_PHASE("mapping + output");
     nb_index_free(ctx, idx);
     nb_volume_free(ctx, dref);
     nbh_volume_free(&ref);
     nbh_volumes_info_free(&vi);
     nb_ctx_destroy(ctx);
+    NBH_PHASE("tear-down");
     return 0;
 }
