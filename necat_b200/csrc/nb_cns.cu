@@ -273,6 +273,7 @@ struct JobShared {
     uint64_t cap;
     std::atomic<uint64_t> used;
     std::vector<uint8_t>* corrected;
+    size_t   n_long;                    // the first n_long templates of the job are its longest (0 = not arranged)
     std::mutex gpu;                     // one chunk at a time submits to the GPU and waits for it: the kernels are sized
                                         // to fill the machine, running two side by side only makes both slower;
                                         // what overlaps is the host work of one chunk with the kernels of another
@@ -285,14 +286,10 @@ struct ChunkTimes { double replay = 0, gather = 0, ext = 0, prep = 0, kern = 0, 
 static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_options& o, std::vector<Tpl>& tpls, std::vector<Can>& cans,
                          size_t c0, size_t c1, JobShared& sh, std::vector<nb_cns_record>& recs, ChunkTimes& tms, unsigned nthreads)
 {
-    cudaStream_t st = ctx->stream;
     HostTimer ht;
     double t_replay = 0, t_gather = 0, t_ext = 0, t_prep = 0, t_kern = 0, t_rec = 0, t_wait = 0, t_init = 0;
     float ext_ms = 0, cns_ms = 0;
-    std::vector<Fill> fills;
     std::vector<uint8_t>& corrected = *sh.corrected;
-    struct { uint64_t used; } so;
-    so.used = 0;                        // chunk-local offsets; rebased once the chunk knows how many bytes it emits
     // ---- extension rounds.  The templates of the chunk form up to NB_MAX_WORKERS groups, each driven by its own host
     //      thread on its own stream; one group at a time holds the GPU (sh.gpu), so the kernels run alone and at full
     //      width while the other groups replay the accept/skip logic and gather their next requests on the host.
@@ -312,14 +309,19 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
     if (n_groups > NB_MAX_WORKERS) n_groups = NB_MAX_WORKERS;
     if (n_groups < 1) n_groups = 1;
     std::vector<ExtGroup> groups((size_t)n_groups);
+    // the job put its longest templates first (sh.n_long of them): they form group 0 of the first chunk
+    const bool long_mode = n_groups >= 2 && c0 == 0 && sh.n_long > 0 && sh.n_long < c1;
     {
+        const size_t r0 = long_mode ? sh.n_long : c0;
+        const int first = long_mode ? 1 : 0;
+        if (long_mode) { groups[0].t0 = c0; groups[0].t1 = r0; }
         uint64_t total = 0, acc = 0;                        // equal numbers of first-round extensions x template length
         auto weight = [&](size_t t) { return (uint64_t)std::min<size_t>(tpls[t].n, 50) * (uint64_t)tpls[t].T; };
-        for (size_t t = c0; t < c1; ++t) total += weight(t);
-        size_t t = c0;
-        for (int k = 0; k < n_groups; ++k) {
+        for (size_t t = r0; t < c1; ++t) total += weight(t);
+        size_t t = r0;
+        for (int k = first; k < n_groups; ++k) {
             groups[(size_t)k].t0 = t;
-            const uint64_t want = total * (uint64_t)(k + 1) / (uint64_t)n_groups;
+            const uint64_t want = total * (uint64_t)(k - first + 1) / (uint64_t)(n_groups - first);
             while (t < c1 && (acc < want || k == n_groups - 1)) { acc += weight(t); ++t; }
             groups[(size_t)k].t1 = t;
         }
@@ -330,6 +332,8 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         ExtGroup& g = groups[(size_t)k];
         g.wc = ctx;
         if (k > 0) { const int rc = nb_worker_ctx(ctx, k, &g.wc); if (rc) return rc; }
+        // with the long group's consensus running beside them, the other groups' extension kernels leave it room on the SMs
+        g.wc->ext_ctas = (long_mode && k > 0) ? 3 : 0;
         group_bufs.emplace_back(g.wc);
         g.D = &group_bufs.back();
     }
@@ -408,14 +412,14 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             std::unique_lock<std::mutex> gpu(sh.gpu);
             g.tm.wait += gt.lap();
             NB_CUDA(wc, cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ExtTask) * tasks.size(), cudaMemcpyHostToDevice, gst));
-            cudaEventRecord(wc->ev0, st);
+            cudaEventRecord(wc->ev0, gst);
             rc = nb_run_extension(wc, reads, reads, d_tasks, (uint32_t)tasks.size(), d_res, d_ops, o.error, o.min_align_size, 4 /* ONC_TAIL_MATCH_LEN_LONG */);
             if (rc) return rc;
-            cudaEventRecord(wc->ev1, st);
+            cudaEventRecord(wc->ev1, gst);
             const size_t r0 = g.res.size();
             g.res.resize(r0 + tasks.size());
             NB_CUDA(wc, cudaMemcpyAsync(g.res.data() + r0, d_res, sizeof(nb_alignment) * tasks.size(), cudaMemcpyDeviceToHost, gst));
-            NB_CUDA(wc, cudaStreamSynchronize(st));
+            NB_CUDA(wc, cudaStreamSynchronize(gst));
             gpu.unlock();
             float ms = 0; cudaEventElapsedTime(&ms, wc->ev0, wc->ev1); g.tm.ext_ms += ms;
             wc->tm.h2d_bytes += sizeof(ExtTask) * tasks.size();
@@ -430,311 +434,361 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         }
         return NB_OK;
     };
+    std::vector<uint8_t> group_of(c1 - c0, 0);
+    for (int k = 0; k < n_groups; ++k)
+        for (size_t t = groups[(size_t)k].t0; t < groups[(size_t)k].t1; ++t) group_of[t - c0] = (uint8_t)k;
+
+    // ---- consensus of templates [a0, b0) on the stream of `cx`: link building, best path, walk-back, ASCII gather,
+    //      record planning.  take_gpu: hold the GPU like an extension round does; the long-template group runs it
+    //      WITHOUT the lock, side by side with the other groups' extension kernels (see below).
+    struct CnsOut {
+        std::vector<nb_cns_record> recs;
+        std::vector<Fill> fills;
+        const char* ascii = NULL;       // consensus stretches, dense (the context's pinned staging buffer)
+        uint64_t used = 0;              // bytes the records take in the output buffer
+        ChunkTimes tm;
+    };
+    auto cns_phase = [&](nb_ctx* cx, size_t a0, size_t b0, CnsOut& out, bool take_gpu) -> int {
+        if (cudaSetDevice(cx->device) != cudaSuccess) return nb_fail(cx, NB_ECUDA, "cudaSetDevice failed");
+        cudaStream_t cst = cx->stream;
+        HostTimer pt;
+        NbDevBuf D(cx);                         // everything this consensus allocates
+
+        // ---- consensus of the chunk
+        std::vector<CnsAln> alns;
+        std::vector<CnsTemplate> dt;
+        std::vector<size_t> dt_tpl;
+        uint64_t out_pool = 0, pos_total = 0, link_total = 0, level_total = 0; uint32_t seg_total = 0;
+        std::vector<size_t> order;
+        for (size_t t = a0; t < b0; ++t) order.push_back(t);
+        static const int kSort = getenv("NB_CNS_SORT") ? atoi(getenv("NB_CNS_SORT")) : 1;
+        static const int kLanes = 1;
+        static const int kWalkLanes = getenv("NB_CNS_WALK_LANES") ? atoi(getenv("NB_CNS_WALK_LANES")) : 1;
+        static const int kDpTest = getenv("NB_CNS_DP_TEST") ? atoi(getenv("NB_CNS_DP_TEST")) : 0;   // 1 = test build of k_cns_dp: tiny fast path and score ring
+        if (kSort) std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tpls[a].T != tpls[b].T ? tpls[a].T > tpls[b].T : a < b; });
+        dt.resize(order.size()); dt_tpl.resize(order.size());
+        {
+            uint32_t aln_total = 0;
+            for (size_t x = 0; x < order.size(); ++x) {
+                const Tpl& T = tpls[order[x]];
+                CnsTemplate& ct = dt[x];
+                memset(&ct, 0, sizeof ct);
+                ct.aln_first = aln_total; ct.n_aln = (uint32_t)T.acc.size(); ct.T = T.T;
+                aln_total += ct.n_aln;
+                ct.seg_cap = (uint32_t)(T.T / std::max(1, (int)(o.min_size * 0.85)) + 2);
+                ct.seg_first = seg_total; seg_total += ct.seg_cap;
+                ct.out_cap = (uint32_t)(T.T * 2 + 1024);
+                ct.out_base = out_pool; out_pool += ct.out_cap;
+                ct.level_cap = (uint32_t)(T.T * 3 + 2048);
+                cx->cc.n_accepted += T.acc.size();
+                dt_tpl[x] = order[x];
+            }
+            alns.resize(aln_total);
+            auto fill = [&](size_t x0, size_t x1) {             // the alignment descriptions, in parallel over templates
+                for (size_t x = x0; x < x1; ++x) {
+                    const size_t t = order[x];
+                    const Tpl& T = tpls[t];
+                    const ExtGroup& G = groups[group_of[t - c0]];
+                    CnsAln* dst = alns.data() + dt[x].aln_first;
+                    uint64_t cols = 0;
+                    for (const Accepted& a : T.acc) {
+                        const Can& c = cans[T.first + (size_t)a.can];
+                        const nb_alignment& r = G.res[(size_t)c.res];
+                        CnsAln ca;
+                        ca.ops = G.res_ops[(size_t)c.res]; ca.qseq_off = reads->h_off[c.qid];
+                        ca.aln_size = r.aln_size; ca.toff = r.toff; ca.tend = r.tend; ca.qstart = r.qoff;
+                        ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight; ca.drop = r.long_ins; ca.pad_ = 0;
+                        *dst++ = ca;
+                        cols += (uint64_t)r.aln_size;
+                    }
+                    dt[x].link_cap = (uint32_t)std::min<uint64_t>(cols + 32, 0xfffffff0ull);      // links <= columns
+                }
+            };
+            const size_t per = (order.size() + nthreads - 1) / nthreads;
+            std::vector<std::thread> th;
+            for (unsigned w = 1; w < nthreads && per; ++w) {
+                const size_t x0 = w * per, x1 = std::min(order.size(), x0 + per);
+                if (x0 >= x1) break;
+                th.emplace_back(fill, x0, x1);
+            }
+            if (per) fill(0, std::min(order.size(), per));
+            for (auto& x : th) x.join();
+        }
+        for (auto& ct : dt) {
+            ct.pos_base = pos_total; pos_total += (uint64_t)ct.T + 2;
+            ct.link_base = link_total; link_total += ct.link_cap;
+            ct.level_base = level_total; level_total += ct.level_cap;
+        }
+        std::vector<CnsSegment> segs(seg_total);
+        std::vector<uint32_t> nseg(dt.size(), 0);
+            std::vector<uint64_t> seg_dense(seg_total, 0);
+        uint8_t* d_seq_pool = NULL;
+        if (!dt.empty()) {
+            int rc;
+            CnsParams P;
+            memset(&P, 0, sizeof P);
+            CnsTemplate* d_tpl; CnsAln* d_aln;
+            if ((rc = D.get(&d_tpl, dt.size()))) return rc;
+            if ((rc = D.get(&d_aln, alns.size()))) return rc;
+            if ((rc = D.get(&P.seg, seg_total))) return rc;
+            if ((rc = D.get(&P.tpl_nseg, dt.size()))) return rc;
+            if ((rc = D.get(&P.seq_pool, out_pool))) return rc;
+            d_seq_pool = P.seq_pool;
+            if ((rc = D.get(&P.next_tpl, 1))) return rc;
+            if ((rc = D.get(&P.pos, pos_total))) return rc;
+            if ((rc = D.get(&P.link, link_total + 512))) return rc;     // k_cns_dp stages batches of 32 links up to 160 links ahead: slack past the last link
+            if ((rc = D.get(&P.bp, level_total))) return rc;
+            if ((rc = D.get(&P.rev, level_total))) return rc;
+            const unsigned links_grid = NB_SMS * 5;          // 20 warps per SM (shared-memory bound)
+            const size_t cursor_area = (size_t)links_grid * CNS_WARPS * CNS_MAX_ALN;    // one per side stream: slices run concurrently
+            if ((rc = D.get(&P.cursor, cursor_area * 2))) return rc;
+            if ((rc = D.get(&P.error_flag, 1))) return rc;
+            if ((rc = D.get(&P.counters, 4))) return rc;
+            CnsRun* d_runs; uint32_t* d_nrun;
+            if ((rc = D.get(&d_runs, seg_total))) return rc;
+            if ((rc = D.get(&d_nrun, dt.size()))) return rc;
+            NB_CUDA(cx, cudaMemcpyAsync(d_tpl, dt.data(), sizeof(CnsTemplate) * dt.size(), cudaMemcpyHostToDevice, cst));
+            NB_CUDA(cx, cudaMemcpyAsync(d_aln, alns.data(), sizeof(CnsAln) * alns.size(), cudaMemcpyHostToDevice, cst));
+            NB_CUDA(cx, cudaMemsetAsync(P.next_tpl, 0, sizeof(uint32_t), cst));
+            NB_CUDA(cx, cudaMemsetAsync(P.error_flag, 0, sizeof(uint32_t), cst));
+            NB_CUDA(cx, cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 4, cst));
+            P.pac = reads->d_pac; P.tpl = d_tpl; P.aln = d_aln; P.n_tpl = (uint32_t)dt.size();
+            P.min_cov = o.min_cov; P.min_size = o.min_size; P.lanes = kLanes < 1 ? 1 : (kLanes > 32 ? 32 : kLanes);
+            P.walk_lanes = kWalkLanes < 1 ? 1 : (kWalkLanes > 32 ? 32 : kWalkLanes);
+            P.flush_slow = getenv("NB_CNS_FLUSH_SLOW") ? atoi(getenv("NB_CNS_FLUSH_SLOW")) : 0;
+            const size_t smem = sizeof(CnsWarpShared) * CNS_WARPS;
+            if (smem > 48 * 1024) NB_CUDA(cx, cudaFuncSetAttribute(k_cns_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            out.tm.prep += pt.lap();
+            std::unique_lock<std::mutex> gpu(sh.gpu, std::defer_lock);
+            if (take_gpu) gpu.lock();
+            out.tm.wait += pt.lap();
+            cudaEventRecord(cx->ev2, cst);
+            // Slices of the length-sorted templates (equal total bases) alternate between two side streams: the
+            // link building of one slice overlaps the latency-bound DP chains of another; the slice with the
+            // longest templates starts first, its DP tail is hidden behind everything else.
+            {
+                static const int kSlices = getenv("NB_CNS_SLICES") ? atoi(getenv("NB_CNS_SLICES")) : 1;
+                int nsl = dt.size() >= 256 ? kSlices : 1;
+                if (nsl < 1) nsl = 1;
+                if (nsl > 64) nsl = 64;
+                uint64_t total_T = 0;
+                for (const auto& ct : dt) total_T += (uint64_t)ct.T;
+                uint32_t* d_next;
+                if ((rc = D.get(&d_next, 64))) return rc;
+                NB_CUDA(cx, cudaMemsetAsync(d_next, 0, sizeof(uint32_t) * 64, cst));
+                NB_CUDA(cx, cudaEventRecord(cx->aux_ev[2], cst));
+                for (int k = 0; k < 2; ++k) NB_CUDA(cx, cudaStreamWaitEvent(cx->aux[k], cx->aux_ev[2], 0));
+                size_t a = 0;
+                uint64_t acc = 0;
+                for (int sl = 0; sl < nsl && a < dt.size(); ++sl) {
+                    size_t b = a;
+                    const uint64_t want = total_T * (uint64_t)(sl + 1) / (uint64_t)nsl;
+                    while (b < dt.size() && (acc < want || sl == nsl - 1)) { acc += (uint64_t)dt[b].T; ++b; }
+                    if (b == a) continue;
+                    cudaStream_t ss = nsl == 1 ? cst : cx->aux[sl & 1];
+                    CnsParams Q = P;
+                    Q.tpl = d_tpl + a; Q.n_tpl = (uint32_t)(b - a); Q.tpl_nseg = P.tpl_nseg + a; Q.next_tpl = d_next + sl;
+                    Q.cursor = P.cursor + (size_t)(sl & 1) * cursor_area;
+                    unsigned lg = (unsigned)((b - a + CNS_WARPS - 1) / CNS_WARPS);
+                    if (lg > links_grid) lg = links_grid;
+                    k_cns_links<<<lg, CNS_WARPS * 32, smem, ss>>>(Q);
+                    NB_LAUNCH_CHECK(cx);
+                    const unsigned dp_warps = (unsigned)(b - a);      // one warp per template; the slice is sorted by length, the longest start first
+                    if (kDpTest) k_cns_dp<3, 8><<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
+                    else k_cns_dp<32, 256><<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
+                    NB_LAUNCH_CHECK(cx);
+                    const unsigned walk_warps = (unsigned)((b - a + Q.walk_lanes - 1) / Q.walk_lanes);
+                    k_cns_walk<<<(walk_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
+                    NB_LAUNCH_CHECK(cx);
+                    a = b;
+                }
+                if (nsl > 1)
+                    for (int k = 0; k < 2; ++k) {
+                        NB_CUDA(cx, cudaEventRecord(cx->aux_ev[k], cx->aux[k]));
+                        NB_CUDA(cx, cudaStreamWaitEvent(cst, cx->aux_ev[k], 0));
+                    }
+            }
+            cudaEventRecord(cx->ev3, cst);
+            uint32_t eflag = 0; unsigned long long cnt[4];
+            NB_CUDA(cx, cudaMemcpyAsync(&eflag, P.error_flag, sizeof eflag, cudaMemcpyDeviceToHost, cst));
+            NB_CUDA(cx, cudaMemcpyAsync(cnt, P.counters, sizeof cnt, cudaMemcpyDeviceToHost, cst));
+            NB_CUDA(cx, cudaMemcpyAsync(segs.data(), P.seg, sizeof(CnsSegment) * seg_total, cudaMemcpyDeviceToHost, cst));
+            NB_CUDA(cx, cudaMemcpyAsync(nseg.data(), P.tpl_nseg, sizeof(uint32_t) * dt.size(), cudaMemcpyDeviceToHost, cst));
+            NB_CUDA(cx, cudaStreamSynchronize(cst));
+            float ms = 0; cudaEventElapsedTime(&ms, cx->ev2, cx->ev3); out.tm.cns_ms += ms;
+            cx->tm.d2h_bytes += sizeof(CnsSegment) * seg_total;
+            cx->cc.n_tags += cnt[1];
+            if (eflag) return nb_fail(cx, NB_ELIMIT, "consensus kernel capacity exceeded (flags %u)", eflag);
+            {
+                // gather the stretches densely as ASCII, one exact-size D2H copy
+                std::vector<uint64_t> gsrc, gdst; std::vector<uint32_t> glen;
+                uint64_t dense = 0;
+                for (size_t x = 0; x < dt.size(); ++x)
+                    for (uint32_t k = 0; k < nseg[x]; ++k) {
+                        const CnsSegment& g = segs[dt[x].seg_first + k];
+                        gsrc.push_back(g.seq_off); gdst.push_back(dense); glen.push_back(g.len);
+                        seg_dense[dt[x].seg_first + k] = dense;
+                        dense += g.len;
+                    }
+                if ((rc = nb_pinned_reserve(cx, dense + 16))) return rc;
+                out.ascii = (const char*)cx->pinned;
+                if (!gsrc.empty()) {
+                    uint64_t *d_src, *d_dst; uint32_t* d_len; char* d_out;
+                    if ((rc = D.get(&d_src, gsrc.size()))) return rc;
+                    if ((rc = D.get(&d_dst, gsrc.size()))) return rc;
+                    if ((rc = D.get(&d_len, gsrc.size()))) return rc;
+                    if ((rc = D.get(&d_out, dense))) return rc;
+                    NB_CUDA(cx, cudaMemcpyAsync(d_src, gsrc.data(), 8 * gsrc.size(), cudaMemcpyHostToDevice, cst));
+                    NB_CUDA(cx, cudaMemcpyAsync(d_dst, gdst.data(), 8 * gsrc.size(), cudaMemcpyHostToDevice, cst));
+                    NB_CUDA(cx, cudaMemcpyAsync(d_len, glen.data(), 4 * gsrc.size(), cudaMemcpyHostToDevice, cst));
+                    k_gather_ascii<<<NB_SMS * 8, 256, 0, cst>>>(d_seq_pool, d_src, d_dst, d_len, (uint32_t)gsrc.size(), d_out);
+                    NB_LAUNCH_CHECK(cx);
+                    NB_CUDA(cx, cudaMemcpyAsync(cx->pinned, d_out, dense, cudaMemcpyDeviceToHost, cst));
+                    NB_CUDA(cx, cudaStreamSynchronize(cst));
+                    cx->tm.d2h_bytes += dense;
+                }
+            }
+            if (take_gpu) gpu.unlock();
+            out.tm.kern += pt.lap();
+        }
+        // ---- records (tasc/cbcns.c:108-264, consensus_one_read.c:20-136): plan, then fill in parallel
+            auto plan = [&](int id, int left, int right, int org, int ncan, int novl, double cutoff, int is_raw, uint32_t len) {
+            nb_cns_record r;
+            r.id = id; r.left = left; r.right = right; r.org_size = org; r.num_can = ncan; r.num_ovlps = novl;
+            r.ident_cutoff = cutoff; r.seq_offset = out.used; r.seq_len = (int)len; r.is_raw = is_raw;
+            out.recs.push_back(r);
+        };
+        auto add_raw = [&](int id, int from, int to) {      // read bases [from, to)
+            Fill f; f.dst = out.used; f.len = (uint32_t)(to - from); f.kind = 1; f.src = reads->h_off[id] + (uint64_t)from;
+            out.fills.push_back(f); out.used += f.len;
+        };
+        auto add_cns = [&](const CnsSegment& g, uint64_t dense_off) {
+            Fill f; f.dst = out.used; f.len = g.len; f.kind = 0; f.src = dense_off;
+            out.fills.push_back(f); out.used += f.len;
+        };
+        for (size_t x = 0; x < dt.size(); ++x) {
+            Tpl& T = tpls[dt_tpl[x]];
+            const CnsSegment* sg = segs.data() + dt[x].seg_first;
+            const uint64_t* sd = seg_dense.data() + dt[x].seg_first;
+            const uint32_t ns = nseg[x];
+            if (!o.full_consensus) {
+                for (uint32_t k = 0; k < ns; ++k) {
+                    plan(T.tid, sg[k].left, sg[k].right, T.T, T.num_can, T.num_ovlps, T.cutoff, 0, sg[k].len);
+                    add_cns(sg[k], sd[k]);
+                    cx->cc.cns_bases += sg[k].len;
+                }
+                // raw stretches between the corrected runs (get_raw_intvs, consensus_one_read.c:20-65)
+                bool first = true, open = true;
+                int left = 0;
+                const int end_off = T.T - 1;
+                for (uint32_t k = 0; k < ns; ++k) {
+                    const int fs = sg[k].left, fe = sg[k].right;
+                    if (first) {
+                        open = false; first = false;
+                        if (fs > 0) left = 0;
+                        else { left = fe + 1; continue; }
+                    }
+                    const int right = fs - 1;
+                    if (right - left + 1 >= 1000) {
+                        plan(T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff, 1, (uint32_t)(right + 1 - left));
+                        add_raw(T.tid, left, right + 1);
+                    }
+                    if (fe >= end_off) { open = false; break; }
+                    left = fe + 1;
+                }
+                if (open) {
+                    const int right = end_off;
+                    if (right - left + 1 >= 1000) {
+                        plan(T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff, 1, (uint32_t)(right + 1 - left));
+                        add_raw(T.tid, left, right + 1);
+                    }
+                }
+                corrected[(size_t)T.tid] = 1;                       // consensus_one_read.c:391 (r stays 1)
+            } else if (ns) {
+                // consensus_unbroken (cbcns.c:218-257): corrected runs spliced into the raw read
+                const uint64_t start = out.used;
+                const size_t ri = out.recs.size();
+                plan(T.tid, 0, T.T, T.T, T.num_can, T.num_ovlps, T.cutoff, 0, 0);
+                int last_raw = 0;
+                for (uint32_t k = 0; k < ns; ++k) {
+                    const int rf = sg[k].cns_from, rt = sg[k].cns_to;
+                    if (rf > last_raw) add_raw(T.tid, last_raw, rf);
+                    add_cns(sg[k], sd[k]);
+                    last_raw = rt;
+                }
+                if (last_raw < T.T) add_raw(T.tid, last_raw, T.T);
+                out.recs[ri].seq_len = (int)(out.used - start);
+                cx->cc.cns_bases += out.used - start;
+                corrected[(size_t)T.tid] = 1;
+            }
+            std::vector<uint16_t>().swap(T.cov);
+        }
+        out.tm.rec += pt.lap();
+        return NB_OK;
+    };
+    // records of one consensus into the job's buffer: place, rebase, fill in parallel
+    auto emit = [&](CnsOut& out) -> int {
+        HostTimer et;
+        const uint64_t base = sh.used.fetch_add(out.used);
+        if (base + out.used > sh.cap) return nb_fail(ctx, NB_ELIMIT, "output exceeds its upper bound");
+        for (auto& r : out.recs) r.seq_offset += base;
+        for (auto& f : out.fills) f.dst += base;
+        run_fills(out.fills, sh.buf, out.ascii, reads, nthreads);
+        recs.insert(recs.end(), out.recs.begin(), out.recs.end());
+        t_prep += out.tm.prep; t_kern += out.tm.kern; t_wait += out.tm.wait; t_rec += out.tm.rec + et.lap(); cns_ms += out.tm.cns_ms;
+        return NB_OK;
+    };
+    auto fold = [&](nb_ctx* wc) {                       // a worker's counters into this context
+        if (wc == ctx) return;
+        ctx->launches += wc->launches; wc->launches = 0;
+        ctx->tm.h2d_bytes += wc->tm.h2d_bytes; ctx->tm.d2h_bytes += wc->tm.d2h_bytes;
+        ctx->cc.n_extensions += wc->cc.n_extensions; ctx->cc.n_block_aligns += wc->cc.n_block_aligns;
+        ctx->cc.n_dp_columns += wc->cc.n_dp_columns; ctx->cc.n_dp_word_updates += wc->cc.n_dp_word_updates;
+        ctx->cc.n_accepted += wc->cc.n_accepted; ctx->cc.n_tags += wc->cc.n_tags; ctx->cc.cns_bases += wc->cc.cns_bases;
+        if (wc->cc.big_ext_word_updates > ctx->cc.big_ext_word_updates) {
+            ctx->cc.big_ext_tasks = wc->cc.big_ext_tasks; ctx->cc.big_ext_block_aligns = wc->cc.big_ext_block_aligns;
+            ctx->cc.big_ext_word_updates = wc->cc.big_ext_word_updates; ctx->cc.big_ext_usec = wc->cc.big_ext_usec;
+        }
+        memset(&wc->cc, 0, sizeof wc->cc); memset(&wc->tm, 0, sizeof wc->tm);
+    };
+    CnsOut out_long, out_main;
+    int rc_long = NB_OK;
     {
+        // Long-template mode: group 0 holds the longest templates.  Its extension rounds go first; its consensus then
+        // runs on this thread WITHOUT the GPU lock while the other groups extend -- the consensus kernels of the
+        // longest templates are one long dependent chain that keeps a handful of warps busy, the extension kernels
+        // fill the rest of the machine.
+        std::atomic<int> long_ext_done(long_mode ? 0 : 1);
         std::vector<std::thread> th;
-        for (int k = 1; k < n_groups; ++k) th.emplace_back([&, k]() { groups[(size_t)k].rc = ext_phase(groups[(size_t)k]); });
+        for (int k = 1; k < n_groups; ++k)
+            th.emplace_back([&, k]() {
+                while (!long_ext_done.load()) std::this_thread::yield();
+                groups[(size_t)k].rc = ext_phase(groups[(size_t)k]);
+            });
         groups[0].rc = ext_phase(groups[0]);
+        long_ext_done.store(1);
+        if (long_mode && groups[0].rc == NB_OK) {
+            rc_long = cns_phase(ctx, groups[0].t0, groups[0].t1, out_long, false);
+            if (rc_long == NB_OK) rc_long = emit(out_long);
+        }
         for (auto& x : th) x.join();
     }
-    std::vector<uint8_t> group_of(c1 - c0, 0);
     for (int k = 0; k < n_groups; ++k) {
         ExtGroup& g = groups[(size_t)k];
         if (g.rc) { if (g.wc != ctx) memcpy(ctx->err, g.wc->err, sizeof ctx->err); return g.rc; }
-        for (size_t t = g.t0; t < g.t1; ++t) group_of[t - c0] = (uint8_t)k;
         t_replay += g.tm.replay; t_gather += g.tm.gather; t_wait += g.tm.wait; t_ext += g.tm.ext; ext_ms += g.tm.ext_ms; t_init += g.tm.prep;
-        if (g.wc != ctx) {                              // fold the worker's counters into this context
-            nb_ctx* wc = g.wc;
-            ctx->launches += wc->launches; wc->launches = 0;
-            ctx->tm.h2d_bytes += wc->tm.h2d_bytes; ctx->tm.d2h_bytes += wc->tm.d2h_bytes;
-            ctx->cc.n_extensions += wc->cc.n_extensions; ctx->cc.n_block_aligns += wc->cc.n_block_aligns;
-            ctx->cc.n_dp_columns += wc->cc.n_dp_columns; ctx->cc.n_dp_word_updates += wc->cc.n_dp_word_updates;
-            if (wc->cc.big_ext_word_updates > ctx->cc.big_ext_word_updates) {
-                ctx->cc.big_ext_tasks = wc->cc.big_ext_tasks; ctx->cc.big_ext_block_aligns = wc->cc.big_ext_block_aligns;
-                ctx->cc.big_ext_word_updates = wc->cc.big_ext_word_updates; ctx->cc.big_ext_usec = wc->cc.big_ext_usec;
-            }
-            memset(&wc->cc, 0, sizeof wc->cc); memset(&wc->tm, 0, sizeof wc->tm);
-        }
+        fold(g.wc);
     }
+    if (rc_long) return rc_long;
     const double t_ext_wall = ht.lap();
-    NbDevBuf D(ctx);                            // everything the consensus of this chunk allocates
-
-    // ---- consensus of the chunk
-    std::vector<CnsAln> alns;
-    std::vector<CnsTemplate> dt;
-    std::vector<size_t> dt_tpl;
-    uint64_t out_pool = 0, pos_total = 0, link_total = 0, level_total = 0; uint32_t seg_total = 0;
-    std::vector<size_t> order;
-    for (size_t t = c0; t < c1; ++t) order.push_back(t);
-    static const int kSort = getenv("NB_CNS_SORT") ? atoi(getenv("NB_CNS_SORT")) : 1;
-    static const int kLanes = 1;
-    static const int kWalkLanes = getenv("NB_CNS_WALK_LANES") ? atoi(getenv("NB_CNS_WALK_LANES")) : 1;
-    static const int kDpTest = getenv("NB_CNS_DP_TEST") ? atoi(getenv("NB_CNS_DP_TEST")) : 0;   // 1 = test build of k_cns_dp: tiny fast path and score ring
-    if (kSort) std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tpls[a].T != tpls[b].T ? tpls[a].T > tpls[b].T : a < b; });
-    dt.resize(order.size()); dt_tpl.resize(order.size());
     {
-        uint32_t aln_total = 0;
-        for (size_t x = 0; x < order.size(); ++x) {
-            const Tpl& T = tpls[order[x]];
-            CnsTemplate& ct = dt[x];
-            memset(&ct, 0, sizeof ct);
-            ct.aln_first = aln_total; ct.n_aln = (uint32_t)T.acc.size(); ct.T = T.T;
-            aln_total += ct.n_aln;
-            ct.seg_cap = (uint32_t)(T.T / std::max(1, (int)(o.min_size * 0.85)) + 2);
-            ct.seg_first = seg_total; seg_total += ct.seg_cap;
-            ct.out_cap = (uint32_t)(T.T * 2 + 1024);
-            ct.out_base = out_pool; out_pool += ct.out_cap;
-            ct.level_cap = (uint32_t)(T.T * 3 + 2048);
-            ctx->cc.n_accepted += T.acc.size();
-            dt_tpl[x] = order[x];
+        const size_t a0 = long_mode ? groups[0].t1 : c0;
+        if (a0 < c1) {
+            int rc = cns_phase(ctx, a0, c1, out_main, true);
+            if (rc) return rc;
+            if ((rc = emit(out_main))) return rc;
         }
-        alns.resize(aln_total);
-        auto fill = [&](size_t x0, size_t x1) {             // the alignment descriptions, in parallel over templates
-            for (size_t x = x0; x < x1; ++x) {
-                const size_t t = order[x];
-                const Tpl& T = tpls[t];
-                const ExtGroup& G = groups[group_of[t - c0]];
-                CnsAln* dst = alns.data() + dt[x].aln_first;
-                uint64_t cols = 0;
-                for (const Accepted& a : T.acc) {
-                    const Can& c = cans[T.first + (size_t)a.can];
-                    const nb_alignment& r = G.res[(size_t)c.res];
-                    CnsAln ca;
-                    ca.ops = G.res_ops[(size_t)c.res]; ca.qseq_off = reads->h_off[c.qid];
-                    ca.aln_size = r.aln_size; ca.toff = r.toff; ca.tend = r.tend; ca.qstart = r.qoff;
-                    ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight; ca.drop = r.long_ins; ca.pad_ = 0;
-                    *dst++ = ca;
-                    cols += (uint64_t)r.aln_size;
-                }
-                dt[x].link_cap = (uint32_t)std::min<uint64_t>(cols + 32, 0xfffffff0ull);      // links <= columns
-            }
-        };
-        const size_t per = (order.size() + nthreads - 1) / nthreads;
-        std::vector<std::thread> th;
-        for (unsigned w = 1; w < nthreads && per; ++w) {
-            const size_t x0 = w * per, x1 = std::min(order.size(), x0 + per);
-            if (x0 >= x1) break;
-            th.emplace_back(fill, x0, x1);
-        }
-        if (per) fill(0, std::min(order.size(), per));
-        for (auto& x : th) x.join();
     }
-    for (auto& ct : dt) {
-        ct.pos_base = pos_total; pos_total += (uint64_t)ct.T + 2;
-        ct.link_base = link_total; link_total += ct.link_cap;
-        ct.level_base = level_total; level_total += ct.level_cap;
-    }
-    std::vector<CnsSegment> segs(seg_total);
-    std::vector<uint32_t> nseg(dt.size(), 0);
-    const char* ascii = NULL;           // consensus stretches of this chunk, dense (pinned staging buffer)
-    std::vector<uint64_t> seg_dense(seg_total, 0);
-    uint8_t* d_seq_pool = NULL;
-    if (!dt.empty()) {
-        int rc;
-        CnsParams P;
-        memset(&P, 0, sizeof P);
-        CnsTemplate* d_tpl; CnsAln* d_aln;
-        if ((rc = D.get(&d_tpl, dt.size()))) return rc;
-        if ((rc = D.get(&d_aln, alns.size()))) return rc;
-        if ((rc = D.get(&P.seg, seg_total))) return rc;
-        if ((rc = D.get(&P.tpl_nseg, dt.size()))) return rc;
-        if ((rc = D.get(&P.seq_pool, out_pool))) return rc;
-        d_seq_pool = P.seq_pool;
-        if ((rc = D.get(&P.next_tpl, 1))) return rc;
-        if ((rc = D.get(&P.pos, pos_total))) return rc;
-        if ((rc = D.get(&P.link, link_total + 512))) return rc;     // k_cns_dp stages batches of 32 links up to 160 links ahead: slack past the last link
-        if ((rc = D.get(&P.bp, level_total))) return rc;
-        if ((rc = D.get(&P.rev, level_total))) return rc;
-        const unsigned links_grid = NB_SMS * 5;          // 20 warps per SM (shared-memory bound)
-        const size_t cursor_area = (size_t)links_grid * CNS_WARPS * CNS_MAX_ALN;    // one per side stream: slices run concurrently
-        if ((rc = D.get(&P.cursor, cursor_area * 2))) return rc;
-        if ((rc = D.get(&P.error_flag, 1))) return rc;
-        if ((rc = D.get(&P.counters, 4))) return rc;
-        CnsRun* d_runs; uint32_t* d_nrun;
-        if ((rc = D.get(&d_runs, seg_total))) return rc;
-        if ((rc = D.get(&d_nrun, dt.size()))) return rc;
-        NB_CUDA(ctx, cudaMemcpyAsync(d_tpl, dt.data(), sizeof(CnsTemplate) * dt.size(), cudaMemcpyHostToDevice, st));
-        NB_CUDA(ctx, cudaMemcpyAsync(d_aln, alns.data(), sizeof(CnsAln) * alns.size(), cudaMemcpyHostToDevice, st));
-        NB_CUDA(ctx, cudaMemsetAsync(P.next_tpl, 0, sizeof(uint32_t), st));
-        NB_CUDA(ctx, cudaMemsetAsync(P.error_flag, 0, sizeof(uint32_t), st));
-        NB_CUDA(ctx, cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 4, st));
-        P.pac = reads->d_pac; P.tpl = d_tpl; P.aln = d_aln; P.n_tpl = (uint32_t)dt.size();
-        P.min_cov = o.min_cov; P.min_size = o.min_size; P.lanes = kLanes < 1 ? 1 : (kLanes > 32 ? 32 : kLanes);
-        P.walk_lanes = kWalkLanes < 1 ? 1 : (kWalkLanes > 32 ? 32 : kWalkLanes);
-        P.flush_slow = getenv("NB_CNS_FLUSH_SLOW") ? atoi(getenv("NB_CNS_FLUSH_SLOW")) : 0;
-        const size_t smem = sizeof(CnsWarpShared) * CNS_WARPS;
-        if (smem > 48 * 1024) NB_CUDA(ctx, cudaFuncSetAttribute(k_cns_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        t_prep += ht.lap();
-        std::unique_lock<std::mutex> gpu(sh.gpu);
-        t_wait += ht.lap();
-        cudaEventRecord(ctx->ev2, st);
-        // Slices of the length-sorted templates (equal total bases) alternate between two side streams: the
-        // link building of one slice overlaps the latency-bound DP chains of another; the slice with the
-        // longest templates starts first, its DP tail is hidden behind everything else.
-        {
-            static const int kSlices = getenv("NB_CNS_SLICES") ? atoi(getenv("NB_CNS_SLICES")) : 1;
-            int nsl = dt.size() >= 256 ? kSlices : 1;
-            if (nsl < 1) nsl = 1;
-            if (nsl > 64) nsl = 64;
-            uint64_t total_T = 0;
-            for (const auto& ct : dt) total_T += (uint64_t)ct.T;
-            uint32_t* d_next;
-            if ((rc = D.get(&d_next, 64))) return rc;
-            NB_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(uint32_t) * 64, st));
-            NB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[2], st));
-            for (int k = 0; k < 2; ++k) NB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[k], ctx->aux_ev[2], 0));
-            size_t a = 0;
-            uint64_t acc = 0;
-            for (int sl = 0; sl < nsl && a < dt.size(); ++sl) {
-                size_t b = a;
-                const uint64_t want = total_T * (uint64_t)(sl + 1) / (uint64_t)nsl;
-                while (b < dt.size() && (acc < want || sl == nsl - 1)) { acc += (uint64_t)dt[b].T; ++b; }
-                if (b == a) continue;
-                cudaStream_t ss = nsl == 1 ? st : ctx->aux[sl & 1];
-                CnsParams Q = P;
-                Q.tpl = d_tpl + a; Q.n_tpl = (uint32_t)(b - a); Q.tpl_nseg = P.tpl_nseg + a; Q.next_tpl = d_next + sl;
-                Q.cursor = P.cursor + (size_t)(sl & 1) * cursor_area;
-                unsigned lg = (unsigned)((b - a + CNS_WARPS - 1) / CNS_WARPS);
-                if (lg > links_grid) lg = links_grid;
-                k_cns_links<<<lg, CNS_WARPS * 32, smem, ss>>>(Q);
-                NB_LAUNCH_CHECK(ctx);
-                const unsigned dp_warps = (unsigned)(b - a);      // one warp per template; the slice is sorted by length, the longest start first
-                if (kDpTest) k_cns_dp<3, 8><<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
-                else k_cns_dp<32, 256><<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
-                NB_LAUNCH_CHECK(ctx);
-                const unsigned walk_warps = (unsigned)((b - a + Q.walk_lanes - 1) / Q.walk_lanes);
-                k_cns_walk<<<(walk_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
-                NB_LAUNCH_CHECK(ctx);
-                a = b;
-            }
-            if (nsl > 1)
-                for (int k = 0; k < 2; ++k) {
-                    NB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[k], ctx->aux[k]));
-                    NB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->aux_ev[k], 0));
-                }
-        }
-        cudaEventRecord(ctx->ev3, st);
-        uint32_t eflag = 0; unsigned long long cnt[4];
-        NB_CUDA(ctx, cudaMemcpyAsync(&eflag, P.error_flag, sizeof eflag, cudaMemcpyDeviceToHost, st));
-        NB_CUDA(ctx, cudaMemcpyAsync(cnt, P.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
-        NB_CUDA(ctx, cudaMemcpyAsync(segs.data(), P.seg, sizeof(CnsSegment) * seg_total, cudaMemcpyDeviceToHost, st));
-        NB_CUDA(ctx, cudaMemcpyAsync(nseg.data(), P.tpl_nseg, sizeof(uint32_t) * dt.size(), cudaMemcpyDeviceToHost, st));
-        NB_CUDA(ctx, cudaStreamSynchronize(st));
-        float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); cns_ms += ms;
-        ctx->tm.d2h_bytes += sizeof(CnsSegment) * seg_total;
-        ctx->cc.n_tags += cnt[1];
-        if (eflag) return nb_fail(ctx, NB_ELIMIT, "consensus kernel capacity exceeded (flags %u)", eflag);
-        {
-            // gather the stretches densely as ASCII, one exact-size D2H copy
-            std::vector<uint64_t> gsrc, gdst; std::vector<uint32_t> glen;
-            uint64_t dense = 0;
-            for (size_t x = 0; x < dt.size(); ++x)
-                for (uint32_t k = 0; k < nseg[x]; ++k) {
-                    const CnsSegment& g = segs[dt[x].seg_first + k];
-                    gsrc.push_back(g.seq_off); gdst.push_back(dense); glen.push_back(g.len);
-                    seg_dense[dt[x].seg_first + k] = dense;
-                    dense += g.len;
-                }
-            if ((rc = nb_pinned_reserve(ctx, dense + 16))) return rc;
-            ascii = (const char*)ctx->pinned;
-            if (!gsrc.empty()) {
-                uint64_t *d_src, *d_dst; uint32_t* d_len; char* d_out;
-                if ((rc = D.get(&d_src, gsrc.size()))) return rc;
-                if ((rc = D.get(&d_dst, gsrc.size()))) return rc;
-                if ((rc = D.get(&d_len, gsrc.size()))) return rc;
-                if ((rc = D.get(&d_out, dense))) return rc;
-                NB_CUDA(ctx, cudaMemcpyAsync(d_src, gsrc.data(), 8 * gsrc.size(), cudaMemcpyHostToDevice, st));
-                NB_CUDA(ctx, cudaMemcpyAsync(d_dst, gdst.data(), 8 * gsrc.size(), cudaMemcpyHostToDevice, st));
-                NB_CUDA(ctx, cudaMemcpyAsync(d_len, glen.data(), 4 * gsrc.size(), cudaMemcpyHostToDevice, st));
-                k_gather_ascii<<<NB_SMS * 8, 256, 0, st>>>(d_seq_pool, d_src, d_dst, d_len, (uint32_t)gsrc.size(), d_out);
-                NB_LAUNCH_CHECK(ctx);
-                NB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, d_out, dense, cudaMemcpyDeviceToHost, st));
-                NB_CUDA(ctx, cudaStreamSynchronize(st));
-                ctx->tm.d2h_bytes += dense;
-            }
-        }
-        gpu.unlock();
-        t_kern += ht.lap();
-    }
-    // ---- records (tasc/cbcns.c:108-264, consensus_one_read.c:20-136): plan, then fill in parallel
-    fills.clear();
-    auto plan = [&](int id, int left, int right, int org, int ncan, int novl, double cutoff, int is_raw, uint32_t len) {
-        nb_cns_record r;
-        r.id = id; r.left = left; r.right = right; r.org_size = org; r.num_can = ncan; r.num_ovlps = novl;
-        r.ident_cutoff = cutoff; r.seq_offset = so.used; r.seq_len = (int)len; r.is_raw = is_raw;
-        recs.push_back(r);
-    };
-    auto add_raw = [&](int id, int from, int to) {      // read bases [from, to)
-        Fill f; f.dst = so.used; f.len = (uint32_t)(to - from); f.kind = 1; f.src = reads->h_off[id] + (uint64_t)from;
-        fills.push_back(f); so.used += f.len;
-    };
-    auto add_cns = [&](const CnsSegment& g, uint64_t dense_off) {
-        Fill f; f.dst = so.used; f.len = g.len; f.kind = 0; f.src = dense_off;
-        fills.push_back(f); so.used += f.len;
-    };
-    for (size_t x = 0; x < dt.size(); ++x) {
-        Tpl& T = tpls[dt_tpl[x]];
-        const CnsSegment* sg = segs.data() + dt[x].seg_first;
-        const uint64_t* sd = seg_dense.data() + dt[x].seg_first;
-        const uint32_t ns = nseg[x];
-        if (!o.full_consensus) {
-            for (uint32_t k = 0; k < ns; ++k) {
-                plan(T.tid, sg[k].left, sg[k].right, T.T, T.num_can, T.num_ovlps, T.cutoff, 0, sg[k].len);
-                add_cns(sg[k], sd[k]);
-                ctx->cc.cns_bases += sg[k].len;
-            }
-            // raw stretches between the corrected runs (get_raw_intvs, consensus_one_read.c:20-65)
-            bool first = true, open = true;
-            int left = 0;
-            const int end_off = T.T - 1;
-            for (uint32_t k = 0; k < ns; ++k) {
-                const int fs = sg[k].left, fe = sg[k].right;
-                if (first) {
-                    open = false; first = false;
-                    if (fs > 0) left = 0;
-                    else { left = fe + 1; continue; }
-                }
-                const int right = fs - 1;
-                if (right - left + 1 >= 1000) {
-                    plan(T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff, 1, (uint32_t)(right + 1 - left));
-                    add_raw(T.tid, left, right + 1);
-                }
-                if (fe >= end_off) { open = false; break; }
-                left = fe + 1;
-            }
-            if (open) {
-                const int right = end_off;
-                if (right - left + 1 >= 1000) {
-                    plan(T.tid, left, right + 1, T.T, T.num_can, T.num_ovlps, T.cutoff, 1, (uint32_t)(right + 1 - left));
-                    add_raw(T.tid, left, right + 1);
-                }
-            }
-            corrected[(size_t)T.tid] = 1;                       // consensus_one_read.c:391 (r stays 1)
-        } else if (ns) {
-            // consensus_unbroken (cbcns.c:218-257): corrected runs spliced into the raw read
-            const uint64_t start = so.used;
-            const size_t ri = recs.size();
-            plan(T.tid, 0, T.T, T.T, T.num_can, T.num_ovlps, T.cutoff, 0, 0);
-            int last_raw = 0;
-            for (uint32_t k = 0; k < ns; ++k) {
-                const int rf = sg[k].cns_from, rt = sg[k].cns_to;
-                if (rf > last_raw) add_raw(T.tid, last_raw, rf);
-                add_cns(sg[k], sd[k]);
-                last_raw = rt;
-            }
-            if (last_raw < T.T) add_raw(T.tid, last_raw, T.T);
-            recs[ri].seq_len = (int)(so.used - start);
-            ctx->cc.cns_bases += so.used - start;
-            corrected[(size_t)T.tid] = 1;
-        }
-        std::vector<uint16_t>().swap(T.cov);
-    }
-    // ---- the chunk's bytes get their place in the job's buffer; then fill in parallel
-    const uint64_t base = sh.used.fetch_add(so.used);
-    if (base + so.used > sh.cap) return nb_fail(ctx, NB_ELIMIT, "output exceeds its upper bound");
-    for (auto& r : recs) r.seq_offset += base;
-    for (auto& f : fills) f.dst += base;
-    run_fills(fills, sh.buf, ascii, reads, nthreads);
-    t_rec += ht.lap();
     tms.replay = t_replay; tms.gather = t_gather; tms.ext = t_ext; tms.prep = t_prep; tms.kern = t_kern; tms.rec = t_rec; tms.wait = t_wait; tms.ext_wall = t_ext_wall; tms.init = t_init;
     tms.ext_ms = ext_ms; tms.cns_ms = cns_ms;
     return NB_OK;
@@ -863,6 +917,31 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
         if (per) build(0, std::min(tpls.size(), per));
         for (auto& x : th) x.join();
     }
+    // The consensus kernels of a template are a dependent chain over its positions, so the longest templates decide
+    // how long the consensus of a batch lasts.  They are moved to the front and get their own group, whose consensus
+    // runs beside the extension of everything else (process_chunk).
+    size_t n_long = 0;
+    {
+        const char* env_long = getenv("NB_CNS_LONG");
+        const char* env_lmin = getenv("NB_CNS_LONG_MIN");   // (tests lower it)
+        const size_t lmin = env_lmin ? (size_t)atoi(env_lmin) : 2048;
+        // off by default: measured on the E. coli workload, the extension kernels lose more (3 CTAs per SM, shared L2 / HBM)
+        // than the overlap gains (537 ms per step against 390), see DESIGN.md
+        if (env_long && atoi(env_long) != 0 && tpls.size() >= lmin && tpls.size() >= 32) {
+            n_long = std::min<size_t>(512, std::max<size_t>(8, tpls.size() / 32));
+            std::vector<uint32_t> idx(tpls.size());
+            for (size_t i = 0; i < idx.size(); ++i) idx[i] = (uint32_t)i;
+            std::nth_element(idx.begin(), idx.begin() + (long)n_long, idx.end(), [&](uint32_t a, uint32_t b) {
+                return tpls[a].T != tpls[b].T ? tpls[a].T > tpls[b].T : a < b; });
+            std::vector<uint8_t> is_long(tpls.size(), 0);
+            for (size_t i = 0; i < n_long; ++i) is_long[idx[i]] = 1;
+            std::vector<Tpl> re;
+            re.reserve(tpls.size());
+            for (size_t i = 0; i < tpls.size(); ++i) if (is_long[i]) re.push_back(std::move(tpls[i]));
+            for (size_t i = 0; i < tpls.size(); ++i) if (!is_long[i]) re.push_back(std::move(tpls[i]));
+            tpls.swap(re);
+        }
+    }
     ctx->cc.n_templates = tpls.size();
     t_setup += ht.lap();
 
@@ -893,7 +972,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
         }
     }
     JobShared sh;
-    sh.used = 0; sh.corrected = &corrected;
+    sh.used = 0; sh.corrected = &corrected; sh.n_long = n_long;
     {
         // upper bound of the output: a template emits at most its consensus pool (2 T + 1024, enforced by the kernel)
         // plus its raw leftovers; every other read of the id range may be dumped whole

@@ -472,8 +472,9 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     cudaStream_t st = ctx->stream;
     static const int kCtas = getenv("NB_EXT_CTAS") ? atoi(getenv("NB_EXT_CTAS")) : 4;
     int ctas_per_sm = kCtas;                // x 8 warps per SM
+    if (ctx->ext_ctas > 0 && ctx->ext_ctas < ctas_per_sm) ctas_per_sm = ctx->ext_ctas;
     const unsigned grid = NB_SMS * ctas_per_sm;
-    const size_t slots = (size_t)grid * EXT_WARPS * 2;       // two candidates in flight per warp
+    const size_t slots = (size_t)NB_SMS * kCtas * EXT_WARPS * 2;     // two candidates in flight per warp (sized for the full grid)
     if (!ctx->ext_mat || ctx->ext_mat_slots < slots) {
         if (ctx->ext_mat) cudaFree(ctx->ext_mat);
         ctx->ext_mat = NULL;

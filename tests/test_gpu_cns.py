@@ -73,6 +73,7 @@ def test_cns_multi_volume(built, tmp_path):
     {"NB_CNS_CHUNKS": "5", "NB_CNS_PIPES": "3"},    # the chunk pipeline: three workers on their own streams
     {"NB_CNS_CHUNKS": "2", "NB_CNS_PIPES": "1"},
     {"NB_CNS_GROUPS": "4", "NB_CNS_GROUPS_MIN": "8"},   # extension rounds of four template groups interleaved on the GPU
+    {"NB_CNS_GROUPS": "3", "NB_CNS_GROUPS_MIN": "8", "NB_CNS_LONG": "1", "NB_CNS_LONG_MIN": "8"},   # + the longest templates' consensus beside the extension
 ])
 def test_cns_kernel_variants(built, tmp_path, env):
     """The tunables of the consensus kernels (templates per warp, score-ring size, sliced launch) change
