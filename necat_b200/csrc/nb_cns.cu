@@ -556,6 +556,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             P.min_cov = o.min_cov; P.min_size = o.min_size; P.lanes = kLanes < 1 ? 1 : (kLanes > 32 ? 32 : kLanes);
             P.walk_lanes = kWalkLanes < 1 ? 1 : (kWalkLanes > 32 ? 32 : kWalkLanes);
             P.flush_slow = getenv("NB_CNS_FLUSH_SLOW") ? atoi(getenv("NB_CNS_FLUSH_SLOW")) : 0;
+            P.links_multi = getenv("NB_CNS_LINKS_MULTI") ? atoi(getenv("NB_CNS_LINKS_MULTI")) : 0;
             const size_t smem = sizeof(CnsWarpShared) * CNS_WARPS;
             if (smem > 48 * 1024) NB_CUDA(cx, cudaFuncSetAttribute(k_cns_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             out.tm.prep += pt.lap();

@@ -110,6 +110,7 @@ struct CnsParams {
     int                lanes;           // k_cns_dp: templates per warp (the other lanes idle)
     int                walk_lanes;      // k_cns_walk: likewise
     int                flush_slow;      // k_cns_links: 1 = always take the list-walking flush (tests)
+    int                links_multi;     // k_cns_links: 1 = reload / store the alignment state every tile even for <= 32 alignments (tests)
     uint32_t*          error_flag;      // 1 = level capacity, 2 = link pool / link capacity, 4 = output capacity
     unsigned long long* counters;       // [0] levels, [1] columns (tags), [2] links
 };
@@ -218,13 +219,23 @@ k_cns_links(CnsParams P)
         uint64_t r_qso = 0;
         double r_w = 0.0;
         bool r_valid = false;
-        if (lane < A) {
-            const CnsAln al = AL[lane];
-            r_ops = al.ops; r_n = al.aln_size; r_toff = al.toff; r_tend = al.tend; r_qso = al.qseq_off;
-            r_ql = (uint32_t)al.qlen | ((uint32_t)al.qdir << 31); r_w = al.weight;
-            r_valid = CU[lane].valid != 0;
-            r_qp = (uint32_t)al.qstart; r_lp = al.toff - 1;
-        }
+        // Up to 32 alignments: their state stays in these registers for the whole template.  More (long templates): the
+        // alignments are taken 32 at a time, every tile loads a group's state from HBM / L1 (coalesced, lane = alignment)
+        // and stores the cursors back afterwards.
+        const bool multi = A > 32 || P.links_multi;
+        auto load_group = [&](int g0) {
+            const int a = g0 + lane;
+            r_valid = false; r_toff = 0; r_tend = 0;
+            if (a < A) {
+                const CnsAln al = AL[a];
+                const CnsCursor cu = CU[a];
+                r_ops = al.ops; r_n = al.aln_size; r_toff = al.toff; r_tend = al.tend; r_qso = al.qseq_off;
+                r_ql = (uint32_t)al.qlen | ((uint32_t)al.qdir << 31); r_w = al.weight;
+                r_valid = cu.valid != 0;
+                r_x = cu.x; r_qp = cu.qpos; r_lp = cu.last_pos; r_ln = cu.last_node;
+            }
+        };
+        if (!multi) load_group(0);
         uint32_t ebase = 0;                     // links written so far
         uint32_t prev_start = 0, prev_cnt = 0;  // links of the last position of the previous tile
         uint32_t prev_nid[CNS_FLUSH_REGS];      // ... and their node ids in key order, when the fast flush left them (prev_fast)
@@ -307,9 +318,10 @@ k_cns_links(CnsParams P)
                     if (n_take < 32) break;
                 }
             };
-            // the first 32 alignments: cursor and description live in the registers of lane a; the op bytes of the next
-            // alignment are fetched while the current one is processed
-            {
+            // cursor and description of an alignment live in the registers of lane a (mod 32); the op bytes and query bases
+            // of the next alignment are fetched while the current one is processed
+            for (int g0 = 0; g0 < A; g0 += 32) {
+                if (multi) load_group(g0);
                 uint32_t amask = __ballot_sync(0xffffffffu, r_valid && r_toff < t1 && r_tend > t0);
                 int a = amask ? __ffs(amask) - 1 : -1;
                 int pre0 = OP_TONLY, pre1 = OP_TONLY;
@@ -350,18 +362,13 @@ k_cns_links(CnsParams P)
                     if (lane == a) { r_x = x; r_qp = qp; r_lp = last_pos; r_ln = last_node; }
                     a = nxt;
                 }
-            }
-            // alignments beyond the 32nd: cursor in HBM / L1
-            for (int a = 32; a < A; ++a) {
-                if (AL[a].toff >= t1 || AL[a].tend <= t0) continue;
-                const CnsCursor cu = CU[a];
-                if (!cu.valid) continue;
-                uint32_t x = cu.x, qp = cu.qpos;
-                int last_pos = cu.last_pos;
-                uint32_t last_node = cu.last_node;
-                sweep(AL[a].ops, AL[a].aln_size, AL[a].qseq_off, AL[a].qlen, AL[a].qdir, AL[a].weight, x, qp, last_pos, last_node, false, 0, 0, 0u, 0);
-                if (lane == 0) { CnsCursor c; c.x = x; c.qpos = qp; c.last_pos = last_pos; c.last_node = (uint16_t)last_node; c.valid = 1; c.pad_ = 0; CU[a] = c; }
-                __syncwarp();
+                if (multi) {
+                    if (g0 + lane < A) {
+                        CnsCursor c; c.x = r_x; c.qpos = r_qp; c.last_pos = r_lp; c.last_node = (uint16_t)r_ln; c.valid = (uint8_t)r_valid; c.pad_ = 0;
+                        CU[g0 + lane] = c;
+                    }
+                    __syncwarp();
+                }
             }
             if (S.pool_used > CNS_POOL) { fail |= 2; break; }
             // ---- flush: lane = position; its links go to HBM in key order, with the index of the

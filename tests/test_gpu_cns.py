@@ -68,7 +68,7 @@ def test_cns_multi_volume(built, tmp_path):
 
 @pytest.mark.parametrize("env", [
     {"NB_CNS_DP_TEST": "1"},                        # k_cns_dp with a 3-link fast path and a score ring of 8: serial + spill paths
-    {"NB_CNS_WALK_LANES": "32"}, {"NB_CNS_FLUSH_SLOW": "1"},
+    {"NB_CNS_WALK_LANES": "32"}, {"NB_CNS_FLUSH_SLOW": "1"}, {"NB_CNS_LINKS_MULTI": "1"},
     {"NB_CNS_SLICES": "4"},
     {"NB_CNS_CHUNKS": "5", "NB_CNS_PIPES": "3"},    # the chunk pipeline: three workers on their own streams
     {"NB_CNS_CHUNKS": "2", "NB_CNS_PIPES": "1"},
