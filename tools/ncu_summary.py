@@ -20,7 +20,7 @@ ki = h.index("Kernel Name")
 seen = {}
 print(f"# {os.path.basename(rep)}: ncu --set full --clock-control none --import-source on (per launch; cold caches, serialised)")
 for r in rows[2:]:
-    name = r[ki].split("(")[0]
+    name = r[ki].split("(")[0].replace("void ", "").split("<")[0]
     n = seen.get(name, 0)
     seen[name] = n + 1
     print(f"\n== {name} (launch #{n})")
