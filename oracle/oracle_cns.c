@@ -5,6 +5,7 @@
  * TEST INFRASTRUCTURE ONLY -- see necat_oracle.h.
  */
 #include "necat_oracle.h"
+#include "oracle_rescue.h"
 
 #include <getopt.h>
 #include <math.h>
@@ -383,10 +384,44 @@ static void emit_record(OCnsRecVec* out, int id, int left, int right, int org, i
     rec_push(out, &r);
 }
 
+/*
+ * cns_extension, consensus/consensus_aux.c:124-215.  The block-wise extension first; with -r 1, if it failed or left more
+ * than 200 bases of the candidate's chain unaligned, the O(nd) local alignment + the global alignment of its range
+ * (oracle_rescue.c) -- whose result is taken when both succeed; otherwise the block-wise result if there was one.
+ * On success A describes the alignment; *rescued_q / *rescued_t (malloc()ed, to be freed by the caller) hold the strings
+ * when they came from the rescue.
+ */
+static int cns_extension(OAligner* al, ORescue* rs, const OCandidate* c, const uint8_t* query, const uint8_t* target, int T,
+                         int min_align_size, int rescue, OAlignment* A, char** rescued_q, char** rescued_t)
+{
+    *rescued_q = NULL; *rescued_t = NULL;
+    const int small = o_onc_align(al, query, (int)c->qoff, (int)c->qsize, target, (int)c->soff, T, 512, min_align_size, 4, A);
+    int r = small;
+    if (r) {
+        const int lhang = A->qoff > (int)c->qbeg ? A->qoff - (int)c->qbeg : 0;
+        const int rhang = A->qend < (int)c->qend ? (int)c->qend - A->qend : 0;
+        if (lhang + rhang > 200) r = 0;
+    }
+    if (r) return 1;
+    if (rescue) {
+        int qb, qe, tb, te, diffs;
+        if (o_rescue_local(rs, query, (int)c->qoff, (int)c->qsize, target, (int)c->soff, T, min_align_size, &qb, &qe, &tb, &te, &diffs)) {
+            OAlignment R;
+            memset(&R, 0, sizeof R);
+            if (o_rescue_global(rs, query, qb, qe, target, tb, te, diffs, min_align_size, 4, &R.qoff, &R.qend, &R.toff, &R.tend,
+                                &R.ident_perc, &R.qaln, &R.taln, &R.aln_size)) {
+                R.ok = 1;
+                *A = R; *rescued_q = R.qaln; *rescued_t = R.taln;
+                return 1;
+            }
+        }
+    }
+    return small;
+}
+
 int o_consensus_one_read(const OVolume* reads, const OPackedCandidate* cans_in, size_t n, const OCnsOptions* opt, OCnsRecVec* out)
 {
     if ((size_t)opt->min_cov > n) return 0;                              /* :218 */
-    if (opt->rescue_long_indels) { fprintf(stderr, "oracle: -r 1 is not restated\n"); exit(2); }
     OPackedCandidate* cans = (OPackedCandidate*)malloc(sizeof(OPackedCandidate) * n);
     memcpy(cans, cans_in, sizeof(OPackedCandidate) * n);
     qsort(cans, n, sizeof(OPackedCandidate), cand_cns_gt);               /* :257 */
@@ -400,6 +435,8 @@ int o_consensus_one_read(const OVolume* reads, const OPackedCandidate* cans_in, 
     uint8_t* query = (uint8_t*)malloc(maxq + 1);
     int* cov = (int*)calloc((size_t)T + 1, sizeof(int));
     OAligner* al = o_aligner_new(opt->error);
+    ORescue* rs = opt->rescue_long_indels ? o_rescue_new(opt->error) : NULL;
+    char *rq = NULL, *rt = NULL;            /* strings of a rescued alignment */
     OTagVec tags = {0, 0, 0};
     /* extended read ids: small linear set (<= 300 entries) */
     int* used = (int*)malloc(sizeof(int) * (n + 1));
@@ -425,12 +462,13 @@ int o_consensus_one_read(const OVolume* reads, const OPackedCandidate* cans_in, 
             c.qsize = (int64_t)reads->seq[c.qid].size; c.ssize = T;
             if (USED(c.qid)) continue;
             o_extract(reads, (uint64_t)c.qid, c.qdir, query);
-            if (!o_onc_align(al, query, (int)c.qoff, (int)c.qsize, target, (int)c.soff, T, 512, opt->min_align_size, 4, &A)) continue;
+            if (!cns_extension(al, rs, &c, query, target, T, opt->min_align_size, opt->rescue_long_indels, &A, &rq, &rt)) continue;
             OPooled* p = &pool[n_pool++];
             p->qid = c.qid; p->qoff = A.qoff; p->qend = A.qend; p->qsize = (int)c.qsize; p->toff = A.toff; p->tend = A.tend;
             p->ident = A.ident_perc; p->aln_size = A.aln_size;
             p->qaln = (char*)malloc((size_t)A.aln_size + 1); memcpy(p->qaln, A.qaln, (size_t)A.aln_size);
             p->taln = (char*)malloc((size_t)A.aln_size + 1); memcpy(p->taln, A.taln, (size_t)A.aln_size);
+            free(rq); free(rt); rq = rt = NULL;
             USE(c.qid);
             if (good_overlap(A.qoff, A.qend, (int)c.qsize, A.toff, A.tend, T)) {
                 ident[n_ident++] = A.ident_perc;
@@ -486,15 +524,16 @@ int o_consensus_one_read(const OVolume* reads, const OPackedCandidate* cans_in, 
             if (USED(c.qid)) continue;
             if (cov_full(cov, (int)c.sbeg, (int)c.send, opt->max_cov)) continue;
             o_extract(reads, (uint64_t)c.qid, c.qdir, query);
-            int ok = o_onc_align(al, query, (int)c.qoff, (int)c.qsize, target, (int)c.soff, T, 512, opt->min_align_size, 4, &A);
+            int ok = cns_extension(al, rs, &c, query, target, T, opt->min_align_size, opt->rescue_long_indels, &A, &rq, &rt);
             ++num_can;
-            if (!ok) continue;
-            if (A.ident_perc < cutoff && !full_cov_ovlp(A.qoff, A.qend, (int)c.qsize, A.toff, A.tend, T, 5000, 100)) continue;
-            if (!mapping_range_ok(A.qoff, A.qend, (int)c.qsize, A.toff, A.tend, T, opt->min_align_size, opt->mapping_ratio)) continue;
-            ++num_ovlps;
-            tags_from_alignment(A.qaln, A.taln, (size_t)A.aln_size, A.toff, cns_weight(A.ident_perc), &tags);
-            for (int t = A.toff; t < A.tend; ++t) ++cov[t];
-            USE(c.qid);
+            if (ok && !(A.ident_perc < cutoff && !full_cov_ovlp(A.qoff, A.qend, (int)c.qsize, A.toff, A.tend, T, 5000, 100)) &&
+                mapping_range_ok(A.qoff, A.qend, (int)c.qsize, A.toff, A.tend, T, opt->min_align_size, opt->mapping_ratio)) {
+                ++num_ovlps;
+                tags_from_alignment(A.qaln, A.taln, (size_t)A.aln_size, A.toff, cns_weight(A.ident_perc), &tags);
+                for (int t = A.toff; t < A.tend; ++t) ++cov[t];
+                USE(c.qid);
+            }
+            free(rq); free(rt); rq = rt = NULL;
         }
     }
     /* consensus, tasc/cbcns.c:108-264 */
@@ -580,6 +619,7 @@ int o_consensus_one_read(const OVolume* reads, const OPackedCandidate* cans_in, 
     backbone_free(&bb);
     free(tags.a); free(used); free(cov); free(query); free(target); free(cans);
     o_aligner_free(al);
+    o_rescue_free(rs);
     return corrected;
 #undef USED
 #undef USE

@@ -10,6 +10,9 @@ Files written:
     cand_k15.bin                             oc2pmov SENSITIVE options (necat.pl:20,32)
     cns_f0.fasta.gz / raw_f0.fasta.gz        oc2pcan + oc2cns CNS_SENSITIVE -r 0 -f 0 on cand_k15.bin
     cns_f1.fasta.gz / raw_f1.fasta.gz        same with -f 1
+    r1/                                      a second, smaller set whose reads carry 300-700 base indels: vol0 + info files,
+                                             cand_k13.bin (oc2pmov), cns_r0 / raw_r0 / cns_r1 / raw_r1 .fasta.gz (oc2cns -r 0 / -r 1:
+                                             the DALIGNER + global-edlib rescue of correction iterations >= 2 changes most records)
     m4_k13.txt.gz                            oc2pmov -j 1 -u 0 -i 1 (M4 text lines, sorted)
     manifest.json                            options, counts, sha256 of the canonical (sorted) outputs
 All outputs are stored in canonical order (records sorted) because the reference's own order varies.
@@ -74,6 +77,32 @@ def main():
                 man[f"{kind}_f{f}"] = {"options": CNS + " -f " + f, "records": data.count(b">"), "sha256": hashlib.sha256(data).hexdigest()}
         for fn in ("vol0", "volume_names.txt", "reads_info.txt"):
             shutil.copy(os.path.join("vol", fn), os.path.join(HERE, fn))
+        # ---- the long-indel set for -r 1 (consensus_aux.c:169-201)
+        _, reads2 = gen_reads.generate(20_000, 18, 777, err=0.10, long_indel=0.5)
+        man["r1"] = {"generator": "gen_reads.generate(20000, 18, 777, err=0.10, long_indel=0.5)", "reads": len(reads2),
+                     "bases": int(sum(r.size for r in reads2))}
+        os.makedirs("r1w")
+        os.chdir("r1w")
+        formats.write_workdir("vol", reads2)
+        out2 = os.path.join(HERE, "r1")
+        os.makedirs(out2, exist_ok=True)
+        pm = "-k 13 -z 10 -q 500 -b 2000 -s 3 -n 500 -a 1000 -d 0.25 -e 0.5 -m 500 -t 1 -j 0 -u 1 -i 1"
+        subprocess.check_call([os.path.join(ref, "oc2pmov")] + pm.split() + ["vol", "0", "cand.bin"], stdout=subprocess.DEVNULL)
+        rec = formats.canonical_records(formats.read_candidates("cand.bin"))
+        rec.astype("<u4").tofile(os.path.join(out2, "cand_k13.bin"))
+        man["r1"]["cand_k13.bin"] = {"options": pm, "records": int(rec.shape[0]), "sha256": hashlib.sha256(rec.tobytes()).hexdigest()}
+        for r in ("0", "1"):
+            shutil.copy("cand.bin", "c.bin")
+            subprocess.check_call([os.path.join(ref, "oc2pcan"), "-t", "1", "vol", "c.bin"], stdout=subprocess.DEVNULL)
+            opts = CNS.replace("-r 0", "-r " + r) + " -f 0"
+            subprocess.check_call([os.path.join(ref, "oc2cns")] + opts.split() + ["-t", "2", "vol", "c.bin", "cns.fa", "raw.fa"], stdout=subprocess.DEVNULL)
+            for kind in ("cns", "raw"):
+                data = canon_fasta_bytes(kind + ".fa")
+                with gzip.GzipFile(os.path.join(out2, f"{kind}_r{r}.fasta.gz"), "wb", mtime=0) as g:
+                    g.write(data)
+                man["r1"][f"{kind}_r{r}"] = {"options": opts, "records": data.count(b">"), "sha256": hashlib.sha256(data).hexdigest()}
+        for fn in ("vol0", "volume_names.txt", "reads_info.txt"):
+            shutil.copy(os.path.join("vol", fn), os.path.join(out2, fn))
     finally:
         os.chdir(ROOT)
         shutil.rmtree(td, ignore_errors=True)

@@ -44,3 +44,21 @@ def test_m4_matches_golden(built, tmp_path):
     exp = gzip.open(os.path.join(util.GOLDEN, "m4_k13.txt.gz")).read().splitlines()
     assert len(exp) == MAN["m4_k13"]["records"] > 100
     assert got == exp
+
+
+@pytest.mark.parametrize("r", ["0", "1"])
+def test_rescue_matches_golden(built, tmp_path, r):
+    """oc2cns -r 1 (consensus_aux.c:169-201: O(nd) local alignment + global edlib where the block-wise extension
+    fails or stops short) on reads that carry 300-700 base indels: the rescue changes most records, and the oracle's
+    restatement of it (oracle/oracle_rescue.c) reproduces the reference's FASTA; -r 0 on the same set for contrast."""
+    wrk = util.golden_workdir_r1(tmp_path)
+    man = MAN["r1"]
+    cand = os.path.join(util.GOLDEN, "r1", "cand_k13.bin")
+    opts = man[f"cns_r{r}"]["options"].split()
+    util.run([util.ORACLE_CLI, "cns"] + opts + ["-M", "1", wrk, cand, "cns.fa", "raw.fa"], cwd=str(tmp_path))
+    exp = util.golden_fasta(f"r1/cns_r{r}")
+    assert len(exp) == man[f"cns_r{r}"]["records"] > 40
+    assert util.fasta_canon(str(tmp_path / "cns.fa")) == exp
+    assert util.fasta_canon(str(tmp_path / "raw.fa")) == util.golden_fasta(f"r1/raw_r{r}")
+    if r == "1":
+        assert exp != util.golden_fasta("r1/cns_r0"), "the fixture must exercise the rescue"

@@ -79,6 +79,16 @@ def golden_workdir(tmp):
     return "vol"
 
 
+def golden_workdir_r1(tmp):
+    """The long-indel golden set (tests/golden/r1): copies its volume into tmp/vol; run commands with cwd=tmp."""
+    import shutil
+    d = os.path.join(str(tmp), "vol")
+    os.makedirs(d, exist_ok=True)
+    for f in ("vol0", "volume_names.txt", "reads_info.txt"):
+        shutil.copy(os.path.join(GOLDEN, "r1", f), os.path.join(d, f))
+    return "vol"
+
+
 def golden_fasta(name):
     import gzip
     data = gzip.open(os.path.join(GOLDEN, name + ".fasta.gz")).read().split(b"\n")

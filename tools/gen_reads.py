@@ -40,10 +40,12 @@ def mutate(seq, rng, err, fsub=0.35, fdel=0.35, fins=0.30):
 
 
 def generate(genome_size, depth, seed, err=0.15, min_len=3000, max_len=60000,
-             mean_log=8.75, sd_log=0.55, repeat_len=0, repeat_copies=0, n_repeats=0):
+             mean_log=8.75, sd_log=0.55, repeat_len=0, repeat_copies=0, n_repeats=0, long_indel=0.0):
     """n_repeats families of `repeat_copies` near-identical (1 % diverged) copies of a
     random repeat_len segment are planted into the genome (exercises the k-mer count
-    cutoff, the 40-seed block cap and block zeroing)."""
+    cutoff, the 40-seed block cap and block zeroing).  long_indel: fraction of reads that
+    get one 300-700 base deletion or random insertion in their middle half (what oc2cns -r 1
+    rescues: the block-wise extension stops there); 0 draws nothing extra from the RNG."""
     rng = np.random.default_rng(seed)
     genome = rng.integers(0, 4, genome_size, dtype=np.uint8)
     for _ in range(n_repeats):
@@ -65,6 +67,13 @@ def generate(genome_size, depth, seed, err=0.15, min_len=3000, max_len=60000,
         if rng.random() < 0.5:
             frag = COMP[frag[::-1]]
         r = mutate(frag, rng, err)
+        if long_indel > 0.0 and rng.random() < long_indel and r.size > 4000:
+            n = int(rng.integers(300, 700))
+            at = int(rng.integers(r.size // 4, 3 * r.size // 4))
+            if rng.random() < 0.5:
+                r = np.concatenate([r[:at], r[at + n:]])
+            else:
+                r = np.concatenate([r[:at], rng.integers(0, 4, n, dtype=np.uint8), r[at:]])
         if r.size < min_len:
             continue
         reads.append(r)
