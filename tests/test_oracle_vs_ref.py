@@ -30,3 +30,25 @@ def test_pipeline_matches_reference(built, tmp_path, gen):
                   str(tmp_path / "o_cns.fa"), str(tmp_path / "o_raw.fa")])
         assert util.fasta_canon(str(tmp_path / "o_cns.fa")) == util.fasta_canon(str(tmp_path / "r_cns.fa")), f"mode {mode}"
         assert util.fasta_canon(str(tmp_path / "o_raw.fa")) == util.fasta_canon(str(tmp_path / "r_raw.fa"))
+
+
+@needs_ref
+def test_rescue_matches_reference(built, tmp_path):
+    """oc2cns -r 1 on a fresh seeded set with long indels: oracle (oracle_rescue.c) == reference binary."""
+    import shutil
+    wrk, _ = util.make_workdir(tmp_path, genome=16_000, depth=16, seed=53, err=0.10, long_indel=0.5)
+    r = util.run_pmov(util.ref_bin("oc2pmov"), PM13, wrk, 0, str(tmp_path / "r.bin"))
+    assert r.shape[0] > 100
+    c = str(tmp_path / "c.bin")
+    shutil.copy(str(tmp_path / "r.bin"), c)
+    util.run([util.ref_bin("oc2pcan"), "-t", "1", wrk, c])
+    out = {}
+    for rescue in ("0", "1"):
+        cns = f"-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0 -r {rescue} -f 0"
+        util.run([util.ref_bin("oc2cns")] + cns.split() + ["-t", "2", wrk, c, str(tmp_path / "r_cns.fa"), str(tmp_path / "r_raw.fa")])
+        util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", "1", wrk, str(tmp_path / "r.bin"),
+                  str(tmp_path / "o_cns.fa"), str(tmp_path / "o_raw.fa")])
+        out[rescue] = util.fasta_canon(str(tmp_path / "r_cns.fa"))
+        assert util.fasta_canon(str(tmp_path / "o_cns.fa")) == out[rescue], f"-r {rescue}"
+        assert util.fasta_canon(str(tmp_path / "o_raw.fa")) == util.fasta_canon(str(tmp_path / "r_raw.fa"))
+    assert len(out["1"]) > 20 and out["0"] != out["1"], "the set must exercise the rescue"
