@@ -185,6 +185,19 @@ int  nb_extend_candidates(nb_ctx* ctx, const nb_volume* reads,
                           double error, int min_align_size, int tail_match_len,
                           nb_alignment** out_aln, uint8_t** out_ops, uint64_t* out_ops_bytes);
 
+/* ------------------------------------------------------------------- rescue */
+/*
+ * First half of the oc2cns -r 1 rescue (consensus/consensus_aux.c:169-178): ocda_go (gapped_align/oc_daligner.c:34-79),
+ * Myers' O(nd) local alignment with path-tip trimming (gapped_align/align.c:382-1945) through the point
+ * (qstart, tstart) of query read qid (strand qdir) and template read sid (forward).  Returns the two ranges and the
+ * number of differences; ok = both ranges span at least min_align_size.  The second half (global alignment of the
+ * ranges, edlib/edlib_wrapper.c:111) is not on the GPU yet: nb_consensus_job refuses -r 1.
+ */
+typedef struct { uint32_t qid, sid; int32_t qdir, qstart, tstart, pad_; } nb_rescue_task;
+typedef struct { int32_t ok, qbeg, qend, tbeg, tend, diffs, overflow, pad_; } nb_rescue_result;
+int  nb_rescue_local(nb_ctx* ctx, const nb_volume* reads, const nb_rescue_task* tasks, uint64_t n, double error,
+                     int min_align_size, nb_rescue_result* results);
+
 /* ---------------------------------------------------------------- consensus */
 /* One FASTA record of oc2cns (common/cns_seq.h:7-41). */
 typedef struct {

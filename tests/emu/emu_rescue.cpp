@@ -1,0 +1,125 @@
+// emu_rescue.cpp -- TEST INFRASTRUCTURE: runs the warp-level core of the -r 1 local alignment kernel
+// (necat_b200/csrc/nb_rescue_core.cuh, the code the CUDA kernel instantiates) on the host, one std::thread per lane
+// with barriers for the warp collectives, and compares its end points with the oracle's (oracle/oracle_rescue.c) on
+// the candidates of a work directory.  No GPU needed: this is how the kernel logic is checked on the CPU-only CI.
+//
+//   emu_rescue <wrk_dir> <candidates.bin> <max_tasks> [error]
+#include <barrier>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../necat_b200/csrc/nb_rescue_core.cuh"
+extern "C" {
+#include "../../oracle/necat_oracle.h"
+#include "../../oracle/oracle_rescue.h"
+}
+
+struct EmuShared {
+    std::barrier<> bar{32};
+    int ival[32];
+    bool pred[32];
+};
+
+struct EmuWarp {
+    int l;
+    EmuShared* s;
+    int lane() const { return l; }
+    void sync() { s->bar.arrive_and_wait(); }
+    uint32_t ballot(bool p)
+    {
+        s->pred[l] = p;
+        s->bar.arrive_and_wait();
+        uint32_t r = 0;
+        for (int i = 0; i < 32; ++i) r |= (uint32_t)s->pred[i] << i;
+        s->bar.arrive_and_wait();
+        return r;
+    }
+    int shfl(int v, int src)
+    {
+        s->ival[l] = v;
+        s->bar.arrive_and_wait();
+        const int r = s->ival[src & 31];
+        s->bar.arrive_and_wait();
+        return r;
+    }
+};
+
+int main(int argc, char** argv)
+{
+    if (argc < 4) { fprintf(stderr, "usage: emu_rescue wrk_dir candidates max_tasks [error]\n"); return 2; }
+    const int max_tasks = atoi(argv[3]);
+    const double error = argc > 4 ? atof(argv[4]) : 0.5;
+    OVolumesInfo vi;
+    if (o_volumes_info_load(argv[1], &vi)) { fprintf(stderr, "cannot load %s\n", argv[1]); return 2; }
+    OVolume vol;
+    if (o_volume_load(vi.names[0], &vol)) { fprintf(stderr, "cannot load volume\n"); return 2; }
+    FILE* f = fopen(argv[2], "rb");
+    if (!f) return 2;
+    std::vector<OPackedCandidate> pc;
+    OPackedCandidate p;
+    while (fread(&p, sizeof p, 1, f) == 1) pc.push_back(p);
+    fclose(f);
+
+    int path_ave;
+    std::vector<int16_t> tt(1 << 15), ts(1 << 15);
+    rs_fill_tables(error, &path_ave, tt.data(), ts.data());
+    RsTables tb{path_ave, tt.data(), ts.data()};
+    const int cap = 8192;
+    std::vector<int> V0(cap), V1(cap), M0(cap), M1(cap);
+    std::vector<uint64_t> T0(cap), T1(cap);
+    ORescue* rs = o_rescue_new(error);
+
+    int n_done = 0, n_bad = 0;
+    const size_t stride = pc.size() / (size_t)max_tasks + 1;
+    for (size_t ci = 0; ci < pc.size() && n_done < max_tasks; ci += stride) {
+        OPackedCandidate q = pc[ci];
+        o_normalise_sdir(&q, (uint32_t)vol.seq[q.item[4]].size, (uint32_t)vol.seq[q.item[1]].size);
+        OCandidate c;
+        o_unpack_candidate(&c, &q);
+        const int qsize = (int)vol.seq[c.qid].size, tsize = (int)vol.seq[c.sid].size;
+        std::vector<uint8_t> qs((size_t)qsize), tsq((size_t)tsize);
+        o_extract(&vol, (uint64_t)c.qid, c.qdir, qs.data());
+        o_extract(&vol, (uint64_t)c.sid, 0, tsq.data());
+        int qb, qe, tb_, te, diffs;
+        const int ok = o_rescue_local(rs, qs.data(), (int)c.qoff, qsize, tsq.data(), (int)c.soff, tsize, 1000, &qb, &qe, &tb_, &te, &diffs);
+        (void)ok;
+        RsSeq A{vol.pac, vol.seq[c.qid].offset, qsize, c.qdir};
+        RsSeq B{vol.pac, vol.seq[c.sid].offset, tsize, 0};
+        const int k0 = (int)c.qoff - (int)c.soff, anti = (int)c.qoff + (int)c.soff;
+        RsTip fwd[32], rev[32];
+        EmuShared sh;
+        std::vector<std::thread> th;
+        for (int l = 0; l < 32; ++l)
+            th.emplace_back([&, l]() {
+                EmuWarp w{l, &sh};
+                RsBand bd{{V0.data(), V1.data()}, {M0.data(), M1.data()}, {T0.data(), T1.data()}, cap, 0};
+                fwd[l] = rs_wave(w, A, B, k0, anti, +1, tb, bd);
+                w.sync();
+                rev[l] = rs_wave(w, A, B, k0, anti, -1, tb, bd);
+            });
+        for (auto& t : th) t.join();
+        const bool same = fwd[0].apos == qe && fwd[0].bpos == te && rev[0].apos == qb && rev[0].bpos == tb_ &&
+                          fwd[0].diffs + rev[0].diffs == diffs && !fwd[0].overflow && !rev[0].overflow;
+        bool uniform = true;
+        for (int l = 1; l < 32; ++l)
+            uniform = uniform && fwd[l].apos == fwd[0].apos && fwd[l].bpos == fwd[0].bpos && fwd[l].diffs == fwd[0].diffs &&
+                      rev[l].apos == rev[0].apos && rev[l].bpos == rev[0].bpos && rev[l].diffs == rev[0].diffs;
+        if (!uniform)
+            for (int l = 1; l < 32; ++l)
+                if (fwd[l].apos != fwd[0].apos || fwd[l].bpos != fwd[0].bpos || fwd[l].diffs != fwd[0].diffs || rev[l].apos != rev[0].apos || rev[l].bpos != rev[0].bpos || rev[l].diffs != rev[0].diffs)
+                    fprintf(stderr, "  lane %d: fwd (%d,%d,%d) rev (%d,%d,%d) vs lane 0 fwd (%d,%d,%d) rev (%d,%d,%d)\n", l, fwd[l].apos, fwd[l].bpos, fwd[l].diffs,
+                            rev[l].apos, rev[l].bpos, rev[l].diffs, fwd[0].apos, fwd[0].bpos, fwd[0].diffs, rev[0].apos, rev[0].bpos, rev[0].diffs);
+        if (!same || !uniform) {
+            ++n_bad;
+            fprintf(stderr, "MISMATCH candidate %zu: oracle (%d,%d)-(%d,%d) d=%d | warp (%d,%d)-(%d,%d) d=%d uniform=%d\n", ci, qb, tb_, qe, te,
+                    diffs, rev[0].apos, rev[0].bpos, fwd[0].apos, fwd[0].bpos, fwd[0].diffs + rev[0].diffs, (int)uniform);
+        }
+        ++n_done;
+    }
+    printf("emu_rescue: %d tasks, %d mismatches\n", n_done, n_bad);
+    o_rescue_free(rs);
+    return n_bad ? 1 : 0;
+}
