@@ -242,3 +242,85 @@ NB_HD RsTip rs_wave(W& w, const RsSeq& A, const RsSeq& B, const int k0, const in
 #undef RS_IX
 #undef RS_CLIPS
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Second half of the rescue, building block: the last column of a GLOBAL edit-distance matrix -- what edlib's
+// Hirschberg step needs from each half (edlib/edlib.cpp:1177-1260: scores of the left half's last column, and of the
+// reversed right half's).  col[i] = D[i][tn] for i = 0 .. qn, D[0][j] = j, D[i][0] = i.
+//
+// Myers' bit-vector recurrence on 32-bit words, strip-mined: a strip is 32 words (1024 query rows), lane = word, the
+// lanes run along the anti-diagonal of the strip exactly like the forward pass of k_extend (the horizontal delta of
+// the row above and the target symbol travel lane to lane in one shuffle).  The horizontal deltas of a strip's bottom
+// row are kept per column (hbuf, one byte each, two generations) and enter the first word of the next strip.
+// q(i) = Q.at(q0 + i * qstep), t(j) = T.at(t0 + j * tstep): qstep = tstep = -1 walks the reversed sequences.
+template <class W>
+NB_HD void rs_nw_column(W& w, const RsSeq& Q, const int q0, const int qn, const int qstep, const RsSeq& T, const int t0, const int tn,
+                        const int tstep, int* col, int8_t* hbuf0, int8_t* hbuf1)
+{
+    const int lane = w.lane();
+    if (lane == 0) col[0] = tn;
+    int base = tn;                                           // D[r0][tn] of the current strip
+    int8_t* hin_buf = hbuf0;
+    int8_t* hout_buf = hbuf1;
+    for (int r0 = 0, strip = 0; r0 < qn; r0 += 1024, ++strip) {
+        const int rows = qn - r0 < 1024 ? qn - r0 : 1024;
+        const int nw = (rows + 31) >> 5;
+        const bool mine = lane < nw;
+        uint32_t pe0 = 0, pe1 = 0, pe2 = 0, pe3 = 0;
+        if (mine) {
+            const int rb = r0 + (lane << 5);
+            for (int r = 0; r < 32 && rb + r < qn; ++r) {
+                const int c = Q.at(q0 + (rb + r) * qstep);
+                const uint32_t bit = 1u << r;
+                pe0 |= c == 0 ? bit : 0; pe1 |= c == 1 ? bit : 0; pe2 |= c == 2 ? bit : 0; pe3 |= c == 3 ? bit : 0;
+            }
+        }
+        uint32_t Pv = 0xffffffffu, Mv = 0;
+        int carry = 0;                                       // (hout + 1) | symbol << 2 of the column this lane just finished
+        const int nsteps = tn + nw - 1;
+        for (int s = 0; s < nsteps; ++s) {
+            int cin = w.shfl(carry, lane > 0 ? lane - 1 : 0);
+            const int col_j = s - lane;
+            if (lane == 0 && col_j < tn) {
+                const int h = strip == 0 ? 1 : (int)hin_buf[col_j];
+                cin = (h + 1) | (T.at(t0 + col_j * tstep) << 2);
+            }
+            if (mine && col_j >= 0 && col_j < tn) {
+                const int hin = (cin & 3) - 1, tc = cin >> 2;
+                uint32_t Eq = tc == 0 ? pe0 : (tc == 1 ? pe1 : (tc == 2 ? pe2 : pe3));
+                const uint32_t Xv = Eq | Mv;
+                if (hin < 0) Eq |= 1u;
+                const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                uint32_t Ph = Mv | ~(Xh | Pv);
+                uint32_t Mh = Pv & Xh;
+                const int hout = (int)(Ph >> 31) - (int)(Mh >> 31);
+                Ph <<= 1; Mh <<= 1;
+                if (hin < 0) Mh |= 1u; else if (hin > 0) Ph |= 1u;
+                Pv = Mh | ~(Xv | Ph);
+                Mv = Ph & Xv;
+                carry = (hout + 1) | (tc << 2);
+                if (lane == nw - 1 && rows == 1024) hout_buf[col_j] = (int8_t)hout;     // bottom row of a full strip
+            }
+        }
+        // scores of this strip's rows in the last column: prefix sums of the vertical deltas
+        int live = 0;                                        // rows of my word
+        if (mine) { live = rows - (lane << 5); if (live > 32) live = 32; }
+        const uint32_t lm = live >= 32 ? 0xffffffffu : ((1u << live) - 1u);
+        int sum = 0;
+        { uint32_t p = Pv & lm, m = Mv & lm; while (p) { p &= p - 1; ++sum; } while (m) { m &= m - 1; --sum; } }
+        int incl = sum;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = w.shfl(incl, lane >= d ? lane - d : lane);
+            if (lane >= d) incl += o;
+        }
+        int v = base + incl - sum;                           // D[r0 + 32 lane][tn]
+        for (int b = 0; b < live; ++b) {
+            v += (int)((Pv >> b) & 1u) - (int)((Mv >> b) & 1u);
+            col[r0 + (lane << 5) + b + 1] = v;
+        }
+        base += w.shfl(incl, 31);
+        w.sync();                                            // hout_buf complete before it is read as hin_buf
+        int8_t* x = hin_buf; hin_buf = hout_buf; hout_buf = x;
+    }
+    w.sync();
+}

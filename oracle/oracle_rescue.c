@@ -334,6 +334,12 @@ static void nw_traceback(ORescue* r, const uint8_t* q, int qn, const uint8_t* t,
     for (size_t x = first, y = out->n; x + 1 < y; ++x) { --y; const uint8_t s = out->a[x]; out->a[x] = out->a[y]; out->a[y] = s; }
 }
 
+/* test hook: the column routine on its own (checked against the kernel core's strip-mined version) */
+void o_nw_last_column(const uint8_t* q, int qn, const uint8_t* t, int tn, int q_step, int t_step, int* col)
+{
+    nw_last_column(q, qn, t, tn, q_step, t_step, col);
+}
+
 static int ceil_div(int x, int y) { return x % y ? x / y + 1 : x / y; }
 
 /* obtainAlignment, edlib.cpp:1106-1161 + obtainAlignmentHirschberg, :1177-1340 */

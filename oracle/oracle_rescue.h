@@ -15,4 +15,6 @@ int o_rescue_local(ORescue* r, const uint8_t* query, int qstart, int qsize, cons
 int o_rescue_global(ORescue* r, const uint8_t* query, int qfrom, int qto, const uint8_t* target, int tfrom, int tto,
                     int tolerance, int min_align_size, int k_match, int* qoff, int* qend, int* toff, int* tend,
                     double* ident_perc, char** qaln, char** taln, int* aln_size);
+/* last column of the global DP (col[i] = D[i][tn], i = 0 .. qn); strides of -1 walk backwards from q / t */
+void o_nw_last_column(const uint8_t* q, int qn, const uint8_t* t, int tn, int q_step, int t_step, int* col);
 #endif

@@ -4,6 +4,7 @@
 // the candidates of a work directory.  No GPU needed: this is how the kernel logic is checked on the CPU-only CI.
 //
 //   emu_rescue <wrk_dir> <candidates.bin> <max_tasks> [error]
+#include <algorithm>
 #include <barrier>
 #include <cstdio>
 #include <cstdlib>
@@ -119,7 +120,41 @@ int main(int argc, char** argv)
         }
         ++n_done;
     }
-    printf("emu_rescue: %d tasks, %d mismatches\n", n_done, n_bad);
+    // ---- the strip-mined last-column routine (Hirschberg's building block) against the oracle's, both directions
+    int n_col = 0, n_col_bad = 0;
+    for (size_t ci = 0; ci < pc.size() && n_col < max_tasks; ci += stride) {
+        OPackedCandidate q = pc[ci];
+        o_normalise_sdir(&q, (uint32_t)vol.seq[q.item[4]].size, (uint32_t)vol.seq[q.item[1]].size);
+        OCandidate c;
+        o_unpack_candidate(&c, &q);
+        const int qsize = (int)vol.seq[c.qid].size, tsize = (int)vol.seq[c.sid].size;
+        std::vector<uint8_t> qs((size_t)qsize), tsq((size_t)tsize);
+        o_extract(&vol, (uint64_t)c.qid, c.qdir, qs.data());
+        o_extract(&vol, (uint64_t)c.sid, 0, tsq.data());
+        RsSeq A{vol.pac, vol.seq[c.qid].offset, qsize, c.qdir};
+        RsSeq B{vol.pac, vol.seq[c.sid].offset, tsize, 0};
+        // a query stretch of 1 to 3 strips against a shorter template stretch; even tasks forwards, odd tasks backwards
+        const int qn = std::min(qsize - 1, 700 + (int)(ci * 37 % 1900)), tn = std::min(tsize - 1, 150 + (int)(ci * 53 % 500));
+        const int back = n_col & 1;
+        const int q0 = back ? qn - 1 : 0, t0 = back ? tn - 1 : 0, step = back ? -1 : 1;
+        std::vector<int> want((size_t)qn + 1), got((size_t)qn + 1, -777);
+        o_nw_last_column(qs.data() + q0, qn, tsq.data() + t0, tn, step, step, want.data());
+        std::vector<int8_t> h0((size_t)tn + 1), h1((size_t)tn + 1);
+        EmuShared sh;
+        std::vector<std::thread> th;
+        for (int l = 0; l < 32; ++l)
+            th.emplace_back([&, l]() { EmuWarp w{l, &sh}; rs_nw_column(w, A, q0, qn, step, B, t0, tn, step, got.data(), h0.data(), h1.data()); });
+        for (auto& t : th) t.join();
+        if (want != got) {
+            ++n_col_bad;
+            size_t x = 0;
+            while (x < want.size() && want[x] == got[x]) ++x;
+            fprintf(stderr, "COLUMN MISMATCH candidate %zu (qn %d tn %d back %d) at row %zu: %d vs %d\n", ci, qn, tn, back, x, want[x], got[x]);
+        }
+        ++n_col;
+    }
+    n_bad += n_col_bad;
+    printf("emu_rescue: %d tasks, %d mismatches; %d columns, %d mismatches\n", n_done, n_bad - n_col_bad, n_col, n_col_bad);
     o_rescue_free(rs);
     return n_bad ? 1 : 0;
 }
