@@ -3,7 +3,7 @@
 // with barriers for the warp collectives, and compares its end points with the oracle's (oracle/oracle_rescue.c) on
 // the candidates of a work directory.  No GPU needed: this is how the kernel logic is checked on the CPU-only CI.
 //
-//   emu_rescue <wrk_dir> <candidates.bin> <max_tasks> [error]
+//   emu_rescue <wrk_dir> <candidates.bin> <wave_tasks> [column_tasks]
 #include <algorithm>
 #include <barrier>
 #include <cstdio>
@@ -52,7 +52,8 @@ int main(int argc, char** argv)
 {
     if (argc < 4) { fprintf(stderr, "usage: emu_rescue wrk_dir candidates max_tasks [error]\n"); return 2; }
     const int max_tasks = atoi(argv[3]);
-    const double error = argc > 4 ? atof(argv[4]) : 0.5;
+    const int max_cols = argc > 4 ? atoi(argv[4]) : max_tasks;
+    const double error = 0.5;
     OVolumesInfo vi;
     if (o_volumes_info_load(argv[1], &vi)) { fprintf(stderr, "cannot load %s\n", argv[1]); return 2; }
     OVolume vol;
@@ -122,7 +123,8 @@ int main(int argc, char** argv)
     }
     // ---- the strip-mined last-column routine (Hirschberg's building block) against the oracle's, both directions
     int n_col = 0, n_col_bad = 0;
-    for (size_t ci = 0; ci < pc.size() && n_col < max_tasks; ci += stride) {
+    const size_t cstride = pc.size() / (size_t)(max_cols > 0 ? max_cols : 1) + 1;
+    for (size_t ci = 0; ci < pc.size() && n_col < max_cols; ci += cstride) {
         OPackedCandidate q = pc[ci];
         o_normalise_sdir(&q, (uint32_t)vol.seq[q.item[4]].size, (uint32_t)vol.seq[q.item[1]].size);
         OCandidate c;
