@@ -324,3 +324,91 @@ NB_HD void rs_nw_column(W& w, const RsSeq& Q, const int q0, const int qn, const 
     }
     w.sync();
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Second half of the rescue, leaf of edlib's recursion: a GLOBAL alignment small enough for the traceback
+// (obtainAlignmentTraceback, edlib/edlib.cpp:887-1090: below 1 MiB of alignment data).  Forward pass as in
+// rs_nw_column, but every (word, column) keeps two bit-vectors -- Pv (cell = upper + 1) and Ph (cell = left + 1) -- in
+// mat[word * tn + column]; the walk back from (qn, tn) prefers up (a query base against a gap, EDLIB_EDOP_INSERT = 1),
+// then left (EDLIB_EDOP_DELETE = 2), then the diagonal (match 0 / mismatch 3), like the reference's traceback.
+// The operations are written backwards into ops[cap - 1], ops[cap - 2], ...; returns their number (cap >= qn + tn).
+struct RsWord2 { uint32_t pv, ph; };
+
+template <class W>
+NB_HD int rs_nw_leaf(W& w, const RsSeq& Q, const int q0, const int qn, const RsSeq& T, const int t0, const int tn,
+                     RsWord2* mat, int8_t* hbuf0, int8_t* hbuf1, uint8_t* ops, const int cap)
+{
+    const int lane = w.lane();
+    // ---- forward, strip by strip
+    int8_t* hin_buf = hbuf0;
+    int8_t* hout_buf = hbuf1;
+    for (int r0 = 0, strip = 0; r0 < qn; r0 += 1024, ++strip) {
+        const int rows = qn - r0 < 1024 ? qn - r0 : 1024;
+        const int nw = (rows + 31) >> 5;
+        const bool mine = lane < nw;
+        uint32_t pe0 = 0, pe1 = 0, pe2 = 0, pe3 = 0;
+        if (mine) {
+            const int rb = r0 + (lane << 5);
+            for (int r = 0; r < 32 && rb + r < qn; ++r) {
+                const int c = Q.at(q0 + rb + r);
+                const uint32_t bit = 1u << r;
+                pe0 |= c == 0 ? bit : 0; pe1 |= c == 1 ? bit : 0; pe2 |= c == 2 ? bit : 0; pe3 |= c == 3 ? bit : 0;
+            }
+        }
+        RsWord2* row = mat + (size_t)((r0 >> 5) + lane) * (size_t)tn;
+        uint32_t Pv = 0xffffffffu, Mv = 0;
+        int carry = 0;
+        const int nsteps = tn + nw - 1;
+        for (int s = 0; s < nsteps; ++s) {
+            int cin = w.shfl(carry, lane > 0 ? lane - 1 : 0);
+            const int col_j = s - lane;
+            if (lane == 0 && col_j < tn) {
+                const int h = strip == 0 ? 1 : (int)hin_buf[col_j];
+                cin = (h + 1) | (T.at(t0 + col_j) << 2);
+            }
+            if (mine && col_j >= 0 && col_j < tn) {
+                const int hin = (cin & 3) - 1, tc = cin >> 2;
+                uint32_t Eq = tc == 0 ? pe0 : (tc == 1 ? pe1 : (tc == 2 ? pe2 : pe3));
+                const uint32_t Xv = Eq | Mv;
+                if (hin < 0) Eq |= 1u;
+                const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                const uint32_t Ph = Mv | ~(Xh | Pv);
+                const uint32_t Mh = Pv & Xh;
+                const int hout = (int)(Ph >> 31) - (int)(Mh >> 31);
+                uint32_t Phs = Ph << 1, Mhs = Mh << 1;
+                if (hin < 0) Mhs |= 1u; else if (hin > 0) Phs |= 1u;
+                Pv = Mhs | ~(Xv | Phs);
+                Mv = Phs & Xv;
+                carry = (hout + 1) | (tc << 2);
+                RsWord2 x; x.pv = Pv; x.ph = Ph;
+                row[col_j] = x;
+                if (lane == nw - 1 && rows == 1024) hout_buf[col_j] = (int8_t)hout;
+            }
+        }
+        w.sync();
+        int8_t* x = hin_buf; hin_buf = hout_buf; hout_buf = x;
+    }
+    w.sync();
+    // ---- walk back (lane 0; the leaf is small)
+    int n = 0;
+    if (lane == 0) {
+        int i = qn, j = tn;
+        while (i > 0 || j > 0) {
+            int op;
+            if (j == 0) { op = 1; --i; }                                    // first column: only up
+            else if (i == 0) { op = 2; --j; }                               // first row: only left
+            else {
+                const RsWord2 x = mat[(size_t)((i - 1) >> 5) * (size_t)tn + (size_t)(j - 1)];
+                const int b = (i - 1) & 31;
+                if ((x.pv >> b) & 1u) { op = 1; --i; }
+                else if ((x.ph >> b) & 1u) { op = 2; --j; }
+                else { op = Q.at(q0 + i - 1) == T.at(t0 + j - 1) ? 0 : 3; --i; --j; }
+            }
+            ops[cap - 1 - n] = (uint8_t)op;
+            ++n;
+        }
+    }
+    n = w.shfl(n, 0);
+    w.sync();
+    return n;
+}

@@ -340,6 +340,19 @@ void o_nw_last_column(const uint8_t* q, int qn, const uint8_t* t, int tn, int q_
     nw_last_column(q, qn, t, tn, q_step, t_step, col);
 }
 
+/* test hook: the leaf (full-matrix traceback) on its own; ops_out receives qn + tn bytes at most, returns their number */
+int o_nw_traceback_ops(const uint8_t* q, int qn, const uint8_t* t, int tn, uint8_t* ops_out)
+{
+    ORescue* r = o_rescue_new(0.5);
+    OpVec v = { NULL, 0, 0 };
+    nw_traceback(r, q, qn, t, tn, &v);
+    memcpy(ops_out, v.a, v.n);
+    const int n = (int)v.n;
+    free(v.a);
+    o_rescue_free(r);
+    return n;
+}
+
 static int ceil_div(int x, int y) { return x % y ? x / y + 1 : x / y; }
 
 /* obtainAlignment, edlib.cpp:1106-1161 + obtainAlignmentHirschberg, :1177-1340 */

@@ -17,4 +17,6 @@ int o_rescue_global(ORescue* r, const uint8_t* query, int qfrom, int qto, const 
                     double* ident_perc, char** qaln, char** taln, int* aln_size);
 /* last column of the global DP (col[i] = D[i][tn], i = 0 .. qn); strides of -1 walk backwards from q / t */
 void o_nw_last_column(const uint8_t* q, int qn, const uint8_t* t, int tn, int q_step, int t_step, int* col);
+/* a leaf of the global alignment: full-matrix traceback (up, left, diagonal); edlib op codes 0 / 1 / 2 / 3 */
+int o_nw_traceback_ops(const uint8_t* q, int qn, const uint8_t* t, int tn, uint8_t* ops_out);
 #endif

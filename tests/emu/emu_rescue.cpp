@@ -155,8 +155,42 @@ int main(int argc, char** argv)
         }
         ++n_col;
     }
-    n_bad += n_col_bad;
-    printf("emu_rescue: %d tasks, %d mismatches; %d columns, %d mismatches\n", n_done, n_bad - n_col_bad, n_col, n_col_bad);
+    // ---- the leaf (forward pass with stored bit-vectors + walk-back) against the oracle's full-matrix traceback
+    int n_leaf = 0, n_leaf_bad = 0;
+    for (size_t ci = 0; ci < pc.size() && n_leaf < max_cols; ci += cstride) {
+        OPackedCandidate q = pc[ci];
+        o_normalise_sdir(&q, (uint32_t)vol.seq[q.item[4]].size, (uint32_t)vol.seq[q.item[1]].size);
+        OCandidate c;
+        o_unpack_candidate(&c, &q);
+        const int qsize = (int)vol.seq[c.qid].size, tsize = (int)vol.seq[c.sid].size;
+        std::vector<uint8_t> qs((size_t)qsize), tsq((size_t)tsize);
+        o_extract(&vol, (uint64_t)c.qid, c.qdir, qs.data());
+        o_extract(&vol, (uint64_t)c.sid, 0, tsq.data());
+        RsSeq A{vol.pac, vol.seq[c.qid].offset, qsize, c.qdir};
+        RsSeq B{vol.pac, vol.seq[c.sid].offset, tsize, 0};
+        // aligned stretches around the candidate's start so that the alignment is not degenerate; 1 or 2 strips
+        const int qn = std::min(qsize - (int)c.qoff, 300 + (int)(ci * 29 % 1100)), tn = std::min(tsize - (int)c.soff, 280 + (int)(ci * 31 % 900));
+        if (qn < 50 || tn < 50) continue;
+        const int q0 = (int)c.qoff, t0 = (int)c.soff;
+        std::vector<uint8_t> want((size_t)qn + tn), got((size_t)qn + tn);
+        const int nwant = o_nw_traceback_ops(qs.data() + q0, qn, tsq.data() + t0, tn, want.data());
+        const int nwords = (qn + 31) / 32;
+        std::vector<RsWord2> mat((size_t)nwords * tn);
+        std::vector<int8_t> h0((size_t)tn + 1), h1((size_t)tn + 1);
+        int ngot[32];
+        EmuShared sh;
+        std::vector<std::thread> th;
+        for (int l = 0; l < 32; ++l)
+            th.emplace_back([&, l]() { EmuWarp w{l, &sh}; ngot[l] = rs_nw_leaf(w, A, q0, qn, B, t0, tn, mat.data(), h0.data(), h1.data(), got.data(), qn + tn); });
+        for (auto& t : th) t.join();
+        bool okk = ngot[0] == nwant;
+        for (int x = 0; okk && x < nwant; ++x) okk = got[(size_t)(qn + tn - nwant + x)] == want[(size_t)x];
+        if (!okk) { ++n_leaf_bad; fprintf(stderr, "LEAF MISMATCH candidate %zu (qn %d tn %d): %d vs %d ops\n", ci, qn, tn, ngot[0], nwant); }
+        ++n_leaf;
+    }
+    printf("emu_rescue: leaves %d, %d mismatches\n", n_leaf, n_leaf_bad);
+    n_bad += n_col_bad + n_leaf_bad;
+    printf("emu_rescue: %d tasks, %d mismatches; %d columns, %d mismatches\n", n_done, n_bad - n_col_bad - n_leaf_bad, n_col, n_col_bad);
     o_rescue_free(rs);
     return n_bad ? 1 : 0;
 }
