@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../necat_b200/csrc/nb_rescue_core.cuh"
+#include "../../necat_b200/csrc/nb_rescue_driver.h"
 extern "C" {
 #include "../../oracle/necat_oracle.h"
 #include "../../oracle/oracle_rescue.h"
@@ -189,6 +190,82 @@ int main(int argc, char** argv)
         ++n_leaf;
     }
     printf("emu_rescue: leaves %d, %d mismatches\n", n_leaf, n_leaf_bad);
+    // ---- the whole global alignment (host-driven Hirschberg of nb_rescue_driver.h over the emulated cores) against
+    //      the oracle's o_rescue_global, on the ranges the local alignment finds
+    struct EmuBackend {
+        void columns(const std::vector<RgTask>& tasks, const std::vector<RgColJob>& jobs, std::vector<std::vector<int>>& cols)
+        {
+            cols.assign(jobs.size(), std::vector<int>());
+            for (size_t x = 0; x < jobs.size(); ++x) {
+                const RgColJob& j = jobs[x];
+                const RgTask& t = tasks[(size_t)j.task];
+                cols[x].assign((size_t)j.qn + 1, 0);
+                std::vector<int8_t> h0((size_t)j.tn + 1), h1((size_t)j.tn + 1);
+                EmuShared sh;
+                std::vector<std::thread> th;
+                for (int l = 0; l < 32; ++l)
+                    th.emplace_back([&, l]() { EmuWarp w{l, &sh}; rs_nw_column(w, t.Q, j.q0, j.qn, j.qstep, t.T, j.t0, j.tn, j.tstep, cols[x].data(), h0.data(), h1.data()); });
+                for (auto& q : th) q.join();
+            }
+        }
+        void leaves(const std::vector<RgTask>& tasks, const std::vector<RgLeafJob>& jobs, std::vector<std::vector<uint8_t>>& ops)
+        {
+            ops.assign(jobs.size(), std::vector<uint8_t>());
+            for (size_t x = 0; x < jobs.size(); ++x) {
+                const RgLeafJob& j = jobs[x];
+                const RgTask& t = tasks[(size_t)j.task];
+                const int cap = j.qn + j.tn;
+                std::vector<uint8_t> buf((size_t)cap);
+                std::vector<RsWord2> mat((size_t)((j.qn + 31) / 32) * (size_t)j.tn);
+                std::vector<int8_t> h0((size_t)j.tn + 1), h1((size_t)j.tn + 1);
+                int nops[32];
+                EmuShared sh;
+                std::vector<std::thread> th;
+                for (int l = 0; l < 32; ++l)
+                    th.emplace_back([&, l]() { EmuWarp w{l, &sh}; nops[l] = rs_nw_leaf(w, t.Q, j.q0, j.qn, t.T, j.t0, j.tn, mat.data(), h0.data(), h1.data(), buf.data(), cap); });
+                for (auto& q : th) q.join();
+                ops[x].assign(buf.begin() + (cap - nops[0]), buf.end());
+            }
+        }
+    } be;
+    int n_glob = 0, n_glob_bad = 0, n_glob_ok = 0;
+    const int max_glob = argc > 5 ? atoi(argv[5]) : 0;
+    for (size_t ci = 0; ci < pc.size() && n_glob < max_glob; ++ci) {
+        OPackedCandidate q = pc[ci];
+        o_normalise_sdir(&q, (uint32_t)vol.seq[q.item[4]].size, (uint32_t)vol.seq[q.item[1]].size);
+        OCandidate c;
+        o_unpack_candidate(&c, &q);
+        const int qsize = (int)vol.seq[c.qid].size, tsize = (int)vol.seq[c.sid].size;
+        std::vector<uint8_t> qs((size_t)qsize), tsq((size_t)tsize);
+        o_extract(&vol, (uint64_t)c.qid, c.qdir, qs.data());
+        o_extract(&vol, (uint64_t)c.sid, 0, tsq.data());
+        int qb, qe, tb_, te, diffs;
+        if (!o_rescue_local(rs, qs.data(), (int)c.qoff, qsize, tsq.data(), (int)c.soff, tsize, 1000, &qb, &qe, &tb_, &te, &diffs)) continue;
+        if (qe - qb > 3200 || qe - qb < 2100) continue;                     // big enough for one or two Hirschberg levels, small enough to emulate
+        int oqoff, oqend, otoff, otend, olen; double oid; char *oqa = NULL, *ota = NULL;
+        const int ook = o_rescue_global(rs, qs.data(), qb, qe, tsq.data(), tb_, te, diffs, 1000, 4, &oqoff, &oqend, &otoff, &otend, &oid, &oqa, &ota, &olen);
+        std::vector<RgTask> tasks(1);
+        tasks[0].Q = RsSeq{vol.pac, vol.seq[c.qid].offset, qsize, c.qdir};
+        tasks[0].T = RsSeq{vol.pac, vol.seq[c.sid].offset, tsize, 0};
+        tasks[0].qfrom = qb; tasks[0].qto = qe; tasks[0].tfrom = tb_; tasks[0].tto = te; tasks[0].tolerance = diffs;
+        std::vector<RgResult> res;
+        rg_run(be, tasks, 0.5, 1000, 4, res);
+        bool same = res[0].ok == ook;
+        if (same && ook) {
+            same = res[0].qoff == oqoff && res[0].qend == oqend && res[0].toff == otoff && res[0].tend == otend && res[0].aln_size == olen;
+            for (int x = 0; same && x < olen; ++x) {
+                const int op = res[0].ops[(size_t)x];
+                const int want = oqa[x] == '-' ? 2 : (ota[x] == '-' ? 1 : (oqa[x] == ota[x] ? 0 : 3));
+                same = op == want;
+            }
+        }
+        free(oqa); free(ota);
+        if (!same) { ++n_glob_bad; fprintf(stderr, "GLOBAL MISMATCH candidate %zu: ok %d vs %d\n", ci, res[0].ok, ook); }
+        n_glob_ok += ook;
+        ++n_glob;
+    }
+    n_bad += n_glob_bad;
+    printf("emu_rescue: global alignments %d (%d ok), %d mismatches\n", n_glob, n_glob_ok, n_glob_bad);
     n_bad += n_col_bad + n_leaf_bad;
     printf("emu_rescue: %d tasks, %d mismatches; %d columns, %d mismatches\n", n_done, n_bad - n_col_bad - n_leaf_bad, n_col, n_col_bad);
     o_rescue_free(rs);

@@ -13,6 +13,7 @@ def test_rescue_core_matches_oracle(built, tmp_path):
     subprocess.check_call(["make", "-s", "-C", util.ORACLE_DIR, "emu"])
     wrk = util.golden_workdir_r1(tmp_path)
     cand = os.path.join(util.GOLDEN, "r1", "cand_k13.bin")
-    p = util.run([os.path.join(util.ORACLE_DIR, "_build", "emu_rescue"), wrk, cand, "3", "6"], cwd=str(tmp_path))
+    p = util.run([os.path.join(util.ORACLE_DIR, "_build", "emu_rescue"), wrk, cand, "3", "6", "2"], cwd=str(tmp_path))
     assert b"3 tasks, 0 mismatches; 6 columns, 0 mismatches" in p.stdout
     assert b"leaves 6, 0 mismatches" in p.stdout
+    assert b"global alignments 2 (2 ok), 0 mismatches" in p.stdout      # host-driven Hirschberg (nb_rescue_driver.h) over the emulated cores
