@@ -198,6 +198,17 @@ typedef struct { int32_t ok, qbeg, qend, tbeg, tend, diffs, overflow, pad_; } nb
 int  nb_rescue_local(nb_ctx* ctx, const nb_volume* reads, const nb_rescue_task* tasks, uint64_t n, double error,
                      int min_align_size, nb_rescue_result* results);
 
+/*
+ * Second half of the rescue: edlib_go with find_path (edlib/edlib_wrapper.c:111-255) -- the global alignment of query
+ * range [qfrom, qto) (strand qdir) with template range [tfrom, tto) if their edit distance is <= tolerance, by edlib's
+ * rules for choosing among co-optimal alignments (Hirschberg's first split row, up / left / diagonal traceback below
+ * 1 MiB of alignment data), trimmed to its first and last run of k_match matches.  Results as nb_extend_candidates.
+ * NOT YET RUN ON A GPU (round 1 ran out of GPU time): its cores and recursion are verified by host emulation only.
+ */
+typedef struct { uint32_t qid, sid; int32_t qdir, qfrom, qto, tfrom, tto, tolerance; } nb_rescue_range;
+int  nb_rescue_global(nb_ctx* ctx, const nb_volume* reads, const nb_rescue_range* ranges, uint64_t n, double error,
+                      int min_align_size, int k_match, nb_alignment** out_aln, uint8_t** out_ops, uint64_t* out_ops_bytes);
+
 /* ---------------------------------------------------------------- consensus */
 /* One FASTA record of oc2cns (common/cns_seq.h:7-41). */
 typedef struct {

@@ -55,7 +55,7 @@ EXPORTS = ["nb_ctx_create", "nb_ctx_destroy", "nb_last_error", "nb_version", "nb
            "nb_index_download", "nb_map_options_default", "nb_map_volume", "nb_map_volume_aln", "nb_pack_candidate", "nb_free",
            "nb_get_map_counters", "nb_cns_options_default", "nb_extend_candidates", "nb_consensus_job",
            "nb_consensus_job_sharded",
-           "nb_get_cns_counters", "nb_rescue_local"]
+           "nb_get_cns_counters", "nb_rescue_local", "nb_rescue_global"]
 
 _lib = None
 

@@ -73,3 +73,76 @@ def test_rescue_local_matches_oracle(built, tmp_path):
         n_ok += ok
     assert len(tasks) > 500 and n_ok > 100
     ctx.free_volume(dvol)
+
+
+class Range(C.Structure):
+    _fields_ = [("qid", C.c_uint32), ("sid", C.c_uint32)] + [(n, C.c_int32) for n in ("qdir", "qfrom", "qto", "tfrom", "tto", "tolerance")]
+
+
+@pytest.mark.skipif(os.environ.get("NB_TEST_UNVERIFIED") != "1",
+                    reason="nb_rescue_global's GPU shells were written after round 1's GPU budget ran out; its cores and "
+                           "recursion are verified by host emulation (tests/test_emu_rescue.py).  Set NB_TEST_UNVERIFIED=1 to run.")
+def test_rescue_global_matches_oracle(built, tmp_path):
+    """edlib_go on the GPU (nb_rescue_global) against the oracle's o_rescue_global on the ranges the local alignment finds."""
+    from necat_b200 import capi, formats
+    import oracle_ffi
+    wrk = util.golden_workdir_r1(tmp_path)
+    os.chdir(str(tmp_path))
+    vol = formats.read_volume(os.path.join(wrk, "vol0"))
+    cand = formats.read_candidates(os.path.join(util.GOLDEN, "r1", "cand_k13.bin"))
+    sizes = vol.info["size"].astype(np.int64)
+    starts = vol.info["offset"].astype(np.int64)
+    codes = formats.unpack_bases(vol.pac, vol.db_size)
+    comp = np.array([3, 2, 1, 0], np.uint8)
+    O = oracle_ffi.lib()
+    O.o_rescue_new.restype = C.c_void_p
+    O.o_rescue_new.argtypes = [C.c_double]
+    O.o_rescue_local.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 5
+    O.o_rescue_global.argtypes = ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] +
+                                  [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_double), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_int)])
+    rs = O.o_rescue_new(0.5)
+    ranges, expect = [], []
+    for rec in cand[::6]:
+        w = int(rec[0])
+        sdir, qdir, flag = w >> 31, (w >> 30) & 1, (w >> 29) & 1
+        sid, sbeg, send, qid, qbeg, qend = (int(x) for x in rec[1:7])
+        if sdir:
+            qdir ^= 1
+            flag ^= 1
+            qbeg, qend = int(sizes[qid]) - qend, int(sizes[qid]) - qbeg
+            sbeg, send = int(sizes[sid]) - send, int(sizes[sid]) - sbeg
+        qoff, soff = (qbeg, sbeg) if flag else (qend, send)
+        q = codes[starts[qid]:starts[qid] + sizes[qid]]
+        if qdir:
+            q = comp[q[::-1]]
+        q = np.ascontiguousarray(q)
+        t = np.ascontiguousarray(codes[starts[sid]:starts[sid] + sizes[sid]])
+        out = [C.c_int() for _ in range(5)]
+        if not O.o_rescue_local(rs, q.ctypes.data_as(C.c_void_p), qoff, int(sizes[qid]), t.ctypes.data_as(C.c_void_p), soff, int(sizes[sid]),
+                                1000, *[C.byref(x) for x in out]):
+            continue
+        qb, qe, tb, te, diffs = (x.value for x in out)
+        o4 = [C.c_int() for _ in range(4)]
+        ident, qa, ta, ln = C.c_double(), C.c_char_p(), C.c_char_p(), C.c_int()
+        ok = O.o_rescue_global(rs, q.ctypes.data_as(C.c_void_p), qb, qe, t.ctypes.data_as(C.c_void_p), tb, te, diffs, 1000, 4,
+                               *[C.byref(x) for x in o4], C.byref(ident), C.byref(qa), C.byref(ta), C.byref(ln))
+        ranges.append(Range(qid, sid, qdir, qb, qe, tb, te, diffs))
+        expect.append((ok, [x.value for x in o4], oracle_ffi.strings_to_ops(qa.value, ta.value) if ok else None))
+    assert len(ranges) > 40 and sum(e[0] for e in expect) > 20
+    L = capi.lib()
+    ctx = capi.Context(0)
+    dvol = ctx.upload(vol)
+    arr = (Range * len(ranges))(*ranges)
+    aln, ops, nb = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    L.nb_rescue_global.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.nb_rescue_global(ctx.h, dvol, arr, len(ranges), 0.5, 1000, 4, C.byref(aln), C.byref(ops), C.byref(nb))
+    assert rc == 0, L.nb_last_error(ctx.h)
+    a = np.frombuffer((C.c_char * (capi.ALIGNMENT.itemsize * len(ranges))).from_address(aln.value), capi.ALIGNMENT).copy()
+    o = np.frombuffer((C.c_char * max(nb.value, 1)).from_address(ops.value), np.uint8).copy()
+    for i, (ok, ends, eops) in enumerate(expect):
+        assert int(a["ok"][i]) == ok, f"range {i}"
+        if ok:
+            assert [int(a[k][i]) for k in ("qoff", "qend", "toff", "tend")] == ends, f"range {i}"
+            got = o[int(a["ops_offset"][i]):int(a["ops_offset"][i]) + int(a["aln_size"][i])]
+            assert np.array_equal(got, eops), f"range {i}"
+    ctx.free_volume(dvol)
