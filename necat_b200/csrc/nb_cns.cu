@@ -30,7 +30,7 @@ struct HostTimer {
 };
 
 struct Can {
-    int qid, qdir, qoff, soff, sbeg, send, qsize, score, qbeg;
+    int qid, qdir, qoff, soff, sbeg, send, qsize, score, qbeg, qend;
     int res;            // index into the template chunk's result arrays, -1 = not extended yet
 };
 
@@ -420,6 +420,63 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             g.res.resize(r0 + tasks.size());
             NB_CUDA(wc, cudaMemcpyAsync(g.res.data() + r0, d_res, sizeof(nb_alignment) * tasks.size(), cudaMemcpyDeviceToHost, gst));
             NB_CUDA(wc, cudaStreamSynchronize(gst));
+            std::vector<const uint8_t*> rescued_ops(tasks.size(), (const uint8_t*)NULL);
+            if (o.rescue_long_indels) {
+                // EXPERIMENTAL (NB_ENABLE_RESCUE): the rescue branch of cns_extension, consensus_aux.c:150-201.  Candidates of this
+                // round whose block-wise extension failed, or left more than 200 bases of their chain unaligned, go through
+                // the O(nd) local alignment and, if that spans enough, the global alignment of its range; where both succeed
+                // the result replaces the block-wise one.
+                std::vector<nb_rescue_task> rt;
+                std::vector<size_t> rt_k;
+                for (size_t k = 0; k < tasks.size(); ++k) {
+                    const nb_alignment& a = g.res[r0 + k];
+                    const Can& c = cans[task_can[k]];
+                    bool fine = a.ok != 0;
+                    if (fine) {
+                        const int lhang = a.qoff > c.qbeg ? a.qoff - c.qbeg : 0, rhang = a.qend < c.qend ? c.qend - a.qend : 0;
+                        if (lhang + rhang > 200) fine = false;
+                    }
+                    if (fine) continue;
+                    nb_rescue_task t;
+                    t.qid = tasks[k].qid; t.sid = tasks[k].sid; t.qdir = tasks[k].qdir; t.qstart = tasks[k].qoff; t.tstart = tasks[k].soff; t.pad_ = 0;
+                    rt.push_back(t); rt_k.push_back(k);
+                }
+                if (!rt.empty()) {
+                    std::vector<nb_rescue_result> rr(rt.size());
+                    if ((rc = nb_rescue_local(wc, reads, rt.data(), rt.size(), o.error, o.min_align_size, rr.data()))) return rc;
+                    std::vector<nb_rescue_range> rg;
+                    std::vector<size_t> rg_k;
+                    for (size_t x = 0; x < rt.size(); ++x) {
+                        if (rr[x].overflow) return nb_fail(wc, NB_ELIMIT, "rescue: the wave band of a candidate exceeds its capacity");
+                        if (!rr[x].ok) continue;
+                        nb_rescue_range q;
+                        q.qid = rt[x].qid; q.sid = rt[x].sid; q.qdir = rt[x].qdir; q.qfrom = rr[x].qbeg; q.qto = rr[x].qend;
+                        q.tfrom = rr[x].tbeg; q.tto = rr[x].tend; q.tolerance = rr[x].diffs;
+                        rg.push_back(q); rg_k.push_back(rt_k[x]);
+                    }
+                    if (!rg.empty()) {
+                        nb_alignment* ga = NULL; uint8_t* gops = NULL; uint64_t gbytes = 0;
+                        if ((rc = nb_rescue_global(wc, reads, rg.data(), rg.size(), o.error, o.min_align_size, 4, &ga, &gops, &gbytes))) return rc;
+                        uint8_t* d_rops = NULL;
+                        if (gbytes) {
+                            if ((rc = g.D->get(&d_rops, gbytes))) { free(ga); free(gops); return rc; }
+                            const cudaError_t e1 = cudaMemcpyAsync(d_rops, gops, gbytes, cudaMemcpyHostToDevice, gst);
+                            const cudaError_t e2 = cudaStreamSynchronize(gst);
+                            if (e1 != cudaSuccess || e2 != cudaSuccess) { free(ga); free(gops); return nb_fail(wc, NB_ECUDA, "rescue: upload of the operations failed"); }
+                        }
+                        for (size_t x = 0; x < rg.size(); ++x) {
+                            if (!ga[x].ok) continue;
+                            nb_alignment a = ga[x];
+                            // a run of >= 255 query-only columns drops the alignment from the tags (align_tags.c:40-44)
+                            int run = 0; a.long_ins = 0;
+                            for (int y = 0; y < a.aln_size; ++y) { run = gops[a.ops_offset + (uint64_t)y] == 1 ? run + 1 : 0; if (run >= 255) { a.long_ins = 1; break; } }
+                            rescued_ops[rg_k[x]] = d_rops + a.ops_offset;
+                            g.res[r0 + rg_k[x]] = a;
+                        }
+                        free(ga); free(gops);
+                    }
+                }
+            }
             gpu.unlock();
             float ms = 0; cudaEventElapsedTime(&ms, wc->ev0, wc->ev1); g.tm.ext_ms += ms;
             wc->tm.h2d_bytes += sizeof(ExtTask) * tasks.size();
@@ -427,7 +484,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             g.res_ops.resize(g.res.size());
             for (size_t k = 0; k < tasks.size(); ++k) {
                 cans[task_can[k]].res = (int)(r0 + k);
-                g.res_ops[r0 + k] = d_ops + g.res[r0 + k].ops_offset;
+                g.res_ops[r0 + k] = rescued_ops[k] ? rescued_ops[k] : d_ops + g.res[r0 + k].ops_offset;
             }
             g.tm.ext += gt.lap();
             if (round > 64) return nb_fail(wc, NB_ECUDA, "extension rounds do not converge");
@@ -815,8 +872,9 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     if (!ctx || !reads || (!cans_in && n_in) || !opt || !out_recs || !n_recs || !out_seq || !out_seq_bytes)
         return nb_fail(ctx, NB_EINVAL, "nb_consensus_job: bad arguments");
     *out_recs = NULL; *n_recs = 0; *out_seq = NULL; *out_seq_bytes = 0;
-    if (opt->rescue_long_indels)
-        return nb_fail(ctx, NB_EINVAL, "-r 1 (DALIGNER rescue, oc_daligner.c) is not implemented in the B200 build");
+    if (opt->rescue_long_indels && !getenv("NB_ENABLE_RESCUE"))
+        return nb_fail(ctx, NB_EINVAL, "-r 1 (DALIGNER rescue, oc_daligner.c) is not enabled in the B200 build: its kernels exist but the second "
+                                       "half has not run on a GPU yet (DESIGN.md); NB_ENABLE_RESCUE=1 switches the experimental path on");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->cc, 0, sizeof ctx->cc);
     ctx->tm.extend_ms = 0; ctx->tm.consensus_ms = 0;
@@ -899,7 +957,7 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
                     Can c;
                     const uint32_t w = p.item[0];
                     c.qid = (int)p.item[4]; c.qdir = (int)((w >> 30) & 1); c.score = (int)(w & ((1u << 29) - 1));
-                    c.sbeg = (int)p.item[2]; c.send = (int)p.item[3]; c.qbeg = (int)p.item[5];
+                    c.sbeg = (int)p.item[2]; c.send = (int)p.item[3]; c.qbeg = (int)p.item[5]; c.qend = (int)p.item[6];
                     if (w & (1u << 29)) { c.qoff = (int)p.item[5]; c.soff = (int)p.item[2]; }
                     else                { c.qoff = (int)p.item[6]; c.soff = (int)p.item[3]; }
                     c.qsize = (int)reads->h_len[c.qid];
