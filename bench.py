@@ -353,7 +353,7 @@ def main():
                 "h2d_bytes_per_step": int((tm1.h2d_bytes - tm0.h2d_bytes) // max(args.steps, 1)),
                 "d2h_bytes_per_step": int((tm1.d2h_bytes - tm0.d2h_bytes) // max(args.steps, 1))},
         "roofline": {"kernel": "k_extend", "bound": "hbm", "achieved": ext_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": ext_gbs / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "frac": ext_gbs / peak, "frac_of_nominal_8TBs": ext_gbs / 8000.0, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "launch": {"what": "largest k_extend launch (round 0, one template group)", "ms": cc["big_ext_usec"] / 1e3,
                                 "tasks": cc["big_ext_tasks"], "block_alignments": cc["big_ext_block_aligns"],
                                 "word_updates": cc["big_ext_word_updates"], "algorithmic_bytes": ext_bytes},
