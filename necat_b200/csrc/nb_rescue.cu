@@ -125,9 +125,6 @@ extern "C" int nb_rescue_local(nb_ctx* ctx, const nb_volume* reads, const nb_res
 // on a GPU yet (tests/test_gpu_rescue.py::test_rescue_global is skipped unless NB_TEST_UNVERIFIED=1).
 #include "nb_rescue_driver.h"
 
-struct RgColJobDev  { RsSeq Q, T; int q0, qn, qstep, t0, tn, tstep; unsigned long long col_off, h_off; };
-struct RgLeafJobDev { RsSeq Q, T; int q0, qn, t0, tn, cap, pad_; unsigned long long mat_off, h_off, ops_off; };
-
 __global__ void __launch_bounds__(RS_WARPS * 32)
 k_rescue_columns(const RgColJobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t* next_job, int* cols, int8_t* hbuf)
 {
@@ -163,90 +160,48 @@ k_rescue_leaves(const RgLeafJobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t
 
 namespace {
 
-struct GpuRescueBackend {
+// what actually runs a slice of pooled jobs on the GPU; the pooling itself (RgPooledBackend, nb_rescue_driver.h) is shared
+// with the host emulation
+struct GpuRescueExec {
     nb_ctx* ctx;
     int rc = NB_OK;
 
-    // launches in slices so that the scratch of one launch stays below ~2 GiB
-    void columns(const std::vector<RgTask>& tasks, const std::vector<RgColJob>& jobs, std::vector<std::vector<int>>& cols)
+    bool run_columns(const std::vector<RgColJobDev>& dj, unsigned long long col_total, unsigned long long h_total, std::vector<int>& h_cols)
     {
-        cols.assign(jobs.size(), std::vector<int>());
         cudaStream_t st = ctx->stream;
-        size_t a = 0;
-        while (a < jobs.size() && rc == NB_OK) {
-            std::vector<RgColJobDev> dj;
-            unsigned long long col_total = 0, h_total = 0;
-            size_t b = a;
-            while (b < jobs.size() && (b == a || (col_total + h_total) < (1ull << 29))) {
-                const RgColJob& j = jobs[b];
-                const RgTask& t = tasks[(size_t)j.task];
-                RgColJobDev d;
-                d.Q = t.Q; d.T = t.T; d.q0 = j.q0; d.qn = j.qn; d.qstep = j.qstep; d.t0 = j.t0; d.tn = j.tn; d.tstep = j.tstep;
-                d.col_off = col_total; d.h_off = h_total;
-                col_total += (unsigned long long)j.qn + 1;
-                h_total += 2ull * ((unsigned long long)j.tn + 1);
-                dj.push_back(d);
-                ++b;
-            }
-            NbDevBuf D(ctx);
-            RgColJobDev* d_jobs; int* d_cols; int8_t* d_h; uint32_t* d_next;
-            if ((rc = D.get(&d_jobs, dj.size())) || (rc = D.get(&d_cols, col_total)) || (rc = D.get(&d_h, h_total + 16)) || (rc = D.get(&d_next, 1))) return;
-            std::vector<int> h_cols((size_t)col_total);
-            cudaMemcpyAsync(d_jobs, dj.data(), sizeof(RgColJobDev) * dj.size(), cudaMemcpyHostToDevice, st);
-            cudaMemsetAsync(d_next, 0, sizeof(uint32_t), st);
-            k_rescue_columns<<<NB_SMS * 4, RS_WARPS * 32, 0, st>>>(d_jobs, (uint32_t)dj.size(), d_next, d_cols, d_h);
-            ctx->launches++;
-            cudaMemcpyAsync(h_cols.data(), d_cols, sizeof(int) * (size_t)col_total, cudaMemcpyDeviceToHost, st);
-            const cudaError_t e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { rc = nb_fail(ctx, NB_ECUDA, "k_rescue_columns -> %s", cudaGetErrorString(e)); return; }
-            for (size_t x = a; x < b; ++x)
-                cols[x].assign(h_cols.begin() + (long)dj[x - a].col_off, h_cols.begin() + (long)dj[x - a].col_off + jobs[x].qn + 1);
-            a = b;
-        }
+        NbDevBuf D(ctx);
+        RgColJobDev* d_jobs; int* d_cols; int8_t* d_h; uint32_t* d_next;
+        if ((rc = D.get(&d_jobs, dj.size())) || (rc = D.get(&d_cols, col_total)) || (rc = D.get(&d_h, h_total + 16)) || (rc = D.get(&d_next, 1))) return false;
+        h_cols.resize((size_t)col_total);
+        cudaMemcpyAsync(d_jobs, dj.data(), sizeof(RgColJobDev) * dj.size(), cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(d_next, 0, sizeof(uint32_t), st);
+        k_rescue_columns<<<NB_SMS * 4, RS_WARPS * 32, 0, st>>>(d_jobs, (uint32_t)dj.size(), d_next, d_cols, d_h);
+        ctx->launches++;
+        cudaMemcpyAsync(h_cols.data(), d_cols, sizeof(int) * (size_t)col_total, cudaMemcpyDeviceToHost, st);
+        const cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = nb_fail(ctx, NB_ECUDA, "k_rescue_columns -> %s", cudaGetErrorString(e)); return false; }
+        return true;
     }
 
-    void leaves(const std::vector<RgTask>& tasks, const std::vector<RgLeafJob>& jobs, std::vector<std::vector<uint8_t>>& ops)
+    bool run_leaves(const std::vector<RgLeafJobDev>& dj, unsigned long long mat_total, unsigned long long h_total, unsigned long long ops_total,
+                    std::vector<uint8_t>& h_ops, std::vector<int>& h_n)
     {
-        ops.assign(jobs.size(), std::vector<uint8_t>());
         cudaStream_t st = ctx->stream;
-        size_t a = 0;
-        while (a < jobs.size() && rc == NB_OK) {
-            std::vector<RgLeafJobDev> dj;
-            unsigned long long mat_total = 0, h_total = 0, ops_total = 0;
-            size_t b = a;
-            while (b < jobs.size() && (b == a || mat_total * sizeof(RsWord2) < (1ull << 31))) {
-                const RgLeafJob& j = jobs[b];
-                const RgTask& t = tasks[(size_t)j.task];
-                RgLeafJobDev d;
-                d.Q = t.Q; d.T = t.T; d.q0 = j.q0; d.qn = j.qn; d.t0 = j.t0; d.tn = j.tn; d.cap = j.qn + j.tn; d.pad_ = 0;
-                d.mat_off = mat_total; d.h_off = h_total; d.ops_off = ops_total;
-                mat_total += (unsigned long long)((j.qn + 31) / 32) * (unsigned long long)j.tn;
-                h_total += 2ull * ((unsigned long long)j.tn + 1);
-                ops_total += (unsigned long long)d.cap;
-                dj.push_back(d);
-                ++b;
-            }
-            NbDevBuf D(ctx);
-            RgLeafJobDev* d_jobs; RsWord2* d_mat; int8_t* d_h; uint8_t* d_ops; int* d_n; uint32_t* d_next;
-            if ((rc = D.get(&d_jobs, dj.size())) || (rc = D.get(&d_mat, mat_total + 1)) || (rc = D.get(&d_h, h_total + 16)) ||
-                (rc = D.get(&d_ops, ops_total + 16)) || (rc = D.get(&d_n, dj.size())) || (rc = D.get(&d_next, 1))) return;
-            std::vector<uint8_t> h_ops((size_t)ops_total);
-            std::vector<int> h_n(dj.size());
-            cudaMemcpyAsync(d_jobs, dj.data(), sizeof(RgLeafJobDev) * dj.size(), cudaMemcpyHostToDevice, st);
-            cudaMemsetAsync(d_next, 0, sizeof(uint32_t), st);
-            k_rescue_leaves<<<NB_SMS * 4, RS_WARPS * 32, 0, st>>>(d_jobs, (uint32_t)dj.size(), d_next, d_mat, d_h, d_ops, d_n);
-            ctx->launches++;
-            cudaMemcpyAsync(h_ops.data(), d_ops, (size_t)ops_total, cudaMemcpyDeviceToHost, st);
-            cudaMemcpyAsync(h_n.data(), d_n, sizeof(int) * dj.size(), cudaMemcpyDeviceToHost, st);
-            const cudaError_t e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { rc = nb_fail(ctx, NB_ECUDA, "k_rescue_leaves -> %s", cudaGetErrorString(e)); return; }
-            for (size_t x = a; x < b; ++x) {
-                const RgLeafJobDev& d = dj[x - a];
-                const int n = h_n[x - a];
-                ops[x].assign(h_ops.begin() + (long)(d.ops_off + (unsigned long long)(d.cap - n)), h_ops.begin() + (long)(d.ops_off + (unsigned long long)d.cap));
-            }
-            a = b;
-        }
+        NbDevBuf D(ctx);
+        RgLeafJobDev* d_jobs; RsWord2* d_mat; int8_t* d_h; uint8_t* d_ops; int* d_n; uint32_t* d_next;
+        if ((rc = D.get(&d_jobs, dj.size())) || (rc = D.get(&d_mat, mat_total + 1)) || (rc = D.get(&d_h, h_total + 16)) ||
+            (rc = D.get(&d_ops, ops_total + 16)) || (rc = D.get(&d_n, dj.size())) || (rc = D.get(&d_next, 1))) return false;
+        h_ops.resize((size_t)ops_total);
+        h_n.resize(dj.size());
+        cudaMemcpyAsync(d_jobs, dj.data(), sizeof(RgLeafJobDev) * dj.size(), cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(d_next, 0, sizeof(uint32_t), st);
+        k_rescue_leaves<<<NB_SMS * 4, RS_WARPS * 32, 0, st>>>(d_jobs, (uint32_t)dj.size(), d_next, d_mat, d_h, d_ops, d_n);
+        ctx->launches++;
+        cudaMemcpyAsync(h_ops.data(), d_ops, (size_t)ops_total, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(h_n.data(), d_n, sizeof(int) * dj.size(), cudaMemcpyDeviceToHost, st);
+        const cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = nb_fail(ctx, NB_ECUDA, "k_rescue_leaves -> %s", cudaGetErrorString(e)); return false; }
+        return true;
     }
 };
 
@@ -270,11 +225,12 @@ extern "C" int nb_rescue_global(nb_ctx* ctx, const nb_volume* reads, const nb_re
         t.T.pac = reads->d_pac; t.T.off = reads->h_off[r.sid]; t.T.len = (int)reads->h_len[r.sid]; t.T.strand = 0;
         t.qfrom = r.qfrom; t.qto = r.qto; t.tfrom = r.tfrom; t.tto = r.tto; t.tolerance = r.tolerance;
     }
-    GpuRescueBackend be;
-    be.ctx = ctx;
+    GpuRescueExec ex;
+    ex.ctx = ctx;
+    RgPooledBackend<GpuRescueExec> be(ex);
     std::vector<RgResult> res;
     rg_run(be, tasks, error, min_align_size, k_match, res);
-    if (be.rc) return be.rc;
+    if (ex.rc) return ex.rc;
     uint64_t total = 0;
     for (const RgResult& r : res) total += r.ops.size();
     nb_alignment* aln = (nb_alignment*)calloc((size_t)n, sizeof(nb_alignment));

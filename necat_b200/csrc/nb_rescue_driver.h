@@ -29,6 +29,80 @@ struct RgResult {
 struct RgColJob  { int task, q0, qn, qstep, t0, tn, tstep; };       // q(i) = Q.at(q0 + i * qstep), likewise t
 struct RgLeafJob { int task, q0, qn, t0, tn; };
 
+// A slice of jobs laid out in pools (what the kernels k_rescue_columns / k_rescue_leaves consume): per job the offsets of
+// its column scores, its two generations of bottom-row deltas, its bit-vector matrix and its operations.
+struct RgColJobDev  { RsSeq Q, T; int q0, qn, qstep, t0, tn, tstep; unsigned long long col_off, h_off; };
+struct RgLeafJobDev { RsSeq Q, T; int q0, qn, t0, tn, cap, pad_; unsigned long long mat_off, h_off, ops_off; };
+
+// Backend of rg_run over an executor that runs one pooled slice: Exec::run_columns(jobs, col_total, h_total, h_cols) and
+// Exec::run_leaves(jobs, mat_total, h_total, ops_total, h_ops, h_n) (false = failed).  Slices keep the scratch of one
+// launch bounded.  The executor is the GPU (nb_rescue.cu) or the host emulation (tests/emu).
+template <class Exec>
+struct RgPooledBackend {
+    Exec& ex;
+    bool failed = false;
+    explicit RgPooledBackend(Exec& e) : ex(e) {}
+
+    void columns(const std::vector<RgTask>& tasks, const std::vector<RgColJob>& jobs, std::vector<std::vector<int>>& cols)
+    {
+        cols.assign(jobs.size(), std::vector<int>());
+        size_t a = 0;
+        while (a < jobs.size()) {
+            std::vector<RgColJobDev> dj;
+            unsigned long long col_total = 0, h_total = 0;
+            size_t b = a;
+            while (b < jobs.size() && (b == a || (col_total + h_total) < (1ull << 29))) {
+                const RgColJob& j = jobs[b];
+                const RgTask& t = tasks[(size_t)j.task];
+                RgColJobDev d;
+                d.Q = t.Q; d.T = t.T; d.q0 = j.q0; d.qn = j.qn; d.qstep = j.qstep; d.t0 = j.t0; d.tn = j.tn; d.tstep = j.tstep;
+                d.col_off = col_total; d.h_off = h_total;
+                col_total += (unsigned long long)j.qn + 1;
+                h_total += 2ull * ((unsigned long long)j.tn + 1);
+                dj.push_back(d);
+                ++b;
+            }
+            std::vector<int> h_cols;
+            if (failed || !ex.run_columns(dj, col_total, h_total, h_cols)) { failed = true; h_cols.assign((size_t)col_total, 0); }
+            for (size_t x = a; x < b; ++x)
+                cols[x].assign(h_cols.begin() + (long)dj[x - a].col_off, h_cols.begin() + (long)dj[x - a].col_off + jobs[x].qn + 1);
+            a = b;
+        }
+    }
+
+    void leaves(const std::vector<RgTask>& tasks, const std::vector<RgLeafJob>& jobs, std::vector<std::vector<uint8_t>>& ops)
+    {
+        ops.assign(jobs.size(), std::vector<uint8_t>());
+        size_t a = 0;
+        while (a < jobs.size()) {
+            std::vector<RgLeafJobDev> dj;
+            unsigned long long mat_total = 0, h_total = 0, ops_total = 0;
+            size_t b = a;
+            while (b < jobs.size() && (b == a || mat_total * sizeof(RsWord2) < (1ull << 31))) {
+                const RgLeafJob& j = jobs[b];
+                const RgTask& t = tasks[(size_t)j.task];
+                RgLeafJobDev d;
+                d.Q = t.Q; d.T = t.T; d.q0 = j.q0; d.qn = j.qn; d.t0 = j.t0; d.tn = j.tn; d.cap = j.qn + j.tn; d.pad_ = 0;
+                d.mat_off = mat_total; d.h_off = h_total; d.ops_off = ops_total;
+                mat_total += (unsigned long long)((j.qn + 31) / 32) * (unsigned long long)j.tn;
+                h_total += 2ull * ((unsigned long long)j.tn + 1);
+                ops_total += (unsigned long long)d.cap;
+                dj.push_back(d);
+                ++b;
+            }
+            std::vector<uint8_t> h_ops;
+            std::vector<int> h_n;
+            if (failed || !ex.run_leaves(dj, mat_total, h_total, ops_total, h_ops, h_n)) { failed = true; h_ops.assign((size_t)ops_total, 0); h_n.assign(dj.size(), 0); }
+            for (size_t x = a; x < b; ++x) {
+                const RgLeafJobDev& d = dj[x - a];
+                const int n = h_n[x - a];
+                ops[x].assign(h_ops.begin() + (long)(d.ops_off + (unsigned long long)(d.cap - n)), h_ops.begin() + (long)(d.ops_off + (unsigned long long)d.cap));
+            }
+            a = b;
+        }
+    }
+};
+
 // edlib.cpp:1139-1141: bytes of alignment data the traceback would need; below 1 MiB it is used, else Hirschberg
 static inline long long rg_traceback_bytes(int qn, int tn)
 {

@@ -192,42 +192,43 @@ int main(int argc, char** argv)
     printf("emu_rescue: leaves %d, %d mismatches\n", n_leaf, n_leaf_bad);
     // ---- the whole global alignment (host-driven Hirschberg of nb_rescue_driver.h over the emulated cores) against
     //      the oracle's o_rescue_global, on the ranges the local alignment finds
-    struct EmuBackend {
-        void columns(const std::vector<RgTask>& tasks, const std::vector<RgColJob>& jobs, std::vector<std::vector<int>>& cols)
+    // the executor the kernels k_rescue_columns / k_rescue_leaves are on the GPU: same pooled jobs, same per-job calls
+    struct EmuExec {
+        bool run_columns(const std::vector<RgColJobDev>& dj, unsigned long long col_total, unsigned long long h_total, std::vector<int>& h_cols)
         {
-            cols.assign(jobs.size(), std::vector<int>());
-            for (size_t x = 0; x < jobs.size(); ++x) {
-                const RgColJob& j = jobs[x];
-                const RgTask& t = tasks[(size_t)j.task];
-                cols[x].assign((size_t)j.qn + 1, 0);
-                std::vector<int8_t> h0((size_t)j.tn + 1), h1((size_t)j.tn + 1);
+            h_cols.assign((size_t)col_total, -1);
+            std::vector<int8_t> hbuf((size_t)h_total + 16);
+            for (const RgColJobDev& J : dj) {
                 EmuShared sh;
                 std::vector<std::thread> th;
                 for (int l = 0; l < 32; ++l)
-                    th.emplace_back([&, l]() { EmuWarp w{l, &sh}; rs_nw_column(w, t.Q, j.q0, j.qn, j.qstep, t.T, j.t0, j.tn, j.tstep, cols[x].data(), h0.data(), h1.data()); });
+                    th.emplace_back([&, l]() { EmuWarp w{l, &sh}; rs_nw_column(w, J.Q, J.q0, J.qn, J.qstep, J.T, J.t0, J.tn, J.tstep, h_cols.data() + J.col_off, hbuf.data() + J.h_off, hbuf.data() + J.h_off + J.tn + 1); });
                 for (auto& q : th) q.join();
             }
+            return true;
         }
-        void leaves(const std::vector<RgTask>& tasks, const std::vector<RgLeafJob>& jobs, std::vector<std::vector<uint8_t>>& ops)
+        bool run_leaves(const std::vector<RgLeafJobDev>& dj, unsigned long long mat_total, unsigned long long h_total, unsigned long long ops_total,
+                        std::vector<uint8_t>& h_ops, std::vector<int>& h_n)
         {
-            ops.assign(jobs.size(), std::vector<uint8_t>());
-            for (size_t x = 0; x < jobs.size(); ++x) {
-                const RgLeafJob& j = jobs[x];
-                const RgTask& t = tasks[(size_t)j.task];
-                const int cap = j.qn + j.tn;
-                std::vector<uint8_t> buf((size_t)cap);
-                std::vector<RsWord2> mat((size_t)((j.qn + 31) / 32) * (size_t)j.tn);
-                std::vector<int8_t> h0((size_t)j.tn + 1), h1((size_t)j.tn + 1);
+            h_ops.assign((size_t)ops_total, 9);
+            h_n.assign(dj.size(), 0);
+            std::vector<RsWord2> mat((size_t)mat_total + 1);
+            std::vector<int8_t> hbuf((size_t)h_total + 16);
+            for (size_t x = 0; x < dj.size(); ++x) {
+                const RgLeafJobDev& J = dj[x];
                 int nops[32];
                 EmuShared sh;
                 std::vector<std::thread> th;
                 for (int l = 0; l < 32; ++l)
-                    th.emplace_back([&, l]() { EmuWarp w{l, &sh}; nops[l] = rs_nw_leaf(w, t.Q, j.q0, j.qn, t.T, j.t0, j.tn, mat.data(), h0.data(), h1.data(), buf.data(), cap); });
+                    th.emplace_back([&, l]() { EmuWarp w{l, &sh}; nops[l] = rs_nw_leaf(w, J.Q, J.q0, J.qn, J.T, J.t0, J.tn, mat.data() + J.mat_off, hbuf.data() + J.h_off, hbuf.data() + J.h_off + J.tn + 1, h_ops.data() + J.ops_off, J.cap); });
                 for (auto& q : th) q.join();
-                ops[x].assign(buf.begin() + (cap - nops[0]), buf.end());
+                h_n[x] = nops[0];
             }
+            return true;
         }
-    } be;
+    } ex;
+    RgPooledBackend<EmuExec> be(ex);
+
     int n_glob = 0, n_glob_bad = 0, n_glob_ok = 0;
     const int max_glob = argc > 5 ? atoi(argv[5]) : 0;
     for (size_t ci = 0; ci < pc.size() && n_glob < max_glob; ++ci) {
