@@ -52,3 +52,33 @@ def test_rescue_matches_reference(built, tmp_path):
         assert util.fasta_canon(str(tmp_path / "o_cns.fa")) == out[rescue], f"-r {rescue}"
         assert util.fasta_canon(str(tmp_path / "o_raw.fa")) == util.fasta_canon(str(tmp_path / "r_raw.fa"))
     assert len(out["1"]) > 20 and out["0"] != out["1"], "the set must exercise the rescue"
+
+
+@needs_ref
+@pytest.mark.parametrize("gen", [
+    # ragged: most reads below the length cut-offs (-a 1000, -m 500, -l 500), many with no candidate at all
+    dict(genome=30_000, depth=12, seed=54, err=0.10, min_len=60, max_len=4000, mean_log=6.6, sd_log=0.8),
+    # starved: coverage below -x 3 almost everywhere, so nearly nothing is corrected and templates fall through to raw
+    dict(genome=60_000, depth=2, seed=55, err=0.10),
+])
+def test_edge_sets_match_reference(built, tmp_path, gen):
+    """Ragged and starved inputs, and an EMPTY candidate file: oracle == reference binaries, no crashes either side."""
+    import shutil
+    wrk, reads = util.make_workdir(tmp_path, **gen)
+    r = util.run_pmov(util.ref_bin("oc2pmov"), PM13, wrk, 0, str(tmp_path / "r.bin"))
+    o = util.run_pmov(util.ORACLE_CLI, PM13, wrk, 0, str(tmp_path / "o.bin"))
+    assert util.same_multiset(r, o)
+    cns = "-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0 -r 0 -f 0"
+    for name, src in (("full", str(tmp_path / "r.bin")), ("empty", None)):
+        plain = str(tmp_path / f"{name}.bin")
+        if src:
+            shutil.copy(src, plain)
+        else:
+            open(plain, "wb").close()
+        c = str(tmp_path / f"{name}_part.bin")
+        shutil.copy(plain, c)
+        util.run([util.ref_bin("oc2pcan"), "-t", "1", wrk, c])
+        util.run([util.ref_bin("oc2cns")] + cns.split() + ["-t", "2", wrk, c, str(tmp_path / "r_cns.fa"), str(tmp_path / "r_raw.fa")])
+        util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", "1", wrk, plain, str(tmp_path / "o_cns.fa"), str(tmp_path / "o_raw.fa")])
+        assert util.fasta_canon(str(tmp_path / "o_cns.fa")) == util.fasta_canon(str(tmp_path / "r_cns.fa")), name
+        assert util.fasta_canon(str(tmp_path / "o_raw.fa")) == util.fasta_canon(str(tmp_path / "r_raw.fa")), name
