@@ -422,7 +422,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             NB_CUDA(wc, cudaStreamSynchronize(gst));
             std::vector<const uint8_t*> rescued_ops(tasks.size(), (const uint8_t*)NULL);
             if (o.rescue_long_indels) {
-                // EXPERIMENTAL (NB_ENABLE_RESCUE): the rescue branch of cns_extension, consensus_aux.c:150-201.  Candidates of this
+                // -r 1: the rescue branch of cns_extension, consensus_aux.c:150-201.  Candidates of this
                 // round whose block-wise extension failed, or left more than 200 bases of their chain unaligned, go through
                 // the O(nd) local alignment and, if that spans enough, the global alignment of its range; where both succeed
                 // the result replaces the block-wise one.
@@ -872,9 +872,6 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     if (!ctx || !reads || (!cans_in && n_in) || !opt || !out_recs || !n_recs || !out_seq || !out_seq_bytes)
         return nb_fail(ctx, NB_EINVAL, "nb_consensus_job: bad arguments");
     *out_recs = NULL; *n_recs = 0; *out_seq = NULL; *out_seq_bytes = 0;
-    if (opt->rescue_long_indels && !getenv("NB_ENABLE_RESCUE"))
-        return nb_fail(ctx, NB_EINVAL, "-r 1 (DALIGNER rescue, oc_daligner.c) is not enabled in the B200 build: its kernels exist but the second "
-                                       "half has not run on a GPU yet (DESIGN.md); NB_ENABLE_RESCUE=1 switches the experimental path on");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->cc, 0, sizeof ctx->cc);
     ctx->tm.extend_ms = 0; ctx->tm.consensus_ms = 0;

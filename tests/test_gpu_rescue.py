@@ -1,5 +1,6 @@
-"""GPU parity of the first half of the oc2cns -r 1 rescue: nb_rescue_local (k_rescue_local: Myers' O(nd) local alignment,
-gapped_align/oc_daligner.c:34-79) against the oracle's o_rescue_local on every candidate of the long-indel golden set."""
+"""GPU parity of the oc2cns -r 1 rescue: nb_rescue_local (k_rescue_local: Myers' O(nd) local alignment,
+gapped_align/oc_daligner.c:34-79) and nb_rescue_global (edlib_go, edlib/edlib_wrapper.c:111-255) against the oracle on the
+long-indel golden set, and oc2cns -r 1 end to end against the reference binary's FASTA."""
 import ctypes as C
 import os
 
@@ -79,9 +80,6 @@ class Range(C.Structure):
     _fields_ = [("qid", C.c_uint32), ("sid", C.c_uint32)] + [(n, C.c_int32) for n in ("qdir", "qfrom", "qto", "tfrom", "tto", "tolerance")]
 
 
-@pytest.mark.skipif(os.environ.get("NB_TEST_UNVERIFIED") != "1",
-                    reason="nb_rescue_global's GPU shells were written after round 1's GPU budget ran out; its cores and "
-                           "recursion are verified by host emulation (tests/test_emu_rescue.py).  Set NB_TEST_UNVERIFIED=1 to run.")
 def test_rescue_global_matches_oracle(built, tmp_path):
     """edlib_go on the GPU (nb_rescue_global) against the oracle's o_rescue_global on the ranges the local alignment finds."""
     from necat_b200 import capi, formats
@@ -148,11 +146,8 @@ def test_rescue_global_matches_oracle(built, tmp_path):
     ctx.free_volume(dvol)
 
 
-@pytest.mark.skipif(os.environ.get("NB_TEST_UNVERIFIED") != "1",
-                    reason="oc2cns -r 1 end to end is wired (NB_ENABLE_RESCUE=1) but its second half has not run on a GPU yet; "
-                           "set NB_TEST_UNVERIFIED=1 to run")
 def test_oc2cns_rescue_matches_golden(built, tmp_path):
-    """oc2cns -r 1 on the long-indel golden set: the experimental GPU path against the reference's FASTA."""
+    """oc2cns -r 1 on the long-indel golden set: FASTA identical to the reference binary's."""
     import json
     import shutil
     man = json.load(open(os.path.join(util.GOLDEN, "manifest.json")))["r1"]
@@ -161,7 +156,6 @@ def test_oc2cns_rescue_matches_golden(built, tmp_path):
     shutil.copy(os.path.join(util.GOLDEN, "r1", "cand_k13.bin"), c)
     util.run([os.path.join(util.BIN_DIR, "oc2pcan"), "-t", "1", wrk, c], cwd=str(tmp_path))
     opts = man["cns_r1"]["options"].split()
-    util.run([os.path.join(util.BIN_DIR, "oc2cns")] + opts + [wrk, c, "cns.fa", "raw.fa"], cwd=str(tmp_path),
-             env=dict(os.environ, NB_ENABLE_RESCUE="1"))
+    util.run([os.path.join(util.BIN_DIR, "oc2cns")] + opts + [wrk, c, "cns.fa", "raw.fa"], cwd=str(tmp_path))
     assert util.fasta_canon(str(tmp_path / "cns.fa")) == util.golden_fasta("r1/cns_r1")
     assert util.fasta_canon(str(tmp_path / "raw.fa")) == util.golden_fasta("r1/raw_r1")
