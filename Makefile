@@ -12,7 +12,7 @@ HOSTC := necat_b200/host/nb_host.c
 CC    := gcc
 CFLAGS := -O2 -g -std=gnu99 -Wall
 
-all: $(LIBD)/libnecat_b200.so $(BIND)/oc2pmov $(BIND)/oc2cns $(BIND)/oc2pcan
+all: $(LIBD)/libnecat_b200.so $(BIND)/oc2pmov $(BIND)/oc2cns $(BIND)/oc2pcan $(BIND)/oc2mkdb $(BIND)/oc2ReorderCnsReads
 
 $(OBJD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/necat_b200.h
 	@mkdir -p $(OBJD)
@@ -21,6 +21,12 @@ $(OBJD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/necat_b200.h
 $(LIBD)/libnecat_b200.so: $(OBJ)
 	@mkdir -p $(LIBD)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
+
+# ingest / reorder hosts: plain C + zlib, no CUDA library (they run where there is no GPU)
+FASTX := necat_b200/host/nb_fastx.c
+$(BIND)/oc2mkdb $(BIND)/oc2ReorderCnsReads: $(BIND)/%: necat_b200/host/%.c $(HOSTC) $(FASTX) necat_b200/host/nb_host.h necat_b200/host/nb_fastx.h
+	@mkdir -p $(BIND)
+	$(CC) $(CFLAGS) -O3 -o $@ $< $(HOSTC) $(FASTX) -lz -lpthread
 
 $(BIND)/%: necat_b200/host/%.c $(HOSTC) necat_b200/host/nb_host.h $(LIBD)/libnecat_b200.so
 	@mkdir -p $(BIND)

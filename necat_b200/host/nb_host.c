@@ -151,3 +151,22 @@ void nbh_volumes_info_free(nbh_volumes_info* vi)
     free(vi->names); free(vi->start_id); free(vi->count);
     memset(vi, 0, sizeof *vi);
 }
+
+int nbh_order_by_id(const nb_cns_record* recs, uint64_t n, uint64_t* order)
+{
+    uint64_t* tmp = (uint64_t*)malloc(8 * (n ? n : 1));
+    if (!tmp) return -1;
+    for (uint64_t i = 0; i < n; ++i) order[i] = i;
+    uint64_t *a = order, *b = tmp;
+    for (int pass = 0; pass < 4; ++pass) {                      /* stable LSD radix sort, 8 bits a pass; ids are >= 0 */
+        uint64_t cnt[257];
+        memset(cnt, 0, sizeof cnt);
+        const int sh = pass * 8;
+        for (uint64_t i = 0; i < n; ++i) cnt[(((uint32_t)recs[a[i]].id >> sh) & 255u) + 1]++;
+        for (int k = 0; k < 256; ++k) cnt[k + 1] += cnt[k];
+        for (uint64_t i = 0; i < n; ++i) b[cnt[((uint32_t)recs[a[i]].id >> sh) & 255u]++] = a[i];
+        uint64_t* t = a; a = b; b = t;
+    }
+    free(tmp);                                                  /* an even number of passes: the result is in `order` */
+    return 0;
+}

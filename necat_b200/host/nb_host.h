@@ -32,6 +32,11 @@ typedef struct {
 int  nbh_volumes_info_load(const char* wrk_dir, nbh_volumes_info* vi);
 void nbh_volumes_info_free(nbh_volumes_info* vi);
 
+/* order[0..n) = indices of recs in ascending read id, records of one id in their given order (stable).  oc2cns writes its
+ * FASTA in this order so that the reorder step after it (reorder_cns_reads/main.c, necat.pl:351) finds sorted input.
+ * Returns -1 when out of memory. */
+int  nbh_order_by_id(const nb_cns_record* recs, uint64_t n, uint64_t* order);
+
 /* "[time] LEVEL: msg (file, line)" banners of common/ontcns_aux.c:29-46 */
 void nbh_log(const char* level, const char* file, int line, const char* fmt, ...);
 #define NBH_LOG(...)   nbh_log("INFO", __FILE__, __LINE__, __VA_ARGS__)

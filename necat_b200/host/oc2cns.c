@@ -130,8 +130,10 @@ int main(int argc, char* argv[])
             if (nb_consensus_job(ctx, dreads, cans, n, &o, &recs, &nrec, &seq, &nseq)) NBH_ERROR("%s", nb_last_error(ctx));
             NBH_PHASE("consensus job");
             char hdr[4096];
-            for (uint64_t i = 0; i < nrec; ++i) {
-                const nb_cns_record* r = &recs[i];
+            uint64_t* order = (uint64_t*)malloc(8 * (nrec ? nrec : 1));
+            if (!order || nbh_order_by_id(recs, nrec, order)) NBH_ERROR("out of memory");
+            for (uint64_t k = 0; k < nrec; ++k) {               /* in read id order */
+                const nb_cns_record* r = &recs[order[k]];
                 FILE* out = r->is_raw ? raw_out : cns_out;
                 const char* name = reads.hdr + reads.hdr_offset[r->id];
                 const size_t hl = format_header(hdr, sizeof hdr, name, r);
@@ -139,6 +141,7 @@ int main(int argc, char* argv[])
                 fwrite(seq + r->seq_offset, 1, (size_t)r->seq_len, out);
                 fputc('\n', out);
             }
+            free(order);
             nb_free(recs);
             nb_free(seq);
             NBH_PHASE("fasta output");

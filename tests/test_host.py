@@ -102,3 +102,11 @@ def test_product_does_not_touch_the_oracle():
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
     assert "oracle" not in open(os.path.join(util.ROOT, "Makefile")).read()
+
+
+def test_fasta_order_helper(built, tmp_path):
+    """nbh_order_by_id (what oc2cns orders its FASTA records with): ascending ids, stable -- tests/host/test_order.c."""
+    exe = str(tmp_path / "test_order")
+    util.run(["gcc", "-O2", "-std=gnu99", "-Wall", "-o", exe, os.path.join(util.ROOT, "tests", "host", "test_order.c"),
+              os.path.join(util.ROOT, "necat_b200", "host", "nb_host.c")])
+    assert util.run([exe]).stdout.strip() == b"ok"
