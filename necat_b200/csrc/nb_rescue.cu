@@ -120,9 +120,9 @@ extern "C" int nb_rescue_local(nb_ctx* ctx, const nb_volume* reads, const nb_res
 // ------------------------------------------------------------------------------------------------------------------
 // Second half of the rescue: edlib_go (edlib/edlib_wrapper.c:111-255) for a batch of ranges.  The recursion is the
 // host's (nb_rescue_driver.h, checked against the oracle in emulation); the two kernels below are the persistent-warp
-// shells around its two warp-level cores.  NOTE: written after the GPU budget of round 1 ran out -- the cores and the
-// driver are verified by the host emulation (tests/test_emu_rescue.py), these shells and nb_rescue_global have not run
-// on a GPU yet (tests/test_gpu_rescue.py::test_rescue_global is skipped unless NB_TEST_UNVERIFIED=1).
+// shells around its two warp-level cores.  The cores and the driver are also run on the host, one thread per lane
+// (tests/test_emu_rescue.py); on the GPU, tests/test_gpu_rescue.py::test_rescue_global_matches_oracle compares
+// nb_rescue_global with the oracle operation by operation.
 #include "nb_rescue_driver.h"
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
