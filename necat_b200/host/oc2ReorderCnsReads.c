@@ -90,7 +90,6 @@ static void* run_job(void* arg)
     char* hdr = NULL; size_t hdr_l = 0, hdr_m = 0;
     int sorted = 1, rc;
     int32_t last_id = INT32_MIN;
-    uint64_t streamed_bytes = 0;
     if (!w.buf) { snprintf(j->err, sizeof j->err, "out of memory"); goto done; }
 
     /* While the ids keep ascending, records go straight to the output.  The first record that breaks the order ends
@@ -107,7 +106,6 @@ static void* run_job(void* arg)
         nbh_pac_clear(&one);
         if (nbh_pac_append(&one, seq, sl)) { snprintf(j->err, sizeof j->err, "out of memory"); goto done; }
         w_record(&w, name, nl, &one, 0, sl);
-        streamed_bytes += nl + sl + 3;
         j->n_records++; j->n_bases += sl;
     }
     if (sorted) {
@@ -177,7 +175,6 @@ done:
     if (fx) nbh_fastx_close(fx);
     nbh_pac_free(&all); nbh_pac_free(&one);
     free(keys); free(info); free(hdr); free(w.buf);
-    (void)streamed_bytes;
     return NULL;
 }
 
