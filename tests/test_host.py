@@ -110,3 +110,29 @@ def test_fasta_order_helper(built, tmp_path):
     util.run(["gcc", "-O2", "-std=gnu99", "-Wall", "-o", exe, os.path.join(util.ROOT, "tests", "host", "test_order.c"),
               os.path.join(util.ROOT, "necat_b200", "host", "nb_host.c")])
     assert util.run([exe]).stdout.strip() == b"ok"
+
+
+@pytest.mark.parametrize("opts", ["-p 40", "-p 25 -f 2", "-p 1000"])
+def test_pcan_many_partitions_match_reference(built, tmp_path, opts):
+    """oc2pcan with small partitions (-p reads per partition, -f files per pass; pcan.c:39-146): same partition count and,
+    partition by partition, the same records as the reference binary."""
+    ref = util.ref_bin("oc2pcan")
+    if not ref:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from necat_b200 import formats
+    wrk = util.golden_workdir(tmp_path)
+    a, b = str(tmp_path / "a.bin"), str(tmp_path / "b.bin")
+    shutil.copy(os.path.join(util.GOLDEN, "cand_k15.bin"), a)
+    shutil.copy(os.path.join(util.GOLDEN, "cand_k15.bin"), b)
+    util.run([ref] + opts.split() + ["-t", "2", wrk, a], cwd=str(tmp_path))
+    util.run([os.path.join(util.BIN_DIR, "oc2pcan")] + opts.split() + ["-t", "2", wrk, b], cwd=str(tmp_path))
+    n = int(open(a + ".partitions").read().split()[0])
+    assert open(b + ".partitions").read() == open(a + ".partitions").read()
+    total = 0
+    for i in range(n):
+        ra, rb = formats.read_candidates(a + ".p%d" % i), formats.read_candidates(b + ".p%d" % i)
+        assert util.same_multiset(ra, rb), f"partition {i}"
+        total += ra.shape[0]
+    assert total == 2 * formats.read_candidates(a).shape[0]
+    if opts == "-p 40":
+        assert n >= 3
