@@ -193,6 +193,7 @@ void o_cns_recvec_free(OCnsRecVec* v);
  * 0 = canonical (order alignments were added), 1 = emulate klib introsort
  * exactly (what the reference binary does). */
 extern int o_cns_tag_order_mode;
+extern int o_cns_partition_size;      /* reads per partition: 100000 as oc2pcan's default (pcan_options.c:10-14), -P in oracle_cli */
 
 /* consensus_one_read.c:216-392 for one template: cans[0..n) are the template's
  * candidates already normalised so that the template is forward.

@@ -14,6 +14,7 @@
 #include <string.h>
 
 int o_cns_tag_order_mode = 0;
+int o_cns_partition_size = 100000;
 
 void o_cns_options_default(OCnsOptions* o)
 {
@@ -635,7 +636,7 @@ static int pcan_sid_lt(const void* x, const void* y)
 
 int o_cns_job(const OVolume* reads, const OPackedCandidate* cans, size_t n, const OCnsOptions* opt, OCnsRecVec* out)
 {
-    const int batch = 100000;                                   /* pcan_options.c:10-14 */
+    const int batch = o_cns_partition_size;                     /* oc2pcan -p, default pcan_options.c:10-14 */
     const int nreads = (int)reads->nseq;
     const int nparts = (nreads + batch - 1) / batch;
     for (int p = 0; p < nparts; ++p) {
@@ -699,7 +700,7 @@ int run_cns(int argc, char** argv)
     o_cns_options_default(&o);
     int c;
     optind = 1;
-    while ((c = getopt(argc - 4, argv, "a:x:y:l:f:e:p:t:r:u:s:M:")) != -1) {
+    while ((c = getopt(argc - 4, argv, "a:x:y:l:f:e:p:t:r:u:s:M:P:")) != -1) {
         switch (c) {
         case 'a': o.min_align_size = atoi(optarg); break;
         case 'x': o.min_cov = atoi(optarg); break;
@@ -713,6 +714,7 @@ int run_cns(int argc, char** argv)
         case 'u': o.use_fixed_ident_cutoff = atoi(optarg); break;
         case 's': o.small_memory = atoi(optarg); break;
         case 'M': o_cns_tag_order_mode = atoi(optarg); break;     /* oracle only: 1 = klib introsort emulation */
+        case 'P': o_cns_partition_size = atoi(optarg); break;     /* oracle only: what oc2pcan -p was given */
         default: return 1;
         }
     }

@@ -82,3 +82,29 @@ def test_edge_sets_match_reference(built, tmp_path, gen):
         util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", "1", wrk, plain, str(tmp_path / "o_cns.fa"), str(tmp_path / "o_raw.fa")])
         assert util.fasta_canon(str(tmp_path / "o_cns.fa")) == util.fasta_canon(str(tmp_path / "r_cns.fa")), name
         assert util.fasta_canon(str(tmp_path / "o_raw.fa")) == util.fasta_canon(str(tmp_path / "r_raw.fa")), name
+
+
+@needs_ref
+def test_many_partitions_match_reference(built, tmp_path):
+    """oc2pcan -p 40 cuts the golden set into several partitions; oc2cns then handles each on its own, and what it dumps
+    as uncorrected depends on the cut (every id of [min_sid, max_sid) of a partition, consensus_one_partition.c:173-194).
+    Run as two nodes (-mn 0 2, -mn 1 2; consensus/main.c:37-41,71-73) and concatenated, as necat.pl does."""
+    import shutil
+    wrk = util.golden_workdir(tmp_path)
+    cand = os.path.join(util.GOLDEN, "cand_k13.bin")
+    c = str(tmp_path / "c.bin")
+    shutil.copy(cand, c)
+    util.run([util.ref_bin("oc2pcan"), "-p", "40", "-t", "1", wrk, c], cwd=str(tmp_path))
+    assert int(open(c + ".partitions").read().split()[0]) >= 3
+    cns = "-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0 -r 0 -f 0"
+    got_c, got_r = [], []
+    for node in (0, 1):
+        util.run([util.ref_bin("oc2cns")] + cns.split() + ["-t", "2", wrk, c, "n_cns.fa", "n_raw.fa", "-mn", str(node), "2"], cwd=str(tmp_path))
+        got_c += util.fasta_canon(str(tmp_path / "n_cns.fa"))
+        got_r += util.fasta_canon(str(tmp_path / "n_raw.fa"))
+    util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", "1", "-P", "40", wrk, cand, "o_cns.fa", "o_raw.fa"], cwd=str(tmp_path))
+    assert sorted(got_c) == util.fasta_canon(str(tmp_path / "o_cns.fa"))
+    assert sorted(got_r) == util.fasta_canon(str(tmp_path / "o_raw.fa"))
+    # and the cut matters: one partition dumps a different set of uncorrected reads
+    util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", "1", wrk, cand, "o1_cns.fa", "o1_raw.fa"], cwd=str(tmp_path))
+    assert sorted(got_c) == util.fasta_canon(str(tmp_path / "o1_cns.fa"))

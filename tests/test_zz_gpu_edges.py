@@ -59,3 +59,22 @@ def test_reads_shorter_than_a_kmer(built, tmp_path):
     o = util.run_pmov(util.ORACLE_CLI, PM13, wrk, 0, str(tmp_path / "o.bin"))
     assert o.shape[0] > 50 and util.same_multiset(g, o)
     assert _cns_pair(tmp_path, wrk, str(tmp_path / "o.bin"), "tiny") > 5
+
+
+def test_many_partitions_two_nodes(built, tmp_path):
+    """oc2pcan -p 40 + oc2cns as two nodes (-mn 0 2, -mn 1 2; consensus/main.c:37-41,71-73), outputs concatenated as
+    necat.pl does, against the oracle cut the same way (the CPU twin of this test pins the oracle on the reference)."""
+    wrk = util.golden_workdir(tmp_path)
+    cand = os.path.join(util.GOLDEN, "cand_k13.bin")
+    c = str(tmp_path / "c.bin")
+    shutil.copy(cand, c)
+    util.run([os.path.join(util.BIN_DIR, "oc2pcan"), "-p", "40", "-t", "1", wrk, c], cwd=str(tmp_path))
+    assert int(open(c + ".partitions").read().split()[0]) >= 3
+    got_c, got_r = [], []
+    for node in (0, 1):
+        util.run([os.path.join(util.BIN_DIR, "oc2cns")] + CNS.split() + [wrk, c, "n_cns.fa", "n_raw.fa", "-mn", str(node), "2"], cwd=str(tmp_path))
+        got_c += util.fasta_canon(str(tmp_path / "n_cns.fa"))
+        got_r += util.fasta_canon(str(tmp_path / "n_raw.fa"))
+    util.run([util.ORACLE_CLI, "cns"] + CNS.split() + ["-M", "0", "-P", "40", wrk, cand, "o_cns.fa", "o_raw.fa"], cwd=str(tmp_path))
+    assert sorted(got_c) == util.fasta_canon(str(tmp_path / "o_cns.fa"))
+    assert sorted(got_r) == util.fasta_canon(str(tmp_path / "o_raw.fa"))
