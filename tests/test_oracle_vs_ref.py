@@ -108,3 +108,15 @@ def test_many_partitions_match_reference(built, tmp_path):
     # and the cut matters: one partition dumps a different set of uncorrected reads
     util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", "1", wrk, cand, "o1_cns.fa", "o1_raw.fa"], cwd=str(tmp_path))
     assert sorted(got_c) == util.fasta_canon(str(tmp_path / "o1_cns.fa"))
+
+
+@needs_ref
+def test_candidate_text_output_matches_reference(built, tmp_path):
+    """oc2pmov -j 0 -u 0: the text form of the UNPACKED candidates (gapped_candidate.h:26-41, pm_worker.c:180-185), which
+    still carries the seed position the 28-byte record drops."""
+    wrk = util.golden_workdir(tmp_path)
+    opts = PM13.replace("-u 1", "-u 0")
+    util.run([util.ref_bin("oc2pmov")] + opts.split() + [wrk, "0", "r.txt"], cwd=str(tmp_path))
+    util.run([util.ORACLE_CLI, "pmov"] + opts.split() + [wrk, "0", "o.txt"], cwd=str(tmp_path))
+    r, o = sorted(open(str(tmp_path / "r.txt")).readlines()), sorted(open(str(tmp_path / "o.txt")).readlines())
+    assert len(r) > 500 and r == o and all(len(x.split("\t")) == 13 for x in r)

@@ -78,3 +78,13 @@ def test_many_partitions_two_nodes(built, tmp_path):
     util.run([util.ORACLE_CLI, "cns"] + CNS.split() + ["-M", "0", "-P", "40", wrk, cand, "o_cns.fa", "o_raw.fa"], cwd=str(tmp_path))
     assert sorted(got_c) == util.fasta_canon(str(tmp_path / "o_cns.fa"))
     assert sorted(got_r) == util.fasta_canon(str(tmp_path / "o_raw.fa"))
+
+
+def test_candidate_text_output(built, tmp_path):
+    """oc2pmov -j 0 -u 0 (text candidates with the seed position, gapped_candidate.h:26-41) against the oracle."""
+    wrk = util.golden_workdir(tmp_path)
+    opts = PM13.replace("-u 1", "-u 0")
+    util.run([os.path.join(util.BIN_DIR, "oc2pmov")] + opts.split() + [wrk, "0", "g.txt"], cwd=str(tmp_path))
+    util.run([util.ORACLE_CLI, "pmov"] + opts.split() + [wrk, "0", "o.txt"], cwd=str(tmp_path))
+    g, o = sorted(open(str(tmp_path / "g.txt")).readlines()), sorted(open(str(tmp_path / "o.txt")).readlines())
+    assert len(o) > 500 and g == o
