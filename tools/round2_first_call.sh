@@ -5,8 +5,7 @@
 #   2. the bench line at N = 1;
 #   3. TWO chained correction iterations at E. coli size, this repo's five executables against the reference's five,
 #      iteration 2 with the FAST overlap options and oc2cns -r 1 (the first run of -r 1 at scale): parity + wall clock
-#      per stage (DESIGN.md "Next", item 1);
-#   4. the launch list of that second iteration's oc2cns (where the time of -r 1 goes).
+#      per stage (DESIGN.md "Next", item 1).
 # usage:  gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1
