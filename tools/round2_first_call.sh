@@ -14,3 +14,6 @@ timeout 400 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.er
 tail -c 700 gpurun_out/bench_n1.json; echo
 timeout 900 python tools/full_parity.py --iterations 2 --out gpurun_out/parity_iter2.json > gpurun_out/parity_iter2.log 2>&1
 grep -E '^\{"iteration"|^GPU|failed' gpurun_out/parity_iter2.log | cut -c1-400
+# random options / read sets, this repo's executables against the oracle (each case ~5 s)
+timeout 600 python tools/soak_oracle.py 1 60 gpu > gpurun_out/soak_gpu.log 2>&1
+grep -v ' OK ' gpurun_out/soak_gpu.log | cut -c1-300 | tail -8
