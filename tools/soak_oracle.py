@@ -39,6 +39,14 @@ for case in range(int(sys.argv[2])):
         util.run([exe("oc2cns")]+cns.split()+["-t","4",wrk,c,str(t/"r_cns.fa"),str(t/"r_raw.fa")])
         util.run([util.ORACLE_CLI,"cns"]+cns.split()+["-M","0" if GPU else "1",wrk,str(t/"r.bin"),str(t/"o_cns.fa"),str(t/"o_raw.fa")])
         ok2=util.fasta_canon(str(t/"r_cns.fa"))==util.fasta_canon(str(t/"o_cns.fa")); ok3=util.fasta_canon(str(t/"r_raw.fa"))==util.fasta_canon(str(t/"o_raw.fa"))
+        # ALN mode (-j 1): M4 text lines, with names or ids
+        ok4 = True
+        if rng.random() < 0.5:
+            pm4 = pm.replace("-j 0 -u 1 -i 1", "-j 1 -u 0 -i %d" % int(rng.choice([0, 1])))
+            util.run([exe("oc2pmov")]+pm4.split()+[wrk,"0",str(t/"r.m4")])
+            util.run([util.ORACLE_CLI,"pmov"]+pm4.split()+[wrk,"0",str(t/"o.m4")])
+            ok4 = sorted(open(t/"r.m4").readlines()) == sorted(open(t/"o.m4").readlines())
+        ok3 = ok3 and ok4
         print(case, "OK" if (ok1 and ok2 and ok3) else "MISMATCH", ok1,ok2,ok3, rr.shape[0], len(util.fasta_canon(str(t/"r_cns.fa"))), "%.0fs"%(time.time()-t0), "|", pm, "|", cns, "|", gen, flush=True)
         bad += not (ok1 and ok2 and ok3)
     except Exception as e:
