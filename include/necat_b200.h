@@ -190,8 +190,8 @@ int  nb_extend_candidates(nb_ctx* ctx, const nb_volume* reads,
  * First half of the oc2cns -r 1 rescue (consensus/consensus_aux.c:169-178): ocda_go (gapped_align/oc_daligner.c:34-79),
  * Myers' O(nd) local alignment with path-tip trimming (gapped_align/align.c:382-1945) through the point
  * (qstart, tstart) of query read qid (strand qdir) and template read sid (forward).  Returns the two ranges and the
- * number of differences; ok = both ranges span at least min_align_size.  The second half (global alignment of the
- * ranges, edlib/edlib_wrapper.c:111) is not on the GPU yet: nb_consensus_job refuses -r 1.
+ * number of differences; ok = both ranges span at least min_align_size.  The second half is nb_rescue_global below;
+ * nb_consensus_job runs both when its options ask for -r 1.
  */
 typedef struct { uint32_t qid, sid; int32_t qdir, qstart, tstart, pad_; } nb_rescue_task;
 typedef struct { int32_t ok, qbeg, qend, tbeg, tend, diffs, overflow, pad_; } nb_rescue_result;
@@ -203,7 +203,7 @@ int  nb_rescue_local(nb_ctx* ctx, const nb_volume* reads, const nb_rescue_task* 
  * range [qfrom, qto) (strand qdir) with template range [tfrom, tto) if their edit distance is <= tolerance, by edlib's
  * rules for choosing among co-optimal alignments (Hirschberg's first split row, up / left / diagonal traceback below
  * 1 MiB of alignment data), trimmed to its first and last run of k_match matches.  Results as nb_extend_candidates.
- * NOT YET RUN ON A GPU (round 1 ran out of GPU time): its cores and recursion are verified by host emulation only.
+ * Checked against the oracle operation by operation on a B200 (tests/test_gpu_rescue.py) and in host emulation.
  */
 typedef struct { uint32_t qid, sid; int32_t qdir, qfrom, qto, tfrom, tto, tolerance; } nb_rescue_range;
 int  nb_rescue_global(nb_ctx* ctx, const nb_volume* reads, const nb_rescue_range* ranges, uint64_t n, double error,
