@@ -1,10 +1,10 @@
-// nb_rescue.cu -- first half of the oc2cns -r 1 rescue (consensus/consensus_aux.c:169-178): the O(nd) local alignment
+// nb_rescue.cu -- the oc2cns -r 1 rescue (consensus/consensus_aux.c:169-201).  First half: the O(nd) local alignment
 // of ocda_go (gapped_align/oc_daligner.c:34-79) for a batch of candidates, one warp per candidate.
 //
 // The wave recurrence itself lives in nb_rescue_core.cuh (lane = diagonal, two generations of the wave vectors in a
 // per-warp band in HBM / L2); this file is the persistent kernel around it and the C-ABI entry.  The second half of
-// the rescue (the global alignment of the range found here) is not on the GPU yet, so nb_consensus_job still refuses
-// -r 1; this entry point exists so that the kernel can be checked against the oracle (tests/test_gpu_rescue.py).
+// the rescue (the global alignment of the range found here, edlib_go) follows further down; nb_consensus_job calls
+// both for -r 1, and both are exported so that they can be checked against the oracle (tests/test_gpu_rescue.py).
 #include <vector>
 
 #include "nb_common.cuh"
