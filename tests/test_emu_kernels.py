@@ -1,0 +1,72 @@
+"""CPU: the product's CUDA kernels themselves, compiled for the host (tests/emu/cudaemu: every CUDA thread a fiber, warp
+collectives and barriers as rendezvous, bulk copies / cp.async landing at once) from the UNMODIFIED sources under
+necat_b200/csrc, driven through the same C-ABI and the same executables, against the oracle.  This is what lets the
+CPU-only suite notice a logic regression in a kernel; it says nothing about speed, and the GPU suite (-m gpu) remains the
+parity gate on the real device.  Inputs are tiny: the emulation runs a few hundred thousand times slower than a B200."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+import util
+
+EMU_DIR = os.path.join(util.ROOT, "tests", "emu")
+EMU_BIN = os.path.join(EMU_DIR, "_build", "cudaemu", "bin")
+PM11 = "-k 11 -z 10 -q 100 -b 2000 -s 3 -n 500 -a 1000 -d 0.25 -e 0.5 -m 500 -t 1 -j 0 -u 1 -i 1"
+
+
+@pytest.fixture(scope="module")
+def emu(built):
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    return lambda name: os.path.join(EMU_BIN, name)
+
+
+def test_emulated_library_is_not_the_product(emu):
+    """The emulated library lives under tests/ and the product never loads it."""
+    from necat_b200 import capi
+    assert os.path.realpath(capi.LIB_PATH).startswith(os.path.join(util.ROOT, "necat_b200"))
+    out = subprocess.run(["ldd", emu("oc2cns")], capture_output=True, text=True).stdout
+    assert "tests/emu/_build/cudaemu/bin/../lib/libnecat_b200.so" in out and "necat_b200/lib" not in out
+
+
+def test_index_probe_vote_chain_kernels(emu, tmp_path):
+    """k_mark_invalid, k_scan_kmers, the scans, k_sort_*, k_probe (bulk copy + mbarrier), k_build_blocks, k_candidates:
+    oc2pmov CAN mode on the golden volume, k = 11."""
+    wrk = util.golden_workdir(tmp_path)
+    os.chdir(str(tmp_path))
+    g = util.run_pmov(emu("oc2pmov"), PM11, wrk, 0, str(tmp_path / "g.bin"))
+    o = util.run_pmov(util.ORACLE_CLI, PM11, wrk, 0, str(tmp_path / "o.bin"))
+    assert o.shape[0] > 1000 and util.same_multiset(g, o)
+
+
+def test_aln_mode_kernels(emu, tmp_path):
+    """oc2pmov -j 1: speculative k_extend + contain-rule replay, M4 text."""
+    wrk, _ = util.make_workdir(tmp_path, genome=8000, depth=10, seed=83, err=0.10)
+    opts = PM11.replace("-j 0 -u 1", "-j 1 -u 0")
+    util.run([emu("oc2pmov")] + opts.split() + [wrk, "0", str(tmp_path / "g.m4")])
+    util.run([util.ORACLE_CLI, "pmov"] + opts.split() + [wrk, "0", str(tmp_path / "o.m4")])
+    g, o = sorted(open(str(tmp_path / "g.m4")).readlines()), sorted(open(str(tmp_path / "o.m4")).readlines())
+    assert len(o) > 20 and g == o
+
+
+@pytest.mark.parametrize("cns,gen", [
+    # k_extend (two candidates per warp), k_cns_links, k_cns_dp (cp.async ring), k_cns_walk, k_gather_ascii
+    ("-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0 -r 0 -f 0", dict(genome=8000, depth=12, seed=81, err=0.10)),
+    # -r 1: k_rescue_local, k_rescue_columns, k_rescue_leaves and the wiring into the extension rounds
+    ("-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0 -r 1 -f 1", dict(genome=6000, depth=10, seed=82, err=0.10, long_indel=0.5)),
+])
+def test_extension_and_consensus_kernels(emu, tmp_path, cns, gen):
+    wrk, _ = util.make_workdir(tmp_path, **gen)
+    cand = str(tmp_path / "o.bin")
+    o = util.run_pmov(util.ORACLE_CLI, PM11, wrk, 0, cand)
+    assert o.shape[0] > 30
+    c = str(tmp_path / "c.bin")
+    shutil.copy(cand, c)
+    util.run([emu("oc2pcan"), "-t", "1", wrk, c])
+    util.run([emu("oc2cns")] + cns.split() + [wrk, c, str(tmp_path / "g_cns.fa"), str(tmp_path / "g_raw.fa")])
+    util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", "0", wrk, cand, str(tmp_path / "o_cns.fa"), str(tmp_path / "o_raw.fa")])
+    exp = util.fasta_canon(str(tmp_path / "o_cns.fa"))
+    assert len(exp) >= 5
+    assert util.fasta_canon(str(tmp_path / "g_cns.fa")) == exp
+    assert util.fasta_canon(str(tmp_path / "g_raw.fa")) == util.fasta_canon(str(tmp_path / "o_raw.fa"))
