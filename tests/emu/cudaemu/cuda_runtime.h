@@ -251,10 +251,11 @@ static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 // fresh device memory is NOT zero: fill it with a pattern so that a kernel that reads before it writes shows up
 static inline cudaError_t cudaMalloc(void** p, size_t n)
 {
-    const size_t bytes = (n + 255) & ~(size_t)255;
-    *p = aligned_alloc(256, bytes ? bytes : 256);
-    if (!*p) return cudaErrorMemoryAllocation;
-    memset(*p, 0xA5, bytes ? bytes : 256);
+    // exactly n bytes (256-byte aligned like the device allocator): under AddressSanitizer a kernel that reads or
+    // writes one byte past what the host code asked for is reported
+    *p = NULL;
+    if (posix_memalign(p, 256, n ? n : 1)) return cudaErrorMemoryAllocation;
+    memset(*p, 0xA5, n ? n : 1);
     return cudaSuccess;
 }
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }

@@ -48,6 +48,18 @@ def convert(src):
     return src, n_launch
 
 
+def strict_allocator(src):
+    """nb_core.cu's caching allocator rounds sizes to 512 bytes and hands out larger cached blocks; with NB_EMU_STRICT=1
+    in the environment the emulated build allocates exactly what was asked for, every time, so that AddressSanitizer sees
+    an overrun of a single byte (tests/emu/README.md)."""
+    a = "    bytes = (bytes + 511) & ~(size_t)511;\n"
+    b = "        if (b.used || b.bytes < bytes || b.bytes > bytes * 2 + (8u << 20)) continue;\n"
+    assert a in src and b in src, "nb_dev_alloc changed: update prep.py"
+    src = src.replace(a, "    const bool emu_strict = getenv(\"NB_EMU_STRICT\") != NULL;\n    if (!emu_strict) bytes = (bytes + 511) & ~(size_t)511;\n")
+    src = src.replace(b, "        if (emu_strict || b.used || b.bytes < bytes || b.bytes > bytes * 2 + (8u << 20)) continue;\n")
+    return src
+
+
 def main():
     csrc, out = sys.argv[1], sys.argv[2]
     os.makedirs(out, exist_ok=True)
@@ -56,6 +68,8 @@ def main():
         if not f.endswith((".cu", ".cuh", ".h")):
             continue
         text, n = convert(open(os.path.join(csrc, f)).read())
+        if f == "nb_core.cu":
+            text = strict_allocator(text)
         total += n
         name = f[:-3] + ".cpp" if f.endswith(".cu") else f
         open(os.path.join(out, name), "w").write(text)
