@@ -65,7 +65,7 @@ extern thread_local void*  dyn_smem;
 const uint64_t* warp_exchange(uint64_t v, uint32_t* mask);
 void block_barrier();
 void yield();               // spin-wait helper: lets the other fibers run
-void run(dim3 grid, dim3 block, size_t smem, void (*entry)(void*), void* arg);
+void run(const char* name, dim3 grid, dim3 block, size_t smem, void (*entry)(void*), void* arg);
 }  // namespace emu
 
 #define threadIdx (emu::cur->tid)
@@ -285,6 +285,7 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAtt
 // ---------------------------------------------------------------- kernel launch:  EMU_LAUNCH((kernel), grid, block, smem, stream)(args...)
 namespace emu {
 template <class... P> struct Launcher {
+    const char* name;
     void (*k)(P...);
     dim3 g, b;
     size_t smem;
@@ -292,9 +293,9 @@ template <class... P> struct Launcher {
     {
         auto body = [&]() { k((P)(a)...); };          // C-style: NULL (a long) becomes a null pointer, as nvcc accepts
         typedef decltype(body) B;
-        run(g, b, smem, [](void* p) { (*static_cast<B*>(p))(); }, &body);
+        run(name, g, b, smem, [](void* p) { (*static_cast<B*>(p))(); }, &body);
     }
 };
-template <class... P> inline Launcher<P...> launcher(void (*k)(P...), dim3 g, dim3 b, size_t smem = 0, cudaStream_t = 0) { return Launcher<P...>{k, g, b, smem}; }
+template <class... P> inline Launcher<P...> launcher(const char* name, void (*k)(P...), dim3 g, dim3 b, size_t smem = 0, cudaStream_t = 0) { return Launcher<P...>{name, k, g, b, smem}; }
 }  // namespace emu
-#define EMU_LAUNCH(k, ...) emu::launcher(k, __VA_ARGS__)
+#define EMU_LAUNCH(k, ...) emu::launcher(#k, k, __VA_ARGS__)

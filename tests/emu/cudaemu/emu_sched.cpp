@@ -46,6 +46,7 @@ thread_local uint3  block_idx;
 thread_local dim3   block_dim, grid_dim;
 thread_local void*  dyn_smem = nullptr;
 static thread_local Sched* S = nullptr;
+static thread_local uint64_t st_coll = 0, st_bar = 0, st_warp_max = 0;
 
 static void to_scheduler() { Fiber* f = cur; emu_ctx_switch(&f->sp, S->sp); }
 
@@ -70,7 +71,7 @@ const uint64_t* warp_exchange(uint64_t v, uint32_t* mask)
     return w->val[g & 1];
 }
 
-void block_barrier() { cur->state = WAIT_BAR; to_scheduler(); }
+void block_barrier() { ++st_bar; cur->state = WAIT_BAR; to_scheduler(); }
 void yield() { cur->state = YIELDED; to_scheduler(); }
 
 static void run_block(unsigned nthreads)
@@ -139,11 +140,17 @@ static void run_block(unsigned nthreads)
             }
         }
     }
+    for (unsigned wi = 0; wi < nwarps; ++wi) { st_coll += s->warps[wi].gen; if (s->warps[wi].gen > st_warp_max) st_warp_max = s->warps[wi].gen; }
     cur = nullptr;
 }
 
-void run(dim3 grid, dim3 block, size_t smem, void (*entry)(void*), void* arg)
+// NB_EMU_STATS=1: per launch, the number of warp collectives and block barriers, in total and the most any single warp
+// executed -- on the GPU the latter is a proxy for the length of the dependent chain that bounds a latency-bound kernel
+
+void run(const char* name, dim3 grid, dim3 block, size_t smem, void (*entry)(void*), void* arg)
 {
+    static const bool stats = getenv("NB_EMU_STATS") != nullptr;
+    st_coll = st_bar = st_warp_max = 0;
     const unsigned nthreads = block.x * block.y * block.z;
     if (nthreads == 0 || nthreads > (unsigned)kMaxThreads) { fprintf(stderr, "cudaemu: %u threads per block\n", nthreads); abort(); }
     if (cur) { fprintf(stderr, "cudaemu: kernel launched from device code\n"); abort(); }
@@ -165,6 +172,9 @@ void run(dim3 grid, dim3 block, size_t smem, void (*entry)(void*), void* arg)
             }
     dyn_smem = nullptr;
     free(sm);
+    if (stats)
+        fprintf(stderr, "[cudaemu] %-34s grid %5u x %4u threads: %10llu warp collectives (longest warp %9llu), %8llu barrier waits\n", name,
+                grid.x * grid.y * grid.z, nthreads, (unsigned long long)st_coll, (unsigned long long)st_warp_max, (unsigned long long)st_bar);
 }
 
 }  // namespace emu
