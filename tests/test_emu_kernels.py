@@ -70,3 +70,46 @@ def test_extension_and_consensus_kernels(emu, tmp_path, cns, gen):
     assert len(exp) >= 5
     assert util.fasta_canon(str(tmp_path / "g_cns.fa")) == exp
     assert util.fasta_canon(str(tmp_path / "g_raw.fa")) == util.fasta_canon(str(tmp_path / "o_raw.fa"))
+
+
+def test_sharded_pipeline_through_the_python_api(emu, tmp_path):
+    """bench.py's multi-GPU recipe with the emulated library behind necat_b200.capi (patched in a child
+    process only): the reads are mapped in two ranges as two ranks would, the candidate records are concatenated as the
+    all-gather does, and each rank corrects the templates it owns; the union of the two ranks' records is what one rank
+    alone produces."""
+    wrk, _ = util.make_workdir(tmp_path, genome=6000, depth=10, seed=84, err=0.10)
+    code = r'''
+import sys, os, numpy as np
+sys.path.insert(0, %(root)r)
+from necat_b200 import capi, formats, dist as nbdist
+capi.LIB_PATH = %(lib)r                      # test only: the emulated build (tests/emu), never the product's path
+vol = formats.read_volume(os.path.join(%(wrk)r, "vol0"))
+ctx = capi.Context(0)
+popt = capi.default_map_options(kmer_size=11, scan_window=10, kmer_cnt_cutoff=100, block_size=2000, block_score_cutoff=3,
+                                num_candidates=500, align_size_cutoff=1000, ddfs_cutoff=0.25, error=0.5, num_output=500)
+copt = capi.default_cns_options(min_align_size=1000, min_cov=3, max_cov=12, min_size=500, error=0.5, mapping_ratio=0.8,
+                                rescue_long_indels=0, use_fixed_ident_cutoff=0, full_consensus=0)
+dvol = ctx.upload(vol)
+idx = ctx.build_index(dvol, 11, 100)
+parts = []
+for rank in range(2):
+    lo, hi = nbdist.shard_range(vol.nseq, rank, 2)
+    parts.append(capi.pack_candidates(ctx.map_volume(idx, dvol, 0, dvol, 0, lo, hi, popt)))
+packed = np.concatenate(parts)
+whole = capi.pack_candidates(ctx.map_volume(idx, dvol, 0, dvol, 0, 0, vol.nseq, popt))
+assert formats.canonical_records(packed).tobytes() == formats.canonical_records(whole).tobytes()
+part = np.concatenate([packed, formats.swap_roles(packed)])
+def records(world, rank):
+    recs, seq = ctx.consensus_job(dvol, part, copt, world, rank)
+    a = seq.array()
+    out = sorted((int(r["id"]), int(r["is_raw"]), int(r["left"]), int(r["right"]), bytes(a[int(r["seq_offset"]):int(r["seq_offset"]) + int(r["seq_len"])])) for r in recs)
+    seq.free()
+    return out
+one = records(1, 0)
+two = sorted(records(2, 0) + records(2, 1))
+assert len(one) > 5 and one == two, (len(one), len(two))
+assert all(nbdist.owns_template([r[0]], 0, 2)[0] for r in records(2, 0))
+print("OK", len(packed), len(one))
+''' % dict(root=util.ROOT, lib=os.path.join(EMU_DIR, "_build", "cudaemu", "lib", "libnecat_b200.so"), wrk=wrk)
+    p = util.run(["python", "-c", code])
+    assert p.stdout.startswith(b"OK")
