@@ -96,15 +96,28 @@ static void run_block(unsigned nthreads)
         f.sp = p - 6;
     }
     unsigned remaining = nthreads;
+    static const int order = [] { const char* e = getenv("NB_EMU_ORDER"); return !e ? 0 : !strcmp(e, "reverse") ? 1 : !strcmp(e, "random") ? 2 : 0; }();
+    static thread_local uint64_t rnd = 0x9E3779B97F4A7C15ull;
     while (remaining) {
         bool progress = false;
         for (Fiber& f : s->fibers) if (f.state == YIELDED) { f.state = READY; progress = true; }
-        for (unsigned wi = 0; wi < nwarps; ++wi) {
+        const unsigned wrot = order == 2 ? (unsigned)((rnd >> 40) % nwarps) : 0;
+        for (unsigned wj = 0; wj < nwarps; ++wj) {
+            const unsigned wi = order == 1 ? nwarps - 1 - wj : (wj + wrot) % nwarps;    // the warps' turns are permuted too
             WarpX& w = s->warps[wi];
             for (;;) {
                 bool ran = false;
                 const unsigned t0 = wi * 32, t1 = t0 + 32 < nthreads ? t0 + 32 : nthreads;
-                for (unsigned t = t0; t < t1; ++t) {
+                for (unsigned u = t0; u < t1; ++u) {
+                    // NB_EMU_ORDER: the order in which the runnable lanes of a warp get their turn.  Results must not
+                    // depend on it; if they do, two lanes communicate without a __syncwarp() / collective between them.
+                    unsigned t = u;
+                    if (order == 1) t = t0 + (t1 - 1 - u);
+                    else if (order == 2) {          // a fresh rotation and direction for every pass: still a permutation
+                        if (u == t0) rnd = rnd * 6364136223846793005ull + 1442695040888963407ull;
+                        const unsigned n = t1 - t0, r = (unsigned)((rnd >> 33) % n), k = u - t0;
+                        t = t0 + (((rnd >> 20) & 1) ? (r + k) % n : (r + n - k) % n);
+                    }
                     Fiber& f = s->fibers[t];
                     if (f.state != READY) continue;
                     cur = &f;

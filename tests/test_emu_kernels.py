@@ -113,3 +113,25 @@ print("OK", len(packed), len(one))
 ''' % dict(root=util.ROOT, lib=os.path.join(EMU_DIR, "_build", "cudaemu", "lib", "libnecat_b200.so"), wrk=wrk)
     p = util.run(["python", "-c", code])
     assert p.stdout.startswith(b"OK")
+
+
+@pytest.mark.parametrize("order", ["reverse", "random"])
+def test_results_do_not_depend_on_lane_order(emu, tmp_path, order):
+    """NB_EMU_ORDER permutes the order in which the runnable lanes of a warp (and the warps of a block) get their turn.
+    Two lanes that communicate through shared or global memory without a __syncwarp() / collective / barrier between them
+    would make the result depend on it."""
+    env = dict(os.environ, NB_EMU_ORDER=order)
+    wrk, _ = util.make_workdir(tmp_path, genome=6000, depth=10, seed=85, err=0.12, long_indel=0.3)
+    cand = str(tmp_path / "o.bin")
+    o = util.run_pmov(util.ORACLE_CLI, PM11, wrk, 0, cand)
+    util.run([emu("oc2pmov")] + PM11.split() + [wrk, "0", str(tmp_path / "g.bin")], env=env)
+    from necat_b200 import formats
+    assert o.shape[0] > 30 and util.same_multiset(formats.read_candidates(str(tmp_path / "g.bin")), o)
+    cns = "-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0 -r 1 -f 0"
+    c = str(tmp_path / "c.bin")
+    shutil.copy(cand, c)
+    util.run([emu("oc2pcan"), "-t", "1", wrk, c])
+    util.run([emu("oc2cns")] + cns.split() + [wrk, c, str(tmp_path / "g_cns.fa"), str(tmp_path / "g_raw.fa")], env=env)
+    util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", "0", wrk, cand, str(tmp_path / "o_cns.fa"), str(tmp_path / "o_raw.fa")])
+    assert util.fasta_canon(str(tmp_path / "g_cns.fa")) == util.fasta_canon(str(tmp_path / "o_cns.fa"))
+    assert util.fasta_canon(str(tmp_path / "g_raw.fa")) == util.fasta_canon(str(tmp_path / "o_raw.fa"))
