@@ -19,4 +19,5 @@ def built():
     """Makes sure the oracle (CPU checker) and the product binaries exist."""
     import util
     util.ensure_oracle()
+    util.ensure_host_tools()
     return util

@@ -22,6 +22,14 @@ def ensure_oracle():
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
 
 
+def ensure_host_tools():
+    """The host-only executables (gcc + zlib, no nvcc needed) are built on demand; the CUDA library and the three
+    executables over it come from `make` / __graft_entry__.build()."""
+    tools = [os.path.join(BIN_DIR, t) for t in ("oc2mkdb", "oc2ReorderCnsReads")]
+    if not all(os.path.exists(t) for t in tools):
+        subprocess.check_call(["make", "-s", "-C", ROOT] + [os.path.relpath(t, ROOT) for t in tools])
+
+
 def ref_bin(name):
     p = os.path.join(REF_DIR, name)
     return p if os.path.exists(p) else None
