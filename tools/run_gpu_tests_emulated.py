@@ -17,9 +17,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join
 import util  # noqa: E402
 
 EMU = os.path.join(ROOT, "tests", "emu")
-subprocess.check_call(["make", "-s", "-C", EMU])
+# NB_EMU_ASAN=1: the AddressSanitizer build with exact-size "device" allocations (tests/emu/README.md), ~3x slower still
+ASAN = os.environ.get("NB_EMU_ASAN") == "1"
+subprocess.check_call(["make", "-s", "-C", EMU] + (["asan"] if ASAN else []))
+if ASAN:
+    os.environ["NB_EMU_STRICT"] = "1"
+    os.environ.setdefault("ASAN_OPTIONS", "detect_leaks=0")
 util.ensure_oracle()
-EMU_BIN = os.path.join(EMU, "_build", "cudaemu", "bin")
+EMU_BIN = os.path.join(EMU, "_build", "cudaemu_asan" if ASAN else "cudaemu", "bin")
 HOST_BIN = util.BIN_DIR
 util.BIN_DIR = EMU_BIN                       # the three executables over the C-ABI come from the emulated build
 import test_iteration_flow as F  # noqa: E402
