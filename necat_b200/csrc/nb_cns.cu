@@ -519,11 +519,14 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         std::vector<size_t> order;
         for (size_t t = a0; t < b0; ++t) order.push_back(t);
         static const int kSort = getenv("NB_CNS_SORT") ? atoi(getenv("NB_CNS_SORT")) : 1;
-        static const int kLanes = 1;
-        static const int kWalkLanes = getenv("NB_CNS_WALK_LANES") ? atoi(getenv("NB_CNS_WALK_LANES")) : 1;
-        static const int kDpTest = getenv("NB_CNS_DP_TEST") ? atoi(getenv("NB_CNS_DP_TEST")) : 0;   // 1 = test build of k_cns_dp: tiny fast path and score ring
+        static const int kDpTest = getenv("NB_CNS_DP_TEST") ? atoi(getenv("NB_CNS_DP_TEST")) : 0;   // 1 = test build of k_cns_dp: score ring of 8 (most templates go to k_cns_dp_serial), 2 = all of them
+        int span = getenv("NB_CNS_SPAN") ? atoi(getenv("NB_CNS_SPAN")) : CNS_SPAN_DEFAULT;           // (tests lower it: many span boundaries on short reads)
+        if (span < CNS_TILE) span = CNS_TILE;
+        span -= span % CNS_TILE;
         if (kSort) std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tpls[a].T != tpls[b].T ? tpls[a].T > tpls[b].T : a < b; });
         dt.resize(order.size()); dt_tpl.resize(order.size());
+        std::vector<CnsUnit> units;
+        uint64_t n_ckpt = 0;
         {
             uint32_t aln_total = 0;
             for (size_t x = 0; x < order.size(); ++x) {
@@ -537,9 +540,12 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                 ct.out_cap = (uint32_t)(T.T * 2 + 1024);
                 ct.out_base = out_pool; out_pool += ct.out_cap;
                 ct.level_cap = (uint32_t)(T.T * 3 + 2048);
+                ct.unit_first = (uint32_t)units.size();
+                for (int s = 0; s * span < T.T; ++s) { CnsUnit u; u.tpl = (uint32_t)x; u.span = (uint32_t)s; units.push_back(u); }
                 cx->cc.n_accepted += T.acc.size();
                 dt_tpl[x] = order[x];
             }
+            if (units.size() >= 0xfffffff0ull) return nb_fail(cx, NB_ELIMIT, "too many consensus units in one chunk");
             alns.resize(aln_total);
             auto fill = [&](size_t x0, size_t x1) {             // the alignment descriptions, in parallel over templates
                 for (size_t x = x0; x < x1; ++x) {
@@ -554,7 +560,8 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                         CnsAln ca;
                         ca.ops = G.res_ops[(size_t)c.res]; ca.qseq_off = reads->h_off[c.qid];
                         ca.aln_size = r.aln_size; ca.toff = r.toff; ca.tend = r.tend; ca.qstart = r.qoff;
-                        ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight; ca.drop = r.long_ins; ca.pad_ = 0;
+                        ca.qlen = c.qsize; ca.qdir = c.qdir; ca.weight = a.weight; ca.drop = r.long_ins;
+                        ca.ckpt_first = 0; ca.unit_first = dt[x].unit_first; ca.pad_ = 0;
                         *dst++ = ca;
                         cols += (uint64_t)r.aln_size;
                     }
@@ -570,6 +577,12 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             }
             if (per) fill(0, std::min(order.size(), per));
             for (auto& x : th) x.join();
+            // span-boundary checkpoints: one per boundary an alignment crosses
+            for (CnsAln& ca : alns) {
+                ca.ckpt_first = (uint32_t)n_ckpt;
+                if (!ca.drop && ca.tend > ca.toff) n_ckpt += (uint64_t)((ca.tend - 1) / span - ca.toff / span);
+            }
+            if (n_ckpt >= 0xfffffff0ull) return nb_fail(cx, NB_ELIMIT, "too many alignment checkpoints in one chunk");
         }
         for (auto& ct : dt) {
             ct.pos_base = pos_total; pos_total += (uint64_t)ct.T + 2;
@@ -584,87 +597,82 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             int rc;
             CnsParams P;
             memset(&P, 0, sizeof P);
-            CnsTemplate* d_tpl; CnsAln* d_aln;
+            CnsTemplate* d_tpl; CnsAln* d_aln; CnsUnit* d_unit;
             if ((rc = D.get(&d_tpl, dt.size()))) return rc;
             if ((rc = D.get(&d_aln, alns.size()))) return rc;
+            if ((rc = D.get(&d_unit, units.size()))) return rc;
             if ((rc = D.get(&P.seg, seg_total))) return rc;
             if ((rc = D.get(&P.tpl_nseg, dt.size()))) return rc;
             if ((rc = D.get(&P.seq_pool, out_pool))) return rc;
             d_seq_pool = P.seq_pool;
-            if ((rc = D.get(&P.next_tpl, 1))) return rc;
+            if ((rc = D.get(&P.next_unit, 1))) return rc;
+            if ((rc = D.get(&P.span_cols, units.size()))) return rc;
+            if ((rc = D.get(&P.span_links, units.size()))) return rc;
+            if ((rc = D.get(&P.ckpt, n_ckpt))) return rc;
             if ((rc = D.get(&P.pos, pos_total))) return rc;
-            if ((rc = D.get(&P.link, link_total + 512))) return rc;     // k_cns_dp stages batches of 32 links up to 160 links ahead: slack past the last link
+            if ((rc = D.get(&P.link, link_total + 64))) return rc;
             if ((rc = D.get(&P.bp, level_total))) return rc;
             if ((rc = D.get(&P.rev, level_total))) return rc;
-            const unsigned links_grid = NB_SMS * 5;          // 20 warps per SM (shared-memory bound)
-            const size_t cursor_area = (size_t)links_grid * CNS_WARPS * CNS_MAX_ALN;    // one per side stream: slices run concurrently
-            if ((rc = D.get(&P.cursor, cursor_area * 2))) return rc;
+            static const int kLinksCtas = getenv("NB_CNS_LINKS_CTAS") ? atoi(getenv("NB_CNS_LINKS_CTAS")) : 6;
+            const unsigned links_grid = NB_SMS * (unsigned)(kLinksCtas < 1 ? 1 : kLinksCtas);
+            if ((rc = D.get(&P.cursor, (size_t)links_grid * CNS_WARPS * CNS_MAX_ALN))) return rc;
+            if ((rc = D.get(&P.ovpool, (size_t)links_grid * CNS_WARPS * CNS_OV))) return rc;
             if ((rc = D.get(&P.error_flag, 1))) return rc;
             if ((rc = D.get(&P.counters, 4))) return rc;
-            CnsRun* d_runs; uint32_t* d_nrun;
-            if ((rc = D.get(&d_runs, seg_total))) return rc;
-            if ((rc = D.get(&d_nrun, dt.size()))) return rc;
+            if ((rc = D.get(&P.runs, seg_total))) return rc;
+            if ((rc = D.get(&P.tpl_nrun, dt.size()))) return rc;
+            if ((rc = D.get(&P.redo, dt.size()))) return rc;
+            if ((rc = D.get(&P.n_redo, 1))) return rc;
             NB_CUDA(cx, cudaMemcpyAsync(d_tpl, dt.data(), sizeof(CnsTemplate) * dt.size(), cudaMemcpyHostToDevice, cst));
             NB_CUDA(cx, cudaMemcpyAsync(d_aln, alns.data(), sizeof(CnsAln) * alns.size(), cudaMemcpyHostToDevice, cst));
-            NB_CUDA(cx, cudaMemsetAsync(P.next_tpl, 0, sizeof(uint32_t), cst));
+            NB_CUDA(cx, cudaMemcpyAsync(d_unit, units.data(), sizeof(CnsUnit) * units.size(), cudaMemcpyHostToDevice, cst));
+            NB_CUDA(cx, cudaMemsetAsync(P.next_unit, 0, sizeof(uint32_t), cst));
+            NB_CUDA(cx, cudaMemsetAsync(P.n_redo, 0, sizeof(uint32_t), cst));
+            NB_CUDA(cx, cudaMemsetAsync(P.span_cols, 0, sizeof(uint32_t) * units.size(), cst));
             NB_CUDA(cx, cudaMemsetAsync(P.error_flag, 0, sizeof(uint32_t), cst));
             NB_CUDA(cx, cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 4, cst));
-            P.pac = reads->d_pac; P.tpl = d_tpl; P.aln = d_aln; P.n_tpl = (uint32_t)dt.size();
-            P.min_cov = o.min_cov; P.min_size = o.min_size; P.lanes = kLanes < 1 ? 1 : (kLanes > 32 ? 32 : kLanes);
-            P.walk_lanes = kWalkLanes < 1 ? 1 : (kWalkLanes > 32 ? 32 : kWalkLanes);
+            P.pac = reads->d_pac; P.tpl = d_tpl; P.aln = d_aln; P.n_tpl = (uint32_t)dt.size(); P.n_aln = (uint32_t)alns.size();
+            P.unit = d_unit; P.n_units = (uint32_t)units.size(); P.span = span;
+            P.min_cov = o.min_cov; P.min_size = o.min_size;
             P.flush_slow = getenv("NB_CNS_FLUSH_SLOW") ? atoi(getenv("NB_CNS_FLUSH_SLOW")) : 0;
-            P.links_multi = getenv("NB_CNS_LINKS_MULTI") ? atoi(getenv("NB_CNS_LINKS_MULTI")) : 0;
-            const size_t smem = sizeof(CnsWarpShared) * CNS_WARPS;
+            P.dp_serial = (o.min_cov < 1 || kDpTest == 2) ? 1 : 0;
+            const size_t smem = sizeof(CnsTileShared) * CNS_WARPS;
             if (smem > 48 * 1024) NB_CUDA(cx, cudaFuncSetAttribute(k_cns_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             out.tm.prep += pt.lap();
             std::unique_lock<std::mutex> gpu(sh.gpu, std::defer_lock);
             if (take_gpu) gpu.lock();
             out.tm.wait += pt.lap();
             cudaEventRecord(cx->ev2, cst);
-            // Slices of the length-sorted templates (equal total bases) alternate between two side streams: the
-            // link building of one slice overlaps the latency-bound DP chains of another; the slice with the
-            // longest templates starts first, its DP tail is hidden behind everything else.
             {
-                static const int kSlices = getenv("NB_CNS_SLICES") ? atoi(getenv("NB_CNS_SLICES")) : 1;
-                int nsl = dt.size() >= 256 ? kSlices : 1;
-                if (nsl < 1) nsl = 1;
-                if (nsl > 64) nsl = 64;
-                uint64_t total_T = 0;
-                for (const auto& ct : dt) total_T += (uint64_t)ct.T;
-                uint32_t* d_next;
-                if ((rc = D.get(&d_next, 64))) return rc;
-                NB_CUDA(cx, cudaMemsetAsync(d_next, 0, sizeof(uint32_t) * 64, cst));
-                NB_CUDA(cx, cudaEventRecord(cx->aux_ev[2], cst));
-                for (int k = 0; k < 2; ++k) NB_CUDA(cx, cudaStreamWaitEvent(cx->aux[k], cx->aux_ev[2], 0));
-                size_t a = 0;
-                uint64_t acc = 0;
-                for (int sl = 0; sl < nsl && a < dt.size(); ++sl) {
-                    size_t b = a;
-                    const uint64_t want = total_T * (uint64_t)(sl + 1) / (uint64_t)nsl;
-                    while (b < dt.size() && (acc < want || sl == nsl - 1)) { acc += (uint64_t)dt[b].T; ++b; }
-                    if (b == a) continue;
-                    cudaStream_t ss = nsl == 1 ? cst : cx->aux[sl & 1];
-                    CnsParams Q = P;
-                    Q.tpl = d_tpl + a; Q.n_tpl = (uint32_t)(b - a); Q.tpl_nseg = P.tpl_nseg + a; Q.next_tpl = d_next + sl;
-                    Q.cursor = P.cursor + (size_t)(sl & 1) * cursor_area;
-                    unsigned lg = (unsigned)((b - a + CNS_WARPS - 1) / CNS_WARPS);
-                    if (lg > links_grid) lg = links_grid;
-                    k_cns_links<<<lg, CNS_WARPS * 32, smem, ss>>>(Q);
-                    NB_LAUNCH_CHECK(cx);
-                    const unsigned dp_warps = (unsigned)(b - a);      // one warp per template; the slice is sorted by length, the longest start first
-                    if (kDpTest) k_cns_dp<3, 8><<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
-                    else k_cns_dp<32, 256><<<(dp_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
-                    NB_LAUNCH_CHECK(cx);
-                    const unsigned walk_warps = (unsigned)((b - a + Q.walk_lanes - 1) / Q.walk_lanes);
-                    k_cns_walk<<<(walk_warps + 3) / 4, 128, 0, ss>>>(Q, d_runs, d_nrun + a);
-                    NB_LAUNCH_CHECK(cx);
-                    a = b;
+                const unsigned n_tpl = (unsigned)dt.size();
+                unsigned g = (n_tpl + 3) / 4;
+                if (g > NB_SMS * 16) g = NB_SMS * 16;
+                k_cns_prep<<<g, 128, 0, cst>>>(P);
+                NB_LAUNCH_CHECK(cx);
+                g = (unsigned)((alns.size() + 3) / 4);
+                if (g > NB_SMS * 16) g = NB_SMS * 16;
+                if (g) { k_cns_ckpt<<<g, 128, 0, cst>>>(P); NB_LAUNCH_CHECK(cx); }
+                unsigned lg = (unsigned)((units.size() + CNS_WARPS - 1) / CNS_WARPS);
+                if (lg > links_grid) lg = links_grid;
+                k_cns_links<<<lg, CNS_WARPS * 32, smem, cst>>>(P);
+                NB_LAUNCH_CHECK(cx);
+                k_cns_fix<<<(unsigned)((units.size() + 127) / 128), 128, 0, cst>>>(P);
+                NB_LAUNCH_CHECK(cx);
+                // sixteen templates per CTA (8 lanes each); the chunk is sorted by length, the longest start first
+                if (kDpTest == 1) {
+                    const size_t dsm = (size_t)16 * (16 * 128 + 8 * 8);
+                    NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+                    k_cns_dp<128, 8><<<(n_tpl + 15) / 16, 128, dsm, cst>>>(P);
+                } else {
+                    const size_t dsm = (size_t)16 * (16 * 128 + 8 * 128);
+                    NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+                    k_cns_dp<128, 128><<<(n_tpl + 15) / 16, 128, dsm, cst>>>(P);
                 }
-                if (nsl > 1)
-                    for (int k = 0; k < 2; ++k) {
-                        NB_CUDA(cx, cudaEventRecord(cx->aux_ev[k], cx->aux[k]));
-                        NB_CUDA(cx, cudaStreamWaitEvent(cst, cx->aux_ev[k], 0));
-                    }
+                NB_LAUNCH_CHECK(cx);
+                k_cns_dp_serial<<<(n_tpl + 127) / 128, 128, 0, cst>>>(P);
+                NB_LAUNCH_CHECK(cx);
+                k_cns_walk<<<(n_tpl + 3) / 4, 128, 0, cst>>>(P);
+                NB_LAUNCH_CHECK(cx);
             }
             cudaEventRecord(cx->ev3, cst);
             uint32_t eflag = 0; unsigned long long cnt[4];

@@ -6,33 +6,56 @@
 // alignment column (~115 k per template), introsorts them and groups them into a
 // graph of (t_pos, delta, base) nodes with weighted links to predecessor nodes.
 //
-// Here no tag array is ever written or sorted.  One warp owns a template and
-// sweeps it in tiles of 32 template positions:
-//   phase A  for every accepted alignment (in acceptance order) the warp reads the
-//            alignment's next op bytes with lane = column, derives (t_pos, delta,
-//            base, predecessor) of each column with ballots/popcounts, and adds the
-//            alignment's weight to the matching link of that position in a
-//            shared-memory pool (per-position lists).  Columns of one alignment hit
-//            distinct (t_pos, delta) keys, alignments are processed one after the
-//            other, so every link weight is the sum in acceptance order -- the
-//            order add_one_align was called (cns_aux.c:48).
-//            At the end of a tile every position's links are written to HBM sorted by
-//            (delta, base, predecessor): k_cns_links.
-//   phase B  k_cns_dp: the best-path recurrence (cns_aux.c:157-184) is a chain over
-//            template positions with ~4 links each -- no intra-template parallelism
-//            worth a warp -- so it runs one THREAD per template, tens of thousands
-//            of templates in flight; per (t_pos, delta) level an 11-bit back pointer
-//            per node is packed into one u64.  At the end of a coverage run the same
-//            thread walks the back pointers (cns_aux.c:187-212) and emits the bases.
+// Here no tag array is ever written or sorted, and no kernel is a chain over a whole template except the
+// best-path recurrence itself (which is one by definition):
+//   k_cns_prep   one warp per template: coverage of every position, the coverage runs that get a consensus
+//                (cbcns.c:129-135), the run table.
+//   k_cns_ckpt   one warp per accepted alignment: the alignment's cursor (column, query position, node of the
+//                previous column) at every span boundary it crosses -- a span is CNS_SPAN template positions --
+//                and the number of its columns inside each span.  With these, the spans of a template are
+//                independent pieces of work.
+//   k_cns_links  one warp per (template, span), taken from a queue: tiles of CNS_TILE positions; for every
+//                alignment that touches the tile (in acceptance order) the warp reads the alignment's next op
+//                bytes with lane = column, derives (t_pos, delta, base, predecessor) of each column with
+//                ballots/popcounts, and adds the alignment's weight to the matching link of that position in a
+//                shared-memory slot table.  Columns of one alignment hit distinct (t_pos, delta) keys and the
+//                alignments are processed one after the other, so every link weight is the sum in acceptance
+//                order -- the order add_one_align was called (cns_aux.c:48).  At the end of a tile every
+//                position's links are written to HBM sorted by (delta, base, predecessor), the weight already
+//                reduced by the coverage penalty (cns_aux.c:164), the predecessor node resolved to a link index.
+//   k_cns_fix    the predecessor indices of the first position of every span (its predecessor position belongs
+//                to another warp's span).
+//   k_cns_dp     the best-path recurrence (cns_aux.c:157-184): 8 lanes per template (lane = link of the current
+//                delta level), four templates per warp in lock step, links streamed through a cp.async ring,
+//                node scores in a shared-memory ring; per level one 16-byte record with the five 11-bit back
+//                pointers.  A template whose predecessor falls out of the score ring is redone by
+//                k_cns_dp_serial (scores in HBM).
+//   k_cns_walk   the walk over the back pointers (cns_aux.c:187-212), level records staged through shared
+//                memory a window at a time.
 #pragma once
 #include "nb_common.cuh"
 #include "nb_extend.cuh"
 
 #define CNS_MAX_ALN 320         // >= MAX_EXAMINED_CAN (consensus_aux.h:15)
 #define CNS_WARPS 4
-#define CNS_POOL 768            // links per tile (shared-memory pool; ~115 used on average)
+#ifndef CNS_TILE
+#define CNS_TILE 64             // template positions per tile of k_cns_links (multiple of 32)
+#endif
+#define CNS_SPAN_DEFAULT 1024   // template positions per unit of k_cns_links (multiple of CNS_TILE)
+#define CNS_SLOTS 8             // links of one position kept in the slot table (more: the overflow chain)
+#define CNS_OV 4096             // overflow links per tile (a pool in HBM per resident warp: crowded positions are rare)
 #define CNS_NOPRED 0xffffffffu
-#define CNS_FLUSH_REGS 8        // links of one position sorted in registers at the flush (more: the list-walking flush)
+#define CNS_PRED_OPEN 0xC0000000u   // | node id wanted at the previous position: resolved by k_cns_fix
+#define CNS_TILE_ROUNDS (CNS_TILE / 32)
+
+// link key: delta(8) << 24 | node-start << 23 | base(3) << 20 | level-start << 19 | pred base(3) << 16 |
+//           run-first << 15 | run-last << 14 | pred rank(11)
+#define CNS_K_NODE     (1u << 23)
+#define CNS_K_LEVEL    (1u << 19)
+#define CNS_K_RUNFIRST (1u << 15)      // on the first link of the first position of a coverage run
+#define CNS_K_RUNLAST  (1u << 14)      // on the first link of the last position of a coverage run
+#define CNS_K_RANK(k)  ((k) & 0x7ffu)
+#define CNS_K_SORTMASK 0xff77ffffu     // the bits links are ordered by (flags are added after sorting)
 
 struct CnsAln {                 // one accepted alignment, in acceptance order
     const uint8_t* ops;
@@ -42,7 +65,9 @@ struct CnsAln {                 // one accepted alignment, in acceptance order
     int32_t  qlen, qdir;
     double   weight;
     int32_t  drop;              // 1 = a run of >= 255 insertions: the alignment produces no tags (align_tags.c:40-44; found by k_extend)
-    int32_t  pad_;
+    uint32_t ckpt_first;        // first of its span-boundary checkpoints
+    uint32_t unit_first;        // first unit (span) of its template
+    uint32_t pad_;
 };
 
 struct CnsTemplate {
@@ -56,25 +81,34 @@ struct CnsTemplate {
     uint64_t link_base;         // into link[]   (link_cap records)
     uint64_t level_base;        // into bp / rev (level_cap slots)
     uint32_t link_cap, level_cap;
+    uint32_t unit_first;        // first unit (span) of this template: ceil(T / span) units
+    uint32_t pad_;
+};
+
+struct CnsUnit { uint32_t tpl, span; };      // one piece of work of k_cns_links
+
+struct __align__(16) CnsCkpt {  // cursor of an alignment at a span boundary b: describes column x - 1, x = first column at position b
+    uint32_t x, qpos;
+    uint32_t last_node;         // delta << 3 | base of column x - 1
+    uint32_t pad_;
 };
 
 struct __align__(16) CnsPos {   // one template position
-    uint32_t start;             // first link (relative to link_base); pos[T].start = total
+    uint32_t start;             // first link (relative to link_base)
     int32_t  cov;               // tag-producing alignments covering it (cns_aux.c:96-98)
     uint32_t flags;             // 1 = in a scored run, 2 = first of run, 4 = last of run
-    uint32_t first_level;       // level index of (t, delta 0), written by k_cns_dp
+    uint32_t n;                 // number of links
 };
 
 struct __align__(16) CnsLink {  // one link = (node, predecessor node), sorted by key inside a position
-    uint32_t key;               // delta(8) << 24 | node-start << 23 | base(3) << 20 | level-start << 19 | pred base(3) << 16 | pred rank(16)
-    uint32_t pred;              // index of the predecessor node's first link, CNS_NOPRED = no scored predecessor
-    double   w;                 // summed weight; k_cns_dp overwrites the first link of a node with the node score
+    uint32_t key;
+    uint32_t pred;              // index of the predecessor node's first link (relative to link_base), CNS_NOPRED = no scored predecessor
+    double   w;                 // summed weight minus the coverage penalty; k_cns_dp_serial overwrites the first link of a node with the node score
 };
 
 struct __align__(16) CnsLevel { // one (position, delta) level of the best-path recurrence, written by k_cns_dp for k_cns_walk
-    unsigned long long packed;  // 5 x 11-bit back pointers, one per base: predecessor delta << 3 | predecessor base, 7 = none
+    uint16_t code[6];           // per base: back pointer = predecessor delta << 3 | predecessor base, 7 = none (only the bases that have a node are written)
     uint32_t prev_first_level;  // level index of (position - 1, delta 0): the walk needs no second load per step
-    uint32_t pad_;
 };
 
 struct CnsSegment {             // one consensus stretch of >= min_size bases
@@ -85,43 +119,49 @@ struct CnsSegment {             // one consensus stretch of >= min_size bases
     uint64_t seq_off;           // into the sequence pool (base codes 0..3)
 };
 
+struct CnsRun {                 // one coverage run of a template: k_cns_prep writes [from, to), k_cns_dp the rest
+    int32_t from, to;
+    int32_t g_level, g_b, g_t, g_delta;     // best node of the run (cns_aux.c:177-184), g_level < 0: none
+    uint32_t first_level;       // level of (from, delta 0)
+    uint32_t pad_;
+};
+
 struct __align__(16) CnsCursor {    // per alignment cursor of k_cns_links (describes column x-1), kept in HBM/L1 per resident warp
     uint32_t x, qpos;
     int32_t  last_pos;
-    uint16_t last_node;             // delta << 3 | base of column x-1; 0xffff = none
-    uint8_t  valid, pad_;
+    uint32_t last_node;             // delta << 3 | base of column x-1; 0xffff = none
 };
 
 struct CnsParams {
     const uint8_t*     pac;
     const CnsTemplate* tpl;
     const CnsAln*      aln;
-    uint32_t           n_tpl;
+    uint32_t           n_tpl, n_aln;
     CnsSegment*        seg;
     uint32_t*          tpl_nseg;        // [n_tpl]
     uint8_t*           seq_pool;
-    uint32_t*          next_tpl;        // work queue of k_cns_links
+    const CnsUnit*     unit;            // work list of k_cns_links, longest templates first
+    uint32_t           n_units;
+    int                span;            // positions per unit
+    uint32_t*          span_cols;       // [n_units] alignment columns inside the span = capacity of its link region
+    uint2*             span_links;      // [n_units] (first link, number of links) written by k_cns_links
+    CnsCkpt*           ckpt;
+    uint32_t*          next_unit;       // work queue of k_cns_links
     CnsPos*            pos;
     CnsLink*           link;
     CnsCursor*         cursor;          // k_cns_links: [resident warps][CNS_MAX_ALN]
+    uint4*             ovpool;          // k_cns_links: [resident warps][CNS_OV] overflow links (key, next, weight)
     CnsLevel*          bp;              // per level: 5 x 11-bit back pointers + where the previous position's levels start
     uint8_t*           rev;
+    CnsRun*            runs;
+    uint32_t*          tpl_nrun;        // [n_tpl]
+    uint32_t*          redo;            // [n_tpl] templates k_cns_dp hands to k_cns_dp_serial
+    uint32_t*          n_redo;
     int                min_cov, min_size;
-    int                lanes;           // k_cns_dp: templates per warp (the other lanes idle)
-    int                walk_lanes;      // k_cns_walk: likewise
     int                flush_slow;      // k_cns_links: 1 = always take the list-walking flush (tests)
-    int                links_multi;     // k_cns_links: 1 = reload / store the alignment state every tile even for <= 32 alignments (tests)
+    int                dp_serial;       // 1 = every template goes to k_cns_dp_serial (min_cov < 1: runs may hold positions without links; tests)
     uint32_t*          error_flag;      // 1 = level capacity, 2 = link pool / link capacity, 4 = output capacity
-    unsigned long long* counters;       // [0] levels, [1] columns (tags), [2] links
-};
-
-struct __align__(16) CnsWarpShared {
-    // links of the current tile: per-position singly linked lists
-    uint32_t e_key[CNS_POOL];
-    double   e_w[CNS_POOL];
-    uint16_t e_next[CNS_POOL];
-    uint32_t head[32];
-    uint32_t pool_used;
+    unsigned long long* counters;       // [0] levels, [1] columns (tags), [2] links, [3] links that went through the overflow pool
 };
 
 __device__ __forceinline__ int cns_qbase(const uint8_t* __restrict__ pac, uint64_t qseq_off, int qlen, int qdir, uint32_t qpos)
@@ -134,42 +174,23 @@ __device__ __forceinline__ int cns_qbase(const uint8_t* __restrict__ pac, uint64
 // rank of a base in the reference's tag order (ASCII: '-' < 'A' < 'C' < 'G' < 'T')
 __device__ __forceinline__ uint32_t cns_char_rank(uint32_t b) { return b == 4 ? 0u : b + 1u; }
 
-// ------------------------------------------------------------------ phase A
-__global__ void __launch_bounds__(CNS_WARPS * 32)
-k_cns_links(CnsParams P)
+// ------------------------------------------------------------------ coverage, runs
+__global__ void __launch_bounds__(128)
+k_cns_prep(CnsParams P)
 {
-    extern __shared__ __align__(16) uint8_t cns_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1, le_mask = lt_mask | (1u << lane);
-    CnsWarpShared& S = reinterpret_cast<CnsWarpShared*>(cns_smem)[wid];
-    CnsCursor* CU = P.cursor + ((size_t)blockIdx.x * CNS_WARPS + wid) * CNS_MAX_ALN;
-    const bool kFlushSlow = P.flush_slow != 0;
-    unsigned long long n_cols_total = 0, n_links_total = 0;
-
-    for (;;) {
-        uint32_t ti = 0;
-        if (lane == 0) ti = atomicAdd(P.next_tpl, 1u);
-        ti = __shfl_sync(0xffffffffu, ti, 0);
-        if (ti >= P.n_tpl) break;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwarp = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t ti = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ti < P.n_tpl; ti += nwarp) {
         const CnsTemplate TP = P.tpl[ti];
         const CnsAln* AL = P.aln + TP.aln_first;
         const int A = (int)TP.n_aln, T = TP.T;
         CnsPos* pos = P.pos + TP.pos_base;
-        CnsLink* link = P.link + TP.link_base;
-        uint32_t fail = 0;
-
-        // ---- 0. cursors; an insertion run of >= 255 drops the whole alignment (align_tags.c:40-44; flagged by k_extend)
-        for (int a = lane; a < A; a += 32) {
-            CnsCursor c; c.x = 0; c.qpos = (uint32_t)AL[a].qstart; c.last_pos = AL[a].toff - 1; c.last_node = 0xffff;
-            c.valid = (uint8_t)!AL[a].drop; c.pad_ = 0;
-            CU[a] = c;
-        }
+        CnsRun* runs = P.runs + TP.seg_first;
+        for (int t = lane; t <= T; t += 32) { CnsPos z; z.start = 0; z.cov = 0; z.flags = 0; z.n = 0; pos[t] = z; }
         __syncwarp();
-        // ---- 1. coverage
-        for (int t = lane; t <= T; t += 32) { CnsPos z; z.start = 0; z.cov = 0; z.flags = 0; z.first_level = 0; pos[t] = z; }
-        __syncwarp();
+        // an insertion run of >= 255 drops the whole alignment (align_tags.c:40-44; flagged by k_extend)
         for (int a = lane; a < A; a += 32)
-            if (CU[a].valid) { atomicAdd(&pos[AL[a].toff].cov, 1); atomicAdd(&pos[AL[a].tend].cov, -1); }
+            if (!AL[a].drop) { atomicAdd(&pos[AL[a].toff].cov, 1); atomicAdd(&pos[AL[a].tend].cov, -1); }
         __syncwarp();
         {
             int carry = 0;
@@ -184,628 +205,943 @@ k_cns_links(CnsParams P)
             }
         }
         __syncwarp();
-        // ---- 2. coverage runs that get a consensus (cbcns.c:129-135)
-        {
-            int i = 0;
-            while (i < T) {
-                for (;;) {
-                    const int t = i + lane;
-                    const uint32_t low = __ballot_sync(0xffffffffu, t < T && pos[t].cov < P.min_cov);
-                    if (low == 0xffffffffu) { i += 32; continue; }
-                    i += __ffs(~low) - 1;
-                    break;
-                }
-                if (i > T) i = T;
-                int j = i + 1;
-                for (;;) {
-                    const int t = j + lane;
-                    const uint32_t hi = __ballot_sync(0xffffffffu, t < T && pos[t].cov >= P.min_cov);
-                    if (hi == 0xffffffffu) { j += 32; continue; }
-                    j += __ffs(~hi) - 1;
-                    break;
-                }
-                if (i < T && (double)(j - i) >= __dmul_rn((double)P.min_size, 0.85)) {
-                    for (int t = i + lane; t < j; t += 32) pos[t].flags = 1u | (t == i ? 2u : 0u) | (t == j - 1 ? 4u : 0u);
-                }
-                i = j;
+        // coverage runs that get a consensus (cbcns.c:129-135)
+        uint32_t nrun = 0;
+        int i = 0;
+        while (i < T) {
+            for (;;) {
+                const int t = i + lane;
+                const uint32_t low = __ballot_sync(0xffffffffu, t < T && pos[t].cov < P.min_cov);
+                if (low == 0xffffffffu) { i += 32; continue; }
+                i += __ffs(~low) - 1;
+                break;
             }
+            if (i > T) i = T;
+            int j = i + 1;
+            for (;;) {
+                const int t = j + lane;
+                const uint32_t hi = __ballot_sync(0xffffffffu, t < T && pos[t].cov >= P.min_cov);
+                if (hi == 0xffffffffu) { j += 32; continue; }
+                j += __ffs(~hi) - 1;
+                break;
+            }
+            if (i < T && (double)(j - i) >= __dmul_rn((double)P.min_size, 0.85)) {
+                for (int t = i + lane; t < j; t += 32) pos[t].flags = 1u | (t == i ? 2u : 0u) | (t == j - 1 ? 4u : 0u);
+                if (lane == 0 && nrun < TP.seg_cap) {
+                    CnsRun r; r.from = i; r.to = j; r.g_level = -1; r.g_b = -1; r.g_t = 0; r.g_delta = 0; r.first_level = 0; r.pad_ = 0;
+                    runs[nrun] = r;
+                }
+                ++nrun;
+            }
+            i = j;
+        }
+        if (lane == 0) {
+            if (nrun > TP.seg_cap) { atomicOr(P.error_flag, 4u); nrun = TP.seg_cap; }
+            P.tpl_nrun[ti] = nrun;
         }
         __syncwarp();
+    }
+}
 
-        // ---- 3. tile sweep: links of 32 positions at a time, alignments in acceptance order
-        uint32_t r_x = 0, r_qp = 0, r_ln = 0xffff, r_ql = 0;       // lane a < 32: cursor and description of alignment a
-        int r_lp = 0, r_n = 0, r_toff = 0, r_tend = 0;
-        const uint8_t* r_ops = NULL;
-        uint64_t r_qso = 0;
-        double r_w = 0.0;
-        bool r_valid = false;
-        // Up to 32 alignments: their state stays in these registers for the whole template.  More (long templates): the
-        // alignments are taken 32 at a time, every tile loads a group's state from HBM / L1 (coalesced, lane = alignment)
-        // and stores the cursors back afterwards.
-        const bool multi = A > 32 || P.links_multi;
-        auto load_group = [&](int g0) {
-            const int a = g0 + lane;
-            r_valid = false; r_toff = 0; r_tend = 0;
-            if (a < A) {
-                const CnsAln al = AL[a];
-                const CnsCursor cu = CU[a];
-                r_ops = al.ops; r_n = al.aln_size; r_toff = al.toff; r_tend = al.tend; r_qso = al.qseq_off;
-                r_ql = (uint32_t)al.qlen | ((uint32_t)al.qdir << 31); r_w = al.weight;
-                r_valid = cu.valid != 0;
-                r_x = cu.x; r_qp = cu.qpos; r_lp = cu.last_pos; r_ln = cu.last_node;
-            }
-        };
-        if (!multi) load_group(0);
-        uint32_t ebase = 0;                     // links written so far
-        uint32_t prev_start = 0, prev_cnt = 0;  // links of the last position of the previous tile
-        uint32_t prev_nid[CNS_FLUSH_REGS];      // ... and their node ids in key order, when the fast flush left them (prev_fast)
-        bool prev_fast = false;
-#pragma unroll
-        for (int j = 0; j < CNS_FLUSH_REGS; ++j) prev_nid[j] = 0xfffu;
-        for (int t0 = 0; t0 < T && !fail; t0 += 32) {
-            const int t1 = (t0 + 32 < T) ? t0 + 32 : T;
-            const uint32_t tile_flag = (t0 + lane < T) ? pos[t0 + lane].flags : 0;
-            const uint32_t tile_any = __ballot_sync(0xffffffffu, tile_flag & 1);
-            if (lane == 0) S.pool_used = 0;
-            S.head[lane] = 0xffffu;
-            __syncwarp();
-            // Columns [x, ..) of one alignment that fall on this tile: derive (position, delta, base, predecessor) of
-            // each column with ballots, add the alignment's weight to the matching link.  cur0 / cur1 are the op bytes
-            // of columns x + lane and x + 32 + lane when `pre` says they were fetched ahead of time.
-            auto sweep = [&](const uint8_t* __restrict__ ops, const int n, const uint64_t qso, const int qlen, const int qdir, const double w,
-                             uint32_t& x, uint32_t& qp, int& last_pos, uint32_t& last_node, const bool pre, const int cur0, const int cur1,
-                             const uint32_t cur_pac, const long long pac_lo) {
-                for (int it = 0; x < (uint32_t)n; ++it) {
-                    const uint32_t c = x + lane;
-                    const bool ok = c < (uint32_t)n;
-                    int op;
-                    if (pre && it == 0) op = cur0;
-                    else if (pre && it == 1) op = cur1;
-                    else op = ok ? ops[c] : OP_TONLY;
-                    const uint32_t tmask = __ballot_sync(0xffffffffu, ok && op != OP_QONLY);
-                    const uint32_t qmask = __ballot_sync(0xffffffffu, ok && op != OP_TONLY);
-                    const uint32_t vmask = __ballot_sync(0xffffffffu, ok);
-                    const uint32_t tle = tmask & le_mask;
-                    const int k = __popc(tle);
-                    const int ps = last_pos + k;
-                    const int delta = (k == 0) ? (int)(last_node >> 3) + lane + 1 : lane - (31 - __clz(tle));
-                    const uint32_t late = __ballot_sync(0xffffffffu, ok && ps >= t1);    // columns of later tiles
-                    const int n_take = late ? __ffs(late) - 1 : __popc(vmask);
-                    if (n_take == 0) break;
-                    const bool take = lane < n_take;
-                    int b = 4;
-                    if (pre && it < 2) {
-                        // lanes 0..16 hold the 17 bytes of packed query bases around the cursor (fetched with the ops)
-                        const uint32_t q = qp + __popc(qmask & lt_mask);
-                        const long long p = qdir ? (long long)qso + (qlen - 1 - (int)q) : (long long)qso + q;
-                        const bool want = take && op != OP_TONLY;
-                        const uint32_t byte = __shfl_sync(0xffffffffu, cur_pac, want ? (int)((p >> 2) - pac_lo) : 0);
-                        if (want) { b = (byte >> (((~p) & 3) << 1)) & 3; if (qdir) b = 3 - b; }
-                    } else if (take && op != OP_TONLY) b = cns_qbase(P.pac, qso, qlen, qdir, qp + __popc(qmask & lt_mask));
-                    const uint32_t node = ((uint32_t)delta << 3) | (uint32_t)b;
-                    uint32_t pnode = __shfl_up_sync(0xffffffffu, node, 1);
-                    if (lane == 0) pnode = last_node;
-                    const int pl = ps - t0;
-                    const bool ins = take && pl >= 0 && ((tile_any >> (pl & 31)) & 1);   // position inside a scored run
-                    uint32_t key = 0;
-                    int e = 0xffff;
-                    if (ins) {
-                        uint32_t rank, pb;
-                        if (pnode == 0xffff) { rank = 0; pb = 7; }
-                        else { pb = pnode & 7; rank = 1 + (delta == 0 ? (pnode >> 3) * 5u : 0u) + cns_char_rank(pb); }
-                        key = ((uint32_t)delta << 24) | ((uint32_t)b << 20) | (pb << 16) | rank;
-                        e = (int)S.head[pl];
-                        while (e != 0xffff && S.e_key[e] != key) e = S.e_next[e];
-                    }
-                    __syncwarp();
-                    if (ins) {
-                        if (e != 0xffff) S.e_w[e] = __dadd_rn(S.e_w[e], w);        // acceptance order (cns_aux.c:48)
-                        else {
-                            const uint32_t ne = atomicAdd(&S.pool_used, 1u);
-                            if (ne < CNS_POOL) {
-                                S.e_key[ne] = key; S.e_w[ne] = w;
-                                S.e_next[ne] = (uint16_t)atomicExch(&S.head[pl], ne);
-                            }
-                        }
-                        ++n_cols_total;
-                    }
-                    const int lastl = n_take - 1;
-                    last_pos = __shfl_sync(0xffffffffu, ps, lastl);
-                    last_node = __shfl_sync(0xffffffffu, node, lastl);
-                    qp += __popc(qmask & ((n_take >= 32) ? 0xffffffffu : ((1u << n_take) - 1)));
-                    x += (uint32_t)n_take;
-                    __syncwarp();
-                    if (n_take < 32) break;
-                }
+// ------------------------------------------------------------------ span-boundary checkpoints
+__global__ void __launch_bounds__(128)
+k_cns_ckpt(CnsParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1, le_mask = lt_mask | (1u << lane);
+    const uint32_t nwarp = gridDim.x * (blockDim.x >> 5);
+    const int span = P.span;
+    for (uint32_t ai = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ai < P.n_aln; ai += nwarp) {
+        const CnsAln al = P.aln[ai];
+        if (al.drop) continue;
+        const uint8_t* __restrict__ ops = al.ops;
+        const uint32_t n = (uint32_t)al.aln_size;
+        int sp = al.toff / span;                        // span of the columns seen so far
+        int b = (sp + 1) * span;                        // next boundary
+        uint32_t x = 0, qp = (uint32_t)al.qstart, last_d = 0xffffu >> 3, x_b = 0, nck = 0;      // last_d: delta of column x - 1
+        int last_pos = al.toff - 1;
+        while (x < n) {
+            const uint32_t c = x + lane;
+            const bool ok = c < n;
+            const int op = ok ? ops[c] : OP_TONLY;
+            const uint32_t tmask = __ballot_sync(0xffffffffu, ok && op != OP_QONLY);
+            const uint32_t qmask = __ballot_sync(0xffffffffu, ok && op != OP_TONLY);
+            const int ps = last_pos + __popc(tmask & le_mask);
+            const uint32_t cross = __ballot_sync(0xffffffffu, ok && ps >= b);
+            const int nv = n - x < 32 ? (int)(n - x) : 32;
+            // delta of column x + l1 (l1 < nv)
+            auto delta_of = [&](int l1) -> uint32_t {
+                const uint32_t tl1 = tmask & ((2u << l1) - 1);                              // t-consuming columns up to l1
+                return tl1 == 0 ? last_d + (uint32_t)l1 + 1u : (uint32_t)(l1 - (31 - __clz(tl1)));
             };
-            // cursor and description of an alignment live in the registers of lane a (mod 32); the op bytes and query bases
-            // of the next alignment are fetched while the current one is processed
-            for (int g0 = 0; g0 < A; g0 += 32) {
-                if (multi) load_group(g0);
-                uint32_t amask = __ballot_sync(0xffffffffu, r_valid && r_toff < t1 && r_tend > t0);
-                int a = amask ? __ffs(amask) - 1 : -1;
-                int pre0 = OP_TONLY, pre1 = OP_TONLY;
-                uint32_t pre_pac = 0;
-                long long pre_lo = 0;
-                auto fetch = [&](int an) {
-                    const uint32_t fx = __shfl_sync(0xffffffffu, r_x, an);
-                    const uint32_t fn = (uint32_t)__shfl_sync(0xffffffffu, r_n, an);
-                    const uint8_t* fo = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, (unsigned long long)r_ops, an));
-                    const uint32_t c = fx + lane;
-                    pre0 = c < fn ? fo[c] : OP_TONLY;
-                    pre1 = c + 32 < fn ? fo[c + 32] : OP_TONLY;
-                    // packed query bases [qp, qp + 64) of that alignment: 17 bytes, one per lane
-                    const uint32_t fq = __shfl_sync(0xffffffffu, r_qp, an), fl = __shfl_sync(0xffffffffu, r_ql, an);
-                    const long long fso = (long long)__shfl_sync(0xffffffffu, (unsigned long long)r_qso, an);
-                    long long lo = (fl >> 31) ? fso + ((int)(fl & 0x7fffffffu) - 1 - (int)(fq + 63)) : fso + fq;
-                    if (lo < 0) lo = 0;
-                    pre_lo = lo >> 2;
-                    pre_pac = lane <= 16 ? __ldg(P.pac + pre_lo + lane) : 0u;
-                };
-                if (a >= 0) fetch(a);
-                while (a >= 0) {
-                    amask &= amask - 1;
-                    const int nxt = amask ? __ffs(amask) - 1 : -1;
-                    uint32_t x = __shfl_sync(0xffffffffu, r_x, a), qp = __shfl_sync(0xffffffffu, r_qp, a);
-                    int last_pos = __shfl_sync(0xffffffffu, r_lp, a);
-                    uint32_t last_node = __shfl_sync(0xffffffffu, r_ln, a);
-                    const uint8_t* ops = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, (unsigned long long)r_ops, a));
-                    const int n = __shfl_sync(0xffffffffu, r_n, a);
-                    const uint64_t qso = __shfl_sync(0xffffffffu, (unsigned long long)r_qso, a);
-                    const uint32_t ql = __shfl_sync(0xffffffffu, r_ql, a);
-                    const double w = __shfl_sync(0xffffffffu, r_w, a);
-                    const int cur0 = pre0, cur1 = pre1;
-                    const uint32_t cur_pac = pre_pac;
-                    const long long cur_lo = pre_lo;
-                    if (nxt >= 0) fetch(nxt);
-                    sweep(ops, n, qso, (int)(ql & 0x7fffffffu), (int)(ql >> 31), w, x, qp, last_pos, last_node, true, cur0, cur1, cur_pac, cur_lo);
-                    if (lane == a) { r_x = x; r_qp = qp; r_lp = last_pos; r_ln = last_node; }
-                    a = nxt;
+            if (cross) {
+                // column x + L is the first one at position b; its checkpoint describes column x + L - 1
+                const int L = __ffs(cross) - 1;
+                uint32_t d1, q1;                            // delta and query index of column x + L - 1
+                int op1;
+                if (L > 0) { d1 = delta_of(L - 1); op1 = __shfl_sync(0xffffffffu, op, L - 1); q1 = qp + __popc(qmask & ((1u << (L - 1)) - 1)); }
+                else { d1 = last_d; op1 = x > 0 ? ops[x - 1] : OP_TONLY; q1 = qp - 1; }
+                int bb = 4;
+                if (op1 != OP_TONLY) bb = cns_qbase(P.pac, al.qseq_off, al.qlen, al.qdir, q1);
+                if (lane == 0) {
+                    CnsCkpt ck; ck.x = x + (uint32_t)L; ck.qpos = qp + __popc(qmask & ((1u << L) - 1)); ck.last_node = (d1 << 3) | (uint32_t)bb; ck.pad_ = 0;
+                    P.ckpt[al.ckpt_first + nck] = ck;
+                    atomicAdd(P.span_cols + al.unit_first + sp, x + (uint32_t)L - x_b);
                 }
-                if (multi) {
-                    if (g0 + lane < A) {
-                        CnsCursor c; c.x = r_x; c.qpos = r_qp; c.last_pos = r_lp; c.last_node = (uint16_t)r_ln; c.valid = (uint8_t)r_valid; c.pad_ = 0;
-                        CU[g0 + lane] = c;
+                x_b = x + (uint32_t)L; ++nck; ++sp; b += span;
+            }
+            last_d = delta_of(nv - 1);
+            last_pos += __popc(tmask);
+            qp += __popc(qmask);
+            x += (uint32_t)nv;
+        }
+        if (lane == 0) atomicAdd(P.span_cols + al.unit_first + sp, n - x_b);
+    }
+}
+
+// ------------------------------------------------------------------ links
+struct __align__(16) CnsTileShared {
+    double   w[CNS_TILE][CNS_SLOTS];
+    uint32_t key[CNS_TILE][CNS_SLOTS];
+    uint32_t cnt[CNS_TILE];
+    uint32_t ov_head[CNS_TILE];
+    uint32_t ord[CNS_TILE];             // flush: slot of the i-th link in key order, 4 bits each
+    uint32_t carry_key[CNS_SLOTS];      // keys of the last position of the previous tile (carry_cnt of them; 0xffff: read them from HBM)
+    uint16_t aidx[CNS_MAX_ALN];
+    uint32_t ov_used;
+    uint32_t carry_cnt;
+    uint32_t pad_[2];
+};
+
+__global__ void __launch_bounds__(CNS_WARPS * 32)
+k_cns_links(CnsParams P)
+{
+    extern __shared__ __align__(16) uint8_t cns_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1, le_mask = lt_mask | (1u << lane);
+    CnsTileShared& S = reinterpret_cast<CnsTileShared*>(cns_smem)[wid];
+    CnsCursor* CU = P.cursor + ((size_t)blockIdx.x * CNS_WARPS + wid) * CNS_MAX_ALN;
+    uint4* OV = P.ovpool + ((size_t)blockIdx.x * CNS_WARPS + wid) * CNS_OV;     // x = key, y = next, (z, w) = weight
+    const bool kFlushSlow = P.flush_slow != 0;
+    const int span = P.span;
+    unsigned long long n_cols_total = 0, n_links_total = 0, n_ov_total = 0;
+
+    for (;;) {
+        uint32_t ui = 0;
+        if (lane == 0) ui = atomicAdd(P.next_unit, 1u);
+        ui = __shfl_sync(0xffffffffu, ui, 0);
+        if (ui >= P.n_units) break;
+        const CnsUnit U = P.unit[ui];
+        const CnsTemplate TP = P.tpl[U.tpl];
+        const CnsAln* __restrict__ AL = P.aln + TP.aln_first;
+        const int A = (int)TP.n_aln, T = TP.T;
+        CnsPos* pos = P.pos + TP.pos_base;
+        CnsLink* link = P.link + TP.link_base;
+        const int s0 = (int)U.span * span, s1 = (s0 + span < T) ? s0 + span : T;
+        uint32_t fail = 0;
+        // ---- link region of this span: behind the regions of the template's earlier spans
+        uint32_t lb = 0;
+        for (uint32_t j = lane; j < U.span; j += 32) lb += P.span_cols[TP.unit_first + j];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) lb += __shfl_xor_sync(0xffffffffu, lb, d);
+        const uint32_t cap = P.span_cols[TP.unit_first + U.span];
+        // ---- nothing to do where no position of the span is in a scored run (k_cns_prep left start = n = 0)
+        {
+            bool any = false;
+            for (int t = s0 + lane; t < s1; t += 32) any |= (pos[t].flags & 1u) != 0;
+            if (!__any_sync(0xffffffffu, any)) {
+                if (lane == 0) P.span_links[TP.unit_first + U.span] = make_uint2(lb, 0u);
+                continue;
+            }
+        }
+        // ---- the alignments that touch the span, in acceptance order, and their cursors at its start
+        int n_ov = 0;
+        for (int a0 = 0; a0 < A; a0 += 32) {
+            const int a = a0 + lane;
+            bool ov = false;
+            int toff = 0;
+            if (a < A) { toff = AL[a].toff; ov = !AL[a].drop && toff < s1 && AL[a].tend > s0; }
+            const uint32_t m = __ballot_sync(0xffffffffu, ov);
+            if (ov) {
+                const int idx = n_ov + __popc(m & lt_mask);
+                S.aidx[idx] = (uint16_t)a;
+                CnsCursor c;
+                if (toff >= s0) { c.x = 0; c.qpos = (uint32_t)AL[a].qstart; c.last_pos = toff - 1; c.last_node = 0xffff; }
+                else {
+                    const CnsCkpt ck = P.ckpt[AL[a].ckpt_first + (uint32_t)((int)U.span - toff / span - 1)];
+                    c.x = ck.x; c.qpos = ck.qpos; c.last_pos = s0 - 1; c.last_node = ck.last_node;
+                }
+                CU[idx] = c;
+            }
+            n_ov += __popc(m);
+        }
+        __syncwarp();
+        // up to 32 alignments: their extent stays in registers (lane = alignment of the compacted list)
+        int r_toff = 0x7fffffff, r_tend = 0;
+        if (lane < n_ov) { const CnsAln& al = AL[S.aidx[lane]]; r_toff = al.toff; r_tend = al.tend; }
+
+        uint32_t ebase = 0;                     // links written so far (relative to lb)
+        uint32_t prev_start = 0, prev_cnt = 0;  // links of the last position of the previous tile
+        for (int t0 = s0; t0 < s1 && !fail; t0 += CNS_TILE) {
+            const int t1 = (t0 + CNS_TILE < s1) ? t0 + CNS_TILE : s1;
+            uint4 tile_pos[CNS_TILE_ROUNDS];    // my positions of the tile: t0 + 32 r + lane
+            uint32_t tile_run[CNS_TILE_ROUNDS]; // bit l of word r: position t0 + 32 r + l is in a scored run
+#pragma unroll
+            for (int r = 0; r < CNS_TILE_ROUNDS; ++r) {
+                const int t = t0 + 32 * r + lane;
+                tile_pos[r] = t < t1 ? *reinterpret_cast<const uint4*>(pos + t) : make_uint4(0, 0, 0, 0);
+                tile_run[r] = __ballot_sync(0xffffffffu, tile_pos[r].z & 1u);
+                S.cnt[32 * r + lane] = 0; S.ov_head[32 * r + lane] = 0xffffu;
+            }
+            if (lane == 0) S.ov_used = 0;
+            uint32_t any_run = 0;
+#pragma unroll
+            for (int r = 0; r < CNS_TILE_ROUNDS; ++r) any_run |= tile_run[r];
+            __syncwarp();
+            if (any_run) {
+            // ---- accumulate: the alignments that touch the tile, in acceptance order
+            for (int g0 = 0; g0 < n_ov; g0 += 32) {
+                if (g0 > 0 || n_ov > 32) {
+                    r_toff = 0x7fffffff; r_tend = 0;
+                    if (g0 + lane < n_ov) { const CnsAln& al = AL[S.aidx[g0 + lane]]; r_toff = al.toff; r_tend = al.tend; }
+                }
+                uint32_t amask = __ballot_sync(0xffffffffu, r_toff < t1 && r_tend > t0);
+                while (amask) {
+                    const int ci = g0 + __ffs(amask) - 1;
+                    amask &= amask - 1;
+                    const CnsAln al = AL[S.aidx[ci]];
+                    const CnsCursor cu = CU[ci];
+                    const uint8_t* __restrict__ ops = al.ops;
+                    const uint32_t n = (uint32_t)al.aln_size;
+                    const uint64_t qso = al.qseq_off;
+                    const int qlen = al.qlen, qdir = al.qdir;
+                    const double w = al.weight;
+                    uint32_t x = cu.x, qp = cu.qpos, last_node = cu.last_node;
+                    int last_pos = cu.last_pos;
+                    int op = (x + lane < n) ? ops[x + lane] : OP_TONLY;
+                    while (x < n) {
+                        const uint32_t c = x + lane;
+                        const bool ok = c < n;
+                        const int op_nx = (c + 32 < n) ? ops[c + 32] : OP_TONLY;       // the next chunk, should this one be taken whole
+                        // packed query bases [qp, qp + 32): 9 bytes, one per lane
+                        long long lo = qdir ? (long long)qso + (qlen - 1 - (int)(qp + 31)) : (long long)qso + qp;
+                        if (lo < 0) lo = 0;
+                        const long long pac_lo = lo >> 2;
+                        const uint32_t pacb = lane <= 8 ? __ldg(P.pac + pac_lo + lane) : 0u;
+                        const uint32_t tmask = __ballot_sync(0xffffffffu, ok && op != OP_QONLY);
+                        const uint32_t qmask = __ballot_sync(0xffffffffu, ok && op != OP_TONLY);
+                        const uint32_t tle = tmask & le_mask;
+                        const int k = __popc(tle);
+                        const int ps = last_pos + k;
+                        const int delta = (k == 0) ? (int)(last_node >> 3) + lane + 1 : lane - (31 - __clz(tle));
+                        const uint32_t late = __ballot_sync(0xffffffffu, ok && ps >= t1);    // columns of later tiles
+                        const int nv = n - x < 32 ? (int)(n - x) : 32;
+                        const int n_take = late ? __ffs(late) - 1 : nv;
+                        if (n_take == 0) break;
+                        const bool take = lane < n_take;
+                        int b = 4;
+                        {
+                            const uint32_t q = qp + __popc(qmask & lt_mask);
+                            const long long p = qdir ? (long long)qso + (qlen - 1 - (int)q) : (long long)qso + q;
+                            const bool want = take && op != OP_TONLY;
+                            const uint32_t byte = __shfl_sync(0xffffffffu, pacb, want ? (int)((p >> 2) - pac_lo) : 0);
+                            if (want) { b = (byte >> (((~p) & 3) << 1)) & 3; if (qdir) b = 3 - b; }
+                        }
+                        const uint32_t node = ((uint32_t)delta << 3) | (uint32_t)b;
+                        uint32_t pnode = __shfl_up_sync(0xffffffffu, node, 1);
+                        if (lane == 0) pnode = last_node;
+                        const int pl = ps - t0;
+                        bool ins = take && pl >= 0;
+                        if (ins) {                                      // position inside a scored run?
+                            uint32_t word = tile_run[0];
+#pragma unroll
+                            for (int r = 1; r < CNS_TILE_ROUNDS; ++r) if ((pl >> 5) == r) word = tile_run[r];
+                            ins = (word >> (pl & 31)) & 1;
+                        }
+                        uint32_t key = 0;
+                        int e = -1, oe = 0xffff;
+                        if (ins) {
+                            uint32_t rank, pb;
+                            if (pnode == 0xffff) { rank = 0; pb = 7; }
+                            else { pb = pnode & 7; rank = 1 + (delta == 0 ? (pnode >> 3) * 5u : 0u) + cns_char_rank(pb); }
+                            key = ((uint32_t)delta << 24) | ((uint32_t)b << 20) | (pb << 16) | rank;
+                            const uint4 k0 = *reinterpret_cast<const uint4*>(&S.key[pl][0]);
+                            const uint4 k1 = *reinterpret_cast<const uint4*>(&S.key[pl][4]);
+                            const uint32_t have = S.cnt[pl];
+                            if (have > 7 && k1.w == key) e = 7;
+                            if (have > 6 && k1.z == key) e = 6;
+                            if (have > 5 && k1.y == key) e = 5;
+                            if (have > 4 && k1.x == key) e = 4;
+                            if (have > 3 && k0.w == key) e = 3;
+                            if (have > 2 && k0.z == key) e = 2;
+                            if (have > 1 && k0.y == key) e = 1;
+                            if (have > 0 && k0.x == key) e = 0;
+                            if (e < 0 && have > CNS_SLOTS) { oe = (int)S.ov_head[pl]; while (oe != 0xffff && OV[oe].x != key) oe = (int)OV[oe].y; }
+                        }
+                        __syncwarp();                                   // every lane has searched before any lane inserts
+                        if (ins) {
+                            if (e >= 0) S.w[pl][e] = __dadd_rn(S.w[pl][e], w);                 // acceptance order (cns_aux.c:48)
+                            else if (oe != 0xffff) { const uint4 v = OV[oe]; const double nw = __dadd_rn(__hiloint2double((int)v.w, (int)v.z), w); OV[oe].z = (uint32_t)__double2loint(nw); OV[oe].w = (uint32_t)__double2hiint(nw); }
+                            else {
+                                const uint32_t slot = atomicAdd(&S.cnt[pl], 1u);
+                                if (slot < CNS_SLOTS) { S.key[pl][slot] = key; S.w[pl][slot] = w; }
+                                else {
+                                    const uint32_t ne = atomicAdd(&S.ov_used, 1u);
+                                    if (ne < CNS_OV) OV[ne] = make_uint4(key, atomicExch(&S.ov_head[pl], ne), (uint32_t)__double2loint(w), (uint32_t)__double2hiint(w));
+                                }
+                            }
+                            ++n_cols_total;
+                        }
+                        const int lastl = n_take - 1;
+                        last_pos = __shfl_sync(0xffffffffu, ps, lastl);
+                        last_node = __shfl_sync(0xffffffffu, node, lastl);
+                        qp += __popc(qmask & ((n_take >= 32) ? 0xffffffffu : ((1u << n_take) - 1)));
+                        x += (uint32_t)n_take;
+                        __syncwarp();
+                        if (n_take < 32) break;
+                        op = op_nx;
                     }
+                    if (lane == 0) { CnsCursor c; c.x = x; c.qpos = qp; c.last_pos = last_pos; c.last_node = last_node; CU[ci] = c; }
                     __syncwarp();
                 }
             }
-            if (S.pool_used > CNS_POOL) { fail |= 2; break; }
-            // ---- flush: lane = position; its links go to HBM in key order, with the index of the
-            //      predecessor node's first link resolved here so that k_cns_dp needs no search
-            // one walk over my position's list: up to CNS_FLUSH_REGS links go to registers as key << 16 | pool slot
-            unsigned long long kv[CNS_FLUSH_REGS];
-            int cnt = 0;
-            int e_walk = (int)S.head[lane];
-#pragma unroll
-            for (int j = 0; j < CNS_FLUSH_REGS; ++j) {
-                kv[j] = ~0ull;
-                if (e_walk != 0xffff) { kv[j] = ((unsigned long long)S.e_key[e_walk] << 16) | (unsigned)e_walk; e_walk = S.e_next[e_walk]; ++cnt; }
             }
-            const bool crowded = e_walk != 0xffff;                  // more links than registers: the slow flush below
-            for (; e_walk != 0xffff; e_walk = S.e_next[e_walk]) ++cnt;
-            const bool any_crowded = __any_sync(0xffffffffu, crowded) || kFlushSlow;
-            int off = cnt;
+            n_ov_total += S.ov_used;
+            if (S.ov_used > CNS_OV) {
+                fail |= 2; break; }
+            // ---- flush: lane = position (CNS_TILE_ROUNDS of them); its links go to HBM in key order, with the index of the
+            //      predecessor node's first link resolved here so that k_cns_dp needs no search.  (Loops are kept rolled on
+            //      purpose: the warps of an SM are at different places of this kernel, its code has to stay in the
+            //      instruction cache.)
+            uint32_t carry = 0;                 // links of the tile before my round
+            // number of links of row q (n of them) whose node id (delta << 4 | base) is below `want`
+            auto row_less = [&](int q, uint32_t n, uint32_t want) -> uint32_t {
+                const uint4 a0 = *reinterpret_cast<const uint4*>(&S.key[q][0]);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(&S.key[q][4]);
+                uint32_t less = (n > 0 && (a0.x >> 20) < want) + (n > 1 && (a0.y >> 20) < want) + (n > 2 && (a0.z >> 20) < want) + (n > 3 && (a0.w >> 20) < want)
+                              + (n > 4 && (a1.x >> 20) < want) + (n > 5 && (a1.y >> 20) < want) + (n > 6 && (a1.z >> 20) < want) + (n > 7 && (a1.w >> 20) < want);
+                if (n > CNS_SLOTS) for (int e = (int)S.ov_head[q]; e != 0xffff; e = (int)OV[e].y) less += (OV[e].x >> 20) < want;
+                return less;
+            };
+#pragma unroll 1
+            for (int r = 0; r < CNS_TILE_ROUNDS; ++r) {
+                const int pl = 32 * r + lane;
+                const int t = t0 + pl;
+                const uint4 tp = t < t1 ? *reinterpret_cast<const uint4*>(pos + t) : make_uint4(0, 0, 0, 0);
+                const int cnt = (int)S.cnt[pl];
+                int off = cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, off, d); if (lane >= d) off += o; }
-            const int tile_total = __shfl_sync(0xffffffffu, off, 31);
-            off -= cnt;
-            if (ebase + (uint32_t)tile_total > TP.link_cap) { fail |= 2; break; }
-            const uint32_t my_start = ebase + (uint32_t)off;
-            if (t0 + lane < T) pos[t0 + lane].start = my_start;
-            // links of the previous position: the lane below, or the last position of the previous tile (in HBM)
-            uint32_t pv_start = __shfl_up_sync(0xffffffffu, my_start, 1);
-            if (lane == 0) pv_start = prev_start;
-            const bool pv_in_run = (tile_flag & 1) && !(tile_flag & 2);            // the previous position belongs to the same run
-            if (!any_crowded) {
-                // ---- fast flush: sort the registers (keys of a position are distinct), publish the node ids of the
-                //      sorted links so that the next lane can locate its predecessors, resolve, write
+                for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, off, d); if (lane >= d) off += o; }
+                const int round_total = __shfl_sync(0xffffffffu, off, 31);
+                off -= cnt;
+                if (ebase + carry + (uint32_t)round_total > cap) { fail |= 2; break; }
+                const uint32_t my_start = lb + ebase + carry + (uint32_t)off;
+                const uint32_t tflag = tp.z;
+                if (t < t1) { uint4 pr = tp; pr.x = my_start; pr.w = (uint32_t)cnt; *reinterpret_cast<uint4*>(pos + t) = pr; }
+                const double pen = __dmul_rn(0.2, (double)(int)tp.y);               // 0.4 * 0.5 * coverage (cns_aux.c:164)
+                // links of the previous position: the lane below, the last lane of the previous round, or the last
+                // position of the previous tile (its keys were kept in S.carry_key, or are read back from HBM)
+                uint32_t pv_start = __shfl_up_sync(0xffffffffu, my_start, 1);
+                if (lane == 0) pv_start = prev_start;
+                const bool pv_in_run = (tflag & 1) && !(tflag & 2);                 // the previous position belongs to the same run
+                const bool pv_open = pv_in_run && pl == 0 && t0 == s0;              // ... and to another span: k_cns_fix
+                const uint32_t flag_run = ((tflag & 2) ? CNS_K_RUNFIRST : 0u) | ((tflag & 4) ? CNS_K_RUNLAST : 0u);
+                // 1. a row of up to CNS_SLOTS links: sort the keys in registers (keys of a position are distinct), put them
+                //    back in key order, remember which slot (weight) each came from
+                const bool small = cnt <= CNS_SLOTS && !kFlushSlow;
+                if (cnt > 0 && small) {
+                    unsigned long long kv[CNS_SLOTS];
+                    {
+                        const uint4 a0 = *reinterpret_cast<const uint4*>(&S.key[pl][0]);
+                        const uint4 a1 = *reinterpret_cast<const uint4*>(&S.key[pl][4]);
+                        const uint32_t kk[CNS_SLOTS] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                        for (int j = 0; j < CNS_SLOTS; ++j) kv[j] = j < cnt ? (((unsigned long long)kk[j] << 4) | (unsigned)j) : ~0ull;
+                    }
 #define CNS_CSWAP(a, b) { const unsigned long long lo_ = kv[a] < kv[b] ? kv[a] : kv[b], hi_ = kv[a] < kv[b] ? kv[b] : kv[a]; kv[a] = lo_; kv[b] = hi_; }
-                CNS_CSWAP(0, 1) CNS_CSWAP(2, 3) CNS_CSWAP(4, 5) CNS_CSWAP(6, 7)
-                CNS_CSWAP(0, 2) CNS_CSWAP(1, 3) CNS_CSWAP(4, 6) CNS_CSWAP(5, 7)
-                CNS_CSWAP(1, 2) CNS_CSWAP(5, 6)
-                CNS_CSWAP(0, 4) CNS_CSWAP(1, 5) CNS_CSWAP(2, 6) CNS_CSWAP(3, 7)
-                CNS_CSWAP(2, 4) CNS_CSWAP(3, 5)
-                CNS_CSWAP(1, 2) CNS_CSWAP(3, 4) CNS_CSWAP(5, 6)
+                    CNS_CSWAP(0, 1) CNS_CSWAP(2, 3) CNS_CSWAP(4, 5) CNS_CSWAP(6, 7)
+                    CNS_CSWAP(0, 2) CNS_CSWAP(1, 3) CNS_CSWAP(4, 6) CNS_CSWAP(5, 7)
+                    CNS_CSWAP(1, 2) CNS_CSWAP(5, 6)
+                    CNS_CSWAP(0, 4) CNS_CSWAP(1, 5) CNS_CSWAP(2, 6) CNS_CSWAP(3, 7)
+                    CNS_CSWAP(2, 4) CNS_CSWAP(3, 5)
+                    CNS_CSWAP(1, 2) CNS_CSWAP(3, 4) CNS_CSWAP(5, 6)
 #undef CNS_CSWAP
-                uint32_t nid[CNS_FLUSH_REGS];                       // delta << 4 | base of each sorted link; 0xfff = none
+                    uint32_t ord = 0;
 #pragma unroll
-                for (int j = 0; j < CNS_FLUSH_REGS; ++j) nid[j] = (uint32_t)(kv[j] >> 36) & 0xfffu;
-                // (the 512 bytes reuse the list pointers: every lane has its whole list in registers by now)
-                uint4* sorted_nid = reinterpret_cast<uint4*>(S.e_next);
-                __syncwarp();
-                {
-                    uint4 pk;
-                    pk.x = nid[0] | (nid[1] << 16); pk.y = nid[2] | (nid[3] << 16); pk.z = nid[4] | (nid[5] << 16); pk.w = nid[6] | (nid[7] << 16);
-                    sorted_nid[lane] = pk;
+                    for (int j = 0; j < CNS_SLOTS; ++j) ord |= ((uint32_t)kv[j] & 15u) << (4 * j);
+                    *reinterpret_cast<uint4*>(&S.key[pl][0]) = make_uint4((uint32_t)(kv[0] >> 4), (uint32_t)(kv[1] >> 4), (uint32_t)(kv[2] >> 4), (uint32_t)(kv[3] >> 4));
+                    *reinterpret_cast<uint4*>(&S.key[pl][4]) = make_uint4((uint32_t)(kv[4] >> 4), (uint32_t)(kv[5] >> 4), (uint32_t)(kv[6] >> 4), (uint32_t)(kv[7] >> 4));
+                    S.ord[pl] = ord;
                 }
                 __syncwarp();
-                uint32_t pn[CNS_FLUSH_REGS];                        // the previous position's sorted node ids
-                {
-                    const uint4 pk = sorted_nid[lane > 0 ? lane - 1 : 0];
-                    pn[0] = pk.x & 0xffff; pn[1] = pk.x >> 16; pn[2] = pk.y & 0xffff; pn[3] = pk.y >> 16;
-                    pn[4] = pk.z & 0xffff; pn[5] = pk.z >> 16; pn[6] = pk.w & 0xffff; pn[7] = pk.w >> 16;
-                }
-                const bool lane0_regs = prev_fast;
-                if (lane == 0 && lane0_regs) {
-#pragma unroll
-                    for (int j = 0; j < CNS_FLUSH_REGS; ++j) pn[j] = prev_nid[j];
-                }
-#pragma unroll
-                for (int i = 0; i < CNS_FLUSH_REGS; ++i) {
-                    if (i < cnt) {
-                        const uint32_t bk = (uint32_t)(kv[i] >> 16);
-                        const int be = (int)(kv[i] & 0xffff);
-                        const uint32_t rank = bk & 0xffff, pb = (bk >> 16) & 7, d = bk >> 24;
-                        uint32_t pred = CNS_NOPRED;
-                        if (rank != 0) {
-                            if (d > 0) {
-                                // node (d - 1, pb) of this position: its first link = number of links of this position below it
-                                const uint32_t want = ((d - 1) << 4) | pb;
+                // 2. my links in key order: resolve the predecessor, write
+                const uint32_t ord = S.ord[pl];
+                const int nslot = cnt < CNS_SLOTS ? cnt : CNS_SLOTS;
+                uint32_t lastkey = 0;
+#pragma unroll 1
+                for (int i = 0; i < cnt; ++i) {
+                    uint32_t bk; double bw;
+                    if (small) { bk = S.key[pl][i]; bw = S.w[pl][(ord >> (4 * i)) & 15u]; }
+                    else {
+                        // crowded position (or the test switch): selection by increasing key over slots + overflow chain
+                        bk = 0xffffffffu; bw = 0.0;
+                        for (int j = 0; j < nslot; ++j) {
+                            const uint32_t kk = S.key[pl][j];
+                            if (kk < bk && (i == 0 || kk > lastkey)) { bk = kk; bw = S.w[pl][j]; }
+                        }
+                        for (int e = (int)S.ov_head[pl]; e != 0xffff; e = (int)OV[e].y) {
+                            const uint4 v = OV[e];
+                            if (v.x < bk && (i == 0 || v.x > lastkey)) { bk = v.x; bw = __hiloint2double((int)v.w, (int)v.z); }
+                        }
+                    }
+                    const uint32_t rank = CNS_K_RANK(bk), pb = (bk >> 16) & 7, d = bk >> 24;
+                    uint32_t pred = CNS_NOPRED;
+                    if (rank != 0) {
+                        if (d > 0) {
+                            // node (d - 1, pb) of this position: its first link = number of links of this position below it
+                            pred = my_start + row_less(pl, (uint32_t)cnt, ((d - 1) << 4) | pb);
+                        } else if (pv_in_run) {
+                            const uint32_t want = (((rank - 1 - cns_char_rank(pb)) / 5u) << 4) | pb;
+                            if (pv_open) pred = CNS_PRED_OPEN | want;
+                            else if (pl > 0) pred = pv_start + row_less(pl - 1, S.cnt[pl - 1], want);
+                            else if (S.carry_cnt <= CNS_SLOTS) {
                                 uint32_t less = 0;
-#pragma unroll
-                                for (int j = 0; j < CNS_FLUSH_REGS; ++j) less += nid[j] < want;
-                                pred = my_start + less;
-                            } else if (pv_in_run) {
-                                const uint32_t want = (((rank - 1 - cns_char_rank(pb)) / 5u) << 4) | pb;
+                                for (uint32_t q = 0; q < S.carry_cnt; ++q) less += (S.carry_key[q] >> 20) < want;
+                                pred = pv_start + less;
+                            } else {
                                 uint32_t less = 0;
-                                if (lane > 0 || lane0_regs) {
-#pragma unroll
-                                    for (int j = 0; j < CNS_FLUSH_REGS; ++j) less += pn[j] < want;
-                                } else {
-                                    for (uint32_t q = 0; q < prev_cnt; ++q) less += ((link[prev_start + q].key >> 20) & 0xff7u) < want;
-                                }
+                                for (uint32_t q = 0; q < prev_cnt; ++q) less += ((link[prev_start + q].key >> 20) & 0xff7u) < want;
                                 pred = pv_start + less;
                             }
                         }
-                        // bit 23: first link of its node, bit 19: first link of its delta level (spares k_cns_dp the key compares)
-                        const uint32_t lastnid = i > 0 ? nid[i > 0 ? i - 1 : 0] : 0xffffu;
-                        const uint32_t fl_node = (i == 0 || nid[i] != lastnid) ? (1u << 23) : 0u;
-                        const uint32_t fl_level = (i == 0 || (nid[i] >> 4) != (lastnid >> 4)) ? (1u << 19) : 0u;
-                        CnsLink L; L.key = bk | fl_node | fl_level; L.pred = pred; L.w = S.e_w[be];
-                        link[my_start + i] = L;
                     }
+                    // bit 23: first link of its node, bit 19: first link of its delta level (spares k_cns_dp the key compares)
+                    const uint32_t fl_node = (i == 0 || (bk >> 20) != (lastkey >> 20)) ? CNS_K_NODE : 0u;
+                    const uint32_t fl_level = (i == 0 || (bk >> 24) != (lastkey >> 24)) ? CNS_K_LEVEL : 0u;
+                    CnsLink L; L.key = bk | fl_node | fl_level | (i == 0 ? flag_run : 0u); L.pred = pred; L.w = __dsub_rn(bw, pen);
+                    link[my_start + i] = L;
+                    lastkey = bk;
                 }
-#pragma unroll
-                for (int j = 0; j < CNS_FLUSH_REGS; ++j) prev_nid[j] = __shfl_sync(0xffffffffu, nid[j], 31);
-                prev_fast = true;
-            } else {
-            prev_fast = false;
-            uint32_t lastkey = 0;
-            for (int i = 0; i < cnt; ++i) {        // selection by increasing key (keys of a position are distinct)
-                uint32_t bk = 0xffffffffu; int be = 0xffff;
-                for (int e = (int)S.head[lane]; e != 0xffff; e = S.e_next[e]) {
-                    const uint32_t kk = S.e_key[e];
-                    if (kk < bk && (i == 0 || kk > lastkey)) { bk = kk; be = e; }
-                }
-                const uint32_t rank = bk & 0xffff, pb = (bk >> 16) & 7, d = bk >> 24;
-                uint32_t pred = CNS_NOPRED;
-                if (rank != 0) {
-                    if (d > 0) {
-                        // node (d - 1, pb) of this position: its first link = number of links of this position below it
-                        const uint32_t want = ((d - 1) << 4) | pb;
-                        uint32_t less = 0;
-                        for (int e = (int)S.head[lane]; e != 0xffff; e = S.e_next[e]) less += (S.e_key[e] >> 20) < want;
-                        pred = my_start + less;
-                    } else if (pv_in_run) {
-                        const uint32_t want = (((rank - 1 - cns_char_rank(pb)) / 5u) << 4) | pb;
-                        uint32_t less = 0;
-                        if (lane > 0) {
-                            for (int e = (int)S.head[lane - 1]; e != 0xffff; e = S.e_next[e]) less += (S.e_key[e] >> 20) < want;
-                        } else {
-                            for (uint32_t q = 0; q < prev_cnt; ++q) less += ((link[prev_start + q].key >> 20) & 0xff7u) < want;
-                        }
-                        pred = pv_start + less;
-                    }
-                }
-                // bit 23: first link of its node, bit 19: first link of its delta level (spares k_cns_dp the key compares)
-                const uint32_t fl_node = (i == 0 || (bk >> 20) != (lastkey >> 20)) ? (1u << 23) : 0u;
-                const uint32_t fl_level = (i == 0 || (bk >> 24) != (lastkey >> 24)) ? (1u << 19) : 0u;
-                CnsLink L; L.key = bk | fl_node | fl_level; L.pred = pred; L.w = S.e_w[be];
-                link[my_start + i] = L;
-                lastkey = bk;
+                __syncwarp();
+                prev_start = __shfl_sync(0xffffffffu, my_start, 31);
+                prev_cnt = (uint32_t)__shfl_sync(0xffffffffu, cnt, 31);
+                carry += (uint32_t)round_total;
             }
+            {
+                // the keys of the tile's last position stay behind for the first position of the next tile
+                const int lp = t1 - t0 - 1;
+                const uint32_t lc = S.cnt[lp];
+                uint32_t kq = 0;
+                if (lane < CNS_SLOTS) kq = S.key[lp][lane];
+                __syncwarp();
+                if (lane < CNS_SLOTS) S.carry_key[lane] = kq;
+                if (lane == 0) S.carry_cnt = lc <= CNS_SLOTS ? lc : 0xffffu;
+                const int lr = lp >> 5, ll = lp & 31;
+                (void)lr;
+                prev_start = __shfl_sync(0xffffffffu, prev_start, 0);       // (already uniform)
+                (void)ll;
             }
-            prev_start = __shfl_sync(0xffffffffu, my_start, 31);
-            prev_cnt = (uint32_t)__shfl_sync(0xffffffffu, cnt, 31);
-            ebase += (uint32_t)tile_total;
+            ebase += carry;
             __syncwarp();
         }
-        if (lane == 0) pos[T].start = ebase;
+        if (lane == 0) P.span_links[TP.unit_first + U.span] = make_uint2(lb, fail ? 0u : ebase);
         n_links_total += ebase;
         if (fail && lane == 0) atomicOr(P.error_flag, fail);
         __syncwarp();
     }
     for (int d = 16; d > 0; d >>= 1) n_cols_total += __shfl_xor_sync(0xffffffffu, n_cols_total, d);
-    if (lane == 0) { atomicAdd(P.counters + 1, n_cols_total); atomicAdd(P.counters + 2, n_links_total); }
+    if (lane == 0) { atomicAdd(P.counters + 1, n_cols_total); atomicAdd(P.counters + 2, n_links_total); atomicAdd(P.counters + 3, n_ov_total); }
 }
 
-// ------------------------------------------------------------------ phase B
-// One run of a template, recorded by k_cns_dp for k_cns_walk.
-struct CnsRun {
-    int32_t from, to;           // coverage run [from, to)
-    int32_t g_level, g_b, g_t, g_delta;     // best node of the run (cns_aux.c:177-184), g_level < 0: none
-};
+// The first position of a span (not of the template): the predecessors of its delta-0 links are nodes of the last
+// position of the previous span, whose links another warp placed.  One thread per unit.
+__global__ void __launch_bounds__(128)
+k_cns_fix(CnsParams P)
+{
+    const uint32_t ui = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ui >= P.n_units) return;
+    const CnsUnit U = P.unit[ui];
+    if (U.span == 0) return;
+    const CnsTemplate TP = P.tpl[U.tpl];
+    const CnsPos* pos = P.pos + TP.pos_base;
+    CnsLink* link = P.link + TP.link_base;
+    const int b = (int)U.span * P.span;
+    const CnsPos cur = pos[b], prv = pos[b - 1];
+    for (uint32_t i = 0; i < cur.n; ++i) {
+        const uint32_t pred = link[cur.start + i].pred;
+        if (pred == CNS_NOPRED || (pred & 0xF0000000u) != CNS_PRED_OPEN) continue;
+        const uint32_t want = pred & 0xfffu;
+        uint32_t less = 0;
+        for (uint32_t q = 0; q < prv.n; ++q) less += ((link[prv.start + q].key >> 20) & 0xff7u) < want;
+        link[cur.start + i].pred = prv.start + less;
+    }
+}
 
-// One template per WARP.  The recurrence is a chain over template positions -- and, inside a position, over its
-// delta levels -- so the only parallelism inside a template is across the links of one level (1 to ~10).  That is
-// still what decides the kernel's duration: the longest template of a job has ~60 k positions, and a single thread
-// walking its ~280 k links and positions one after the other takes longer than all other templates together.  Here
-// the lanes of the warp take the links of the current position (lane = link), so a position costs one pass per delta
-// level instead of one iteration per link:
-//   * links are streamed through a 256-link ring in shared memory with cp.async, 128 links ahead of their use;
-//   * position records are loaded 32 at a time (lane = position), one chunk ahead, and handed out by shuffles;
-//   * node scores live in a 256-entry ring in shared memory indexed by the first link of the node; a predecessor is
-//     at most two positions back, so the ring misses only where two neighbouring positions hold more than SC_RING
-//     links -- those positions also spill their scores into link[].w (where the reference-shaped kernel kept them);
-//   * the links of a node are reduced with shuffles (max score, ties to the lower predecessor rank), the five 11-bit
-//     back pointers of a level are OR-reduced into one u64, the best node of a run is tracked per lane and reduced
-//     when the run ends (ties to the lowest link index = the first one in the reference's traversal order).
-// A position with more than FAST_MAX links is handed to lane 0, which scores it link by link.
-#define CNS_DP_LINK_RING 256
-
+// ------------------------------------------------------------------ best path
 __device__ __forceinline__ void cns_cp_async16(void* dst_smem, const void* src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(nb_smem_addr(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cns_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cns_cp_async_wait(int pending)      // at most `pending` (0..3) groups stay in flight
+__device__ __forceinline__ void cns_cp_async_wait(int pending)      // at most `pending` (0 or CNS_DP_PEND) groups stay in flight
 {
     if (pending <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
-    else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-    else asm volatile("cp.async.wait_group 3;" ::: "memory");
+    else asm volatile("cp.async.wait_group 6;" ::: "memory");
 }
+#define CNS_DP_PEND 6
 
 __device__ __forceinline__ uint32_t cns_bp_code(uint32_t key)       // back pointer of a node whose best link has this key
 {
-    const uint32_t rank = key & 0xffff, pb = (key >> 16) & 7;
+    const uint32_t rank = CNS_K_RANK(key), pb = (key >> 16) & 7;
     if (rank == 0) return 7u;
     return (((key >> 24) == 0 ? (rank - 1 - cns_char_rank(pb)) / 5u : 0u) << 3) | pb;
 }
 
-template <int FAST_MAX, int SC_RING>
+// Eight lanes per template, four templates per warp, all in lock step.  The recurrence is a chain over the delta levels
+// of a template, so what decides the kernel's duration is the latency of one step of that chain for the longest
+// template and how little else sits between two steps.  One trip of the loop takes the next (up to 8) links of every
+// template of the warp, lane = link, cut so that they are whole levels of ONE position, and walks their levels:
+//   * the links of a template are a dense stream per span (k_cns_links): they are staged through a ring in shared
+//     memory with cp.async, LR links ahead; position, run and level boundaries are flags of the link keys, so no
+//     position record is read;
+//   * a predecessor scored in an earlier trip comes from a ring of node scores in shared memory, indexed by the dense
+//     sequence number of the node's first link (a predecessor is a node of this or of the previous position: the ring
+//     misses only where two neighbouring positions hold more than SR links, and such a template is handed to
+//     k_cns_dp_serial); a predecessor inside the trip comes from its lane by shuffle;
+//   * the links of a node are adjacent lanes: maximum by shuffles (ties to the lower predecessor rank); every node
+//     stores its own 11-bit back pointer into the level record, the best node of a run is tracked per lane and
+//     reduced when the run has ended (ties to the lowest link = the first one in the reference's traversal order);
+//   * everything that is rare (a run ended, a level of more than 8 links, the staging ring has to catch up, a
+//     template is finished) is announced in ONE ballot at the top of the next trip.
+#define CNS_DP_G 8
+
+template <int LR, int SR>
 __global__ void __launch_bounds__(128)
-k_cns_dp(CnsParams P, CnsRun* __restrict__ runs, uint32_t* __restrict__ tpl_nrun)
+k_cns_dp(CnsParams P)
 {
-    __shared__ __align__(16) uint4 s_links[4][CNS_DP_LINK_RING];
-    __shared__ double s_score[4][SC_RING];
+    extern __shared__ __align__(16) uint8_t dp_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t ti = blockIdx.x * 4 + wid;
-    if (ti >= P.n_tpl) return;
-    uint4* LK = s_links[wid];
-    double* SC = s_score[wid];
-    const uint32_t lt_mask = (1u << lane) - 1, le_mask = lt_mask | (1u << lane);
+    const int gl = lane & (CNS_DP_G - 1), grp = lane >> 3, gsh = grp * CNS_DP_G;
+    const uint32_t le8 = (2u << gl) - 1;                    // lanes of my group up to mine (group-relative bits)
+    const uint32_t slot = (blockIdx.x * 4 + wid) * 4 + grp;
+    uint4* LK = reinterpret_cast<uint4*>(dp_smem) + (size_t)(wid * 4 + grp) * LR;
+    double* SC = reinterpret_cast<double*>(dp_smem + (size_t)16 * 16 * LR) + (size_t)(wid * 4 + grp) * SR;
+    bool done = slot >= P.n_tpl;
+    const uint32_t ti = done ? 0 : slot;
     const CnsTemplate TP = P.tpl[ti];
-    const int T = TP.T;
-    CnsPos* pos = P.pos + TP.pos_base;
-    CnsLink* link = P.link + TP.link_base;
-    CnsLevel* bp = P.bp + TP.level_base;
-    CnsRun* my_runs = runs + TP.seg_first;
-    uint32_t nrun = 0, fail = 0, level = 0;
-    uint32_t prev_fl = 0;                       // first level of the previous scored position
-    // best node of the current run, per lane
-    double g_best = -1.0;
-    int g_level = -1, g_b = -1, g_t = 0, g_delta = 0, run_from = 0;
-    uint32_t g_x = 0xffffffffu;
-    // link staging: batches of 32 links, [.., fill) issued, [.., landed) known to have arrived
-    uint32_t fill = 0, landed = 0;
-    auto issue_batch = [&]() {
-        cns_cp_async16(LK + ((fill + lane) & (CNS_DP_LINK_RING - 1)), link + fill + lane);     // the pool has slack past the end
+    const CnsLink* __restrict__ link = P.link + TP.link_base;
+    uint4* bp = reinterpret_cast<uint4*>(P.bp + TP.level_base);
+    uint16_t* bp16 = reinterpret_cast<uint16_t*>(bp);
+    CnsRun* my_runs = P.runs + TP.seg_first;
+    const uint2* __restrict__ spans = P.span_links + TP.unit_first;
+    const int n_spans = (TP.T + P.span - 1) / P.span;
+    const uint32_t n_runs = done ? 0 : P.tpl_nrun[ti];
+    // consumer / producer cursors over the link stream
+    int ck = -1, fk = -1;
+    uint32_t c = 0, c_end = 0, seq = 0, f = 0, f_end = 0, fseq = 0;
+    auto next_span = [&](int& k, uint32_t& a, uint32_t& a_end) {
+        while (a == a_end && k < n_spans) {
+            ++k;
+            if (k < n_spans) { const uint2 e = spans[k]; a = e.x; a_end = e.x + e.y; }
+        }
+    };
+    bool redo = false;
+    if (!done && P.dp_serial) { redo = true; done = true; }
+    if (!done) { next_span(ck, c, c_end); fk = ck; f = c; f_end = c_end; if (ck >= n_spans) done = true; }
+    uint32_t p_abs = 0, p_seq = 0, q_abs = 0, q_seq = 0;
+    uint32_t level = 0, cur_fl = 0, prev_fl = 0, run_started = 0, run_emitted = 0, fail = 0;
+    int t = 0;
+    bool p_last = false, pend_emit = false, pend_serial = false, unsure = !done;
+    // best node of the current run, per lane; and of the run that has just ended (emitted at the top of the next trip)
+    double g_best = -1.0, e_best = -1.0;
+    int g_level = -1, g_b = -1, g_t = 0, g_delta = 0, e_level = -1, e_b = -1, e_t = 0, e_delta = 0, e_end = 0;
+    uint32_t g_x = 0xffffffffu, e_x = 0xffffffffu;
+    auto issue = [&]() {
+        const uint32_t nb = f_end - f < CNS_DP_G ? f_end - f : CNS_DP_G;
+        if ((uint32_t)gl < nb) cns_cp_async16(LK + ((fseq + gl) & (LR - 1)), link + f + gl);
+        f += nb; fseq += nb;
+        if (f == f_end) next_span(fk, f, f_end);
+    };
+    for (;;) {
+        // ---- one ballot for everything that is not the common case: bit 0 of a group = finished, 1 = the links of this trip
+        //      may not have landed, 2 = a run ended, 3 = a level of more than 8 links is next
+        const uint32_t ev = __ballot_sync(0xffffffffu, gl == 0 ? done : gl == 1 ? unsure : gl == 2 ? pend_emit : gl == 3 ? pend_serial : false);
+        if ((ev & 0x01010101u) == 0x01010101u && !(ev & 0x04040404u)) break;
+        // ---- staging: keep the ring full
+        if (!done && fseq - seq <= (uint32_t)(LR - CNS_DP_G) && f < f_end) issue();
         cns_cp_async_commit();
-        fill += 32;
-    };
-    auto load_pos = [&](int tbase) {
-        const int idx = tbase + lane;
-        return *reinterpret_cast<const uint4*>(pos + (idx <= T ? idx : T));
-    };
-    uint4 pc = load_pos(0), pn = load_pos(32);
-    for (int t0 = 0; t0 < T; t0 += 32) {
-        // lane j describes position t0 + j: first link, number of links, flags, whether its scores must be spilled
-        const uint32_t n0 = __shfl_sync(0xffffffffu, pn.x, 0), n1 = __shfl_sync(0xffffffffu, pn.x, 1);
-        uint32_t e1 = __shfl_down_sync(0xffffffffu, pc.x, 1), e2 = __shfl_down_sync(0xffffffffu, pc.x, 2);
-        if (lane == 31) { e1 = n0; e2 = n1; }
-        if (lane == 30) e2 = n0;
-        const bool inside = t0 + lane < T;
-        const uint32_t my_n = inside ? e1 - pc.x : 0u;
-        const uint32_t my_info = (my_n & 0xffffu) | ((inside ? pc.z & 7u : 0u) << 16) | ((e2 - pc.x > (uint32_t)SC_RING ? 1u : 0u) << 20);
-        const int jn = T - t0 < 32 ? T - t0 : 32;
-        for (int j = 0; j < jn; ++j) {
-            const int t = t0 + j;
-            const uint32_t s = __shfl_sync(0xffffffffu, pc.x, j);
-            const uint32_t info = __shfl_sync(0xffffffffu, my_info, j);
-            const uint32_t n = info & 0xffffu, fl = (info >> 16) & 7u;
-            const bool spill = (info >> 20) & 1u;
-            if (fl & 2) { g_best = -1.0; g_level = -1; g_x = 0xffffffffu; run_from = t; }
-            if ((fl & 1) && n > 0) {
-                const int cov = __shfl_sync(0xffffffffu, (int)pc.y, j);
-                const double pen = __dmul_rn(0.2, (double)cov);                 // 0.4 * 0.5 * coverage (cns_aux.c:164)
-                if (lane == 0) pos[t].first_level = level;
-                const uint32_t cur_fl = level;
-                const uint32_t e = s + n;
-                if (n <= (uint32_t)FAST_MAX) {
-                    // ---- staging: the links of this position must have landed; keep 128 links ahead
-                    if ((s & ~31u) > fill) { cns_cp_async_wait(0); fill = s & ~31u; landed = fill; }      // after a position that bypassed the ring
-                    while (fill < e + 128 && fill + 32 - (s & ~31u) <= CNS_DP_LINK_RING) issue_batch();
-                    if (e > landed) {
-                        const uint32_t pending = (fill - ((e + 31) & ~31u)) >> 5;
-                        cns_cp_async_wait((int)pending);
-                        landed = fill - 32 * (pending > 3 ? 3 : pending);
-                        __syncwarp();
-                    }
-                    const bool act = (uint32_t)lane < n;
-                    const uint32_t x = s + lane;
-                    uint4 lr = make_uint4(0, CNS_NOPRED, 0, 0);
-                    if (act) lr = LK[x & (CNS_DP_LINK_RING - 1)];
-                    const uint32_t key = lr.x, pred = lr.y;
-                    const double base = __dsub_rn(__hiloint2double((int)lr.w, (int)lr.z), pen);
-                    const bool isstart = act && ((key >> 23) & 1);
-                    uint32_t lf = __ballot_sync(0xffffffffu, act && ((key >> 19) & 1));
-                    while (lf) {                                                // one pass per delta level
-                        const int lo = __ffs(lf) - 1;
-                        lf &= lf - 1;
-                        const int hi = lf ? __ffs(lf) - 1 : (int)n;
-                        const bool in = lane >= lo && lane < hi;
-                        double sc = base;
-                        if (in && pred != CNS_NOPRED)                           // never-scored predecessors count 0 (cns_aux.c:63-70)
-                            sc = __dadd_rn(base, (x - pred < (uint32_t)SC_RING) ? SC[pred & (SC_RING - 1)] : link[pred].w);
-                        const uint32_t nf = __ballot_sync(0xffffffffu, in && isstart);
-                        const uint32_t above = nf & ~le_mask;
-                        const int nend = above ? __ffs(above) - 1 : hi;         // my node ends here (meaningful in its first lane)
-                        const int len = (in && isstart) ? nend - lane : 0;
-                        const int maxlen = __reduce_max_sync(0xffffffffu, len);
-                        double best = sc;
-                        uint32_t bkey = key;
-                        bool chosen = in && sc > -1.0;
-                        for (int k = 1; k < maxlen; ++k) {                      // the other links of the node, one shuffle distance at a time
-                            const double osc = __shfl_down_sync(0xffffffffu, sc, k);
-                            const uint32_t okey = __shfl_down_sync(0xffffffffu, key, k);
-                            if (lane + k < nend && osc > -1.0 &&
-                                (!chosen || osc > best || (osc == best && (okey & 0xffff) < (bkey & 0xffff)))) { best = osc; bkey = okey; chosen = true; }
-                        }
-                        unsigned long long contrib = 0;
-                        if (in && isstart) {
-                            const double ns = chosen ? best : -1.0;
-                            SC[x & (SC_RING - 1)] = ns;
-                            if (spill) link[x].w = ns;
-                            const uint32_t b = (key >> 20) & 7;
-                            contrib = (unsigned long long)(chosen ? cns_bp_code(bkey) : 7u) << (11 * b);
-                            if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)b; g_t = t; g_delta = (int)(key >> 24); g_x = x; }
-                        }
-                        const uint32_t plo = __reduce_or_sync(0xffffffffu, (uint32_t)contrib);
-                        const uint32_t phi = __reduce_or_sync(0xffffffffu, (uint32_t)(contrib >> 32));
-                        if (lane == 0) {
-                            if (level < TP.level_cap) { CnsLevel L; L.packed = ((unsigned long long)phi << 32) | plo; L.prev_first_level = prev_fl; L.pad_ = 0; bp[level] = L; }
-                            else fail |= 1;
-                        }
-                        ++level;
-                        __syncwarp();
-                    }
-                } else {
-                    // ---- a crowded position: lane 0 scores it link by link, straight from HBM
-                    if (lane == 0) {
-                        bool have_node = false, have_level = false, chosen = false;
-                        uint32_t cur_d = 0, cur_b = 0, node_first = 0, best_key = 0;
-                        double best = -1.0;
-                        unsigned long long packed = 0;
-                        auto close_node = [&]() {
-                            const double ns = chosen ? best : -1.0;
-                            SC[node_first & (SC_RING - 1)] = ns;
-                            if (spill) link[node_first].w = ns;
-                            packed |= (unsigned long long)(chosen ? cns_bp_code(best_key) : 7u) << (11 * cur_b);
-                            if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)cur_d; g_x = node_first; }
-                        };
-                        auto put_level = [&]() {
-                            if (level < TP.level_cap) { CnsLevel L; L.packed = packed; L.prev_first_level = prev_fl; L.pad_ = 0; bp[level] = L; }
-                            else fail |= 1;
-                        };
-                        for (uint32_t x = s; x < e; ++x) {
-                            const uint4 lr = *reinterpret_cast<const uint4*>(link + x);
-                            const uint32_t key = lr.x, pred = lr.y;
-                            if ((key >> 23) & 1) {
-                                if (have_node) close_node();
-                                if ((key >> 19) & 1) {
-                                    if (have_level) { put_level(); ++level; }
-                                    have_level = true; packed = 0;
-                                }
-                                have_node = true; cur_b = (key >> 20) & 7; cur_d = key >> 24; node_first = x; best = -1.0; best_key = 0; chosen = false;
-                            }
-                            double sc = __dsub_rn(__hiloint2double((int)lr.w, (int)lr.z), pen);
-                            if (pred != CNS_NOPRED)
-                                sc = __dadd_rn(sc, (x - pred < (uint32_t)SC_RING) ? SC[pred & (SC_RING - 1)] : link[pred].w);
-                            const bool better = chosen ? (sc > best || (sc == best && (key & 0xffff) < (best_key & 0xffff))) : (sc > -1.0);
-                            if (better) { best = sc; best_key = key; chosen = true; }
-                        }
-                        if (have_node) close_node();
-                        if (have_level) { put_level(); ++level; }
-                    }
-                    level = __shfl_sync(0xffffffffu, level, 0);
-                    __syncwarp();
-                }
-                prev_fl = cur_fl;
+        if (ev & 0x02020202u) {
+            if (unsure) {
+                const uint32_t left = c_end - c;
+                const uint32_t need = seq + (left < CNS_DP_G + 1 ? left : CNS_DP_G + 1);
+                while (fseq < need && f < f_end) issue();
             }
-            if (fl & 4) {
-                // ---- the run ends at t: its best node (cns_aux.c:177-184) = highest score, first in traversal order
-                double mx = g_best;
+            cns_cp_async_commit();
+            cns_cp_async_wait(0);
+        } else cns_cp_async_wait(CNS_DP_PEND);
+        __syncwarp();
+        if (ev & 0x0c0c0c0cu) {
+            if (ev & 0x04040404u) {
+                // the best node of the run that ended (cns_aux.c:177-184): highest score, first in traversal order
+                double mx = e_best;
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, mx, d); mx = o > mx ? o : mx; }
-                const uint32_t cand = __ballot_sync(0xffffffffu, g_best == mx);
-                const uint32_t mnx = __reduce_min_sync(0xffffffffu, g_best == mx ? g_x : 0xffffffffu);
-                const uint32_t win = __ballot_sync(0xffffffffu, g_best == mx && g_x == mnx) & cand;
-                const int wl = __ffs(win) - 1;
-                const int r_level = __shfl_sync(0xffffffffu, g_level, wl), r_b = __shfl_sync(0xffffffffu, g_b, wl);
-                const int r_t = __shfl_sync(0xffffffffu, g_t, wl), r_delta = __shfl_sync(0xffffffffu, g_delta, wl);
-                if (lane == 0 && nrun < TP.seg_cap) {
-                    CnsRun r; r.from = run_from; r.to = t + 1; r.g_level = r_level; r.g_b = r_b; r.g_t = r_t; r.g_delta = r_delta;
-                    my_runs[nrun] = r;
+                for (int d = 4; d > 0; d >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, mx, d, CNS_DP_G); mx = o > mx ? o : mx; }
+                uint32_t mnx = e_best == mx ? e_x : 0xffffffffu;
+#pragma unroll
+                for (int d = 4; d > 0; d >>= 1) { const uint32_t o = __shfl_xor_sync(0xffffffffu, mnx, d, CNS_DP_G); mnx = o < mnx ? o : mnx; }
+                const uint32_t win = (__ballot_sync(0xffffffffu, e_best == mx && e_x == mnx) >> gsh) & 0xffu;
+                const int wl = win ? __ffs(win) - 1 : 0;
+                const int r_level = __shfl_sync(0xffffffffu, e_level, wl, CNS_DP_G), r_b = __shfl_sync(0xffffffffu, e_b, wl, CNS_DP_G);
+                const int r_t = __shfl_sync(0xffffffffu, e_t, wl, CNS_DP_G), r_delta = __shfl_sync(0xffffffffu, e_delta, wl, CNS_DP_G);
+                if (pend_emit) {
+                    if (gl == 0 && run_emitted < n_runs) {
+                        CnsRun r = my_runs[run_emitted];                // from and first_level were written at the run's start
+                        r.to = e_end + 1; r.g_level = r_level; r.g_b = r_b; r.g_t = r_t; r.g_delta = r_delta;
+                        my_runs[run_emitted] = r;
+                    }
+                    ++run_emitted;
+                    pend_emit = false;
                 }
-                ++nrun;
+            }
+            if (ev & 0x08080808u) {
+                // ---- a level of more than 8 links: the group's first lane scores it link by link
+                if (pend_serial && gl == 0) {
+                    bool have_node = false, chosen = false;
+                    uint32_t cur_b = 0, node_first = 0, best_key = 0, x = c, xs = seq;
+                    const uint32_t cur_d = link[c].key >> 24;
+                    double best = -1.0;
+                    auto close_node = [&]() {
+                        const double ns = chosen ? best : -1.0;
+                        SC[node_first & (SR - 1)] = ns;
+                        if (level < TP.level_cap) bp16[(size_t)level * 8 + cur_b] = (uint16_t)(chosen ? cns_bp_code(best_key) : 7u);
+                        if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)cur_d; g_x = node_first; }
+                    };
+                    for (; x < c_end; ++x, ++xs) {
+                        const uint4 e = *reinterpret_cast<const uint4*>(link + x);
+                        if (x != c && (e.x & CNS_K_LEVEL)) break;
+                        if (e.x & CNS_K_NODE) {
+                            if (have_node) close_node();
+                            have_node = true; cur_b = (e.x >> 20) & 7; node_first = xs; best = -1.0; best_key = 0; chosen = false;
+                        }
+                        double sc = __hiloint2double((int)e.w, (int)e.z);
+                        if (e.y != CNS_NOPRED) {
+                            const uint32_t ps = cur_d ? p_seq + (e.y - p_abs) : q_seq + (e.y - q_abs);
+                            if (xs - ps >= (uint32_t)SR) redo = true;
+                            sc = __dadd_rn(sc, SC[ps & (SR - 1)]);
+                        }
+                        const bool better = chosen ? (sc > best || (sc == best && CNS_K_RANK(e.x) < CNS_K_RANK(best_key))) : (sc > -1.0);
+                        if (better) { best = sc; best_key = e.x; chosen = true; }
+                    }
+                    if (have_node) close_node();
+                    if (level < TP.level_cap) bp[level].w = prev_fl; else fail |= 1;
+                    c = x; seq = xs;
+                }
+                const uint32_t c2 = __shfl_sync(0xffffffffu, c, 0, CNS_DP_G), s2 = __shfl_sync(0xffffffffu, seq, 0, CNS_DP_G);
+                const int r2 = __shfl_sync(0xffffffffu, (int)redo, 0, CNS_DP_G);
+                if (pend_serial) {
+                    c = c2; seq = s2; redo = r2 != 0;
+                    ++level;
+                    if (c == c_end) next_span(ck, c, c_end);
+                    if (ck >= n_spans || redo) done = true;
+                    pend_serial = false;
+                }
+                __syncwarp();
+            }
+            if (done && p_last && !redo) {              // the stream ended inside a run's last position
+                pend_emit = true; p_last = false;
+                e_best = g_best; e_level = g_level; e_b = g_b; e_t = g_t; e_delta = g_delta; e_x = g_x; e_end = t;
             }
         }
-        pc = pn;
-        pn = load_pos(t0 + 64);
+        // ---- the next 8 links of the stream
+        const bool valid = !done && c + gl < c_end;
+        uint4 lr = make_uint4(CNS_K_LEVEL | CNS_K_NODE, CNS_NOPRED, 0, 0);         // past the end: looks like the start of a position
+        if (valid) lr = LK[(seq + gl) & (LR - 1)];
+        const uint32_t peek = LK[(seq + CNS_DP_G) & (LR - 1)].x;
+        const uint32_t key = lr.x, pred = lr.y;
+        const double base = __hiloint2double((int)lr.w, (int)lr.z);
+        const bool is_ls = (key & CNS_K_LEVEL) != 0, is_ps = is_ls && (key >> 24) == 0;
+        const uint32_t bL = (__ballot_sync(0xffffffffu, is_ls) >> gsh) & 0xffu;
+        const uint32_t bP = (__ballot_sync(0xffffffffu, is_ps) >> gsh) & 0xffu;
+        // ---- extent of the trip: whole levels of one position
+        int take;
+        {
+            const uint32_t stop = bP & ~1u;
+            const int e = stop ? __ffs(stop) - 1 : CNS_DP_G;
+            if (e < CNS_DP_G) take = e;
+            else if (!(c + CNS_DP_G < c_end) || (peek & CNS_K_LEVEL)) take = CNS_DP_G;
+            else { const uint32_t hi = bL & ~1u; take = hi ? 31 - __clz(hi) : 0; }        // 0: a level of more than 8 links
+        }
+        if (done) take = 0;
+        if (!done && take == 0) pend_serial = true;
+        const bool in = gl < take;
+        const uint32_t bT = __ballot_sync(0xffffffffu, in);
+        const uint32_t bN = __ballot_sync(0xffffffffu, in && (key & CNS_K_NODE));
+        const uint32_t tm = (bT >> gsh) & 0xffu;
+        const int nlev = __popc(bL & tm);
+        const int mylev = __popc(bL & tm & le8) - 1;
+        int maxlev;
+        {
+            const uint32_t lv = __ballot_sync(0xffffffffu, in && is_ls);
+            const int l0 = __popc(lv & 0xffu), l1 = __popc(lv & 0xff00u), l2 = __popc(lv & 0xff0000u), l3 = __popc(lv & 0xff000000u);
+            const int m0 = l0 > l1 ? l0 : l1, m1 = l2 > l3 ? l2 : l3;
+            maxlev = m0 > m1 ? m0 : m1;
+        }
+        const uint32_t nonstart = bT & ~bN;
+        const bool long_nodes = (nonstart & (nonstart >> 1) & 0x7f7f7f7fu) != 0;           // some node has three or more links
+        // ---- position / run bookkeeping (uniform inside the group)
+        const uint32_t key0 = __shfl_sync(0xffffffffu, key, 0, CNS_DP_G);
+        if (!done && c < c_end && (key0 >> 24) == 0) {                                      // the trip starts a position
+            if (p_last) {                                                                  // ... and the previous one ended a run
+                pend_emit = true;
+                e_best = g_best; e_level = g_level; e_b = g_b; e_t = g_t; e_delta = g_delta; e_x = g_x; e_end = t;
+            }
+            q_abs = p_abs; q_seq = p_seq; p_abs = c; p_seq = seq;
+            prev_fl = cur_fl; cur_fl = level;
+            if (key0 & CNS_K_RUNFIRST) {
+                t = run_started < n_runs ? my_runs[run_started].from : 0;
+                g_best = -1.0; g_level = -1; g_x = 0xffffffffu;
+                if (gl == 0 && run_started < n_runs) my_runs[run_started].first_level = level;
+                ++run_started;
+            } else ++t;
+            p_last = (key0 & CNS_K_RUNLAST) != 0;
+        }
+        // ---- predecessors scored in earlier trips come from the ring, those of this trip from their lane
+        const bool has_pred = in && pred != CNS_NOPRED;                     // never-scored predecessors count 0 (cns_aux.c:63-70)
+        uint32_t pseq = seq;
+        if (has_pred) pseq = (key >> 24) ? p_seq + (pred - p_abs) : q_seq + (pred - q_abs);
+        const bool in_trip = has_pred && pseq >= seq;
+        double rs = 0.0;
+        if (has_pred && !in_trip) {
+            if (seq + gl - pseq >= (uint32_t)SR) redo = true;
+            rs = SC[pseq & (SR - 1)];
+        }
+        const int src = in_trip ? (int)(pseq - seq) : 0;
+        const bool isstart = in && (key & CNS_K_NODE);
+        const uint32_t above = ((bN >> gsh) & 0xffu) & ~le8;
+        const int nend = above ? __ffs(above) - 1 : take;                   // my node ends here (meaningful in its first lane)
+        double nsc = -1.0, sc = base;
+        uint32_t bkey = key;
+        for (int lv = 0; lv < maxlev; ++lv) {
+            const double from = __shfl_sync(0xffffffffu, nsc, src, CNS_DP_G);
+            const bool act = in && mylev == lv;
+            if (act && has_pred) sc = __dadd_rn(base, in_trip ? from : rs);
+            // the links of a node are adjacent lanes of one level
+            double best = sc;
+            uint32_t bk = key;
+            bool chosen = act && sc > -1.0;
+            {
+                const double osc = __shfl_down_sync(0xffffffffu, sc, 1, CNS_DP_G);
+                const uint32_t okey = __shfl_down_sync(0xffffffffu, key, 1, CNS_DP_G);
+                if (gl + 1 < nend && osc > -1.0 &&
+                    (!chosen || osc > best || (osc == best && CNS_K_RANK(okey) < CNS_K_RANK(bk)))) { best = osc; bk = okey; chosen = true; }
+            }
+            if (long_nodes) {
+                for (int k = 2; k < CNS_DP_G; ++k) {
+                    const double osc = __shfl_down_sync(0xffffffffu, sc, k, CNS_DP_G);
+                    const uint32_t okey = __shfl_down_sync(0xffffffffu, key, k, CNS_DP_G);
+                    if (gl + k < nend && osc > -1.0 &&
+                        (!chosen || osc > best || (osc == best && CNS_K_RANK(okey) < CNS_K_RANK(bk)))) { best = osc; bk = okey; chosen = true; }
+                }
+            }
+            if (act && isstart) { nsc = chosen ? best : -1.0; bkey = chosen ? bk : 0u; }
+        }
+        __syncwarp();                                                       // every score of the ring was read before it is overwritten
+        if (isstart) {
+            const uint32_t lvl = level + (uint32_t)mylev;
+            SC[(seq + gl) & (SR - 1)] = nsc;
+            const uint32_t b = (key >> 20) & 7;
+            if (lvl < TP.level_cap) bp16[(size_t)lvl * 8 + b] = (uint16_t)cns_bp_code(bkey);
+            else fail |= 1;
+            if (nsc > g_best) { g_best = nsc; g_level = (int)lvl; g_b = (int)b; g_t = t; g_delta = (int)(key >> 24); g_x = seq + gl; }
+        }
+        if (in && is_ls) { const uint32_t lvl = level + (uint32_t)mylev; if (lvl < TP.level_cap) bp[lvl].w = prev_fl; }
+        redo = ((__ballot_sync(0xffffffffu, redo) >> gsh) & 0xffu) != 0;
+        if (!done) {
+            level += (uint32_t)nlev;
+            c += (uint32_t)take; seq += (uint32_t)take;
+            if (c == c_end) next_span(ck, c, c_end);
+            if (ck >= n_spans || redo) done = true;
+            // have the links of the next trip landed for sure?
+            const uint32_t left = c_end - c;
+            unsure = !done && seq + (left < CNS_DP_G + 1 ? left : CNS_DP_G + 1) + CNS_DP_G * CNS_DP_PEND > fseq;
+        }
+        if (done && p_last && !redo && !pend_emit) {
+            pend_emit = true; p_last = false;
+            e_best = g_best; e_level = g_level; e_b = g_b; e_t = g_t; e_delta = g_delta; e_x = g_x; e_end = t;
+        }
     }
     cns_cp_async_wait(0);
-    if (lane == 0) {
-        if (fail) atomicOr(P.error_flag, fail);
-        if (nrun > TP.seg_cap) { atomicOr(P.error_flag, 4u); nrun = TP.seg_cap; }
-        tpl_nrun[ti] = nrun;
-        atomicAdd(P.counters + 0, (unsigned long long)level);
+    if (gl == 0 && slot < P.n_tpl) {
+        if (redo) P.redo[atomicAdd(P.n_redo, 1u)] = ti;
+        else {
+            if (fail) atomicOr(P.error_flag, fail);
+            atomicAdd(P.counters + 0, (unsigned long long)level);
+        }
     }
 }
 
-// Walk-back of the runs of one template per thread (cns_aux.c:187-212).
+// The same recurrence for the templates k_cns_dp could not finish (a predecessor further back than its score ring):
+// one thread per template, node scores kept in the first link of each node in HBM.
 __global__ void __launch_bounds__(128)
-k_cns_walk(CnsParams P, const CnsRun* __restrict__ runs, const uint32_t* __restrict__ tpl_nrun)
+k_cns_dp_serial(CnsParams P)
 {
-    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((int)(gt & 31) >= P.walk_lanes) return;
-    const uint32_t ti = (gt >> 5) * (uint32_t)P.walk_lanes + (gt & 31);
-    if (ti >= P.n_tpl) return;
+    const uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ri >= *P.n_redo) return;
+    const uint32_t ti = P.redo[ri];
     const CnsTemplate TP = P.tpl[ti];
+    CnsLink* link = P.link + TP.link_base;
+    CnsLevel* bp = P.bp + TP.level_base;
+    CnsRun* my_runs = P.runs + TP.seg_first;
+    const uint32_t n_runs = P.tpl_nrun[ti];
+    uint32_t level = 0, cur_fl = 0, prev_fl = 0, run = 0, fail = 0;
+    int t = 0, node_t = 0;
+    bool have_node = false, have_level = false, chosen = false;
+    double g_best = -1.0, best = -1.0;
+    int g_level = -1, g_b = -1, g_t = 0, g_delta = 0;
+    uint32_t cur_b = 0, cur_d = 0, node_first = 0, best_key = 0;
+    auto close_node = [&]() {
+        const double ns = chosen ? best : -1.0;
+        link[node_first].w = ns;
+        if (level < TP.level_cap) bp[level].code[cur_b] = (uint16_t)(chosen ? cns_bp_code(best_key) : 7u);
+        if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = node_t; g_delta = (int)cur_d; }
+        have_node = false;
+    };
+    auto close_level = [&]() {
+        if (level < TP.level_cap) bp[level].prev_first_level = prev_fl;
+        else fail |= 1;
+        ++level; have_level = false;
+    };
+    auto close_run = [&]() {
+        if (run < n_runs) {
+            CnsRun r = my_runs[run];
+            r.to = t + 1; r.g_level = g_level; r.g_b = g_b; r.g_t = g_t; r.g_delta = g_delta;
+            my_runs[run] = r;
+        }
+        ++run;
+    };
     const CnsPos* pos = P.pos + TP.pos_base;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const int from = my_runs[r].from, to = my_runs[r].to;
+        g_best = -1.0; g_level = -1;
+        my_runs[r].first_level = level;
+        for (t = from; t < to; ++t) {
+            const CnsPos ps = pos[t];
+            if (ps.n) {
+                if (have_node) close_node();
+                if (have_level) close_level();
+                prev_fl = cur_fl; cur_fl = level;
+            }
+            for (uint32_t x = ps.start; x < ps.start + ps.n; ++x) {
+                const uint4 e = *reinterpret_cast<const uint4*>(link + x);
+                const uint32_t key = e.x;
+                if (key & CNS_K_NODE) {
+                    if (have_node) close_node();
+                    if (key & CNS_K_LEVEL) {
+                        if (have_level) close_level();
+                        have_level = true;
+                    }
+                    have_node = true; cur_b = (key >> 20) & 7; cur_d = key >> 24; node_first = x; node_t = t; best = -1.0; best_key = 0; chosen = false;
+                }
+                double sc = __hiloint2double((int)e.w, (int)e.z);
+                if (e.y != CNS_NOPRED) sc = __dadd_rn(sc, link[e.y].w);
+                const bool better = chosen ? (sc > best || (sc == best && CNS_K_RANK(key) < CNS_K_RANK(best_key))) : (sc > -1.0);
+                if (better) { best = sc; best_key = key; chosen = true; }
+            }
+        }
+        if (have_node) close_node();
+        if (have_level) close_level();
+        t = to - 1;
+        close_run();
+    }
+    if (fail) atomicOr(P.error_flag, fail);
+    atomicAdd(P.counters + 0, (unsigned long long)level);
+}
+
+// ------------------------------------------------------------------ walk-back of the runs (cns_aux.c:187-212)
+// One warp per template.  The walk is a pointer chase over the level records, always towards smaller level indices and
+// never more than the levels of two positions at a time: the warp stages a window of CNS_WALK_WIN records in shared
+// memory, its first lane walks inside it and collects the emitted bases in shared memory, the warp writes them out.
+#define CNS_WALK_WIN 512
+#define CNS_WALK_OUT 512
+
+__global__ void __launch_bounds__(128)
+k_cns_walk(CnsParams P)
+{
+    __shared__ __align__(16) uint4 s_win[4][CNS_WALK_WIN];
+    __shared__ uint8_t s_out[4][CNS_WALK_OUT];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t ti = blockIdx.x * 4 + wid;
+    if (ti >= P.n_tpl) return;
+    uint4* W = s_win[wid];
+    uint8_t* O = s_out[wid];
+    const CnsTemplate TP = P.tpl[ti];
     const CnsLevel* bp = P.bp + TP.level_base;
     uint8_t* rev = P.rev + TP.level_base;
-    const uint32_t nrun = tpl_nrun[ti];
+    const uint32_t nrun = P.tpl_nrun[ti];
     uint32_t nseg = 0, out_used = 0, fail = 0;
     for (uint32_t k = 0; k < nrun; ++k) {
-        const CnsRun R = runs[TP.seg_first + k];
+        const CnsRun R = P.runs[TP.seg_first + k];
         if (R.g_level < 0) continue;
         int cs = R.g_level, cb = R.g_b, ct = R.g_t, cd = R.g_delta;
-        uint8_t* out = rev + pos[R.from].first_level;        // a run emits at most one base per level
+        uint8_t* out = rev + R.first_level;                 // a run emits at most one base per level
         uint32_t n = 0;
         int cns_from = 0;
-        for (;;) {
-            const uint4 lv = *reinterpret_cast<const uint4*>(bp + cs);             // packed (x, y), prev_first_level (z)
-            const uint32_t code = (uint32_t)((((unsigned long long)lv.y << 32) | lv.x) >> (11 * cb)) & 0x7ff;
-            const uint32_t pb = code & 7;
-            if (pb == 7) break;                         // best_p_t_pos == -1: this node is not emitted
-            const int emit = cb;
-            int ns, nt, nd;
-            bool stop_after = false;
-            if (cd > 0) { ns = cs - 1; nt = ct; nd = cd - 1; }
-            else {
-                nt = ct - 1; nd = (int)(code >> 3);
-                if (nt < R.from) { stop_after = true; ns = 0; }     // predecessor outside the run: never scored
-                else ns = (int)lv.z + nd;
+        bool finished = false;
+        while (!finished) {
+            // window [wlo, cs]
+            const int wlo = cs + 1 > CNS_WALK_WIN ? cs + 1 - CNS_WALK_WIN : 0;
+            for (int i = lane; i <= cs - wlo; i += 32) W[i] = *reinterpret_cast<const uint4*>(bp + wlo + i);
+            __syncwarp();
+            uint32_t no = 0;
+            if (lane == 0) {
+                while (cs >= wlo && no < CNS_WALK_OUT) {
+                    const uint4 lv = W[cs - wlo];                                           // five 16-bit codes (x, y, z), prev_first_level (w)
+                    const uint32_t word = cb < 2 ? lv.x : (cb < 4 ? lv.y : lv.z);
+                    const uint32_t code = (word >> ((cb & 1) << 4)) & 0xffffu;
+                    const uint32_t pb = code & 7;
+                    if (pb == 7) { finished = true; break; }    // best_p_t_pos == -1: this node is not emitted
+                    const int emit = cb;
+                    int ns, nt, nd;
+                    bool stop_after = false;
+                    if (cd > 0) { ns = cs - 1; nt = ct; nd = cd - 1; }
+                    else {
+                        nt = ct - 1; nd = (int)(code >> 3);
+                        if (nt < R.from) { stop_after = true; ns = 0; }     // predecessor outside the run: never scored
+                        else ns = (int)lv.w + nd;
+                    }
+                    cns_from = nt;
+                    if (emit != 4) O[no++] = (uint8_t)emit;
+                    if (stop_after) { finished = true; break; }
+                    cs = ns; cb = (int)pb; ct = nt; cd = nd;
+                }
             }
-            cns_from = nt;
-            if (emit != 4) { out[n] = (uint8_t)emit; ++n; }
-            if (stop_after) break;
-            cs = ns; cb = (int)pb; ct = nt; cd = nd;
+            __syncwarp();
+            no = __shfl_sync(0xffffffffu, no, 0);
+            finished = __shfl_sync(0xffffffffu, (int)finished, 0) != 0;
+            cs = __shfl_sync(0xffffffffu, cs, 0); cb = __shfl_sync(0xffffffffu, cb, 0);
+            ct = __shfl_sync(0xffffffffu, ct, 0); cd = __shfl_sync(0xffffffffu, cd, 0);
+            cns_from = __shfl_sync(0xffffffffu, cns_from, 0);
+            for (uint32_t i = lane; i < no; i += 32) out[n + i] = O[i];
+            n += no;
+            __syncwarp();
         }
         if ((int)n >= P.min_size) {
             if (nseg < TP.seg_cap && out_used + n <= TP.out_cap) {
                 uint8_t* dst = P.seq_pool + TP.out_base + out_used;
-                for (uint32_t i = 0; i < n; ++i) dst[i] = out[n - 1 - i];
-                CnsSegment sg;
-                sg.left = R.from; sg.right = R.to; sg.cns_from = cns_from; sg.cns_to = R.g_t + 1;
-                sg.len = n; sg.pad_ = 0; sg.seq_off = TP.out_base + out_used;
-                P.seg[TP.seg_first + nseg] = sg;
+                __syncwarp();
+                for (uint32_t i = lane; i < n; i += 32) dst[i] = out[n - 1 - i];
+                if (lane == 0) {
+                    CnsSegment sg;
+                    sg.left = R.from; sg.right = R.to; sg.cns_from = cns_from; sg.cns_to = R.g_t + 1;
+                    sg.len = n; sg.pad_ = 0; sg.seq_off = TP.out_base + out_used;
+                    P.seg[TP.seg_first + nseg] = sg;
+                }
                 ++nseg; out_used += n;
             } else fail |= 4;
         }
     }
-    if (fail) atomicOr(P.error_flag, fail);
-    P.tpl_nseg[ti] = nseg;
+    if (lane == 0) {
+        if (fail) atomicOr(P.error_flag, fail);
+        P.tpl_nseg[ti] = nseg;
+    }
 }

@@ -67,16 +67,18 @@ def test_cns_multi_volume(built, tmp_path):
 
 
 @pytest.mark.parametrize("env", [
-    {"NB_CNS_DP_TEST": "1"},                        # k_cns_dp with a 3-link fast path and a score ring of 8: serial + spill paths
-    {"NB_CNS_WALK_LANES": "32"}, {"NB_CNS_FLUSH_SLOW": "1"}, {"NB_CNS_LINKS_MULTI": "1"},
-    {"NB_CNS_SLICES": "4"},
+    {"NB_CNS_DP_TEST": "1"},                        # k_cns_dp with a score ring of 8: most templates are redone by k_cns_dp_serial
+    {"NB_CNS_DP_TEST": "2"},                        # every template through k_cns_dp_serial
+    {"NB_CNS_FLUSH_SLOW": "1"},                     # k_cns_links: the selection flush for every position
+    {"NB_CNS_SPAN": "64"},                          # k_cns_links: one tile per unit, a checkpoint every 64 positions
+    {"NB_CNS_SPAN": "192", "NB_CNS_DP_TEST": "1"},
     {"NB_CNS_CHUNKS": "5", "NB_CNS_PIPES": "3"},    # the chunk pipeline: three workers on their own streams
     {"NB_CNS_CHUNKS": "2", "NB_CNS_PIPES": "1"},
     {"NB_CNS_GROUPS": "4", "NB_CNS_GROUPS_MIN": "8"},   # extension rounds of four template groups interleaved on the GPU
     {"NB_CNS_GROUPS": "3", "NB_CNS_GROUPS_MIN": "8", "NB_CNS_LONG": "1", "NB_CNS_LONG_MIN": "8"},   # + the longest templates' consensus beside the extension
 ])
 def test_cns_kernel_variants(built, tmp_path, env):
-    """The tunables of the consensus kernels (templates per warp, score-ring size, sliced launch) change
+    """The tunables of the consensus kernels (span length, score-ring size, flush path, pipelines) change
     the schedule, never the result."""
     wrk, _ = util.make_workdir(tmp_path, genome=70_000, depth=30, seed=46, err=0.12)
     cand = str(tmp_path / "cand.bin")

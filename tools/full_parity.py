@@ -106,7 +106,11 @@ def iterations_main(a):
             os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
             json.dump(res, open(a.out, "w"), indent=1)
     finally:
-        shutil.rmtree(td, ignore_errors=True)
+        if a.keep:
+            shutil.rmtree(a.keep, ignore_errors=True)
+            shutil.move(td, a.keep)
+        else:
+            shutil.rmtree(td, ignore_errors=True)
 
 
 def main():
@@ -121,6 +125,7 @@ def main():
     ap.add_argument("--iterations", type=int, default=1, help=">= 2: chain correction iterations like necat.pl (see iterations_main)")
     ap.add_argument("--pm2", default="-k 15 -z 20 -q 500 -b 2000 -s 3 -n 500 -a 1000 -d 0.25 -e 0.5 -m 500 -j 0 -u 1 -i 1")
     ap.add_argument("--cns2", default="-a 2000 -x 4 -y 12 -l 1000 -e 0.5 -p 0.8 -u 0 -r 1 -f 0")
+    ap.add_argument("--keep", default=None, help="--iterations: keep the work directory of the run under this path (for profiling)")
     ap.add_argument("--gpu-bins", default=None, help="directory of the executables of the first arm (default necat_b200/bin)")
     a = ap.parse_args()
     if a.iterations > 1:
