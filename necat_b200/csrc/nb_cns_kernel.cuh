@@ -886,8 +886,9 @@ k_cns_dp(CnsParams P)
             const int m0 = l0 > l1 ? l0 : l1, m1 = l2 > l3 ? l2 : l3;
             maxlev = m0 > m1 ? m0 : m1;
         }
-        const uint32_t nonstart = bT & ~bN;
-        const bool long_nodes = (nonstart & (nonstart >> 1) & 0x7f7f7f7fu) != 0;           // some node has three or more links
+        // longest node of the warp's trips: runs of lanes that continue the node of the lane below
+        int extra = 0;
+        for (uint32_t r = bT & ~bN; r; r = r & (r >> 1) & 0x7f7f7f7fu) ++extra;
         // ---- position / run bookkeeping (uniform inside the group)
         const uint32_t key0 = __shfl_sync(0xffffffffu, key, 0, CNS_DP_G);
         if (!done && c < c_end && (key0 >> 24) == 0) {                                      // the trip starts a position
@@ -929,19 +930,11 @@ k_cns_dp(CnsParams P)
             double best = sc;
             uint32_t bk = key;
             bool chosen = act && sc > -1.0;
-            {
-                const double osc = __shfl_down_sync(0xffffffffu, sc, 1, CNS_DP_G);
-                const uint32_t okey = __shfl_down_sync(0xffffffffu, key, 1, CNS_DP_G);
-                if (gl + 1 < nend && osc > -1.0 &&
+            for (int k = 1; k <= extra; ++k) {
+                const double osc = __shfl_down_sync(0xffffffffu, sc, k, CNS_DP_G);
+                const uint32_t okey = __shfl_down_sync(0xffffffffu, key, k, CNS_DP_G);
+                if (gl + k < nend && osc > -1.0 &&
                     (!chosen || osc > best || (osc == best && CNS_K_RANK(okey) < CNS_K_RANK(bk)))) { best = osc; bk = okey; chosen = true; }
-            }
-            if (long_nodes) {
-                for (int k = 2; k < CNS_DP_G; ++k) {
-                    const double osc = __shfl_down_sync(0xffffffffu, sc, k, CNS_DP_G);
-                    const uint32_t okey = __shfl_down_sync(0xffffffffu, key, k, CNS_DP_G);
-                    if (gl + k < nend && osc > -1.0 &&
-                        (!chosen || osc > best || (osc == best && CNS_K_RANK(okey) < CNS_K_RANK(bk)))) { best = osc; bk = okey; chosen = true; }
-                }
             }
             if (act && isstart) { nsc = chosen ? best : -1.0; bkey = chosen ? bk : 0u; }
         }

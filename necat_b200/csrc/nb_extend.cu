@@ -32,48 +32,50 @@ __device__ __forceinline__ int seq_base(const SeqView& v, int idx)
     return v.strand ? 3 - b : b;
 }
 
-// Shared memory of one warp.  A warp works on TWO candidates at a time: a 512-row block fills only 16 of the 32
-// lanes of the forward pass, so the two half-warps run the forward passes of two different candidates side by
-// side; everything else (block loading, walk-back, bookkeeping) is done by the whole warp, one candidate after
-// the other.
-struct HalfScratch {
-    uint8_t q[EXT_MAX_BLK];
-    uint8_t t[EXT_MAX_BLK + 64];        // padded: lane 0 of the forward pass reads up to 31 columns past the block
-};
+// ---------------------------------------------------------------------------------------------------------------------
+// A warp keeps EXT_SLOTS = 32 candidates in flight, lane = slot.  The pieces of a candidate's state machine that are one
+// dependent chain per candidate -- cutting the next block, the walk-back over the (Pv, Ph) bits, the bookkeeping
+// between blocks -- run with every lane on its own candidate; the forward passes, which have 16 to 26 independent
+// 32-row words per DP column, are run by the whole warp, two candidates at a time in its two halves.
+//
+// Only the words of a DP column that lie within +-48 rows (at least) of the block's diagonal are kept for the walk-back:
+// 4 words per column instead of 16-26 (8 words, +-112 rows around the middle between the diagonal and the end cell, for
+// the last block of a side, whose two sides differ by up to 30 %).  A walk that leaves the band (the path of a 512-column
+// block of 15 %-error reads wanders ~10 rows) makes the forward pass of that block run again with the band centred on
+// the diagonal the walk has reached, and continues from where it stopped.
+#define EXT_SLOTS 32
+#define EXT_BAND_WORDS 8        // at most
 
-// State of one candidate in flight (shared memory: written by lane 0, read by the whole warp).
-struct ExtCtx {
-    int      active;
-    uint32_t ti;
-    uint64_t qoff_, toff_;              // volume offsets of the two reads
-    int      qlen, qstrand, tlen;
-    uint64_t ops_base;
-    int      lcap;
-    int      QS, TS;                    // extension origin; moved to the start of the kept left part afterwards
-    int      phase;                     // 0 = left of the seed, 1 = right of it
-    int      q_origin, t_origin, q_total, t_total, dir;
-    long long out_base;                 // column x of the current side lives at ops[out_base + x * out_dir]
-    int      out_dir;
-    int      qidx, tidx, ncol;
-    int      qblk, tblk, last;          // current block
-    int      best, bestj;               // forward pass result
-    int      L, left_keep, acnt;        // left side: columns, kept columns, columns cut at the seed end
+enum {
+    X_STATE, X_TI, X_QOFF_LO, X_QOFF_HI, X_TOFF_LO, X_TOFF_HI, X_QLEN, X_QSTRAND, X_TLEN, X_OPS_LO, X_OPS_HI, X_LCAP, X_QS, X_TS,
+    X_PHASE, X_QORG, X_TORG, X_QTOT, X_TTOT, X_DIR, X_OUTB, X_OUTDIR, X_QIDX, X_TIDX, X_NCOL, X_QBLK, X_TBLK, X_LAST,
+    X_BEST, X_BESTJ, X_L, X_LKEEP, X_ACNT, X_SHIFT, X_NBW,
+    X_WI, X_WJ, X_WR, X_WFLAGS, X_WACNT, X_WQCNT, X_WTCNT, X_WM, X_WACC,
+    X_NF
+};
+enum { ST_IDLE = 0, ST_BLOCK = 1, ST_WALK = 2, ST_FINISH = 3 };
+
+struct HalfScratch {
+    uint8_t q[EXT_MAX_BLK + 32];        // the block's bases start at q[qa]: 16-base words are unpacked at 16-byte boundaries
+    uint8_t t[EXT_MAX_BLK + 96];        // likewise; lane 0 of the forward pass reads up to 31 columns past the block
 };
 
 struct WarpScratch {
     HalfScratch h[2];
-    uint8_t     rev[2 * EXT_MAX_BLK];
-    ExtCtx      ctx[2];
+    int32_t     f[X_NF][EXT_SLOTS];     // state of the 32 candidates, one field per row: f[field][slot]
 };
+
+#define XF(field, slot) S.f[field][slot]
 
 // Forward pass over one block, WIDTH lanes per block (16: two blocks per warp, 32: one).  Lane `lid` of the group
 // owns query rows [32 lid, 32 lid + 32) and works on column s - lid at step s.  What travels from lane to lane
 // with one shuffle per step is the horizontal delta of the row above (bit 31: +1, bit 30: -1) together with the
 // symbol of that column (bits 0..1) -- the neighbour needs exactly that column next; the four match masks stay
-// in registers.  Returns the best prefix distance and its column in every lane of the group.
+// in registers.  (Pv, Ph) of a word goes to mat[col][k], k = word - first word of the column's band.
+// Returns the best prefix distance and its column in every lane of the group.
 template <int WIDTH>
 __device__ __forceinline__ void myers_forward(const uint8_t* __restrict__ sq, const uint8_t* __restrict__ st, int qblk, int tblk,
-                                              uint2* __restrict__ mat, int lid, int* best_out, int* bestj_out)
+                                              uint2* __restrict__ mat, int shift, int nbw, int lid, int* best_out, int* bestj_out)
 {
     const int nw = (qblk + 31) >> 5;
     uint32_t pe0 = 0, pe1 = 0, pe2 = 0, pe3 = 0;
@@ -94,9 +96,9 @@ __device__ __forceinline__ void myers_forward(const uint8_t* __restrict__ sq, co
     int nsteps = qblk > 0 ? tblk + nw - 1 : 0;
     if (WIDTH < 32) { const int o = __shfl_xor_sync(0xffffffffu, nsteps, WIDTH); nsteps = nsteps > o ? nsteps : o; }
     const bool mine = lid < nw;
-    uint2* mp = mat + lid;                                  // skewed [step][lane] layout, advanced by nw per step
+    const int u0 = 16 + shift - lid, hb = nbw >> 1;         // band of column c: words ((c + 16 + shift) >> 5) - nbw / 2 .. + nbw / 2 - 1
     uint32_t cout = 0;
-    for (int s = 0; s < nsteps; ++s, mp += nw) {
+    for (int s = 0; s < nsteps; ++s) {
         uint32_t cin = __shfl_up_sync(0xffffffffu, cout, 1, WIDTH);
         if (lid == 0) cin = 0x80000000u | (uint32_t)(st[s] & 3);        // row 0 of the matrix: D[0][j] = j
         const int col = s - lid;
@@ -116,151 +118,72 @@ __device__ __forceinline__ void myers_forward(const uint8_t* __restrict__ sq, co
             const uint32_t Mhs = __funnelshift_l(cin << 1, Mh, 1);      // (Mh << 1) | (hin < 0)
             Pv = Mhs | ~(Xv | Phs);
             Mv = Phs & Xv;
-            *mp = make_uint2(Pv, Ph);
+            const int k = lid + hb - ((s + u0) >> 5);
+            if ((unsigned)k < (unsigned)nbw) mat[col * nbw + k] = make_uint2(Pv, Ph);
         }
     }
     *best_out = __shfl_sync(0xffffffffu, best, lw, WIDTH);
     *bestj_out = __shfl_sync(0xffffffffu, bestj, lw, WIDTH);
 }
 
-// Walk back from (qblk, jstar).  Columns are produced last to first into `rev`.
-// Also reports the last run of M matches (counted from the end, oc_aligner.c:225-240).
-//
-// The walk reads the (Pv, Ph) scratch through a register window of 32 columns x 32 diagonals: at a refill lane l
-// takes the two words of column j - l that hold rows i - l - 16 .. i - l + 15 and turns them into three masks
-// indexed by diagonal (bit dd <-> diagonal (i - j) + dd - 16): "cell = upper + 1", "cell = left + 1", "cell
-// exists".  Whatever path the walk takes inside the window, the state of the cell (i - k, j - k) is then one bit
-// test in lane l0 + k: every iteration resolves a whole run of diagonal moves with three ballots, plus the gap
-// move that ended it.
-struct WalkInfo { int asize, found, acnt, qcnt, tcnt; };
+// ---- whole-warp pieces ------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ WalkInfo myers_walkback(const uint8_t* __restrict__ sq, const uint8_t* __restrict__ st, uint8_t* __restrict__ rev,
-                                                   int qblk, int jstar, const uint2* __restrict__ mat, int lane, int M)
+// Unpacks the bases of the block of candidate `slot` (both reads) into H: one 32-bit word of 16 bases per lane and
+// trip, written as one 16-byte store.  Base x of the block lands at q[qa + x] (t[ta + x]).
+__device__ __noinline__ int ext_stage(WarpScratch& S, HalfScratch& H, const ExtParams& P, int slot, int lane)
 {
-    const int nw = (qblk + 31) >> 5;
-    int i = qblk, j = jstar, r = 0;
-    WalkInfo W; W.asize = 0; W.found = 0; W.acnt = 0; W.qcnt = 0; W.tcnt = 0;
-    int m = 0;
-    int jw = -(1 << 28), D0 = 0;                    // the window was filled at column jw on diagonal D0
-    uint32_t UP = 0, LEFT = 0, VALID = 0;
-    while (i > 0 || j > 0) {
-        if (i == 0 || j == 0) {                                 // along the matrix border
-            const int op = (i == 0) ? OP_TONLY : OP_QONLY;
-            if (i == 0) --j; else --i;
-            if (lane == 0) rev[r] = (uint8_t)op;
-            ++r;
-            if (!W.found) {
-                W.qcnt += op != OP_TONLY; W.tcnt += op != OP_QONLY; m = 0; ++W.acnt;
+    const int dir = XF(X_DIR, slot);
+    int qa = 0, ta = 0;
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        const uint8_t* pac = side ? P.pac : P.q_pac;
+        const uint64_t off = side ? (((uint64_t)(uint32_t)XF(X_TOFF_HI, slot) << 32) | (uint32_t)XF(X_TOFF_LO, slot))
+                                  : (((uint64_t)(uint32_t)XF(X_QOFF_HI, slot) << 32) | (uint32_t)XF(X_QOFF_LO, slot));
+        const int len = side ? XF(X_TLEN, slot) : XF(X_QLEN, slot);
+        const int strand = side ? 0 : XF(X_QSTRAND, slot);
+        const int blk = side ? XF(X_TBLK, slot) : XF(X_QBLK, slot);
+        const int s0 = (side ? XF(X_TORG, slot) : XF(X_QORG, slot)) + dir * (side ? XF(X_TIDX, slot) : XF(X_QIDX, slot));   // sequence index of x = 0
+        uint8_t* dst = side ? H.t : H.q;
+        // physical base index of x: p0 + g x
+        const long long p0 = strand ? (long long)off + (len - 1 - s0) : (long long)off + s0;
+        const int g = strand ? -dir : dir;
+        const long long plo = g > 0 ? p0 : p0 - (blk - 1), phi = g > 0 ? p0 + (blk - 1) : p0;
+        const int a = g > 0 ? (int)(p0 & 15) : 15 - (int)(p0 & 15);
+        const long long w0 = g > 0 ? (p0 >> 4) : (p0 >> 4);
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(pac);
+        for (long long w = (plo >> 4) + lane; w <= (phi >> 4); w += 32) {
+            const uint32_t v = __ldg(words + w);
+            // byte i of v holds bases 4 i .. 4 i + 3, first base in its top bits
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t x = (v >> (8 * i)) & 0xffu;
+                uint32_t r = (x >> 6) | (((x >> 4) & 3u) << 8) | (((x >> 2) & 3u) << 16) | ((x & 3u) << 24);
+                if (strand) r ^= 0x03030303u;
+                o[i] = r;
             }
-            continue;
+            uint4 st4;
+            long long idx;
+            if (g > 0) { st4 = make_uint4(o[0], o[1], o[2], o[3]); idx = (w - w0) * 16; }
+            else {
+                st4 = make_uint4(__byte_perm(o[3], 0, 0x0123), __byte_perm(o[2], 0, 0x0123), __byte_perm(o[1], 0, 0x0123), __byte_perm(o[0], 0, 0x0123));
+                idx = (w0 - w) * 16;
+            }
+            *reinterpret_cast<uint4*>(dst + idx) = st4;
         }
-        int l0 = jw - j, dd = (i - j) - D0 + 16;
-        uint32_t bv = 0;
-        bool have = (unsigned)l0 < 32u && (unsigned)dd < 32u;
-        if (have) { bv = __ballot_sync(0xffffffffu, (VALID >> dd) & 1); have = (bv >> l0) & 1; }
-        if (!have) {
-            // refill, centred on the diagonal through (i, j): my column is j - lane, its rows i - lane - 16 .. i - lane + 15
-            jw = j; D0 = i - j; l0 = 0; dd = 16;
-            const int col = j - lane, rc = i - lane;
-            int ww = (rc - 17) >> 5;                            // word of row rc - 16 (row x is bit (x - 1) & 31 of word (x - 1) >> 5)
-            ww = ww < 0 ? 0 : (ww > nw - 1 ? nw - 1 : ww);
-            uint2 a = make_uint2(0, 0), b = make_uint2(0, 0);
-            if (col >= 1) {
-                a = mat[(size_t)(col - 1 + ww) * nw + ww];
-                if (ww + 1 < nw) b = mat[(size_t)(col + ww) * nw + ww + 1];
-            }
-            const int s0 = rc - 17 - 32 * ww;                   // bit of diagonal dd = 0 in the 64-bit value b:a
-            if (s0 >= 0) { UP = __funnelshift_r(a.x, b.x, s0); LEFT = __funnelshift_r(a.y, b.y, s0); }     // s0 <= 31
-            else if (s0 > -32) { UP = a.x << (-s0); LEFT = a.y << (-s0); }
-            else { UP = 0; LEFT = 0; }
-            const int first = 17 - rc;                          // rows below 1 do not exist
-            VALID = col >= 1 ? (first <= 0 ? 0xffffffffu : (first < 32 ? 0xffffffffu << first : 0u)) : 0u;
-            bv = __ballot_sync(0xffffffffu, (VALID >> dd) & 1);
-        }
-        const uint32_t bu = __ballot_sync(0xffffffffu, (UP >> dd) & 1);
-        const uint32_t bl = __ballot_sync(0xffffffffu, (LEFT >> dd) & 1);
-        const uint32_t dm = (bv & ~bu & ~bl) >> l0;             // lane l0 + k: the cell (i - k, j - k) is a diagonal move
-        const int run = (dm == 0xffffffffu) ? 32 : __ffs(~dm) - 1;
-        if (run > 0) {
-            // a run of diagonal moves: all its columns at once
-            const int k = lane - l0;
-            bool mt = false;
-            if (k >= 0 && k < run) {
-                mt = sq[i - k - 1] == st[j - k - 1];
-                rev[r + k] = (uint8_t)(mt ? OP_MATCH : OP_MISMATCH);
-            }
-            if (!W.found) {
-                const uint32_t mm = __ballot_sync(0xffffffffu, mt) >> l0;
-                for (int p = 0; p < run; ++p) {
-                    ++W.qcnt; ++W.tcnt; ++W.acnt;
-                    m = ((mm >> p) & 1) ? m + 1 : 0;
-                    if (m == M) { W.found = 1; break; }
-                }
-            }
-            i -= run; j -= run; r += run; l0 += run;
-        }
-        // the move that ended the run, when its cell is in the window (then it is an up or a left move)
-        if (i > 0 && j > 0 && l0 < 32 && ((bv >> l0) & 1)) {
-            int op;
-            if ((bu >> l0) & 1) { op = OP_QONLY; --i; }
-            else { op = OP_TONLY; --j; }
-            if (lane == 0) rev[r] = (uint8_t)op;
-            ++r;
-            if (!W.found) {
-                W.qcnt += op != OP_TONLY;
-                W.tcnt += op != OP_QONLY;
-                m = 0;
-                ++W.acnt;
-            }
-        }
-    }
-    W.asize = r;
-    return W;
-}
-
-// ---- the per-candidate state machine (oc_aligner.c:157-286 per side, :303-451 around it)
-
-// Starts a side of the extension: columns go to ops[out_base + x * out_dir].
-__device__ __forceinline__ void ext_begin_side(ExtCtx& C, int lane, int phase, int q_origin, int q_total, int t_origin, int t_total,
-                                               int dir, long long out_base, int out_dir)
-{
-    if (lane == 0) {
-        C.phase = phase; C.q_origin = q_origin; C.q_total = q_total; C.t_origin = t_origin; C.t_total = t_total; C.dir = dir;
-        C.out_base = out_base; C.out_dir = out_dir; C.qidx = 0; C.tidx = 0; C.ncol = 0;
+        if (side) ta = a; else qa = a;
     }
     __syncwarp();
-}
-
-// Cuts the next block of the current side and unpacks its bases.  False: nothing left on one of the reads.
-__device__ __forceinline__ bool ext_next_block(ExtCtx& C, HalfScratch& H, const ExtParams& P, int lane)
-{
-    const int bs = P.block_size;
-    const int qidx = C.qidx, tidx = C.tidx;
-    const int qleft = C.q_total - qidx, tleft = C.t_total - tidx;
-    int qblk, tblk, last;
-    if (qleft < bs + 100 || tleft < bs + 100) {             // oc_aligner.c:127-137
-        qblk = (int)__dmul_rn((double)tleft, 1.3); qblk = qblk < qleft ? qblk : qleft;
-        tblk = (int)__dmul_rn((double)qleft, 1.3); tblk = tblk < tleft ? tblk : tleft;
-        last = 1;
-    } else { qblk = tblk = bs; last = 0; }
-    if (qblk == 0 || tblk == 0) return false;
-    SeqView qv; qv.pac = P.q_pac; qv.off = C.qoff_; qv.len = C.qlen; qv.strand = C.qstrand;
-    SeqView tv; tv.pac = P.pac; tv.off = C.toff_; tv.len = C.tlen; tv.strand = 0;
-    const int dir = C.dir, qo = C.q_origin + dir * qidx, to = C.t_origin + dir * tidx;
-    __syncwarp();
-    for (int x = lane; x < qblk; x += 32) H.q[x] = (uint8_t)seq_base(qv, qo + dir * x);
-    for (int x = lane; x < tblk; x += 32) H.t[x] = (uint8_t)seq_base(tv, to + dir * x);
-    if (lane == 0) { C.qblk = qblk; C.tblk = tblk; C.last = last; }
-    __syncwarp();
-    return true;
+    return qa | (ta << 8);
 }
 
 // End of the right side: assemble the result (oc_aligner.c:385-451).
-__device__ __forceinline__ void ext_finish(ExtCtx& C, const ExtParams& P, int lane)
+__device__ __noinline__ void ext_finish(WarpScratch& S, const ExtParams& P, int slot, int lane)
 {
-    uint8_t* ops = P.ops + C.ops_base;
-    const int R = C.ncol, lcap = C.lcap, L = C.L, left_keep = C.left_keep, acnt = C.acnt;
-    int QS = C.QS, TS = C.TS;
+    const uint64_t ops_base = ((uint64_t)(uint32_t)XF(X_OPS_HI, slot) << 32) | (uint32_t)XF(X_OPS_LO, slot);
+    uint8_t* ops = P.ops + ops_base;
+    const int R = XF(X_NCOL, slot), lcap = XF(X_LCAP, slot), L = XF(X_L, slot), left_keep = XF(X_LKEEP, slot), acnt = XF(X_ACNT, slot);
+    int QS = XF(X_QS, slot), TS = XF(X_TS, slot);
     uint8_t* rbase = ops + (left_keep ? lcap - acnt : lcap);
     int rstart = 0, right_keep = R;
     if (!left_keep) {                                   // :385-415
@@ -308,21 +231,66 @@ __device__ __forceinline__ void ext_finish(ExtCtx& C, const ExtParams& P, int la
         A.ok = n_all >= P.min_align_size;
         A.long_ins = long_ins;
         A.ops_offset = (uint64_t)(fin - P.ops);
-        P.results[C.ti] = A;
-        C.active = 0;
+        P.results[XF(X_TI, slot)] = A;
+        XF(X_STATE, slot) = ST_IDLE;
     }
     __syncwarp();
 }
 
-// The current side has ended.  Left side: re-anchor at the first run of 8 matches counted from the seed
-// (oc_aligner.c:329-367) and start the right side; right side: finish the candidate.  On return the candidate
-// either has a block ready for the forward pass or is no longer active.
-__device__ __forceinline__ void ext_end_side(ExtCtx& C, HalfScratch& H, const ExtParams& P, int lane)
+// ---- per-lane pieces (slot = lane) ---------------------------------------------------------------------------------------
+
+struct LaneCtx {            // the views a lane needs of its candidate
+    SeqView qv, tv;
+    uint8_t* ops;           // the candidate's region of the pool
+};
+
+__device__ __forceinline__ LaneCtx lane_ctx(WarpScratch& S, const ExtParams& P, int lane)
 {
-    __syncwarp();
-    if (C.phase == 0) {
-        const uint8_t* ops = P.ops + C.ops_base;
-        const int L = C.ncol, lcap = C.lcap;
+    LaneCtx C;
+    C.qv.pac = P.q_pac; C.qv.off = ((uint64_t)(uint32_t)XF(X_QOFF_HI, lane) << 32) | (uint32_t)XF(X_QOFF_LO, lane);
+    C.qv.len = XF(X_QLEN, lane); C.qv.strand = XF(X_QSTRAND, lane);
+    C.tv.pac = P.pac; C.tv.off = ((uint64_t)(uint32_t)XF(X_TOFF_HI, lane) << 32) | (uint32_t)XF(X_TOFF_LO, lane);
+    C.tv.len = XF(X_TLEN, lane); C.tv.strand = 0;
+    C.ops = P.ops + (((uint64_t)(uint32_t)XF(X_OPS_HI, lane) << 32) | (uint32_t)XF(X_OPS_LO, lane));
+    return C;
+}
+
+// Starts a side of the extension: columns go to ops[out_base + x * out_dir].
+__device__ __forceinline__ void lp_begin_side(WarpScratch& S, int lane, int phase, int q_origin, int q_total, int t_origin, int t_total,
+                                              int dir, int out_base, int out_dir)
+{
+    XF(X_PHASE, lane) = phase; XF(X_QORG, lane) = q_origin; XF(X_QTOT, lane) = q_total; XF(X_TORG, lane) = t_origin; XF(X_TTOT, lane) = t_total;
+    XF(X_DIR, lane) = dir; XF(X_OUTB, lane) = out_base; XF(X_OUTDIR, lane) = out_dir; XF(X_QIDX, lane) = 0; XF(X_TIDX, lane) = 0; XF(X_NCOL, lane) = 0;
+}
+
+// Cuts the next block of the current side.  False: nothing left on one of the reads.
+__device__ __forceinline__ bool lp_next_block(WarpScratch& S, const ExtParams& P, int lane)
+{
+    const int bs = P.block_size;
+    const int qleft = XF(X_QTOT, lane) - XF(X_QIDX, lane), tleft = XF(X_TTOT, lane) - XF(X_TIDX, lane);
+    int qblk, tblk, last;
+    if (qleft < bs + 100 || tleft < bs + 100) {             // oc_aligner.c:127-137
+        qblk = (int)__dmul_rn((double)tleft, 1.3); qblk = qblk < qleft ? qblk : qleft;
+        tblk = (int)__dmul_rn((double)qleft, 1.3); tblk = tblk < tleft ? tblk : tleft;
+        last = 1;
+    } else { qblk = tblk = bs; last = 0; }
+    if (qblk == 0 || tblk == 0) return false;
+    XF(X_QBLK, lane) = qblk; XF(X_TBLK, lane) = tblk; XF(X_LAST, lane) = last; XF(X_WFLAGS, lane) = 0;
+    {
+        const int d = qblk - tblk, wide = d > 32 || d < -32;
+        XF(X_NBW, lane) = wide ? 8 : 4; XF(X_SHIFT, lane) = wide ? d / 2 : 0;
+    }
+    XF(X_STATE, lane) = ST_BLOCK;
+    return true;
+}
+
+// The current side has ended.  Left side: re-anchor at the first run of 8 matches counted from the seed
+// (oc_aligner.c:329-367) and start the right side; right side: the candidate waits for ext_finish.
+__device__ __noinline__ void lp_end_side(WarpScratch& S, const ExtParams& P, int lane)
+{
+    if (XF(X_PHASE, lane) == 0) {
+        const uint8_t* ops = P.ops + (((uint64_t)(uint32_t)XF(X_OPS_HI, lane) << 32) | (uint32_t)XF(X_OPS_LO, lane));
+        const int L = XF(X_NCOL, lane), lcap = XF(X_LCAP, lane);
         int acnt = 0, qcnt = 0, tcnt = 0, m = 0;
         for (int x = 0; x < L; ++x) {
             const int op = ops[lcap - 1 - x];
@@ -331,131 +299,207 @@ __device__ __forceinline__ void ext_end_side(ExtCtx& C, HalfScratch& H, const Ex
             ++acnt;
             if (m == 8) break;
         }
-        int QS = C.QS, TS = C.TS, left_keep = 0;
+        int QS = XF(X_QS, lane), TS = XF(X_TS, lane), left_keep = 0;
         if (m == 8) { QS -= qcnt; TS -= tcnt; left_keep = L - acnt; }
         else acnt = 0;
-        __syncwarp();
-        if (lane == 0) { C.QS = QS; C.TS = TS; C.L = L; C.left_keep = left_keep; C.acnt = acnt; }
+        XF(X_QS, lane) = QS; XF(X_TS, lane) = TS; XF(X_L, lane) = L; XF(X_LKEEP, lane) = left_keep; XF(X_ACNT, lane) = acnt;
         // final alignment = ops[lcap - L, lcap - acnt) ++ right extension written from lcap - acnt
-        ext_begin_side(C, lane, 1, QS, C.qlen - QS, TS, C.tlen - TS, +1, (long long)(left_keep ? lcap - acnt : lcap), +1);
-        if (ext_next_block(C, H, P, lane)) return;
+        lp_begin_side(S, lane, 1, QS, XF(X_QLEN, lane) - QS, TS, XF(X_TLEN, lane) - TS, +1, left_keep ? lcap - acnt : lcap, +1);
+        if (lp_next_block(S, P, lane)) return;
     }
-    ext_finish(C, P, lane);
+    XF(X_STATE, lane) = ST_FINISH;
 }
 
-// Fetches the next candidate for this slot and prepares its first block.
-__device__ __forceinline__ void ext_start_task(ExtCtx& C, HalfScratch& H, const ExtParams& P, uint32_t ti, int lane)
+// Fetches candidate ti into my slot and cuts its first block.
+__device__ __forceinline__ void lp_start_task(WarpScratch& S, const ExtParams& P, uint32_t ti, int lane)
 {
     const ExtTask T = P.tasks[ti];
-    __syncwarp();
-    if (lane == 0) {
-        C.active = 1; C.ti = ti;
-        C.qoff_ = P.q_off[T.qid]; C.qlen = (int)P.q_len[T.qid]; C.qstrand = T.qdir;
-        C.toff_ = P.seq_off[T.sid]; C.tlen = (int)P.seq_len[T.sid];
-        C.ops_base = T.ops_base; C.lcap = (int)T.lcap; C.QS = T.qoff; C.TS = T.soff;
-        C.L = 0; C.left_keep = 0; C.acnt = 0;
-    }
+    const uint64_t qo = P.q_off[T.qid], to = P.seq_off[T.sid];
+    XF(X_TI, lane) = (int)ti;
+    XF(X_QOFF_LO, lane) = (int)(uint32_t)qo; XF(X_QOFF_HI, lane) = (int)(uint32_t)(qo >> 32);
+    XF(X_TOFF_LO, lane) = (int)(uint32_t)to; XF(X_TOFF_HI, lane) = (int)(uint32_t)(to >> 32);
+    XF(X_QLEN, lane) = (int)P.q_len[T.qid]; XF(X_QSTRAND, lane) = T.qdir; XF(X_TLEN, lane) = (int)P.seq_len[T.sid];
+    XF(X_OPS_LO, lane) = (int)(uint32_t)T.ops_base; XF(X_OPS_HI, lane) = (int)(uint32_t)(T.ops_base >> 32);
+    XF(X_LCAP, lane) = (int)T.lcap; XF(X_QS, lane) = T.qoff; XF(X_TS, lane) = T.soff;
+    XF(X_L, lane) = 0; XF(X_LKEEP, lane) = 0; XF(X_ACNT, lane) = 0;
     // left of the seed, read right to left (oc_aligner.c:313-327); column x lives at lcap - 1 - x
-    ext_begin_side(C, lane, 0, T.qoff - 1, T.qoff, T.soff - 1, T.soff, -1, (long long)(T.lcap ? T.lcap - 1 : 0), -1);
-    if (!ext_next_block(C, H, P, lane)) ext_end_side(C, H, P, lane);
+    lp_begin_side(S, lane, 0, T.qoff - 1, T.qoff, T.soff - 1, T.soff, -1, (int)(T.lcap ? T.lcap - 1 : 0), -1);
+    if (!lp_next_block(S, P, lane)) lp_end_side(S, P, lane);
 }
 
-// After the forward pass of a block: walk back, keep the part up to the last run of matches (oc_aligner.c:213-262),
-// then cut the next block or end the side.
-__device__ __forceinline__ void ext_post_block(ExtCtx& C, HalfScratch& H, uint8_t* rev, const ExtParams& P, const uint2* mat, int lane)
+// After the forward pass of my block: walk back from (qblk, j*) preferring up, then left, then diagonal
+// (edlib_ex.c:463,500,540), keep the part up to the last run of M matches (oc_aligner.c:213-262), then cut the next
+// block or end the side.  The walk reads the band of (Pv, Ph) words the forward pass left in `mat`; its columns go,
+// last to first, to `rev` (four op bytes per word).
+__device__ __forceinline__ void lp_walk_post(WarpScratch& S, const ExtParams& P, const uint2* __restrict__ mat, uint32_t* __restrict__ rev, int lane)
 {
-    const int qblk = C.qblk, tblk = C.tblk, last = C.last, best = C.best, bestj = C.bestj;
+    const LaneCtx C = lane_ctx(S, P, lane);
+    const int qblk = XF(X_QBLK, lane), tblk = XF(X_TBLK, lane), last = XF(X_LAST, lane), best = XF(X_BEST, lane), bestj = XF(X_BESTJ, lane);
+    const int dir = XF(X_DIR, lane);
+    const int q0 = XF(X_QORG, lane) + dir * XF(X_QIDX, lane), t0 = XF(X_TORG, lane) + dir * XF(X_TIDX, lane);     // sequence index of base 0 of the block
     const int mn = qblk < tblk ? qblk : tblk;
     const int k0 = (int)__dmul_rn(__dmul_rn((double)mn, P.error), 1.1);         // edlib_ex.c:751
     const bool failed = best > k0;
     int done = last;
     if (failed && qblk > 30 && tblk > 30) done = 1;                             // oc_aligner.c:220 (qfae = tfae = 0)
     const int M = done ? P.tail_match_len : 8;
-    WalkInfo W; W.asize = 0; W.found = 0; W.acnt = 0; W.qcnt = 0; W.tcnt = 0;
-    if (!failed) W = myers_walkback(H.q, H.t, rev, qblk, bestj + 1, mat, lane, M);
-    __syncwarp();
-    uint8_t* out = P.ops + C.ops_base + C.out_base;
-    const int out_dir = C.out_dir, ncol = C.ncol;
-    const int kcut = W.asize - W.acnt;
-    if (!W.found || kcut < 1) {
+    int asize = 0, found = 0, acnt = 0, qcnt = 0, tcnt = 0;
+    if (!failed) {
+        int i = qblk, j = bestj + 1, r = 0, m = 0;
+        uint32_t acc = 0;
+        if (XF(X_WFLAGS, lane) & 2) {           // continue after the band was moved
+            i = XF(X_WI, lane); j = XF(X_WJ, lane); r = XF(X_WR, lane); found = XF(X_WFLAGS, lane) & 1;
+            acnt = XF(X_WACNT, lane); qcnt = XF(X_WQCNT, lane); tcnt = XF(X_WTCNT, lane); m = XF(X_WM, lane); acc = (uint32_t)XF(X_WACC, lane);
+        }
+        const int shift = XF(X_SHIFT, lane), nbw = XF(X_NBW, lane), hb = nbw >> 1;
+        const int band_lo = P.band_test ? hb - 1 : 0, band_hi = P.band_test ? hb + 1 : nbw;
+        bool moved = false;
+        while (i > 0 || j > 0) {
+            int op;
+            if (i == 0) { op = OP_TONLY; --j; }
+            else if (j == 0) { op = OP_QONLY; --i; }
+            else {
+                const int wi = (i - 1) >> 5;
+                const int k = wi + hb - ((j - 1 + 16 + shift) >> 5);
+                if (k < band_lo || k >= band_hi) { moved = true; break; }
+                const uint2 v = mat[(j - 1) * nbw + k];
+                const int bit = (i - 1) & 31;
+                if ((v.x >> bit) & 1) { op = OP_QONLY; --i; }
+                else if ((v.y >> bit) & 1) { op = OP_TONLY; --j; }
+                else {
+                    op = seq_base(C.qv, q0 + dir * (i - 1)) == seq_base(C.tv, t0 + dir * (j - 1)) ? OP_MATCH : OP_MISMATCH;
+                    --i; --j;
+                }
+            }
+            acc |= (uint32_t)op << (8 * (r & 3));
+            if ((r & 3) == 3) { rev[r >> 2] = acc; acc = 0; }
+            ++r;
+            if (!found) {
+                qcnt += op != OP_TONLY; tcnt += op != OP_QONLY; ++acnt;
+                m = op == OP_MATCH ? m + 1 : 0;
+                if (m == M) found = 1;
+            }
+        }
+        if (moved) {
+            // the walk left the band: the forward pass runs again with the band on this diagonal
+            XF(X_WI, lane) = i; XF(X_WJ, lane) = j; XF(X_WR, lane) = r; XF(X_WFLAGS, lane) = 2 | found;
+            XF(X_WACNT, lane) = acnt; XF(X_WQCNT, lane) = qcnt; XF(X_WTCNT, lane) = tcnt; XF(X_WM, lane) = m; XF(X_WACC, lane) = (int)acc;
+            XF(X_SHIFT, lane) = i - j;
+            XF(X_STATE, lane) = ST_BLOCK;
+            atomicAdd(P.counters + 3, 1ull);
+            return;
+        }
+        if (r & 3) rev[r >> 2] = acc;
+        asize = r;
+    }
+    uint8_t* out = C.ops + XF(X_OUTB, lane);
+    const int out_dir = XF(X_OUTDIR, lane), ncol = XF(X_NCOL, lane);
+    const int kcut = asize - acnt;
+    if (!found || kcut < 1) {
         // exact-match prefix only, then stop (:243-253)
         int n = 0;
-        for (int base = 0; base < mn; base += 32) {
-            const int x = base + lane;
-            const bool eq = x < mn && H.q[x] == H.t[x];
-            const uint32_t bal = __ballot_sync(0xffffffffu, eq);
-            if (bal == 0xffffffffu) { n += 32; continue; }
-            n += __ffs(~bal) - 1;
-            break;
-        }
-        for (int x = lane; x < n; x += 32) out[(long long)(ncol + x) * out_dir] = OP_MATCH;
-        __syncwarp();
-        if (lane == 0) C.ncol = ncol + n;
-        ext_end_side(C, H, P, lane);
+        while (n < mn && seq_base(C.qv, q0 + dir * n) == seq_base(C.tv, t0 + dir * n)) ++n;
+        for (int x = 0; x < n; ++x) out[(long long)(ncol + x) * out_dir] = OP_MATCH;
+        XF(X_NCOL, lane) = ncol + n;
+        lp_end_side(S, P, lane);
         return;
     }
     const int keep = kcut + (done ? M : 0);
-    for (int x = lane; x < keep; x += 32) out[(long long)(ncol + x) * out_dir] = rev[W.asize - 1 - x];
-    __syncwarp();
-    if (lane == 0) {
-        C.qidx += qblk - W.qcnt;            // qfae = qblk
-        C.tidx += (bestj + 1) - W.tcnt;     // tfae = j*
-        C.ncol = ncol + keep;
+    {
+        // out[(ncol + x) * out_dir] = rev[asize - 1 - x], x < keep: in address order d[u], u < keep, that is a copy of
+        // rev[asize - keep + u] (left side) or of rev[asize - 1 - u] (right side)
+        const uint8_t* rb = reinterpret_cast<const uint8_t*>(rev);
+        uint8_t* d = out_dir > 0 ? out + ncol : out - (ncol + keep - 1);
+        const int sidx = out_dir > 0 ? asize - 1 : asize - keep, sdir = out_dir > 0 ? -1 : 1;
+        int u = 0;
+        while (u < keep && ((uintptr_t)(d + u) & 3)) { d[u] = rb[sidx + sdir * u]; ++u; }
+        for (; u + 4 <= keep; u += 4) {
+            const uint32_t w = (uint32_t)rb[sidx + sdir * u] | ((uint32_t)rb[sidx + sdir * (u + 1)] << 8) |
+                               ((uint32_t)rb[sidx + sdir * (u + 2)] << 16) | ((uint32_t)rb[sidx + sdir * (u + 3)] << 24);
+            *reinterpret_cast<uint32_t*>(d + u) = w;
+        }
+        for (; u < keep; ++u) d[u] = rb[sidx + sdir * u];
     }
-    __syncwarp();
-    if (done || !ext_next_block(C, H, P, lane)) ext_end_side(C, H, P, lane);
+    XF(X_QIDX, lane) += qblk - qcnt;            // qfae = qblk
+    XF(X_TIDX, lane) += (bestj + 1) - tcnt;     // tfae = j*
+    XF(X_NCOL, lane) = ncol + keep;
+    if (done || !lp_next_block(S, P, lane)) lp_end_side(S, P, lane);
 }
 
-__global__ void __launch_bounds__(EXT_WARPS * 32, 4)
+__global__ void __launch_bounds__(EXT_WARPS * 32, 3)
 k_extend(ExtParams P)
 {
     extern __shared__ __align__(16) uint8_t ext_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1;
     WarpScratch& S = reinterpret_cast<WarpScratch*>(ext_smem)[wid];
-    const size_t slot = (size_t)blockIdx.x * EXT_WARPS + wid;
-    uint2* mat0 = P.mat + slot * 2 * EXT_MAT_STRIDE;
-    uint2* mat1 = mat0 + EXT_MAT_STRIDE;
+    const size_t wslot = ((size_t)blockIdx.x * EXT_WARPS + wid) * EXT_SLOTS;
+    uint2* mat = P.mat + (wslot + lane) * EXT_MAT_STRIDE;                               // of my slot
+    uint32_t* rev = reinterpret_cast<uint32_t*>(P.rev + (wslot + lane) * EXT_REV_STRIDE);
     unsigned long long nb = 0, nc = 0, nwd = 0;
-    if (lane == 0) { S.ctx[0].active = 0; S.ctx[1].active = 0; }
+    XF(X_STATE, lane) = ST_IDLE;
     __syncwarp();
     bool drained = false;
     for (;;) {
-        // ---- refill the idle slots from the queue
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            while (!S.ctx[h].active && !drained) {
-                uint32_t ti = 0;
-                if (lane == 0) ti = atomicAdd(P.next_task, 1u);
-                ti = __shfl_sync(0xffffffffu, ti, 0);
-                if (ti >= P.n_tasks) { drained = true; break; }
-                ext_start_task(S.ctx[h], S.h[h], P, ti, lane);          // may finish the candidate right away
+        // ---- idle slots take candidates from the queue
+        const uint32_t idle = __ballot_sync(0xffffffffu, XF(X_STATE, lane) == ST_IDLE);
+        if (idle && !drained) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(P.next_task, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (XF(X_STATE, lane) == ST_IDLE) {
+                const uint32_t ti = base + (uint32_t)__popc(idle & lt_mask);
+                if (ti < P.n_tasks) lp_start_task(S, P, ti, lane);
             }
-        }
-        const int a0 = S.ctx[0].active, a1 = S.ctx[1].active;
-        if (!a0 && !a1) break;
-        // ---- forward passes: side by side in the two half-warps when both blocks fit 16 lanes
-        const int q0 = a0 ? S.ctx[0].qblk : 0, t0 = a0 ? S.ctx[0].tblk : 0;
-        const int q1 = a1 ? S.ctx[1].qblk : 0, t1 = a1 ? S.ctx[1].tblk : 0;
-        int best, bestj;
-        if (q0 <= 512 && q1 <= 512) {
-            const int hh = lane >> 4;
-            myers_forward<16>(S.h[hh].q, S.h[hh].t, hh ? q1 : q0, hh ? t1 : t0, hh ? mat1 : mat0, lane & 15, &best, &bestj);
-            __syncwarp();
-            if (lane == 0 && a0) { S.ctx[0].best = best; S.ctx[0].bestj = bestj; }
-            if (lane == 16 && a1) { S.ctx[1].best = best; S.ctx[1].bestj = bestj; }
-        } else {
-            if (a0) { myers_forward<32>(S.h[0].q, S.h[0].t, q0, t0, mat0, lane, &best, &bestj); if (lane == 0) { S.ctx[0].best = best; S.ctx[0].bestj = bestj; } }
-            __syncwarp();
-            if (a1) { myers_forward<32>(S.h[1].q, S.h[1].t, q1, t1, mat1, lane, &best, &bestj); if (lane == 0) { S.ctx[1].best = best; S.ctx[1].bestj = bestj; } }
-        }
-        if (lane == 0) {
-            if (a0) { nb += 1; nc += (unsigned long long)t0; nwd += (unsigned long long)t0 * ((q0 + 31) >> 5); }
-            if (a1) { nb += 1; nc += (unsigned long long)t1; nwd += (unsigned long long)t1 * ((q1 + 31) >> 5); }
+            if (base + (uint32_t)__popc(idle) >= P.n_tasks) drained = true;
         }
         __syncwarp();
-        // ---- walk-backs and bookkeeping, one candidate after the other, whole warp
-        if (a0) ext_post_block(S.ctx[0], S.h[0], S.rev, P, mat0, lane);
-        if (a1) ext_post_block(S.ctx[1], S.h[1], S.rev, P, mat1, lane);
+        // ---- candidates whose right side has ended: result record, whole warp
+        uint32_t fin = __ballot_sync(0xffffffffu, XF(X_STATE, lane) == ST_FINISH);
+        while (fin) {
+            const int slot = __ffs(fin) - 1;
+            fin &= fin - 1;
+            ext_finish(S, P, slot, lane);
+        }
+        const uint32_t blk = __ballot_sync(0xffffffffu, XF(X_STATE, lane) == ST_BLOCK);
+        if (!blk) {
+            if (drained && __ballot_sync(0xffffffffu, XF(X_STATE, lane) != ST_IDLE) == 0) break;
+            continue;
+        }
+        // ---- forward passes: side by side in the two half-warps when both blocks fit 16 lanes
+        uint32_t small = blk & __ballot_sync(0xffffffffu, XF(X_QBLK, lane) <= 512), big = blk & ~small;
+        while (small | big) {
+            int sa, sb = -1;
+            if (small) {
+                sa = __ffs(small) - 1; small &= small - 1;
+                if (small) { sb = __ffs(small) - 1; small &= small - 1; }
+            } else { sa = __ffs(big) - 1; big &= big - 1; }
+            const int qb0 = XF(X_QBLK, sa), tb0 = XF(X_TBLK, sa);
+            const int a0 = ext_stage(S, S.h[0], P, sa, lane), a1 = sb >= 0 ? ext_stage(S, S.h[1], P, sb, lane) : 0;
+            const int qa0 = a0 & 255, ta0 = a0 >> 8, qa1 = a1 & 255, ta1 = a1 >> 8;
+            int best, bestj;
+            if (qb0 <= 512) {
+                const int hh = lane >> 4;
+                const int sl = hh ? sb : sa;
+                const int qb = sl >= 0 ? XF(X_QBLK, sl) : 0, tb = sl >= 0 ? XF(X_TBLK, sl) : 0;
+                myers_forward<16>(S.h[hh].q + (hh ? qa1 : qa0), S.h[hh].t + (hh ? ta1 : ta0), qb, tb,
+                                  P.mat + (wslot + (sl >= 0 ? sl : 0)) * EXT_MAT_STRIDE, sl >= 0 ? XF(X_SHIFT, sl) : 0, sl >= 0 ? XF(X_NBW, sl) : 4, lane & 15, &best, &bestj);
+                __syncwarp();
+                if ((lane & 15) == 0 && sl >= 0) { XF(X_BEST, sl) = best; XF(X_BESTJ, sl) = bestj; XF(X_STATE, sl) = ST_WALK; }
+            } else {
+                myers_forward<32>(S.h[0].q + qa0, S.h[0].t + ta0, qb0, tb0, P.mat + (wslot + sa) * EXT_MAT_STRIDE, XF(X_SHIFT, sa), XF(X_NBW, sa), lane, &best, &bestj);
+                __syncwarp();
+                if (lane == 0) { XF(X_BEST, sa) = best; XF(X_BESTJ, sa) = bestj; XF(X_STATE, sa) = ST_WALK; }
+            }
+            if (lane == 0) {
+                nb += 1; nc += (unsigned long long)tb0; nwd += (unsigned long long)tb0 * ((qb0 + 31) >> 5);
+                if (sb >= 0) { const int q1 = XF(X_QBLK, sb), t1 = XF(X_TBLK, sb); nb += 1; nc += (unsigned long long)t1; nwd += (unsigned long long)t1 * ((q1 + 31) >> 5); }
+            }
+            __syncwarp();
+        }
+        // ---- walk-backs and bookkeeping: every lane on its own candidate
+        if (XF(X_STATE, lane) == ST_WALK) lp_walk_post(S, P, mat, rev, lane);
+        __syncwarp();
     }
     if (lane == 0) {
         atomicAdd(P.counters + 0, nb);
@@ -470,18 +514,24 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
 {
     if (n_tasks == 0) return NB_OK;
     cudaStream_t st = ctx->stream;
-    static const int kCtas = getenv("NB_EXT_CTAS") ? atoi(getenv("NB_EXT_CTAS")) : 4;
-    int ctas_per_sm = kCtas;                // x 8 warps per SM
+    static const int kCtas = getenv("NB_EXT_CTAS") ? atoi(getenv("NB_EXT_CTAS")) : 3;
+    int ctas_per_sm = kCtas < 1 ? 1 : kCtas;        // x 8 warps x 32 candidates per SM
     if (ctx->ext_ctas > 0 && ctx->ext_ctas < ctas_per_sm) ctas_per_sm = ctx->ext_ctas;
-    const unsigned grid = NB_SMS * ctas_per_sm;
-    const size_t slots = (size_t)NB_SMS * kCtas * EXT_WARPS * 2;     // two candidates in flight per warp (sized for the full grid)
+    unsigned grid = NB_SMS * ctas_per_sm;
+    {
+        // no more warps than there are candidates to fill a good part of their 32 slots
+        const unsigned want = (unsigned)((n_tasks + EXT_WARPS * 8 - 1) / (EXT_WARPS * 8));
+        if (grid > want) grid = want ? want : 1;
+    }
+    const size_t slots = (size_t)NB_SMS * (kCtas < 1 ? 1 : kCtas) * EXT_WARPS * EXT_SLOTS;      // candidates in flight (sized for the full grid)
     if (!ctx->ext_mat || ctx->ext_mat_slots < slots) {
         if (ctx->ext_mat) cudaFree(ctx->ext_mat);
         ctx->ext_mat = NULL;
-        NB_CUDA(ctx, cudaMalloc(&ctx->ext_mat, sizeof(uint2) * EXT_MAT_STRIDE * slots));
+        NB_CUDA(ctx, cudaMalloc(&ctx->ext_mat, (sizeof(uint2) * EXT_MAT_STRIDE + EXT_REV_STRIDE) * slots));
         ctx->ext_mat_slots = slots;
     }
     uint2* s_mat = (uint2*)ctx->ext_mat;
+    uint8_t* s_rev = (uint8_t*)ctx->ext_mat + sizeof(uint2) * EXT_MAT_STRIDE * slots;
     NbDevBuf B(ctx);
     uint32_t* d_next = NULL;
     unsigned long long* d_cnt = NULL;
@@ -491,9 +541,10 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     ExtParams P;
     P.pac = templates->d_pac; P.seq_off = templates->d_off; P.seq_len = templates->d_len;
     P.q_pac = queries->d_pac; P.q_off = queries->d_off; P.q_len = queries->d_len;
-    P.tasks = d_tasks; P.n_tasks = n_tasks; P.results = d_results; P.ops = d_ops; P.mat = s_mat;
+    P.tasks = d_tasks; P.n_tasks = n_tasks; P.results = d_results; P.ops = d_ops; P.mat = s_mat; P.rev = s_rev;
     P.next_task = d_next; P.counters = d_cnt;
     P.error = error; P.min_align_size = min_align_size; P.tail_match_len = tail_match_len; P.block_size = 512;
+    P.band_test = getenv("NB_EXT_BAND_TEST") ? atoi(getenv("NB_EXT_BAND_TEST")) : 0;     // (read at every launch: tests switch it)
     const size_t smem = sizeof(WarpScratch) * EXT_WARPS;
     NB_CUDA(ctx, cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEventRecord(ctx->ev2, st);
@@ -507,6 +558,7 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     ctx->cc.n_block_aligns += cnt[0];
     ctx->cc.n_dp_columns += cnt[1];
     ctx->cc.n_dp_word_updates += cnt[2];
+    if (getenv("NB_TRACE")) fprintf(stderr, "[nb_run_extension] %u tasks, %llu block passes, %llu band moves\n", n_tasks, cnt[0], cnt[3]);
     if (cnt[2] > ctx->cc.big_ext_word_updates) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);

@@ -21,7 +21,6 @@ struct ExtTask {
 
 #define EXT_MAX_BLK 832         // >= 1.3 * 611 + slack (oc_aligner.c:127-137), multiple of 32
 #define EXT_WARPS 8             // warps per CTA
-#define EXT_MAT_WORDS 26        // 32-bit words per column (832 / 32)
 
 struct ExtParams {
     const uint8_t*  pac;            // template (subject) volume
@@ -34,16 +33,19 @@ struct ExtParams {
     uint32_t        n_tasks;
     nb_alignment*   results;
     uint8_t*        ops;            // pool
-    uint2*          mat;            // per resident warp: (EXT_MAX_BLK + 32) * EXT_MAT_WORDS entries
+    uint2*          mat;            // per candidate in flight: EXT_MAT_STRIDE entries, the (Pv, Ph) words of the band, [column][4]
+    uint8_t*        rev;            // per candidate in flight: EXT_REV_STRIDE bytes, the columns of the current block, last to first
     uint32_t*       next_task;      // work queue cursor
     unsigned long long* counters;   // [0] block alignments, [1] DP columns, [2] word updates
     double          error;
     int             min_align_size;
     int             tail_match_len;
     int             block_size;     // 512
+    int             band_test;      // 1: the walk-back only trusts the two middle words of a column's band (tests: exercises the moving band)
 };
 
-#define EXT_MAT_STRIDE ((size_t)(EXT_MAX_BLK + 32) * EXT_MAT_WORDS)
+#define EXT_MAT_STRIDE ((size_t)(EXT_MAX_BLK + 32) * 8)
+#define EXT_REV_STRIDE ((size_t)2 * EXT_MAX_BLK)
 
 int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* templates, const ExtTask* d_tasks, uint32_t n_tasks,
                      nb_alignment* d_results, uint8_t* d_ops, double error, int min_align_size, int tail_match_len);
