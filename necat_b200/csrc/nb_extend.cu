@@ -62,6 +62,8 @@ struct HalfScratch {
 
 struct WarpScratch {
     HalfScratch h[2];
+    uint32_t    pe[4][32];              // forward pass: match mask of lane l's 32 query rows for symbol c at pe[c][l]
+    uint2       sb[2][28];              // forward pass: per 32 steps the (+1, -1) bits of the last query row, per half-warp
     int32_t     f[X_NF][EXT_SLOTS];     // state of the 32 candidates, one field per row: f[field][slot]
 };
 
@@ -69,61 +71,108 @@ struct WarpScratch {
 
 // Forward pass over one block, WIDTH lanes per block (16: two blocks per warp, 32: one).  Lane `lid` of the group
 // owns query rows [32 lid, 32 lid + 32) and works on column s - lid at step s.  What travels from lane to lane
-// with one shuffle per step is the horizontal delta of the row above (bit 31: +1, bit 30: -1) together with the
-// symbol of that column (bits 0..1) -- the neighbour needs exactly that column next; the four match masks stay
-// in registers.  (Pv, Ph) of a word goes to mat[col][k], k = word - first word of the column's band.
+// with one shuffle per step is the horizontal delta of the row above (bit 31: +1, bit 0: -1) together with the
+// symbol of that column (bits 7..8, so that it is the byte offset of the symbol's row in S.pe) -- the neighbour needs
+// exactly that column next.  The loop has no branch: a lane computes on whatever arrives before its first column and
+// after its last one, its state is set when its first column comes up, and what it stores for columns that do not
+// exist is never read.
+//   * (Pv, Ph) of word-row w and column c is kept where c is within the band of row w: mat[w * 32 nbw + c - cl(w)],
+//     cl(w) = 32 (w - nbw / 2 + 1) - 16 - shift, 32 nbw columns per row -- a lane writes consecutive addresses, and so
+//     reads the walk-back when it follows a diagonal.
+//   * the score of the last query row is not tracked in the loop: its +1 / -1 bits are collected 32 steps at a time
+//     and the first minimum over the columns is found afterwards, 32 steps per lane.
 // Returns the best prefix distance and its column in every lane of the group.
 template <int WIDTH>
-__device__ __forceinline__ void myers_forward(const uint8_t* __restrict__ sq, const uint8_t* __restrict__ st, int qblk, int tblk,
-                                              uint2* __restrict__ mat, int shift, int nbw, int lid, int* best_out, int* bestj_out)
+__device__ __forceinline__ void myers_forward(WarpScratch& S, const uint8_t* __restrict__ sq, const uint8_t* __restrict__ st, int qblk, int tblk,
+                                              uint2* __restrict__ mat, int shift, int nbw, int lane, int* best_out, int* bestj_out)
 {
+    const int lid = lane & (WIDTH - 1), half = WIDTH < 32 ? lane >> 4 : 0;
     const int nw = (qblk + 31) >> 5;
-    uint32_t pe0 = 0, pe1 = 0, pe2 = 0, pe3 = 0;
-    if (lid < nw) {
-        const int r0 = lid << 5;
+    {
+        uint32_t pe0 = 0, pe1 = 0, pe2 = 0, pe3 = 0;
+        if (lid < nw) {
+            const int r0 = lid << 5;
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-            if (r0 + r < qblk) {
-                const int c = sq[r0 + r];
-                const uint32_t bit = 1u << r;
-                pe0 |= c == 0 ? bit : 0; pe1 |= c == 1 ? bit : 0; pe2 |= c == 2 ? bit : 0; pe3 |= c == 3 ? bit : 0;
+            for (int r = 0; r < 32; ++r) {
+                if (r0 + r < qblk) {
+                    const int c = sq[r0 + r];
+                    const uint32_t bit = 1u << r;
+                    pe0 |= c == 0 ? bit : 0; pe1 |= c == 1 ? bit : 0; pe2 |= c == 2 ? bit : 0; pe3 |= c == 3 ? bit : 0;
+                }
             }
         }
+        S.pe[0][lane] = pe0; S.pe[1][lane] = pe1; S.pe[2][lane] = pe2; S.pe[3][lane] = pe3;
     }
-    uint32_t Pv = 0xffffffffu, Mv = 0;
     const int lw = qblk > 0 ? (qblk - 1) >> 5 : 0, lb = (qblk - 1) & 31;
-    int score = qblk, best = 0x7fffffff, bestj = -1;
     int nsteps = qblk > 0 ? tblk + nw - 1 : 0;
     if (WIDTH < 32) { const int o = __shfl_xor_sync(0xffffffffu, nsteps, WIDTH); nsteps = nsteps > o ? nsteps : o; }
-    const bool mine = lid < nw;
-    const int u0 = 16 + shift - lid, hb = nbw >> 1;         // band of column c: words ((c + 16 + shift) >> 5) - nbw / 2 .. + nbw / 2 - 1
-    uint32_t cout = 0;
-    for (int s = 0; s < nsteps; ++s) {
-        uint32_t cin = __shfl_up_sync(0xffffffffu, cout, 1, WIDTH);
-        if (lid == 0) cin = 0x80000000u | (uint32_t)(st[s] & 3);        // row 0 of the matrix: D[0][j] = j
-        const int col = s - lid;
-        if (mine && (unsigned)col < (unsigned)tblk) {
-            const uint32_t tc = cin & 3;
-            const uint32_t elo = (tc & 1) ? pe1 : pe0, ehi = (tc & 1) ? pe3 : pe2;
-            uint32_t Eq = (tc & 2) ? ehi : elo;
+    const int W = 32 * nbw;
+    const int cl = 32 * (lid - (nbw >> 1) + 1) - 16 - shift;
+    uint2* __restrict__ row = mat + (size_t)lid * W;
+    int rel = lid < nw ? -lid - cl : 0x40000000;            // column - cl(lid) of the step; never in [0, W) for a lane without rows
+    const char* pe_base = reinterpret_cast<const char*>(&S.pe[0][lane]);
+    uint32_t Pv = 0xffffffffu, Mv = 0, cout = 0, accP = 0, accM = 0;
+    __syncwarp();
+    int s = 0;
+    const int nchunk = (nsteps + 31) >> 5;
+    for (int c = 0; c < nchunk; ++c) {
+        const int n = nsteps - 32 * c < 32 ? nsteps - 32 * c : 32;
+#pragma unroll 4
+        for (int b = 0; b < n; ++b, ++s, ++rel) {
+            uint32_t cin = __shfl_up_sync(0xffffffffu, cout, 1, WIDTH);
+            if (lid == 0) cin = 0x80000000u | ((uint32_t)st[s] << 7);       // row 0 of the matrix: D[0][j] = j
+            const uint32_t symoff = cin & 0x180u;
+            uint32_t Eq = *reinterpret_cast<const uint32_t*>(pe_base + symoff);
             const uint32_t Xv = Eq | Mv;
-            Eq |= (cin >> 30) & 1;
+            Eq |= cin & 1u;
             const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
             const uint32_t Ph = Mv | ~(Xh | Pv);
             const uint32_t Mh = Pv & Xh;
-            cout = (Ph & 0x80000000u) | ((Mh >> 1) & 0x40000000u) | tc;
-            score += (int)((Ph >> lb) & 1) - (int)((Mh >> lb) & 1);     // meaningful in lane lw only
-            if (score < best) { best = score; bestj = col; }
-            const uint32_t Phs = __funnelshift_l(cin, Ph, 1);           // (Ph << 1) | (hin > 0)
-            const uint32_t Mhs = __funnelshift_l(cin << 1, Mh, 1);      // (Mh << 1) | (hin < 0)
+            cout = (Ph & 0x80000000u) | symoff | (Mh >> 31);
+            accP = __funnelshift_r(accP, Ph >> lb, 1);
+            accM = __funnelshift_r(accM, Mh >> lb, 1);
+            const uint32_t Phs = (Ph << 1) | (cin >> 31);
+            const uint32_t Mhs = (Mh << 1) | (cin & 1u);
             Pv = Mhs | ~(Xv | Phs);
             Mv = Phs & Xv;
-            const int k = lid + hb - ((s + u0) >> 5);
-            if ((unsigned)k < (unsigned)nbw) mat[col * nbw + k] = make_uint2(Pv, Ph);
+            if ((unsigned)rel < (unsigned)W) row[rel] = make_uint2(Pv, Ph);
+            if (s == lid - 1) { Pv = 0xffffffffu; Mv = 0; }                 // my first column is next
         }
+        if (lid == lw) S.sb[half][c] = make_uint2(accP >> (32 - n), accM >> (32 - n));     // bit b: step 32 c + b
     }
-    *best_out = __shfl_sync(0xffffffffu, best, lw, WIDTH);
-    *bestj_out = __shfl_sync(0xffffffffu, bestj, lw, WIDTH);
+    __syncwarp();
+    // ---- first minimum of qblk + sum of (+1, -1) over the columns: lane = 32 steps
+    int best = 0x7fffffff, bests = 0x7fffffff, carry = 0;
+    for (int c0 = 0; c0 < nchunk; c0 += WIDTH) {
+        const int c = c0 + lid;
+        uint32_t bp = 0, bm = 0;
+        if (c < nchunk) { const uint2 v = S.sb[half][c]; bp = v.x; bm = v.y; }
+        // steps of lane lw that are columns of the block: [lw, lw + tblk)
+        const int lo = lw - 32 * c, hi = lw + tblk - 32 * c;
+        uint32_t vm = 0xffffffffu;
+        if (lo > 0) vm = lo >= 32 ? 0u : vm << lo;
+        if (hi < 32) vm = hi <= 0 ? 0u : vm & (0xffffffffu >> (32 - hi));
+        bp &= vm; bm &= vm;
+        const int tot = __popc(bp) - __popc(bm);
+        int pre = tot;                                                  // inclusive sum over the lanes of the group
+#pragma unroll
+        for (int d = 1; d < WIDTH; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, pre, d, WIDTH); if (lid >= d) pre += o; }
+        int run = qblk + carry + pre - tot, lmin = 0x7fffffff, lpos = 0;
+#pragma unroll 4
+        for (int b = 0; b < 32; ++b) {
+            run += (int)((bp >> b) & 1u) - (int)((bm >> b) & 1u);
+            if (((vm >> b) & 1u) && run < lmin) { lmin = run; lpos = b; }
+        }
+        if (lmin < best) { best = lmin; bests = 32 * c + lpos; }
+        carry += __shfl_sync(0xffffffffu, pre, WIDTH - 1, WIDTH);
+    }
+#pragma unroll
+    for (int d = WIDTH >> 1; d > 0; d >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, best, d, WIDTH), os = __shfl_xor_sync(0xffffffffu, bests, d, WIDTH);
+        if (ob < best || (ob == best && os < bests)) { best = ob; bests = os; }
+    }
+    *best_out = best;
+    *bestj_out = best == 0x7fffffff ? -1 : bests - lw;
 }
 
 // ---- whole-warp pieces ------------------------------------------------------------------------------------------------
@@ -351,8 +400,9 @@ __device__ __forceinline__ void lp_walk_post(WarpScratch& S, const ExtParams& P,
             i = XF(X_WI, lane); j = XF(X_WJ, lane); r = XF(X_WR, lane); found = XF(X_WFLAGS, lane) & 1;
             acnt = XF(X_WACNT, lane); qcnt = XF(X_WQCNT, lane); tcnt = XF(X_WTCNT, lane); m = XF(X_WM, lane); acc = (uint32_t)XF(X_WACC, lane);
         }
-        const int shift = XF(X_SHIFT, lane), nbw = XF(X_NBW, lane), hb = nbw >> 1;
-        const int band_lo = P.band_test ? hb - 1 : 0, band_hi = P.band_test ? hb + 1 : nbw;
+        const int shift = XF(X_SHIFT, lane), nbw = XF(X_NBW, lane), W = 32 * nbw;
+        const int c0 = 32 * ((nbw >> 1) - 1) + 16 + shift;              // column - cl(w) = column - 32 w + c0
+        const int band_lo = P.band_test ? (W >> 1) - 32 : 0, band_hi = P.band_test ? (W >> 1) + 32 : W;
         bool moved = false;
         while (i > 0 || j > 0) {
             int op;
@@ -360,9 +410,9 @@ __device__ __forceinline__ void lp_walk_post(WarpScratch& S, const ExtParams& P,
             else if (j == 0) { op = OP_QONLY; --i; }
             else {
                 const int wi = (i - 1) >> 5;
-                const int k = wi + hb - ((j - 1 + 16 + shift) >> 5);
-                if (k < band_lo || k >= band_hi) { moved = true; break; }
-                const uint2 v = mat[(j - 1) * nbw + k];
+                const int rel = j - 1 - 32 * wi + c0;
+                if (rel < band_lo || rel >= band_hi) { moved = true; break; }
+                const uint2 v = mat[wi * W + rel];
                 const int bit = (i - 1) & 31;
                 if ((v.x >> bit) & 1) { op = OP_QONLY; --i; }
                 else if ((v.y >> bit) & 1) { op = OP_TONLY; --j; }
@@ -407,15 +457,17 @@ __device__ __forceinline__ void lp_walk_post(WarpScratch& S, const ExtParams& P,
     const int keep = kcut + (done ? M : 0);
     {
         // out[(ncol + x) * out_dir] = rev[asize - 1 - x], x < keep: in address order d[u], u < keep, that is a copy of
-        // rev[asize - keep + u] (left side) or of rev[asize - 1 - u] (right side)
+        // rev[asize - keep + u] (left side) or of rev[asize - 1 - u] (right side); four bytes at a time where d is aligned
         const uint8_t* rb = reinterpret_cast<const uint8_t*>(rev);
         uint8_t* d = out_dir > 0 ? out + ncol : out - (ncol + keep - 1);
         const int sidx = out_dir > 0 ? asize - 1 : asize - keep, sdir = out_dir > 0 ? -1 : 1;
         int u = 0;
         while (u < keep && ((uintptr_t)(d + u) & 3)) { d[u] = rb[sidx + sdir * u]; ++u; }
         for (; u + 4 <= keep; u += 4) {
-            const uint32_t w = (uint32_t)rb[sidx + sdir * u] | ((uint32_t)rb[sidx + sdir * (u + 1)] << 8) |
-                               ((uint32_t)rb[sidx + sdir * (u + 2)] << 16) | ((uint32_t)rb[sidx + sdir * (u + 3)] << 24);
+            const int lo = sdir > 0 ? sidx + u : sidx - u - 3;                          // the four source bytes are rev[lo .. lo + 3]
+            const uint32_t w0 = rev[lo >> 2], w1 = rev[(lo >> 2) + 1];
+            uint32_t w = __funnelshift_r(w0, w1, 8 * (lo & 3));
+            if (sdir < 0) w = __byte_perm(w, 0, 0x0123);
             *reinterpret_cast<uint32_t*>(d + u) = w;
         }
         for (; u < keep; ++u) d[u] = rb[sidx + sdir * u];
@@ -482,12 +534,12 @@ k_extend(ExtParams P)
                 const int hh = lane >> 4;
                 const int sl = hh ? sb : sa;
                 const int qb = sl >= 0 ? XF(X_QBLK, sl) : 0, tb = sl >= 0 ? XF(X_TBLK, sl) : 0;
-                myers_forward<16>(S.h[hh].q + (hh ? qa1 : qa0), S.h[hh].t + (hh ? ta1 : ta0), qb, tb,
-                                  P.mat + (wslot + (sl >= 0 ? sl : 0)) * EXT_MAT_STRIDE, sl >= 0 ? XF(X_SHIFT, sl) : 0, sl >= 0 ? XF(X_NBW, sl) : 4, lane & 15, &best, &bestj);
+                myers_forward<16>(S, S.h[hh].q + (hh ? qa1 : qa0), S.h[hh].t + (hh ? ta1 : ta0), qb, tb,
+                                  P.mat + (wslot + (sl >= 0 ? sl : 0)) * EXT_MAT_STRIDE, sl >= 0 ? XF(X_SHIFT, sl) : 0, sl >= 0 ? XF(X_NBW, sl) : 4, lane, &best, &bestj);
                 __syncwarp();
                 if ((lane & 15) == 0 && sl >= 0) { XF(X_BEST, sl) = best; XF(X_BESTJ, sl) = bestj; XF(X_STATE, sl) = ST_WALK; }
             } else {
-                myers_forward<32>(S.h[0].q + qa0, S.h[0].t + ta0, qb0, tb0, P.mat + (wslot + sa) * EXT_MAT_STRIDE, XF(X_SHIFT, sa), XF(X_NBW, sa), lane, &best, &bestj);
+                myers_forward<32>(S, S.h[0].q + qa0, S.h[0].t + ta0, qb0, tb0, P.mat + (wslot + sa) * EXT_MAT_STRIDE, XF(X_SHIFT, sa), XF(X_NBW, sa), lane, &best, &bestj);
                 __syncwarp();
                 if (lane == 0) { XF(X_BEST, sa) = best; XF(X_BESTJ, sa) = bestj; XF(X_STATE, sa) = ST_WALK; }
             }

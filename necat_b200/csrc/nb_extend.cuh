@@ -45,7 +45,7 @@ struct ExtParams {
 };
 
 #define EXT_MAT_STRIDE ((size_t)(EXT_MAX_BLK + 32) * 8)
-#define EXT_REV_STRIDE ((size_t)2 * EXT_MAX_BLK)
+#define EXT_REV_STRIDE ((size_t)2 * EXT_MAX_BLK + 32)
 
 int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* templates, const ExtTask* d_tasks, uint32_t n_tasks,
                      nb_alignment* d_results, uint8_t* d_ops, double error, int min_align_size, int tail_match_len);
