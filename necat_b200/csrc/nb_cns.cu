@@ -981,6 +981,9 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
         if (per) build(0, std::min(tpls.size(), per));
         for (auto& x : th) x.join();
     }
+    // Longest templates first: their candidates are the longest chains of block alignments of an extension launch (k_extend
+    // takes the tasks in order), started first they do not end up as its tail.  (Records are put in id order by the caller.)
+    std::stable_sort(tpls.begin(), tpls.end(), [](const Tpl& a, const Tpl& b) { return a.T > b.T; });
     // The consensus kernels of a template are a dependent chain over its positions, so the longest templates decide
     // how long the consensus of a batch lasts.  They are moved to the front and get their own group, whose consensus
     // runs beside the extension of everything else (process_chunk).

@@ -33,7 +33,7 @@ __device__ __forceinline__ int seq_base(const SeqView& v, int idx)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// A warp keeps EXT_SLOTS = 32 candidates in flight, lane = slot.  The pieces of a candidate's state machine that are one
+// A warp keeps EXT_SLOTS candidates in flight, lane = slot (the lanes beyond have none).  The pieces of a candidate's state machine that are one
 // dependent chain per candidate -- cutting the next block, the walk-back over the (Pv, Ph) bits, the bookkeeping
 // between blocks -- run with every lane on its own candidate; the forward passes, which have 16 to 26 independent
 // 32-row words per DP column, are run by the whole warp, two candidates at a time in its two halves.
@@ -43,7 +43,9 @@ __device__ __forceinline__ int seq_base(const SeqView& v, int idx)
 // the last block of a side, whose two sides differ by up to 30 %).  A walk that leaves the band (the path of a 512-column
 // block of 15 %-error reads wanders ~10 rows) makes the forward pass of that block run again with the band centred on
 // the diagonal the walk has reached, and continues from where it stopped.
-#define EXT_SLOTS 32
+#ifndef EXT_SLOTS
+#define EXT_SLOTS 8           // candidates in flight per warp: more of them make the per-lane phases denser, fewer keep the chain of one
+#endif                      // candidate (forward passes of all slots, then its walk-back) short and the launch's tail with it
 #define EXT_BAND_WORDS 8        // at most
 
 enum {
@@ -64,7 +66,7 @@ struct WarpScratch {
     HalfScratch h[2];
     uint32_t    pe[4][32];              // forward pass: match mask of lane l's 32 query rows for symbol c at pe[c][l]
     uint2       sb[2][28];              // forward pass: per 32 steps the (+1, -1) bits of the last query row, per half-warp
-    int32_t     f[X_NF][EXT_SLOTS];     // state of the 32 candidates, one field per row: f[field][slot]
+    int32_t     f[X_NF][EXT_SLOTS];     // state of the candidates in flight, one field per row: f[field][slot]
 };
 
 #define XF(field, slot) S.f[field][slot]
@@ -393,6 +395,17 @@ __device__ __forceinline__ void lp_walk_post(WarpScratch& S, const ExtParams& P,
     if (failed && qblk > 30 && tblk > 30) done = 1;                             // oc_aligner.c:220 (qfae = tfae = 0)
     const int M = done ? P.tail_match_len : 8;
     int asize = 0, found = 0, acnt = 0, qcnt = 0, tcnt = 0;
+    // bases of the two reads through one cached 16-base word each
+    uint32_t qw = 0, tw = 0;
+    long long qwi = -1, twi = -1;
+    auto cached_base = [](const SeqView& v, int idx, uint32_t& w, long long& wi) -> int {
+        const uint64_t p = v.strand ? v.off + (uint64_t)(v.len - 1 - idx) : v.off + (uint64_t)idx;
+        const long long i = (long long)(p >> 4);
+        if (i != wi) { w = __ldg(reinterpret_cast<const uint32_t*>(v.pac) + i); wi = i; }
+        const int k = (int)(p & 15);
+        const int b = (w >> (8 * (k >> 2) + 2 * (3 - (k & 3)))) & 3;
+        return v.strand ? 3 - b : b;
+    };
     if (!failed) {
         int i = qblk, j = bestj + 1, r = 0, m = 0;
         uint32_t acc = 0;
@@ -417,7 +430,7 @@ __device__ __forceinline__ void lp_walk_post(WarpScratch& S, const ExtParams& P,
                 if ((v.x >> bit) & 1) { op = OP_QONLY; --i; }
                 else if ((v.y >> bit) & 1) { op = OP_TONLY; --j; }
                 else {
-                    op = seq_base(C.qv, q0 + dir * (i - 1)) == seq_base(C.tv, t0 + dir * (j - 1)) ? OP_MATCH : OP_MISMATCH;
+                    op = cached_base(C.qv, q0 + dir * (i - 1), qw, qwi) == cached_base(C.tv, t0 + dir * (j - 1), tw, twi) ? OP_MATCH : OP_MISMATCH;
                     --i; --j;
                 }
             }
@@ -448,7 +461,7 @@ __device__ __forceinline__ void lp_walk_post(WarpScratch& S, const ExtParams& P,
     if (!found || kcut < 1) {
         // exact-match prefix only, then stop (:243-253)
         int n = 0;
-        while (n < mn && seq_base(C.qv, q0 + dir * n) == seq_base(C.tv, t0 + dir * n)) ++n;
+        while (n < mn && cached_base(C.qv, q0 + dir * n, qw, qwi) == cached_base(C.tv, t0 + dir * n, tw, twi)) ++n;
         for (int x = 0; x < n; ++x) out[(long long)(ncol + x) * out_dir] = OP_MATCH;
         XF(X_NCOL, lane) = ncol + n;
         lp_end_side(S, P, lane);
@@ -486,20 +499,21 @@ k_extend(ExtParams P)
     const uint32_t lt_mask = (1u << lane) - 1;
     WarpScratch& S = reinterpret_cast<WarpScratch*>(ext_smem)[wid];
     const size_t wslot = ((size_t)blockIdx.x * EXT_WARPS + wid) * EXT_SLOTS;
-    uint2* mat = P.mat + (wslot + lane) * EXT_MAT_STRIDE;                               // of my slot
-    uint32_t* rev = reinterpret_cast<uint32_t*>(P.rev + (wslot + lane) * EXT_REV_STRIDE);
+    uint2* mat = P.mat + (wslot + (lane & (EXT_SLOTS - 1))) * EXT_MAT_STRIDE;          // of my slot
+    uint32_t* rev = reinterpret_cast<uint32_t*>(P.rev + (wslot + (lane & (EXT_SLOTS - 1))) * EXT_REV_STRIDE);
     unsigned long long nb = 0, nc = 0, nwd = 0;
-    XF(X_STATE, lane) = ST_IDLE;
+    const bool has = lane < EXT_SLOTS;                  // this lane owns a slot
+    if (has) XF(X_STATE, lane) = ST_IDLE;
     __syncwarp();
     bool drained = false;
     for (;;) {
         // ---- idle slots take candidates from the queue
-        const uint32_t idle = __ballot_sync(0xffffffffu, XF(X_STATE, lane) == ST_IDLE);
+        const uint32_t idle = __ballot_sync(0xffffffffu, has && XF(X_STATE, lane) == ST_IDLE);
         if (idle && !drained) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(P.next_task, (uint32_t)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (XF(X_STATE, lane) == ST_IDLE) {
+            if (has && XF(X_STATE, lane) == ST_IDLE) {
                 const uint32_t ti = base + (uint32_t)__popc(idle & lt_mask);
                 if (ti < P.n_tasks) lp_start_task(S, P, ti, lane);
             }
@@ -507,19 +521,19 @@ k_extend(ExtParams P)
         }
         __syncwarp();
         // ---- candidates whose right side has ended: result record, whole warp
-        uint32_t fin = __ballot_sync(0xffffffffu, XF(X_STATE, lane) == ST_FINISH);
+        uint32_t fin = __ballot_sync(0xffffffffu, has && XF(X_STATE, lane) == ST_FINISH);
         while (fin) {
             const int slot = __ffs(fin) - 1;
             fin &= fin - 1;
             ext_finish(S, P, slot, lane);
         }
-        const uint32_t blk = __ballot_sync(0xffffffffu, XF(X_STATE, lane) == ST_BLOCK);
+        const uint32_t blk = __ballot_sync(0xffffffffu, has && XF(X_STATE, lane) == ST_BLOCK);
         if (!blk) {
-            if (drained && __ballot_sync(0xffffffffu, XF(X_STATE, lane) != ST_IDLE) == 0) break;
+            if (drained && __ballot_sync(0xffffffffu, has && XF(X_STATE, lane) != ST_IDLE) == 0) break;
             continue;
         }
         // ---- forward passes: side by side in the two half-warps when both blocks fit 16 lanes
-        uint32_t small = blk & __ballot_sync(0xffffffffu, XF(X_QBLK, lane) <= 512), big = blk & ~small;
+        uint32_t small = blk & __ballot_sync(0xffffffffu, has && XF(X_QBLK, lane) <= 512), big = blk & ~small;
         while (small | big) {
             int sa, sb = -1;
             if (small) {
@@ -550,7 +564,7 @@ k_extend(ExtParams P)
             __syncwarp();
         }
         // ---- walk-backs and bookkeeping: every lane on its own candidate
-        if (XF(X_STATE, lane) == ST_WALK) lp_walk_post(S, P, mat, rev, lane);
+        if (has && XF(X_STATE, lane) == ST_WALK) lp_walk_post(S, P, mat, rev, lane);
         __syncwarp();
     }
     if (lane == 0) {
@@ -572,7 +586,7 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     unsigned grid = NB_SMS * ctas_per_sm;
     {
         // no more warps than there are candidates to fill a good part of their 32 slots
-        const unsigned want = (unsigned)((n_tasks + EXT_WARPS * 8 - 1) / (EXT_WARPS * 8));
+        const unsigned want = (unsigned)((n_tasks + EXT_WARPS * EXT_SLOTS - 1) / (EXT_WARPS * EXT_SLOTS));
         if (grid > want) grid = want ? want : 1;
     }
     const size_t slots = (size_t)NB_SMS * (kCtas < 1 ? 1 : kCtas) * EXT_WARPS * EXT_SLOTS;      // candidates in flight (sized for the full grid)
