@@ -658,6 +658,10 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                 NB_LAUNCH_CHECK(cx);
                 k_cns_fix<<<(unsigned)((units.size() + 127) / 128), 128, 0, cst>>>(P);
                 NB_LAUNCH_CHECK(cx);
+                g = (unsigned)((units.size() + 3) / 4);
+                if (g > NB_SMS * 16) g = NB_SMS * 16;
+                k_cns_plan<<<g, 128, 0, cst>>>(P);
+                NB_LAUNCH_CHECK(cx);
                 // sixteen templates per CTA (8 lanes each); the chunk is sorted by length, the longest start first
                 if (kDpTest == 1) {
                     const size_t dsm = (size_t)16 * (16 * 128 + 8 * 8);

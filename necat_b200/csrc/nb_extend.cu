@@ -44,7 +44,7 @@ __device__ __forceinline__ int seq_base(const SeqView& v, int idx)
 // block of 15 %-error reads wanders ~10 rows) makes the forward pass of that block run again with the band centred on
 // the diagonal the walk has reached, and continues from where it stopped.
 #ifndef EXT_SLOTS
-#define EXT_SLOTS 8           // candidates in flight per warp: more of them make the per-lane phases denser, fewer keep the chain of one
+#define EXT_SLOTS 16          // candidates in flight per warp: more of them make the per-lane phases denser, fewer keep the chain of one
 #endif                      // candidate (forward passes of all slots, then its walk-back) short and the launch's tail with it
 #define EXT_BAND_WORDS 8        // at most
 
