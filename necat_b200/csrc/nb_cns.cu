@@ -951,6 +951,8 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
                     const uint32_t sb = ss - p.item[3], se = ss - p.item[2];
                     p.item[2] = sb; p.item[3] = se;
                 }
+                // -s 1 (consensus_one_read.c:249-255): more than MAX_EXAMINED_CAN records are cut in load order and stay unsorted
+                if (!(o.small_memory && one.size() > 300))
                 std::sort(one.begin(), one.end(), [](const nb_packed_candidate& a, const nb_packed_candidate& b) {
                     // PackedGappedCandidate_CnsScoreGT, gapped_candidate.c:96-126
                     const int as = (int)(a.item[0] & ((1u << 29) - 1)), bs = (int)(b.item[0] & ((1u << 29) - 1));
@@ -1025,6 +1027,31 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     size_t n_chunks = env_chunks ? (size_t)atoi(env_chunks) : 1;
     const size_t kChunkMax = 32768;
     if (n_chunks < (tpls.size() + kChunkMax - 1) / kChunkMax) n_chunks = (tpls.size() + kChunkMax - 1) / kChunkMax;
+    // ... and the device memory of a chunk: the op bytes of its extension rounds (every speculative extension reserves
+    // query + template + slack bytes; round 0 is counted exactly, the later rounds as 60 % more) and the link, level and
+    // position records of its consensus (16 B per alignment column, ~1.3 columns per template base and alignment)
+    std::vector<uint64_t> need(tpls.size());
+    uint64_t need_total = 0;
+    for (size_t t = 0; t < tpls.size(); ++t) {
+        const Tpl& T = tpls[t];
+        uint64_t r0 = 0;
+        for (size_t k = 0; k < T.n && k < 50; ++k) {
+            const Can& c = cans[T.first + k];
+            r0 += ((uint64_t)c.qsize + (uint64_t)T.T + (uint64_t)std::min(c.qoff, c.soff) + 64 + 15) & ~15ull;
+        }
+        const uint64_t alns = std::min<uint64_t>(T.n, (uint64_t)o.max_cov + 4);
+        need[t] = r0 + r0 * 6 / 10 + (uint64_t)T.T * (21 * alns + 120);
+        need_total += need[t];
+    }
+    {
+        size_t fr = 0, tot = 0;
+        NB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+        uint64_t budget = (uint64_t)fr / 2;
+        if (getenv("NB_CNS_MEM")) budget = strtoull(getenv("NB_CNS_MEM"), NULL, 10);       // (tests)
+        if (budget < (64ull << 20)) budget = 64ull << 20;
+        const size_t by_mem = (size_t)((need_total + budget - 1) / budget);
+        if (n_chunks < by_mem) n_chunks = by_mem;
+    }
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > tpls.size()) n_chunks = tpls.size() ? tpls.size() : 1;
     int n_workers = env_pipes ? atoi(env_pipes) : 1;
@@ -1033,13 +1060,12 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     if (n_workers < 1) n_workers = 1;
     std::vector<size_t> cut(n_chunks + 1, tpls.size());
     {
-        uint64_t total_T = 0, acc = 0;
-        for (const Tpl& t : tpls) total_T += (uint64_t)t.T;
+        uint64_t acc = 0;
         size_t k = 1;
         cut[0] = 0;
         for (size_t t = 0; t < tpls.size() && k < n_chunks; ++t) {
-            acc += (uint64_t)tpls[t].T;
-            if (acc * n_chunks >= total_T * k || t + 1 - cut[k - 1] >= kChunkMax) cut[k++] = t + 1;
+            acc += need[t];
+            if (acc * n_chunks >= need_total * k || t + 1 - cut[k - 1] >= kChunkMax) cut[k++] = t + 1;
         }
     }
     JobShared sh;
@@ -1108,7 +1134,8 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     // ---- reads of [min_id, max_id) that were never corrected go to raw_out whole (consensus_one_partition.c:173-194)
     fills.clear();
     uint64_t used = sh.used.load();
-    for (int id = min_id; id < max_id; ++id) {
+    // (-s 1: the reference then has no merged read store and skips this dump, consensus_one_partition.c:173)
+    for (int id = min_id; id < max_id && !o.small_memory; ++id) {
         if (corrected[(size_t)id] || id % shard_count != shard_index) continue;
         const int L = (int)reads->h_len[id];
         nb_cns_record r;

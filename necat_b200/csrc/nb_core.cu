@@ -183,7 +183,8 @@ extern "C" int nb_volume_upload(nb_ctx* ctx, const uint8_t* pac, uint64_t db_siz
 {
     if (!ctx || !out || (!pac && db_size) || (nseq && (!seq_offset || !seq_size)))
         return nb_fail(ctx, NB_EINVAL, "nb_volume_upload: bad arguments");
-    if (db_size >= (1ull << 32)) return nb_fail(ctx, NB_ELIMIT, "volume of %llu bases exceeds the 2^32 limit", (unsigned long long)db_size);
+    // (no size limit here: offsets are 64-bit everywhere.  A volume that gets an index has to stay below 2^32 bases --
+    //  nb_index_build checks that -- the merged read store of oc2cns may be as large as device memory allows.)
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     nb_volume* v = (nb_volume*)calloc(1, sizeof(nb_volume));
     if (!v) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
@@ -194,16 +195,25 @@ extern "C" int nb_volume_upload(nb_ctx* ctx, const uint8_t* pac, uint64_t db_siz
     const uint64_t nb = (db_size + 3) >> 2;
     const uint64_t padded = ((nb + 15) & ~15ull) + 256;
     int rc;
-    if ((rc = nb_dev_alloc(ctx, (void**)&v->d_pac, padded))) return rc;
-    if ((rc = nb_dev_alloc(ctx, (void**)&v->d_off, sizeof(uint64_t) * (nseq + 1)))) return rc;
-    if ((rc = nb_dev_alloc(ctx, (void**)&v->d_len, sizeof(uint32_t) * (nseq + 1)))) return rc;
+    auto drop = [&](int code) {             // error exit: nothing of the half-built volume stays behind
+        if (v->d_pac) nb_dev_release(ctx, v->d_pac);
+        if (v->d_off) nb_dev_release(ctx, v->d_off);
+        if (v->d_len) nb_dev_release(ctx, v->d_len);
+        free(v->h_off); free(v->h_len);
+        if (v->h_pac) cudaFreeHost(v->h_pac);
+        free(v);
+        return code;
+    };
+    if ((rc = nb_dev_alloc(ctx, (void**)&v->d_pac, padded))) return drop(rc);
+    if ((rc = nb_dev_alloc(ctx, (void**)&v->d_off, sizeof(uint64_t) * (nseq + 1)))) return drop(rc);
+    if ((rc = nb_dev_alloc(ctx, (void**)&v->d_len, sizeof(uint32_t) * (nseq + 1)))) return drop(rc);
     v->h_off = (uint64_t*)malloc(sizeof(uint64_t) * (nseq + 1));
     v->h_len = (uint32_t*)malloc(sizeof(uint32_t) * (nseq + 1));
-    if (!v->h_off || !v->h_len) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    if (!v->h_off || !v->h_len) return drop(nb_fail(ctx, NB_ENOMEM, "out of host memory"));
     v->max_len = 0;
     for (uint64_t i = 0; i < nseq; ++i) {
         if (seq_size[i] >= (1ull << 31) || seq_offset[i] + seq_size[i] > db_size) {
-            return nb_fail(ctx, NB_EINVAL, "sequence %llu out of range", (unsigned long long)i);
+            return drop(nb_fail(ctx, NB_EINVAL, "sequence %llu out of range", (unsigned long long)i));
         }
         v->h_off[i] = seq_offset[i];
         v->h_len[i] = (uint32_t)seq_size[i];
@@ -217,7 +227,7 @@ extern "C" int nb_volume_upload(nb_ctx* ctx, const uint8_t* pac, uint64_t db_siz
             ctx->pin_cache[k] = NULL; ctx->pin_cache_bytes[k] = 0;
         }
     if (!v->h_pac) {
-        NB_CUDA(ctx, cudaHostAlloc((void**)&v->h_pac, padded, cudaHostAllocDefault));
+        if (cudaHostAlloc((void**)&v->h_pac, padded, cudaHostAllocDefault) != cudaSuccess) { v->h_pac = NULL; return drop(nb_fail(ctx, NB_ENOMEM, "out of pinned host memory (%llu bytes)", (unsigned long long)padded)); }
         v->h_pac_bytes = padded;
     }
     memcpy(v->h_pac, pac, nb);

@@ -246,6 +246,7 @@ extern "C" int nb_index_build(nb_ctx* ctx, const nb_volume* ref, int k, int q, n
     if (!ctx || !ref || !out) return nb_fail(ctx, NB_EINVAL, "nb_index_build: bad arguments");
     if (k < 4 || k > 15) return nb_fail(ctx, NB_ELIMIT, "kmer size %d unsupported (4..15; reference HashBits = 30)", k);
     if (q < 1) return nb_fail(ctx, NB_EINVAL, "kmer count cutoff must be >= 1");
+    if (ref->db_size >= (1ull << 32)) return nb_fail(ctx, NB_ELIMIT, "a volume of %llu bases cannot be indexed: index positions are 32-bit (oc2mkdb cuts volumes at 2 Gbp)", (unsigned long long)ref->db_size);
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     nb_index* ix = (nb_index*)calloc(1, sizeof(nb_index));

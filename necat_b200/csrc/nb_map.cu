@@ -687,20 +687,15 @@ k_candidates(MapDev P)
 
 // ------------------------------------------------------------------- host
 
-extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, int ref_start_id,
-                             const nb_volume* reads, int read_start_id, uint64_t read_lo, uint64_t read_hi,
-                             const nb_map_options* opt, nb_candidate** out, uint64_t* n_out)
+// Candidates of the reads [read_lo, read_hi) appended to `acc`.  *too_big: the seed hits of the range need more scratch than
+// hit_budget allows and the range holds more than one read -- nothing was appended, the caller splits the range.
+static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, int ref_start_id,
+                        const nb_volume* reads, int read_start_id, uint64_t read_lo, uint64_t read_hi,
+                        const nb_map_options* opt, uint64_t hit_budget, std::vector<nb_candidate>& acc, bool* too_big)
 {
-    if (!ctx || !idx || !ref || !reads || !opt || !out || !n_out) return nb_fail(ctx, NB_EINVAL, "nb_map_volume: bad arguments");
-    *out = NULL; *n_out = 0;
-    if (read_hi > reads->nseq || read_lo > read_hi) return nb_fail(ctx, NB_EINVAL, "read range out of bounds");
-    if (opt->kmer_size != idx->k) return nb_fail(ctx, NB_EINVAL, "kmer size %d differs from the index (%d)", opt->kmer_size, idx->k);
-    if (opt->block_size < 1 || opt->block_size > 32767) return nb_fail(ctx, NB_ELIMIT, "block size must be in 1..32767 (reference uses short offsets)");
-    if (opt->scan_window < 1) return nb_fail(ctx, NB_EINVAL, "scan window must be >= 1");
-    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    *too_big = false;
     cudaStream_t st = ctx->stream;
     const uint64_t nreads = read_hi - read_lo;
-    memset(&ctx->mc, 0, sizeof ctx->mc);
     if (nreads == 0) return NB_OK;
     if (nreads * 2 >= (1ull << 31)) return nb_fail(ctx, NB_ELIMIT, "too many reads in one call");
     const uint32_t U = (uint32_t)(nreads * 2);
@@ -776,6 +771,7 @@ extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* 
         }
     }
     hit_base[U] = H;
+    if (H + scratch > hit_budget && nreads > 1) { *too_big = true; return NB_OK; }
     NB_CUDA(ctx, cudaMemcpyAsync(d_hit_base, hit_base.data(), sizeof(uint64_t) * (U + 1), cudaMemcpyHostToDevice, st));
     NB_CUDA(ctx, cudaMemcpyAsync(d_scratch_base, scratch_base.data(), sizeof(uint64_t) * U, cudaMemcpyHostToDevice, st));
     if ((rc = S.get(&P.seed_kid, H))) return rc;
@@ -821,8 +817,8 @@ extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* 
     }
     NB_CUDA(ctx, cudaStreamSynchronize(st));
     float ms;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev2); ctx->tm.map_ms = ms;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->tm.map_probe_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev2); ctx->tm.map_ms += ms;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->tm.map_probe_ms += ms;
     ctx->tm.d2h_bytes += C * (sizeof(nb_candidate) + 8) + U * 4;
     ctx->tm.h2d_bytes += (U + 1) * 16 + U * 8;
 
@@ -842,8 +838,6 @@ extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* 
             if (first[u + 1] - first[u] > 1)
                 std::sort(order.begin() + first[u], order.begin() + first[u + 1], [&](uint64_t a, uint64_t b) { return cseq[a] < cseq[b]; });
     }
-    nb_candidate* res = (nb_candidate*)malloc(sizeof(nb_candidate) * (C ? C : 1));
-    if (!res) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
     uint64_t nres = 0;
     std::vector<nb_candidate> one;
     for (uint64_t i = 0; i < C;) {
@@ -867,12 +861,70 @@ extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* 
             });
             one.resize((size_t)opt->num_candidates);
         }
-        for (auto& c : one) res[nres++] = c;
+        for (auto& c : one) { acc.push_back(c); ++nres; }
         i = j;
     }
+    ctx->mc.n_units += U; ctx->mc.n_probes += np; ctx->mc.n_hits += H; ctx->mc.n_seeds += cnts[1];
+    ctx->mc.n_blocks += cnts[2]; ctx->mc.n_eligible += cnts[3]; ctx->mc.n_candidates += nres; ctx->mc.query_bases += qbases * 2;
+    return NB_OK;
+}
+
+// The reads of the range are mapped in pieces: a piece holds at most kProbeChunk probes (the probe arrays are sized by it)
+// and its seed hits (13 scratch arrays of one entry per hit) have to fit a share of the free device memory -- a piece that
+// does not is cut in two, down to single reads.
+extern "C" int nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, int ref_start_id,
+                             const nb_volume* reads, int read_start_id, uint64_t read_lo, uint64_t read_hi,
+                             const nb_map_options* opt, nb_candidate** out, uint64_t* n_out)
+{
+    if (!ctx || !idx || !ref || !reads || !opt || !out || !n_out) return nb_fail(ctx, NB_EINVAL, "nb_map_volume: bad arguments");
+    *out = NULL; *n_out = 0;
+    if (read_hi > reads->nseq || read_lo > read_hi) return nb_fail(ctx, NB_EINVAL, "read range out of bounds");
+    if (opt->kmer_size != idx->k) return nb_fail(ctx, NB_EINVAL, "kmer size %d differs from the index (%d)", opt->kmer_size, idx->k);
+    if (opt->block_size < 1 || opt->block_size > 32767) return nb_fail(ctx, NB_ELIMIT, "block size must be in 1..32767 (reference uses short offsets)");
+    if (opt->scan_window < 1) return nb_fail(ctx, NB_EINVAL, "scan window must be >= 1");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(&ctx->mc, 0, sizeof ctx->mc);
+    ctx->tm.map_ms = 0; ctx->tm.map_probe_ms = 0;
+    const uint64_t kProbeChunk = getenv("NB_MAP_PROBES") ? strtoull(getenv("NB_MAP_PROBES"), NULL, 10) : (96ull << 20);
+    uint64_t hit_budget;
+    {
+        size_t fr = 0, tot = 0;
+        NB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+        hit_budget = (uint64_t)(fr / 2) / 64;               // ~52 bytes of scratch per hit, half of what is free
+        if (getenv("NB_MAP_HITS")) hit_budget = strtoull(getenv("NB_MAP_HITS"), NULL, 10);      // (tests)
+        if (hit_budget < 1024) hit_budget = 1024;
+    }
+    std::vector<nb_candidate> acc;
+    std::vector<std::pair<uint64_t, uint64_t>> todo;        // stack of read ranges, lowest reads on top
+    {
+        std::vector<std::pair<uint64_t, uint64_t>> fwd;
+        const int k = opt->kmer_size, z = opt->scan_window;
+        uint64_t lo = read_lo, np = 0;
+        for (uint64_t r = read_lo; r < read_hi; ++r) {
+            const uint32_t L = reads->h_len[r];
+            const uint64_t n = L >= (uint32_t)k ? 2ull * ((L - k) / z + 1) : 0;
+            if (np + n > kProbeChunk && r > lo) { fwd.push_back({lo, r}); lo = r; np = 0; }
+            np += n;
+        }
+        if (lo < read_hi) fwd.push_back({lo, read_hi});
+        todo.assign(fwd.rbegin(), fwd.rend());
+    }
+    while (!todo.empty()) {
+        const auto rg = todo.back();
+        todo.pop_back();
+        bool too_big = false;
+        const int rc = nb_map_range(ctx, idx, ref, ref_start_id, reads, read_start_id, rg.first, rg.second, opt, hit_budget, acc, &too_big);
+        if (rc) return rc;
+        if (too_big) {
+            const uint64_t mid = rg.first + (rg.second - rg.first) / 2;
+            todo.push_back({mid, rg.second});
+            todo.push_back({rg.first, mid});
+        }
+    }
+    nb_candidate* res = (nb_candidate*)malloc(sizeof(nb_candidate) * (acc.size() ? acc.size() : 1));
+    if (!res) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    if (!acc.empty()) memcpy(res, acc.data(), sizeof(nb_candidate) * acc.size());
     *out = res;
-    *n_out = nres;
-    ctx->mc.n_units = U; ctx->mc.n_probes = np; ctx->mc.n_hits = H; ctx->mc.n_seeds = cnts[1];
-    ctx->mc.n_blocks = cnts[2]; ctx->mc.n_eligible = cnts[3]; ctx->mc.n_candidates = nres; ctx->mc.query_bases = qbases * 2;
+    *n_out = acc.size();
     return NB_OK;
 }

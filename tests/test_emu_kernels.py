@@ -135,3 +135,32 @@ def test_results_do_not_depend_on_lane_order(emu, tmp_path, order):
     util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", "0", wrk, cand, str(tmp_path / "o_cns.fa"), str(tmp_path / "o_raw.fa")])
     assert util.fasta_canon(str(tmp_path / "g_cns.fa")) == util.fasta_canon(str(tmp_path / "o_cns.fa"))
     assert util.fasta_canon(str(tmp_path / "g_raw.fa")) == util.fasta_canon(str(tmp_path / "o_raw.fa"))
+
+
+def test_small_memory_mode_matches_reference(emu, tmp_path):
+    """oc2cns -s 1 against the reference binary (consensus/main.c:66, consensus_one_read.c:249-255,
+    consensus_one_partition.c:173): no dump of the uncorrected reads of the id range."""
+    if not util.ref_bin("oc2cns"):
+        pytest.skip("oracle/_ref is not built")
+    wrk, _ = util.make_workdir(tmp_path, genome=8000, depth=12, seed=86, err=0.10)
+    cand = str(tmp_path / "o.bin")
+    util.run_pmov(util.ORACLE_CLI, PM11, wrk, 0, cand)
+    cns = "-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0 -r 0 -f 0 -s 1"
+    for tag, bins in (("g", EMU_BIN), ("r", util.REF_DIR)):
+        c = str(tmp_path / f"{tag}.bin")
+        shutil.copy(cand, c)
+        util.run([os.path.join(bins, "oc2pcan"), "-t", "1", wrk, c])
+        util.run([os.path.join(bins, "oc2cns")] + cns.split() + ["-t", "1", wrk, c, str(tmp_path / f"{tag}_cns.fa"), str(tmp_path / f"{tag}_raw.fa")])
+    assert len(util.fasta_canon(str(tmp_path / "r_cns.fa"))) >= 5
+    assert util.fasta_canon(str(tmp_path / "g_cns.fa")) == util.fasta_canon(str(tmp_path / "r_cns.fa"))
+    assert util.fasta_canon(str(tmp_path / "g_raw.fa")) == util.fasta_canon(str(tmp_path / "r_raw.fa"))
+
+
+def test_mapping_in_pieces(emu, tmp_path):
+    """nb_map_volume cuts the read range by probe count and halves a piece whose seed hits exceed the scratch budget."""
+    wrk, _ = util.make_workdir(tmp_path, genome=8000, depth=12, seed=87, err=0.10)
+    o = util.run_pmov(util.ORACLE_CLI, PM11, wrk, 0, str(tmp_path / "o.bin"))
+    from necat_b200 import formats
+    for env in ({"NB_MAP_PROBES": "3000"}, {"NB_MAP_HITS": "1500"}, {"NB_MAP_PROBES": "5000", "NB_MAP_HITS": "1100"}):
+        util.run([emu("oc2pmov")] + PM11.split() + [wrk, "0", str(tmp_path / "g.bin")], env=dict(os.environ, **env))
+        assert o.shape[0] > 30 and util.same_multiset(formats.read_candidates(str(tmp_path / "g.bin")), o), env
