@@ -7,9 +7,10 @@ A "step" is one full pass over the read set: k-mer index build, candidate findin
 candidate regrouping, extension + consensus.  `value` = corrected bases per second
 with the packed reads already resident in HBM; `e2e` = the same through the C-ABI
 with host buffers (volume upload included; candidates and FASTA records always come
-back to the host).  One process per GPU; N > 1 shards the query reads for the mapping
-half, exchanges the 28-byte candidate records with an NCCL all-gather, and shards
-the templates (id mod N) for the correction half.
+back to the host).  One process per GPU; N > 1 (necat_b200/pipeline.py): the index is built
+in N shards of the hash space and all-gathered over NCCL, the query reads are split for
+the mapping half, the 28-byte candidate records go through an all-to-all-v, and the
+templates of the one partition are corrected id mod N.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 """
@@ -36,6 +37,12 @@ CNS_OPTS = dict(min_align_size=2000, min_cov=4, max_cov=12, min_size=1000, full_
 PM_STR = "-k 15 -z 10 -q 500 -b 2000 -s 3 -n 500 -a 1000 -d 0.25 -e 0.5 -m 500 -j 0 -u 1 -i 1"
 CNS_STR = "-a 2000 -x 4 -y 12 -l 1000 -e 0.5 -p 0.8 -u 0 -r 0 -f 0"
 SEED = 20260925
+
+
+def workload_name(args):
+    """One string for both arms (the driver compares the two lines' config)."""
+    return (f"E. coli-size {args.genome / 1e6:.1f} Mb x {args.depth:g} synthetic ONT reads (15% error, seed {SEED}), "
+            "one correction iteration: oc2pmov SENSITIVE (-j 0) -> oc2pcan -> oc2cns -r 0 -f 0")
 
 
 def make_reads(genome, depth):
@@ -120,6 +127,42 @@ def run_reference(genome, depth, threads, td, reads=None):
     return t
 
 
+def exe_parity(td, threads, ref):
+    """Runs necat_b200/bin/{oc2pmov,oc2pcan,oc2cns} on td/vol (where run_reference left the reference's outputs) and
+    compares.  -> (parity dict, e2e_exe dict)"""
+    from necat_b200 import formats
+    import shutil
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    B = os.path.join(ROOT, "necat_b200", "bin")
+    wrk = os.path.join(td, "vol")
+    cand = os.path.join(td, "g_cand.bin")
+    t0 = time.perf_counter()
+    subprocess.run([os.path.join(B, "oc2pmov")] + PM_STR.split() + ["-t", str(threads), wrk, "0", cand], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t1 = time.perf_counter()
+    part = cand + ".part"
+    shutil.copy(cand, part)
+    subprocess.run([os.path.join(B, "oc2pcan"), "-t", str(threads), wrk, part], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t2 = time.perf_counter()
+    subprocess.run([os.path.join(B, "oc2cns")] + CNS_STR.split() + ["-t", str(threads), wrk, part, os.path.join(td, "g_cns.fasta"),
+                   os.path.join(td, "g_raw.fasta")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t3 = time.perf_counter()
+    gc, rc = formats.read_candidates(cand), formats.read_candidates(os.path.join(td, "cns_candidates.txt"))
+    g_cns, r_cns = util.fasta_canon(os.path.join(td, "g_cns.fasta")), util.fasta_canon(os.path.join(td, "cns.fasta"))
+    parity = {"candidates": bool(util.same_multiset(gc, rc)), "cns": g_cns == r_cns,
+              "raw": util.fasta_canon(os.path.join(td, "g_raw.fasta")) == util.fasta_canon(os.path.join(td, "raw.fasta")),
+              "n_candidates": int(gc.shape[0]), "cns_records": len(g_cns),
+              "against": "the unmodified reference binaries (oracle/_ref) on the same work directory, canonical order, off the clock"}
+    wall = t3 - t0
+    bases = sum(len(x) for _, x in g_cns)
+    e2e_exe = {"value": bases / wall, "unit": "bases/s", "ms_per_step": wall * 1e3,
+               "stage_s": {"oc2pmov": t1 - t0, "oc2pcan": t2 - t1, "oc2cns": t3 - t2},
+               "what": "the three drop-in executables as necat.pl runs them (cold processes, files in and out)",
+               "speedup_vs_reference_executables": ref["total_s"] / wall}
+    return parity, e2e_exe
+
+
 def reference_sample_genome(args, threads):
     """Genome size the reference binaries are timed on: the full workload when the host can finish it in
     about a minute per pass (>= 12 threads: ~40 s on 16 and on 128), else a bounded sample.  The reference pays
@@ -163,10 +206,9 @@ def reference_arm(args, rank):
               f"{warm} warm-up pass(es) and {len(times)} of {args.steps} timed pass(es) executed (time budget {budget_s:.0f} s)")
     print(json.dumps({
         "impl": "reference", "metric": "corrected_bases_per_sec", "value": val, "unit": "bases/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"E. coli-size {args.genome / 1e6:.1f} Mb x {args.depth:g} synthetic ONT reads, one correction iteration "
-                               "(oc2pmov SENSITIVE -> oc2pcan -> oc2cns -r 0 -f 0)", "bounded_sample": sample},
+        "steps": len(times), "steps_requested": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "bounded_sample": sample},
         "overlaps_per_sec": last["n_candidates"] / sec,
         "stage_s": {k: last[k] for k in ("pmov_s", "pmov_mapping_s", "pcan_s", "cns_s") if k in last},
         "cpu_baseline": {"value": val, "unit": "bases/s", "cores": threads, "kind": "reference", "sample": sample},
@@ -196,8 +238,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from necat_b200 import capi, formats
-    from necat_b200 import dist as nbdist
+    from necat_b200 import capi, formats, pipeline
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -218,7 +259,6 @@ def main():
     ctx = capi.Context(local_rank)
     popt = capi.default_map_options(**PM_OPTS)
     copt = capi.default_cns_options(**CNS_OPTS)
-    lo, hi = nbdist.shard_range(nreads, rank, world)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
@@ -230,33 +270,21 @@ def main():
     stats = {}
 
     def one_step(dvol):
-        """index -> candidates -> exchange -> regroup -> correct.  Returns corrected bases of this rank."""
+        """index -> candidates -> exchange -> regroup -> correct (necat_b200/pipeline.py: the index of the one volume is
+        built in `world` shards of the hash space and all-gathered, the query reads are split over the ranks, the records
+        go through the all-to-all-v, the one partition is shared by all ranks).  Returns corrected bases of this rank."""
+        st = {}
         w0 = time.perf_counter()
-        idx = ctx.build_index(dvol, PM_OPTS["kmer_size"], PM_OPTS["kmer_cnt_cutoff"])
-        t = ctx.timings(); stats["index_ms"] = t.index_ms
-        w1 = time.perf_counter()
-        cands = ctx.map_volume(idx, dvol, 0, dvol, 0, lo, hi, popt)
-        w2 = time.perf_counter()
-        t = ctx.timings(); stats["map_ms"] = t.map_ms; stats["map_probe_ms"] = t.map_probe_ms
-        mc = ctx.map_counters()
-        stats["map_counters"] = {k: int(getattr(mc, k)) for k, _ in mc._fields_}
-        ctx.free_index(idx)
-        packed = capi.pack_candidates(cands)
-        # the one exchange step (SURVEY 8e): every rank needs the candidates of all query shards
-        packed = nbdist.all_gather_records(packed, dev, world)
-        stats["n_candidates"] = int(packed.shape[0])
-        # oc2pcan: every record under its subject and (swapped) under its query; one partition (< 100000 reads)
-        part = np.concatenate([packed, formats.swap_roles(packed)])
-        w3 = time.perf_counter()
-        recs, seq = ctx.consensus_job(dvol, part, copt, world, rank)
-        w4 = time.perf_counter()
-        stats["wall_ms"] = {"index_call": (w1 - w0) * 1e3, "map_call": (w2 - w1) * 1e3, "exchange_regroup": (w3 - w2) * 1e3,
-                            "consensus_call": (w4 - w3) * 1e3}
-        t = ctx.timings(); stats["extend_ms"] = t.extend_ms; stats["consensus_ms"] = t.consensus_ms
-        cc = ctx.cns_counters()
-        stats["cns_counters"] = {k: int(getattr(cc, k)) for k, _ in cc._fields_}
-        seq.free()
-        return int(recs["seq_len"][recs["is_raw"] == 0].sum())
+        res = pipeline.correct_iteration(ctx, [vol], popt, copt, rank, world, dev, part_size=pipeline.PART_SIZE, stats=st,
+                                         dvols={0: dvol}, dmerged=dvol)
+        bases = 0
+        for recs, seq in res:
+            bases += int(recs["seq_len"][recs["is_raw"] == 0].sum())
+            seq.free()
+        stats.update(st)
+        stats["wall_ms"] = {"index_call": st["wall_index_ms"], "map_call": st["wall_map_ms"], "exchange_regroup": st["wall_exchange_ms"],
+                            "consensus_call": st["wall_consensus_ms"], "step": (time.perf_counter() - w0) * 1e3}
+        return bases
 
     def timed(n_steps, upload_each):
         dvol = None if upload_each else ctx.upload(vol)
@@ -313,6 +341,11 @@ def main():
         del os.environ["NB_CNS_GROUPS"]
     else:
         os.environ["NB_CNS_GROUPS"] = keep
+    # candidates found by all ranks (off the clock)
+    nc = torch.tensor([stats["n_candidates_local"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(nc, op=dist.ReduceOp.SUM)
+    stats["n_candidates"] = int(nc.item())
     if rank != 0:
         return
     sec = dt / args.steps
@@ -323,29 +356,44 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     cc, mc = stats["cns_counters"], stats["map_counters"]
-    # dominant kernel = the extension kernel k_extend.  The roofline describes its largest launch (round 0
-    # of the extensions, one template group: the extra pass above): algorithmic bytes of that launch = walk-back state
-    # written once (8 B per 32-row word per DP column) + packed bases of every block (0.25 B per base, ~2 x 512 per
-    # block) + one op byte per alignment column (~1.2 x 512 per block), divided by the launch's duration (CUDA events
-    # on the library's stream, around the kernel alone).
-    ext_bytes = cc["big_ext_word_updates"] * 8 + cc["big_ext_block_aligns"] * (0.25 * 1024 + 620)
+    # Dominant kernel = the extension kernel k_extend.  The roofline describes its largest launch (round 0 of
+    # the extensions, one template group: the extra pass above).  Algorithmic bytes of that launch: per DP column the
+    # band of (Pv, Ph) words the walk-back needs, written once by the forward pass and read once by the walk (4 words x
+    # 8 B each way; the last block of a side keeps 8 words) + the packed bases of every block (0.25 B per base, ~2 x 512
+    # per block) + the op bytes of its columns (written to the block's buffer, read, written to the alignment:
+    # 3 x ~620 B per block).  Divided by the launch's duration (CUDA events on the library's stream, around the kernel
+    # alone).  The kernel is bound by instruction issue, not by HBM ("work, not bytes, is the natural
+    # unit"): word-updates per second are reported beside the bytes.
+    ext_bytes = cc["big_ext_dp_columns"] * 64 + cc["big_ext_block_aligns"] * (0.25 * 1024 + 3 * 620)
     ext_s = cc["big_ext_usec"] * 1e-6
     ext_gbs = ext_bytes / ext_s / 1e9 if ext_s else 0.0
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        if tj.get("word_updates") and cc["big_ext_word_updates"]:
-            # DRAM bytes of the same launch under ncu --set full, scaled by the launch's word-updates
-            traffic = tj["dram_bytes"] * cc["big_ext_word_updates"] / tj["word_updates"]
-            traffic_src = tj.get("source")
+    tpath = os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")
+    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    if tj.get("k_extend", {}).get("dp_columns") and cc["big_ext_dp_columns"]:
+        # DRAM bytes of the same launch under ncu --set full, scaled by the launch's DP columns
+        traffic = tj["k_extend"]["dram_bytes"] * cc["big_ext_dp_columns"] / tj["k_extend"]["dp_columns"]
+        traffic_src = tj["k_extend"].get("source")
+    # The kernel north_star names: seed probe + vote (k_probe + k_build_blocks).  Algorithmic bytes (with this
+    # repo's 4-byte CSR entries): the packed reads once per strand + 8 B of row pointers per probe + 4 B per hit + 12 B
+    # per kept seed; DRAM traffic of the two kernels from the ncu capture (random 8-byte gathers fetch whole sectors).
+    sv_bytes = mc["query_bases"] * 0.25 + mc["n_probes"] * 8 + mc["n_hits"] * 4 + mc["n_seeds"] * 12
+    sv_s = stats["map_probe_ms"] * 1e-3
+    sv = {"kernel": "k_probe + k_build_blocks", "bound": "hbm", "achieved": sv_bytes / sv_s / 1e9 if sv_s else 0.0, "peak": peak, "unit": "GB/s",
+          "algorithmic_bytes": sv_bytes, "ms": stats["map_probe_ms"], "traffic": None}
+    sv["frac"] = sv["achieved"] / peak
+    if tj.get("seed_vote", {}).get("n_probes") and mc["n_probes"]:
+        sv["traffic"] = tj["seed_vote"]["dram_bytes"] * mc["n_probes"] / tj["seed_vote"]["n_probes"]
+        sv["traffic_source"] = tj["seed_vote"].get("source")
+        sv["dram_frac_of_peak"] = sv["traffic"] / sv_s / 1e9 / peak if sv_s else None
     out = {
         "metric": "corrected_bases_per_sec", "value": bases / sec, "unit": "bases/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"E. coli-size {args.genome / 1e6:.1f} Mb x {args.depth:g} synthetic ONT reads (15% error, seed {SEED}), "
-                               "one correction iteration: oc2pmov SENSITIVE (-j 0) -> oc2pcan -> oc2cns -r 0 -f 0",
-                   "reads": int(nreads), "bases": int(vol.db_size), "parallelism": f"reads/templates sharded x{world}",
+        "config": {"workload": workload_name(args),
+                   "reads": int(nreads), "bases": int(vol.db_size),
+                   "parallelism": f"x{world}: index built in {world} shards of the hash space + NCCL all-gather, query reads split, "
+                                  "all-to-all-v of the 28-byte records, templates of the one partition id mod N",
                    "l2": "512 MB flush write between iterations; index (4 GiB table) and DP scratch exceed L2"},
         "overlaps_per_sec": stats["n_candidates"] / sec,
         "corrected_bases": bases, "candidates": stats["n_candidates"],
@@ -362,9 +410,10 @@ def main():
         "roofline": {"kernel": "k_extend", "bound": "hbm", "achieved": ext_gbs, "peak": peak, "unit": "GB/s",
                      "frac": ext_gbs / peak, "frac_of_nominal_8TBs": ext_gbs / 8000.0, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "launch": {"what": "largest k_extend launch (round 0, one template group)", "ms": cc["big_ext_usec"] / 1e3,
-                                "tasks": cc["big_ext_tasks"], "block_alignments": cc["big_ext_block_aligns"],
+                                "tasks": cc["big_ext_tasks"], "block_alignments": cc["big_ext_block_aligns"], "dp_columns": cc["big_ext_dp_columns"],
                                 "word_updates": cc["big_ext_word_updates"], "algorithmic_bytes": ext_bytes},
                      "word_updates_per_s": cc["big_ext_word_updates"] / ext_s if ext_s else 0.0},
+        "roofline_seed_vote": sv,
         "counters": {"map": mc, "cns": cc},
     }
     if not args.no_cpu_baseline:
@@ -373,10 +422,14 @@ def main():
             sg = reference_sample_genome(args, threads)
             with tempfile.TemporaryDirectory() as td:
                 r = run_reference(sg, args.depth, threads, td, reads=reads if sg == args.genome else None)
-            out["cpu_baseline"] = {"value": r["cns_bases"] / r["total_s"], "unit": "bases/s", "cores": threads, "kind": "reference",
-                                   "sample": f"{sg / 1e6:.2f} Mb genome x {args.depth:g} ({'the full workload' if sg == args.genome else 'bounded sample'}), same generator; "
-                                             f"oc2pmov {r['pmov_s']:.1f}s (mapping {r.get('pmov_mapping_s', 0):.2f}s) + oc2pcan "
-                                             f"{r['pcan_s']:.2f}s + oc2cns {r['cns_s']:.1f}s"}
+                out["cpu_baseline"] = {"value": r["cns_bases"] / r["total_s"], "unit": "bases/s", "cores": threads, "kind": "reference",
+                                       "sample": f"{sg / 1e6:.2f} Mb genome x {args.depth:g} ({'the full workload' if sg == args.genome else 'bounded sample'}), same generator; "
+                                                 f"oc2pmov {r['pmov_s']:.1f}s (mapping {r.get('pmov_mapping_s', 0):.2f}s) + oc2pcan "
+                                                 f"{r['pcan_s']:.2f}s + oc2cns {r['cns_s']:.1f}s"}
+                # Off the clock: this repo's drop-in executables on the SAME work directory, outputs compared with the
+                # reference's in canonical order, and their wall clock as necat.pl would see it (cold
+                # processes: CUDA context creation included).
+                out["parity"], out["e2e_exe"] = exe_parity(td, threads, r)
         else:
             out["cpu_baseline"] = {"value": None, "unit": "bases/s", "cores": threads, "kind": "reference",
                                    "sample": "oracle/_ref missing"}

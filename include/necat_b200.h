@@ -84,6 +84,20 @@ void nb_index_free(nb_ctx* ctx, nb_index* idx);
 int  nb_index_stats(nb_ctx* ctx, const nb_index* idx, uint64_t* n_offsets, uint64_t* n_distinct);
 int  nb_index_download(nb_ctx* ctx, const nb_index* idx, uint32_t* starts, uint32_t* offsets);
 
+/*
+ * The index of one volume built by several GPUs together (multi-GPU form of build_lookup_table,
+ * lookup_table/lookup_table.c:149-164): GPU number `shard` of `nshards` builds the CSR of the shard-th
+ * slice of ceil(4^k / nshards) hash values; nb_index_shard_export writes its starts (plus `base`, the number of
+ * positions of the slices before it) and positions into the device arrays the GPUs assemble -- the caller all-gathers
+ * those (NCCL) and wraps the result with nb_index_adopt, which does not take ownership of the arrays.
+ */
+typedef struct nb_index_shard nb_index_shard;
+int  nb_index_build_shard(nb_ctx* ctx, const nb_volume* ref, int k, int q, int shard, int nshards,
+                          nb_index_shard** out, uint64_t* n_offsets, uint64_t* n_distinct);
+int  nb_index_shard_export(nb_ctx* ctx, nb_index_shard* shard, uint64_t base, uint32_t* d_tbl_dst, uint32_t* d_off_dst);
+int  nb_index_adopt(nb_ctx* ctx, int k, int q, uint32_t* d_tbl, uint32_t* d_off, uint64_t n_offsets, uint64_t n_distinct,
+                    nb_index** out);
+
 /* --------------------------------------------------------------- candidates */
 /* common/map_options.h:10-25 (same meaning, same defaults via nb_map_options_default) */
 typedef struct {
@@ -249,7 +263,7 @@ typedef struct {
     uint64_t n_templates, n_extensions, n_block_aligns, n_dp_columns, n_dp_word_updates;
     uint64_t n_accepted, n_tags, n_cns_records, cns_bases;
     /* the largest k_extend launch of the job (the roofline of bench.py describes this launch) */
-    uint64_t big_ext_tasks, big_ext_block_aligns, big_ext_word_updates, big_ext_usec;
+    uint64_t big_ext_tasks, big_ext_block_aligns, big_ext_word_updates, big_ext_usec, big_ext_dp_columns;
 } nb_cns_counters;
 void nb_get_cns_counters(const nb_ctx* ctx, nb_cns_counters* out);
 

@@ -38,7 +38,7 @@ class MapCounters(C.Structure):
 class CnsCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_templates", "n_extensions", "n_block_aligns", "n_dp_columns",
                                           "n_dp_word_updates", "n_accepted", "n_tags", "n_cns_records", "cns_bases",
-                                          "big_ext_tasks", "big_ext_block_aligns", "big_ext_word_updates", "big_ext_usec")]
+                                          "big_ext_tasks", "big_ext_block_aligns", "big_ext_word_updates", "big_ext_usec", "big_ext_dp_columns")]
 
 
 CANDIDATE = np.dtype([("qid", "<i4"), ("sid", "<i4"), ("qdir", "<i4"), ("sdir", "<i4"), ("score", "<i4"),
@@ -52,7 +52,7 @@ CNS_RECORD = np.dtype([("id", "<i4"), ("left", "<i4"), ("right", "<i4"), ("org_s
 
 EXPORTS = ["nb_ctx_create", "nb_ctx_destroy", "nb_last_error", "nb_version", "nb_launch_count", "nb_get_timings",
            "nb_volume_upload", "nb_volume_free", "nb_index_build", "nb_index_free", "nb_index_stats",
-           "nb_index_download", "nb_map_options_default", "nb_map_volume", "nb_map_volume_aln", "nb_pack_candidate", "nb_free",
+           "nb_index_download", "nb_index_build_shard", "nb_index_shard_export", "nb_index_adopt", "nb_map_options_default", "nb_map_volume", "nb_map_volume_aln", "nb_pack_candidate", "nb_free",
            "nb_get_map_counters", "nb_cns_options_default", "nb_extend_candidates", "nb_consensus_job",
            "nb_consensus_job_sharded",
            "nb_get_cns_counters", "nb_rescue_local", "nb_rescue_global"]
@@ -150,6 +150,50 @@ class Context:
 
     def free_index(self, h):
         self.L.nb_index_free(self.h, h)
+        self._index_keep.pop(h.value, None)
+
+    _index_keep = {}        # torch tensors that back an assembled index stay alive with its handle
+
+    def build_index_sharded(self, dvol, k, q, group_ranks, rank, device, group=None):
+        """The index of one volume built ONCE by the ranks of `group_ranks` together: rank number s of them builds the
+        CSR of the s-th slice of the hash space (nb_index_build_shard), the slices are all-gathered over NCCL into a
+        table every rank holds (lookup_table.c:149-164 builds it serially on one host)."""
+        import torch
+        import torch.distributed as dist
+        n = len(group_ranks)
+        s = group_ranks.index(rank)
+        sh = C.c_void_p(); n_off = C.c_uint64(); n_dist = C.c_uint64()
+        self._check(self.L.nb_index_build_shard(self.h, dvol, C.c_int(k), C.c_int(q), C.c_int(s), C.c_int(n),
+                                                C.byref(sh), C.byref(n_off), C.byref(n_dist)))
+        n_hash = 1 << (2 * k)
+        slice_len = (n_hash + n - 1) // n
+        cnt = torch.tensor([n_off.value, n_dist.value], dtype=torch.int64, device=device)
+        allc = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(n)]
+        dist.all_gather(allc, cnt, group=group)
+        offs_n = [int(c[0].item()) for c in allc]
+        total, distinct = sum(offs_n), sum(int(c[1].item()) for c in allc)
+        base = sum(offs_n[:s])
+        tbl = torch.empty(n * slice_len + 8, dtype=torch.int32, device=device)
+        offs = torch.empty(total + 16, dtype=torch.int32, device=device)
+        width = max(max(offs_n), 1)
+        mine = torch.zeros(width, dtype=torch.int32, device=device)
+        self._check(self.L.nb_index_shard_export(self.h, sh, C.c_uint64(base), C.c_void_p(tbl.data_ptr() + 4 * s * slice_len),
+                                                 C.c_void_p(mine.data_ptr())))
+        torch.cuda.synchronize(device)
+        dist.all_gather_into_tensor(tbl[:n * slice_len], tbl[s * slice_len:(s + 1) * slice_len], group=group)
+        bufs = [torch.empty(width, dtype=torch.int32, device=device) for _ in range(n)]
+        dist.all_gather(bufs, mine, group=group)
+        pos = 0
+        for b, c in zip(bufs, offs_n):
+            offs[pos:pos + c] = b[:c]
+            pos += c
+        tbl[n_hash] = total if total < 2 ** 31 else total - 2 ** 32
+        torch.cuda.synchronize(device)
+        h = C.c_void_p()
+        self._check(self.L.nb_index_adopt(self.h, C.c_int(k), C.c_int(q), C.c_void_p(tbl.data_ptr()), C.c_void_p(offs.data_ptr()),
+                                          C.c_uint64(total), C.c_uint64(distinct), C.byref(h)))
+        self._index_keep[h.value] = (tbl, offs)
+        return h
 
     def index_arrays(self, idx, k):
         n_off, n_dist = C.c_uint64(), C.c_uint64()

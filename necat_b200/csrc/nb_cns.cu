@@ -817,7 +817,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         ctx->cc.n_accepted += wc->cc.n_accepted; ctx->cc.n_tags += wc->cc.n_tags; ctx->cc.cns_bases += wc->cc.cns_bases;
         if (wc->cc.big_ext_word_updates > ctx->cc.big_ext_word_updates) {
             ctx->cc.big_ext_tasks = wc->cc.big_ext_tasks; ctx->cc.big_ext_block_aligns = wc->cc.big_ext_block_aligns;
-            ctx->cc.big_ext_word_updates = wc->cc.big_ext_word_updates; ctx->cc.big_ext_usec = wc->cc.big_ext_usec;
+            ctx->cc.big_ext_word_updates = wc->cc.big_ext_word_updates; ctx->cc.big_ext_usec = wc->cc.big_ext_usec; ctx->cc.big_ext_dp_columns = wc->cc.big_ext_dp_columns;
         }
         memset(&wc->cc, 0, sizeof wc->cc); memset(&wc->tm, 0, sizeof wc->tm);
     };

@@ -59,6 +59,7 @@ struct nb_index {
     uint32_t* d_off;        // [n_off] positions, ascending inside a run
     uint64_t  n_off;
     uint64_t  n_distinct;
+    int       external;     // 1: d_tbl / d_off belong to the caller (nb_index_adopt)
 };
 
 extern char g_nb_err[512];

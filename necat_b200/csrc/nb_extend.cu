@@ -628,7 +628,7 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     if (cnt[2] > ctx->cc.big_ext_word_updates) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
-        ctx->cc.big_ext_tasks = n_tasks; ctx->cc.big_ext_block_aligns = cnt[0]; ctx->cc.big_ext_word_updates = cnt[2];
+        ctx->cc.big_ext_tasks = n_tasks; ctx->cc.big_ext_block_aligns = cnt[0]; ctx->cc.big_ext_word_updates = cnt[2]; ctx->cc.big_ext_dp_columns = cnt[1];
         ctx->cc.big_ext_usec = (uint64_t)(ms * 1000.0f);
     }
     return NB_OK;

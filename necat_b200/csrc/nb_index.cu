@@ -30,7 +30,7 @@ __global__ void k_mark_invalid(const uint64_t* __restrict__ off, const uint32_t*
 template <bool FILL>
 __global__ void __launch_bounds__(IDX_THREADS)
 k_scan_kmers(const uint32_t* __restrict__ words, uint64_t db_size, const uint32_t* __restrict__ invalid, int k,
-             uint32_t* __restrict__ cnt, uint32_t* __restrict__ tbl, uint32_t* __restrict__ offs)
+             uint32_t* __restrict__ cnt, uint32_t* __restrict__ tbl, uint32_t* __restrict__ offs, uint32_t h_lo, uint32_t h_n)
 {
     const uint64_t nchunk = (db_size + 15) >> 4;
     const uint32_t mask = (uint32_t)((1ull << (2 * k)) - 1);
@@ -42,7 +42,8 @@ k_scan_kmers(const uint32_t* __restrict__ words, uint64_t db_size, const uint32_
         for (int i = 0; i < 16; ++i) {
             if ((bad >> i) & 1) continue;
             if (p0 + i >= db_size) continue;
-            uint32_t h = (uint32_t)(v >> (64 - 2 * i - 2 * k)) & mask;
+            uint32_t h = ((uint32_t)(v >> (64 - 2 * i - 2 * k)) & mask) - h_lo;      // inside this build's slice of the hash space?
+            if (h >= h_n) continue;
             if (!FILL) {
                 atomicAdd(cnt + h, 1u);                 // RED.ADD, result unused
             } else if (__ldg(cnt + h)) {
@@ -241,28 +242,21 @@ k_sort_long_runs(const uint32_t* __restrict__ tbl, uint32_t* __restrict__ offs, 
     }
 }
 
-extern "C" int nb_index_build(nb_ctx* ctx, const nb_volume* ref, int k, int q, nb_index** out)
+// CSR of the hash values [h_lo, h_lo + h_n) of the volume: d_tbl[h_n + 1] (starts from 0), d_off.
+static int index_build_range(nb_ctx* ctx, const nb_volume* ref, int k, int q, uint64_t h_lo, uint64_t h_n,
+                             uint32_t** out_tbl, uint32_t** out_off, uint64_t* out_n_off, uint64_t* out_n_distinct)
 {
-    if (!ctx || !ref || !out) return nb_fail(ctx, NB_EINVAL, "nb_index_build: bad arguments");
-    if (k < 4 || k > 15) return nb_fail(ctx, NB_ELIMIT, "kmer size %d unsupported (4..15; reference HashBits = 30)", k);
-    if (q < 1) return nb_fail(ctx, NB_EINVAL, "kmer count cutoff must be >= 1");
-    if (ref->db_size >= (1ull << 32)) return nb_fail(ctx, NB_ELIMIT, "a volume of %llu bases cannot be indexed: index positions are 32-bit (oc2mkdb cuts volumes at 2 Gbp)", (unsigned long long)ref->db_size);
-    NB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    nb_index* ix = (nb_index*)calloc(1, sizeof(nb_index));
-    if (!ix) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
-    ix->k = k; ix->q = q; ix->n_hash = 1ull << (2 * k);
-    const uint64_t nh = ix->n_hash;
+    const uint64_t nh = h_n;
     const uint32_t ntiles = (uint32_t)((nh + SCAN_TILE - 1) / SCAN_TILE);
-    uint32_t *d_cnt = NULL, *d_invalid = NULL, *d_tile = NULL, *d_tiled = NULL, *d_long = NULL, *d_nlong = NULL;
+    uint32_t *d_cnt = NULL, *d_invalid = NULL, *d_tile = NULL, *d_tiled = NULL, *d_long = NULL, *d_nlong = NULL, *d_tbl = NULL, *d_off = NULL;
     uint64_t* d_tot = NULL;
     const uint64_t inv_words = ((ref->db_size + 31) >> 5) + 2;
-    cudaEventRecord(ctx->ev0, st);
     NbDevBuf B(ctx);
     {
         int rc;
         if ((rc = B.get(&d_cnt, nh + 8))) return rc;
-        if ((rc = nb_dev_alloc(ctx, (void**)&ix->d_tbl, sizeof(uint32_t) * (nh + 8)))) return rc;
+        if ((rc = nb_dev_alloc(ctx, (void**)&d_tbl, sizeof(uint32_t) * (nh + 8)))) return rc;
         if ((rc = B.get(&d_invalid, inv_words))) return rc;
         if ((rc = B.get(&d_tile, ntiles))) return rc;
         if ((rc = B.get(&d_tiled, ntiles))) return rc;
@@ -282,38 +276,60 @@ extern "C" int nb_index_build(nb_ctx* ctx, const nb_volume* ref, int k, int q, n
         k_mark_invalid<<<(unsigned)((ref->nseq + 255) / 256), 256, 0, st>>>(ref->d_off, ref->d_len, ref->nseq, k, d_invalid);
         NB_LAUNCH_CHECK(ctx);
     }
-    k_scan_kmers<false><<<grid_scan, IDX_THREADS, 0, st>>>(words, ref->db_size, d_invalid, k, d_cnt, NULL, NULL);
+    k_scan_kmers<false><<<grid_scan, IDX_THREADS, 0, st>>>(words, ref->db_size, d_invalid, k, d_cnt, NULL, NULL, (uint32_t)h_lo, (uint32_t)h_n);
     NB_LAUNCH_CHECK(ctx);
     k_mask_reduce<<<ntiles, SCAN_THREADS, 0, st>>>(d_cnt, nh, (uint32_t)q, d_tile, d_tiled);
     NB_LAUNCH_CHECK(ctx);
     k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(d_tile, d_tiled, ntiles, d_tot);
     NB_LAUNCH_CHECK(ctx);
-    k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(d_cnt, nh, d_tile, ix->d_tbl);
+    k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(d_cnt, nh, d_tile, d_tbl);
     NB_LAUNCH_CHECK(ctx);
     uint64_t tot[2];
     NB_CUDA(ctx, cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
     NB_CUDA(ctx, cudaStreamSynchronize(st));
-    ix->n_off = tot[0];
-    ix->n_distinct = tot[1];
     {
         int rc;
-        if ((rc = nb_dev_alloc(ctx, (void**)&ix->d_off, sizeof(uint32_t) * (ix->n_off + 16)))) return rc;
-        if ((rc = B.get(&d_long, ix->n_off / LONG_RUN + 16))) return rc;
+        if ((rc = nb_dev_alloc(ctx, (void**)&d_off, sizeof(uint32_t) * (tot[0] + 16)))) return rc;
+        if ((rc = B.get(&d_long, tot[0] / LONG_RUN + 16))) return rc;
     }
-    k_scan_kmers<true><<<grid_scan, IDX_THREADS, 0, st>>>(words, ref->db_size, d_invalid, k, d_cnt, ix->d_tbl, ix->d_off);
+    k_scan_kmers<true><<<grid_scan, IDX_THREADS, 0, st>>>(words, ref->db_size, d_invalid, k, d_cnt, d_tbl, d_off, (uint32_t)h_lo, (uint32_t)h_n);
     NB_LAUNCH_CHECK(ctx);
     unsigned grid_h = (unsigned)((nh + IDX_THREADS - 1) / IDX_THREADS);
     if (grid_h > NB_SMS * 64) grid_h = NB_SMS * 64;
-    k_sort_short_runs<<<grid_h, IDX_THREADS, 0, st>>>(ix->d_tbl, nh, ix->d_off, d_long, d_nlong);
+    k_sort_short_runs<<<grid_h, IDX_THREADS, 0, st>>>(d_tbl, nh, d_off, d_long, d_nlong);
     NB_LAUNCH_CHECK(ctx);
     uint32_t n_long = 0;
     NB_CUDA(ctx, cudaMemcpyAsync(&n_long, d_nlong, sizeof n_long, cudaMemcpyDeviceToHost, st));
     NB_CUDA(ctx, cudaStreamSynchronize(st));
     if (n_long) {
         unsigned g = n_long < NB_SMS * 16 ? n_long : NB_SMS * 16;
-        k_sort_long_runs<<<g, 128, 0, st>>>(ix->d_tbl, ix->d_off, d_long, n_long);
+        k_sort_long_runs<<<g, 128, 0, st>>>(d_tbl, d_off, d_long, n_long);
         NB_LAUNCH_CHECK(ctx);
     }
+    *out_tbl = d_tbl; *out_off = d_off; *out_n_off = tot[0]; *out_n_distinct = tot[1];
+    return NB_OK;
+}
+
+static int index_check_args(nb_ctx* ctx, const nb_volume* ref, int k, int q)
+{
+    if (k < 4 || k > 15) return nb_fail(ctx, NB_ELIMIT, "kmer size %d unsupported (4..15; reference HashBits = 30)", k);
+    if (q < 1) return nb_fail(ctx, NB_EINVAL, "kmer count cutoff must be >= 1");
+    if (ref->db_size >= (1ull << 32)) return nb_fail(ctx, NB_ELIMIT, "a volume of %llu bases cannot be indexed: index positions are 32-bit (oc2mkdb cuts volumes at 2 Gbp)", (unsigned long long)ref->db_size);
+    return NB_OK;
+}
+
+extern "C" int nb_index_build(nb_ctx* ctx, const nb_volume* ref, int k, int q, nb_index** out)
+{
+    if (!ctx || !ref || !out) return nb_fail(ctx, NB_EINVAL, "nb_index_build: bad arguments");
+    { const int rc = index_check_args(ctx, ref, k, q); if (rc) return rc; }
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    nb_index* ix = (nb_index*)calloc(1, sizeof(nb_index));
+    if (!ix) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    ix->k = k; ix->q = q; ix->n_hash = 1ull << (2 * k);
+    cudaEventRecord(ctx->ev0, st);
+    const int rc = index_build_range(ctx, ref, k, q, 0, ix->n_hash, &ix->d_tbl, &ix->d_off, &ix->n_off, &ix->n_distinct);
+    if (rc) { free(ix); return rc; }
     cudaEventRecord(ctx->ev1, st);
     NB_CUDA(ctx, cudaStreamSynchronize(st));
     cudaEventElapsedTime(&ctx->tm.index_ms, ctx->ev0, ctx->ev1);
@@ -321,10 +337,80 @@ extern "C" int nb_index_build(nb_ctx* ctx, const nb_volume* ref, int k, int q, n
     return NB_OK;
 }
 
+// ---- the index of one volume built by several GPUs together: every GPU the CSR of one slice of the hash space
+struct nb_index_shard {
+    uint32_t* d_tbl;        // [h_n + 1] starts from 0
+    uint32_t* d_off;
+    uint64_t  h_n, n_off;
+};
+
+__global__ void k_shard_export(const uint32_t* __restrict__ tbl, uint64_t n, uint32_t base, uint32_t* __restrict__ dst)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = tbl[i] + base;
+}
+
+extern "C" int nb_index_build_shard(nb_ctx* ctx, const nb_volume* ref, int k, int q, int shard, int nshards,
+                                    nb_index_shard** out, uint64_t* n_offsets, uint64_t* n_distinct)
+{
+    if (!ctx || !ref || !out || !n_offsets || !n_distinct || nshards < 1 || shard < 0 || shard >= nshards)
+        return nb_fail(ctx, NB_EINVAL, "nb_index_build_shard: bad arguments");
+    { const int rc = index_check_args(ctx, ref, k, q); if (rc) return rc; }
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_hash = 1ull << (2 * k), slice = (n_hash + nshards - 1) / nshards;
+    const uint64_t h_lo = slice * (uint64_t)shard;
+    const uint64_t h_n = h_lo >= n_hash ? 0 : (h_lo + slice <= n_hash ? slice : n_hash - h_lo);
+    nb_index_shard* sh = (nb_index_shard*)calloc(1, sizeof(nb_index_shard));
+    if (!sh) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    sh->h_n = h_n;
+    cudaEventRecord(ctx->ev0, st);
+    uint64_t nd = 0;
+    const int rc = index_build_range(ctx, ref, k, q, h_lo, h_n, &sh->d_tbl, &sh->d_off, &sh->n_off, &nd);
+    if (rc) { free(sh); return rc; }
+    cudaEventRecord(ctx->ev1, st);
+    NB_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ctx->tm.index_ms, ctx->ev0, ctx->ev1);
+    *out = sh; *n_offsets = sh->n_off; *n_distinct = nd;
+    return NB_OK;
+}
+
+// Writes the shard into the table all GPUs assemble: starts + base into d_tbl_dst[0, h_n), positions into d_off_dst[0, n_off)
+// (both device pointers of the caller, e.g. torch tensors that NCCL all-gathers afterwards).  Frees the shard.
+extern "C" int nb_index_shard_export(nb_ctx* ctx, nb_index_shard* sh, uint64_t base, uint32_t* d_tbl_dst, uint32_t* d_off_dst)
+{
+    if (!ctx || !sh || !d_tbl_dst || !d_off_dst) return nb_fail(ctx, NB_EINVAL, "nb_index_shard_export: bad arguments");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (sh->h_n) {
+        unsigned g = (unsigned)((sh->h_n + 255) / 256);
+        if (g > NB_SMS * 32) g = NB_SMS * 32;
+        k_shard_export<<<g, 256, 0, st>>>(sh->d_tbl, sh->h_n, (uint32_t)base, d_tbl_dst);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    if (sh->n_off) NB_CUDA(ctx, cudaMemcpyAsync(d_off_dst, sh->d_off, sizeof(uint32_t) * sh->n_off, cudaMemcpyDeviceToDevice, st));
+    NB_CUDA(ctx, cudaStreamSynchronize(st));
+    nb_dev_release(ctx, sh->d_tbl); nb_dev_release(ctx, sh->d_off);
+    free(sh);
+    return NB_OK;
+}
+
+// An index over arrays the caller owns (and keeps alive until nb_index_free, which does not free them).
+extern "C" int nb_index_adopt(nb_ctx* ctx, int k, int q, uint32_t* d_tbl, uint32_t* d_off, uint64_t n_off, uint64_t n_distinct, nb_index** out)
+{
+    if (!ctx || !d_tbl || !d_off || !out || k < 4 || k > 15) return nb_fail(ctx, NB_EINVAL, "nb_index_adopt: bad arguments");
+    nb_index* ix = (nb_index*)calloc(1, sizeof(nb_index));
+    if (!ix) return nb_fail(ctx, NB_ENOMEM, "out of host memory");
+    ix->k = k; ix->q = q; ix->n_hash = 1ull << (2 * k); ix->d_tbl = d_tbl; ix->d_off = d_off; ix->n_off = n_off; ix->n_distinct = n_distinct;
+    ix->external = 1;
+    *out = ix;
+    return NB_OK;
+}
+
 extern "C" void nb_index_free(nb_ctx* ctx, nb_index* ix)
 {
     if (!ix) return;
-    if (ctx) { cudaSetDevice(ctx->device); nb_dev_release(ctx, ix->d_tbl); nb_dev_release(ctx, ix->d_off); }
+    if (ix->external) { }       // the arrays belong to the caller (nb_index_adopt)
+    else if (ctx) { cudaSetDevice(ctx->device); nb_dev_release(ctx, ix->d_tbl); nb_dev_release(ctx, ix->d_off); }
     else { cudaFree(ix->d_tbl); cudaFree(ix->d_off); }
     free(ix);
 }

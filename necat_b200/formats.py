@@ -183,3 +183,17 @@ def partition_records(rec, sizes, lo=0, hi=None):
     allr = np.concatenate([a, b])
     allr = allr[np.argsort(allr[:, 1], kind="stable")]
     return normalise_sdir(allr, sizes)
+
+
+def cns_fasta_records(recs, seq, names):
+    """(cns, raw) lists of (header, sequence) as oc2cns writes them (common/cns_seq.h:23-41) from the records of
+    nb_consensus_job: recs = CNS_RECORD array, seq = uint8 array of all sequences, names[id] = read name (bytes)."""
+    cns, raw = [], []
+    for r in recs:
+        name = names[int(r["id"])]
+        head = b">" + name + b"_" if name.startswith(b"ontsa_id") else b">ontsa_id_%d_" % int(r["id"])
+        head += b"(%d_%d_%d_%d_%d_%d_%f)" % (int(r["left"]), int(r["right"]), int(r["seq_len"]), int(r["org_size"]),
+                                               int(r["num_can"]), int(r["num_ovlps"]), float(r["ident_cutoff"]))
+        s = bytes(seq[int(r["seq_offset"]):int(r["seq_offset"]) + int(r["seq_len"])])
+        (raw if r["is_raw"] else cns).append((head, s))
+    return cns, raw

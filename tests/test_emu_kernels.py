@@ -164,3 +164,51 @@ def test_mapping_in_pieces(emu, tmp_path):
     for env in ({"NB_MAP_PROBES": "3000"}, {"NB_MAP_HITS": "1500"}, {"NB_MAP_PROBES": "5000", "NB_MAP_HITS": "1100"}):
         util.run([emu("oc2pmov")] + PM11.split() + [wrk, "0", str(tmp_path / "g.bin")], env=dict(os.environ, **env))
         assert o.shape[0] > 30 and util.same_multiset(formats.read_candidates(str(tmp_path / "g.bin")), o), env
+
+
+def test_sharded_index_build(emu, tmp_path):
+    """nb_index_build_shard / nb_index_shard_export / nb_index_adopt: three slices of the hash space assembled by hand
+    (on a GPU box the slices come from different ranks and are all-gathered over NCCL, necat_b200/capi.py) give the
+    arrays of nb_index_build, and the adopted index maps like it."""
+    wrk, _ = util.make_workdir(tmp_path, genome=6000, depth=10, seed=88, err=0.10)
+    code = r'''
+import sys, os, ctypes as C, numpy as np
+sys.path.insert(0, %(root)r)
+from necat_b200 import capi, formats
+capi.LIB_PATH = %(lib)r                      # test only: the emulated build (tests/emu), never the product's path
+vol = formats.read_volume(os.path.join(%(wrk)r, "vol0"))
+ctx = capi.Context(0)
+L = ctx.L
+dvol = ctx.upload(vol)
+k, q, n = 11, 100, 3
+idx = ctx.build_index(dvol, k, q)
+starts, offs, nd = ctx.index_arrays(idx, k)
+n_hash = 1 << (2 * k)
+slice_len = (n_hash + n - 1) // n
+tbl = np.zeros(n * slice_len + 8, np.uint32)
+shards, counts = [], []
+for s in range(n):
+    sh = C.c_void_p(); no = C.c_uint64(); dd = C.c_uint64()
+    assert L.nb_index_build_shard(ctx.h, dvol, C.c_int(k), C.c_int(q), C.c_int(s), C.c_int(n), C.byref(sh), C.byref(no), C.byref(dd)) == 0
+    shards.append(sh); counts.append((no.value, dd.value))
+total = sum(c[0] for c in counts)
+of = np.zeros(total + 16, np.uint32)
+base = 0
+for s in range(n):
+    assert L.nb_index_shard_export(ctx.h, shards[s], C.c_uint64(base), C.c_void_p(tbl.ctypes.data + 4 * s * slice_len), C.c_void_p(of.ctypes.data + 4 * base)) == 0
+    base += counts[s][0]
+tbl[n_hash] = total
+assert total == offs.size and sum(c[1] for c in counts) == nd
+assert np.array_equal(tbl[:n_hash + 1], starts) and np.array_equal(of[:total], offs)
+h = C.c_void_p()
+assert L.nb_index_adopt(ctx.h, C.c_int(k), C.c_int(q), C.c_void_p(tbl.ctypes.data), C.c_void_p(of.ctypes.data), C.c_uint64(total), C.c_uint64(nd), C.byref(h)) == 0
+popt = capi.default_map_options(kmer_size=11, scan_window=10, kmer_cnt_cutoff=100, block_size=2000, block_score_cutoff=3,
+                                num_candidates=500, align_size_cutoff=1000, ddfs_cutoff=0.25, error=0.5, num_output=500)
+a = capi.pack_candidates(ctx.map_volume(idx, dvol, 0, dvol, 0, 0, vol.nseq, popt))
+b = capi.pack_candidates(ctx.map_volume(h, dvol, 0, dvol, 0, 0, vol.nseq, popt))
+assert a.shape[0] > 10 and formats.canonical_records(a).tobytes() == formats.canonical_records(b).tobytes()
+ctx.free_index(h); ctx.free_index(idx)
+print("OK", total, a.shape[0])
+''' % dict(root=util.ROOT, lib=os.path.join(EMU_DIR, "_build", "cudaemu", "lib", "libnecat_b200.so"), wrk=wrk)
+    p = util.run(["python", "-c", code])
+    assert p.stdout.startswith(b"OK")
