@@ -301,6 +301,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         std::vector<const uint8_t*> res_ops;    // device pointer of each result's ops
         ChunkTimes tm;
         int rc = NB_OK;
+        std::atomic<int>* round0_done = NULL;    // set once the group's first (by far largest) extension launch has finished
     };
     const char* env_groups = getenv("NB_CNS_GROUPS");
     int n_groups = env_groups ? atoi(env_groups) : 3;
@@ -333,7 +334,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         g.wc = ctx;
         if (k > 0) { const int rc = nb_worker_ctx(ctx, k, &g.wc); if (rc) return rc; }
         // with the long group's consensus running beside them, the other groups' extension kernels leave it room on the SMs
-        g.wc->ext_ctas = (long_mode && k > 0) ? 3 : 0;
+        g.wc->ext_ctas = (long_mode && k > 0) ? 2 : 0;
         group_bufs.emplace_back(g.wc);
         g.D = &group_bufs.back();
     }
@@ -487,6 +488,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                 g.res_ops[r0 + k] = rescued_ops[k] ? rescued_ops[k] : d_ops + g.res[r0 + k].ops_offset;
             }
             g.tm.ext += gt.lap();
+            if (g.round0_done) g.round0_done->store(1);
             if (round > 64) return nb_fail(wc, NB_ECUDA, "extension rounds do not converge");
         }
         return NB_OK;
@@ -821,37 +823,65 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         }
         memset(&wc->cc, 0, sizeof wc->cc); memset(&wc->tm, 0, sizeof wc->tm);
     };
+    // Overlap mode (several groups): every group runs its own consensus right after its extension rounds, on its own
+    // stream and WITHOUT the GPU lock, while the next group's extension kernel holds the machine.  The best-path kernel
+    // of a group is a dependent chain over its longest template (the groups are cut from the length-sorted templates:
+    // group 0 has the longest) and keeps few warps busy; the extension kernel leaves it room (2 CTAs per SM instead
+    // of 3).  The groups start their first -- by far largest -- extension launch in order, so that group k's consensus
+    // falls behind group k + 1's extension.
+    static const int kOverlap = getenv("NB_CNS_OVERLAP") ? atoi(getenv("NB_CNS_OVERLAP")) : 1;
+    const bool overlap = kOverlap && n_groups > 1 && !long_mode;
+    std::mutex emit_mx;
+    std::vector<CnsOut> outs((size_t)n_groups);
+    std::vector<int> cns_rc((size_t)n_groups, NB_OK);
     CnsOut out_long, out_main;
     int rc_long = NB_OK;
     {
-        // Long-template mode: group 0 holds the longest templates.  Its extension rounds go first; its consensus then
-        // runs on this thread WITHOUT the GPU lock while the other groups extend -- the consensus kernels of the
-        // longest templates are one long dependent chain that keeps a handful of warps busy, the extension kernels
-        // fill the rest of the machine.
+        std::vector<std::atomic<int>> r0done((size_t)n_groups);
+        for (auto& x : r0done) x.store(0);
         std::atomic<int> long_ext_done(long_mode ? 0 : 1);
+        auto group_work = [&](int k) {
+            ExtGroup& g = groups[(size_t)k];
+            if (overlap) {
+                g.round0_done = &r0done[(size_t)k];
+                g.wc->ext_ctas = 2;
+                if (k > 0) while (!r0done[(size_t)k - 1].load()) std::this_thread::yield();
+            }
+            g.rc = ext_phase(g);
+            if (overlap) {
+                r0done[(size_t)k].store(1);
+                if (g.rc == NB_OK && g.t0 < g.t1) {
+                    cns_rc[(size_t)k] = cns_phase(g.wc, g.t0, g.t1, outs[(size_t)k], false);
+                    if (cns_rc[(size_t)k] == NB_OK) { std::lock_guard<std::mutex> lk(emit_mx); cns_rc[(size_t)k] = emit(outs[(size_t)k]); }
+                }
+            }
+        };
         std::vector<std::thread> th;
         for (int k = 1; k < n_groups; ++k)
             th.emplace_back([&, k]() {
                 while (!long_ext_done.load()) std::this_thread::yield();
-                groups[(size_t)k].rc = ext_phase(groups[(size_t)k]);
+                group_work(k);
             });
-        groups[0].rc = ext_phase(groups[0]);
+        group_work(0);
         long_ext_done.store(1);
         if (long_mode && groups[0].rc == NB_OK) {
+            // Long-template mode (off by default): group 0 holds the longest templates; its consensus runs on this thread
+            // without the GPU lock while the other groups extend.
             rc_long = cns_phase(ctx, groups[0].t0, groups[0].t1, out_long, false);
-            if (rc_long == NB_OK) rc_long = emit(out_long);
+            if (rc_long == NB_OK) { std::lock_guard<std::mutex> lk(emit_mx); rc_long = emit(out_long); }
         }
         for (auto& x : th) x.join();
     }
     for (int k = 0; k < n_groups; ++k) {
         ExtGroup& g = groups[(size_t)k];
         if (g.rc) { if (g.wc != ctx) memcpy(ctx->err, g.wc->err, sizeof ctx->err); return g.rc; }
+        if (cns_rc[(size_t)k]) { if (g.wc != ctx) memcpy(ctx->err, g.wc->err, sizeof ctx->err); return cns_rc[(size_t)k]; }
         t_replay += g.tm.replay; t_gather += g.tm.gather; t_wait += g.tm.wait; t_ext += g.tm.ext; ext_ms += g.tm.ext_ms; t_init += g.tm.prep;
         fold(g.wc);
     }
     if (rc_long) return rc_long;
     const double t_ext_wall = ht.lap();
-    {
+    if (!overlap) {
         const size_t a0 = long_mode ? groups[0].t1 : c0;
         if (a0 < c1) {
             int rc = cns_phase(ctx, a0, c1, out_main, true);

@@ -33,6 +33,7 @@ struct nb_ctx {
     nb_ctx*      workers[NB_MAX_WORKERS];   // [1..]: shadow contexts of the pipeline workers (own stream, events, staging,
                                             // scratch; they share dev_cache with their parent), created on first use
     int          is_worker;
+    nb_ctx*      parent;         // of a worker: the context that owns the shared scratch (extension kernel launches are serialised)
     int          ext_ctas;       // k_extend CTAs per SM for launches of this context (0 = default)
 };
 

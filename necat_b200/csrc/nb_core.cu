@@ -131,6 +131,7 @@ int nb_worker_ctx(nb_ctx* parent, int w, nb_ctx** out)
         if (!c) return nb_fail(parent, NB_ENOMEM, "out of host memory");
         c->device = parent->device;
         c->is_worker = 1;
+        c->parent = parent;
         c->dev_cache = parent->dev_cache;
         NB_CUDA(parent, cudaSetDevice(parent->device));
         const int rc = nb_ctx_init_streams(c);

@@ -590,14 +590,16 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
         if (grid > want) grid = want ? want : 1;
     }
     const size_t slots = (size_t)NB_SMS * (kCtas < 1 ? 1 : kCtas) * EXT_WARPS * EXT_SLOTS;      // candidates in flight (sized for the full grid)
-    if (!ctx->ext_mat || ctx->ext_mat_slots < slots) {
-        if (ctx->ext_mat) cudaFree(ctx->ext_mat);
-        ctx->ext_mat = NULL;
-        NB_CUDA(ctx, cudaMalloc(&ctx->ext_mat, (sizeof(uint2) * EXT_MAT_STRIDE + EXT_REV_STRIDE) * slots));
-        ctx->ext_mat_slots = slots;
+    // the scratch belongs to the job's context: its workers' launches never run side by side (nb_consensus_job's GPU lock)
+    nb_ctx* own = ctx->parent ? ctx->parent : ctx;
+    if (!own->ext_mat || own->ext_mat_slots < slots) {
+        if (own->ext_mat) cudaFree(own->ext_mat);
+        own->ext_mat = NULL;
+        NB_CUDA(ctx, cudaMalloc(&own->ext_mat, (sizeof(uint2) * EXT_MAT_STRIDE + EXT_REV_STRIDE) * slots));
+        own->ext_mat_slots = slots;
     }
-    uint2* s_mat = (uint2*)ctx->ext_mat;
-    uint8_t* s_rev = (uint8_t*)ctx->ext_mat + sizeof(uint2) * EXT_MAT_STRIDE * slots;
+    uint2* s_mat = (uint2*)own->ext_mat;
+    uint8_t* s_rev = (uint8_t*)own->ext_mat + sizeof(uint2) * EXT_MAT_STRIDE * own->ext_mat_slots;
     NbDevBuf B(ctx);
     uint32_t* d_next = NULL;
     unsigned long long* d_cnt = NULL;
