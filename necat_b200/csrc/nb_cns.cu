@@ -607,7 +607,6 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             if ((rc = D.get(&P.tpl_nseg, dt.size()))) return rc;
             if ((rc = D.get(&P.seq_pool, out_pool))) return rc;
             d_seq_pool = P.seq_pool;
-            if ((rc = D.get(&P.next_unit, 1))) return rc;
             if ((rc = D.get(&P.span_cols, units.size()))) return rc;
             if ((rc = D.get(&P.span_links, units.size()))) return rc;
             if ((rc = D.get(&P.ckpt, n_ckpt))) return rc;
@@ -617,19 +616,16 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             if ((rc = D.get(&P.rev, level_total))) return rc;
             static const int kLinksCtas = getenv("NB_CNS_LINKS_CTAS") ? atoi(getenv("NB_CNS_LINKS_CTAS")) : 6;
             const unsigned links_grid = NB_SMS * (unsigned)(kLinksCtas < 1 ? 1 : kLinksCtas);
-            if ((rc = D.get(&P.cursor, (size_t)links_grid * CNS_WARPS * CNS_MAX_ALN))) return rc;
-            if ((rc = D.get(&P.ovpool, (size_t)links_grid * CNS_WARPS * CNS_OV))) return rc;
+            if ((rc = D.get(&P.cursor, (size_t)2 * links_grid * CNS_WARPS * CNS_MAX_ALN))) return rc;     // x 2: two slices side by side
+            if ((rc = D.get(&P.ovpool, (size_t)2 * links_grid * CNS_WARPS * CNS_OV))) return rc;
             if ((rc = D.get(&P.error_flag, 1))) return rc;
             if ((rc = D.get(&P.counters, 4))) return rc;
             if ((rc = D.get(&P.runs, seg_total))) return rc;
             if ((rc = D.get(&P.tpl_nrun, dt.size()))) return rc;
             if ((rc = D.get(&P.redo, dt.size()))) return rc;
-            if ((rc = D.get(&P.n_redo, 1))) return rc;
             NB_CUDA(cx, cudaMemcpyAsync(d_tpl, dt.data(), sizeof(CnsTemplate) * dt.size(), cudaMemcpyHostToDevice, cst));
             NB_CUDA(cx, cudaMemcpyAsync(d_aln, alns.data(), sizeof(CnsAln) * alns.size(), cudaMemcpyHostToDevice, cst));
             NB_CUDA(cx, cudaMemcpyAsync(d_unit, units.data(), sizeof(CnsUnit) * units.size(), cudaMemcpyHostToDevice, cst));
-            NB_CUDA(cx, cudaMemsetAsync(P.next_unit, 0, sizeof(uint32_t), cst));
-            NB_CUDA(cx, cudaMemsetAsync(P.n_redo, 0, sizeof(uint32_t), cst));
             NB_CUDA(cx, cudaMemsetAsync(P.span_cols, 0, sizeof(uint32_t) * units.size(), cst));
             NB_CUDA(cx, cudaMemsetAsync(P.error_flag, 0, sizeof(uint32_t), cst));
             NB_CUDA(cx, cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 4, cst));
@@ -646,39 +642,88 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             out.tm.wait += pt.lap();
             cudaEventRecord(cx->ev2, cst);
             {
-                const unsigned n_tpl = (unsigned)dt.size();
-                unsigned g = (n_tpl + 3) / 4;
-                if (g > NB_SMS * 16) g = NB_SMS * 16;
-                k_cns_prep<<<g, 128, 0, cst>>>(P);
-                NB_LAUNCH_CHECK(cx);
-                g = (unsigned)((alns.size() + 3) / 4);
-                if (g > NB_SMS * 16) g = NB_SMS * 16;
-                if (g) { k_cns_ckpt<<<g, 128, 0, cst>>>(P); NB_LAUNCH_CHECK(cx); }
-                unsigned lg = (unsigned)((units.size() + CNS_WARPS - 1) / CNS_WARPS);
-                if (lg > links_grid) lg = links_grid;
-                k_cns_links<<<lg, CNS_WARPS * 32, smem, cst>>>(P);
-                NB_LAUNCH_CHECK(cx);
-                k_cns_fix<<<(unsigned)((units.size() + 127) / 128), 128, 0, cst>>>(P);
-                NB_LAUNCH_CHECK(cx);
-                g = (unsigned)((units.size() + 3) / 4);
-                if (g > NB_SMS * 16) g = NB_SMS * 16;
-                k_cns_plan<<<g, 128, 0, cst>>>(P);
-                NB_LAUNCH_CHECK(cx);
-                // sixteen templates per CTA (8 lanes each); the chunk is sorted by length, the longest start first
-                if (kDpTest == 1) {
-                    const size_t dsm = (size_t)16 * (16 * 128 + 8 * 8);
-                    NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-                    k_cns_dp<128, 8><<<(n_tpl + 15) / 16, 128, dsm, cst>>>(P);
-                } else {
-                    const size_t dsm = (size_t)16 * (16 * 128 + 8 * 128);
-                    NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-                    k_cns_dp<128, 128><<<(n_tpl + 15) / 16, 128, dsm, cst>>>(P);
+                // The templates are sorted by length.  The best-path kernel is a dependent chain over a template's levels:
+                // for the longest templates it lasts several times longer than all their other kernels together, while
+                // it keeps only a few warps busy.  So the longest templates (slice 0, kLongShare of the bases) run on a
+                // side stream of their own, and their chain is hidden behind the link building of everything else.
+                static const int kLongPct = getenv("NB_CNS_LONG_PCT") ? atoi(getenv("NB_CNS_LONG_PCT")) : 8;
+                size_t cutx = 0;
+                if (kLongPct > 0 && dt.size() >= (getenv("NB_CNS_LONG_PCT") ? 4u : 64u)) {
+                    uint64_t total_T = 0, acc = 0;
+                    for (const auto& ct : dt) total_T += (uint64_t)ct.T;
+                    while (cutx < dt.size() && acc * 100 < total_T * (uint64_t)kLongPct) acc += (uint64_t)dt[cutx++].T;
+                    if (cutx >= dt.size()) cutx = 0;
                 }
-                NB_LAUNCH_CHECK(cx);
-                k_cns_dp_serial<<<(n_tpl + 127) / 128, 128, 0, cst>>>(P);
-                NB_LAUNCH_CHECK(cx);
-                k_cns_walk<<<(n_tpl + 3) / 4, 128, 0, cst>>>(P);
-                NB_LAUNCH_CHECK(cx);
+                const int nsl = cutx ? 2 : 1;
+                uint32_t* d_ctr;                                    // per slice: unit queue, redo count
+                if ((rc = D.get(&d_ctr, 8))) return rc;
+                NB_CUDA(cx, cudaMemsetAsync(d_ctr, 0, sizeof(uint32_t) * 8, cst));
+                if (nsl > 1) {
+                    NB_CUDA(cx, cudaEventRecord(cx->aux_ev[2], cst));
+                    for (int k = 0; k < 2; ++k) NB_CUDA(cx, cudaStreamWaitEvent(cx->aux[k], cx->aux_ev[2], 0));
+                }
+                for (int sl = 0; sl < nsl; ++sl) {
+                    const size_t a = sl == 0 ? 0 : cutx, b = (sl == 0 && nsl > 1) ? cutx : dt.size();
+                    cudaStream_t ss = nsl == 1 ? cst : cx->aux[sl];
+                    CnsParams Q = P;
+                    Q.tpl0 = d_tpl; Q.tpl = d_tpl + a; Q.n_tpl = (uint32_t)(b - a);
+                    Q.tpl_nseg = P.tpl_nseg + a; Q.tpl_nrun = P.tpl_nrun + a; Q.redo = P.redo + a;
+                    Q.next_unit = d_ctr + sl; Q.n_redo = d_ctr + 4 + sl;
+                    const uint32_t u0 = dt[a].unit_first, u1 = b < dt.size() ? dt[b].unit_first : (uint32_t)units.size();
+                    Q.unit = d_unit + u0; Q.n_units = u1 - u0;
+                    const uint32_t al0 = dt[a].aln_first, al1 = b < dt.size() ? dt[b].aln_first : (uint32_t)alns.size();
+                    Q.aln = d_aln;                                  // (CnsTemplate::aln_first indexes all alignments)
+                    Q.cursor = P.cursor + (size_t)sl * links_grid * CNS_WARPS * CNS_MAX_ALN;
+                    Q.ovpool = P.ovpool + (size_t)sl * links_grid * CNS_WARPS * CNS_OV;
+                    const unsigned n_tpl = Q.n_tpl;
+                    unsigned g = (n_tpl + 3) / 4;
+                    if (g > NB_SMS * 16) g = NB_SMS * 16;
+                    k_cns_prep<<<g, 128, 0, ss>>>(Q);
+                    NB_LAUNCH_CHECK(cx);
+                    if (al1 > al0) {
+                        CnsParams R = Q;
+                        R.aln = d_aln + al0; R.n_aln = al1 - al0;
+                        g = (unsigned)((al1 - al0 + 3) / 4);
+                        if (g > NB_SMS * 16) g = NB_SMS * 16;
+                        k_cns_ckpt<<<g, 128, 0, ss>>>(R);
+                        NB_LAUNCH_CHECK(cx);
+                    }
+                    // with the long slice's chain running beside them, the links of the rest leave it room on the SMs
+                    unsigned lmax = links_grid;
+                    if (nsl > 1 && sl == 1 && links_grid > NB_SMS) lmax = links_grid - NB_SMS * 2 > NB_SMS ? links_grid - NB_SMS * 2 : NB_SMS;
+                    unsigned lg = (unsigned)((Q.n_units + CNS_WARPS - 1) / CNS_WARPS);
+                    if (lg > lmax) lg = lmax;
+                    if (lg) {
+                        k_cns_links<<<lg, CNS_WARPS * 32, smem, ss>>>(Q);
+                        NB_LAUNCH_CHECK(cx);
+                        k_cns_fix<<<(unsigned)((Q.n_units + 127) / 128), 128, 0, ss>>>(Q);
+                        NB_LAUNCH_CHECK(cx);
+                        g = (unsigned)((Q.n_units + 3) / 4);
+                        if (g > NB_SMS * 16) g = NB_SMS * 16;
+                        k_cns_plan<<<g, 128, 0, ss>>>(Q);
+                        NB_LAUNCH_CHECK(cx);
+                    }
+                    // sixteen templates per CTA (8 lanes each); sorted by length, the longest start first
+                    if (kDpTest == 1) {
+                        const size_t dsm = (size_t)16 * (16 * 128 + 8 * 8);
+                        NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+                        k_cns_dp<128, 8><<<(n_tpl + 15) / 16, 128, dsm, ss>>>(Q);
+                    } else {
+                        const size_t dsm = (size_t)16 * (16 * 128 + 8 * 128);
+                        NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+                        k_cns_dp<128, 128><<<(n_tpl + 15) / 16, 128, dsm, ss>>>(Q);
+                    }
+                    NB_LAUNCH_CHECK(cx);
+                    k_cns_dp_serial<<<(n_tpl + 127) / 128, 128, 0, ss>>>(Q);
+                    NB_LAUNCH_CHECK(cx);
+                    k_cns_walk<<<(n_tpl + 3) / 4, 128, 0, ss>>>(Q);
+                    NB_LAUNCH_CHECK(cx);
+                }
+                if (nsl > 1)
+                    for (int k = 0; k < 2; ++k) {
+                        NB_CUDA(cx, cudaEventRecord(cx->aux_ev[k], cx->aux[k]));
+                        NB_CUDA(cx, cudaStreamWaitEvent(cst, cx->aux_ev[k], 0));
+                    }
             }
             cudaEventRecord(cx->ev3, cst);
             uint32_t eflag = 0; unsigned long long cnt[4];

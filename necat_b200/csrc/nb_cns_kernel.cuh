@@ -134,7 +134,8 @@ struct __align__(16) CnsCursor {    // per alignment cursor of k_cns_links (desc
 
 struct CnsParams {
     const uint8_t*     pac;
-    const CnsTemplate* tpl;
+    const CnsTemplate* tpl;             // the templates of this launch (a slice of the chunk)
+    const CnsTemplate* tpl0;            // all templates of the chunk: CnsUnit::tpl indexes these
     const CnsAln*      aln;
     uint32_t           n_tpl, n_aln;
     CnsSegment*        seg;
@@ -332,7 +333,7 @@ k_cns_links(CnsParams P)
         ui = __shfl_sync(0xffffffffu, ui, 0);
         if (ui >= P.n_units) break;
         const CnsUnit U = P.unit[ui];
-        const CnsTemplate TP = P.tpl[U.tpl];
+        const CnsTemplate TP = P.tpl0[U.tpl];
         const CnsAln* __restrict__ AL = P.aln + TP.aln_first;
         const int A = (int)TP.n_aln, T = TP.T;
         CnsPos* pos = P.pos + TP.pos_base;
@@ -662,7 +663,7 @@ k_cns_fix(CnsParams P)
     if (ui >= P.n_units) return;
     const CnsUnit U = P.unit[ui];
     if (U.span == 0) return;
-    const CnsTemplate TP = P.tpl[U.tpl];
+    const CnsTemplate TP = P.tpl0[U.tpl];
     const CnsPos* pos = P.pos + TP.pos_base;
     CnsLink* link = P.link + TP.link_base;
     const int b = (int)U.span * P.span;
@@ -711,7 +712,7 @@ k_cns_plan(CnsParams P)
     const uint32_t nwarp = gridDim.x * (blockDim.x >> 5);
     for (uint32_t ui = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ui < P.n_units; ui += nwarp) {
         const CnsUnit U = P.unit[ui];
-        const CnsTemplate TP = P.tpl[U.tpl];
+        const CnsTemplate TP = P.tpl0[U.tpl];
         const CnsPos* pos = P.pos + TP.pos_base;
         uint4* link = reinterpret_cast<uint4*>(P.link + TP.link_base);
         const int s0 = (int)U.span * P.span, s1 = (s0 + P.span < TP.T) ? s0 + P.span : TP.T;

@@ -117,31 +117,42 @@ __device__ __forceinline__ void myers_forward(WarpScratch& S, const uint8_t* __r
     __syncwarp();
     int s = 0;
     const int nchunk = (nsteps + 31) >> 5;
+    // one step of the anti-diagonal sweep
+#define EXT_STEP(RESET)                                                                                           \
+    {                                                                                                             \
+        uint32_t cin = __shfl_up_sync(0xffffffffu, cout, 1, WIDTH);                                               \
+        if (lid == 0) cin = 0x80000000u | ((uint32_t)st[s] << 7);       /* row 0 of the matrix: D[0][j] = j */    \
+        const uint32_t symoff = cin & 0x180u;                                                                     \
+        uint32_t Eq = *reinterpret_cast<const uint32_t*>(pe_base + symoff);                                       \
+        const uint32_t Xv = Eq | Mv;                                                                              \
+        Eq |= cin & 1u;                                                                                           \
+        const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;                                                         \
+        const uint32_t Ph = Mv | ~(Xh | Pv);                                                                      \
+        const uint32_t Mh = Pv & Xh;                                                                              \
+        cout = (Ph & 0x80000000u) | symoff | (Mh >> 31);                                                          \
+        accP = __funnelshift_r(accP, Ph >> lb, 1);                                                                \
+        accM = __funnelshift_r(accM, Mh >> lb, 1);                                                                \
+        const uint32_t Phs = (Ph << 1) | (cin >> 31);                                                             \
+        const uint32_t Mhs = (Mh << 1) | (cin & 1u);                                                              \
+        Pv = Mhs | ~(Xv | Phs);                                                                                   \
+        Mv = Phs & Xv;                                                                                            \
+        if ((unsigned)rel < (unsigned)W) row[rel] = make_uint2(Pv, Ph);                                           \
+        if (RESET && s == lid - 1) { Pv = 0xffffffffu; Mv = 0; }        /* my first column is next */             \
+        ++s; ++rel;                                                                                               \
+    }
     for (int c = 0; c < nchunk; ++c) {
         const int n = nsteps - 32 * c < 32 ? nsteps - 32 * c : 32;
+        if (c == 0 || n < 32) {
+            // the first chunk (lanes meet their first column: lid <= 31) and the last, partial one
 #pragma unroll 4
-        for (int b = 0; b < n; ++b, ++s, ++rel) {
-            uint32_t cin = __shfl_up_sync(0xffffffffu, cout, 1, WIDTH);
-            if (lid == 0) cin = 0x80000000u | ((uint32_t)st[s] << 7);       // row 0 of the matrix: D[0][j] = j
-            const uint32_t symoff = cin & 0x180u;
-            uint32_t Eq = *reinterpret_cast<const uint32_t*>(pe_base + symoff);
-            const uint32_t Xv = Eq | Mv;
-            Eq |= cin & 1u;
-            const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-            const uint32_t Ph = Mv | ~(Xh | Pv);
-            const uint32_t Mh = Pv & Xh;
-            cout = (Ph & 0x80000000u) | symoff | (Mh >> 31);
-            accP = __funnelshift_r(accP, Ph >> lb, 1);
-            accM = __funnelshift_r(accM, Mh >> lb, 1);
-            const uint32_t Phs = (Ph << 1) | (cin >> 31);
-            const uint32_t Mhs = (Mh << 1) | (cin & 1u);
-            Pv = Mhs | ~(Xv | Phs);
-            Mv = Phs & Xv;
-            if ((unsigned)rel < (unsigned)W) row[rel] = make_uint2(Pv, Ph);
-            if (s == lid - 1) { Pv = 0xffffffffu; Mv = 0; }                 // my first column is next
+            for (int b = 0; b < n; ++b) EXT_STEP(true)
+        } else {
+#pragma unroll 8
+            for (int b = 0; b < 32; ++b) EXT_STEP(false)
         }
         if (lid == lw) S.sb[half][c] = make_uint2(accP >> (32 - n), accM >> (32 - n));     // bit b: step 32 c + b
     }
+#undef EXT_STEP
     __syncwarp();
     // ---- first minimum of qblk + sum of (+1, -1) over the columns: lane = 32 steps
     int best = 0x7fffffff, bests = 0x7fffffff, carry = 0;
@@ -491,7 +502,10 @@ __device__ __forceinline__ void lp_walk_post(WarpScratch& S, const ExtParams& P,
     if (done || !lp_next_block(S, P, lane)) lp_end_side(S, P, lane);
 }
 
-__global__ void __launch_bounds__(EXT_WARPS * 32, 3)
+#ifndef EXT_MIN_CTAS
+#define EXT_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(EXT_WARPS * 32, EXT_MIN_CTAS)
 k_extend(ExtParams P)
 {
     extern __shared__ __align__(16) uint8_t ext_smem[];
@@ -580,7 +594,7 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
 {
     if (n_tasks == 0) return NB_OK;
     cudaStream_t st = ctx->stream;
-    static const int kCtas = getenv("NB_EXT_CTAS") ? atoi(getenv("NB_EXT_CTAS")) : 3;
+    static const int kCtas = getenv("NB_EXT_CTAS") ? atoi(getenv("NB_EXT_CTAS")) : EXT_MIN_CTAS;
     int ctas_per_sm = kCtas < 1 ? 1 : kCtas;        // x 8 warps x 32 candidates per SM
     if (ctx->ext_ctas > 0 && ctx->ext_ctas < ctas_per_sm) ctas_per_sm = ctx->ext_ctas;
     unsigned grid = NB_SMS * ctas_per_sm;
