@@ -343,30 +343,32 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         if (cudaSetDevice(wc->device) != cudaSuccess) return nb_fail(wc, NB_ECUDA, "cudaSetDevice failed");
         cudaStream_t gst = wc->stream;
         HostTimer gt;
+        // The round-0 requests: the first 50 candidates (phase 1), or nothing with -u 1 (the replay then asks for the first
+        // window).  The coverage arrays (2 bytes per template base: hundreds of MB to clear) are only needed by the first
+        // replay: they are set up by side threads while the first extension launch runs.
+        for (size_t t = g.t0; t < g.t1; ++t) {
+            Tpl& T = tpls[t];
+            T.request.clear();
+            if (!o.use_fixed_ident_cutoff) for (size_t k = 0; k < T.n && k < 50; ++k) T.request.push_back(k);
+        }
+        std::vector<std::thread> cov_threads;
         {
-            // coverage arrays (2 bytes per template base) and the round-0 requests: the first 50 candidates (phase 1),
-            // or nothing with -u 1 (the replay then asks for the first window)
-            auto init = [&](size_t a, size_t b) {
-                for (size_t t = a; t < b; ++t) {
-                    Tpl& T = tpls[t];
-                    T.cov.assign((size_t)T.T + 1, 0); T.n_below = o.max_cov > 0 ? T.T : 0;
-                    T.request.clear();
-                    if (!o.use_fixed_ident_cutoff) for (size_t k = 0; k < T.n && k < 50; ++k) T.request.push_back(k);
-                }
+            auto init = [&tpls, &o](size_t a, size_t b) {
+                for (size_t t = a; t < b; ++t) { Tpl& T = tpls[t]; T.cov.assign((size_t)T.T + 1, 0); T.n_below = o.max_cov > 0 ? T.T : 0; }
             };
-            const size_t nt = g.t1 - g.t0, per = (nt + nthreads - 1) / nthreads;
-            std::vector<std::thread> th;
-            for (unsigned w = 1; w < nthreads && per; ++w) {
+            const unsigned nside = std::max(1u, nthreads / 2);
+            const size_t nt = g.t1 - g.t0, per = (nt + nside - 1) / nside;
+            for (unsigned w = 0; w < nside && per; ++w) {
                 const size_t a = g.t0 + w * per, b = std::min(g.t1, a + per);
                 if (a >= b) break;
-                th.emplace_back(init, a, b);
+                cov_threads.emplace_back(init, a, b);
             }
-            init(g.t0, std::min(g.t1, g.t0 + per));
-            for (auto& x : th) x.join();
         }
+        struct Joiner { std::vector<std::thread>& th; ~Joiner() { for (auto& x : th) if (x.joinable()) x.join(); } } cov_joiner{cov_threads};
         g.tm.prep += gt.lap();
         for (int round = 0;; ++round) {
             if (round > 0 || o.use_fixed_ident_cutoff) {
+                for (auto& x : cov_threads) if (x.joinable()) x.join();
                 // replay in parallel over templates
                 std::vector<std::thread> th;
                 std::vector<size_t> todo;
@@ -380,27 +382,54 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                 for (auto& x : th) x.join();
             }
             g.tm.replay += gt.lap();
-            // gather requests
+            // gather requests: sizes per template, prefix, fill in parallel
             std::vector<ExtTask> tasks;
             std::vector<size_t> task_can;
             uint64_t pool = 0;
-            for (size_t t = g.t0; t < g.t1; ++t) {
-                Tpl& T = tpls[t];
-                if (T.stage == 2) continue;
-                for (size_t k : T.request) {
-                    const Can& c = cans[T.first + k];
-                    ExtTask e;
-                    e.qid = (uint32_t)c.qid; e.sid = (uint32_t)T.tid; e.qoff = c.qoff; e.soff = c.soff; e.qdir = c.qdir; e.pad_ = 0;
-                    if (c.qoff < 0 || c.soff < 0 || c.qoff > c.qsize || c.soff > T.T)
-                        return nb_fail(wc, NB_EINVAL, "candidate offsets out of range (template %d)", T.tid);
-                    const uint64_t mn = (uint64_t)std::min(c.qoff, c.soff);
-                    e.lcap = (uint32_t)(c.qoff + c.soff);
-                    e.ops_cap = (uint32_t)((uint64_t)c.qsize + (uint64_t)T.T + mn + 64);
-                    e.ops_base = pool;
-                    pool += (e.ops_cap + 15) & ~15ull;
-                    tasks.push_back(e);
-                    task_can.push_back(T.first + k);
-                }
+            {
+                const size_t nt = g.t1 - g.t0;
+                std::vector<uint64_t> t_cnt(nt + 1, 0), t_bytes(nt + 1, 0);
+                std::atomic<int> bad(-1);
+                auto each = [&](size_t a, size_t b, bool fill) {
+                    for (size_t x = a; x < b; ++x) {
+                        Tpl& T = tpls[g.t0 + x];
+                        if (T.stage == 2) continue;
+                        uint64_t n = 0, bytes = 0;
+                        for (size_t k : T.request) {
+                            const Can& c = cans[T.first + k];
+                            const uint64_t mn = (uint64_t)std::min(c.qoff, c.soff);
+                            const uint32_t cap = (uint32_t)((uint64_t)c.qsize + (uint64_t)T.T + mn + 64);
+                            if (fill) {
+                                ExtTask e;
+                                e.qid = (uint32_t)c.qid; e.sid = (uint32_t)T.tid; e.qoff = c.qoff; e.soff = c.soff; e.qdir = c.qdir; e.pad_ = 0;
+                                e.lcap = (uint32_t)(c.qoff + c.soff);
+                                e.ops_cap = cap;
+                                e.ops_base = t_bytes[x] + bytes;
+                                tasks[t_cnt[x] + n] = e;
+                                task_can[t_cnt[x] + n] = T.first + k;
+                            } else if (c.qoff < 0 || c.soff < 0 || c.qoff > c.qsize || c.soff > T.T) bad.store(T.tid);
+                            ++n; bytes += (cap + 15) & ~15ull;
+                        }
+                        if (!fill) { t_cnt[x + 1] = n; t_bytes[x + 1] = bytes; }
+                    }
+                };
+                auto spread = [&](bool fill) {
+                    const size_t per = (nt + nthreads - 1) / nthreads;
+                    std::vector<std::thread> th;
+                    for (unsigned w = 1; w < nthreads && per; ++w) {
+                        const size_t a = w * per, b = std::min(nt, a + per);
+                        if (a >= b) break;
+                        th.emplace_back(each, a, b, fill);
+                    }
+                    if (per) each(0, std::min(nt, per), fill);
+                    for (auto& x : th) x.join();
+                };
+                spread(false);
+                if (bad.load() >= 0) return nb_fail(wc, NB_EINVAL, "candidate offsets out of range (template %d)", bad.load());
+                for (size_t x = 0; x < nt; ++x) { t_cnt[x + 1] += t_cnt[x]; t_bytes[x + 1] += t_bytes[x]; }
+                tasks.resize(t_cnt[nt]); task_can.resize(t_cnt[nt]);
+                pool = t_bytes[nt];
+                if (!tasks.empty()) spread(true);
             }
             g.tm.gather += gt.lap();
             if (tasks.empty()) break;
