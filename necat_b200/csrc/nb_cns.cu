@@ -727,20 +727,14 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                         NB_LAUNCH_CHECK(cx);
                         k_cns_fix<<<(unsigned)((Q.n_units + 127) / 128), 128, 0, ss>>>(Q);
                         NB_LAUNCH_CHECK(cx);
-                        g = (unsigned)((Q.n_units + 3) / 4);
-                        if (g > NB_SMS * 16) g = NB_SMS * 16;
-                        k_cns_plan<<<g, 128, 0, ss>>>(Q);
-                        NB_LAUNCH_CHECK(cx);
                     }
-                    // sixteen templates per CTA (8 lanes each); sorted by length, the longest start first
+                    // one lane per template, 32 templates per CTA; sorted by length, the longest start first
                     if (kDpTest == 1) {
-                        const size_t dsm = (size_t)16 * (16 * 128 + 8 * 8);
-                        NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-                        k_cns_dp<128, 8><<<(n_tpl + 15) / 16, 128, dsm, ss>>>(Q);
+                        const size_t dsm = (size_t)32 * (16 * CNS_DP_LR + 8 * 8);
+                        k_cns_dp<8><<<(n_tpl + 31) / 32, 32, dsm, ss>>>(Q);
                     } else {
-                        const size_t dsm = (size_t)16 * (16 * 128 + 8 * 128);
-                        NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-                        k_cns_dp<128, 128><<<(n_tpl + 15) / 16, 128, dsm, ss>>>(Q);
+                        const size_t dsm = (size_t)32 * (16 * CNS_DP_LR + 8 * 128);
+                        k_cns_dp<128><<<(n_tpl + 31) / 32, 32, dsm, ss>>>(Q);
                     }
                     NB_LAUNCH_CHECK(cx);
                     k_cns_dp_serial<<<(n_tpl + 127) / 128, 128, 0, ss>>>(Q);

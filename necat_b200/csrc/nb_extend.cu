@@ -516,7 +516,7 @@ k_extend(ExtParams P)
     uint2* mat = P.mat + (wslot + (lane & (EXT_SLOTS - 1))) * EXT_MAT_STRIDE;          // of my slot
     uint32_t* rev = reinterpret_cast<uint32_t*>(P.rev + (wslot + (lane & (EXT_SLOTS - 1))) * EXT_REV_STRIDE);
     unsigned long long nb = 0, nc = 0, nwd = 0;
-    const bool has = lane < EXT_SLOTS;                  // this lane owns a slot
+    const bool has = lane < P.slots;                    // this lane owns a slot
     if (has) XF(X_STATE, lane) = ST_IDLE;
     __syncwarp();
     bool drained = false;
@@ -598,9 +598,16 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     int ctas_per_sm = kCtas < 1 ? 1 : kCtas;        // x 8 warps x 32 candidates per SM
     if (ctx->ext_ctas > 0 && ctx->ext_ctas < ctas_per_sm) ctas_per_sm = ctx->ext_ctas;
     unsigned grid = NB_SMS * ctas_per_sm;
+    // A small launch spreads its candidates over all the warps there are: a candidate is a chain of block alignments, and a
+    // warp runs the forward passes of its slots one pair after the other -- with few candidates per warp the chain of each
+    // is that much shorter (the later extension rounds of a consensus job are a few hundred candidates).
+    int n_slots = (int)((n_tasks + (uint64_t)grid * EXT_WARPS - 1) / ((uint64_t)grid * EXT_WARPS));
+    n_slots = (n_slots + 1) & ~1;
+    if (n_slots < 2) n_slots = 2;
+    if (n_slots > EXT_SLOTS) n_slots = EXT_SLOTS;
     {
-        // no more warps than there are candidates to fill a good part of their 32 slots
-        const unsigned want = (unsigned)((n_tasks + EXT_WARPS * EXT_SLOTS - 1) / (EXT_WARPS * EXT_SLOTS));
+        // no more warps than there are candidates to fill their slots
+        const unsigned want = (unsigned)((n_tasks + EXT_WARPS * (unsigned)n_slots - 1) / (EXT_WARPS * (unsigned)n_slots));
         if (grid > want) grid = want ? want : 1;
     }
     const size_t slots = (size_t)NB_SMS * (kCtas < 1 ? 1 : kCtas) * EXT_WARPS * EXT_SLOTS;      // candidates in flight (sized for the full grid)
@@ -626,6 +633,7 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     P.tasks = d_tasks; P.n_tasks = n_tasks; P.results = d_results; P.ops = d_ops; P.mat = s_mat; P.rev = s_rev;
     P.next_task = d_next; P.counters = d_cnt;
     P.error = error; P.min_align_size = min_align_size; P.tail_match_len = tail_match_len; P.block_size = 512;
+    P.slots = n_slots;
     P.band_test = getenv("NB_EXT_BAND_TEST") ? atoi(getenv("NB_EXT_BAND_TEST")) : 0;     // (read at every launch: tests switch it)
     const size_t smem = sizeof(WarpScratch) * EXT_WARPS;
     NB_CUDA(ctx, cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

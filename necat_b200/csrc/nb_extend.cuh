@@ -41,6 +41,8 @@ struct ExtParams {
     int             min_align_size;
     int             tail_match_len;
     int             block_size;     // 512
+    int             slots;          // candidates in flight per warp (2 .. EXT_SLOTS): few when the launch is small, so that a candidate's chain of blocks
+                                    // does not wait for the forward passes of fifteen others
     int             band_test;      // 1: the walk-back only trusts the two middle words of a column's band (tests: exercises the moving band)
 };
 
