@@ -6,11 +6,17 @@
 //   reference: dense u64 table (count<<34|start) + u64 offset list, built by two
 //              serial scans and a 4-pass LSD radix sort of (hash<<34|pos) words;
 //   here:      dense u32 CSR row-pointer table tbl[4^k + 1] + u32 offsets.
-//              count (RED.ADD per k-mer) -> mask > q -> exclusive scan -> fill
-//              with an atomic cursor per hash -> sort the (short) runs.
-// Algorithmic HBM bytes per indexed base: 2 x 0.25 B packed read +
-// 2 x 4 B random RMW on the count/cursor tables + 4 B offset write + table
-// sweeps 4^k x (4+4+4+4+4) B.
+// Counting k-mers straight into a 4 GiB table is one random 32-byte sector of HBM per k-mer and pass (the first
+// version of this file: 39 ms for 184 M k-mers).  Now the (hash, position) pairs are first partitioned by the top bits
+// of the hash -- one or two passes of at most 256 bins, tiles staged in shared memory and written out as runs per bin --
+// into buckets of 2^14 consecutive hash values, so that the counters of a bucket live in shared memory:
+//   k_part_count / k_part_scatter   (x 1 or 2)   pairs grouped by bucket (order inside a bucket arbitrary)
+//   k_bucket_count                  per bucket: count per hash in shared memory, cut-off > q, kept / distinct totals
+//   k_bucket_fill                   per bucket: counts again, exclusive scan, the bucket's slice of tbl (every entry of
+//                                   the table is written exactly once, coalesced), positions placed run by run, short
+//                                   runs put in ascending order on the spot, long ones (> 24) listed for k_sort_long_runs
+// HBM bytes per indexed base: the pair array (8 B) is written and read twice by the partition passes and read
+// twice more by the bucket kernels; table 4 B x 4^k written once; offsets 4 B.
 #include "nb_common.cuh"
 
 #define IDX_THREADS 256
@@ -26,171 +32,305 @@ __global__ void k_mark_invalid(const uint64_t* __restrict__ off, const uint32_t*
     for (uint64_t p = beg; p < end; ++p) atomicOr(invalid + (p >> 5), 1u << (p & 31));
 }
 
-// ---- count pass / fill pass share the k-mer enumeration: one thread per 16 bases
-template <bool FILL>
-__global__ void __launch_bounds__(IDX_THREADS)
-k_scan_kmers(const uint32_t* __restrict__ words, uint64_t db_size, const uint32_t* __restrict__ invalid, int k,
-             uint32_t* __restrict__ cnt, uint32_t* __restrict__ tbl, uint32_t* __restrict__ offs, uint32_t h_lo, uint32_t h_n)
-{
-    const uint64_t nchunk = (db_size + 15) >> 4;
-    const uint32_t mask = (uint32_t)((1ull << (2 * k)) - 1);
-    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunk; c += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t v = nb_load_be64(words, c);
-        uint32_t bad = __ldg(invalid + (c >> 1)) >> ((c & 1) * 16);
-        uint64_t p0 = c << 4;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if ((bad >> i) & 1) continue;
-            if (p0 + i >= db_size) continue;
-            uint32_t h = ((uint32_t)(v >> (64 - 2 * i - 2 * k)) & mask) - h_lo;      // inside this build's slice of the hash space?
-            if (h >= h_n) continue;
-            if (!FILL) {
-                atomicAdd(cnt + h, 1u);                 // RED.ADD, result unused
-            } else if (__ldg(cnt + h)) {
-                uint32_t slot = atomicAdd(tbl + h + 1, 1u);
-                offs[slot] = (uint32_t)(p0 + i);
-            }
-        }
-    }
-}
+#define IDX_LB 14                       // hash values per bucket = 2^IDX_LB: one u32 counter each = 64 KB of shared memory
+#define IDX_BUCKET (1u << IDX_LB)
+#define IDX_TILE 4096                   // pairs per tile of a partition pass
+#define IDX_BINS 256                    // bins of a partition pass (at most)
+#define IDX_FILL_THREADS 512
+#define LONG_RUN 24
 
-// ---- mask (count > q -> 0) + 3-phase exclusive scan into tbl[h + 1]
-#define SCAN_ITEMS 8
-#define SCAN_THREADS 1024
-#define SCAN_TILE (SCAN_ITEMS * SCAN_THREADS)
+struct IdxGeom {
+    uint32_t h_lo, h_n;                 // this build's slice of the hash space
+    int      k;
+    int      sh1, nb1;                  // pass 1: bin = hr >> sh1 (nb1 bins)
+    int      sh2, nb2;                  // pass 2: bin = (hr >> sh2) & (nb2 - 1); nb2 = 1: no second pass
+    uint32_t n_buckets;
+};
 
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total)
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* s_warp, uint32_t* total)
 {
-    __shared__ uint32_t warp_sums[32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint32_t inc = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) warp_sums[wid] = inc;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        uint32_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+        const uint32_t w = lane < nw ? s_warp[lane] : 0;
         uint32_t winc = w;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
-            if (lane >= d) winc += t;
-        }
-        warp_sums[lane] = winc - w;     // exclusive
-        if (lane == 31) *total = winc;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += t; }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
     }
     __syncthreads();
-    uint32_t r = warp_sums[wid] + inc - v;
+    const uint32_t r = s_warp[wid] + inc - v;
+    if (total) *total = s_warp[32];
     __syncthreads();
     return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_mask_reduce(uint32_t* __restrict__ cnt, uint64_t n, uint32_t q, uint32_t* __restrict__ tile_sum,
-              uint32_t* __restrict__ tile_distinct)
+// The k-mers of 16 consecutive start positions (chunk c of the volume) that are valid and lie in the slice: relative hash
+// values into hr[], bit i of the result set for position 16 c + i.
+__device__ __forceinline__ uint32_t idx_chunk_kmers(const uint32_t* __restrict__ words, const uint32_t* __restrict__ invalid, uint64_t db_size,
+                                                    uint64_t c, const IdxGeom& G, uint32_t hr[16])
 {
-    __shared__ uint32_t tot, totd;
-    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
-    uint32_t s = 0, d = 0;
-    if (base + SCAN_ITEMS <= n) {
-        uint4 a = *reinterpret_cast<uint4*>(cnt + base), b = *reinterpret_cast<uint4*>(cnt + base + 4);
-        uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        bool dirty = false;
+    const uint32_t mask = (uint32_t)((1ull << (2 * G.k)) - 1);
+    const uint64_t v = nb_load_be64(words, c);
+    const uint32_t bad = __ldg(invalid + (c >> 1)) >> ((c & 1) * 16);
+    const uint64_t p0 = c << 4;
+    uint32_t ok = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (x[i] > q) { x[i] = 0; dirty = true; }
-            s += x[i];
-            d += x[i] != 0;
-        }
-        if (dirty) {
-            *reinterpret_cast<uint4*>(cnt + base) = make_uint4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<uint4*>(cnt + base + 4) = make_uint4(x[4], x[5], x[6], x[7]);
-        }
-    } else {
-        for (int i = 0; i < SCAN_ITEMS; ++i)
-            if (base + i < n) {
-                uint32_t x = cnt[base + i];
-                if (x > q) { x = 0; cnt[base + i] = 0; }
-                s += x;
-                d += x != 0;
-            }
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t h = ((uint32_t)(v >> (64 - 2 * i - 2 * G.k)) & mask) - G.h_lo;
+        hr[i] = h;
+        if (!((bad >> i) & 1) && p0 + i < db_size && h < G.h_n) ok |= 1u << i;
     }
-    block_exclusive_scan(s, &tot);
-    block_exclusive_scan(d, &totd);
-    if (threadIdx.x == 0) { tile_sum[blockIdx.x] = tot; tile_distinct[blockIdx.x] = totd; }
+    return ok;
 }
 
-// single block: exclusive scan of the tile sums (in place), totals to out[0..1]
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_tiles(uint32_t* __restrict__ tile_sum, const uint32_t* __restrict__ tile_distinct, uint32_t ntiles,
-             uint64_t* __restrict__ out)
+// ---- partition pass 1, over the packed reads: bin sizes
+__global__ void __launch_bounds__(IDX_THREADS)
+k_part1_count(const uint32_t* __restrict__ words, uint64_t db_size, const uint32_t* __restrict__ invalid, IdxGeom G, uint32_t* __restrict__ hist)
 {
-    __shared__ uint32_t tot;
-    uint32_t carry = 0;
-    uint64_t dsum = 0;
-    for (uint32_t base = 0; base < ntiles; base += SCAN_THREADS) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < ntiles ? tile_sum[i] : 0;
-        uint32_t ex = block_exclusive_scan(v, &tot);
-        if (i < ntiles) tile_sum[i] = carry + ex;
-        carry += tot;
+    __shared__ uint32_t s_cnt[IDX_BINS];
+    s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t nchunk = (db_size + 15) >> 4;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunk; c += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t hr[16];
+        const uint32_t ok = idx_chunk_kmers(words, invalid, db_size, c, G, hr);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if ((ok >> i) & 1) atomicAdd(&s_cnt[hr[i] >> G.sh1], 1u);
+    }
+    __syncthreads();
+    if (s_cnt[threadIdx.x]) atomicAdd(hist + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+// Exclusive scan of n bin sizes (n <= 65536) into base[n + 1] and the scatter cursors; tiles of IDX_TILE pairs per bin
+// into tile_first[n + 1] (the work list of the next partition pass).  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024)
+k_part_scan(const uint32_t* __restrict__ hist, uint32_t n, uint32_t* __restrict__ base, uint32_t* __restrict__ cursor, uint32_t* __restrict__ tile_first)
+{
+    __shared__ uint32_t s_warp[33];
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t i0 = threadIdx.x * per, i1 = i0 + per < n ? i0 + per : n;
+    uint32_t s = 0, t = 0;
+    for (uint32_t i = i0; i < i1; ++i) { s += hist[i]; t += (hist[i] + IDX_TILE - 1) / IDX_TILE; }
+    uint32_t tot_s = 0, tot_t = 0;
+    uint32_t bs = block_scan_excl(s, s_warp, &tot_s), bt = block_scan_excl(t, s_warp, &tot_t);
+    for (uint32_t i = i0; i < i1; ++i) {
+        base[i] = bs; cursor[i] = bs;
+        if (tile_first) tile_first[i] = bt;
+        bs += hist[i]; bt += (hist[i] + IDX_TILE - 1) / IDX_TILE;
+    }
+    if (threadIdx.x == 0) { base[n] = tot_s; if (tile_first) tile_first[n] = tot_t; }
+}
+
+// One tile of a partition pass, the pairs already in registers (NPER per thread, valid ones flagged in `ok`): rank inside
+// the bin, space for the tile's share of every bin taken from the bin's cursor (the order of tiles inside a bin is
+// arbitrary), the pairs staged bin by bin in shared memory and written out as runs.
+template <int NPER>
+__device__ __forceinline__ void idx_scatter_tile(const uint32_t (&hr)[NPER], const uint32_t (&pos)[NPER], uint32_t ok, int sh, uint32_t binmask,
+                                                 uint32_t* __restrict__ cursor, uint2* __restrict__ dst,
+                                                 uint32_t* s_cnt, uint32_t* s_loff, uint32_t* s_goff, uint32_t* s_warp, uint2* s_stage)
+{
+    s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t rank[NPER];
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) if ((ok >> i) & 1) rank[i] = atomicAdd(&s_cnt[(hr[i] >> sh) & binmask], 1u);
+    __syncthreads();
+    {
+        const uint32_t c = s_cnt[threadIdx.x];
+        uint32_t total;
+        const uint32_t lo = block_scan_excl(c, s_warp, &total);
+        s_loff[threadIdx.x] = lo;
+        s_goff[threadIdx.x] = c ? atomicAdd(cursor + threadIdx.x, c) : 0u;
+        if (threadIdx.x == 0) s_loff[IDX_BINS] = total;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) if ((ok >> i) & 1) s_stage[s_loff[(hr[i] >> sh) & binmask] + rank[i]] = make_uint2(hr[i], pos[i]);
+    __syncthreads();
+    const uint32_t total = s_loff[IDX_BINS];
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint2 e = s_stage[i];
+        const uint32_t b = (e.x >> sh) & binmask;
+        dst[s_goff[b] + (i - s_loff[b])] = e;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(IDX_THREADS)
+k_part1_scatter(const uint32_t* __restrict__ words, uint64_t db_size, const uint32_t* __restrict__ invalid, IdxGeom G,
+                uint32_t* __restrict__ cursor, uint2* __restrict__ dst)
+{
+    __shared__ uint32_t s_cnt[IDX_BINS], s_loff[IDX_BINS + 1], s_goff[IDX_BINS], s_warp[33];
+    __shared__ uint2 s_stage[IDX_TILE];
+    const uint64_t nchunk = (db_size + 15) >> 4;
+    const uint64_t ntile = (nchunk + IDX_THREADS - 1) / IDX_THREADS;
+    for (uint64_t t = blockIdx.x; t < ntile; t += gridDim.x) {
+        const uint64_t c = t * IDX_THREADS + threadIdx.x;
+        uint32_t hr[16], pos[16], ok = 0;
+        if (c < nchunk) ok = idx_chunk_kmers(words, invalid, db_size, c, G, hr);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pos[i] = (uint32_t)(c << 4) + i;
+        idx_scatter_tile<16>(hr, pos, ok, G.sh1, 0xffffffffu, cursor, dst, s_cnt, s_loff, s_goff, s_warp, s_stage);
+    }
+}
+
+// ---- partition pass 2, over the pairs of every pass-1 bin: tile -> (bin, range) through tile_first
+__device__ __forceinline__ bool idx_tile_range(uint32_t tile, const uint32_t* __restrict__ tile_first, const uint32_t* __restrict__ base1, int nb1,
+                                               uint32_t* bin, uint32_t* lo, uint32_t* hi)
+{
+    if (tile >= tile_first[nb1]) return false;
+    int a = 0, b = nb1;                             // last bin whose first tile is <= tile
+    while (b - a > 1) { const int m = (a + b) >> 1; if (tile_first[m] <= tile) a = m; else b = m; }
+    *bin = (uint32_t)a;
+    const uint32_t s = base1[a] + (tile - tile_first[a]) * IDX_TILE, e = base1[a + 1];
+    *lo = s; *hi = s + IDX_TILE < e ? s + IDX_TILE : e;
+    return true;
+}
+
+__global__ void __launch_bounds__(IDX_THREADS)
+k_part2_count(const uint2* __restrict__ src, const uint32_t* __restrict__ tile_first, const uint32_t* __restrict__ base1, IdxGeom G,
+              uint32_t max_tiles, uint32_t* __restrict__ hist2)
+{
+    __shared__ uint32_t s_cnt[IDX_BINS];
+    for (uint32_t tile = blockIdx.x; tile < max_tiles; tile += gridDim.x) {
+        uint32_t bin, lo, hi;
+        if (!idx_tile_range(tile, tile_first, base1, G.nb1, &bin, &lo, &hi)) break;
+        s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[(src[i].x >> G.sh2) & (uint32_t)(G.nb2 - 1)], 1u);
+        __syncthreads();
+        if (threadIdx.x < (unsigned)G.nb2 && s_cnt[threadIdx.x]) atomicAdd(hist2 + (size_t)bin * G.nb2 + threadIdx.x, s_cnt[threadIdx.x]);
         __syncthreads();
     }
-    // distinct count: plain strided sum by thread 0..1023 then reduce
-    uint64_t local = 0;
-    for (uint32_t i = threadIdx.x; i < ntiles; i += SCAN_THREADS) local += tile_distinct[i];
-    __shared__ unsigned long long dtot;
-    if (threadIdx.x == 0) dtot = 0;
-    __syncthreads();
-    atomicAdd(&dtot, (unsigned long long)local);
-    __syncthreads();
-    dsum = dtot;
-    if (threadIdx.x == 0) { out[0] = carry; out[1] = dsum; }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_apply(const uint32_t* __restrict__ cnt, uint64_t n, const uint32_t* __restrict__ tile_base,
-             uint32_t* __restrict__ tbl)
-{
-    __shared__ uint32_t tot;
-    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
-    uint32_t x[SCAN_ITEMS];
-    uint32_t s = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        x[i] = base + i < n ? cnt[base + i] : 0;
-        s += x[i];
-    }
-    uint32_t run = tile_base[blockIdx.x] + block_exclusive_scan(s, &tot);
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        if (base + i < n) tbl[base + i + 1] = run;      // cursor of hash (base+i) = start of its run
-        run += x[i];
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) tbl[0] = 0;
-}
-
-// ---- order every run by position (the atomic cursor fills runs in arbitrary order)
-#define LONG_RUN 24
 __global__ void __launch_bounds__(IDX_THREADS)
-k_sort_short_runs(const uint32_t* __restrict__ tbl, uint64_t n_hash, uint32_t* __restrict__ offs,
-                  uint32_t* __restrict__ long_list, uint32_t* __restrict__ n_long)
+k_part2_scatter(const uint2* __restrict__ src, const uint32_t* __restrict__ tile_first, const uint32_t* __restrict__ base1, IdxGeom G,
+                uint32_t max_tiles, uint32_t* __restrict__ cursor2, uint2* __restrict__ dst)
 {
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < n_hash; h += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t lo = __ldg(tbl + h), hi = __ldg(tbl + h + 1);
-        uint32_t n = hi - lo;
-        if (n < 2) continue;
-        if (n > LONG_RUN) { long_list[atomicAdd(n_long, 1u)] = (uint32_t)h; continue; }
-        uint32_t* a = offs + lo;
-        for (uint32_t i = 1; i < n; ++i) {
-            uint32_t v = a[i];
-            uint32_t j = i;
-            while (j > 0 && a[j - 1] > v) { a[j] = a[j - 1]; --j; }
-            a[j] = v;
+    __shared__ uint32_t s_cnt[IDX_BINS], s_loff[IDX_BINS + 1], s_goff[IDX_BINS], s_warp[33];
+    __shared__ uint2 s_stage[IDX_TILE];
+    for (uint32_t tile = blockIdx.x; tile < max_tiles; tile += gridDim.x) {
+        uint32_t bin, lo, hi;
+        if (!idx_tile_range(tile, tile_first, base1, G.nb1, &bin, &lo, &hi)) break;
+        uint32_t hr[16], pos[16], ok = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t x = lo + i * IDX_THREADS + threadIdx.x;
+            hr[i] = 0; pos[i] = 0;
+            if (x < hi) { const uint2 e = src[x]; hr[i] = e.x; pos[i] = e.y; ok |= 1u << i; }
         }
+        idx_scatter_tile<16>(hr, pos, ok, G.sh2, (uint32_t)(G.nb2 - 1), cursor2 + (size_t)bin * G.nb2, dst, s_cnt, s_loff, s_goff, s_warp, s_stage);
+    }
+}
+
+// ---- per bucket: counts in shared memory, the cut-off, totals
+__global__ void __launch_bounds__(IDX_FILL_THREADS)
+k_bucket_count(const uint2* __restrict__ pairs, const uint32_t* __restrict__ bbase, IdxGeom G, uint32_t q,
+               uint32_t* __restrict__ bucket_kept, uint32_t* __restrict__ bucket_distinct)
+{
+    extern __shared__ __align__(16) uint32_t s_a[];             // [IDX_BUCKET]
+    __shared__ uint32_t s_red[2];
+    for (uint32_t b = blockIdx.x; b < G.n_buckets; b += gridDim.x) {
+        const uint32_t lo = bbase[b], hi = bbase[b + 1];
+        if (lo == hi) { if (threadIdx.x == 0) { bucket_kept[b] = 0; bucket_distinct[b] = 0; } continue; }
+        for (uint32_t i = threadIdx.x; i < IDX_BUCKET; i += blockDim.x) s_a[i] = 0;
+        if (threadIdx.x < 2) s_red[threadIdx.x] = 0;
+        __syncthreads();
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_a[pairs[i].x & (IDX_BUCKET - 1)], 1u);
+        __syncthreads();
+        uint32_t kept = 0, dist = 0;
+        for (uint32_t i = threadIdx.x; i < IDX_BUCKET; i += blockDim.x) { const uint32_t c = s_a[i]; if (c && c <= q) { kept += c; ++dist; } }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { kept += __shfl_xor_sync(0xffffffffu, kept, d); dist += __shfl_xor_sync(0xffffffffu, dist, d); }
+        if ((threadIdx.x & 31) == 0 && kept) { atomicAdd(&s_red[0], kept); atomicAdd(&s_red[1], dist); }
+        __syncthreads();
+        if (threadIdx.x == 0) { bucket_kept[b] = s_red[0]; bucket_distinct[b] = s_red[1]; }
+        __syncthreads();
+    }
+}
+
+// Exclusive scan of the buckets' kept counts (in place) and the totals: out[0] = indexed positions, out[1] = distinct k-mers.
+__global__ void __launch_bounds__(1024)
+k_bucket_scan(uint32_t* __restrict__ bucket_kept, const uint32_t* __restrict__ bucket_distinct, uint32_t n, uint64_t* __restrict__ out)
+{
+    __shared__ uint32_t s_warp[33];
+    __shared__ unsigned long long s_d;
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t i0 = threadIdx.x * per, i1 = i0 + per < n ? i0 + per : n;
+    uint32_t s = 0;
+    unsigned long long d = 0;
+    for (uint32_t i = i0; i < i1; ++i) { s += bucket_kept[i]; d += bucket_distinct[i]; }
+    if (threadIdx.x == 0) s_d = 0;
+    uint32_t tot = 0;
+    uint32_t bs = block_scan_excl(s, s_warp, &tot);
+    for (uint32_t i = i0; i < i1; ++i) { const uint32_t c = bucket_kept[i]; bucket_kept[i] = bs; bs += c; }
+    if (d) atomicAdd(&s_d, d);
+    __syncthreads();
+    if (threadIdx.x == 0) { out[0] = tot; out[1] = s_d; bucket_kept[n] = tot; }
+}
+
+// ---- per bucket: the slice of the table, the positions run by run
+__global__ void __launch_bounds__(IDX_FILL_THREADS)
+k_bucket_fill(const uint2* __restrict__ pairs, const uint32_t* __restrict__ bbase, const uint32_t* __restrict__ kbase, IdxGeom G, uint32_t q,
+              uint32_t* __restrict__ tbl, uint32_t* __restrict__ offs, uint32_t* __restrict__ long_list, uint32_t* __restrict__ n_long)
+{
+    extern __shared__ __align__(16) uint32_t s_a[];             // [IDX_BUCKET] counts, then ends, then starts of the runs
+    __shared__ uint32_t s_drop[IDX_BUCKET / 32];                // bit: the k-mer occurs more than q times
+    __shared__ uint32_t s_warp[33];
+    const uint32_t per = IDX_BUCKET / IDX_FILL_THREADS;         // consecutive hash values of a thread in the scan: 32 = one word of s_drop
+    for (uint32_t b = blockIdx.x; b < G.n_buckets; b += gridDim.x) {
+        const uint32_t lo = bbase[b], hi = bbase[b + 1], kb = kbase[b], kept = kbase[b + 1] - kb;
+        const uint32_t h0 = b << IDX_LB;
+        const uint32_t nh = G.h_n - h0 < IDX_BUCKET ? G.h_n - h0 : IDX_BUCKET;
+        if (b == 0 && threadIdx.x == 0) tbl[0] = 0;
+        if (kept == 0) {                                        // nothing kept: the slice is flat
+            for (uint32_t i = threadIdx.x; i < nh; i += blockDim.x) tbl[(size_t)h0 + i + 1] = kb;
+            continue;
+        }
+        for (uint32_t i = threadIdx.x; i < IDX_BUCKET; i += blockDim.x) s_a[i] = 0;
+        __syncthreads();
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_a[pairs[i].x & (IDX_BUCKET - 1)], 1u);
+        __syncthreads();
+        {
+            const uint32_t i0 = threadIdx.x * per;
+            uint32_t drop = 0, sum = 0;
+            for (uint32_t j = 0; j < per; ++j) { const uint32_t c = s_a[i0 + j]; if (c > q) drop |= 1u << j; else sum += c; }
+            s_drop[threadIdx.x] = drop;
+            uint32_t run = block_scan_excl(sum, s_warp, NULL);
+            for (uint32_t j = 0; j < per; ++j) { const uint32_t c = s_a[i0 + j]; if (!((drop >> j) & 1)) run += c; s_a[i0 + j] = run; }     // end of the run
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nh; i += blockDim.x) tbl[(size_t)h0 + i + 1] = kb + s_a[i];
+        __syncthreads();
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const uint2 e = pairs[i];
+            const uint32_t hl = e.x & (IDX_BUCKET - 1);
+            if ((s_drop[hl >> 5] >> (hl & 31)) & 1) continue;
+            offs[kb + atomicSub(&s_a[hl], 1u) - 1] = e.y;       // the run fills from its end; s_a[hl] ends up as its start
+        }
+        __syncthreads();
+        // ascending positions inside every run (the reference gets them from scan order + a stable sort)
+        for (uint32_t i = threadIdx.x; i < IDX_BUCKET; i += blockDim.x) {
+            const uint32_t st = s_a[i], en = i + 1 < IDX_BUCKET ? s_a[i + 1] : kept;
+            const uint32_t n = en - st;
+            if (n < 2) continue;
+            if (n > LONG_RUN) { long_list[atomicAdd(n_long, 1u)] = h0 + i; continue; }
+            uint32_t* a = offs + kb + st;
+            for (uint32_t x = 1; x < n; ++x) {
+                const uint32_t v = a[x];
+                uint32_t y = x;
+                while (y > 0 && a[y - 1] > v) { a[y] = a[y - 1]; --y; }
+                a[y] = v;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -247,42 +387,84 @@ static int index_build_range(nb_ctx* ctx, const nb_volume* ref, int k, int q, ui
                              uint32_t** out_tbl, uint32_t** out_off, uint64_t* out_n_off, uint64_t* out_n_distinct)
 {
     cudaStream_t st = ctx->stream;
-    const uint64_t nh = h_n;
-    const uint32_t ntiles = (uint32_t)((nh + SCAN_TILE - 1) / SCAN_TILE);
-    uint32_t *d_cnt = NULL, *d_invalid = NULL, *d_tile = NULL, *d_tiled = NULL, *d_long = NULL, *d_nlong = NULL, *d_tbl = NULL, *d_off = NULL;
+    IdxGeom G;
+    memset(&G, 0, sizeof G);
+    G.h_lo = (uint32_t)h_lo; G.h_n = (uint32_t)h_n; G.k = k;
+    G.n_buckets = (uint32_t)((h_n + IDX_BUCKET - 1) >> IDX_LB);
+    if (G.n_buckets == 0) G.n_buckets = 1;
+    {
+        int tb = 0;                                             // bits of the bucket number
+        while ((1ull << tb) < G.n_buckets) ++tb;
+        const int t1 = tb < 8 ? tb : 8, t2 = tb - t1;           // tb <= 16
+        G.sh1 = IDX_LB + t2; G.nb1 = 1 << t1;
+        G.sh2 = IDX_LB; G.nb2 = 1 << t2;
+    }
+    const uint32_t nbk = (uint32_t)G.nb1 * (uint32_t)G.nb2;     // >= n_buckets; bucket = bin1 * nb2 + bin2
+    uint32_t *d_invalid = NULL, *d_hist1 = NULL, *d_base1 = NULL, *d_cur1 = NULL, *d_tile1 = NULL, *d_hist2 = NULL, *d_base2 = NULL, *d_cur2 = NULL;
+    uint32_t *d_kept = NULL, *d_dist = NULL, *d_long = NULL, *d_nlong = NULL, *d_tbl = NULL, *d_off = NULL;
+    uint2 *d_pa = NULL, *d_pb = NULL;
     uint64_t* d_tot = NULL;
     const uint64_t inv_words = ((ref->db_size + 31) >> 5) + 2;
     NbDevBuf B(ctx);
     {
         int rc;
-        if ((rc = B.get(&d_cnt, nh + 8))) return rc;
-        if ((rc = nb_dev_alloc(ctx, (void**)&d_tbl, sizeof(uint32_t) * (nh + 8)))) return rc;
+        if ((rc = nb_dev_alloc(ctx, (void**)&d_tbl, sizeof(uint32_t) * (h_n + 8)))) return rc;
         if ((rc = B.get(&d_invalid, inv_words))) return rc;
-        if ((rc = B.get(&d_tile, ntiles))) return rc;
-        if ((rc = B.get(&d_tiled, ntiles))) return rc;
+        if ((rc = B.get(&d_hist1, IDX_BINS))) return rc;
+        if ((rc = B.get(&d_base1, IDX_BINS + 1))) return rc;
+        if ((rc = B.get(&d_cur1, IDX_BINS))) return rc;
+        if ((rc = B.get(&d_tile1, IDX_BINS + 1))) return rc;
+        if ((rc = B.get(&d_hist2, nbk))) return rc;
+        if ((rc = B.get(&d_base2, nbk + 1))) return rc;
+        if ((rc = B.get(&d_cur2, nbk))) return rc;
+        if ((rc = B.get(&d_kept, nbk + 1))) return rc;
+        if ((rc = B.get(&d_dist, nbk))) return rc;
         if ((rc = B.get(&d_tot, 2))) return rc;
         if ((rc = B.get(&d_nlong, 1))) return rc;
+        if ((rc = B.get(&d_pa, ref->db_size + 16))) return rc;
+        if (G.nb2 > 1 && (rc = B.get(&d_pb, ref->db_size + 16))) return rc;
     }
-    NB_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * (nh + 8), st));
     NB_CUDA(ctx, cudaMemsetAsync(d_invalid, 0, sizeof(uint32_t) * inv_words, st));
+    NB_CUDA(ctx, cudaMemsetAsync(d_hist1, 0, sizeof(uint32_t) * IDX_BINS, st));
+    NB_CUDA(ctx, cudaMemsetAsync(d_hist2, 0, sizeof(uint32_t) * nbk, st));
     NB_CUDA(ctx, cudaMemsetAsync(d_nlong, 0, sizeof(uint32_t), st));
 
     const uint32_t* words = reinterpret_cast<const uint32_t*>(ref->d_pac);
     const uint64_t nchunk = (ref->db_size + 15) >> 4;
-    unsigned grid_scan = (unsigned)((nchunk + IDX_THREADS - 1) / IDX_THREADS);
-    if (grid_scan > NB_SMS * 32) grid_scan = NB_SMS * 32;
-    if (grid_scan == 0) grid_scan = 1;
+    const uint64_t ntile1 = (nchunk + IDX_THREADS - 1) / IDX_THREADS;
+    unsigned grid1 = (unsigned)(ntile1 < NB_SMS * 8 ? ntile1 : NB_SMS * 8);
+    if (grid1 == 0) grid1 = 1;
     if (ref->nseq) {
         k_mark_invalid<<<(unsigned)((ref->nseq + 255) / 256), 256, 0, st>>>(ref->d_off, ref->d_len, ref->nseq, k, d_invalid);
         NB_LAUNCH_CHECK(ctx);
     }
-    k_scan_kmers<false><<<grid_scan, IDX_THREADS, 0, st>>>(words, ref->db_size, d_invalid, k, d_cnt, NULL, NULL, (uint32_t)h_lo, (uint32_t)h_n);
+    k_part1_count<<<grid1, IDX_THREADS, 0, st>>>(words, ref->db_size, d_invalid, G, d_hist1);
     NB_LAUNCH_CHECK(ctx);
-    k_mask_reduce<<<ntiles, SCAN_THREADS, 0, st>>>(d_cnt, nh, (uint32_t)q, d_tile, d_tiled);
+    k_part_scan<<<1, 1024, 0, st>>>(d_hist1, (uint32_t)G.nb1, d_base1, d_cur1, d_tile1);
     NB_LAUNCH_CHECK(ctx);
-    k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(d_tile, d_tiled, ntiles, d_tot);
+    k_part1_scatter<<<grid1, IDX_THREADS, 0, st>>>(words, ref->db_size, d_invalid, G, d_cur1, d_pa);
     NB_LAUNCH_CHECK(ctx);
-    k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(d_cnt, nh, d_tile, d_tbl);
+    const uint2* d_pairs = d_pa;
+    const uint32_t* d_bbase = d_base1;
+    if (G.nb2 > 1) {
+        // every pass-1 bin is cut into tiles of IDX_TILE pairs: at most db_size / IDX_TILE + nb1 of them
+        const uint64_t max_tiles = ref->db_size / IDX_TILE + (uint64_t)G.nb1 + 1;
+        unsigned grid2 = (unsigned)(max_tiles < NB_SMS * 8 ? max_tiles : NB_SMS * 8);
+        k_part2_count<<<grid2, IDX_THREADS, 0, st>>>(d_pa, d_tile1, d_base1, G, (uint32_t)max_tiles, d_hist2);
+        NB_LAUNCH_CHECK(ctx);
+        k_part_scan<<<1, 1024, 0, st>>>(d_hist2, nbk, d_base2, d_cur2, NULL);
+        NB_LAUNCH_CHECK(ctx);
+        k_part2_scatter<<<grid2, IDX_THREADS, 0, st>>>(d_pa, d_tile1, d_base1, G, (uint32_t)max_tiles, d_cur2, d_pb);
+        NB_LAUNCH_CHECK(ctx);
+        d_pairs = d_pb; d_bbase = d_base2;
+    }
+    const size_t bsm = sizeof(uint32_t) * IDX_BUCKET;
+    NB_CUDA(ctx, cudaFuncSetAttribute(k_bucket_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    NB_CUDA(ctx, cudaFuncSetAttribute(k_bucket_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    const unsigned gridb = G.n_buckets < NB_SMS * 3 ? G.n_buckets : NB_SMS * 3;
+    k_bucket_count<<<gridb, IDX_FILL_THREADS, bsm, st>>>(d_pairs, d_bbase, G, (uint32_t)q, d_kept, d_dist);
+    NB_LAUNCH_CHECK(ctx);
+    k_bucket_scan<<<1, 1024, 0, st>>>(d_kept, d_dist, G.n_buckets, d_tot);
     NB_LAUNCH_CHECK(ctx);
     uint64_t tot[2];
     NB_CUDA(ctx, cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
@@ -292,11 +474,7 @@ static int index_build_range(nb_ctx* ctx, const nb_volume* ref, int k, int q, ui
         if ((rc = nb_dev_alloc(ctx, (void**)&d_off, sizeof(uint32_t) * (tot[0] + 16)))) return rc;
         if ((rc = B.get(&d_long, tot[0] / LONG_RUN + 16))) return rc;
     }
-    k_scan_kmers<true><<<grid_scan, IDX_THREADS, 0, st>>>(words, ref->db_size, d_invalid, k, d_cnt, d_tbl, d_off, (uint32_t)h_lo, (uint32_t)h_n);
-    NB_LAUNCH_CHECK(ctx);
-    unsigned grid_h = (unsigned)((nh + IDX_THREADS - 1) / IDX_THREADS);
-    if (grid_h > NB_SMS * 64) grid_h = NB_SMS * 64;
-    k_sort_short_runs<<<grid_h, IDX_THREADS, 0, st>>>(d_tbl, nh, d_off, d_long, d_nlong);
+    k_bucket_fill<<<gridb, IDX_FILL_THREADS, bsm, st>>>(d_pairs, d_bbase, d_kept, G, (uint32_t)q, d_tbl, d_off, d_long, d_nlong);
     NB_LAUNCH_CHECK(ctx);
     uint32_t n_long = 0;
     NB_CUDA(ctx, cudaMemcpyAsync(&n_long, d_nlong, sizeof n_long, cudaMemcpyDeviceToHost, st));
