@@ -82,18 +82,53 @@ inline double ident_of(const nb_alignment& a) { return a.aln_size ? 100.0 * a.n_
 
 inline bool is_used(const Tpl& t, int qid) { for (int u : t.used) if (u == qid) return true; return false; }
 inline void set_used(Tpl& t, int qid) { if (!is_used(t, qid)) t.used.push_back(qid); }
+// The two per-base loops of the replay (2 G coverage increments on the E. coli-size set): plain loops the compiler turns
+// into 16-lane AVX2 code where the host has it (chosen once, at load time), scalar otherwise.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__CUDA_ARCH__)
+#define NB_SIMD_TARGET __attribute__((target("avx2"), optimize("O3")))
+#else
+#define NB_SIMD_TARGET
+#endif
+static int cov_add_plain(uint16_t* c, int n, int max_cov) { int r = 0; for (int i = 0; i < n; ++i) r += (++c[i] == max_cov); return r; }
+static int cov_below_plain(const uint16_t* c, int n, int max_cov) { for (int i = 0; i < n; ++i) if (c[i] < max_cov) return 1; return 0; }
+NB_SIMD_TARGET static int cov_add_simd(uint16_t* __restrict__ c, int n, int max_cov)
+{
+    const uint16_t m = (uint16_t)max_cov;
+    int r = 0;
+    for (int i = 0; i < n; ++i) { const uint16_t v = (uint16_t)(c[i] + 1); c[i] = v; r += v == m; }
+    return r;
+}
+NB_SIMD_TARGET static int cov_below_simd(const uint16_t* __restrict__ c, int n, int max_cov)
+{
+    int i = 0;
+    for (; i + 64 <= n; i += 64) {                  // whole 64-base pieces without an early exit inside: they vectorise
+        int any = 0;
+        for (int k = 0; k < 64; ++k) any |= c[i + k] < max_cov;
+        if (any) return 1;
+    }
+    for (; i < n; ++i) if (c[i] < max_cov) return 1;
+    return 0;
+}
+static bool host_has_avx2()
+{
+#if defined(__x86_64__) && defined(__GNUC__)
+    return __builtin_cpu_supports("avx2");
+#else
+    return false;
+#endif
+}
+static int (*const cov_add)(uint16_t*, int, int) = host_has_avx2() ? cov_add_simd : cov_add_plain;
+static int (*const cov_below)(const uint16_t*, int, int) = host_has_avx2() ? cov_below_simd : cov_below_plain;
+
 inline bool cov_full(const Tpl& t, int from, int to, int max_cov)   // consensus_one_read.c:139-145
 {
-    for (int i = from; i < to; ++i) if (t.cov[i] < max_cov) return false;
-    return true;
+    return to <= from || !cov_below(t.cov.data() + from, to - from, max_cov);
 }
 inline void accept(Tpl& t, size_t ci, const nb_alignment& a, int max_cov)
 {
     Accepted ac; ac.can = (int)ci; ac.weight = cns_weight(ident_of(a));
     t.acc.push_back(ac);
-    int reached = 0;
-    for (int i = a.toff; i < a.tend; ++i) reached += (++t.cov[i] == max_cov);
-    t.n_below -= reached;
+    if (a.tend > a.toff) t.n_below -= cov_add(t.cov.data() + a.toff, a.tend - a.toff, max_cov);
 }
 
 // Replays consensus_one_read for one template as far as the available extension results allow.
@@ -727,14 +762,20 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                         NB_LAUNCH_CHECK(cx);
                         k_cns_fix<<<(unsigned)((Q.n_units + 127) / 128), 128, 0, ss>>>(Q);
                         NB_LAUNCH_CHECK(cx);
+                        g = (unsigned)((Q.n_units + 3) / 4);
+                        if (g > NB_SMS * 16) g = NB_SMS * 16;
+                        k_cns_plan<<<g, 128, 0, ss>>>(Q);
+                        NB_LAUNCH_CHECK(cx);
                     }
-                    // one lane per template, 32 templates per CTA; sorted by length, the longest start first
+                    // sixteen templates per CTA (8 lanes each); sorted by length, the longest start first
                     if (kDpTest == 1) {
-                        const size_t dsm = (size_t)32 * (16 * CNS_DP_LR + 8 * 8);
-                        k_cns_dp<8><<<(n_tpl + 31) / 32, 32, dsm, ss>>>(Q);
+                        const size_t dsm = (size_t)16 * (16 * 128 + 8 * 8);
+                        NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+                        k_cns_dp<128, 8><<<(n_tpl + 15) / 16, 128, dsm, ss>>>(Q);
                     } else {
-                        const size_t dsm = (size_t)32 * (16 * CNS_DP_LR + 8 * 128);
-                        k_cns_dp<128><<<(n_tpl + 31) / 32, 32, dsm, ss>>>(Q);
+                        const size_t dsm = (size_t)16 * (16 * 128 + 8 * 128);
+                        NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+                        k_cns_dp<128, 128><<<(n_tpl + 15) / 16, 128, dsm, ss>>>(Q);
                     }
                     NB_LAUNCH_CHECK(cx);
                     k_cns_dp_serial<<<(n_tpl + 127) / 128, 128, 0, ss>>>(Q);

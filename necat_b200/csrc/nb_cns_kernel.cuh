@@ -685,155 +685,419 @@ __device__ __forceinline__ uint32_t cns_bp_code(uint32_t key)       // back poin
     return (((key >> 24) == 0 ? (rank - 1 - cns_char_rank(pb)) / 5u : 0u) << 3) | pb;
 }
 
+// ------------------------------------------------------------------ what k_cns_dp reads
+// k_cns_links / k_cns_fix leave every link as (key, index of the predecessor node's first link, weight).  k_cns_plan
+// turns the first two words, in place, into what the recurrence needs and nothing else, so that k_cns_dp -- one
+// dependent chain per template -- spends no instruction on decoding:
+//   ctl   bits 0-2 base | 3 node start | 4-6 links of the node - 1 | 7-8 level inside its trip | 9 first link of a trip |
+//         10-12 links of the trip - 1 | 13-14 levels of the trip - 1 | 15-17 longest node of the trip - 1 |
+//         18 first link of a position | 19 ... of a run | 20 ... of the last position of a run | 21 first link of a level |
+//         22 the level has more than 8 links (it is a trip by itself and scored link by link)
+//   aux   bits 0-15 dense distance back to the predecessor node's first link (0: none) | 16-26 the back pointer this
+//         link stands for | 27-31 its rank inside the node (ties between equal scores go to the lower)
+// A trip is what one pass of k_cns_dp's loop takes: whole levels of one position, at most 8 links and 4 levels.
+// One thread per position.
+#define CNS_C_NODE   (1u << 3)
+#define CNS_C_TRIP   (1u << 9)
+#define CNS_C_POS    (1u << 18)
+#define CNS_C_RUN0   (1u << 19)
+#define CNS_C_RUNZ   (1u << 20)
+#define CNS_C_LEVEL  (1u << 21)
+#define CNS_C_LONG   (1u << 22)
+
+__global__ void __launch_bounds__(128)
+k_cns_plan(CnsParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwarp = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t ui = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ui < P.n_units; ui += nwarp) {
+        const CnsUnit U = P.unit[ui];
+        const CnsTemplate TP = P.tpl0[U.tpl];
+        const CnsPos* pos = P.pos + TP.pos_base;
+        uint4* link = reinterpret_cast<uint4*>(P.link + TP.link_base);
+        const int s0 = (int)U.span * P.span, s1 = (s0 + P.span < TP.T) ? s0 + P.span : TP.T;
+        for (int t = s0 + lane; t < s1; t += 32) {
+            const CnsPos ps = pos[t];
+            const uint32_t n = ps.n;
+            if (n == 0) continue;
+            // the dense stream of the template has the previous position's links right before this one's
+            uint32_t pv_end = 0;
+            if (t > 0) { const CnsPos pv = pos[t - 1]; pv_end = pv.start + pv.n; }
+            const uint32_t x0 = ps.start;
+            unsigned long long NS = 0, LS = 0;              // node starts, level starts (n <= 64)
+            // ---- pass 1: aux of every link; the boundaries
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint4 e = link[x0 + i];
+                const uint32_t key = e.x, pred = e.y;
+                if (n <= 64) { if (key & CNS_K_NODE) NS |= 1ull << i; if (key & CNS_K_LEVEL) LS |= 1ull << i; }
+                uint32_t dist = 0;
+                if (pred != CNS_NOPRED) dist = (key >> 24) ? x0 + i - pred : i + (pv_end - pred);
+                if (dist >= 0xf000u) { atomicOr(P.error_flag, 2u); dist = 0; }
+                // rank inside the node: links of the node with a lower predecessor rank
+                uint32_t prio = 0;
+                {
+                    const uint32_t nid = (key >> 20) & 0xff7u, rk = CNS_K_RANK(key);
+                    for (uint32_t j = i; j-- > 0;) {
+                        const uint32_t kj = link[x0 + j].x;
+                        if (((kj >> 20) & 0xff7u) != nid) break;
+                        prio += CNS_K_RANK(kj) < rk;
+                    }
+                    for (uint32_t j = i + 1; j < n; ++j) {
+                        const uint32_t kj = link[x0 + j].x;
+                        if (((kj >> 20) & 0xff7u) != nid) break;
+                        prio += CNS_K_RANK(kj) < rk;
+                    }
+                }
+                if (prio > 31) prio = 31;
+                link[x0 + i].y = dist | (cns_bp_code(key) << 16) | (prio << 27);
+            }
+            // ---- pass 2: ctl of every link
+            const uint32_t posflags = CNS_C_POS | ((ps.flags & 2) ? CNS_C_RUN0 : 0u) | ((ps.flags & 4) ? CNS_C_RUNZ : 0u);
+            if (n > 64) {
+                // a very crowded position: every level is scored link by link
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint32_t key = link[x0 + i].x;
+                    uint32_t c = (key >> 20) & 7u;
+                    if (key & CNS_K_NODE) c |= CNS_C_NODE;
+                    if (key & CNS_K_LEVEL) c |= CNS_C_LEVEL | CNS_C_TRIP | CNS_C_LONG;
+                    if (i == 0) c |= posflags;
+                    link[x0 + i].x = c;
+                }
+                continue;
+            }
+            uint32_t i = 0;
+            while (i < n) {
+                // a trip starts at level start i: whole levels while they fit 8 links and 4 levels
+                uint32_t j = i, nlev = 0, maxnode = 1;
+                bool lng = false;
+                for (;;) {
+                    // the level that starts at j ends at the next level start
+                    const unsigned long long rest = LS >> (j + 1);
+                    const uint32_t le = rest ? j + 1 + (uint32_t)__ffsll((long long)rest) - 1 : n;
+                    if (le - i > 8 || nlev == 4) { if (nlev == 0) { lng = true; j = le; nlev = 1; } break; }
+                    j = le; ++nlev;
+                    if (j >= n) break;
+                }
+                // links [i, j) are the trip
+                if (!lng) {
+                    for (uint32_t a = i; a < j;) {          // longest node
+                        const unsigned long long rest = NS >> (a + 1);
+                        uint32_t ne = rest ? a + 1 + (uint32_t)__ffsll((long long)rest) - 1 : n;
+                        if (ne > j) ne = j;
+                        if (ne - a > maxnode) maxnode = ne - a;
+                        a = ne;
+                    }
+                }
+                uint32_t lv = 0;
+                for (uint32_t a = i; a < j; ++a) {
+                    const uint32_t key = link[x0 + a].x;
+                    uint32_t c = (key >> 20) & 7u;
+                    if (a > i && ((LS >> a) & 1)) ++lv;
+                    if ((NS >> a) & 1) {
+                        const unsigned long long rest = NS >> (a + 1);
+                        uint32_t ne = rest ? a + 1 + (uint32_t)__ffsll((long long)rest) - 1 : n;
+                        if (ne > j) ne = j;
+                        uint32_t nl = ne - a; if (nl > 8) nl = 8;
+                        c |= CNS_C_NODE | ((nl - 1) << 4);
+                    }
+                    if ((LS >> a) & 1) c |= CNS_C_LEVEL;
+                    c |= (lng ? 0u : lv) << 7;
+                    if (a == i) {
+                        c |= CNS_C_TRIP;
+                        if (lng) c |= CNS_C_LONG;
+                        else c |= ((j - i - 1) << 10) | ((nlev - 1) << 13) | ((maxnode - 1) << 15);
+                        if (i == 0) c |= posflags;
+                    }
+                    link[x0 + a].x = c;
+                }
+                i = j;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ best path
 __device__ __forceinline__ void cns_cp_async16(void* dst_smem, const void* src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(nb_smem_addr(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cns_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-#define CNS_DP_LR 16                // links of a template staged ahead of the recurrence (a ring in shared memory)
-__device__ __forceinline__ void cns_cp_async_wait_ring() { asm volatile("cp.async.wait_group 15;" ::: "memory"); }   // CNS_DP_LR - 1 groups may stay in flight
-__device__ __forceinline__ void cns_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cns_cp_async_wait(int pending)      // at most `pending` (0 or CNS_DP_PEND) groups stay in flight
+{
+    if (pending <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.wait_group 6;" ::: "memory");
+}
+#define CNS_DP_PEND 6
 
-// The recurrence (cns_aux.c:157-184) is one dependent chain per template: link after link, every score needs the score
-// of a node that closed a few links earlier.  Nothing inside a template runs side by side, so the kernel gives every
-// template ONE lane and makes the step of that chain as short as it can be: no collective, no shuffle, no position or
-// plan record -- a lane walks the dense link stream k_cns_links / k_cns_fix left (key, first link of the predecessor
-// node, weight), 32 templates per warp in a flat loop of one link per trip:
-//   * the links come through a per-lane ring in shared memory, CNS_DP_LR - 1 links ahead (one 16-byte cp.async per lane
-//     and trip, one commit per trip: the cadence is the same in every lane whatever its template does);
-//   * node scores live in a per-lane ring in shared memory indexed by the dense number of the node's first link
-//     (a predecessor is a node of this or of the previous position: the ring misses only where two neighbouring
-//     positions hold more than SR links; such a template is handed to k_cns_dp_serial);
-//   * node / level / position / run boundaries are bits of the key (a position starts with its delta-0 level); the
-//     links of a node compete in stream order, ties between equal scores go to the lower predecessor rank = the one
-//     the reference meets first (cns_aux.c:166); the best node of a run is the first one with the highest score.
-// Both ring layouts are [slot][lane]: whatever slot a lane is at, the 32 lanes hit 32 different bank groups.
-template <int SR>
-__global__ void __launch_bounds__(32)
+
+// Eight lanes per template, four templates per warp, all in lock step.  The recurrence is a chain over the delta levels
+// of a template, so what decides the kernel's duration is how few instructions one step of that chain takes for the
+// longest template.  One trip of the loop takes the next trip of every template of the warp (k_cns_plan: whole levels
+// of one position, at most 8 links, lane = link) and walks its levels:
+//   * the links of a template are a dense stream per span (k_cns_links): they are staged through a ring in shared
+//     memory with cp.async, LR links ahead; everything the trip needs to know about them is in their two control
+//     words, no position record is read and nothing is decoded from keys;
+//   * a predecessor scored in an earlier trip comes from a ring of node scores in shared memory, indexed by the dense
+//     sequence number of the node's first link (a predecessor is a node of this or of the previous position: the ring
+//     misses only where two neighbouring positions hold more than SR links, and such a template is handed to
+//     k_cns_dp_serial); a predecessor inside the trip comes from its lane by shuffle;
+//   * the links of a node are adjacent lanes: maximum by shuffles (ties to the lower rank); every node stores its own
+//     back pointer into the level record, the best node of a run is tracked per lane and reduced when the run has
+//     ended (ties to the lowest link = the first one in the reference's traversal order);
+//   * ONE warp-wide OR per trip carries everything the four templates have to agree on: the number of level steps,
+//     the longest node, and whether anything rare is due (a run ended, a level of more than 8 links, the staging ring
+//     has to catch up, a span of the stream ended, all templates finished).
+#define CNS_DP_G 8
+#define CNS_EV_NOTDONE (1u << 12)
+#define CNS_EV_EMIT    (1u << 13)
+#define CNS_EV_LONG    (1u << 14)
+#define CNS_EV_UNSURE  (1u << 15)
+#define CNS_EV_SPAN    (1u << 16)
+
+template <int LR, int SR>
+__global__ void __launch_bounds__(128)
 k_cns_dp(CnsParams P)
 {
     extern __shared__ __align__(16) uint8_t dp_smem[];
-    const int lane = threadIdx.x;
-    uint4* LK = reinterpret_cast<uint4*>(dp_smem) + lane;
-    double* SC = reinterpret_cast<double*>(dp_smem + (size_t)16 * 32 * CNS_DP_LR) + lane;
-    const uint32_t slot = blockIdx.x * 32 + lane;
-    bool live = slot < P.n_tpl;
-    const uint32_t ti = live ? slot : 0;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gl = lane & (CNS_DP_G - 1), grp = lane >> 3;
+    const uint32_t slot = (blockIdx.x * 4 + wid) * 4 + grp;
+    uint4* LK = reinterpret_cast<uint4*>(dp_smem) + (size_t)(wid * 4 + grp) * LR;
+    double* SC = reinterpret_cast<double*>(dp_smem + (size_t)16 * 16 * LR) + (size_t)(wid * 4 + grp) * SR;
+    bool done = slot >= P.n_tpl;
+    const uint32_t ti = done ? 0 : slot;
     const CnsTemplate TP = P.tpl[ti];
-    const uint4* __restrict__ link = reinterpret_cast<const uint4*>(P.link + TP.link_base);
+    const CnsLink* __restrict__ link = P.link + TP.link_base;
     uint4* bp = reinterpret_cast<uint4*>(P.bp + TP.level_base);
     uint16_t* bp16 = reinterpret_cast<uint16_t*>(bp);
     CnsRun* my_runs = P.runs + TP.seg_first;
     const uint2* __restrict__ spans = P.span_links + TP.unit_first;
     const int n_spans = (TP.T + P.span - 1) / P.span;
-    const uint32_t n_runs = live ? P.tpl_nrun[ti] : 0;
-    bool redo = false;
-    if (live && P.dp_serial) { redo = true; live = false; }
-    // consumer (x) and fetch (f) cursors over the link stream: link indices inside the current span, dense numbers
+    const uint32_t n_runs = done ? 0 : P.tpl_nrun[ti];
+    // consumer / producer cursors over the link stream
     int ck = -1, fk = -1;
-    uint32_t x = 0, x_end = 0, seq = 0, f = 0, f_end = 0, fseq = 0;
+    uint32_t c = 0, c_end = 0, seq = 0, f = 0, f_end = 0, fseq = 0;
     auto next_span = [&](int& k, uint32_t& a, uint32_t& a_end) {
         while (a == a_end && k < n_spans) {
             ++k;
             if (k < n_spans) { const uint2 e = spans[k]; a = e.x; a_end = e.x + e.y; }
         }
     };
-    if (live) { next_span(ck, x, x_end); fk = ck; f = x; f_end = x_end; if (ck >= n_spans) live = false; }
-    if (!live) fk = n_spans;
-    auto fetch = [&]() {
-        if (fk < n_spans) {
-            cns_cp_async16(LK + (fseq & (CNS_DP_LR - 1)) * 32, link + f);
-            ++f; ++fseq;
-            if (f == f_end) next_span(fk, f, f_end);
-        }
-        cns_cp_async_commit();
-    };
-#pragma unroll 1
-    for (int i = 0; i < CNS_DP_LR - 1; ++i) fetch();
-    uint32_t smx = 0u - x;                          // dense number - link index, of the span being consumed
-    uint32_t pos_x0 = x, pos_smx = smx, pv_smx = smx;   // first link of the current position; smx of it and of the previous position
+    bool redo = false;
+    if (!done && P.dp_serial) { redo = true; done = true; }
+    if (!done) { next_span(ck, c, c_end); fk = ck; f = c; f_end = c_end; if (ck >= n_spans) done = true; }
     uint32_t level = 0, cur_fl = 0, prev_fl = 0, run_started = 0, run_emitted = 0, fail = 0;
     int t = 0;
-    bool p_last = false, have_node = false, chosen = false;
-    uint32_t cur_b = 0, node_seq = 0, best_key = 0;
-    double best = -1.0, g_best = -1.0;
-    int g_level = -1, g_b = -1, g_t = 0, g_delta = 0;
-    auto close_node = [&]() {
-        const double ns = chosen ? best : -1.0;
-        SC[(node_seq & (SR - 1)) * 32] = ns;
-        if (level < TP.level_cap) bp16[(size_t)level * 8 + cur_b] = (uint16_t)(chosen ? cns_bp_code(best_key) : 7u);
-        else fail |= 1;
-        if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)(level - cur_fl); }
+    bool p_last = false, pend_emit = false, pend_long = false, pend_span = false, unsure = !done;
+    // best node of the current run, per lane; and of the run that has just ended (emitted at the top of the next trip)
+    double g_best = -1.0, e_best = -1.0;
+    int g_level = -1, g_b = -1, g_t = 0, g_delta = 0, e_level = -1, e_b = -1, e_t = 0, e_delta = 0, e_end = 0;
+    uint32_t g_x = 0xffffffffu, e_x = 0xffffffffu;
+    uint32_t ev = CNS_EV_UNSURE | CNS_EV_NOTDONE;           // what the previous trip's OR announced
+    auto issue = [&]() {
+        const uint32_t nb = f_end - f < CNS_DP_G ? f_end - f : CNS_DP_G;
+        if ((uint32_t)gl < nb) cns_cp_async16(LK + ((fseq + gl) & (LR - 1)), link + f + gl);
+        f += nb; fseq += nb;
+        if (f == f_end) next_span(fk, f, f_end);
     };
-    auto close_level = [&]() {
-        if (level < TP.level_cap) bp[level].w = prev_fl; else fail |= 1;
-        ++level;
+    auto snapshot = [&]() {
+        pend_emit = true;
+        e_best = g_best; e_level = g_level; e_b = g_b; e_t = g_t; e_delta = g_delta; e_x = g_x; e_end = t;
     };
-    auto emit_run = [&]() {                         // the best node of the run that ended (cns_aux.c:177-184)
-        if (run_emitted < n_runs) {
-            CnsRun r = my_runs[run_emitted];        // from and first_level were written at the run's start
-            r.to = t + 1; r.g_level = g_level; r.g_b = g_b; r.g_t = g_t; r.g_delta = g_delta;
-            my_runs[run_emitted] = r;
+    for (;;) {
+        // ---- a span of the stream ended with the previous trip
+        if ((ev & CNS_EV_SPAN) && pend_span) {
+            next_span(ck, c, c_end);
+            if (ck >= n_spans) done = true;
+            pend_span = false;
         }
-        ++run_emitted;
-    };
-    while (live) {
-        fetch();
-        cns_cp_async_wait_ring();
-        const uint4 e = LK[(seq & (CNS_DP_LR - 1)) * 32];
-        const uint32_t key = e.x, pred = e.y;
-        const double w = __hiloint2double((int)e.w, (int)e.z);
-        if (key & CNS_K_NODE) {
-            if (have_node) close_node();
-            if (key & CNS_K_LEVEL) {
-                if (have_node) close_level();
-                if ((key >> 24) == 0) {
-                    // a position starts with its delta-0 level
-                    if (p_last) emit_run();
-                    prev_fl = cur_fl; cur_fl = level;
-                    if (key & CNS_K_RUNFIRST) {
-                        t = run_started < n_runs ? my_runs[run_started].from : 0;
-                        g_best = -1.0; g_level = -1; g_b = -1;
-                        if (run_started < n_runs) my_runs[run_started].first_level = level;
-                        ++run_started;
-                    } else ++t;
-                    p_last = (key & CNS_K_RUNLAST) != 0;
-                    pv_smx = pos_smx; pos_smx = smx; pos_x0 = x;
+        // ---- staging: keep the ring full
+        if (!done && fseq - seq <= (uint32_t)(LR - CNS_DP_G) && f < f_end) issue();
+        cns_cp_async_commit();
+        if (ev & CNS_EV_UNSURE) {
+            if (unsure && !done) {
+                const uint32_t left = c_end - c;
+                const uint32_t need = seq + (left < CNS_DP_G + 1 ? left : CNS_DP_G + 1);
+                while (fseq < need && f < f_end) issue();
+            }
+            cns_cp_async_commit();
+            cns_cp_async_wait(0);
+        } else cns_cp_async_wait(CNS_DP_PEND);
+        __syncwarp();
+        if (ev & (CNS_EV_EMIT | CNS_EV_LONG)) {
+            if (ev & CNS_EV_EMIT) {
+                // the best node of the run that ended (cns_aux.c:177-184): highest score, first in traversal order
+                double mx = e_best;
+#pragma unroll
+                for (int d = 4; d > 0; d >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, mx, d, CNS_DP_G); mx = o > mx ? o : mx; }
+                uint32_t mnx = e_best == mx ? e_x : 0xffffffffu;
+#pragma unroll
+                for (int d = 4; d > 0; d >>= 1) { const uint32_t o = __shfl_xor_sync(0xffffffffu, mnx, d, CNS_DP_G); mnx = o < mnx ? o : mnx; }
+                const uint32_t win = (__ballot_sync(0xffffffffu, e_best == mx && e_x == mnx) >> (grp * CNS_DP_G)) & 0xffu;
+                const int wl = win ? __ffs(win) - 1 : 0;
+                const int r_level = __shfl_sync(0xffffffffu, e_level, wl, CNS_DP_G), r_b = __shfl_sync(0xffffffffu, e_b, wl, CNS_DP_G);
+                const int r_t = __shfl_sync(0xffffffffu, e_t, wl, CNS_DP_G), r_delta = __shfl_sync(0xffffffffu, e_delta, wl, CNS_DP_G);
+                if (pend_emit) {
+                    if (gl == 0 && run_emitted < n_runs) {
+                        CnsRun r = my_runs[run_emitted];                // from and first_level were written at the run's start
+                        r.to = e_end + 1; r.g_level = r_level; r.g_b = r_b; r.g_t = r_t; r.g_delta = r_delta;
+                        my_runs[run_emitted] = r;
+                    }
+                    ++run_emitted;
+                    pend_emit = false;
                 }
             }
-            have_node = true; cur_b = (key >> 20) & 7u; node_seq = seq; best = -1.0; chosen = false;
+            if (ev & CNS_EV_LONG) {
+                // ---- a level of more than 8 links: the group's first lane scores it link by link, straight from HBM
+                if (pend_long && gl == 0) {
+                    bool have_node = false, chosen = false;
+                    uint32_t cur_b = 0, node_first = 0, best_aux = 0, x = c, xs = seq;
+                    double best = -1.0;
+                    auto close_node = [&]() {
+                        const double ns = chosen ? best : -1.0;
+                        SC[node_first & (SR - 1)] = ns;
+                        if (level < TP.level_cap) bp16[(size_t)level * 8 + cur_b] = (uint16_t)(chosen ? (best_aux >> 16) & 0x7ffu : 7u);
+                        if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)(level - cur_fl); g_x = node_first; }
+                    };
+                    for (; x < c_end; ++x, ++xs) {
+                        const uint4 e = *reinterpret_cast<const uint4*>(link + x);
+                        if (x != c && (e.x & CNS_C_LEVEL)) break;
+                        if (e.x & CNS_C_NODE) {
+                            if (have_node) close_node();
+                            have_node = true; cur_b = e.x & 7u; node_first = xs; best = -1.0; best_aux = 0; chosen = false;
+                        }
+                        double sc = __hiloint2double((int)e.w, (int)e.z);
+                        const uint32_t dist = e.y & 0xffffu;
+                        if (dist) {
+                            if (dist >= (uint32_t)SR) redo = true;
+                            sc = __dadd_rn(sc, SC[(xs - dist) & (SR - 1)]);
+                        }
+                        const bool better = chosen ? (sc > best || (sc == best && (e.y >> 27) < (best_aux >> 27))) : (sc > -1.0);
+                        if (better) { best = sc; best_aux = e.y; chosen = true; }
+                    }
+                    if (have_node) close_node();
+                    if (level < TP.level_cap) bp[level].w = prev_fl; else fail |= 1;
+                    c = x; seq = xs;
+                }
+                const uint32_t c2 = __shfl_sync(0xffffffffu, c, 0, CNS_DP_G), s2 = __shfl_sync(0xffffffffu, seq, 0, CNS_DP_G);
+                const int r2 = __shfl_sync(0xffffffffu, (int)redo, 0, CNS_DP_G);
+                if (pend_long) {
+                    c = c2; seq = s2; redo = r2 != 0;
+                    ++level;
+                    pend_long = false;
+                    if (c == c_end) { next_span(ck, c, c_end); if (ck >= n_spans) done = true; }
+                    if (redo) done = true;
+                    // the staging ring starts over behind the level
+                    if (fseq < seq || fk != ck) { fk = ck; f = c; f_end = c_end; fseq = seq; }
+                    if (!done) {
+                        const uint32_t left = c_end - c;
+                        const uint32_t need = seq + (left < CNS_DP_G + 1 ? left : CNS_DP_G + 1);
+                        while (fseq < need && f < f_end) issue();
+                    }
+                }
+                cns_cp_async_commit();
+                cns_cp_async_wait(0);
+                __syncwarp();
+            }
+            if (done && p_last && !redo && !pend_emit) { snapshot(); p_last = false; }
         }
-        double sc = w;
-        if (pred != CNS_NOPRED) {                    // never-scored predecessors count 0 (cns_aux.c:63-70)
-            const uint32_t ps = pred + (pred >= pos_x0 ? pos_smx : pv_smx);     // dense number of the predecessor node's first link
-            if (seq - ps >= (uint32_t)SR) { redo = true; live = false; }
-            sc = __dadd_rn(w, SC[(ps & (SR - 1)) * 32]);
+        // ---- the next trip of the stream
+        uint32_t hdr = 0;
+        uint4 me = make_uint4(0, 0, 0, 0);
+        if (!done) { hdr = LK[seq & (LR - 1)].x; me = LK[(seq + gl) & (LR - 1)]; }
+        const bool lng = (hdr & CNS_C_LONG) != 0;
+        const int take = (done || lng) ? 0 : (int)((hdr >> 10) & 7u) + 1;
+        const int nlev = take ? (int)((hdr >> 13) & 3u) + 1 : 0;
+        if (lng) pend_long = true;
+        // ---- position / run bookkeeping (uniform inside the group)
+        if (hdr & CNS_C_POS) {
+            if (p_last) snapshot();                                         // the previous position ended a run
+            prev_fl = cur_fl; cur_fl = level;
+            if (hdr & CNS_C_RUN0) {
+                t = run_started < n_runs ? my_runs[run_started].from : 0;
+                g_best = -1.0; g_level = -1; g_x = 0xffffffffu;
+                if (gl == 0 && run_started < n_runs) my_runs[run_started].first_level = level;
+                ++run_started;
+            } else ++t;
+            p_last = (hdr & CNS_C_RUNZ) != 0;
         }
-        const bool better = chosen ? (sc > best || (sc == best && CNS_K_RANK(key) < CNS_K_RANK(best_key))) : (sc > -1.0);
-        if (better) { best = sc; best_key = key; chosen = true; }
-        ++x; ++seq;
-        if (x == x_end) {
-            next_span(ck, x, x_end);
-            if (ck >= n_spans) live = false;
-            smx = seq - x;
+        const bool in = gl < take;
+        // ---- what the templates of the warp have to agree on
+        {
+            const uint32_t c_next = c + (uint32_t)take, left = c_end - c_next;
+            const bool span_end = take > 0 && c_next == c_end;
+            const bool unsure_next = !done && seq + (uint32_t)take + (left < CNS_DP_G + 1 ? left : CNS_DP_G + 1) + CNS_DP_G * CNS_DP_PEND > fseq;
+            uint32_t bits = 0;
+            if (take) bits |= (1u << (nlev - 1)) | (1u << (4 + ((hdr >> 15) & 7u)));
+            if (!done) bits |= CNS_EV_NOTDONE;
+            if (pend_emit) bits |= CNS_EV_EMIT | CNS_EV_NOTDONE;
+            if (pend_long) bits |= CNS_EV_LONG;
+            if (unsure_next || span_end) bits |= CNS_EV_UNSURE;
+            if (span_end) { bits |= CNS_EV_SPAN; pend_span = true; }
+            if (done && p_last && !redo && !pend_emit) { snapshot(); p_last = false; bits |= CNS_EV_EMIT | CNS_EV_NOTDONE; }
+            unsure = unsure_next || span_end;
+            ev = __reduce_or_sync(0xffffffffu, bits);
         }
+        if (!(ev & CNS_EV_NOTDONE)) break;
+        const int maxlev = 32 - __clz((int)(ev & 0xfu)), extra = 31 - __clz((int)(((ev >> 4) & 0xffu) | 1u));
+        // ---- predecessors scored in earlier trips come from the ring, those of this trip from their lane
+        const uint32_t dist = me.y & 0xffffu;
+        const bool has_pred = in && dist != 0;                              // never-scored predecessors count 0 (cns_aux.c:63-70)
+        const bool in_trip = has_pred && dist <= (uint32_t)gl;
+        const double base = __hiloint2double((int)me.w, (int)me.z);
+        double rs = 0.0;
+        if (has_pred && !in_trip) {
+            if (dist >= (uint32_t)SR) redo = true;
+            rs = SC[(seq + gl - dist) & (SR - 1)];
+        }
+        const int src = in_trip ? gl - (int)dist : 0;
+        const bool isstart = in && (me.x & CNS_C_NODE);
+        const int nend = gl + (int)((me.x >> 4) & 7u) + 1;                  // my node ends here (meaningful in its first lane)
+        const int mylev = (int)((me.x >> 7) & 3u);
+        const uint32_t kp = me.y >> 16;                                     // back pointer (11 bits) | rank inside the node << 11
+        double nsc = -1.0, sc = base;
+        uint32_t bkp = kp;
+        for (int lv = 0; lv < maxlev; ++lv) {
+            const double from = __shfl_sync(0xffffffffu, nsc, src, CNS_DP_G);
+            const bool act = in && mylev == lv;
+            if (act && has_pred) sc = __dadd_rn(base, in_trip ? from : rs);
+            // the links of a node are adjacent lanes of one level
+            double best = sc;
+            uint32_t bk = kp;
+            bool chosen = act && sc > -1.0;
+            for (int k = 1; k <= extra; ++k) {
+                const double osc = __shfl_down_sync(0xffffffffu, sc, k, CNS_DP_G);
+                const uint32_t okp = __shfl_down_sync(0xffffffffu, kp, k, CNS_DP_G);
+                if (gl + k < nend && osc > -1.0 &&
+                    (!chosen || osc > best || (osc == best && (okp >> 11) < (bk >> 11)))) { best = osc; bk = okp; chosen = true; }
+            }
+            if (act && isstart) { nsc = chosen ? best : -1.0; bkp = chosen ? bk & 0x7ffu : 7u; }
+        }
+        __syncwarp();                                                       // every score of the ring was read before it is overwritten
+        if (isstart) {
+            const uint32_t lvl = level + (uint32_t)mylev;
+            SC[(seq + gl) & (SR - 1)] = nsc;
+            const uint32_t b = me.x & 7u;
+            if (lvl < TP.level_cap) bp16[(size_t)lvl * 8 + b] = (uint16_t)bkp;
+            else fail |= 1;
+            if (nsc > g_best) { g_best = nsc; g_level = (int)lvl; g_b = (int)b; g_t = t; g_delta = (int)(lvl - cur_fl); g_x = seq + gl; }
+        }
+        if (in && (me.x & CNS_C_LEVEL)) { const uint32_t lvl = level + (uint32_t)mylev; if (lvl < TP.level_cap) bp[lvl].w = prev_fl; }
+        level += (uint32_t)nlev;
+        c += (uint32_t)take; seq += (uint32_t)take;
     }
-    cns_cp_async_wait_all();
-    if (slot < P.n_tpl) {
+    cns_cp_async_wait(0);
+    if (gl == 0 && slot < P.n_tpl) {
         if (redo) P.redo[atomicAdd(P.n_redo, 1u)] = ti;
-        else if (!P.dp_serial) {
-            if (have_node) { close_node(); close_level(); }
-            if (p_last) emit_run();
+        else {
             if (fail) atomicOr(P.error_flag, fail);
             atomicAdd(P.counters + 0, (unsigned long long)level);
         }
     }
 }
 
-// The same recurrence for the templates k_cns_dp could not finish (a predecessor further back than its score ring) and
-// for min_cov < 1 (runs may then hold positions without links): one thread per template, over the position records,
-// node scores kept in the weight field of the first link of each node in HBM.
+// The same recurrence for the templates k_cns_dp could not finish (a predecessor further back than its score ring):
+// one thread per template, over the position records, node scores kept in the first link of each node in HBM.
 __global__ void __launch_bounds__(128)
 k_cns_dp_serial(CnsParams P)
 {
@@ -852,39 +1116,41 @@ k_cns_dp_serial(CnsParams P)
         double g_best = -1.0;
         int g_level = -1, g_b = -1, g_t = 0, g_delta = 0;
         my_runs[r].first_level = level;
+        uint32_t pv_end = 0;                        // end of the links of the last position that had any
         for (int t = from; t < to; ++t) {
             const CnsPos ps = pos[t];
             if (ps.n == 0) continue;
             prev_fl = cur_fl; cur_fl = level;
             bool have_node = false, chosen = false;
-            uint32_t cur_b = 0, node_first = 0, best_key = 0;
+            uint32_t cur_b = 0, node_first = 0, best_aux = 0;
             double best = -1.0;
             auto close_node = [&]() {
                 const double ns = chosen ? best : -1.0;
                 link[node_first].w = ns;
-                if (level < TP.level_cap) bp[level].code[cur_b] = (uint16_t)(chosen ? cns_bp_code(best_key) : 7u);
+                if (level < TP.level_cap) bp[level].code[cur_b] = (uint16_t)(chosen ? (best_aux >> 16) & 0x7ffu : 7u);
                 if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)(level - cur_fl); }
             };
             for (uint32_t i = 0; i < ps.n; ++i) {
                 const uint32_t x = ps.start + i;
                 const uint4 e = *reinterpret_cast<const uint4*>(link + x);
-                const uint32_t key = e.x, pred = e.y;
-                if (key & CNS_K_NODE) {
+                if (e.x & CNS_C_NODE) {
                     if (have_node) close_node();
-                    if ((key & CNS_K_LEVEL) && i > 0) {
+                    if ((e.x & CNS_C_LEVEL) && i > 0) {
                         if (level < TP.level_cap) bp[level].prev_first_level = prev_fl; else fail |= 1;
                         ++level;
                     }
-                    have_node = true; cur_b = (key >> 20) & 7u; node_first = x; best = -1.0; chosen = false;
+                    have_node = true; cur_b = e.x & 7u; node_first = x; best = -1.0; best_aux = 0; chosen = false;
                 }
                 double sc = __hiloint2double((int)e.w, (int)e.z);
-                if (pred != CNS_NOPRED) sc = __dadd_rn(sc, link[pred].w);
-                const bool better = chosen ? (sc > best || (sc == best && CNS_K_RANK(key) < CNS_K_RANK(best_key))) : (sc > -1.0);
-                if (better) { best = sc; best_key = key; chosen = true; }
+                const uint32_t dist = e.y & 0xffffu;
+                if (dist) sc = __dadd_rn(sc, link[dist <= i ? x - dist : pv_end - (dist - i)].w);
+                const bool better = chosen ? (sc > best || (sc == best && (e.y >> 27) < (best_aux >> 27))) : (sc > -1.0);
+                if (better) { best = sc; best_aux = e.y; chosen = true; }
             }
             if (have_node) close_node();
             if (level < TP.level_cap) bp[level].prev_first_level = prev_fl; else fail |= 1;
             ++level;
+            pv_end = ps.start + ps.n;
         }
         CnsRun rr = my_runs[r];
         rr.g_level = g_level; rr.g_b = g_b; rr.g_t = g_t; rr.g_delta = g_delta;

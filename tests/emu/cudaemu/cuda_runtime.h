@@ -224,8 +224,7 @@ static inline void nb_tma_load_1d(void* dst, const void* src, uint32_t bytes, ui
 static inline void nb_mbar_wait(uint64_t* bar, uint32_t parity) { while ((*(volatile uint64_t*)bar & 1) == parity) emu::yield(); }
 static inline void cns_cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
 static inline void cns_cp_async_commit() { }
-static inline void cns_cp_async_wait_ring() { }
-static inline void cns_cp_async_wait_all() { }
+static inline void cns_cp_async_wait(int) { }
 
 // ---------------------------------------------------------------- runtime API (everything is synchronous host memory)
 typedef int cudaError_t;

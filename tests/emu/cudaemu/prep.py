@@ -14,7 +14,7 @@ import re
 import sys
 
 PTX_HELPERS = ["nb_smem_addr", "nb_mbar_init", "nb_mbar_expect_tx", "nb_tma_load_1d", "nb_mbar_wait",
-               "cns_cp_async16", "cns_cp_async_commit", "cns_cp_async_wait_ring", "cns_cp_async_wait_all"]
+               "cns_cp_async16", "cns_cp_async_commit", "cns_cp_async_wait"]
 
 
 def drop_function(src, name):
