@@ -80,8 +80,21 @@ inline double cns_weight(double ident)      // consensus_one_read.c:11-16
 }
 inline double ident_of(const nb_alignment& a) { return a.aln_size ? 100.0 * a.n_match / a.aln_size : 0.0; }
 
-inline bool is_used(const Tpl& t, int qid) { for (int u : t.used) if (u == qid) return true; return false; }
-inline void set_used(Tpl& t, int qid) { if (!is_used(t, qid)) t.used.push_back(qid); }
+// "was this read already extended against the template" (ReadIdPool, consensus_aux.h): the template keeps the list, the
+// thread that replays it a stamp per read id (set up from the list when the replay starts) so that a look-up is one load.
+struct UsedStamps {
+    std::vector<uint32_t> stamp;
+    uint32_t epoch = 0;
+    void begin(const Tpl& t, size_t nseq)
+    {
+        if (stamp.size() < nseq) stamp.assign(nseq, 0);
+        if (++epoch == 0) { std::fill(stamp.begin(), stamp.end(), 0u); epoch = 1; }
+        for (int u : t.used) stamp[(size_t)u] = epoch;
+    }
+};
+static thread_local UsedStamps tl_used;
+inline bool is_used(const Tpl&, int qid) { return tl_used.stamp[(size_t)qid] == tl_used.epoch; }
+inline void set_used(Tpl& t, int qid) { if (!is_used(t, qid)) { t.used.push_back(qid); tl_used.stamp[(size_t)qid] = tl_used.epoch; } }
 // The two per-base loops of the replay (2 G coverage increments on the E. coli-size set): plain loops the compiler turns
 // into 16-lane AVX2 code where the host has it (chosen once, at load time), scalar otherwise.
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__CUDA_ARCH__)
@@ -132,8 +145,9 @@ inline void accept(Tpl& t, size_t ci, const nb_alignment& a, int max_cov)
 }
 
 // Replays consensus_one_read for one template as far as the available extension results allow.
-void replay(Tpl& t, std::vector<Can>& cans, const std::vector<nb_alignment>& res, const nb_cns_options& o)
+void replay(Tpl& t, std::vector<Can>& cans, const std::vector<nb_alignment>& res, const nb_cns_options& o, size_t nseq)
 {
+    tl_used.begin(t, nseq);
     t.request.clear();
     Can* c = cans.data() + t.first;
     if (t.stage == 0) {
@@ -339,7 +353,9 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         std::atomic<int>* round0_done = NULL;    // set once the group's first (by far largest) extension launch has finished
     };
     const char* env_groups = getenv("NB_CNS_GROUPS");
-    int n_groups = env_groups ? atoi(env_groups) : 3;
+    // default 1: with the replay's per-base loops vectorised, what several groups hide of the host phases is less than what their
+    // smaller extension launches lose (measured, E. coli-size set: 355 ms per step with one group, 378 with three)
+    int n_groups = env_groups ? atoi(env_groups) : 1;
     const char* env_gmin = getenv("NB_CNS_GROUPS_MIN");       // (tests lower it to run small sets through several groups)
     if (ctx->is_worker || c1 - c0 < (size_t)(env_gmin ? atoi(env_gmin) : 1024)) n_groups = 1;   // workers of the chunk pipeline have no workers of their own
     if (n_groups > NB_MAX_WORKERS) n_groups = NB_MAX_WORKERS;
@@ -381,11 +397,6 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         // The round-0 requests: the first 50 candidates (phase 1), or nothing with -u 1 (the replay then asks for the first
         // window).  The coverage arrays (2 bytes per template base: hundreds of MB to clear) are only needed by the first
         // replay: they are set up by side threads while the first extension launch runs.
-        for (size_t t = g.t0; t < g.t1; ++t) {
-            Tpl& T = tpls[t];
-            T.request.clear();
-            if (!o.use_fixed_ident_cutoff) for (size_t k = 0; k < T.n && k < 50; ++k) T.request.push_back(k);
-        }
         std::vector<std::thread> cov_threads;
         {
             auto init = [&tpls, &o](size_t a, size_t b) {
@@ -402,7 +413,8 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         struct Joiner { std::vector<std::thread>& th; ~Joiner() { for (auto& x : th) if (x.joinable()) x.join(); } } cov_joiner{cov_threads};
         g.tm.prep += gt.lap();
         for (int round = 0;; ++round) {
-            if (round > 0 || o.use_fixed_ident_cutoff) {
+            if (round == 0 && o.use_fixed_ident_cutoff) continue;         // -u 1: nothing to extend before the first replay
+            if (round > 0) {
                 for (auto& x : cov_threads) if (x.joinable()) x.join();
                 // replay in parallel over templates
                 std::vector<std::thread> th;
@@ -412,7 +424,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                 for (unsigned w = 0; w < nthreads && per; ++w) {
                     const size_t a = w * per, b = std::min(todo.size(), a + per);
                     if (a >= b) break;
-                    th.emplace_back([&, a, b]() { for (size_t x = a; x < b; ++x) replay(tpls[todo[x]], cans, g.res, o); });
+                    th.emplace_back([&, a, b]() { for (size_t x = a; x < b; ++x) replay(tpls[todo[x]], cans, g.res, o, (size_t)reads->nseq); });
                 }
                 for (auto& x : th) x.join();
             }
@@ -430,7 +442,10 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                         Tpl& T = tpls[g.t0 + x];
                         if (T.stage == 2) continue;
                         uint64_t n = 0, bytes = 0;
-                        for (size_t k : T.request) {
+                        // round 0 asks for the first 50 candidates of every template (phase 1); later rounds for what the replay listed
+                        const size_t nreq = round == 0 ? std::min<size_t>(T.n, 50) : T.request.size();
+                        for (size_t ri = 0; ri < nreq; ++ri) {
+                            const size_t k = round == 0 ? ri : T.request[ri];
                             const Can& c = cans[T.first + k];
                             const uint64_t mn = (uint64_t)std::min(c.qoff, c.soff);
                             const uint32_t cap = (uint32_t)((uint64_t)c.qsize + (uint64_t)T.T + mn + 64);
