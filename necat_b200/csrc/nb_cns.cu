@@ -777,20 +777,17 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                         NB_LAUNCH_CHECK(cx);
                         k_cns_fix<<<(unsigned)((Q.n_units + 127) / 128), 128, 0, ss>>>(Q);
                         NB_LAUNCH_CHECK(cx);
-                        g = (unsigned)((Q.n_units + 3) / 4);
-                        if (g > NB_SMS * 16) g = NB_SMS * 16;
-                        k_cns_plan<<<g, 128, 0, ss>>>(Q);
-                        NB_LAUNCH_CHECK(cx);
                     }
-                    // sixteen templates per CTA (8 lanes each); sorted by length, the longest start first
-                    if (kDpTest == 1) {
-                        const size_t dsm = (size_t)16 * (16 * 128 + 8 * 8);
-                        NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-                        k_cns_dp<128, 8><<<(n_tpl + 15) / 16, 128, dsm, ss>>>(Q);
-                    } else {
-                        const size_t dsm = (size_t)16 * (16 * 128 + 8 * 128);
-                        NB_CUDA(cx, cudaFuncSetAttribute(k_cns_dp<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-                        k_cns_dp<128, 128><<<(n_tpl + 15) / 16, 128, dsm, ss>>>(Q);
+                    // the longest templates (slice 0 of two) get a warp each: their chain of levels is what lasts; the rest
+                    // four to a warp
+                    {
+                        const bool wide = nsl > 1 && sl == 0;
+                        const unsigned per_cta = wide ? 4u : 16u;
+                        const int sr = kDpTest == 1 ? 8 : 128;
+                        const size_t dsm = (size_t)per_cta * sr * 8;
+                        const unsigned dg = (n_tpl + per_cta - 1) / per_cta;
+                        if (wide) { if (sr == 8) k_cns_dp<32, 8><<<dg, 128, dsm, ss>>>(Q); else k_cns_dp<32, 128><<<dg, 128, dsm, ss>>>(Q); }
+                        else      { if (sr == 8) k_cns_dp<8, 8><<<dg, 128, dsm, ss>>>(Q);  else k_cns_dp<8, 128><<<dg, 128, dsm, ss>>>(Q); }
                     }
                     NB_LAUNCH_CHECK(cx);
                     k_cns_dp_serial<<<(n_tpl + 127) / 128, 128, 0, ss>>>(Q);

@@ -25,11 +25,10 @@
 //                reduced by the coverage penalty (cns_aux.c:164), the predecessor node resolved to a link index.
 //   k_cns_fix    the predecessor indices of the first position of every span (its predecessor position belongs
 //                to another warp's span).
-//   k_cns_dp     the best-path recurrence (cns_aux.c:157-184): 8 lanes per template (lane = link of the current
-//                delta level), four templates per warp in lock step, links streamed through a cp.async ring,
-//                node scores in a shared-memory ring; per level one 16-byte record with the five 11-bit back
-//                pointers.  A template whose predecessor falls out of the score ring is redone by
-//                k_cns_dp_serial (scores in HBM).
+//   k_cns_dp     the best-path recurrence (cns_aux.c:157-184): G lanes per template hold a window of G links of the
+//                dense stream and take its delta levels one per trip (lane = link of the level); node scores in a
+//                shared-memory ring; per level one 16-byte record with the back pointers of its nodes.  A template
+//                whose predecessor falls out of the score ring is redone by k_cns_dp_serial (scores in HBM).
 //   k_cns_walk   the walk over the back pointers (cns_aux.c:187-212), level records staged through shared
 //                memory a window at a time.
 #pragma once
@@ -107,7 +106,7 @@ struct __align__(16) CnsLink {  // one link = (node, predecessor node), sorted b
 };
 
 struct __align__(16) CnsLevel { // one (position, delta) level of the best-path recurrence, written by k_cns_dp for k_cns_walk
-    uint16_t code[6];           // per base: back pointer = predecessor delta << 3 | predecessor base, 7 = none (only the bases that have a node are written)
+    uint16_t code[6];           // per base: back pointer = predecessor rank << 3 | predecessor base, rank 0 = none (only the bases that have a node are written)
     uint32_t prev_first_level;  // level index of (position - 1, delta 0): the walk needs no second load per step
 };
 
@@ -655,7 +654,8 @@ k_cns_links(CnsParams P)
 }
 
 // The first position of a span (not of the template): the predecessors of its delta-0 links are nodes of the last
-// position of the previous span, whose links another warp placed.  One thread per unit.
+// position of the previous span, whose links another warp placed (in its own region: the spans of a template are not
+// adjacent in memory).  One thread per unit.
 __global__ void __launch_bounds__(128)
 k_cns_fix(CnsParams P)
 {
@@ -674,430 +674,244 @@ k_cns_fix(CnsParams P)
         const uint32_t want = pred & 0xfffu;
         uint32_t less = 0;
         for (uint32_t q = 0; q < prv.n; ++q) less += ((link[prv.start + q].key >> 20) & 0xff7u) < want;
-        link[cur.start + i].pred = prv.start + less;
-    }
-}
-
-__device__ __forceinline__ uint32_t cns_bp_code(uint32_t key)       // back pointer of a node whose best link has this key
-{
-    const uint32_t rank = CNS_K_RANK(key), pb = (key >> 16) & 7;
-    if (rank == 0) return 7u;
-    return (((key >> 24) == 0 ? (rank - 1 - cns_char_rank(pb)) / 5u : 0u) << 3) | pb;
-}
-
-// ------------------------------------------------------------------ what k_cns_dp reads
-// k_cns_links / k_cns_fix leave every link as (key, index of the predecessor node's first link, weight).  k_cns_plan
-// turns the first two words, in place, into what the recurrence needs and nothing else, so that k_cns_dp -- one
-// dependent chain per template -- spends no instruction on decoding:
-//   ctl   bits 0-2 base | 3 node start | 4-6 links of the node - 1 | 7-8 level inside its trip | 9 first link of a trip |
-//         10-12 links of the trip - 1 | 13-14 levels of the trip - 1 | 15-17 longest node of the trip - 1 |
-//         18 first link of a position | 19 ... of a run | 20 ... of the last position of a run | 21 first link of a level |
-//         22 the level has more than 8 links (it is a trip by itself and scored link by link)
-//   aux   bits 0-15 dense distance back to the predecessor node's first link (0: none) | 16-26 the back pointer this
-//         link stands for | 27-31 its rank inside the node (ties between equal scores go to the lower)
-// A trip is what one pass of k_cns_dp's loop takes: whole levels of one position, at most 8 links and 4 levels.
-// One thread per position.
-#define CNS_C_NODE   (1u << 3)
-#define CNS_C_TRIP   (1u << 9)
-#define CNS_C_POS    (1u << 18)
-#define CNS_C_RUN0   (1u << 19)
-#define CNS_C_RUNZ   (1u << 20)
-#define CNS_C_LEVEL  (1u << 21)
-#define CNS_C_LONG   (1u << 22)
-
-__global__ void __launch_bounds__(128)
-k_cns_plan(CnsParams P)
-{
-    const int lane = threadIdx.x & 31;
-    const uint32_t nwarp = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t ui = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ui < P.n_units; ui += nwarp) {
-        const CnsUnit U = P.unit[ui];
-        const CnsTemplate TP = P.tpl0[U.tpl];
-        const CnsPos* pos = P.pos + TP.pos_base;
-        uint4* link = reinterpret_cast<uint4*>(P.link + TP.link_base);
-        const int s0 = (int)U.span * P.span, s1 = (s0 + P.span < TP.T) ? s0 + P.span : TP.T;
-        for (int t = s0 + lane; t < s1; t += 32) {
-            const CnsPos ps = pos[t];
-            const uint32_t n = ps.n;
-            if (n == 0) continue;
-            // the dense stream of the template has the previous position's links right before this one's
-            uint32_t pv_end = 0;
-            if (t > 0) { const CnsPos pv = pos[t - 1]; pv_end = pv.start + pv.n; }
-            const uint32_t x0 = ps.start;
-            unsigned long long NS = 0, LS = 0;              // node starts, level starts (n <= 64)
-            // ---- pass 1: aux of every link; the boundaries
-            for (uint32_t i = 0; i < n; ++i) {
-                const uint4 e = link[x0 + i];
-                const uint32_t key = e.x, pred = e.y;
-                if (n <= 64) { if (key & CNS_K_NODE) NS |= 1ull << i; if (key & CNS_K_LEVEL) LS |= 1ull << i; }
-                uint32_t dist = 0;
-                if (pred != CNS_NOPRED) dist = (key >> 24) ? x0 + i - pred : i + (pv_end - pred);
-                if (dist >= 0xf000u) { atomicOr(P.error_flag, 2u); dist = 0; }
-                // rank inside the node: links of the node with a lower predecessor rank
-                uint32_t prio = 0;
-                {
-                    const uint32_t nid = (key >> 20) & 0xff7u, rk = CNS_K_RANK(key);
-                    for (uint32_t j = i; j-- > 0;) {
-                        const uint32_t kj = link[x0 + j].x;
-                        if (((kj >> 20) & 0xff7u) != nid) break;
-                        prio += CNS_K_RANK(kj) < rk;
-                    }
-                    for (uint32_t j = i + 1; j < n; ++j) {
-                        const uint32_t kj = link[x0 + j].x;
-                        if (((kj >> 20) & 0xff7u) != nid) break;
-                        prio += CNS_K_RANK(kj) < rk;
-                    }
-                }
-                if (prio > 31) prio = 31;
-                link[x0 + i].y = dist | (cns_bp_code(key) << 16) | (prio << 27);
-            }
-            // ---- pass 2: ctl of every link
-            const uint32_t posflags = CNS_C_POS | ((ps.flags & 2) ? CNS_C_RUN0 : 0u) | ((ps.flags & 4) ? CNS_C_RUNZ : 0u);
-            if (n > 64) {
-                // a very crowded position: every level is scored link by link
-                for (uint32_t i = 0; i < n; ++i) {
-                    const uint32_t key = link[x0 + i].x;
-                    uint32_t c = (key >> 20) & 7u;
-                    if (key & CNS_K_NODE) c |= CNS_C_NODE;
-                    if (key & CNS_K_LEVEL) c |= CNS_C_LEVEL | CNS_C_TRIP | CNS_C_LONG;
-                    if (i == 0) c |= posflags;
-                    link[x0 + i].x = c;
-                }
-                continue;
-            }
-            uint32_t i = 0;
-            while (i < n) {
-                // a trip starts at level start i: whole levels while they fit 8 links and 4 levels
-                uint32_t j = i, nlev = 0, maxnode = 1;
-                bool lng = false;
-                for (;;) {
-                    // the level that starts at j ends at the next level start
-                    const unsigned long long rest = LS >> (j + 1);
-                    const uint32_t le = rest ? j + 1 + (uint32_t)__ffsll((long long)rest) - 1 : n;
-                    if (le - i > 8 || nlev == 4) { if (nlev == 0) { lng = true; j = le; nlev = 1; } break; }
-                    j = le; ++nlev;
-                    if (j >= n) break;
-                }
-                // links [i, j) are the trip
-                if (!lng) {
-                    for (uint32_t a = i; a < j;) {          // longest node
-                        const unsigned long long rest = NS >> (a + 1);
-                        uint32_t ne = rest ? a + 1 + (uint32_t)__ffsll((long long)rest) - 1 : n;
-                        if (ne > j) ne = j;
-                        if (ne - a > maxnode) maxnode = ne - a;
-                        a = ne;
-                    }
-                }
-                uint32_t lv = 0;
-                for (uint32_t a = i; a < j; ++a) {
-                    const uint32_t key = link[x0 + a].x;
-                    uint32_t c = (key >> 20) & 7u;
-                    if (a > i && ((LS >> a) & 1)) ++lv;
-                    if ((NS >> a) & 1) {
-                        const unsigned long long rest = NS >> (a + 1);
-                        uint32_t ne = rest ? a + 1 + (uint32_t)__ffsll((long long)rest) - 1 : n;
-                        if (ne > j) ne = j;
-                        uint32_t nl = ne - a; if (nl > 8) nl = 8;
-                        c |= CNS_C_NODE | ((nl - 1) << 4);
-                    }
-                    if ((LS >> a) & 1) c |= CNS_C_LEVEL;
-                    c |= (lng ? 0u : lv) << 7;
-                    if (a == i) {
-                        c |= CNS_C_TRIP;
-                        if (lng) c |= CNS_C_LONG;
-                        else c |= ((j - i - 1) << 10) | ((nlev - 1) << 13) | ((maxnode - 1) << 15);
-                        if (i == 0) c |= posflags;
-                    }
-                    link[x0 + a].x = c;
-                }
-                i = j;
-            }
-        }
+        // as if the previous position's links were stored right before this span's: link index - pred is then the dense
+        // distance k_cns_dp needs, everywhere (inside a span the links of neighbouring positions ARE adjacent)
+        link[cur.start + i].pred = cur.start - (prv.n - less);
     }
 }
 
 // ------------------------------------------------------------------ best path
-__device__ __forceinline__ void cns_cp_async16(void* dst_smem, const void* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(nb_smem_addr(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cns_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cns_cp_async_wait(int pending)      // at most `pending` (0 or CNS_DP_PEND) groups stay in flight
-{
-    if (pending <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
-    else asm volatile("cp.async.wait_group 6;" ::: "memory");
-}
-#define CNS_DP_PEND 6
-
-
-// Eight lanes per template, four templates per warp, all in lock step.  The recurrence is a chain over the delta levels
-// of a template, so what decides the kernel's duration is how few instructions one step of that chain takes for the
-// longest template.  One trip of the loop takes the next trip of every template of the warp (k_cns_plan: whole levels
-// of one position, at most 8 links, lane = link) and walks its levels:
-//   * the links of a template are a dense stream per span (k_cns_links): they are staged through a ring in shared
-//     memory with cp.async, LR links ahead; everything the trip needs to know about them is in their two control
-//     words, no position record is read and nothing is decoded from keys;
-//   * a predecessor scored in an earlier trip comes from a ring of node scores in shared memory, indexed by the dense
-//     sequence number of the node's first link (a predecessor is a node of this or of the previous position: the ring
-//     misses only where two neighbouring positions hold more than SR links, and such a template is handed to
-//     k_cns_dp_serial); a predecessor inside the trip comes from its lane by shuffle;
-//   * the links of a node are adjacent lanes: maximum by shuffles (ties to the lower rank); every node stores its own
-//     back pointer into the level record, the best node of a run is tracked per lane and reduced when the run has
-//     ended (ties to the lowest link = the first one in the reference's traversal order);
-//   * ONE warp-wide OR per trip carries everything the four templates have to agree on: the number of level steps,
-//     the longest node, and whether anything rare is due (a run ended, a level of more than 8 links, the staging ring
-//     has to catch up, a span of the stream ended, all templates finished).
-#define CNS_DP_G 8
-#define CNS_EV_NOTDONE (1u << 12)
-#define CNS_EV_EMIT    (1u << 13)
-#define CNS_EV_LONG    (1u << 14)
-#define CNS_EV_UNSURE  (1u << 15)
-#define CNS_EV_SPAN    (1u << 16)
-
-template <int LR, int SR>
+// The recurrence (cns_aux.c:157-184) is a chain over the delta LEVELS of a template: the links of one level only need
+// node scores of earlier levels, so a level is the unit of parallel work and the number of levels (2.5 per position)
+// times the duration of one level step is what the longest template costs.  G lanes own a template (32 / G templates
+// per warp, all in lock step, one level per trip):
+//   * the lanes hold a WINDOW of G consecutive links of the dense stream k_cns_links / k_cns_fix left (key, first link
+//     of the predecessor node, weight; inside a span the links of neighbouring positions are adjacent, so link index -
+//     pred is the dense distance back to the predecessor node).  Two ballots over the keys give the level and node
+//     starts of the whole window; the levels in it are then taken one after the other without touching memory for
+//     links again.  The last level start of a window is where the next window begins (that level may be cut off by the
+//     window's end), known as soon as the window is loaded -- so the next window is fetched into registers right then
+//     and has landed by the time the levels of this one are done.  No staging ring, no control words, no plan pass;
+//   * node scores live in a ring in shared memory indexed by the dense number of the node's first link (a predecessor
+//     is a node of this or of the previous position: the ring misses only where two neighbouring positions hold more
+//     than SR links; such a template is handed to k_cns_dp_serial);
+//   * the links of a node are adjacent lanes: their maximum by shuffles (as many rounds as the longest node of the
+//     level needs, none in the common level of single-link nodes), ties between equal scores to the lower predecessor
+//     rank = the link the reference meets first (cns_aux.c:166); every node stores its own back pointer into the level
+//     record; the best node of a run is tracked per lane and reduced when the run has ended (ties to the lowest dense
+//     number = the first one in the reference's traversal order);
+//   * a level of more than G links (a window that holds no second level start) is walked link by link by the group's
+//     first lane, straight from HBM.
+template <int G, int SR>
 __global__ void __launch_bounds__(128)
 k_cns_dp(CnsParams P)
 {
     extern __shared__ __align__(16) uint8_t dp_smem[];
+    constexpr int TPW = 32 / G;
+    constexpr uint32_t GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+    const uint32_t full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int gl = lane & (CNS_DP_G - 1), grp = lane >> 3;
-    const uint32_t slot = (blockIdx.x * 4 + wid) * 4 + grp;
-    uint4* LK = reinterpret_cast<uint4*>(dp_smem) + (size_t)(wid * 4 + grp) * LR;
-    double* SC = reinterpret_cast<double*>(dp_smem + (size_t)16 * 16 * LR) + (size_t)(wid * 4 + grp) * SR;
+    const int gl = lane & (G - 1), gsh = lane & ~(G - 1);          // my lane inside the group; the group's first lane
+    const uint32_t slot = (blockIdx.x * 4 + wid) * TPW + (uint32_t)(lane / G);
+    double* SC = reinterpret_cast<double*>(dp_smem) + (size_t)(wid * TPW + lane / G) * SR;
     bool done = slot >= P.n_tpl;
     const uint32_t ti = done ? 0 : slot;
     const CnsTemplate TP = P.tpl[ti];
-    const CnsLink* __restrict__ link = P.link + TP.link_base;
+    const uint4* __restrict__ link = reinterpret_cast<const uint4*>(P.link + TP.link_base);
     uint4* bp = reinterpret_cast<uint4*>(P.bp + TP.level_base);
     uint16_t* bp16 = reinterpret_cast<uint16_t*>(bp);
     CnsRun* my_runs = P.runs + TP.seg_first;
     const uint2* __restrict__ spans = P.span_links + TP.unit_first;
     const int n_spans = (TP.T + P.span - 1) / P.span;
     const uint32_t n_runs = done ? 0 : P.tpl_nrun[ti];
-    // consumer / producer cursors over the link stream
-    int ck = -1, fk = -1;
-    uint32_t c = 0, c_end = 0, seq = 0, f = 0, f_end = 0, fseq = 0;
+    bool redo = false;
+    if (!done && P.dp_serial) { redo = true; done = true; }
     auto next_span = [&](int& k, uint32_t& a, uint32_t& a_end) {
         while (a == a_end && k < n_spans) {
             ++k;
-            if (k < n_spans) { const uint2 e = spans[k]; a = e.x; a_end = e.x + e.y; }
+            if (k < n_spans) { const uint2 s = spans[k]; a = s.x; a_end = s.x + s.y; }
         }
     };
-    bool redo = false;
-    if (!done && P.dp_serial) { redo = true; done = true; }
-    if (!done) { next_span(ck, c, c_end); fk = ck; f = c; f_end = c_end; if (ck >= n_spans) done = true; }
+    // the window: lane gl holds link x + gl of span k (x_end: end of the span); sq = dense number of link x
+    int k = -1, nk = -1;
+    uint32_t x = 0, x_end = 0, nx = 0, nx_end = 0, sq = 0;
+    uint32_t a = 0, top = 0;            // the next level starts at window lane a; the window's last level start is lane top
+    uint4 e = make_uint4(0, 0, 0, 0), en = make_uint4(0, 0, 0, 0);
+    if (!done) {
+        next_span(nk, nx, nx_end);
+        if (nk < n_spans && nx + (uint32_t)gl < nx_end) en = link[nx + gl];
+    }
     uint32_t level = 0, cur_fl = 0, prev_fl = 0, run_started = 0, run_emitted = 0, fail = 0;
     int t = 0;
-    bool p_last = false, pend_emit = false, pend_long = false, pend_span = false, unsure = !done;
-    // best node of the current run, per lane; and of the run that has just ended (emitted at the top of the next trip)
-    double g_best = -1.0, e_best = -1.0;
-    int g_level = -1, g_b = -1, g_t = 0, g_delta = 0, e_level = -1, e_b = -1, e_t = 0, e_delta = 0, e_end = 0;
-    uint32_t g_x = 0xffffffffu, e_x = 0xffffffffu;
-    uint32_t ev = CNS_EV_UNSURE | CNS_EV_NOTDONE;           // what the previous trip's OR announced
-    auto issue = [&]() {
-        const uint32_t nb = f_end - f < CNS_DP_G ? f_end - f : CNS_DP_G;
-        if ((uint32_t)gl < nb) cns_cp_async16(LK + ((fseq + gl) & (LR - 1)), link + f + gl);
-        f += nb; fseq += nb;
-        if (f == f_end) next_span(fk, f, f_end);
-    };
-    auto snapshot = [&]() {
-        pend_emit = true;
-        e_best = g_best; e_level = g_level; e_b = g_b; e_t = g_t; e_delta = g_delta; e_x = g_x; e_end = t;
-    };
+    bool p_last = false, fin = false;
+    // best node of the current run among the nodes this lane closed
+    double g_best = -1.0;
+    uint32_t g_x = 0xffffffffu, g_lb = 0xffffffffu, g_fl = 0;
+    int g_t = 0;
     for (;;) {
-        // ---- a span of the stream ended with the previous trip
-        if ((ev & CNS_EV_SPAN) && pend_span) {
-            next_span(ck, c, c_end);
-            if (ck >= n_spans) done = true;
-            pend_span = false;
+        // ---- 1. a group whose window holds no complete level any more moves on to the window it fetched
+        const bool adv = !done && a >= top;
+        if (adv) {
+            sq += top;
+            k = nk; x = nx; x_end = nx_end; e = en; a = 0;
+            if (k >= n_spans) { done = true; fin = p_last; }
         }
-        // ---- staging: keep the ring full
-        if (!done && fseq - seq <= (uint32_t)(LR - CNS_DP_G) && f < f_end) issue();
-        cns_cp_async_commit();
-        if (ev & CNS_EV_UNSURE) {
-            if (unsure && !done) {
-                const uint32_t left = c_end - c;
-                const uint32_t need = seq + (left < CNS_DP_G + 1 ? left : CNS_DP_G + 1);
-                while (fseq < need && f < f_end) issue();
-            }
-            cns_cp_async_commit();
-            cns_cp_async_wait(0);
-        } else cns_cp_async_wait(CNS_DP_PEND);
-        __syncwarp();
-        if (ev & (CNS_EV_EMIT | CNS_EV_LONG)) {
-            if (ev & CNS_EV_EMIT) {
-                // the best node of the run that ended (cns_aux.c:177-184): highest score, first in traversal order
-                double mx = e_best;
-#pragma unroll
-                for (int d = 4; d > 0; d >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, mx, d, CNS_DP_G); mx = o > mx ? o : mx; }
-                uint32_t mnx = e_best == mx ? e_x : 0xffffffffu;
-#pragma unroll
-                for (int d = 4; d > 0; d >>= 1) { const uint32_t o = __shfl_xor_sync(0xffffffffu, mnx, d, CNS_DP_G); mnx = o < mnx ? o : mnx; }
-                const uint32_t win = (__ballot_sync(0xffffffffu, e_best == mx && e_x == mnx) >> (grp * CNS_DP_G)) & 0xffu;
-                const int wl = win ? __ffs(win) - 1 : 0;
-                const int r_level = __shfl_sync(0xffffffffu, e_level, wl, CNS_DP_G), r_b = __shfl_sync(0xffffffffu, e_b, wl, CNS_DP_G);
-                const int r_t = __shfl_sync(0xffffffffu, e_t, wl, CNS_DP_G), r_delta = __shfl_sync(0xffffffffu, e_delta, wl, CNS_DP_G);
-                if (pend_emit) {
-                    if (gl == 0 && run_emitted < n_runs) {
-                        CnsRun r = my_runs[run_emitted];                // from and first_level were written at the run's start
-                        r.to = e_end + 1; r.g_level = r_level; r.g_b = r_b; r.g_t = r_t; r.g_delta = r_delta;
-                        my_runs[run_emitted] = r;
-                    }
-                    ++run_emitted;
-                    pend_emit = false;
-                }
-            }
-            if (ev & CNS_EV_LONG) {
-                // ---- a level of more than 8 links: the group's first lane scores it link by link, straight from HBM
-                if (pend_long && gl == 0) {
-                    bool have_node = false, chosen = false;
-                    uint32_t cur_b = 0, node_first = 0, best_aux = 0, x = c, xs = seq;
-                    double best = -1.0;
-                    auto close_node = [&]() {
-                        const double ns = chosen ? best : -1.0;
-                        SC[node_first & (SR - 1)] = ns;
-                        if (level < TP.level_cap) bp16[(size_t)level * 8 + cur_b] = (uint16_t)(chosen ? (best_aux >> 16) & 0x7ffu : 7u);
-                        if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)(level - cur_fl); g_x = node_first; }
-                    };
-                    for (; x < c_end; ++x, ++xs) {
-                        const uint4 e = *reinterpret_cast<const uint4*>(link + x);
-                        if (x != c && (e.x & CNS_C_LEVEL)) break;
-                        if (e.x & CNS_C_NODE) {
-                            if (have_node) close_node();
-                            have_node = true; cur_b = e.x & 7u; node_first = xs; best = -1.0; best_aux = 0; chosen = false;
-                        }
-                        double sc = __hiloint2double((int)e.w, (int)e.z);
-                        const uint32_t dist = e.y & 0xffffu;
-                        if (dist) {
-                            if (dist >= (uint32_t)SR) redo = true;
-                            sc = __dadd_rn(sc, SC[(xs - dist) & (SR - 1)]);
-                        }
-                        const bool better = chosen ? (sc > best || (sc == best && (e.y >> 27) < (best_aux >> 27))) : (sc > -1.0);
-                        if (better) { best = sc; best_aux = e.y; chosen = true; }
-                    }
-                    if (have_node) close_node();
-                    if (level < TP.level_cap) bp[level].w = prev_fl; else fail |= 1;
-                    c = x; seq = xs;
-                }
-                const uint32_t c2 = __shfl_sync(0xffffffffu, c, 0, CNS_DP_G), s2 = __shfl_sync(0xffffffffu, seq, 0, CNS_DP_G);
-                const int r2 = __shfl_sync(0xffffffffu, (int)redo, 0, CNS_DP_G);
-                if (pend_long) {
-                    c = c2; seq = s2; redo = r2 != 0;
-                    ++level;
-                    pend_long = false;
-                    if (c == c_end) { next_span(ck, c, c_end); if (ck >= n_spans) done = true; }
-                    if (redo) done = true;
-                    // the staging ring starts over behind the level
-                    if (fseq < seq || fk != ck) { fk = ck; f = c; f_end = c_end; fseq = seq; }
-                    if (!done) {
-                        const uint32_t left = c_end - c;
-                        const uint32_t need = seq + (left < CNS_DP_G + 1 ? left : CNS_DP_G + 1);
-                        while (fseq < need && f < f_end) issue();
-                    }
-                }
-                cns_cp_async_commit();
-                cns_cp_async_wait(0);
-                __syncwarp();
-            }
-            if (done && p_last && !redo && !pend_emit) { snapshot(); p_last = false; }
+        // ---- 2. level and node starts of the windows (a group that did not move gets what it had)
+        const bool valid = !done && x + (uint32_t)gl < x_end;
+        const uint32_t lvb = __ballot_sync(full, valid && (e.x & CNS_K_LEVEL));
+        const uint32_t ndb = __ballot_sync(full, valid && (e.x & CNS_K_NODE));
+        const uint32_t nvalid = done ? 0u : (x_end - x < (uint32_t)G ? x_end - x : (uint32_t)G);
+        const uint32_t sent = nvalid < (uint32_t)G ? (1u << nvalid) : 0u;       // the span ends inside the window, and its last level with it
+        const uint32_t lv = ((lvb >> gsh) & GM) | sent, nd = ((ndb >> gsh) & GM) | sent;
+        top = 31u - (uint32_t)__clz((int)(lv | 1u));
+        const bool lng = !done && top == 0;                 // one level fills the window (or runs past it)
+        // ---- 3. groups that moved fetch the window after this one: it begins at the last level start of this one
+        if (adv && !done && !lng) {
+            nk = k; nx = x + top; nx_end = x_end;
+            if (nx == x_end) next_span(nk, nx, nx_end);
+            if (nk < n_spans && nx + (uint32_t)gl < nx_end) en = link[nx + gl];
         }
-        // ---- the next trip of the stream
-        uint32_t hdr = 0;
-        uint4 me = make_uint4(0, 0, 0, 0);
-        if (!done) { hdr = LK[seq & (LR - 1)].x; me = LK[(seq + gl) & (LR - 1)]; }
-        const bool lng = (hdr & CNS_C_LONG) != 0;
-        const int take = (done || lng) ? 0 : (int)((hdr >> 10) & 7u) + 1;
-        const int nlev = take ? (int)((hdr >> 13) & 3u) + 1 : 0;
-        if (lng) pend_long = true;
-        // ---- position / run bookkeeping (uniform inside the group)
-        if (hdr & CNS_C_POS) {
-            if (p_last) snapshot();                                         // the previous position ended a run
+        if (__all_sync(full, done && !fin)) break;
+        const bool lev = !done && !lng;                     // (then a < top: a complete level starts at lane a)
+        // ---- 4. position / run bookkeeping from the first link of the level (uniform inside a group)
+        const uint32_t k0 = __shfl_sync(full, e.x, gsh + (int)a);
+        const bool newpos = (lev || lng) && (k0 >> 24) == 0;           // a position starts with its delta-0 level
+        if (__any_sync(full, fin || (newpos && p_last))) {
+            // the best node of the run that ended (cns_aux.c:177-184): highest score, first in traversal order
+            double mx = g_best;
+#pragma unroll
+            for (int d = G >> 1; d > 0; d >>= 1) { const double o = __shfl_xor_sync(full, mx, d, G); mx = o > mx ? o : mx; }
+            uint32_t mnx = g_best == mx ? g_x : 0xffffffffu;
+#pragma unroll
+            for (int d = G >> 1; d > 0; d >>= 1) { const uint32_t o = __shfl_xor_sync(full, mnx, d, G); mnx = o < mnx ? o : mnx; }
+            const uint32_t win = (__ballot_sync(full, g_best == mx && g_x == mnx) >> gsh) & GM;
+            const int wl = gsh + (win ? __ffs((int)win) - 1 : 0);
+            const uint32_t r_lb = __shfl_sync(full, g_lb, wl), r_fl = __shfl_sync(full, g_fl, wl);
+            const int r_t = __shfl_sync(full, g_t, wl);
+            if (fin || (newpos && p_last)) {
+                if (gl == 0 && run_emitted < n_runs) {
+                    CnsRun r = my_runs[run_emitted];                // from and first_level were written at the run's start
+                    r.to = t + 1;
+                    if (r_lb == 0xffffffffu) { r.g_level = -1; r.g_b = -1; r.g_t = 0; r.g_delta = 0; }
+                    else { r.g_level = (int)(r_lb >> 3); r.g_b = (int)(r_lb & 7u); r.g_t = r_t; r.g_delta = (int)((r_lb >> 3) - r_fl); }
+                    my_runs[run_emitted] = r;
+                }
+                ++run_emitted;
+                p_last = false; fin = false;
+            }
+        }
+        if (newpos) {
             prev_fl = cur_fl; cur_fl = level;
-            if (hdr & CNS_C_RUN0) {
+            if (k0 & CNS_K_RUNFIRST) {
                 t = run_started < n_runs ? my_runs[run_started].from : 0;
-                g_best = -1.0; g_level = -1; g_x = 0xffffffffu;
+                g_best = -1.0; g_x = 0xffffffffu; g_lb = 0xffffffffu;
                 if (gl == 0 && run_started < n_runs) my_runs[run_started].first_level = level;
                 ++run_started;
             } else ++t;
-            p_last = (hdr & CNS_C_RUNZ) != 0;
+            p_last = (k0 & CNS_K_RUNLAST) != 0;
         }
-        const bool in = gl < take;
-        // ---- what the templates of the warp have to agree on
-        {
-            const uint32_t c_next = c + (uint32_t)take, left = c_end - c_next;
-            const bool span_end = take > 0 && c_next == c_end;
-            const bool unsure_next = !done && seq + (uint32_t)take + (left < CNS_DP_G + 1 ? left : CNS_DP_G + 1) + CNS_DP_G * CNS_DP_PEND > fseq;
-            uint32_t bits = 0;
-            if (take) bits |= (1u << (nlev - 1)) | (1u << (4 + ((hdr >> 15) & 7u)));
-            if (!done) bits |= CNS_EV_NOTDONE;
-            if (pend_emit) bits |= CNS_EV_EMIT | CNS_EV_NOTDONE;
-            if (pend_long) bits |= CNS_EV_LONG;
-            if (unsure_next || span_end) bits |= CNS_EV_UNSURE;
-            if (span_end) { bits |= CNS_EV_SPAN; pend_span = true; }
-            if (done && p_last && !redo && !pend_emit) { snapshot(); p_last = false; bits |= CNS_EV_EMIT | CNS_EV_NOTDONE; }
-            unsure = unsure_next || span_end;
-            ev = __reduce_or_sync(0xffffffffu, bits);
-        }
-        if (!(ev & CNS_EV_NOTDONE)) break;
-        const int maxlev = 32 - __clz((int)(ev & 0xfu)), extra = 31 - __clz((int)(((ev >> 4) & 0xffu) | 1u));
-        // ---- predecessors scored in earlier trips come from the ring, those of this trip from their lane
-        const uint32_t dist = me.y & 0xffffu;
-        const bool has_pred = in && dist != 0;                              // never-scored predecessors count 0 (cns_aux.c:63-70)
-        const bool in_trip = has_pred && dist <= (uint32_t)gl;
-        const double base = __hiloint2double((int)me.w, (int)me.z);
-        double rs = 0.0;
-        if (has_pred && !in_trip) {
-            if (dist >= (uint32_t)SR) redo = true;
-            rs = SC[(seq + gl - dist) & (SR - 1)];
-        }
-        const int src = in_trip ? gl - (int)dist : 0;
-        const bool isstart = in && (me.x & CNS_C_NODE);
-        const int nend = gl + (int)((me.x >> 4) & 7u) + 1;                  // my node ends here (meaningful in its first lane)
-        const int mylev = (int)((me.x >> 7) & 3u);
-        const uint32_t kp = me.y >> 16;                                     // back pointer (11 bits) | rank inside the node << 11
-        double nsc = -1.0, sc = base;
-        uint32_t bkp = kp;
-        for (int lv = 0; lv < maxlev; ++lv) {
-            const double from = __shfl_sync(0xffffffffu, nsc, src, CNS_DP_G);
-            const bool act = in && mylev == lv;
-            if (act && has_pred) sc = __dadd_rn(base, in_trip ? from : rs);
-            // the links of a node are adjacent lanes of one level
-            double best = sc;
-            uint32_t bk = kp;
-            bool chosen = act && sc > -1.0;
-            for (int k = 1; k <= extra; ++k) {
-                const double osc = __shfl_down_sync(0xffffffffu, sc, k, CNS_DP_G);
-                const uint32_t okp = __shfl_down_sync(0xffffffffu, kp, k, CNS_DP_G);
-                if (gl + k < nend && osc > -1.0 &&
-                    (!chosen || osc > best || (osc == best && (okp >> 11) < (bk >> 11)))) { best = osc; bk = okp; chosen = true; }
+        __syncwarp();                                       // the scores of the previous trip are in the ring
+        // ---- 5. a level of more than G links: the group's first lane walks it
+        if (__any_sync(full, lng)) {
+            uint32_t used = 0;
+            if (lng && gl == 0) {
+                bool have = false;
+                uint32_t cb = 0, nfirst = 0, bkey = 0, xi = x, si = sq;
+                double best = -1.0;
+                auto close_node = [&]() {
+                    SC[nfirst & (SR - 1)] = best;
+                    const uint32_t lb = level * 8 + cb;
+                    if (level < TP.level_cap) bp16[lb] = (uint16_t)((CNS_K_RANK(bkey) << 3) | ((bkey >> 16) & 7u)); else fail = 1;
+                    if (best > g_best) { g_best = best; g_x = nfirst; g_lb = lb; g_t = t; g_fl = cur_fl; }
+                };
+                for (; xi < x_end; ++xi, ++si) {
+                    const uint4 q = link[xi];
+                    if (xi != x && (q.x & CNS_K_LEVEL)) break;
+                    if (q.x & CNS_K_NODE) {
+                        if (have) close_node();
+                        have = true; cb = (q.x >> 20) & 7u; nfirst = si; best = -1.0; bkey = 0;
+                    }
+                    double s2 = __hiloint2double((int)q.w, (int)q.z);
+                    if (q.y != CNS_NOPRED) {
+                        const uint32_t d = xi - q.y;
+                        if (d >= (uint32_t)SR) redo = true;
+                        s2 = __dadd_rn(s2, SC[(si - d) & (SR - 1)]);
+                    }
+                    if (s2 > -1.0 && (s2 > best || (s2 == best && CNS_K_RANK(q.x) < CNS_K_RANK(bkey)))) { best = s2; bkey = q.x; }
+                }
+                if (have) close_node();
+                if (level < TP.level_cap) bp[level].w = prev_fl; else fail = 1;
+                used = xi - x;
             }
-            if (act && isstart) { nsc = chosen ? best : -1.0; bkp = chosen ? bk & 0x7ffu : 7u; }
+            used = __shfl_sync(full, used, gsh);
+            if (lng) {
+                ++level;
+                sq += used;
+                nk = k; nx = x + used; nx_end = x_end;
+                if (nx == x_end) next_span(nk, nx, nx_end);
+                en = make_uint4(0, 0, 0, 0);
+                if (nk < n_spans && nx + (uint32_t)gl < nx_end) en = link[nx + gl];
+                a = 0; top = 0;                             // the next trip moves on to that window
+            }
+            __syncwarp();
         }
-        __syncwarp();                                                       // every score of the ring was read before it is overwritten
-        if (isstart) {
-            const uint32_t lvl = level + (uint32_t)mylev;
-            SC[(seq + gl) & (SR - 1)] = nsc;
-            const uint32_t b = me.x & 7u;
-            if (lvl < TP.level_cap) bp16[(size_t)lvl * 8 + b] = (uint16_t)bkp;
-            else fail |= 1;
-            if (nsc > g_best) { g_best = nsc; g_level = (int)lvl; g_b = (int)b; g_t = t; g_delta = (int)(lvl - cur_fl); g_x = seq + gl; }
+        // ---- 6. the level at window lane a: lanes [a, a + n)
+        const uint32_t n = lev ? (uint32_t)__ffs((int)(lv >> (a + 1))) : 0u;
+        const bool act = lev && (uint32_t)gl >= a && (uint32_t)gl < a + n;
+        const uint32_t key = e.x, pred = e.y;
+        double sc = -1.0;
+        uint32_t bkey = 0;
+        if (act) {
+            // never-scored predecessors count 0 (cns_aux.c:63-70)
+            double rs = 0.0;
+            if (pred != CNS_NOPRED) {
+                const uint32_t d = x + (uint32_t)gl - pred;
+                if (d >= (uint32_t)SR) redo = true;
+                rs = SC[(sq + (uint32_t)gl - d) & (SR - 1)];
+            }
+            const double s1 = __dadd_rn(__hiloint2double((int)e.w, (int)e.z), rs);
+            if (s1 > -1.0) { sc = s1; bkey = key; }         // a link has to score above -1 to count (cns_aux.c:160,170)
         }
-        if (in && (me.x & CNS_C_LEVEL)) { const uint32_t lvl = level + (uint32_t)mylev; if (lvl < TP.level_cap) bp[lvl].w = prev_fl; }
-        level += (uint32_t)nlev;
-        c += (uint32_t)take; seq += (uint32_t)take;
+        // the longest node of the level decides the rounds (all groups of the warp run the same number)
+        int rounds = 0;
+        {
+            uint32_t z = lev ? ((~nd) >> a) & ((1u << n) - 1u) : 0u;     // window lanes of the level that continue a node
+            while (z) { z &= z >> 1; ++rounds; }
+        }
+        rounds = __reduce_max_sync(full, rounds);
+        if (rounds) {
+            const int node_end = act ? gl + __ffs((int)(nd >> (gl + 1))) : 0;      // the next node start above me (the level's end is one)
+            const double msc = sc;
+            const uint32_t mkey = bkey;
+            for (int r = 1; r <= rounds; ++r) {
+                const double osc = __shfl_down_sync(full, msc, r, G);
+                const uint32_t okey = __shfl_down_sync(full, mkey, r, G);
+                if (gl + r < node_end && (osc > sc || (osc == sc && CNS_K_RANK(okey) < CNS_K_RANK(bkey)))) { sc = osc; bkey = okey; }
+            }
+        }
+        if (act && (key & CNS_K_NODE)) {
+            SC[(sq + (uint32_t)gl) & (SR - 1)] = sc;
+            const uint32_t lb = level * 8 + ((key >> 20) & 7u);
+            if (level < TP.level_cap) bp16[lb] = (uint16_t)((CNS_K_RANK(bkey) << 3) | ((bkey >> 16) & 7u)); else fail = 1;
+            if (sc > g_best) { g_best = sc; g_x = sq + (uint32_t)gl; g_lb = lb; g_t = t; g_fl = cur_fl; }
+            if ((uint32_t)gl == a && level < TP.level_cap) bp[level].w = prev_fl;
+        }
+        if (lev) { ++level; a += n; }
     }
-    cns_cp_async_wait(0);
+    redo = ((__ballot_sync(full, redo) >> gsh) & GM) != 0;
+    const bool gfail = ((__ballot_sync(full, fail != 0) >> gsh) & GM) != 0;
     if (gl == 0 && slot < P.n_tpl) {
         if (redo) P.redo[atomicAdd(P.n_redo, 1u)] = ti;
-        else {
-            if (fail) atomicOr(P.error_flag, fail);
+        else if (!P.dp_serial) {
+            if (gfail) atomicOr(P.error_flag, 1u);
             atomicAdd(P.counters + 0, (unsigned long long)level);
         }
     }
 }
 
-// The same recurrence for the templates k_cns_dp could not finish (a predecessor further back than its score ring):
-// one thread per template, over the position records, node scores kept in the first link of each node in HBM.
+// The same recurrence for the templates k_cns_dp could not finish (a predecessor further back than its score ring) and
+// for min_cov < 1 (runs may then hold positions without links): one thread per template, over the position records,
+// node scores kept in the weight field of the first link of each node in HBM.
 __global__ void __launch_bounds__(128)
 k_cns_dp_serial(CnsParams P)
 {
@@ -1122,30 +936,32 @@ k_cns_dp_serial(CnsParams P)
             if (ps.n == 0) continue;
             prev_fl = cur_fl; cur_fl = level;
             bool have_node = false, chosen = false;
-            uint32_t cur_b = 0, node_first = 0, best_aux = 0;
+            uint32_t cur_b = 0, node_first = 0, best_key = 0;
             double best = -1.0;
             auto close_node = [&]() {
                 const double ns = chosen ? best : -1.0;
                 link[node_first].w = ns;
-                if (level < TP.level_cap) bp[level].code[cur_b] = (uint16_t)(chosen ? (best_aux >> 16) & 0x7ffu : 7u);
+                if (level < TP.level_cap) bp[level].code[cur_b] = (uint16_t)(chosen ? (CNS_K_RANK(best_key) << 3) | ((best_key >> 16) & 7u) : 0u);
                 if (ns > g_best) { g_best = ns; g_level = (int)level; g_b = (int)cur_b; g_t = t; g_delta = (int)(level - cur_fl); }
             };
             for (uint32_t i = 0; i < ps.n; ++i) {
                 const uint32_t x = ps.start + i;
                 const uint4 e = *reinterpret_cast<const uint4*>(link + x);
-                if (e.x & CNS_C_NODE) {
+                const uint32_t key = e.x, pred = e.y;
+                if (key & CNS_K_NODE) {
                     if (have_node) close_node();
-                    if ((e.x & CNS_C_LEVEL) && i > 0) {
+                    if ((key & CNS_K_LEVEL) && i > 0) {
                         if (level < TP.level_cap) bp[level].prev_first_level = prev_fl; else fail |= 1;
                         ++level;
                     }
-                    have_node = true; cur_b = e.x & 7u; node_first = x; best = -1.0; best_aux = 0; chosen = false;
+                    have_node = true; cur_b = (key >> 20) & 7u; node_first = x; best = -1.0; chosen = false;
                 }
                 double sc = __hiloint2double((int)e.w, (int)e.z);
-                const uint32_t dist = e.y & 0xffffu;
-                if (dist) sc = __dadd_rn(sc, link[dist <= i ? x - dist : pv_end - (dist - i)].w);
-                const bool better = chosen ? (sc > best || (sc == best && (e.y >> 27) < (best_aux >> 27))) : (sc > -1.0);
-                if (better) { best = sc; best_aux = e.y; chosen = true; }
+                // a predecessor in the previous position: pred counts back from this position's first link as if that
+                // position's links were stored right before it (they are, except across a span boundary: k_cns_fix)
+                if (pred != CNS_NOPRED) sc = __dadd_rn(sc, link[pred >= ps.start ? pred : pv_end - (ps.start - pred)].w);
+                const bool better = chosen ? (sc > best || (sc == best && CNS_K_RANK(key) < CNS_K_RANK(best_key))) : (sc > -1.0);
+                if (better) { best = sc; best_key = key; chosen = true; }
             }
             if (have_node) close_node();
             if (level < TP.level_cap) bp[level].prev_first_level = prev_fl; else fail |= 1;
@@ -1201,14 +1017,14 @@ k_cns_walk(CnsParams P)
                     const uint4 lv = W[cs - wlo];                                           // five 16-bit codes (x, y, z), prev_first_level (w)
                     const uint32_t word = cb < 2 ? lv.x : (cb < 4 ? lv.y : lv.z);
                     const uint32_t code = (word >> ((cb & 1) << 4)) & 0xffffu;
-                    const uint32_t pb = code & 7;
-                    if (pb == 7) { finished = true; break; }    // best_p_t_pos == -1: this node is not emitted
+                    const uint32_t pb = code & 7, prank = code >> 3;           // predecessor base, predecessor rank (0: none)
+                    if (prank == 0) { finished = true; break; }     // best_p_t_pos == -1: this node is not emitted
                     const int emit = cb;
                     int ns, nt, nd;
                     bool stop_after = false;
                     if (cd > 0) { ns = cs - 1; nt = ct; nd = cd - 1; }
                     else {
-                        nt = ct - 1; nd = (int)(code >> 3);
+                        nt = ct - 1; nd = (int)((prank - 1 - cns_char_rank(pb)) / 5u);     // rank = 1 + delta * 5 + base rank
                         if (nt < R.from) { stop_after = true; ns = 0; }     // predecessor outside the run: never scored
                         else ns = (int)lv.w + nd;
                     }
