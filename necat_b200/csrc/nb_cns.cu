@@ -420,12 +420,18 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                 std::vector<std::thread> th;
                 std::vector<size_t> todo;
                 for (size_t t = g.t0; t < g.t1; ++t) if (tpls[t].stage != 2) todo.push_back(t);
-                const size_t per = (todo.size() + nthreads - 1) / nthreads;
-                for (unsigned w = 0; w < nthreads && per; ++w) {
-                    const size_t a = w * per, b = std::min(todo.size(), a + per);
-                    if (a >= b) break;
-                    th.emplace_back([&, a, b]() { for (size_t x = a; x < b; ++x) replay(tpls[todo[x]], cans, g.res, o, (size_t)reads->nseq); });
-                }
+                // the templates are sorted by length: handed out a few at a time, not in equal ranges
+                std::atomic<size_t> next_todo(0);
+                auto work = [&]() {
+                    for (;;) {
+                        const size_t a = next_todo.fetch_add(8), b = std::min(todo.size(), a + 8);
+                        if (a >= todo.size()) break;
+                        for (size_t x = a; x < b; ++x) replay(tpls[todo[x]], cans, g.res, o, (size_t)reads->nseq);
+                    }
+                };
+                const unsigned nw = (unsigned)std::min<size_t>(nthreads, (todo.size() + 7) / 8);
+                for (unsigned w = 1; w < nw; ++w) th.emplace_back(work);
+                work();
                 for (auto& x : th) x.join();
             }
             g.tm.replay += gt.lap();
@@ -695,8 +701,8 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             if ((rc = D.get(&P.rev, level_total))) return rc;
             static const int kLinksCtas = getenv("NB_CNS_LINKS_CTAS") ? atoi(getenv("NB_CNS_LINKS_CTAS")) : 6;
             const unsigned links_grid = NB_SMS * (unsigned)(kLinksCtas < 1 ? 1 : kLinksCtas);
-            if ((rc = D.get(&P.cursor, (size_t)2 * links_grid * CNS_WARPS * CNS_MAX_ALN))) return rc;     // x 2: two slices side by side
-            if ((rc = D.get(&P.ovpool, (size_t)2 * links_grid * CNS_WARPS * CNS_OV))) return rc;
+            if ((rc = D.get(&P.cursor, (size_t)links_grid * CNS_WARPS * CNS_MAX_ALN))) return rc;
+            if ((rc = D.get(&P.ovpool, (size_t)links_grid * CNS_WARPS * CNS_OV))) return rc;
             if ((rc = D.get(&P.error_flag, 1))) return rc;
             if ((rc = D.get(&P.counters, 4))) return rc;
             if ((rc = D.get(&P.runs, seg_total))) return rc;
@@ -721,39 +727,52 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             out.tm.wait += pt.lap();
             cudaEventRecord(cx->ev2, cst);
             {
-                // The templates are sorted by length.  The best-path kernel is a dependent chain over a template's levels:
-                // for the longest templates it lasts several times longer than all their other kernels together, while
-                // it keeps only a few warps busy.  So the longest templates (slice 0, kLongShare of the bases) run on a
-                // side stream of their own, and their chain is hidden behind the link building of everything else.
+                // The templates are sorted by length.  The best-path kernel is a dependent chain over a template's levels: it
+                // lasts as long as its longest template has levels and keeps few warps busy, while the link kernel is
+                // throughput work that fills the machine.  So the templates are cut into slices, every slice on a stream
+                // of its own: the link kernels run one after the other (events), and the chain of a slice runs beside the
+                // link kernels of the slices behind it.  Slice 0 holds the longest templates (kLongPct of the bases) and
+                // gets a warp per template; the rest is cut into kRest slices of equal size.
                 static const int kLongPct = getenv("NB_CNS_LONG_PCT") ? atoi(getenv("NB_CNS_LONG_PCT")) : 8;
-                size_t cutx = 0;
+                static const int kRest = getenv("NB_CNS_SLICES") ? atoi(getenv("NB_CNS_SLICES")) : 3;
+                std::vector<size_t> cut(1, 0);
                 if (kLongPct > 0 && dt.size() >= (getenv("NB_CNS_LONG_PCT") ? 4u : 64u)) {
                     uint64_t total_T = 0, acc = 0;
                     for (const auto& ct : dt) total_T += (uint64_t)ct.T;
+                    size_t cutx = 0;
                     while (cutx < dt.size() && acc * 100 < total_T * (uint64_t)kLongPct) acc += (uint64_t)dt[cutx++].T;
-                    if (cutx >= dt.size()) cutx = 0;
+                    if (cutx < dt.size()) {
+                        cut.push_back(cutx);
+                        const int nrest = std::max(1, std::min(kRest, NB_AUX - 1));
+                        const uint64_t rest_T = total_T - acc;
+                        uint64_t racc = 0;
+                        for (size_t x = cutx; x < dt.size(); ++x) {
+                            racc += (uint64_t)dt[x].T;
+                            if ((int)cut.size() < nrest + 1 && racc * (uint64_t)nrest >= rest_T * (uint64_t)(cut.size() - 1) && x + 1 < dt.size()) cut.push_back(x + 1);
+                        }
+                    }
                 }
-                const int nsl = cutx ? 2 : 1;
+                cut.push_back(dt.size());
+                const int nsl = (int)cut.size() - 1;
                 uint32_t* d_ctr;                                    // per slice: unit queue, redo count
-                if ((rc = D.get(&d_ctr, 8))) return rc;
-                NB_CUDA(cx, cudaMemsetAsync(d_ctr, 0, sizeof(uint32_t) * 8, cst));
+                if ((rc = D.get(&d_ctr, 2 * NB_AUX))) return rc;
+                NB_CUDA(cx, cudaMemsetAsync(d_ctr, 0, sizeof(uint32_t) * 2 * NB_AUX, cst));
                 if (nsl > 1) {
-                    NB_CUDA(cx, cudaEventRecord(cx->aux_ev[2], cst));
-                    for (int k = 0; k < 2; ++k) NB_CUDA(cx, cudaStreamWaitEvent(cx->aux[k], cx->aux_ev[2], 0));
+                    NB_CUDA(cx, cudaEventRecord(cx->aux_ev[NB_AUX], cst));
+                    for (int k = 0; k < nsl; ++k) NB_CUDA(cx, cudaStreamWaitEvent(cx->aux[k], cx->aux_ev[NB_AUX], 0));
                 }
                 for (int sl = 0; sl < nsl; ++sl) {
-                    const size_t a = sl == 0 ? 0 : cutx, b = (sl == 0 && nsl > 1) ? cutx : dt.size();
+                    const size_t a = cut[(size_t)sl], b = cut[(size_t)sl + 1];
                     cudaStream_t ss = nsl == 1 ? cst : cx->aux[sl];
                     CnsParams Q = P;
                     Q.tpl0 = d_tpl; Q.tpl = d_tpl + a; Q.n_tpl = (uint32_t)(b - a);
                     Q.tpl_nseg = P.tpl_nseg + a; Q.tpl_nrun = P.tpl_nrun + a; Q.redo = P.redo + a;
-                    Q.next_unit = d_ctr + sl; Q.n_redo = d_ctr + 4 + sl;
+                    Q.next_unit = d_ctr + sl; Q.n_redo = d_ctr + NB_AUX + sl;
                     const uint32_t u0 = dt[a].unit_first, u1 = b < dt.size() ? dt[b].unit_first : (uint32_t)units.size();
                     Q.unit = d_unit + u0; Q.n_units = u1 - u0;
                     const uint32_t al0 = dt[a].aln_first, al1 = b < dt.size() ? dt[b].aln_first : (uint32_t)alns.size();
                     Q.aln = d_aln;                                  // (CnsTemplate::aln_first indexes all alignments)
-                    Q.cursor = P.cursor + (size_t)sl * links_grid * CNS_WARPS * CNS_MAX_ALN;
-                    Q.ovpool = P.ovpool + (size_t)sl * links_grid * CNS_WARPS * CNS_OV;
+                    Q.cursor = P.cursor; Q.ovpool = P.ovpool;      // (the link kernels run one at a time)
                     const unsigned n_tpl = Q.n_tpl;
                     unsigned g = (n_tpl + 3) / 4;
                     if (g > NB_SMS * 16) g = NB_SMS * 16;
@@ -769,19 +788,23 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                     }
                     // with the long slice's chain running beside them, the links of the rest leave it room on the SMs
                     unsigned lmax = links_grid;
-                    if (nsl > 1 && sl == 1 && links_grid > NB_SMS) lmax = links_grid - NB_SMS * 2 > NB_SMS ? links_grid - NB_SMS * 2 : NB_SMS;
+                    if (nsl > 1 && sl >= 1 && links_grid > NB_SMS) lmax = links_grid - NB_SMS * 2 > NB_SMS ? links_grid - NB_SMS * 2 : NB_SMS;
                     unsigned lg = (unsigned)((Q.n_units + CNS_WARPS - 1) / CNS_WARPS);
                     if (lg > lmax) lg = lmax;
+                    if (nsl > 1 && sl > 0) NB_CUDA(cx, cudaStreamWaitEvent(ss, cx->link_ev[sl - 1], 0));
                     if (lg) {
                         k_cns_links<<<lg, CNS_WARPS * 32, smem, ss>>>(Q);
                         NB_LAUNCH_CHECK(cx);
+                    }
+                    if (nsl > 1) NB_CUDA(cx, cudaEventRecord(cx->link_ev[sl], ss));
+                    if (lg) {
                         k_cns_fix<<<(unsigned)((Q.n_units + 127) / 128), 128, 0, ss>>>(Q);
                         NB_LAUNCH_CHECK(cx);
                     }
                     // the longest templates (slice 0 of two) get a warp each: their chain of levels is what lasts; the rest
                     // four to a warp
                     {
-                        const bool wide = nsl > 1 && sl == 0;
+                        const bool wide = nsl > 1 && sl == 0;           // (slice 0 of several = the longest templates)
                         const unsigned per_cta = wide ? 4u : 16u;
                         const int sr = kDpTest == 1 ? 8 : 128;
                         const size_t dsm = (size_t)per_cta * sr * 8;
@@ -796,7 +819,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                     NB_LAUNCH_CHECK(cx);
                 }
                 if (nsl > 1)
-                    for (int k = 0; k < 2; ++k) {
+                    for (int k = 0; k < nsl; ++k) {
                         NB_CUDA(cx, cudaEventRecord(cx->aux_ev[k], cx->aux[k]));
                         NB_CUDA(cx, cudaStreamWaitEvent(cst, cx->aux_ev[k], 0));
                     }

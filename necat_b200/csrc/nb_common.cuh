@@ -11,6 +11,7 @@
 
 #define NB_SMS 148          // B200: 2 dies x 74 SMs
 #define NB_MAX_WORKERS 4    // pipeline workers of nb_consensus_job (the context itself is worker 0)
+#define NB_AUX 6            // side streams of a context
 
 struct nb_ctx {
     int          device;
@@ -21,8 +22,9 @@ struct nb_ctx {
     nb_map_counters mc;
     nb_cns_counters cc;
     cudaEvent_t  ev0, ev1, ev2, ev3;
-    cudaStream_t aux[2];         // side streams: slices of the consensus pipeline overlap (links of one, DP chain of another)
-    cudaEvent_t  aux_ev[3];
+    cudaStream_t aux[NB_AUX];    // side streams: slices of the consensus pipeline overlap (links of one, best-path chains of others)
+    cudaEvent_t  aux_ev[NB_AUX + 1];    // [i]: slice i has finished; [NB_AUX]: the fork
+    cudaEvent_t  link_ev[NB_AUX];       // [i]: the link kernel of slice i has finished (the next slice's waits for it)
     void*        pinned;         // pinned host staging buffer for large device-to-host copies
     size_t       pinned_bytes;
     void*        ext_mat;        // walk-back scratch of the extension kernel (kept across calls)

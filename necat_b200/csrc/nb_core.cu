@@ -117,8 +117,9 @@ static int nb_ctx_init_streams(nb_ctx* c)
     NB_CUDA(NULL, cudaEventCreate(&c->ev1));
     NB_CUDA(NULL, cudaEventCreate(&c->ev2));
     NB_CUDA(NULL, cudaEventCreate(&c->ev3));
-    for (int i = 0; i < 2; ++i) NB_CUDA(NULL, cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
-    for (int i = 0; i < 3; ++i) NB_CUDA(NULL, cudaEventCreateWithFlags(&c->aux_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < NB_AUX; ++i) NB_CUDA(NULL, cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+    for (int i = 0; i < NB_AUX + 1; ++i) NB_CUDA(NULL, cudaEventCreateWithFlags(&c->aux_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < NB_AUX; ++i) NB_CUDA(NULL, cudaEventCreateWithFlags(&c->link_ev[i], cudaEventDisableTiming));
     return NB_OK;
 }
 
@@ -152,8 +153,9 @@ extern "C" void nb_ctx_destroy(nb_ctx* c)
         cudaStreamSynchronize(k->stream);
         cudaEventDestroy(k->ev0); cudaEventDestroy(k->ev1); cudaEventDestroy(k->ev2); cudaEventDestroy(k->ev3);
         cudaStreamDestroy(k->stream);
-        for (int i = 0; i < 2; ++i) cudaStreamDestroy(k->aux[i]);
-        for (int i = 0; i < 3; ++i) cudaEventDestroy(k->aux_ev[i]);
+        for (int i = 0; i < NB_AUX; ++i) cudaStreamDestroy(k->aux[i]);
+        for (int i = 0; i < NB_AUX + 1; ++i) cudaEventDestroy(k->aux_ev[i]);
+        for (int i = 0; i < NB_AUX; ++i) cudaEventDestroy(k->link_ev[i]);
         if (k->ext_mat) cudaFree(k->ext_mat);
         if (k->pinned) cudaFreeHost(k->pinned);
         free(k);
@@ -164,8 +166,9 @@ extern "C" void nb_ctx_destroy(nb_ctx* c)
     cudaEventDestroy(c->ev2);
     cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->stream);
-    for (int i = 0; i < 2; ++i) cudaStreamDestroy(c->aux[i]);
-    for (int i = 0; i < 3; ++i) cudaEventDestroy(c->aux_ev[i]);
+    for (int i = 0; i < NB_AUX; ++i) cudaStreamDestroy(c->aux[i]);
+    for (int i = 0; i < NB_AUX + 1; ++i) cudaEventDestroy(c->aux_ev[i]);
+    for (int i = 0; i < NB_AUX; ++i) cudaEventDestroy(c->link_ev[i]);
     if (c->ext_mat) cudaFree(c->ext_mat);
     nb_dev_cache_destroy(c);
     if (c->pinned) cudaFreeHost(c->pinned);

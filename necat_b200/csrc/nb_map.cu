@@ -22,6 +22,7 @@
 // The reference's per-thread dense ScoringBlock table over the whole volume
 // (252 B x volume/2000) becomes a per-unit sorted list of touched blocks.
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "nb_common.cuh"
@@ -695,6 +696,10 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
 {
     *too_big = false;
     cudaStream_t st = ctx->stream;
+    const bool trace = getenv("NB_TRACE") != NULL;
+    std::chrono::steady_clock::time_point tr0 = std::chrono::steady_clock::now();
+    double tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto lap = [&](int i) { auto t1 = std::chrono::steady_clock::now(); tr[i] += std::chrono::duration<double, std::milli>(t1 - tr0).count(); tr0 = t1; };
     const uint64_t nreads = read_hi - read_lo;
     if (nreads == 0) return NB_OK;
     if (nreads * 2 >= (1ull << 31)) return nb_fail(ctx, NB_ELIMIT, "too many reads in one call");
@@ -747,6 +752,7 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
     NB_CUDA(ctx, cudaMemsetAsync(P.counters, 0, 8 * sizeof(unsigned long long), st));
     NB_CUDA(ctx, cudaMemcpyAsync(d_probe_base, probe_base.data(), sizeof(uint64_t) * (U + 1), cudaMemcpyHostToDevice, st));
 
+    lap(0);
     cudaEventRecord(ctx->ev0, st);
     if (probe_smem > 48 * 1024)
         NB_CUDA(ctx, cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probe_smem));
@@ -757,6 +763,7 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
     std::vector<uint32_t> unit_hits(U);
     NB_CUDA(ctx, cudaMemcpyAsync(unit_hits.data(), P.unit_hits, sizeof(uint32_t) * U, cudaMemcpyDeviceToHost, st));
     NB_CUDA(ctx, cudaStreamSynchronize(st));
+    lap(1);
     std::vector<uint64_t> hit_base(U + 1), scratch_base(U);
     uint64_t H = 0, scratch = 0;
     for (uint32_t u = 0; u < U; ++u) {
@@ -789,6 +796,7 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
     if ((rc = S.get(&P.dp_v, H))) return rc;
     if ((rc = S.get(&P.sort_scratch, scratch))) return rc;
 
+    lap(2);
     k_build_blocks<<<U, BUILD_THREADS, 0, st>>>(P);
     NB_LAUNCH_CHECK(ctx);
     cudaEventRecord(ctx->ev1, st);
@@ -796,6 +804,7 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
     unsigned long long cnts[8];
     NB_CUDA(ctx, cudaMemcpyAsync(cnts, P.counters, sizeof cnts, cudaMemcpyDeviceToHost, st));
     NB_CUDA(ctx, cudaStreamSynchronize(st));
+    lap(3);
     const uint64_t E = cnts[3];
     if ((rc = S.get(&P.out, E))) return rc;
     if ((rc = S.get(&P.out_unit, E))) return rc;
@@ -806,6 +815,7 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
     cudaEventRecord(ctx->ev2, st);
     NB_CUDA(ctx, cudaMemcpyAsync(cnts, P.counters, sizeof cnts, cudaMemcpyDeviceToHost, st));
     NB_CUDA(ctx, cudaStreamSynchronize(st));
+    lap(4);
     const uint64_t C = cnts[0];
     std::vector<nb_candidate> cand(C);
     std::vector<uint32_t> cu(C), cseq(C);
@@ -822,6 +832,7 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
     ctx->tm.d2h_bytes += C * (sizeof(nb_candidate) + 8) + U * 4;
     ctx->tm.h2d_bytes += (U + 1) * 16 + U * 8;
 
+    lap(5);
     // ---- host: per-read grouping (FWD before REV, emission order), -n truncation, global ids
     std::vector<uint64_t> order(C);
     {
@@ -864,6 +875,9 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
         for (auto& c : one) { acc.push_back(c); ++nres; }
         i = j;
     }
+    lap(6);
+    if (trace) fprintf(stderr, "[nb_map_range] wall ms: layout+alloc %.2f probe+sync %.2f hit layout+alloc %.2f blocks+sync %.2f candidates+sync %.2f download %.2f grouping %.2f\n",
+                       tr[0], tr[1], tr[2], tr[3], tr[4], tr[5], tr[6]);
     ctx->mc.n_units += U; ctx->mc.n_probes += np; ctx->mc.n_hits += H; ctx->mc.n_seeds += cnts[1];
     ctx->mc.n_blocks += cnts[2]; ctx->mc.n_eligible += cnts[3]; ctx->mc.n_candidates += nres; ctx->mc.query_bases += qbases * 2;
     return NB_OK;
