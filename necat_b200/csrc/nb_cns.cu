@@ -351,6 +351,8 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         ChunkTimes tm;
         int rc = NB_OK;
         std::atomic<int>* round0_done = NULL;    // set once the group's first (by far largest) extension launch has finished
+        std::atomic<int>* submitted = NULL;      // pipelined groups: set when the group's first launch is being queued
+        std::atomic<int>* prev_submitted = NULL; // ... that of the group before
     };
     const char* env_groups = getenv("NB_CNS_GROUPS");
     // default 1: with the replay's per-base loops vectorised, what several groups hide of the host phases is less than what their
@@ -363,7 +365,25 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
     std::vector<ExtGroup> groups((size_t)n_groups);
     // the job put its longest templates first (sh.n_long of them): they form group 0 of the first chunk
     const bool long_mode = n_groups >= 2 && c0 == 0 && sh.n_long > 0 && sh.n_long < c1;
-    {
+    // Pipelined groups (several groups, not the long-template mode): group k takes every n-th template of the
+    // length-sorted list, so the groups are alike; each has its own stream, walk-back scratch and host thread, nothing is
+    // locked.  The first extension launches are queued in group order: the persistent CTAs of group k + 1 move in as those
+    // of group k drain (no idle tail), and while group k + 1 extends, the host replays group k and prepares its consensus,
+    // whose kernels in turn run behind group k + 1's extension.
+    static const int kOverlap = getenv("NB_CNS_OVERLAP") ? atoi(getenv("NB_CNS_OVERLAP")) : 1;
+    const bool overlap = kOverlap && n_groups > 1 && !long_mode;
+    if (overlap) {
+        const size_t n = c1 - c0, ng = (size_t)n_groups;
+        std::vector<Tpl> re;
+        re.reserve(n);
+        size_t t = c0;
+        for (size_t k = 0; k < ng; ++k) {
+            groups[k].t0 = t;
+            for (size_t i = k; i < n; i += ng) { re.push_back(std::move(tpls[c0 + i])); ++t; }
+            groups[k].t1 = t;
+        }
+        for (size_t i = 0; i < n; ++i) tpls[c0 + i] = std::move(re[i]);
+    } else {
         const size_t r0 = long_mode ? sh.n_long : c0;
         const int first = long_mode ? 1 : 0;
         if (long_mode) { groups[0].t0 = c0; groups[0].t1 = r0; }
@@ -386,6 +406,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         if (k > 0) { const int rc = nb_worker_ctx(ctx, k, &g.wc); if (rc) return rc; }
         // with the long group's consensus running beside them, the other groups' extension kernels leave it room on the SMs
         g.wc->ext_ctas = (long_mode && k > 0) ? 2 : 0;
+        g.wc->ext_private = (overlap && k > 0) ? 1 : 0;
         group_bufs.emplace_back(g.wc);
         g.D = &group_bufs.back();
     }
@@ -495,10 +516,13 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             if ((rc = g.D->get(&d_tasks, tasks.size()))) return rc;
             if ((rc = g.D->get(&d_res, tasks.size()))) return rc;
             if ((rc = g.D->get(&d_ops, pool + 64))) return rc;
-            std::unique_lock<std::mutex> gpu(sh.gpu);
+            std::unique_lock<std::mutex> gpu(sh.gpu, std::defer_lock);
+            if (!overlap) gpu.lock();
+            else if (round == 0 && g.prev_submitted) while (!g.prev_submitted->load()) std::this_thread::yield();   // launches queue in group order
             g.tm.wait += gt.lap();
             NB_CUDA(wc, cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(ExtTask) * tasks.size(), cudaMemcpyHostToDevice, gst));
             cudaEventRecord(wc->ev0, gst);
+            if (round == 0 && g.submitted) g.submitted->store(1);
             rc = nb_run_extension(wc, reads, reads, d_tasks, (uint32_t)tasks.size(), d_res, d_ops, o.error, o.min_align_size, 4 /* ONC_TAIL_MATCH_LEN_LONG */);
             if (rc) return rc;
             cudaEventRecord(wc->ev1, gst);
@@ -563,7 +587,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
                     }
                 }
             }
-            gpu.unlock();
+            if (gpu.owns_lock()) gpu.unlock();
             float ms = 0; cudaEventElapsedTime(&ms, wc->ev0, wc->ev1); g.tm.ext_ms += ms;
             wc->tm.h2d_bytes += sizeof(ExtTask) * tasks.size();
             wc->tm.d2h_bytes += sizeof(nb_alignment) * tasks.size();
@@ -967,14 +991,6 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         }
         memset(&wc->cc, 0, sizeof wc->cc); memset(&wc->tm, 0, sizeof wc->tm);
     };
-    // Overlap mode (several groups): every group runs its own consensus right after its extension rounds, on its own
-    // stream and WITHOUT the GPU lock, while the next group's extension kernel holds the machine.  The best-path kernel
-    // of a group is a dependent chain over its longest template (the groups are cut from the length-sorted templates:
-    // group 0 has the longest) and keeps few warps busy; the extension kernel leaves it room (2 CTAs per SM instead
-    // of 3).  The groups start their first -- by far largest -- extension launch in order, so that group k's consensus
-    // falls behind group k + 1's extension.
-    static const int kOverlap = getenv("NB_CNS_OVERLAP") ? atoi(getenv("NB_CNS_OVERLAP")) : 1;
-    const bool overlap = kOverlap && n_groups > 1 && !long_mode;
     std::mutex emit_mx;
     std::vector<CnsOut> outs((size_t)n_groups);
     std::vector<int> cns_rc((size_t)n_groups, NB_OK);
@@ -987,13 +1003,12 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
         auto group_work = [&](int k) {
             ExtGroup& g = groups[(size_t)k];
             if (overlap) {
-                g.round0_done = &r0done[(size_t)k];
-                g.wc->ext_ctas = 2;
-                if (k > 0) while (!r0done[(size_t)k - 1].load()) std::this_thread::yield();
+                g.submitted = &r0done[(size_t)k];
+                if (k > 0) g.prev_submitted = &r0done[(size_t)k - 1];
             }
             g.rc = ext_phase(g);
             if (overlap) {
-                r0done[(size_t)k].store(1);
+                r0done[(size_t)k].store(1);                 // (also when the group had nothing to launch)
                 if (g.rc == NB_OK && g.t0 < g.t1) {
                     cns_rc[(size_t)k] = cns_phase(g.wc, g.t0, g.t1, outs[(size_t)k], false);
                     if (cns_rc[(size_t)k] == NB_OK) { std::lock_guard<std::mutex> lk(emit_mx); cns_rc[(size_t)k] = emit(outs[(size_t)k]); }

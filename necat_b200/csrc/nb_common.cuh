@@ -37,6 +37,7 @@ struct nb_ctx {
     int          is_worker;
     nb_ctx*      parent;         // of a worker: the context that owns the shared scratch (extension kernel launches are serialised)
     int          ext_ctas;       // k_extend CTAs per SM for launches of this context (0 = default)
+    int          ext_private;    // 1: this worker's extension launches use its own walk-back scratch (they may run beside the parent's)
 };
 
 struct nb_volume {

@@ -612,7 +612,7 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     }
     const size_t slots = (size_t)NB_SMS * (kCtas < 1 ? 1 : kCtas) * EXT_WARPS * EXT_SLOTS;      // candidates in flight (sized for the full grid)
     // the scratch belongs to the job's context: its workers' launches never run side by side (nb_consensus_job's GPU lock)
-    nb_ctx* own = ctx->parent ? ctx->parent : ctx;
+    nb_ctx* own = (ctx->parent && !ctx->ext_private) ? ctx->parent : ctx;
     if (!own->ext_mat || own->ext_mat_slots < slots) {
         if (own->ext_mat) cudaFree(own->ext_mat);
         own->ext_mat = NULL;

@@ -851,18 +851,27 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
     }
     uint64_t nres = 0;
     std::vector<nb_candidate> one;
+    acc.reserve(acc.size() + C);
     for (uint64_t i = 0; i < C;) {
         uint64_t j = i;
         const uint32_t rd = cu[order[i]] >> 1;
-        one.clear();
-        while (j < C && (cu[order[j]] >> 1) == rd) {
-            nb_candidate c = cand[order[j]];
-            c.qid += read_start_id;     // pm_worker.c:164-167
-            c.sid += ref_start_id;
-            one.push_back(c);
-            ++j;
-        }
-        if (one.size() > (size_t)opt->num_candidates) {     // pm_worker.c:168-171, order of pm_worker.c:15-24
+        while (j < C && (cu[order[j]] >> 1) == rd) ++j;
+        if (j - i <= (uint64_t)opt->num_candidates) {
+            for (uint64_t x = i; x < j; ++x) {
+                nb_candidate c = cand[order[x]];
+                c.qid += read_start_id;     // pm_worker.c:164-167
+                c.sid += ref_start_id;
+                acc.push_back(c);
+            }
+            nres += j - i;
+        } else {                            // pm_worker.c:168-171, order of pm_worker.c:15-24
+            one.clear();
+            for (uint64_t x = i; x < j; ++x) {
+                nb_candidate c = cand[order[x]];
+                c.qid += read_start_id;
+                c.sid += ref_start_id;
+                one.push_back(c);
+            }
             std::stable_sort(one.begin(), one.end(), [](const nb_candidate& a, const nb_candidate& b) {
                 if (a.score != b.score) return a.score > b.score;
                 if (a.qdir != b.qdir) return a.qdir < b.qdir;
@@ -871,8 +880,8 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
                 return a.soff < b.soff;
             });
             one.resize((size_t)opt->num_candidates);
+            for (auto& c : one) { acc.push_back(c); ++nres; }
         }
-        for (auto& c : one) { acc.push_back(c); ++nres; }
         i = j;
     }
     lap(6);
