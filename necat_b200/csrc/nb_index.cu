@@ -277,11 +277,14 @@ k_bucket_scan(uint32_t* __restrict__ bucket_kept, const uint32_t* __restrict__ b
 }
 
 // ---- per bucket: the slice of the table, the positions run by run
+// In the scan a thread owns 32 consecutive entries (= one word of the drop mask); with entry i at i ^ ((i >> 5) & 31) the 32
+// threads of a warp are on 32 different banks there, and a warp reading consecutive entries still is.
+#define IDX_SW(i) ((i) ^ (((i) >> 5) & 31u))
 __global__ void __launch_bounds__(IDX_FILL_THREADS)
 k_bucket_fill(const uint2* __restrict__ pairs, const uint32_t* __restrict__ bbase, const uint32_t* __restrict__ kbase, IdxGeom G, uint32_t q,
               uint32_t* __restrict__ tbl, uint32_t* __restrict__ offs, uint32_t* __restrict__ long_list, uint32_t* __restrict__ n_long)
 {
-    extern __shared__ __align__(16) uint32_t s_a[];             // [IDX_BUCKET] counts, then ends, then starts of the runs
+    extern __shared__ __align__(16) uint32_t s_a[];             // [IDX_BUCKET] counts, then ends, then starts of the runs; entry i lives at IDX_SW(i)
     __shared__ uint32_t s_drop[IDX_BUCKET / 32];                // bit: the k-mer occurs more than q times
     __shared__ uint32_t s_warp[33];
     const uint32_t per = IDX_BUCKET / IDX_FILL_THREADS;         // consecutive hash values of a thread in the scan: 32 = one word of s_drop
@@ -294,31 +297,31 @@ k_bucket_fill(const uint2* __restrict__ pairs, const uint32_t* __restrict__ bbas
             for (uint32_t i = threadIdx.x; i < nh; i += blockDim.x) tbl[(size_t)h0 + i + 1] = kb;
             continue;
         }
-        for (uint32_t i = threadIdx.x; i < IDX_BUCKET; i += blockDim.x) s_a[i] = 0;
+        for (uint32_t i = threadIdx.x; i < IDX_BUCKET; i += blockDim.x) s_a[IDX_SW(i)] = 0;
         __syncthreads();
-        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_a[pairs[i].x & (IDX_BUCKET - 1)], 1u);
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) { const uint32_t hl = pairs[i].x & (IDX_BUCKET - 1); atomicAdd(&s_a[IDX_SW(hl)], 1u); }
         __syncthreads();
         {
             const uint32_t i0 = threadIdx.x * per;
             uint32_t drop = 0, sum = 0;
-            for (uint32_t j = 0; j < per; ++j) { const uint32_t c = s_a[i0 + j]; if (c > q) drop |= 1u << j; else sum += c; }
+            for (uint32_t j = 0; j < per; ++j) { const uint32_t c = s_a[IDX_SW(i0 + j)]; if (c > q) drop |= 1u << j; else sum += c; }
             s_drop[threadIdx.x] = drop;
             uint32_t run = block_scan_excl(sum, s_warp, NULL);
-            for (uint32_t j = 0; j < per; ++j) { const uint32_t c = s_a[i0 + j]; if (!((drop >> j) & 1)) run += c; s_a[i0 + j] = run; }     // end of the run
+            for (uint32_t j = 0; j < per; ++j) { const uint32_t c = s_a[IDX_SW(i0 + j)]; if (!((drop >> j) & 1)) run += c; s_a[IDX_SW(i0 + j)] = run; }     // end of the run
         }
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < nh; i += blockDim.x) tbl[(size_t)h0 + i + 1] = kb + s_a[i];
+        for (uint32_t i = threadIdx.x; i < nh; i += blockDim.x) tbl[(size_t)h0 + i + 1] = kb + s_a[IDX_SW(i)];
         __syncthreads();
         for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
             const uint2 e = pairs[i];
             const uint32_t hl = e.x & (IDX_BUCKET - 1);
             if ((s_drop[hl >> 5] >> (hl & 31)) & 1) continue;
-            offs[kb + atomicSub(&s_a[hl], 1u) - 1] = e.y;       // the run fills from its end; s_a[hl] ends up as its start
+            offs[kb + atomicSub(&s_a[IDX_SW(hl)], 1u) - 1] = e.y;       // the run fills from its end; s_a[IDX_SW(hl)] ends up as its start
         }
         __syncthreads();
         // ascending positions inside every run (the reference gets them from scan order + a stable sort)
         for (uint32_t i = threadIdx.x; i < IDX_BUCKET; i += blockDim.x) {
-            const uint32_t st = s_a[i], en = i + 1 < IDX_BUCKET ? s_a[i + 1] : kept;
+            const uint32_t st = s_a[IDX_SW(i)], en = i + 1 < IDX_BUCKET ? s_a[IDX_SW(i + 1)] : kept;
             const uint32_t n = en - st;
             if (n < 2) continue;
             if (n > LONG_RUN) { long_list[atomicAdd(n_long, 1u)] = h0 + i; continue; }
