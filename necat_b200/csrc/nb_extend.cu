@@ -428,31 +428,34 @@ __device__ __forceinline__ void lp_walk_post(WarpScratch& S, const ExtParams& P,
         const int c0 = 32 * ((nbw >> 1) - 1) + 16 + shift;              // column - cl(w) = column - 32 w + c0
         const int band_lo = P.band_test ? (W >> 1) - 32 : 0, band_hi = P.band_test ? (W >> 1) + 32 : W;
         bool moved = false;
-        while (i > 0 || j > 0) {
-            int op;
-            if (i == 0) { op = OP_TONLY; --j; }
-            else if (j == 0) { op = OP_QONLY; --i; }
-            else {
-                const int wi = (i - 1) >> 5;
-                const int rel = j - 1 - 32 * wi + c0;
-                if (rel < band_lo || rel >= band_hi) { moved = true; break; }
-                const uint2 v = mat[wi * W + rel];
-                const int bit = (i - 1) & 31;
-                if ((v.x >> bit) & 1) { op = OP_QONLY; --i; }
-                else if ((v.y >> bit) & 1) { op = OP_TONLY; --j; }
-                else {
-                    op = cached_base(C.qv, q0 + dir * (i - 1), qw, qwi) == cached_base(C.tv, t0 + dir * (j - 1), tw, twi) ? OP_MATCH : OP_MISMATCH;
-                    --i; --j;
-                }
-            }
+        // One cell per trip, no branch inside a trip (the lanes of the warp walk different candidates: whatever one of them
+        // branches on, all of them pay for): the two stored bits select the move, the bases are compared on every trip.
+        auto book = [&](int op) {
             acc |= (uint32_t)op << (8 * (r & 3));
             if ((r & 3) == 3) { rev[r >> 2] = acc; acc = 0; }
             ++r;
-            if (!found) {
-                qcnt += op != OP_TONLY; tcnt += op != OP_QONLY; ++acnt;
-                m = op == OP_MATCH ? m + 1 : 0;
-                if (m == M) found = 1;
-            }
+            const int nf = found ^ 1;
+            qcnt += nf & (op != OP_TONLY); tcnt += nf & (op != OP_QONLY); acnt += nf;
+            m = op == OP_MATCH ? m + 1 : 0;
+            found |= (m == M);
+        };
+        while (i > 0 && j > 0) {
+            const int wi = (i - 1) >> 5;
+            const int rel = j - 1 - 32 * wi + c0;
+            if ((unsigned)(rel - band_lo) >= (unsigned)(band_hi - band_lo)) { moved = true; break; }
+            const uint2 v = mat[wi * W + rel];
+            const int bit = (i - 1) & 31;
+            const uint32_t up = (v.x >> bit) & 1u;                      // cell = upper + 1: query base against a gap
+            const uint32_t lf = ((v.y >> bit) & 1u) & (up ^ 1u);        // cell = left + 1: gap against a template base
+            const uint32_t dg = (up | lf) ^ 1u;
+            const int qb = cached_base(C.qv, q0 + dir * (i - 1), qw, qwi), tb = cached_base(C.tv, t0 + dir * (j - 1), tw, twi);
+            const int op = up ? OP_QONLY : (lf ? OP_TONLY : (qb == tb ? OP_MATCH : OP_MISMATCH));
+            i -= (int)(up | dg); j -= (int)(lf | dg);
+            book(op);
+        }
+        if (!moved) {
+            for (; j > 0; --j) book(OP_TONLY);                         // row 0 of the matrix
+            for (; i > 0; --i) book(OP_QONLY);                         // column 0
         }
         if (moved) {
             // the walk left the band: the forward pass runs again with the band on this diagonal

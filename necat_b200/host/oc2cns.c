@@ -92,9 +92,7 @@ int main(int argc, char* argv[])
     fclose(pf);
 
     NBH_PHASE("volume load");
-    int dev = 0;
-    const char* devs = getenv("NECAT_B200_DEVICE");
-    if (devs) dev = atoi(devs);
+    const int dev = nbh_pick_device();
     nb_ctx* ctx = NULL;
     if (nb_ctx_create(dev, &ctx)) NBH_ERROR("%s", nb_last_error(NULL));
     NBH_PHASE("context");
@@ -150,6 +148,7 @@ int main(int argc, char* argv[])
         NBH_LOG("'%s' takes %.2lf secs.", job, nbh_now() - t0);
     }
     if (fclose(cns_out) || fclose(raw_out)) NBH_ERROR("closing the output files failed");
+    if (nbh_fast_exit()) { fflush(NULL); _exit(0); }
     nb_volume_free(ctx, dreads);
     nb_ctx_destroy(ctx);
     nbh_volume_free(&reads);

@@ -61,9 +61,7 @@ int main(int argc, char* argv[])
     nbh_volumes_info vi;
     if (nbh_volumes_info_load(wrk_dir, &vi)) NBH_ERROR("cannot read volume info in '%s'", wrk_dir);
     if (vid < 0 || vid >= vi.num_volumes) NBH_ERROR("volume id %d out of range", vid);
-    int dev = 0;
-    const char* devs = getenv("NECAT_B200_DEVICE");
-    if (devs) dev = atoi(devs);
+    const int dev = nbh_pick_device();
     nb_ctx* ctx = NULL;
     if (nb_ctx_create(dev, &ctx)) NBH_ERROR("%s", nb_last_error(NULL));
     NBH_PHASE("context");
@@ -141,6 +139,7 @@ int main(int argc, char* argv[])
     }
     if (fclose(out)) NBH_ERROR("closing '%s' failed", output);
     NBH_PHASE("mapping + output");
+    if (nbh_fast_exit()) { fflush(NULL); _exit(0); }
     nb_index_free(ctx, idx);
     nb_volume_free(ctx, dref);
     nbh_volume_free(&ref);

@@ -18,11 +18,11 @@ CN="-a 2000 -x 4 -y 12 -l 1000 -e 0.5 -p 0.8 -u 0 -r 0 -f 0"
 export NB_TRACE=1
 for i in 1 2; do
   t0=$(date +%s.%N); $B/oc2pmov $PM -t 16 vol 0 cand.bin > pm.log 2> pm.err; t1=$(date +%s.%N)
-  grep phase pm.err; echo "oc2pmov wall $(echo "$t1 - $t0" | bc) s"
+  grep phase pm.err; echo "oc2pmov wall $(python -c "print(round($t1 - $t0, 3))") s"
 done
 $B/oc2pcan -t 16 vol cand.bin > /dev/null
 for i in 1 2; do
   t0=$(date +%s.%N); $B/oc2cns $CN -t 16 vol cand.bin cns.fa raw.fa > cn.log 2> cn.err; t1=$(date +%s.%N)
-  grep -E "phase|nb_consensus" cn.err | cut -c1-300; echo "oc2cns wall $(echo "$t1 - $t0" | bc) s"
+  grep -E "phase|nb_consensus" cn.err | cut -c1-300; echo "oc2cns wall $(python -c "print(round($t1 - $t0, 3))") s"
 done
 rm -rf "$W"

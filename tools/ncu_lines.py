@@ -8,10 +8,13 @@ import sys
 rep, kern = sys.argv[1], sys.argv[2]
 skip = sys.argv[3] if len(sys.argv) > 3 else "0"
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kern, "--launch-skip", skip,
+# regex: so that template instances (k_cns_dp<8, 128>) and mangled forms match by their base name
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern, "--launch-skip", skip,
                       "--launch-count", "1", "--print-source", "cuda,sass"], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Line No")
+hi = next((i for i, r in enumerate(rows) if r and r[0] == "Line No"), None)
+if hi is None:
+    sys.exit(f"no source page for kernel '{kern}' (launch-skip {skip}) in {rep}: " + out[:300].replace("\n", " "))
 h = rows[hi]
 ci, cs = h.index("Instructions Executed"), h.index("# Samples")
 agg = {}
