@@ -12,7 +12,7 @@ HOSTC := necat_b200/host/nb_host.c
 CC    := gcc
 CFLAGS := -O2 -g -std=gnu99 -Wall
 
-all: $(LIBD)/libnecat_b200.so $(BIND)/oc2pmov $(BIND)/oc2cns $(BIND)/oc2pcan $(BIND)/oc2mkdb $(BIND)/oc2ReorderCnsReads
+all: $(LIBD)/libnecat_b200.so $(BIND)/oc2pmov $(BIND)/oc2cns $(BIND)/oc2pcan $(BIND)/oc2mkdb $(BIND)/oc2ReorderCnsReads $(BIND)/nb_helperd
 
 $(OBJD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/necat_b200.h
 	@mkdir -p $(OBJD)
@@ -28,9 +28,15 @@ $(BIND)/oc2mkdb $(BIND)/oc2ReorderCnsReads: $(BIND)/%: necat_b200/host/%.c $(HOS
 	@mkdir -p $(BIND)
 	$(CC) $(CFLAGS) -O3 -o $@ $< $(HOSTC) $(FASTX) -lz -lpthread
 
-$(BIND)/%: necat_b200/host/%.c $(HOSTC) necat_b200/host/nb_host.h $(LIBD)/libnecat_b200.so
+HELPER := necat_b200/host/nb_helper.c
+$(BIND)/%: necat_b200/host/%.c $(HOSTC) $(HELPER) necat_b200/host/nb_host.h necat_b200/host/nb_helper.h $(LIBD)/libnecat_b200.so
 	@mkdir -p $(BIND)
-	$(CC) $(CFLAGS) -o $@ $< $(HOSTC) -L$(LIBD) -lnecat_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm
+	$(CC) $(CFLAGS) -o $@ $< $(HOSTC) $(HELPER) -L$(LIBD) -lnecat_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm
+
+# the resident helper (NECAT_B200_HELPER=1): the two tools as functions of one process that keeps the CUDA context
+$(BIND)/nb_helperd: necat_b200/host/nb_helperd.c necat_b200/host/oc2pmov.c necat_b200/host/oc2cns.c $(HOSTC) $(HELPER) necat_b200/host/nb_host.h necat_b200/host/nb_helper.h $(LIBD)/libnecat_b200.so
+	@mkdir -p $(BIND)
+	$(CC) $(CFLAGS) -DNBH_AS_LIBRARY -o $@ necat_b200/host/nb_helperd.c necat_b200/host/oc2pmov.c necat_b200/host/oc2cns.c $(HOSTC) $(HELPER) -L$(LIBD) -lnecat_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm
 
 clean:
 	rm -rf build $(LIBD) $(BIND)

@@ -50,6 +50,8 @@ double nbh_now(void);
  * box costs each short-lived process several hundred ms it has no use for. */
 static inline int nbh_pick_device(void)
 {
+    static int picked = -1;                 /* decided once per process (the resident helper runs many jobs) */
+    if (picked >= 0) return picked;
     const char* devs = getenv("NECAT_B200_DEVICE");
     int dev = devs ? atoi(devs) : 0;
     if (!getenv("CUDA_VISIBLE_DEVICES") && dev >= 0) {
@@ -58,6 +60,7 @@ static inline int nbh_pick_device(void)
         setenv("CUDA_VISIBLE_DEVICES", b, 1);
         dev = 0;
     }
+    picked = dev;
     return dev;
 }
 /* End of a drop-in executable whose outputs are closed: the process image goes away without the device blocks, pinned

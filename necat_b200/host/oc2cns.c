@@ -12,7 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "nb_host.h"
+#include "nb_helper.h"
 
 static void usage(const char* prog)
 {
@@ -38,8 +38,15 @@ static size_t format_header(char* buf, size_t cap, const char* name, const nb_cn
     return (size_t)n;
 }
 
+#ifdef NBH_AS_LIBRARY
+int oc2cns_main(int argc, char* argv[])
+#else
 int main(int argc, char* argv[])
+#endif
 {
+#ifndef NBH_AS_LIBRARY
+    { int st = 0; if (nbh_try_helper(NBH_TOOL_CNS, argc, argv, &st)) return st; }      /* NECAT_B200_HELPER=1: the resident helper runs it */
+#endif
     int spid = 0, nnode = 1;
     if (argc >= 4 && strcmp(argv[argc - 3], "-mn") == 0) {       /* consensus/main.c:37-41 */
         spid = atoi(argv[argc - 2]);
@@ -94,7 +101,7 @@ int main(int argc, char* argv[])
     NBH_PHASE("volume load");
     const int dev = nbh_pick_device();
     nb_ctx* ctx = NULL;
-    if (nb_ctx_create(dev, &ctx)) NBH_ERROR("%s", nb_last_error(NULL));
+    if (nbh_ctx_get(dev, &ctx)) NBH_ERROR("%s", nb_last_error(NULL));
     NBH_PHASE("context");
     nb_volume* dreads = NULL;
     if (nb_volume_upload(ctx, reads.pac, reads.db_size, reads.offset, reads.size, reads.nseq, &dreads)) NBH_ERROR("%s", nb_last_error(ctx));
@@ -148,9 +155,9 @@ int main(int argc, char* argv[])
         NBH_LOG("'%s' takes %.2lf secs.", job, nbh_now() - t0);
     }
     if (fclose(cns_out) || fclose(raw_out)) NBH_ERROR("closing the output files failed");
-    if (nbh_fast_exit()) { fflush(NULL); _exit(0); }
+    if (nbh_fast_exit() && !nbh_in_helper) { fflush(NULL); _exit(0); }
     nb_volume_free(ctx, dreads);
-    nb_ctx_destroy(ctx);
+    nbh_ctx_put(ctx);
     nbh_volume_free(&reads);
     nbh_volumes_info_free(&vi);
     NBH_PHASE("tear-down");

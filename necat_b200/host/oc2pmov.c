@@ -15,7 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "nb_host.h"
+#include "nb_helper.h"
 
 static void usage(const char* prog)
 {
@@ -27,8 +27,15 @@ static void usage(const char* prog)
                     "-u <0 or 1>\toutput binary results: 0 = no, 1 = yes\n-i <0 or 1>\tuse header as sequence id: 0 = no, 1 = yes\n");
 }
 
+#ifdef NBH_AS_LIBRARY
+int oc2pmov_main(int argc, char* argv[])
+#else
 int main(int argc, char* argv[])
+#endif
 {
+#ifndef NBH_AS_LIBRARY
+    { int st = 0; if (nbh_try_helper(NBH_TOOL_PMOV, argc, argv, &st)) return st; }      /* NECAT_B200_HELPER=1: the resident helper runs it */
+#endif
     if (argc < 4) { usage(argv[0]); return 1; }
     nb_map_options o;
     nb_map_options_default(&o);
@@ -63,7 +70,7 @@ int main(int argc, char* argv[])
     if (vid < 0 || vid >= vi.num_volumes) NBH_ERROR("volume id %d out of range", vid);
     const int dev = nbh_pick_device();
     nb_ctx* ctx = NULL;
-    if (nb_ctx_create(dev, &ctx)) NBH_ERROR("%s", nb_last_error(NULL));
+    if (nbh_ctx_get(dev, &ctx)) NBH_ERROR("%s", nb_last_error(NULL));
     NBH_PHASE("context");
 
     nbh_volume ref;
@@ -139,12 +146,12 @@ int main(int argc, char* argv[])
     }
     if (fclose(out)) NBH_ERROR("closing '%s' failed", output);
     NBH_PHASE("mapping + output");
-    if (nbh_fast_exit()) { fflush(NULL); _exit(0); }
+    if (nbh_fast_exit() && !nbh_in_helper) { fflush(NULL); _exit(0); }
     nb_index_free(ctx, idx);
     nb_volume_free(ctx, dref);
     nbh_volume_free(&ref);
     nbh_volumes_info_free(&vi);
-    nb_ctx_destroy(ctx);
+    nbh_ctx_put(ctx);
     NBH_PHASE("tear-down");
     return 0;
 }
