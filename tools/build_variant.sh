@@ -12,6 +12,6 @@ done
 wait
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $V/lib/libnecat_b200.so $V/obj/*.o -cudart static
 for e in oc2cns oc2pmov; do
-  gcc -O2 -g -std=gnu99 -o $V/bin/$e necat_b200/host/$e.c necat_b200/host/nb_host.c -L$V/lib -lnecat_b200 -Wl,-rpath,'$ORIGIN/../lib' -lm
+  gcc -O2 -g -std=gnu99 -o $V/bin/$e necat_b200/host/$e.c necat_b200/host/nb_host.c necat_b200/host/nb_helper.c -L$V/lib -lnecat_b200 -Wl,-rpath,'$ORIGIN/../lib' -lm
 done
 echo built $V
