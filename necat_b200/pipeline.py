@@ -18,6 +18,8 @@ Layout, following the reference's own job structure:
 The union of the ranks' records is what one GPU -- and the reference -- produce; tests/test_dist_cpu.py checks the
 plumbing at world size 2 over gloo, tests/test_gpu_multi.py the whole thing on GPUs.
 """
+import os
+
 import numpy as np
 
 from . import formats
@@ -72,11 +74,29 @@ def exchange_records(packed, n_reads, world, rank, device, part_size=PART_SIZE):
     rank corrects, grouped nowhere in particular (nb_consensus_job groups by template)."""
     n_part = (int(n_reads) + part_size - 1) // part_size
     S, _ = correction_plan(n_part, world)
-    both = np.concatenate([packed, formats.swap_roles(packed)]) if packed.shape[0] else np.zeros((0, 7), np.uint32)
     if world == 1:
-        return both
+        return np.concatenate([packed, formats.swap_roles(packed)]) if packed.shape[0] else np.zeros((0, 7), np.uint32)
     import torch
     import torch.distributed as dist
+    if S == world:
+        # One partition shared by all ranks (E. coli, yeast: fewer than 100 000 reads): every rank corrects a share of the
+        # templates of every record, so every rank needs every record -- the all-to-all-v degenerates into an all-gather
+        # of the records as they were found; the role swap (gapped_candidate.c:54-69) happens after the receipt.
+        n = int(packed.shape[0])
+        cnt = torch.tensor([n], dtype=torch.int64, device=device)
+        allc = torch.empty(world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(allc, cnt)
+        counts = [int(x) for x in allc.cpu().tolist()]
+        width = max(max(counts), 1)
+        send = torch.zeros(width * 7, dtype=torch.int32, device=device)
+        if n:
+            send[:n * 7] = torch.from_numpy(np.ascontiguousarray(packed).view(np.int32).reshape(-1)).to(device)
+        recv = torch.empty(world * width * 7, dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(recv, send)
+        r = recv.cpu().numpy().view(np.uint32).reshape(world, width, 7)
+        allp = np.concatenate([r[i, :counts[i]] for i in range(world)])
+        return np.concatenate([allp, formats.swap_roles(allp)]) if allp.shape[0] else np.zeros((0, 7), np.uint32)
+    both = np.concatenate([packed, formats.swap_roles(packed)]) if packed.shape[0] else np.zeros((0, 7), np.uint32)
     out_parts, counts = [], np.zeros(world, np.int64)
     dests = record_destinations(both[:, 1], part_size, S, world)
     send = []
@@ -140,7 +160,9 @@ def correct_iteration(ctx, vols, popt, copt, rank=0, world=1, device=None, part_
             if idx is not None:
                 ctx.free_index(idx)
             w0 = time.perf_counter()
-            if groups is not None and len(groups[i]) > 1:
+            # NECAT_B200_INDEX=replicated: every rank of the group builds the whole index (no collective); default: built
+            # once, in shards of the hash space, and all-gathered
+            if groups is not None and len(groups[i]) > 1 and os.environ.get("NECAT_B200_INDEX", "sharded") != "replicated":
                 idx = ctx.build_index_sharded(dvols[i], popt.kmer_size, popt.kmer_cnt_cutoff, groups[i], rank, device,
                                               group=None if len(groups[i]) == world else group_of(groups[i]))
             else:
