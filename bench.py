@@ -420,8 +420,9 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(args),
                    "reads": int(nreads), "bases": int(vol.db_size),
-                   "parallelism": f"x{world}: index built in {world} shards of the hash space + NCCL all-gather, query reads split, "
-                                  "all-to-all-v of the 28-byte records, templates of the one partition id mod N",
+                   "parallelism": f"x{world}: index of the one volume built by every rank (10 ms; volumes of >= 600 Mbp: in {world} shards of the "
+                                  "hash space + NCCL all-gather), query reads split, exchange of the 28-byte records (one partition shared by all "
+                                  "ranks: all-gather), templates of the one partition id mod N",
                    "l2": "512 MB flush write between iterations; index (4 GiB table) and DP scratch exceed L2"},
         "overlaps_per_sec": stats["n_candidates"] / sec,
         "corrected_bases": bases, "candidates": stats["n_candidates"],

@@ -52,7 +52,7 @@ CNS_RECORD = np.dtype([("id", "<i4"), ("left", "<i4"), ("right", "<i4"), ("org_s
 
 EXPORTS = ["nb_ctx_create", "nb_ctx_destroy", "nb_last_error", "nb_version", "nb_launch_count", "nb_get_timings",
            "nb_volume_upload", "nb_volume_free", "nb_index_build", "nb_index_free", "nb_index_stats",
-           "nb_index_download", "nb_index_build_shard", "nb_index_shard_export", "nb_index_adopt", "nb_map_options_default", "nb_map_volume", "nb_map_volume_aln", "nb_pack_candidate", "nb_free",
+           "nb_index_download", "nb_index_build_shard", "nb_index_shard_export", "nb_index_adopt", "nb_map_options_default", "nb_map_volume", "nb_map_volume_aln", "nb_pack_candidate", "nb_swap_candidate_roles", "nb_free",
            "nb_get_map_counters", "nb_cns_options_default", "nb_extend_candidates", "nb_consensus_job",
            "nb_consensus_job_sharded",
            "nb_get_cns_counters", "nb_rescue_local", "nb_rescue_global"]
@@ -266,6 +266,21 @@ def default_cns_options(**kw):
     for k, v in kw.items():
         setattr(o, k, v)
     return o
+
+
+def with_swapped_roles(packed_parts):
+    """(n, 7) uint32 records (a list of arrays, concatenated) followed by their role-swapped copies
+    (nb_swap_candidate_roles): the 2 n records a correction job takes (pcan.c:86-91)."""
+    n = int(sum(p.shape[0] for p in packed_parts))
+    out = np.empty((2 * n, 7), np.uint32)
+    pos = 0
+    for p in packed_parts:
+        out[pos:pos + p.shape[0]] = p
+        pos += p.shape[0]
+    if n:
+        L = lib()
+        L.nb_swap_candidate_roles(out.ctypes.data_as(C.c_void_p), C.c_uint64(n), C.c_void_p(out.ctypes.data + 28 * n))
+    return out
 
 
 def pack_candidates(cands):

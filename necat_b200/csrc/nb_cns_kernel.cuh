@@ -736,6 +736,8 @@ k_cns_dp(CnsParams P)
     int k = -1, nk = -1;
     uint32_t x = 0, x_end = 0, nx = 0, nx_end = 0, sq = 0;
     uint32_t a = 0, top = 0;            // the next level starts at window lane a; the window's last level start is lane top
+    uint32_t lv = 1, nd = 1, p0m = 0, rfm = 0, rlm = 0;     // level / node starts of the window (and, one group per warp: position starts, run flags)
+    bool primed = false;
     uint4 e = make_uint4(0, 0, 0, 0), en = make_uint4(0, 0, 0, 0);
     if (!done) {
         next_span(nk, nx, nx_end);
@@ -756,13 +758,22 @@ k_cns_dp(CnsParams P)
             k = nk; x = nx; x_end = nx_end; e = en; a = 0;
             if (k >= n_spans) { done = true; fin = p_last; }
         }
-        // ---- 2. level and node starts of the windows (a group that did not move gets what it had)
-        const bool valid = !done && x + (uint32_t)gl < x_end;
-        const uint32_t lvb = __ballot_sync(full, valid && (e.x & CNS_K_LEVEL));
-        const uint32_t ndb = __ballot_sync(full, valid && (e.x & CNS_K_NODE));
-        const uint32_t nvalid = done ? 0u : (x_end - x < (uint32_t)G ? x_end - x : (uint32_t)G);
-        const uint32_t sent = nvalid < (uint32_t)G ? (1u << nvalid) : 0u;       // the span ends inside the window, and its last level with it
-        const uint32_t lv = ((lvb >> gsh) & GM) | sent, nd = ((ndb >> gsh) & GM) | sent;
+        // ---- 2. level and node starts of the windows (a group that did not move gets what it had; with one group per warp
+        //         the votes are only taken when it moved, and three more of them spare every level a shuffle)
+        if (G < 32 || adv || !primed) {
+            const bool valid = !done && x + (uint32_t)gl < x_end;
+            const uint32_t lvb = __ballot_sync(full, valid && (e.x & CNS_K_LEVEL));
+            const uint32_t ndb = __ballot_sync(full, valid && (e.x & CNS_K_NODE));
+            const uint32_t nvalid = done ? 0u : (x_end - x < (uint32_t)G ? x_end - x : (uint32_t)G);
+            const uint32_t sent = nvalid < (uint32_t)G ? (1u << nvalid) : 0u;   // the span ends inside the window, and its last level with it
+            lv = ((lvb >> gsh) & GM) | sent; nd = ((ndb >> gsh) & GM) | sent;
+            if (G == 32) {
+                p0m = __ballot_sync(full, valid && (e.x & CNS_K_LEVEL) && (e.x >> 24) == 0);
+                rfm = __ballot_sync(full, valid && (e.x & CNS_K_RUNFIRST));
+                rlm = __ballot_sync(full, valid && (e.x & CNS_K_RUNLAST));
+            }
+            primed = true;
+        }
         top = 31u - (uint32_t)__clz((int)(lv | 1u));
         const bool lng = !done && top == 0;                 // one level fills the window (or runs past it)
         // ---- 3. groups that moved fetch the window after this one: it begins at the last level start of this one
@@ -771,12 +782,19 @@ k_cns_dp(CnsParams P)
             if (nx == x_end) next_span(nk, nx, nx_end);
             if (nk < n_spans && nx + (uint32_t)gl < nx_end) en = link[nx + gl];
         }
-        if (__all_sync(full, done && !fin)) break;
         const bool lev = !done && !lng;                     // (then a < top: a complete level starts at lane a)
         // ---- 4. position / run bookkeeping from the first link of the level (uniform inside a group)
-        const uint32_t k0 = __shfl_sync(full, e.x, gsh + (int)a);
-        const bool newpos = (lev || lng) && (k0 >> 24) == 0;           // a position starts with its delta-0 level
-        if (__any_sync(full, fin || (newpos && p_last))) {
+        bool newpos, runfirst, runlast;
+        if (G == 32) { newpos = (lev || lng) && ((p0m >> a) & 1u); runfirst = (rfm >> a) & 1u; runlast = (rlm >> a) & 1u; }
+        else {
+            const uint32_t k0 = __shfl_sync(full, e.x, gsh + (int)a);
+            newpos = (lev || lng) && (k0 >> 24) == 0;       // a position starts with its delta-0 level
+            runfirst = (k0 & CNS_K_RUNFIRST) != 0; runlast = (k0 & CNS_K_RUNLAST) != 0;
+        }
+        // one vote for everything the groups of the warp have to agree on: anybody still at work, a run to close, a long level
+        const uint32_t ev = __reduce_or_sync(full, ((done && !fin) ? 0u : 1u) | ((fin || (newpos && p_last)) ? 2u : 0u) | (lng ? 4u : 0u));
+        if (!(ev & 1u)) break;
+        if (ev & 2u) {
             // the best node of the run that ended (cns_aux.c:177-184): highest score, first in traversal order
             double mx = g_best;
 #pragma unroll
@@ -802,17 +820,17 @@ k_cns_dp(CnsParams P)
         }
         if (newpos) {
             prev_fl = cur_fl; cur_fl = level;
-            if (k0 & CNS_K_RUNFIRST) {
+            if (runfirst) {
                 t = run_started < n_runs ? my_runs[run_started].from : 0;
                 g_best = -1.0; g_x = 0xffffffffu; g_lb = 0xffffffffu;
                 if (gl == 0 && run_started < n_runs) my_runs[run_started].first_level = level;
                 ++run_started;
             } else ++t;
-            p_last = (k0 & CNS_K_RUNLAST) != 0;
+            p_last = runlast;
         }
         __syncwarp();                                       // the scores of the previous trip are in the ring
         // ---- 5. a level of more than G links: the group's first lane walks it
-        if (__any_sync(full, lng)) {
+        if (ev & 4u) {
             uint32_t used = 0;
             if (lng && gl == 0) {
                 bool have = false;
@@ -878,7 +896,7 @@ k_cns_dp(CnsParams P)
             uint32_t z = lev ? ((~nd) >> a) & ((1u << n) - 1u) : 0u;     // window lanes of the level that continue a node
             while (z) { z &= z >> 1; ++rounds; }
         }
-        rounds = __reduce_max_sync(full, rounds);
+        if (G < 32) rounds = __reduce_max_sync(full, rounds);
         if (rounds) {
             const int node_end = act ? gl + __ffs((int)(nd >> (gl + 1))) : 0;      // the next node start above me (the level's end is one)
             const double msc = sc;

@@ -287,6 +287,19 @@ extern "C" void nb_cns_options_default(nb_cns_options* o)
     o->use_fixed_ident_cutoff = 0; o->small_memory = 0;
 }
 
+extern "C" void nb_swap_candidate_roles(const nb_packed_candidate* in, uint64_t n, nb_packed_candidate* out)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        const nb_packed_candidate a = in[i];
+        const uint32_t w = a.item[0];
+        nb_packed_candidate b;
+        b.item[0] = (w & ((1u << 30) - 1)) | (((w >> 31) & 1u) << 30) | (((w >> 30) & 1u) << 31);
+        b.item[1] = a.item[4]; b.item[2] = a.item[5]; b.item[3] = a.item[6];
+        b.item[4] = a.item[1]; b.item[5] = a.item[2]; b.item[6] = a.item[3];
+        out[i] = b;
+    }
+}
+
 extern "C" void nb_pack_candidate(const nb_candidate* c, nb_packed_candidate* p)
 {
     uint32_t w = 0;

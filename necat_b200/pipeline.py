@@ -25,6 +25,7 @@ import numpy as np
 from . import formats
 
 PART_SIZE = 100000          # oc2pcan -p (necat.pl never passes it: partition_candidates/main.c default)
+INDEX_SHARD_MIN_BASES = 600_000_000     # volumes below this are indexed by every rank that needs them (see correct_iteration)
 
 
 # ------------------------------------------------------------------------------------------------ who does what
@@ -74,8 +75,9 @@ def exchange_records(packed, n_reads, world, rank, device, part_size=PART_SIZE):
     rank corrects, grouped nowhere in particular (nb_consensus_job groups by template)."""
     n_part = (int(n_reads) + part_size - 1) // part_size
     S, _ = correction_plan(n_part, world)
+    from . import capi
     if world == 1:
-        return np.concatenate([packed, formats.swap_roles(packed)]) if packed.shape[0] else np.zeros((0, 7), np.uint32)
+        return capi.with_swapped_roles([packed])
     import torch
     import torch.distributed as dist
     if S == world:
@@ -94,8 +96,7 @@ def exchange_records(packed, n_reads, world, rank, device, part_size=PART_SIZE):
         recv = torch.empty(world * width * 7, dtype=torch.int32, device=device)
         dist.all_gather_into_tensor(recv, send)
         r = recv.cpu().numpy().view(np.uint32).reshape(world, width, 7)
-        allp = np.concatenate([r[i, :counts[i]] for i in range(world)])
-        return np.concatenate([allp, formats.swap_roles(allp)]) if allp.shape[0] else np.zeros((0, 7), np.uint32)
+        return capi.with_swapped_roles([r[i, :counts[i]] for i in range(world)])
     both = np.concatenate([packed, formats.swap_roles(packed)]) if packed.shape[0] else np.zeros((0, 7), np.uint32)
     out_parts, counts = [], np.zeros(world, np.int64)
     dests = record_destinations(both[:, 1], part_size, S, world)
@@ -160,9 +161,13 @@ def correct_iteration(ctx, vols, popt, copt, rank=0, world=1, device=None, part_
             if idx is not None:
                 ctx.free_index(idx)
             w0 = time.perf_counter()
-            # NECAT_B200_INDEX=replicated: every rank of the group builds the whole index (no collective); default: built
-            # once, in shards of the hash space, and all-gathered
-            if groups is not None and len(groups[i]) > 1 and os.environ.get("NECAT_B200_INDEX", "sharded") != "replicated":
+            # The ranks that share an index volume either build its index ONCE, in shards of the hash space, and all-gather
+            # it (4.3 GB of row pointers + the positions over NVLink: ~7 ms at 2 ranks, ~13 ms at 4), or every one of them
+            # builds all of it (no collective; 10 ms for a 184 Mbp volume, proportional to the volume).  Measured on the
+            # E. coli-size set the replicated build wins at every N (N = 4: 10.0 ms against 16.5); a volume of the full
+            # 2 Gbp takes ~110 ms to index, there the sharded build wins.  NECAT_B200_INDEX=sharded|replicated overrides.
+            mode = os.environ.get("NECAT_B200_INDEX", "replicated" if vols[i].db_size < INDEX_SHARD_MIN_BASES else "sharded")
+            if groups is not None and len(groups[i]) > 1 and mode != "replicated":
                 idx = ctx.build_index_sharded(dvols[i], popt.kmer_size, popt.kmer_cnt_cutoff, groups[i], rank, device,
                                               group=None if len(groups[i]) == world else group_of(groups[i]))
             else:

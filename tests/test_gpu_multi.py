@@ -26,6 +26,7 @@ def _worker(rank, world, port, wrk, part_size, out_dir):
     from necat_b200 import capi, formats, pipeline
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["NECAT_B200_INDEX"] = "sharded"          # (small volumes would be indexed by every rank: the test wants the sharded build)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
