@@ -519,22 +519,33 @@ k_extend(ExtParams P)
     uint2* mat = P.mat + (wslot + (lane & (EXT_SLOTS - 1))) * EXT_MAT_STRIDE;          // of my slot
     uint32_t* rev = reinterpret_cast<uint32_t*>(P.rev + (wslot + (lane & (EXT_SLOTS - 1))) * EXT_REV_STRIDE);
     unsigned long long nb = 0, nc = 0, nwd = 0;
-    const bool has = lane < P.slots;                    // this lane owns a slot
-    if (has) XF(X_STATE, lane) = ST_IDLE;
+    // A candidate is a chain of block alignments, and a warp runs the forward passes of its slots one pair after the other: the
+    // chain of a 60 kb candidate in a warp of 16 takes half as long as the whole launch of one GPU, and longer than the launch
+    // of one GPU of eight.  So the longest candidates (the front of the task list) have a queue of their own, served by a few
+    // warps that keep only two in flight; when it is empty those warps join the others.
+    bool long_warp = (uint32_t)(blockIdx.x * EXT_WARPS + wid) < P.n_long_warps;
+    bool has = lane < (long_warp ? 2 : P.slots);        // this lane owns a slot
+    if (lane < EXT_SLOTS) XF(X_STATE, lane) = ST_IDLE;
     __syncwarp();
     bool drained = false;
     for (;;) {
         // ---- idle slots take candidates from the queue
         const uint32_t idle = __ballot_sync(0xffffffffu, has && XF(X_STATE, lane) == ST_IDLE);
         if (idle && !drained) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(P.next_task, (uint32_t)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, 0);
+            uint32_t base = 0, lim = 0, moved = 0;
+            if (lane == 0) {
+                const uint32_t want = (uint32_t)__popc(idle);
+                int q = long_warp ? 1 : 0;
+                base = atomicAdd(P.next_task + q, want); lim = q ? P.n_long : P.n_tasks;
+                if (base >= lim) { q ^= 1; moved = 1; base = atomicAdd(P.next_task + q, want); lim = q ? P.n_long : P.n_tasks; }    // that queue is empty: the other one
+            }
+            base = __shfl_sync(0xffffffffu, base, 0); lim = __shfl_sync(0xffffffffu, lim, 0); moved = __shfl_sync(0xffffffffu, moved, 0);
             if (has && XF(X_STATE, lane) == ST_IDLE) {
                 const uint32_t ti = base + (uint32_t)__popc(idle & lt_mask);
-                if (ti < P.n_tasks) lp_start_task(S, P, ti, lane);
+                if (ti < lim) lp_start_task(S, P, ti, lane);
             }
-            if (base + (uint32_t)__popc(idle) >= P.n_tasks) drained = true;
+            if (base >= lim) drained = true;                                    // both are
+            if (moved && long_warp) { long_warp = false; has = lane < P.slots; }     // from now on a warp like the others
         }
         __syncwarp();
         // ---- candidates whose right side has ended: result record, whole warp
@@ -627,8 +638,14 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     NbDevBuf B(ctx);
     uint32_t* d_next = NULL;
     unsigned long long* d_cnt = NULL;
-    { int rc; if ((rc = B.get(&d_next, 1))) return rc; if ((rc = B.get(&d_cnt, 4))) return rc; }
-    NB_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(uint32_t), st));
+    { int rc; if ((rc = B.get(&d_next, 2))) return rc; if ((rc = B.get(&d_cnt, 4))) return rc; }
+    // the queue of the longest candidates: 2 % of a large launch, an eighth of the warps
+    static const int kLongQ = getenv("NB_EXT_LONGQ") ? atoi(getenv("NB_EXT_LONGQ")) : 1;
+    uint32_t n_long = 0, n_long_warps = 0;
+    if (kLongQ == 1 && n_slots > 2 && n_tasks >= 4u * grid * EXT_WARPS) { n_long = n_tasks / 50; n_long_warps = grid * EXT_WARPS / 8; }
+    if (kLongQ == 2 && n_tasks >= 4) { n_long = n_tasks / 4; n_long_warps = grid * EXT_WARPS / 2 ? grid * EXT_WARPS / 2 : 1; }      // (tests: any launch)
+    const uint32_t h_next[2] = {n_long, 0u};
+    NB_CUDA(ctx, cudaMemcpyAsync(d_next, h_next, sizeof h_next, cudaMemcpyHostToDevice, st));
     NB_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 4, st));
     ExtParams P;
     P.pac = templates->d_pac; P.seq_off = templates->d_off; P.seq_len = templates->d_len;
@@ -636,7 +653,7 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     P.tasks = d_tasks; P.n_tasks = n_tasks; P.results = d_results; P.ops = d_ops; P.mat = s_mat; P.rev = s_rev;
     P.next_task = d_next; P.counters = d_cnt;
     P.error = error; P.min_align_size = min_align_size; P.tail_match_len = tail_match_len; P.block_size = 512;
-    P.slots = n_slots;
+    P.slots = n_slots; P.n_long = n_long; P.n_long_warps = n_long_warps;
     P.band_test = getenv("NB_EXT_BAND_TEST") ? atoi(getenv("NB_EXT_BAND_TEST")) : 0;     // (read at every launch: tests switch it)
     const size_t smem = sizeof(WarpScratch) * EXT_WARPS;
     NB_CUDA(ctx, cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -35,7 +35,9 @@ struct ExtParams {
     uint8_t*        ops;            // pool
     uint2*          mat;            // per candidate in flight: EXT_MAT_STRIDE entries, the (Pv, Ph) words of the band, [column][4]
     uint8_t*        rev;            // per candidate in flight: EXT_REV_STRIDE bytes, the columns of the current block, last to first
-    uint32_t*       next_task;      // work queue cursor
+    uint32_t*       next_task;      // work queue cursors: [0] over the tasks [n_long, n_tasks), [1] over the longest ones [0, n_long)
+    uint32_t        n_long;         // the first n_long tasks (the caller lists the longest first) go to warps that keep only two in flight
+    uint32_t        n_long_warps;   // ... the first n_long_warps warps of the grid, until that queue is empty
     unsigned long long* counters;   // [0] block alignments, [1] DP columns, [2] word updates
     double          error;
     int             min_align_size;

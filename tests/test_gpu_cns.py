@@ -76,6 +76,7 @@ def test_cns_multi_volume(built, tmp_path):
     {"NB_CNS_LONG_PCT": "10", "NB_CNS_SLICES": "5"},    # six slices: link kernels one after the other, best-path chains beside them
     {"NB_CNS_LONG_PCT": "30", "NB_CNS_SLICES": "1", "NB_CNS_DP_TEST": "1"},
     {"NB_CNS_LONG_PCT": "0"},                       # one slice
+    {"NB_EXT_LONGQ": "2"},                          # k_extend: a quarter of every launch through the queue of the longest candidates (two-slot warps)
     {"NB_CNS_CHUNKS": "5", "NB_CNS_PIPES": "3"},    # the chunk pipeline: three workers on their own streams
     {"NB_CNS_CHUNKS": "2", "NB_CNS_PIPES": "1"},
     {"NB_CNS_GROUPS": "4", "NB_CNS_GROUPS_MIN": "8"},   # extension rounds of four template groups interleaved on the GPU
