@@ -1178,7 +1178,16 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     }
     // Longest templates first: their candidates are the longest chains of block alignments of an extension launch (k_extend
     // takes the tasks in order), started first they do not end up as its tail.  (Records are put in id order by the caller.)
-    std::stable_sort(tpls.begin(), tpls.end(), [](const Tpl& a, const Tpl& b) { return a.T > b.T; });
+    {
+        // (an index is sorted and the templates are moved once: a Tpl is four vectors and a dozen fields)
+        std::vector<uint32_t> ix(tpls.size());
+        for (size_t i = 0; i < ix.size(); ++i) ix[i] = (uint32_t)i;
+        std::stable_sort(ix.begin(), ix.end(), [&](uint32_t a, uint32_t b) { return tpls[a].T > tpls[b].T; });
+        std::vector<Tpl> re;
+        re.reserve(tpls.size());
+        for (uint32_t i : ix) re.push_back(std::move(tpls[i]));
+        tpls.swap(re);
+    }
     // The consensus kernels of a template are a dependent chain over its positions, so the longest templates decide
     // how long the consensus of a batch lasts.  They are moved to the front and get their own group, whose consensus
     // runs beside the extension of everything else (process_chunk).

@@ -642,7 +642,9 @@ int nb_run_extension(nb_ctx* ctx, const nb_volume* queries, const nb_volume* tem
     // the queue of the longest candidates: 2 % of a large launch, an eighth of the warps
     static const int kLongQ = getenv("NB_EXT_LONGQ") ? atoi(getenv("NB_EXT_LONGQ")) : 1;
     uint32_t n_long = 0, n_long_warps = 0;
-    if (kLongQ == 1 && n_slots > 2 && n_tasks >= 4u * grid * EXT_WARPS) { n_long = n_tasks / 50; n_long_warps = grid * EXT_WARPS / 8; }
+    // (measured, one rank of N on the E. coli-size set: 37.5 -> 33.7 ms at N = 4, 28.9 -> 26.1 at N = 8, nothing at N = 2, and
+    //  86.2 -> 88.7 at N = 1, where the launch lasts four times the longest chain anyway: large launches go without)
+    if (kLongQ == 1 && n_slots > 2 && n_tasks >= 4u * grid * EXT_WARPS && n_tasks <= 80000u) { n_long = n_tasks / 50; n_long_warps = grid * EXT_WARPS / 8; }
     if (kLongQ == 2 && n_tasks >= 4) { n_long = n_tasks / 4; n_long_warps = grid * EXT_WARPS / 2 ? grid * EXT_WARPS / 2 : 1; }      // (tests: any launch)
     const uint32_t h_next[2] = {n_long, 0u};
     NB_CUDA(ctx, cudaMemcpyAsync(d_next, h_next, sizeof h_next, cudaMemcpyHostToDevice, st));
