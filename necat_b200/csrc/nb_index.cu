@@ -231,22 +231,36 @@ k_part2_scatter(const uint2* __restrict__ src, const uint32_t* __restrict__ tile
 }
 
 // ---- per bucket: counts in shared memory, the cut-off, totals
+// The counters of a bucket are swept as uint4 (a bucket holds ~2 800 pairs for 16 384 counters at E. coli size: the sweeps,
+// not the pairs, are the work).  Entry i lives in 16-byte slot v ^ ((v >> 3) & 7), v = i >> 2: where a thread owns 32
+// consecutive entries (8 slots, the scan of k_bucket_fill) the 8 lanes of a quarter warp are on 8 different bank groups,
+// and a warp reading consecutive slots still is.
+__device__ __forceinline__ uint32_t idx_slot(uint32_t v) { return v ^ ((v >> 3) & 7u); }
+__device__ __forceinline__ uint32_t idx_entry(uint32_t i) { return (idx_slot(i >> 2) << 2) | (i & 3u); }
+
 __global__ void __launch_bounds__(IDX_FILL_THREADS)
 k_bucket_count(const uint2* __restrict__ pairs, const uint32_t* __restrict__ bbase, IdxGeom G, uint32_t q,
                uint32_t* __restrict__ bucket_kept, uint32_t* __restrict__ bucket_distinct)
 {
     extern __shared__ __align__(16) uint32_t s_a[];             // [IDX_BUCKET]
     __shared__ uint32_t s_red[2];
+    uint4* s4 = reinterpret_cast<uint4*>(s_a);
     for (uint32_t b = blockIdx.x; b < G.n_buckets; b += gridDim.x) {
         const uint32_t lo = bbase[b], hi = bbase[b + 1];
         if (lo == hi) { if (threadIdx.x == 0) { bucket_kept[b] = 0; bucket_distinct[b] = 0; } continue; }
-        for (uint32_t i = threadIdx.x; i < IDX_BUCKET; i += blockDim.x) s_a[i] = 0;
+        for (uint32_t v = threadIdx.x; v < IDX_BUCKET / 4; v += blockDim.x) s4[v] = make_uint4(0, 0, 0, 0);
         if (threadIdx.x < 2) s_red[threadIdx.x] = 0;
         __syncthreads();
-        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_a[pairs[i].x & (IDX_BUCKET - 1)], 1u);
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_a[idx_entry(pairs[i].x & (IDX_BUCKET - 1))], 1u);
         __syncthreads();
         uint32_t kept = 0, dist = 0;
-        for (uint32_t i = threadIdx.x; i < IDX_BUCKET; i += blockDim.x) { const uint32_t c = s_a[i]; if (c && c <= q) { kept += c; ++dist; } }
+        for (uint32_t v = threadIdx.x; v < IDX_BUCKET / 4; v += blockDim.x) {
+            const uint4 c = s4[v];                              // (any four entries: only totals are wanted)
+            if (c.x && c.x <= q) { kept += c.x; ++dist; }
+            if (c.y && c.y <= q) { kept += c.y; ++dist; }
+            if (c.z && c.z <= q) { kept += c.z; ++dist; }
+            if (c.w && c.w <= q) { kept += c.w; ++dist; }
+        }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { kept += __shfl_xor_sync(0xffffffffu, kept, d); dist += __shfl_xor_sync(0xffffffffu, dist, d); }
         if ((threadIdx.x & 31) == 0 && kept) { atomicAdd(&s_red[0], kept); atomicAdd(&s_red[1], dist); }
@@ -277,53 +291,78 @@ k_bucket_scan(uint32_t* __restrict__ bucket_kept, const uint32_t* __restrict__ b
 }
 
 // ---- per bucket: the slice of the table, the positions run by run
-// In the scan a thread owns 32 consecutive entries (= one word of the drop mask); with entry i at i ^ ((i >> 5) & 31) the 32
-// threads of a warp are on 32 different banks there, and a warp reading consecutive entries still is.
-#define IDX_SW(i) ((i) ^ (((i) >> 5) & 31u))
+// tbl[h] = start of the run of hash h (tbl[h_n] = number of positions): thread t owns the 32 hash values [32 t, 32 t + 32) of
+// the bucket in the scan, writes their starts to the table as eight 16-byte stores, and later puts in order the runs of
+// two and more positions among them (a bit mask it kept from the scan: no sweep over the counters for that).
 __global__ void __launch_bounds__(IDX_FILL_THREADS)
 k_bucket_fill(const uint2* __restrict__ pairs, const uint32_t* __restrict__ bbase, const uint32_t* __restrict__ kbase, IdxGeom G, uint32_t q,
               uint32_t* __restrict__ tbl, uint32_t* __restrict__ offs, uint32_t* __restrict__ long_list, uint32_t* __restrict__ n_long)
 {
-    extern __shared__ __align__(16) uint32_t s_a[];             // [IDX_BUCKET] counts, then ends, then starts of the runs; entry i lives at IDX_SW(i)
+    extern __shared__ __align__(16) uint32_t s_a[];             // [IDX_BUCKET] counts, then run starts / fill cursors, then run ends
     __shared__ uint32_t s_drop[IDX_BUCKET / 32];                // bit: the k-mer occurs more than q times
     __shared__ uint32_t s_warp[33];
-    const uint32_t per = IDX_BUCKET / IDX_FILL_THREADS;         // consecutive hash values of a thread in the scan: 32 = one word of s_drop
+    uint4* s4 = reinterpret_cast<uint4*>(s_a);
+    static_assert(IDX_BUCKET / IDX_FILL_THREADS == 32, "a thread owns one 32-entry row of the bucket");
     for (uint32_t b = blockIdx.x; b < G.n_buckets; b += gridDim.x) {
         const uint32_t lo = bbase[b], hi = bbase[b + 1], kb = kbase[b], kept = kbase[b + 1] - kb;
         const uint32_t h0 = b << IDX_LB;
         const uint32_t nh = G.h_n - h0 < IDX_BUCKET ? G.h_n - h0 : IDX_BUCKET;
-        if (b == 0 && threadIdx.x == 0) tbl[0] = 0;
+        if (b == G.n_buckets - 1 && threadIdx.x == 0) tbl[G.h_n] = kbase[G.n_buckets];
+        uint32_t* trow = tbl + (size_t)h0 + 32u * threadIdx.x;  // my 32 entries of the table (16-byte aligned: h0 is a multiple of 2^14)
+        const bool whole = 32u * threadIdx.x + 32u <= nh;       // (the last bucket of a slice may be cut short)
         if (kept == 0) {                                        // nothing kept: the slice is flat
-            for (uint32_t i = threadIdx.x; i < nh; i += blockDim.x) tbl[(size_t)h0 + i + 1] = kb;
+            if (whole) { for (int j = 0; j < 8; ++j) reinterpret_cast<uint4*>(trow)[j] = make_uint4(kb, kb, kb, kb); }
+            else for (uint32_t j = 0; j < 32 && 32u * threadIdx.x + j < nh; ++j) trow[j] = kb;
             continue;
         }
-        for (uint32_t i = threadIdx.x; i < IDX_BUCKET; i += blockDim.x) s_a[IDX_SW(i)] = 0;
+        for (uint32_t v = threadIdx.x; v < IDX_BUCKET / 4; v += blockDim.x) s4[v] = make_uint4(0, 0, 0, 0);
         __syncthreads();
-        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) { const uint32_t hl = pairs[i].x & (IDX_BUCKET - 1); atomicAdd(&s_a[IDX_SW(hl)], 1u); }
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_a[idx_entry(pairs[i].x & (IDX_BUCKET - 1))], 1u);
         __syncthreads();
+        uint32_t multi = 0;                                     // my entries whose run has two or more positions
         {
-            const uint32_t i0 = threadIdx.x * per;
+            uint4 c[8];
             uint32_t drop = 0, sum = 0;
-            for (uint32_t j = 0; j < per; ++j) { const uint32_t c = s_a[IDX_SW(i0 + j)]; if (c > q) drop |= 1u << j; else sum += c; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                c[j] = s4[idx_slot(8u * threadIdx.x + j)];
+                uint32_t* e = &c[j].x;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    if (e[x] > q) { drop |= 1u << (4 * j + x); e[x] = 0; }
+                    sum += e[x];
+                    if (e[x] >= 2) multi |= 1u << (4 * j + x);
+                }
+            }
             s_drop[threadIdx.x] = drop;
             uint32_t run = block_scan_excl(sum, s_warp, NULL);
-            for (uint32_t j = 0; j < per; ++j) { const uint32_t c = s_a[IDX_SW(i0 + j)]; if (!((drop >> j) & 1)) run += c; s_a[IDX_SW(i0 + j)] = run; }     // end of the run
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint4 st;
+                st.x = run; run += c[j].x; st.y = run; run += c[j].y; st.z = run; run += c[j].z; st.w = run; run += c[j].w;
+                s4[idx_slot(8u * threadIdx.x + j)] = st;        // start of the run = where its first position goes
+                if (whole) reinterpret_cast<uint4*>(trow)[j] = make_uint4(kb + st.x, kb + st.y, kb + st.z, kb + st.w);
+                else {
+                    const uint32_t v4[4] = {st.x, st.y, st.z, st.w};
+                    for (uint32_t x = 0; x < 4; ++x) if (32u * threadIdx.x + 4u * j + x < nh) trow[4 * j + x] = kb + v4[x];
+                }
+            }
         }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < nh; i += blockDim.x) tbl[(size_t)h0 + i + 1] = kb + s_a[IDX_SW(i)];
         __syncthreads();
         for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
             const uint2 e = pairs[i];
             const uint32_t hl = e.x & (IDX_BUCKET - 1);
             if ((s_drop[hl >> 5] >> (hl & 31)) & 1) continue;
-            offs[kb + atomicSub(&s_a[IDX_SW(hl)], 1u) - 1] = e.y;       // the run fills from its end; s_a[IDX_SW(hl)] ends up as its start
+            offs[kb + atomicAdd(&s_a[idx_entry(hl)], 1u)] = e.y;      // the cursor of the run ends up as its end
         }
         __syncthreads();
         // ascending positions inside every run (the reference gets them from scan order + a stable sort)
-        for (uint32_t i = threadIdx.x; i < IDX_BUCKET; i += blockDim.x) {
-            const uint32_t st = s_a[IDX_SW(i)], en = i + 1 < IDX_BUCKET ? s_a[IDX_SW(i + 1)] : kept;
+        while (multi) {
+            const uint32_t j = (uint32_t)__ffs((int)multi) - 1;
+            multi &= multi - 1;
+            const uint32_t i = 32u * threadIdx.x + j;
+            const uint32_t en = s_a[idx_entry(i)], st = i ? s_a[idx_entry(i - 1)] : 0u;    // the run before mine ends where mine starts
             const uint32_t n = en - st;
-            if (n < 2) continue;
             if (n > LONG_RUN) { long_list[atomicAdd(n_long, 1u)] = h0 + i; continue; }
             uint32_t* a = offs + kb + st;
             for (uint32_t x = 1; x < n; ++x) {
