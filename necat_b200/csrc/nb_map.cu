@@ -77,6 +77,9 @@ struct MapDev {
     nb_candidate*   out;
     uint32_t*       out_unit;
     uint32_t*       out_seq;
+    uint32_t*       unit_ncand;     // [n_units + 1] candidates emitted per unit; after k_cand_scan: where the unit's candidates start
+    nb_candidate*   out_sorted;     // the candidates by unit, emission order inside (FWD before REV of a read: units 2 r, 2 r + 1)
+    int             qid_add, sid_add;   // global ids (pm_worker.c:164-167)
     unsigned long long* counters;   // [0] candidates, [1] seeds, [2] blocks, [3] eligible
 };
 
@@ -456,7 +459,7 @@ k_candidates(MapDev P)
     const uint32_t u = blockIdx.x * CAND_WARPS + w;
     if (u >= P.n_units) return;
     const uint32_t nelig = P.unit_nelig[u];
-    if (nelig == 0) return;
+    if (nelig == 0) return;                                     // (unit_ncand was cleared)
     const uint64_t hb = P.hit_base[u];
     UnitView U;
     U.hb = hb; U.nblk = P.unit_nblk[u];
@@ -684,6 +687,47 @@ k_candidates(MapDev P)
         }
         if (keep) ++emitted;
     }
+    if (lane == 0) P.unit_ncand[u] = emitted;
+}
+
+// The candidates leave k_candidates in the order the warps got their output slots.  What the caller wants is per read, FWD
+// strand before REV, emission order inside (pm_worker.c:163-186): an exclusive scan of the per-unit counts (one CTA) and a
+// scatter put them there, with the global read ids added, so that the host copies them out as they are.
+__global__ void __launch_bounds__(1024)
+k_cand_scan(uint32_t* __restrict__ unit_ncand, uint32_t n_units)
+{
+    __shared__ uint32_t s_warp[33];
+    const uint32_t per = (n_units + 1023) / 1024;
+    const uint32_t i0 = threadIdx.x * per, i1 = i0 + per < n_units ? i0 + per : n_units;
+    uint32_t sum = 0;
+    for (uint32_t i = i0; i < i1; ++i) sum += unit_ncand[i];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += t; }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[wid] + inc - sum;
+    for (uint32_t i = i0; i < i1; ++i) { const uint32_t c = unit_ncand[i]; unit_ncand[i] = run; run += c; }
+    if (threadIdx.x == 0) unit_ncand[n_units] = s_warp[32];
+}
+
+__global__ void k_cand_place(MapDev P, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    nb_candidate c = P.out[i];
+    c.qid += P.qid_add; c.sid += P.sid_add;
+    P.out_sorted[P.unit_ncand[P.out_unit[i]] + P.out_seq[i]] = c;
 }
 
 // ------------------------------------------------------------------- host
@@ -748,6 +792,9 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
     if ((rc = S.get(&P.probe_lo, np))) return rc;
     if ((rc = S.get(&P.probe_n, np))) return rc;
     if ((rc = S.get(&P.counters, 8))) return rc;
+    if ((rc = S.get(&P.unit_ncand, (uint64_t)U + 1))) return rc;
+    NB_CUDA(ctx, cudaMemsetAsync(P.unit_ncand, 0, sizeof(uint32_t) * ((size_t)U + 1), st));
+    P.qid_add = read_start_id; P.sid_add = ref_start_id;
     P.probe_base = d_probe_base; P.hit_base = d_hit_base; P.scratch_base = d_scratch_base;
     NB_CUDA(ctx, cudaMemsetAsync(P.counters, 0, 8 * sizeof(unsigned long long), st));
     NB_CUDA(ctx, cudaMemcpyAsync(d_probe_base, probe_base.data(), sizeof(uint64_t) * (U + 1), cudaMemcpyHostToDevice, st));
@@ -817,72 +864,54 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
     NB_CUDA(ctx, cudaStreamSynchronize(st));
     lap(4);
     const uint64_t C = cnts[0];
-    std::vector<nb_candidate> cand(C);
-    std::vector<uint32_t> cu(C), cseq(C);
+    if (C >= (1ull << 32)) return nb_fail(ctx, NB_ELIMIT, "too many candidates in one piece");
+    std::vector<uint32_t> cbase((size_t)U + 1);
+    const size_t a0 = acc.size();
+    acc.resize(a0 + C);
     cudaEventRecord(ctx->ev3, st);
     if (C) {
-        NB_CUDA(ctx, cudaMemcpyAsync(cand.data(), P.out, sizeof(nb_candidate) * C, cudaMemcpyDeviceToHost, st));
-        NB_CUDA(ctx, cudaMemcpyAsync(cu.data(), P.out_unit, sizeof(uint32_t) * C, cudaMemcpyDeviceToHost, st));
-        NB_CUDA(ctx, cudaMemcpyAsync(cseq.data(), P.out_seq, sizeof(uint32_t) * C, cudaMemcpyDeviceToHost, st));
+        if ((rc = S.get(&P.out_sorted, C))) return rc;
+        k_cand_scan<<<1, 1024, 0, st>>>(P.unit_ncand, U);
+        NB_LAUNCH_CHECK(ctx);
+        k_cand_place<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(P, (uint32_t)C);
+        NB_LAUNCH_CHECK(ctx);
+        NB_CUDA(ctx, cudaMemcpyAsync(acc.data() + a0, P.out_sorted, sizeof(nb_candidate) * C, cudaMemcpyDeviceToHost, st));
+        NB_CUDA(ctx, cudaMemcpyAsync(cbase.data(), P.unit_ncand, sizeof(uint32_t) * ((size_t)U + 1), cudaMemcpyDeviceToHost, st));
     }
     NB_CUDA(ctx, cudaStreamSynchronize(st));
     float ms;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev2); ctx->tm.map_ms += ms;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->tm.map_probe_ms += ms;
-    ctx->tm.d2h_bytes += C * (sizeof(nb_candidate) + 8) + U * 4;
+    ctx->tm.d2h_bytes += C * sizeof(nb_candidate) + U * 8;
     ctx->tm.h2d_bytes += (U + 1) * 16 + U * 8;
-
     lap(5);
-    // ---- host: per-read grouping (FWD before REV, emission order), -n truncation, global ids
-    std::vector<uint64_t> order(C);
-    {
-        // counting sort on the unit, then the few records of a unit by their emission number
-        std::vector<uint32_t> first(U + 1, 0);
-        for (uint64_t i = 0; i < C; ++i) {
-            if (cu[i] >= U) return nb_fail(ctx, NB_ECUDA, "candidate kernel returned unit %u of %u", cu[i], U);
-            ++first[cu[i] + 1];
-        }
-        for (uint32_t u = 0; u < U; ++u) first[u + 1] += first[u];
-        std::vector<uint32_t> cur(first.begin(), first.end() - 1);
-        for (uint64_t i = 0; i < C; ++i) order[cur[cu[i]]++] = i;
-        for (uint32_t u = 0; u < U; ++u)
-            if (first[u + 1] - first[u] > 1)
-                std::sort(order.begin() + first[u], order.begin() + first[u + 1], [&](uint64_t a, uint64_t b) { return cseq[a] < cseq[b]; });
-    }
-    uint64_t nres = 0;
-    std::vector<nb_candidate> one;
-    acc.reserve(acc.size() + C);
-    for (uint64_t i = 0; i < C;) {
-        uint64_t j = i;
-        const uint32_t rd = cu[order[i]] >> 1;
-        while (j < C && (cu[order[j]] >> 1) == rd) ++j;
-        if (j - i <= (uint64_t)opt->num_candidates) {
-            for (uint64_t x = i; x < j; ++x) {
-                nb_candidate c = cand[order[x]];
-                c.qid += read_start_id;     // pm_worker.c:164-167
-                c.sid += ref_start_id;
-                acc.push_back(c);
+    // ---- host: -n truncation of the reads that have more candidates than that (pm_worker.c:168-171, order of pm_worker.c:15-24)
+    uint64_t nres = C;
+    if (C) {
+        bool over = false;
+        for (uint32_t u = 0; u < U && !over; u += 2) over = cbase[u + 2] - cbase[u] > (uint32_t)opt->num_candidates;
+        if (over) {
+            std::vector<nb_candidate> kept;
+            kept.reserve(C);
+            std::vector<nb_candidate> one;
+            for (uint32_t u = 0; u < U; u += 2) {
+                const nb_candidate* f = acc.data() + a0 + cbase[u];
+                const size_t m = cbase[u + 2] - cbase[u];
+                if (m <= (size_t)opt->num_candidates) { kept.insert(kept.end(), f, f + m); continue; }
+                one.assign(f, f + m);
+                std::stable_sort(one.begin(), one.end(), [](const nb_candidate& a, const nb_candidate& b) {
+                    if (a.score != b.score) return a.score > b.score;
+                    if (a.qdir != b.qdir) return a.qdir < b.qdir;
+                    if (a.sid != b.sid) return a.sid < b.sid;
+                    if (a.qoff != b.qoff) return a.qoff < b.qoff;
+                    return a.soff < b.soff;
+                });
+                kept.insert(kept.end(), one.begin(), one.begin() + opt->num_candidates);
             }
-            nres += j - i;
-        } else {                            // pm_worker.c:168-171, order of pm_worker.c:15-24
-            one.clear();
-            for (uint64_t x = i; x < j; ++x) {
-                nb_candidate c = cand[order[x]];
-                c.qid += read_start_id;
-                c.sid += ref_start_id;
-                one.push_back(c);
-            }
-            std::stable_sort(one.begin(), one.end(), [](const nb_candidate& a, const nb_candidate& b) {
-                if (a.score != b.score) return a.score > b.score;
-                if (a.qdir != b.qdir) return a.qdir < b.qdir;
-                if (a.sid != b.sid) return a.sid < b.sid;
-                if (a.qoff != b.qoff) return a.qoff < b.qoff;
-                return a.soff < b.soff;
-            });
-            one.resize((size_t)opt->num_candidates);
-            for (auto& c : one) { acc.push_back(c); ++nres; }
+            nres = kept.size();
+            acc.resize(a0 + nres);
+            if (nres) memcpy(acc.data() + a0, kept.data(), sizeof(nb_candidate) * nres);
         }
-        i = j;
     }
     lap(6);
     if (trace) fprintf(stderr, "[nb_map_range] wall ms: layout+alloc %.2f probe+sync %.2f hit layout+alloc %.2f blocks+sync %.2f candidates+sync %.2f download %.2f grouping %.2f\n",
