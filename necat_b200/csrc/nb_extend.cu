@@ -1,4 +1,4 @@
-// nb_extend.cu -- block-wise Myers bit-vector extension, one warp per candidate.
+// nb_extend.cu -- block-wise Myers bit-vector extension, up to 16 candidates in flight per warp.
 //
 // Replaces onc_align / oca_extend / Edlib_align (gapped_align/oc_aligner.c:157-451,
 // gapped_align/edlib_ex.c:733-800).  Per 512-base block the reference runs a banded
@@ -7,14 +7,17 @@
 // result equals: best prefix distance d* over target prefixes (first minimum), fail
 // if d* > (int)(min(qn,tn)*error*1.1); walk back from (qn, j*) preferring up, then
 // left, then diagonal (edlib_ex.c:463,500,540).  Here:
-//   * one unbanded pass, 32-bit words, lane w owns query rows [32w, 32w+32); the
+//   * one unbanded forward pass, 32-bit words, lane w owns query rows [32w, 32w+32); the
 //     horizontal carry travels lane to lane by shuffle along the anti-diagonal
-//     (lane w works on column s-w at step s);
+//     (lane w works on column s-w at step s); two 512-row blocks side by side in the two
+//     half-warps;
 //   * per cell only two bits are kept for the walk-back: Pv (cell = upper + 1) and
-//     Ph (cell = left + 1), written as one coalesced uint2 per lane per step into a
-//     skewed [step][lane] scratch in HBM/L2;
-//   * the walk-back reads that scratch through a 32-column register window and
-//     finds the last run of M matches (oc_aligner.c:222-240) on the fly.
+//     Ph (cell = left + 1), and only for the words within +-48 rows of the block's diagonal
+//     (4 words per column; the walk that leaves that band makes the pass run again around
+//     the diagonal it reached);
+//   * the walk-backs of a warp's candidates run lane-parallel (lane = candidate), one cell
+//     per trip without a branch, and find the last run of M matches
+//     (oc_aligner.c:222-240) on the fly.
 // Integer/bitwise work only: no tensor cores.
 #include "nb_extend.cuh"
 

@@ -292,8 +292,8 @@ k_bucket_scan(uint32_t* __restrict__ bucket_kept, const uint32_t* __restrict__ b
 
 // ---- per bucket: the slice of the table, the positions run by run
 // tbl[h] = start of the run of hash h (tbl[h_n] = number of positions): thread t owns the 32 hash values [32 t, 32 t + 32) of
-// the bucket in the scan, writes their starts to the table as eight 16-byte stores, and later puts in order the runs of
-// two and more positions among them (a bit mask it kept from the scan: no sweep over the counters for that).
+// the bucket in the scan and later puts in order the runs of two and more positions among them (a bit mask it kept from
+// the scan: no sweep over the counters for that); the starts go to the table in one coalesced sweep of 16-byte stores.
 __global__ void __launch_bounds__(IDX_FILL_THREADS)
 k_bucket_fill(const uint2* __restrict__ pairs, const uint32_t* __restrict__ bbase, const uint32_t* __restrict__ kbase, IdxGeom G, uint32_t q,
               uint32_t* __restrict__ tbl, uint32_t* __restrict__ offs, uint32_t* __restrict__ long_list, uint32_t* __restrict__ n_long)
@@ -308,11 +308,12 @@ k_bucket_fill(const uint2* __restrict__ pairs, const uint32_t* __restrict__ bbas
         const uint32_t h0 = b << IDX_LB;
         const uint32_t nh = G.h_n - h0 < IDX_BUCKET ? G.h_n - h0 : IDX_BUCKET;
         if (b == G.n_buckets - 1 && threadIdx.x == 0) tbl[G.h_n] = kbase[G.n_buckets];
-        uint32_t* trow = tbl + (size_t)h0 + 32u * threadIdx.x;  // my 32 entries of the table (16-byte aligned: h0 is a multiple of 2^14)
-        const bool whole = 32u * threadIdx.x + 32u <= nh;       // (the last bucket of a slice may be cut short)
         if (kept == 0) {                                        // nothing kept: the slice is flat
-            if (whole) { for (int j = 0; j < 8; ++j) reinterpret_cast<uint4*>(trow)[j] = make_uint4(kb, kb, kb, kb); }
-            else for (uint32_t j = 0; j < 32 && 32u * threadIdx.x + j < nh; ++j) trow[j] = kb;
+            for (uint32_t v = threadIdx.x; v < IDX_BUCKET / 4; v += blockDim.x) {
+                uint32_t* t4 = tbl + (size_t)h0 + 4u * v;
+                if (4u * v + 4u <= nh) *reinterpret_cast<uint4*>(t4) = make_uint4(kb, kb, kb, kb);
+                else for (uint32_t x = 0; x < 4; ++x) if (4u * v + x < nh) t4[x] = kb;
+            }
             continue;
         }
         for (uint32_t v = threadIdx.x; v < IDX_BUCKET / 4; v += blockDim.x) s4[v] = make_uint4(0, 0, 0, 0);
@@ -341,14 +342,20 @@ k_bucket_fill(const uint2* __restrict__ pairs, const uint32_t* __restrict__ bbas
                 uint4 st;
                 st.x = run; run += c[j].x; st.y = run; run += c[j].y; st.z = run; run += c[j].z; st.w = run; run += c[j].w;
                 s4[idx_slot(8u * threadIdx.x + j)] = st;        // start of the run = where its first position goes
-                if (whole) reinterpret_cast<uint4*>(trow)[j] = make_uint4(kb + st.x, kb + st.y, kb + st.z, kb + st.w);
-                else {
-                    const uint32_t v4[4] = {st.x, st.y, st.z, st.w};
-                    for (uint32_t x = 0; x < 4; ++x) if (32u * threadIdx.x + 4u * j + x < nh) trow[4 * j + x] = kb + v4[x];
-                }
             }
         }
         __syncthreads();
+        // the bucket's slice of the table: consecutive lanes, consecutive 16 bytes
+        for (uint32_t v = threadIdx.x; v < IDX_BUCKET / 4; v += blockDim.x) {
+            const uint4 st = s4[idx_slot(v)];
+            uint32_t* t4 = tbl + (size_t)h0 + 4u * v;
+            if (4u * v + 4u <= nh) *reinterpret_cast<uint4*>(t4) = make_uint4(kb + st.x, kb + st.y, kb + st.z, kb + st.w);
+            else {
+                const uint32_t v4[4] = {st.x, st.y, st.z, st.w};
+                for (uint32_t x = 0; x < 4; ++x) if (4u * v + x < nh) t4[x] = kb + v4[x];
+            }
+        }
+        __syncthreads();                                        // the starts are out before they turn into cursors
         for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
             const uint2 e = pairs[i];
             const uint32_t hl = e.x & (IDX_BUCKET - 1);
