@@ -136,3 +136,16 @@ def test_pcan_many_partitions_match_reference(built, tmp_path, opts):
     assert total == 2 * formats.read_candidates(a).shape[0]
     if opts == "-p 40":
         assert n >= 3
+
+
+def test_swap_candidate_roles_matches_numpy(built):
+    """nb_swap_candidate_roles (C-ABI, host code) == formats.swap_roles (numpy restatement of change_pcan_roles,
+    gapped_candidate.c:54-69); capi.with_swapped_roles lays out [records, swapped records]."""
+    from necat_b200 import capi, formats
+    rng = np.random.default_rng(7)
+    rec = rng.integers(0, 2**32, size=(1000, 7), dtype=np.uint64).astype(np.uint32)
+    both = capi.with_swapped_roles([rec[:400], rec[400:]])
+    assert both.shape == (2000, 7)
+    assert np.array_equal(both[:1000], rec)
+    assert np.array_equal(both[1000:], formats.swap_roles(rec))
+    assert capi.with_swapped_roles([rec[:0]]).shape == (0, 7)
