@@ -723,7 +723,7 @@ static int process_chunk(nb_ctx* ctx, const nb_volume* reads, const nb_cns_optio
             if ((rc = D.get(&P.link, link_total + 64))) return rc;
             if ((rc = D.get(&P.bp, level_total))) return rc;
             if ((rc = D.get(&P.rev, level_total))) return rc;
-            static const int kLinksCtas = getenv("NB_CNS_LINKS_CTAS") ? atoi(getenv("NB_CNS_LINKS_CTAS")) : 6;
+            static const int kLinksCtas = getenv("NB_CNS_LINKS_CTAS") ? atoi(getenv("NB_CNS_LINKS_CTAS")) : 8;
             const unsigned links_grid = NB_SMS * (unsigned)(kLinksCtas < 1 ? 1 : kLinksCtas);
             if ((rc = D.get(&P.cursor, (size_t)links_grid * CNS_WARPS * CNS_MAX_ALN))) return rc;
             if ((rc = D.get(&P.ovpool, (size_t)links_grid * CNS_WARPS * CNS_OV))) return rc;
