@@ -1088,6 +1088,9 @@ extern "C" int nb_consensus_job_sharded(nb_ctx* ctx, const nb_volume* reads, con
     //      kept inside a group (a stable counting sort on the template id)
     unsigned nthreads = std::thread::hardware_concurrency();
     if (nthreads == 0) nthreads = 4;
+    // NB_HOST_THREADS: the host threads of this job (several ranks on one host share its cores: necat_b200/pipeline.py
+    // gives every rank cores / local world size)
+    if (getenv("NB_HOST_THREADS") && atoi(getenv("NB_HOST_THREADS")) > 0) nthreads = (unsigned)atoi(getenv("NB_HOST_THREADS"));
     if (nthreads > 64) nthreads = 64;
     std::vector<uint32_t> grp_start(reads->nseq + 1, 0);
     for (uint64_t i = 0; i < n_in; ++i) {

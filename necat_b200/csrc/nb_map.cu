@@ -48,6 +48,7 @@ struct MapDev {
     uint32_t        n_units;
     int             k, z, bs, s, a_cut;
     int             same_volume;    // query ids fall inside the reference volume (word_finder.c:121-127)
+    uint32_t        stage_bytes;    // k_probe: shared memory of the launch; a longer read is read from global memory
     // per unit
     const uint64_t* probe_base;     // [n_units + 1]
     uint32_t*       unit_hits;      // [n_units]
@@ -116,14 +117,21 @@ k_probe(MapDev P)
     // stage the packed read: 16-byte aligned window [byte0, byte0 + nbytes)
     const uint64_t byte0 = (off >> 2) & ~15ull;
     const uint32_t nbytes = (uint32_t)(((((off + L + 3) >> 2) - byte0) + 8 + 15) & ~15ull);
-    if (threadIdx.x == 0) nb_mbar_init(&bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        nb_mbar_expect_tx(&bar, nbytes);
-        nb_tma_load_1d(smem_raw, P.rd_pac + byte0, nbytes, &bar);
-    }
-    nb_mbar_wait(&bar, 0);
     const uint32_t* words = reinterpret_cast<const uint32_t*>(smem_raw);
+    if (nbytes <= P.stage_bytes) {
+        if (threadIdx.x == 0) nb_mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            nb_mbar_expect_tx(&bar, nbytes);
+            nb_tma_load_1d(smem_raw, P.rd_pac + byte0, nbytes, &bar);
+        }
+        nb_mbar_wait(&bar, 0);
+    } else {
+        // a read beyond the stage (> ~800 kb): its k-mers come straight from global memory (16-byte aligned window; the
+        // volume ends in a zero pad, so the second word of the last k-mer exists)
+        words = reinterpret_cast<const uint32_t*>(P.rd_pac + byte0);
+        __syncthreads();
+    }
     const uint32_t rel0 = (uint32_t)(off - (byte0 << 2));
 
     uint64_t soff_max = ~0ull;
@@ -218,7 +226,7 @@ k_build_blocks(MapDev P)
             for (uint32_t t = 0; t < cnt; ++t) {
                 uint32_t pos = __ldg(P.offs + lo + t);
                 uint32_t b = pos / bs;
-                keys[dst + t] = ((unsigned long long)b << 32) | ((unsigned long long)i << 16) | (pos - b * bs);
+                keys[dst + t] = ((unsigned long long)b << 40) | ((unsigned long long)i << 16) | (pos - b * bs);     // block 24 | probe 24 | offset 16 bits
             }
         }
         carry += s_total;
@@ -247,16 +255,16 @@ k_build_blocks(MapDev P)
     for (uint32_t base = 0; base < n; base += BUILD_THREADS) {
         uint32_t i = base + threadIdx.x;
         uint32_t head = 0;
-        if (i < n) head = (i == 0) || ((uint32_t)(keys[i] >> 32) != (uint32_t)(keys[i - 1] >> 32));
+        if (i < n) head = (i == 0) || ((uint32_t)(keys[i] >> 40) != (uint32_t)(keys[i - 1] >> 40));
         uint32_t ex = cta_exclusive_scan_u32(head, s_warp, &s_total);
         if (head) {
             const uint32_t j = nblk + ex;
-            const uint32_t b = (uint32_t)(keys[i] >> 32);
+            const uint32_t b = (uint32_t)(keys[i] >> 40);
             uint32_t acc = 0, last_probe = 0xffffffffu;
             for (uint32_t t = i; t < n && acc < BLK_SEEDS; ++t) {
                 unsigned long long key = keys[t];
-                if ((uint32_t)(key >> 32) != b) break;
-                uint32_t probe = (uint32_t)(key >> 16) & 0xffffu;
+                if ((uint32_t)(key >> 40) != b) break;
+                uint32_t probe = (uint32_t)(key >> 16) & 0xffffffu;
                 if (probe == last_probe) continue;          // one seed per probe per block (:91)
                 P.seed_kid[hb + i + acc] = probe + 1;
                 P.seed_off[hb + i + acc] = (uint16_t)(key & 0xffffu);
@@ -757,14 +765,18 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
         probe_base[u] = np;
         uint32_t L = reads->h_len[read_lo + (u >> 1)];
         uint32_t n = L >= (uint32_t)k ? (L - k) / z + 1 : 0;
-        if (n > 65535) return nb_fail(ctx, NB_ELIMIT, "read %llu needs %u probes (> 65535)", (unsigned long long)(read_lo + (u >> 1)), n);
+        if (n > 0xffffffu) return nb_fail(ctx, NB_ELIMIT, "read %llu needs %u probes (> 2^24 - 1)", (unsigned long long)(read_lo + (u >> 1)), n);
         np += n;
         qbases += L;
     }
     probe_base[U] = np;
     const uint32_t max_len = reads->max_len;
-    const size_t probe_smem = ((size_t)max_len / 4 + 64 + 15) & ~(size_t)15;
-    if (probe_smem > 200 * 1024) return nb_fail(ctx, NB_ELIMIT, "read of %u bases does not fit the shared-memory stage", max_len);
+    size_t probe_smem = ((size_t)max_len / 4 + 64 + 15) & ~(size_t)15;
+    if (probe_smem > 200 * 1024) probe_smem = 200 * 1024;          // longer reads are probed from global memory
+    if (getenv("NB_MAP_STAGE")) probe_smem = std::min<size_t>(probe_smem, (strtoull(getenv("NB_MAP_STAGE"), NULL, 10) + 15) & ~(size_t)15);      // (tests)
+    // sort keys of k_build_blocks: block id and probe number of a hit in 24 bits each
+    if (((uint64_t)ref->db_size + (uint64_t)opt->block_size - 1) / (uint64_t)opt->block_size >= (1ull << 24))
+        return nb_fail(ctx, NB_ELIMIT, "block size %d gives this volume more than 2^24 blocks", opt->block_size);
 
     NbDevBuf S(ctx);
     MapDev P;
@@ -772,7 +784,7 @@ static int nb_map_range(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, 
     P.tbl = idx->d_tbl; P.offs = idx->d_off;
     P.ref_off = ref->d_off; P.ref_len = ref->d_len; P.ref_nseq = (uint32_t)ref->nseq;
     P.rd_pac = reads->d_pac; P.rd_off = reads->d_off; P.rd_len = reads->d_len;
-    P.read_lo = read_lo; P.n_units = U;
+    P.read_lo = read_lo; P.n_units = U; P.stage_bytes = (uint32_t)probe_smem;
     P.k = k; P.z = z; P.bs = opt->block_size; P.s = opt->block_score_cutoff; P.a_cut = opt->align_size_cutoff;
     // word_finder.c:121-127: the self-hit cut applies when the query's global id lies in the reference volume
     {

@@ -140,6 +140,11 @@ def correct_iteration(ctx, vols, popt, copt, rank=0, world=1, device=None, part_
     correction units of this rank.  dvols / dmerged: device handles of the volumes / of the merged store when the
     caller keeps them resident."""
     from . import capi
+    if world > 1 and "NB_HOST_THREADS" not in os.environ:
+        # the ranks of a host share its cores: the host phases of the library (replay, request gathering, record filling)
+        # get cores / local world size threads each instead of one thread per core in every rank
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        os.environ["NB_HOST_THREADS"] = str(max(2, (os.cpu_count() or 4) // max(1, local_world)))
     n_vol = len(vols)
     start = np.concatenate([[0], np.cumsum([v.nseq for v in vols])]).astype(np.int64)
     n_reads = int(start[-1])

@@ -40,6 +40,18 @@ def test_index_probe_vote_chain_kernels(emu, tmp_path):
     assert o.shape[0] > 1000 and util.same_multiset(g, o)
 
 
+def test_long_reads_many_probes_and_unstaged_probe_path(emu, tmp_path):
+    """Reads of more than 65 535 probes (-z 1 on ~75 kb reads: the probe number of a hit takes 24 bits of the sort key of
+    k_build_blocks) whose packed bases are probed from global memory instead of the shared-memory stage (NB_MAP_STAGE
+    lowers the stage so that these reads are 'too long' for it)."""
+    wrk, reads = util.make_workdir(tmp_path, genome=90_000, depth=3, seed=91, err=0.10, min_len=70_000, max_len=88_000, mean_log=11.3, sd_log=0.1)
+    assert max(r.size for r in reads) > 65_535 + 15
+    opts = PM11.replace("-z 10", "-z 1").replace("-k 11", "-k 13")
+    g = util.run_pmov(emu("oc2pmov"), opts, wrk, 0, str(tmp_path / "g.bin"), prefix=("env", "NB_MAP_STAGE=4096"))
+    o = util.run_pmov(util.ORACLE_CLI, opts, wrk, 0, str(tmp_path / "o.bin"))
+    assert o.shape[0] >= 2 and util.same_multiset(g, o)
+
+
 def test_aln_mode_kernels(emu, tmp_path):
     """oc2pmov -j 1: speculative k_extend + contain-rule replay, M4 text."""
     wrk, _ = util.make_workdir(tmp_path, genome=8000, depth=10, seed=83, err=0.10)

@@ -33,6 +33,30 @@ def test_candidates_match_oracle(built, tmp_path, opts, gen):
     assert util.same_multiset(got, exp), f"gpu {got.shape} vs oracle {exp.shape}"
 
 
+def test_ultra_long_reads(built, tmp_path):
+    """Reads of 0.7-1.1 Mb: more than 65 535 probes each at -z 10 (24-bit probe numbers in the sort keys of
+    k_build_blocks) and, beyond ~800 kb, probed from global memory instead of the shared-memory stage of k_probe; then the
+    same reads through oc2pcan + oc2cns (extension chains of ~2000 blocks, templates of a million positions)."""
+    import shutil
+    wrk, reads = util.make_workdir(tmp_path, genome=1_300_000, depth=5, seed=31, min_len=700_000, max_len=1_100_000, mean_log=13.7, sd_log=0.15)
+    assert max(r.size for r in reads) > 850_000 and min(r.size for r in reads) > 655_360 + 15
+    cand = str(tmp_path / "oracle.bin")
+    got = util.run_pmov(OC2PMOV, util.PM_SENSITIVE, wrk, 0, str(tmp_path / "gpu.bin"))
+    exp = util.run_pmov(util.ORACLE_CLI, util.PM_SENSITIVE, wrk, 0, cand)
+    assert exp.shape[0] >= 4
+    assert util.same_multiset(got, exp), f"gpu {got.shape} vs oracle {exp.shape}"
+    cns = "-a 2000 -x 2 -y 12 -l 1000 -e 0.5 -p 0.8 -u 0 -r 0 -f 0"
+    c = str(tmp_path / "c.bin")
+    shutil.copy(cand, c)
+    util.run([os.path.join(util.BIN_DIR, "oc2pcan"), "-t", "1", wrk, c])
+    util.run([os.path.join(util.BIN_DIR, "oc2cns")] + cns.split() + [wrk, c, str(tmp_path / "g_cns.fa"), str(tmp_path / "g_raw.fa")])
+    util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", "0", wrk, cand, str(tmp_path / "o_cns.fa"), str(tmp_path / "o_raw.fa")])
+    exp_cns = util.fasta_canon(str(tmp_path / "o_cns.fa"))
+    assert len(exp_cns) >= 1
+    assert util.fasta_canon(str(tmp_path / "g_cns.fa")) == exp_cns
+    assert util.fasta_canon(str(tmp_path / "g_raw.fa")) == util.fasta_canon(str(tmp_path / "o_raw.fa"))
+
+
 def test_multi_volume(built, tmp_path):
     """Volume pairs (vid, i >= vid): cross-volume queries have no self-hit cut (word_finder.c:121-127)."""
     wrk, _ = util.make_workdir(tmp_path, genome=100_000, depth=24, seed=21, vol_size=900_000)
