@@ -144,6 +144,10 @@ def main():
     ap.add_argument("--workers", type=int, default=0)
     ap.add_argument("--ref-parts", default="0", help="partitions the reference oc2cns runs (comma list, 'all', or 'none')")
     ap.add_argument("--skip-ref", action="store_true")
+    ap.add_argument("--ref-cns-only", action="store_true",
+                    help="the reference arm is oc2cns alone, on THIS repo's work directory and partition files (the candidates were "
+                         "compared on the 2.4 Gbp run): what a full-size configuration-4 set affords; --ref-parts counts from the "
+                         "end when negative (-1 = the last partition: reads beyond 2^32 bases of the merged store)")
     ap.add_argument("--ref-min-mem-gb", type=float, default=90.0, help="host memory the reference arm needs to be attempted")
     ap.add_argument("--gpu-bins", default=None, help="directory of the executables of the first arm (default necat_b200/bin)")
     ap.add_argument("--tmp", default=None)
@@ -188,6 +192,26 @@ def main():
         ref_ok = not a.skip_ref and util.ref_bin("oc2cns") and a.ref_parts != "skip"
         if ref_ok and mem_available_gb() < a.ref_min_mem_gb:
             res["ref_skipped"] = "only %.0f GB of host memory available" % mem_available_gb()
+            ref_ok = False
+        if ref_ok and a.ref_cns_only:
+            pc = gcand + ".pcan"
+            count = g["partitions"]
+            parts = [int(x) % count for x in a.ref_parts.split(",")]
+            if not all(os.path.exists("%s.p%d" % (pc, i)) for i in parts):      # (oc2cns leaves them to necat.pl; be sure)
+                shutil.copy(gcand, pc)
+                timed([os.path.join(util.BIN_DIR, "oc2pcan"), "-t", str(threads), gwrk, pc])
+            r = {"cns_parts": parts, "cns_s": [], "what": "reference oc2cns on this repo's volumes and partition files"}
+            res["partitions_compared"] = []
+            for i in parts:
+                c, rr = os.path.join(td, "ref_cns_%d.fa" % i), os.path.join(td, "ref_raw_%d.fa" % i)
+                sec, _ = timed([os.path.join(util.REF_DIR, "oc2cns")] + CNS.split() + ["-t", str(threads), gwrk, pc, c, rr, "-mn", str(i), str(count)])
+                r["cns_s"].append(sec)
+                log("ref oc2cns partition %d of %d: %.1f s" % (i, count, sec))
+                row = {"partition": i, "gpu_s": g["cns_s"][i], "ref_s": sec}
+                row["cns_identical"] = util.fasta_canon(gout[i][0]) == util.fasta_canon(c)
+                row["raw_identical"] = util.fasta_canon(gout[i][1]) == util.fasta_canon(rr)
+                res["partitions_compared"].append(row)
+            res["ref"] = r
             ref_ok = False
         if ref_ok:
             parts = None if a.ref_parts == "all" else ([] if a.ref_parts == "none" else [int(x) for x in a.ref_parts.split(",")])
