@@ -128,6 +128,8 @@ int  nb_map_volume(nb_ctx* ctx, const nb_index* idx, const nb_volume* ref, int r
                    const nb_volume* reads, int read_start_id, uint64_t read_lo, uint64_t read_hi,
                    const nb_map_options* opt, nb_candidate** out, uint64_t* n_out);
 void nb_pack_candidate(const nb_candidate* c, nb_packed_candidate* p);  /* gapped_candidate.c:13-28 */
+/* the same over n records: what the CAN-mode output loop does to every candidate before it is written (pm_worker.c:168-171) */
+void nb_pack_candidates(const nb_candidate* c, uint64_t n, nb_packed_candidate* out);
 /* change_pcan_roles (gapped_candidate.c:54-69) over n records: query and subject swapped, strands with them.
  * What oc2pcan does to every record before it files it under its query read as well (pcan.c:86-91). */
 void nb_swap_candidate_roles(const nb_packed_candidate* in, uint64_t n, nb_packed_candidate* out);

@@ -52,7 +52,7 @@ CNS_RECORD = np.dtype([("id", "<i4"), ("left", "<i4"), ("right", "<i4"), ("org_s
 
 EXPORTS = ["nb_ctx_create", "nb_ctx_destroy", "nb_last_error", "nb_version", "nb_launch_count", "nb_get_timings",
            "nb_volume_upload", "nb_volume_free", "nb_index_build", "nb_index_free", "nb_index_stats",
-           "nb_index_download", "nb_index_build_shard", "nb_index_shard_export", "nb_index_adopt", "nb_map_options_default", "nb_map_volume", "nb_map_volume_aln", "nb_pack_candidate", "nb_swap_candidate_roles", "nb_free",
+           "nb_index_download", "nb_index_build_shard", "nb_index_shard_export", "nb_index_adopt", "nb_map_options_default", "nb_map_volume", "nb_map_volume_aln", "nb_pack_candidate", "nb_pack_candidates", "nb_swap_candidate_roles", "nb_free",
            "nb_get_map_counters", "nb_cns_options_default", "nb_extend_candidates", "nb_consensus_job",
            "nb_consensus_job_sharded",
            "nb_get_cns_counters", "nb_rescue_local", "nb_rescue_global"]
@@ -71,8 +71,9 @@ def lib():
         L.nb_version.restype = C.c_char_p
         L.nb_launch_count.restype = C.c_uint64
         L.nb_launch_count.argtypes = [C.c_void_p]
-        for f in ("nb_ctx_destroy", "nb_free"):
+        for f in ("nb_ctx_destroy", "nb_free", "nb_pack_candidates", "nb_swap_candidate_roles"):
             getattr(L, f).restype = None
+        L.nb_pack_candidates.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -216,6 +217,19 @@ class Context:
             arr = np.zeros(0, CANDIDATE)
         self.L.nb_free(out)
         return arr
+
+    def map_volume_packed(self, idx, dref, ref_start, dreads, read_start, lo, hi, opt):
+        """map_volume with the records packed by the library (nb_pack_candidates) straight from its result buffer:
+        (n, 7) uint32 PackedGappedCandidate records, what oc2pmov writes in CAN mode."""
+        out = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self.L.nb_map_volume(self.h, idx, dref, C.c_int(ref_start), dreads, C.c_int(read_start),
+                                         C.c_uint64(lo), C.c_uint64(hi), C.byref(opt), C.byref(out), C.byref(n)))
+        packed = np.empty((n.value, 7), np.uint32)
+        if n.value:
+            self.L.nb_pack_candidates(out, C.c_uint64(n.value), packed.ctypes.data_as(C.c_void_p))
+        self.L.nb_free(out)
+        return packed
 
     def consensus_job(self, dreads, recs, opt, shard_count=1, shard_index=0):
         """recs: (n, 7) uint32 partition records.  Returns (CNS_RECORD array, bytes of all sequences)."""

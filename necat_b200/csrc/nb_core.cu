@@ -287,6 +287,11 @@ extern "C" void nb_cns_options_default(nb_cns_options* o)
     o->use_fixed_ident_cutoff = 0; o->small_memory = 0;
 }
 
+extern "C" void nb_pack_candidates(const nb_candidate* c, uint64_t n, nb_packed_candidate* out)
+{
+    for (uint64_t i = 0; i < n; ++i) nb_pack_candidate(c + i, out + i);
+}
+
 extern "C" void nb_swap_candidate_roles(const nb_packed_candidate* in, uint64_t n, nb_packed_candidate* out)
 {
     for (uint64_t i = 0; i < n; ++i) {

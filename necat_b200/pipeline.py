@@ -184,8 +184,7 @@ def correct_iteration(ctx, vols, popt, copt, rank=0, world=1, device=None, part_
         n = vols[j].nseq
         lo, hi = (n * s) // shares, (n * (s + 1)) // shares
         w0 = time.perf_counter()
-        c = ctx.map_volume(idx, dvols[i], int(start[i]), dvols[j], int(start[j]), lo, hi, popt)
-        found.append(capi.pack_candidates(c))
+        found.append(ctx.map_volume_packed(idx, dvols[i], int(start[i]), dvols[j], int(start[j]), lo, hi, popt))
         if stats is not None:
             t = ctx.timings()
             stats["map_ms"] += t.map_ms; stats["map_probe_ms"] += t.map_probe_ms

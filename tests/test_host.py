@@ -149,3 +149,22 @@ def test_swap_candidate_roles_matches_numpy(built):
     assert np.array_equal(both[:1000], rec)
     assert np.array_equal(both[1000:], formats.swap_roles(rec))
     assert capi.with_swapped_roles([rec[:0]]).shape == (0, 7)
+
+
+def test_pack_candidates_matches_numpy(built):
+    """nb_pack_candidates (C-ABI, host code; what Context.map_volume_packed uses) == capi.pack_candidates (numpy restatement
+    of pack_gapped_candidate, gapped_candidate.c:13-28), including the score cap and the three flag bits."""
+    import ctypes as C
+    from necat_b200 import capi
+    rng = np.random.default_rng(11)
+    n = 5000
+    c = np.zeros(n, capi.CANDIDATE)
+    for f in ("sid", "qid", "sbeg", "send", "qbeg", "qend", "ssize", "qsize"):
+        if f in c.dtype.names:
+            c[f] = rng.integers(0, 2**31 - 1, n)
+    c["score"] = rng.integers(0, 3_000_000, n)
+    c["qdir"] = rng.integers(0, 2, n); c["sdir"] = rng.integers(0, 2, n)
+    c["qoff"] = np.where(rng.random(n) < 0.5, c["qbeg"], c["qend"])
+    out = np.empty((n, 7), np.uint32)
+    capi.lib().nb_pack_candidates(c.ctypes.data_as(C.c_void_p), C.c_uint64(n), out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, capi.pack_candidates(c))
