@@ -31,12 +31,12 @@ $(BIND)/oc2mkdb $(BIND)/oc2ReorderCnsReads: $(BIND)/%: necat_b200/host/%.c $(HOS
 HELPER := necat_b200/host/nb_helper.c
 $(BIND)/%: necat_b200/host/%.c $(HOSTC) $(HELPER) necat_b200/host/nb_host.h necat_b200/host/nb_helper.h $(LIBD)/libnecat_b200.so
 	@mkdir -p $(BIND)
-	$(CC) $(CFLAGS) -o $@ $< $(HOSTC) $(HELPER) -L$(LIBD) -lnecat_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm
+	$(CC) $(CFLAGS) -o $@ $< $(HOSTC) $(HELPER) -L$(LIBD) -lnecat_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm -lpthread
 
 # the resident helper (NECAT_B200_HELPER=1): the two tools as functions of one process that keeps the CUDA context
 $(BIND)/nb_helperd: necat_b200/host/nb_helperd.c necat_b200/host/oc2pmov.c necat_b200/host/oc2cns.c $(HOSTC) $(HELPER) necat_b200/host/nb_host.h necat_b200/host/nb_helper.h $(LIBD)/libnecat_b200.so
 	@mkdir -p $(BIND)
-	$(CC) $(CFLAGS) -DNBH_AS_LIBRARY -o $@ necat_b200/host/nb_helperd.c necat_b200/host/oc2pmov.c necat_b200/host/oc2cns.c $(HOSTC) $(HELPER) -L$(LIBD) -lnecat_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm
+	$(CC) $(CFLAGS) -DNBH_AS_LIBRARY -o $@ necat_b200/host/nb_helperd.c necat_b200/host/oc2pmov.c necat_b200/host/oc2cns.c $(HOSTC) $(HELPER) -L$(LIBD) -lnecat_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm -lpthread
 
 clean:
 	rm -rf build $(LIBD) $(BIND)

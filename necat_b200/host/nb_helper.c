@@ -13,6 +13,8 @@
 
 #include "nb_helper.h"
 
+#include <pthread.h>
+
 extern char** environ;
 int nbh_in_helper = 0;
 static nb_ctx* g_ctx = NULL;
@@ -25,6 +27,32 @@ int nbh_ctx_get(int device, nb_ctx** out)
     const int rc = nb_ctx_create(device, out);
     if (rc == 0 && nbh_in_helper) { g_ctx = *out; g_ctx_dev = device; }
     return rc;
+}
+
+static pthread_t g_bg_thread;
+static int g_bg_started = 0, g_bg_device = 0, g_bg_rc = 0;
+static nb_ctx* g_bg_ctx = NULL;
+
+static void* bg_ctx_main(void* arg)
+{
+    (void)arg;
+    g_bg_rc = nbh_ctx_get(g_bg_device, &g_bg_ctx);
+    return NULL;
+}
+
+void nbh_ctx_begin(int device)
+{
+    g_bg_device = device; g_bg_ctx = NULL; g_bg_rc = 0;
+    g_bg_started = pthread_create(&g_bg_thread, NULL, bg_ctx_main, NULL) == 0;
+}
+
+int nbh_ctx_wait(nb_ctx** out)
+{
+    if (!g_bg_started) return nbh_ctx_get(g_bg_device, out);       /* no thread: create it here */
+    pthread_join(g_bg_thread, NULL);
+    g_bg_started = 0;
+    *out = g_bg_ctx;
+    return g_bg_rc;
 }
 
 void nbh_ctx_put(nb_ctx* ctx)

@@ -22,6 +22,10 @@ int nbh_try_helper(int tool, int argc, char** argv, int* status);
 extern int nbh_in_helper;
 int  nbh_ctx_get(int device, nb_ctx** out);
 void nbh_ctx_put(nb_ctx* ctx);
+/* the same in the background: the context is created (1 - 3 s) on a thread while the caller reads its volumes;
+ * nbh_ctx_wait joins it.  One at a time. */
+void nbh_ctx_begin(int device);
+int  nbh_ctx_wait(nb_ctx** out);
 
 int oc2pmov_main(int argc, char** argv);
 int oc2cns_main(int argc, char** argv);

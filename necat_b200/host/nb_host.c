@@ -91,20 +91,43 @@ int nbh_volume_append(nbh_volume* d, const nbh_volume* s)
     memcpy(d->hdr + hbase, s->hdr, s->hdr_size);
     d->hdr_size += s->hdr_size;
     d->hdr[d->hdr_size] = 0;
-    const uint64_t nb = (base + s->db_size + 3) >> 2;
-    uint8_t* np = (uint8_t*)calloc(nb + 16, 1);
+    /* the store grows in place; the bases of s follow those of d without a gap (pdb_merge), which puts them at a bit
+     * offset of 0, 2, 4 or 6 inside the bytes: whole 64-bit words are shifted (a 2 Gbp volume in ~0.1 s; the
+     * base-by-base loop this replaces took 2.5 s per volume on the 5.6 Gbp set of BASELINE config 4) */
+    const uint64_t nb = (base + s->db_size + 3) >> 2, old_nb = (base + 3) >> 2;
+    uint8_t* np = (uint8_t*)realloc(d->pac, nb + 16);
     if (!np) return -1;
-    memcpy(np, d->pac, (base + 3) >> 2);
-    if ((base & 3) == 0) {
-        memcpy(np + (base >> 2), s->pac, (s->db_size + 3) >> 2);
-    } else {
-        for (uint64_t i = 0; i < s->db_size; ++i) {
-            int c = (s->pac[i >> 2] >> (((~i) & 3) << 1)) & 3;
-            uint64_t j = base + i;
-            np[j >> 2] |= (uint8_t)(c << (((~j) & 3) << 1));
+    memset(np + old_nb, 0, nb + 16 - old_nb);
+    {
+        const unsigned r = (unsigned)(base & 3) * 2;
+        const uint64_t sb = (s->db_size + 3) >> 2;
+        uint8_t* o = np + (base >> 2);
+        if (r == 0) {
+            memcpy(o, s->pac, sb);
+        } else {
+            uint8_t carry = (uint8_t)(o[0] & (0xff << (8 - r)));     /* its top r bits are the last bases of d */
+            uint64_t k = 0;
+            for (; k + 8 <= sb; k += 8) {
+                uint64_t w;
+                memcpy(&w, s->pac + k, 8);
+                w = __builtin_bswap64(w);               /* the first base of a byte sits in its top bits */
+                uint64_t x = ((uint64_t)carry << 56) | (w >> r);
+                carry = (uint8_t)(w << (8 - r));
+                x = __builtin_bswap64(x);
+                memcpy(o + k, &x, 8);
+            }
+            for (; k < sb; ++k) {
+                const uint8_t b = s->pac[k];
+                o[k] = (uint8_t)(carry | (b >> r));
+                carry = (uint8_t)(b << (8 - r));
+            }
+            o[k] = carry;                               /* (inside the 16 bytes of slack when nothing is left) */
         }
+        /* whatever the last byte of s held beyond its bases must not reach the store */
+        const uint64_t last = base + s->db_size;
+        if (last & 3) np[last >> 2] &= (uint8_t)(0xff << (8 - 2 * (unsigned)(last & 3)));
+        memset(np + nb, 0, 16);
     }
-    free(d->pac);
     d->pac = np;
     d->db_size = base + s->db_size;
     d->nseq = n0 + s->nseq;

@@ -80,6 +80,8 @@ int main(int argc, char* argv[])
     if (nnode < 1) NBH_ERROR("invalid node count %d", nnode);
 
     nbh_phase_t0 = nbh_now();
+    const int dev = nbh_pick_device();
+    nbh_ctx_begin(dev);                                          /* the CUDA context comes up while the volumes are read */
     nbh_volumes_info vi;
     if (nbh_volumes_info_load(wrk_dir, &vi)) NBH_ERROR("cannot read volume info in '%s'", wrk_dir);
     nbh_volume reads;
@@ -99,10 +101,9 @@ int main(int argc, char* argv[])
     fclose(pf);
 
     NBH_PHASE("volume load");
-    const int dev = nbh_pick_device();
     nb_ctx* ctx = NULL;
-    if (nbh_ctx_get(dev, &ctx)) NBH_ERROR("%s", nb_last_error(NULL));
-    NBH_PHASE("context");
+    if (nbh_ctx_wait(&ctx)) NBH_ERROR("%s", nb_last_error(NULL));
+    NBH_PHASE("context (rest)");
     nb_volume* dreads = NULL;
     if (nb_volume_upload(ctx, reads.pac, reads.db_size, reads.offset, reads.size, reads.nseq, &dreads)) NBH_ERROR("%s", nb_last_error(ctx));
     NBH_PHASE("volume upload");

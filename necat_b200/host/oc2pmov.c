@@ -69,13 +69,13 @@ int main(int argc, char* argv[])
     if (nbh_volumes_info_load(wrk_dir, &vi)) NBH_ERROR("cannot read volume info in '%s'", wrk_dir);
     if (vid < 0 || vid >= vi.num_volumes) NBH_ERROR("volume id %d out of range", vid);
     const int dev = nbh_pick_device();
-    nb_ctx* ctx = NULL;
-    if (nbh_ctx_get(dev, &ctx)) NBH_ERROR("%s", nb_last_error(NULL));
-    NBH_PHASE("context");
-
+    nbh_ctx_begin(dev);                                          /* the CUDA context comes up while the volume is read */
     nbh_volume ref;
     if (nbh_volume_load(vi.names[vid], &ref)) NBH_ERROR("cannot load volume '%s'", vi.names[vid]);
     NBH_PHASE("volume load");
+    nb_ctx* ctx = NULL;
+    if (nbh_ctx_wait(&ctx)) NBH_ERROR("%s", nb_last_error(NULL));
+    NBH_PHASE("context (rest)");
     nb_volume* dref = NULL;
     if (nb_volume_upload(ctx, ref.pac, ref.db_size, ref.offset, ref.size, ref.nseq, &dref)) NBH_ERROR("%s", nb_last_error(ctx));
     NBH_PHASE("volume upload");

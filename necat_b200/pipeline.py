@@ -120,19 +120,34 @@ def exchange_records(packed, n_reads, world, rank, device, part_size=PART_SIZE):
 
 # ------------------------------------------------------------------------------------------------ one iteration
 def merge_volumes(vols):
-    """consensus/main.c:66: one read store with global ids."""
+    """consensus/main.c:66: one read store with global ids.  The packed bases of a volume follow those of the previous one
+    without a gap (pdb_merge, packed_db.c:419-448): at a bit offset of 0, 2, 4 or 6, so whole bytes are shifted."""
     if len(vols) == 1:
         return vols[0]
     info = np.concatenate([v.info for v in vols]).copy()
-    off, hdr_off, pieces, hdr = 0, 0, [], b""
+    total = sum(int(v.db_size) for v in vols)
+    pac = np.zeros((total + 3) // 4 + 1, np.uint8)
+    off, hdr_off, hdr = 0, 0, b""
     k = 0
     for v in vols:
         info["offset"][k:k + v.nseq] = v.info["offset"] + off
         info["hdr_offset"][k:k + v.nseq] = v.info["hdr_offset"] + hdr_off
-        pieces.append(formats.unpack_bases(v.pac, v.db_size))
-        off += int(v.db_size); hdr_off += len(v.hdr); hdr += v.hdr
+        n = int(v.db_size)
+        nb = (n + 3) // 4
+        src = v.pac[:nb]
+        if n & 3 and nb:                                    # bits behind the last base of a volume stay out of the store
+            src = src.copy()
+            src[-1] &= (0xff << (8 - 2 * (n & 3))) & 0xff
+        r = 2 * (off & 3)
+        o = off >> 2
+        if r == 0:
+            pac[o:o + nb] = src
+        else:
+            pac[o:o + nb] |= src >> r
+            pac[o + 1:o + nb + 1] |= (src << (8 - r)).astype(np.uint8)
+        off += n; hdr_off += len(v.hdr); hdr += v.hdr
         k += v.nseq
-    return formats.Volume(formats.pack_bases(np.concatenate(pieces)), off, info, hdr)
+    return formats.Volume(pac[:(total + 3) // 4], off, info, hdr)
 
 
 def correct_iteration(ctx, vols, popt, copt, rank=0, world=1, device=None, part_size=PART_SIZE, stats=None, dvols=None, dmerged=None):

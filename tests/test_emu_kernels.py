@@ -84,6 +84,28 @@ def test_extension_and_consensus_kernels(emu, tmp_path, cns, gen):
     assert util.fasta_canon(str(tmp_path / "g_raw.fa")) == util.fasta_canon(str(tmp_path / "o_raw.fa"))
 
 
+def test_consensus_over_several_volumes(emu, tmp_path):
+    """oc2cns merges the volumes of the work directory into one read store (consensus/main.c:66; nbh_volume_append shifts
+    the packed bytes of every further volume to the bit offset the store ends at)."""
+    wrk, _ = util.make_workdir(tmp_path, genome=7000, depth=12, seed=85, err=0.10, vol_size=20_001)
+    assert int(open(os.path.join(wrk, "reads_info.txt")).read().split()[0]) >= 3
+    cns = "-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0 -r 0 -f 0"
+    cand = str(tmp_path / "o.bin")
+    with open(cand, "wb") as f:
+        for vid in range(int(open(os.path.join(wrk, "reads_info.txt")).read().split()[0])):
+            util.run_pmov(util.ORACLE_CLI, PM11, wrk, vid, str(tmp_path / "v.bin"))
+            f.write(open(str(tmp_path / "v.bin"), "rb").read())
+    c = str(tmp_path / "c.bin")
+    shutil.copy(cand, c)
+    util.run([emu("oc2pcan"), "-t", "1", wrk, c])
+    util.run([emu("oc2cns")] + cns.split() + [wrk, c, str(tmp_path / "g_cns.fa"), str(tmp_path / "g_raw.fa")])
+    util.run([util.ORACLE_CLI, "cns"] + cns.split() + ["-M", "0", wrk, cand, str(tmp_path / "o_cns.fa"), str(tmp_path / "o_raw.fa")])
+    exp = util.fasta_canon(str(tmp_path / "o_cns.fa"))
+    assert len(exp) >= 5
+    assert util.fasta_canon(str(tmp_path / "g_cns.fa")) == exp
+    assert util.fasta_canon(str(tmp_path / "g_raw.fa")) == util.fasta_canon(str(tmp_path / "o_raw.fa"))
+
+
 def test_sharded_pipeline_through_the_python_api(emu, tmp_path):
     """bench.py's multi-GPU recipe with the emulated library behind necat_b200.capi (patched in a child
     process only): the reads are mapped in two ranges as two ranks would, the candidate records are concatenated as the

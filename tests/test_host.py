@@ -168,3 +168,80 @@ def test_pack_candidates_matches_numpy(built):
     out = np.empty((n, 7), np.uint32)
     capi.lib().nb_pack_candidates(c.ctypes.data_as(C.c_void_p), C.c_uint64(n), out.ctypes.data_as(C.c_void_p))
     assert np.array_equal(out, capi.pack_candidates(c))
+
+
+def test_volume_append_shifts_whole_words(built, tmp_path):
+    """nbh_volume_append (host/nb_host.c; pdb_merge, packed_db.c:419-448): the merged read store of oc2cns, volumes of
+    every length mod 4 appended at every bit offset, against a base-by-base merge; stray bits behind the last base of a
+    volume file do not leak into the store."""
+    src = tmp_path / "t.c"
+    src.write_text(r"""
+#include "nb_host.h"
+#include <string.h>
+static unsigned long long rs = 88172645463325252ull;
+static unsigned rnd(void) { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (unsigned)(rs >> 11); }
+static int base_at(const unsigned char* p, unsigned long long i) { return (p[i >> 2] >> (((~i) & 3) << 1)) & 3; }
+int main(void) {
+    for (int trial = 0; trial < 300; ++trial) {
+        const int nv = 2 + rnd() % 4;
+        unsigned char* all = malloc(1 << 16); unsigned long long total = 0;
+        nbh_volume d; memset(&d, 0, sizeof d);
+        for (int v = 0; v < nv; ++v) {
+            nbh_volume s; memset(&s, 0, sizeof s);
+            s.db_size = (trial < 8 && v == 0) ? (unsigned long long)(trial % 4) : 1 + rnd() % 300;
+            if (trial % 7 == 0) s.db_size += 64 * (rnd() % 9);
+            s.nseq = 1;
+            s.offset = calloc(2, 8); s.size = calloc(2, 8); s.hdr_offset = calloc(2, 8);
+            s.size[0] = s.db_size; s.hdr = strdup("r"); s.hdr_size = 2;
+            const unsigned long long nb = (s.db_size + 3) >> 2;
+            s.pac = calloc(nb + 16, 1);
+            for (unsigned long long i = 0; i < nb; ++i) s.pac[i] = (unsigned char)rnd();      /* pad bits of the last byte: garbage */
+            for (unsigned long long i = 0; i < s.db_size; ++i) all[total + i] = (unsigned char)base_at(s.pac, i);
+            total += s.db_size;
+            if (v == 0) d = s;
+            else { if (nbh_volume_append(&d, &s)) return 2; nbh_volume_free(&s); }
+        }
+        if (d.db_size != total || d.nseq != (unsigned long long)nv) return 3;
+        for (unsigned long long i = 0; i < total; ++i) if (base_at(d.pac, i) != all[i]) { fprintf(stderr, "trial %d base %llu\n", trial, i); return 4; }
+        unsigned long long off = 0;
+        for (int v = 0; v < nv; ++v) { if (d.offset[v] != off) return 5; off += d.size[v]; }
+        if (nv > 1) {       /* behind the last base: zero (the first volume's own pad bits are masked when the next is appended) */
+            if ((total & 3) && (d.pac[total >> 2] & (0xff >> (2 * (total & 3))))) return 6;
+            for (int k = 0; k < 16; ++k) if (d.pac[((total + 3) >> 2) + k]) return 7;
+        }
+        nbh_volume_free(&d); free(all);
+    }
+    puts("ok");
+    return 0;
+}
+""")
+    host = os.path.join(util.ROOT, "necat_b200", "host")
+    exe = str(tmp_path / "t")
+    util.run(["gcc", "-O2", "-std=gnu99", "-I", host, "-o", exe, str(src), os.path.join(host, "nb_host.c")])
+    assert util.run([exe]).stdout.strip() == b"ok"
+
+
+def test_merge_volumes_matches_base_by_base():
+    """pipeline.merge_volumes (the merged read store of the correction half, consensus/main.c:66): byte-shifted packed
+    volumes == the bases of the volumes one after the other, offsets cumulative, nothing behind the last base."""
+    from necat_b200 import formats, pipeline
+    rng = np.random.default_rng(3)
+    for trial in range(120):
+        vols, allb = [], []
+        for _ in range(int(rng.integers(2, 5))):
+            n = int(rng.integers(0, 300)) if trial % 5 else int(rng.integers(0, 4))
+            codes = rng.integers(0, 4, n, dtype=np.uint8)
+            pac = formats.pack_bases(codes).copy()
+            if n & 3 and pac.size:
+                pac[-1] |= int(rng.integers(0, 256)) & (0xff >> (2 * (n & 3)))      # garbage behind the last base
+            info = np.zeros(1, formats.SEQINFO)
+            info["size"] = n
+            vols.append(formats.Volume(pac, n, info, b"r\0"))
+            allb.append(codes)
+        m = pipeline.merge_volumes(vols)
+        exp = np.concatenate(allb)
+        assert m.db_size == exp.size and m.pac.size == (exp.size + 3) // 4
+        assert np.array_equal(formats.unpack_bases(m.pac, m.db_size), exp)
+        if exp.size & 3:
+            assert (int(m.pac[-1]) & (0xff >> (2 * (exp.size & 3)))) == 0
+        assert np.array_equal(m.info["offset"], np.cumsum([0] + [int(v.db_size) for v in vols])[:-1])
