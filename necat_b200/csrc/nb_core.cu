@@ -105,15 +105,6 @@ extern "C" int nb_ctx_create(int device, nb_ctx** out)
     nb_ctx* c = (nb_ctx*)calloc(1, sizeof(nb_ctx));
     if (!c) return nb_fail(NULL, NB_ENOMEM, "out of host memory");
     c->device = device;
-    // NB_L2_FETCH=32|64|128 (experiments): what the L2 fetches from HBM per miss; the random 8-byte gathers of k_probe move
-    // ~200 B of DRAM traffic per probe at the default
-    if (getenv("NB_L2_FETCH") && atoi(getenv("NB_L2_FETCH")) > 0) {
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(getenv("NB_L2_FETCH")));
-        size_t got = 0;
-        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
-        if (getenv("NB_TRACE")) fprintf(stderr, "[nb_ctx_create] L2 fetch granularity %zu B\n", got);
-        cudaGetLastError();
-    }
     { const int rc = nb_ctx_init_streams(c); if (rc) { free(c); return rc; } }
     *out = c;
     return NB_OK;
