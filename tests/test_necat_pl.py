@@ -39,6 +39,14 @@ SMALL_MEMORY=0
 """
 
 
+# what `necat.pl config` writes into a fresh configuration file (necat.pl:22-34); a file without these lines makes necat.pl
+# fall back to "-j 1 -u 0" (M4 text) for the overlap step, which oc2pcan cannot read -- with either set of binaries
+DEFAULT_OVLP = ("OVLP_FAST_OPTIONS=-n 500 -z 20 -b 2000 -e 0.5 -j 0 -u 1 -a 1000\n"
+                "OVLP_SENSITIVE_OPTIONS=-n 500 -z 10 -e 0.5 -j 0 -u 1 -a 1000\n")
+DEFAULT_CNS = ("CNS_FAST_OPTIONS=-a 2000 -x 4 -y 12 -l 1000 -e 0.5 -p 0.8 -u 0\n"
+               "CNS_SENSITIVE_OPTIONS=-a 2000 -x 4 -y 12 -l 1000 -e 0.5 -p 0.8 -u 0\n")
+
+
 def _need_pipeline():
     if not (os.path.exists(os.path.join(PIPE, "necat.pl")) and util.ref_bin("oc2cns")):
         pytest.skip("oracle/_ref/pipeline is not built (make -C oracle ref, needs /root/reference)")
@@ -58,7 +66,7 @@ def _bin_dir(path, tool_dirs):
     return path
 
 
-def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp="", cns=""):
+def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DEFAULT_CNS):
     import gen_reads  # noqa: F401  (tools/ on the path through util's conftest)
     os.makedirs(run_dir)
     A = np.frombuffer(b"ACGT", np.uint8)
@@ -77,7 +85,7 @@ def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp="", cns=""):
     return out
 
 
-def _compare(tmp_path, ours, reads, genome, min_len, ovlp="", cns=""):
+def _compare(tmp_path, ours, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DEFAULT_CNS):
     ref = {t: util.REF_DIR for t in TOOLS}
     a = _correct(_bin_dir(str(tmp_path / "bin_ref"), ref), str(tmp_path / "run_ref"), reads, genome, min_len, ovlp, cns)
     b = _correct(_bin_dir(str(tmp_path / "bin_ours"), ours), str(tmp_path / "run_ours"), reads, genome, min_len, ovlp, cns)
