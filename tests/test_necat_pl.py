@@ -35,7 +35,7 @@ CNS_OUTPUT_COVERAGE=30
 CLEANUP=0
 USE_GRID=false
 GRID_NODE=0
-SMALL_MEMORY=0
+SMALL_MEMORY={small}
 """
 
 
@@ -66,7 +66,7 @@ def _bin_dir(path, tool_dirs):
     return path
 
 
-def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DEFAULT_CNS):
+def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DEFAULT_CNS, small=0):
     import gen_reads  # noqa: F401  (tools/ on the path through util's conftest)
     os.makedirs(run_dir)
     A = np.frombuffer(b"ACGT", np.uint8)
@@ -75,7 +75,7 @@ def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DE
             f.write(b">r%d\n" % i + A[r].tobytes() + b"\n")
     lst = os.path.join(run_dir, "list.txt")
     open(lst, "w").write(os.path.join(run_dir, "reads.fasta") + "\n")
-    open(os.path.join(run_dir, "cfg.txt"), "w").write(CFG.format(list=lst, genome=genome, min_len=min_len, ovlp=ovlp, cns=cns))
+    open(os.path.join(run_dir, "cfg.txt"), "w").write(CFG.format(list=lst, genome=genome, min_len=min_len, ovlp=ovlp, cns=cns, small=small))
     p = subprocess.run([os.path.join(bin_dir, "necat.pl"), "correct", "cfg.txt"], cwd=run_dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     log = p.stdout.decode(errors="replace")
     assert p.returncode == 0 and "Failed to run script" not in log and "[Error]" not in log, log[-3000:]
@@ -85,16 +85,18 @@ def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DE
     return out
 
 
-def _compare(tmp_path, ours, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DEFAULT_CNS):
+def _compare(tmp_path, ours, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DEFAULT_CNS, small=0):
     ref = {t: util.REF_DIR for t in TOOLS}
-    a = _correct(_bin_dir(str(tmp_path / "bin_ref"), ref), str(tmp_path / "run_ref"), reads, genome, min_len, ovlp, cns)
-    b = _correct(_bin_dir(str(tmp_path / "bin_ours"), ours), str(tmp_path / "run_ours"), reads, genome, min_len, ovlp, cns)
+    a = _correct(_bin_dir(str(tmp_path / "bin_ref"), ref), str(tmp_path / "run_ref"), reads, genome, min_len, ovlp, cns, small)
+    b = _correct(_bin_dir(str(tmp_path / "bin_ours"), ours), str(tmp_path / "run_ours"), reads, genome, min_len, ovlp, cns, small)
     assert a["cns_iter1/cns.fasta.gz"].count(b">") >= 20 and a["cns_final.fasta.gz"].count(b">") >= 20
     for f in a:
         assert a[f] == b[f], f"{f} differs: {len(a[f])} vs {len(b[f])} bytes"
 
 
-def test_necat_pl_correct_with_the_emulated_executables(built, tmp_path):
+@pytest.mark.parametrize("small", [0, 1])
+def test_necat_pl_correct_with_the_emulated_executables(built, tmp_path, small):
+    """small = 1: SMALL_MEMORY=1 in the configuration, which necat.pl hands to oc2cns as -s 1 (necat.pl:300)."""
     import gen_reads
     _need_pipeline()
     subprocess.check_call(["make", "-s", "-C", os.path.join(util.ROOT, "tests", "emu")])
@@ -105,7 +107,7 @@ def test_necat_pl_correct_with_the_emulated_executables(built, tmp_path):
              ovlp="OVLP_FAST_OPTIONS=-k 11 -q 100 -n 500 -z 20 -b 2000 -e 0.5 -j 0 -u 1 -a 1000\n"
                   "OVLP_SENSITIVE_OPTIONS=-k 11 -q 100 -n 500 -z 10 -e 0.5 -j 0 -u 1 -a 1000\n",
              cns="CNS_FAST_OPTIONS=-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0\n"
-                 "CNS_SENSITIVE_OPTIONS=-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0\n")
+                 "CNS_SENSITIVE_OPTIONS=-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0\n", small=small)
 
 
 @pytest.mark.gpu
