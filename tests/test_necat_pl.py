@@ -14,6 +14,7 @@ import gzip
 import os
 import shutil
 import subprocess
+import tempfile
 
 import numpy as np
 import pytest
@@ -66,7 +67,7 @@ def _bin_dir(path, tool_dirs):
     return path
 
 
-def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DEFAULT_CNS, small=0):
+def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DEFAULT_CNS, small=0, env=None):
     import gen_reads  # noqa: F401  (tools/ on the path through util's conftest)
     os.makedirs(run_dir)
     A = np.frombuffer(b"ACGT", np.uint8)
@@ -76,7 +77,8 @@ def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DE
     lst = os.path.join(run_dir, "list.txt")
     open(lst, "w").write(os.path.join(run_dir, "reads.fasta") + "\n")
     open(os.path.join(run_dir, "cfg.txt"), "w").write(CFG.format(list=lst, genome=genome, min_len=min_len, ovlp=ovlp, cns=cns, small=small))
-    p = subprocess.run([os.path.join(bin_dir, "necat.pl"), "correct", "cfg.txt"], cwd=run_dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    p = subprocess.run([os.path.join(bin_dir, "necat.pl"), "correct", "cfg.txt"], cwd=run_dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       env=dict(os.environ, **(env or {})))
     log = p.stdout.decode(errors="replace")
     assert p.returncode == 0 and "Failed to run script" not in log and "[Error]" not in log, log[-3000:]
     out = {}
@@ -85,29 +87,34 @@ def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DE
     return out
 
 
-def _compare(tmp_path, ours, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DEFAULT_CNS, small=0):
+def _compare(tmp_path, ours, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DEFAULT_CNS, small=0, env=None):
     ref = {t: util.REF_DIR for t in TOOLS}
     a = _correct(_bin_dir(str(tmp_path / "bin_ref"), ref), str(tmp_path / "run_ref"), reads, genome, min_len, ovlp, cns, small)
-    b = _correct(_bin_dir(str(tmp_path / "bin_ours"), ours), str(tmp_path / "run_ours"), reads, genome, min_len, ovlp, cns, small)
+    b = _correct(_bin_dir(str(tmp_path / "bin_ours"), ours), str(tmp_path / "run_ours"), reads, genome, min_len, ovlp, cns, small, env)
     assert a["cns_iter1/cns.fasta.gz"].count(b">") >= 20 and a["cns_final.fasta.gz"].count(b">") >= 20
     for f in a:
         assert a[f] == b[f], f"{f} differs: {len(a[f])} vs {len(b[f])} bytes"
 
 
-@pytest.mark.parametrize("small", [0, 1])
-def test_necat_pl_correct_with_the_emulated_executables(built, tmp_path, small):
-    """small = 1: SMALL_MEMORY=1 in the configuration, which necat.pl hands to oc2cns as -s 1 (necat.pl:300)."""
+@pytest.mark.parametrize("small,helper", [(0, 0), (1, 0), (0, 1)])
+def test_necat_pl_correct_with_the_emulated_executables(built, tmp_path, small, helper):
+    """small = 1: SMALL_MEMORY=1 in the configuration, which necat.pl hands to oc2cns as -s 1 (necat.pl:300).
+    helper = 1: NECAT_B200_HELPER=1 in necat.pl's environment -- every oc2pmov / oc2cns call of the run is served by one
+    resident helper process."""
     import gen_reads
     _need_pipeline()
     subprocess.check_call(["make", "-s", "-C", os.path.join(util.ROOT, "tests", "emu")])
     util.ensure_host_tools()
     _, reads = gen_reads.generate(12000, 15, 5, err=0.10, min_len=1500, max_len=6000, mean_log=7.8, sd_log=0.4)
     ours = {t: (EMU_BIN if t in ("oc2pmov", "oc2pcan", "oc2cns") else util.BIN_DIR) for t in TOOLS}
+    sock_dir = tempfile.mkdtemp(prefix="nbh", dir="/tmp")       # (a UNIX socket path holds ~100 characters)
     _compare(tmp_path, ours, reads, 12000, 1000,
              ovlp="OVLP_FAST_OPTIONS=-k 11 -q 100 -n 500 -z 20 -b 2000 -e 0.5 -j 0 -u 1 -a 1000\n"
                   "OVLP_SENSITIVE_OPTIONS=-k 11 -q 100 -n 500 -z 10 -e 0.5 -j 0 -u 1 -a 1000\n",
              cns="CNS_FAST_OPTIONS=-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0\n"
-                 "CNS_SENSITIVE_OPTIONS=-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0\n", small=small)
+                 "CNS_SENSITIVE_OPTIONS=-a 1000 -x 3 -y 12 -l 500 -e 0.5 -p 0.8 -u 0\n", small=small,
+             env={"NECAT_B200_HELPER": "1", "NECAT_B200_HELPER_IDLE": "3", "NECAT_B200_HELPER_DIR": sock_dir} if helper else None)
+    shutil.rmtree(sock_dir, ignore_errors=True)
 
 
 @pytest.mark.gpu
