@@ -12,7 +12,8 @@ HOSTC := necat_b200/host/nb_host.c
 CC    := gcc
 CFLAGS := -O2 -g -std=gnu99 -Wall
 
-all: $(LIBD)/libnecat_b200.so $(BIND)/oc2pmov $(BIND)/oc2cns $(BIND)/oc2pcan $(BIND)/oc2mkdb $(BIND)/oc2ReorderCnsReads $(BIND)/nb_helperd
+all: $(LIBD)/libnecat_b200.so $(BIND)/oc2pmov $(BIND)/oc2cns $(BIND)/oc2pcan $(BIND)/oc2mkdb $(BIND)/oc2ReorderCnsReads $(BIND)/nb_helperd \
+     $(BIND)/fsa_rd_tools $(BIND)/pigz
 
 $(OBJD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/necat_b200.h
 	@mkdir -p $(OBJD)
@@ -27,6 +28,11 @@ FASTX := necat_b200/host/nb_fastx.c
 $(BIND)/oc2mkdb $(BIND)/oc2ReorderCnsReads: $(BIND)/%: necat_b200/host/%.c $(HOSTC) $(FASTX) necat_b200/host/nb_host.h necat_b200/host/nb_fastx.h
 	@mkdir -p $(BIND)
 	$(CC) $(CFLAGS) -O3 -o $@ $< $(HOSTC) $(FASTX) -lz -lpthread
+
+# the two helpers necat.pl runs around a correction iteration: self-contained C + zlib
+$(BIND)/fsa_rd_tools $(BIND)/pigz: $(BIND)/%: necat_b200/host/%.c
+	@mkdir -p $(BIND)
+	$(CC) $(CFLAGS) -O3 -o $@ $< -lz -lpthread
 
 HELPER := necat_b200/host/nb_helper.c
 $(BIND)/%: necat_b200/host/%.c $(HOSTC) $(HELPER) necat_b200/host/nb_host.h necat_b200/host/nb_helper.h $(LIBD)/libnecat_b200.so

@@ -1,7 +1,8 @@
 """The drop-in claim itself: the reference's UNMODIFIED pipeline driver, `necat.pl correct` (src/pipeline/necat.pl: two
 correction iterations -- fsa_rd_tools longest, oc2mkdb, oc2pmov per volume, cat, oc2pcan, oc2cns per partition, cat,
 oc2ReorderCnsReads, pigz; iteration 2 with the FAST overlap options and -r 1), run twice on the same reads: once with the
-reference's five binaries in its bin directory, once with this repo's five executables in their place.  necat.pl calls its
+reference's binaries in its bin directory, once with this repo's executables in their place -- the five of the hot path and
+the drop-ins of the two helpers around it (fsa_rd_tools longest / n50, pigz).  necat.pl calls its
 tools as "$FindBin::RealBin/<tool>" (necat.pl:91), i.e. from the directory necat.pl itself lives in -- so the executables
 are put (linked) THERE, which is what INTEGRATION.md tells a user to do.  cns.fasta / raw.fasta of both iterations and
 cns_final.fasta must be byte-identical.
@@ -55,13 +56,17 @@ def _need_pipeline():
         pytest.skip("perl is not installed")
 
 
-def _bin_dir(path, tool_dirs):
-    """A NECAT bin directory: the pipeline scripts, fsa_rd_tools and pigz of oracle/_ref/pipeline, the five tools linked
-    from tool_dirs[tool]."""
+def _bin_dir(path, tool_dirs, own_helpers=False):
+    """A NECAT bin directory: the pipeline scripts of oracle/_ref/pipeline, the five tools linked from tool_dirs[tool],
+    fsa_rd_tools and pigz either the reference's (pigz: the gzip stand-in of oracle/Makefile.ref) or, own_helpers, this
+    repo's drop-ins of the two."""
     os.makedirs(path)
     for f in os.listdir(PIPE):
         src = os.path.join(PIPE, f)
-        (shutil.copytree if os.path.isdir(src) else shutil.copy)(src, os.path.join(path, f))
+        if own_helpers and f in ("fsa_rd_tools", "pigz"):
+            os.symlink(os.path.join(util.BIN_DIR, f), os.path.join(path, f))
+        else:
+            (shutil.copytree if os.path.isdir(src) else shutil.copy)(src, os.path.join(path, f))
     for t in TOOLS:
         os.symlink(os.path.join(tool_dirs[t], t), os.path.join(path, t))
     return path
@@ -90,7 +95,7 @@ def _correct(bin_dir, run_dir, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DE
 def _compare(tmp_path, ours, reads, genome, min_len, ovlp=DEFAULT_OVLP, cns=DEFAULT_CNS, small=0, env=None):
     ref = {t: util.REF_DIR for t in TOOLS}
     a = _correct(_bin_dir(str(tmp_path / "bin_ref"), ref), str(tmp_path / "run_ref"), reads, genome, min_len, ovlp, cns, small)
-    b = _correct(_bin_dir(str(tmp_path / "bin_ours"), ours), str(tmp_path / "run_ours"), reads, genome, min_len, ovlp, cns, small, env)
+    b = _correct(_bin_dir(str(tmp_path / "bin_ours"), ours, own_helpers=True), str(tmp_path / "run_ours"), reads, genome, min_len, ovlp, cns, small, env)
     assert a["cns_iter1/cns.fasta.gz"].count(b">") >= 20 and a["cns_final.fasta.gz"].count(b">") >= 20
     for f in a:
         assert a[f] == b[f], f"{f} differs: {len(a[f])} vs {len(b[f])} bytes"

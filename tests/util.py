@@ -25,7 +25,7 @@ def ensure_oracle():
 def ensure_host_tools():
     """The host-only executables (gcc + zlib, no nvcc needed) are built on demand; the CUDA library and the three
     executables over it come from `make` / __graft_entry__.build()."""
-    tools = [os.path.join(BIN_DIR, t) for t in ("oc2mkdb", "oc2ReorderCnsReads")]
+    tools = [os.path.join(BIN_DIR, t) for t in ("oc2mkdb", "oc2ReorderCnsReads", "fsa_rd_tools", "pigz")]
     if not all(os.path.exists(t) for t in tools):
         subprocess.check_call(["make", "-s", "-C", ROOT] + [os.path.relpath(t, ROOT) for t in tools])
 
