@@ -135,7 +135,6 @@ static int parse_head(const char* line, size_t n, char mark, rec_t* r)
 }
 
 typedef void (*rec_fn)(const rec_t* r, void* arg);
-static int g_warned = 0;
 
 static void each_fasta(const char* path, rec_fn fn, void* arg)
 {
@@ -157,7 +156,7 @@ static void each_fasta(const char* path, rec_fn fn, void* arg)
         }
         fn(&r, arg);
     }
-    if (!at_end(&L)) { logmsg("WARNING", "No all reads in file are loaded: %s", path, 0); g_warned = 1; }
+    if (!at_end(&L)) { logmsg("WARNING", "No all reads in file are loaded: %s", path, 0); }
     lines_close(&L);
     free(r.head.p); free(r.sub.p); free(r.seq.p);
 }
@@ -178,7 +177,7 @@ static void each_fastq(const char* path, rec_fn fn, void* arg)
         next_stripped(&L);                      /* quality */
         fn(&r, arg);
     }
-    if (!(L.eof && L.io_at == L.io_n)) { logmsg("WARNING", "No all reads in file are loaded: %s", path, 0); g_warned = 1; }
+    if (!(L.eof && L.io_at == L.io_n)) { logmsg("WARNING", "No all reads in file are loaded: %s", path, 0); }
     lines_close(&L);
     free(r.head.p); free(r.sub.p); free(r.seq.p);
 }
